@@ -1,0 +1,186 @@
+/*
+ * qdm.h -- C ABI of libqdm.so: the B200 (sm_100a) quantized-linear hot path.
+ *
+ * This is the drop-in boundary for the quantized-linear path of
+ * maani3/Quantization---Diffusion-Models.  The reference has no FFI of its own
+ * (it is pure Python on torch); every entry point below replaces a torch-op
+ * sequence inside one reference function, cited as `file:line` relative to the
+ * reference root.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller allocates every output; the library never retains or frees
+ *     user memory and never allocates in a hot call (workspaces are passed in,
+ *     sized by the matching qdm_*_workspace_bytes());
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: QDM_OK or a negative code; qdm_last_error() gives the
+ *     thread-local message.  The Python mirror raises ValueError for
+ *     QDM_ERR_INVALID and RuntimeError for the rest (the reference's own
+ *     exception types: quantize/fake_quant.py:198,253; quantize/scale.py:71);
+ *   - dtype enum: QDM_F16 / QDM_BF16 / QDM_F32 (tensor element type).  All
+ *     floating-point arithmetic replays torch's op-by-op rounding: each
+ *     reference torch op is evaluated in fp32 and rounded to `dtype` before the
+ *     next op (true IEEE division, round-half-even), so integer codes, scales
+ *     and zeros are bit-exact with the reference.
+ *   - no CPU fallback exists: on a non-sm_100 device every call fails.
+ */
+#ifndef QDM_H_
+#define QDM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QDM_OK               0
+#define QDM_ERR_INVALID     (-1) /* bad argument            -> ValueError   */
+#define QDM_ERR_CUDA        (-2) /* CUDA runtime failure    -> RuntimeError */
+#define QDM_ERR_UNSUPPORTED (-3) /* shape/dtype not built   -> RuntimeError */
+#define QDM_ERR_DEVICE      (-4) /* not a cc 10.0 device    -> RuntimeError */
+
+#define QDM_F16  0
+#define QDM_BF16 1
+#define QDM_F32  2
+
+/* flags for qdm_quant_group */
+#define QDM_Q_ZERO_POINT 1u /* asymmetric min/max + zero point (quantizer.py:172-182)      */
+#define QDM_Q_NO_CLAMP   2u /* symmetric, codes not clamped (fake_quant.py:44-46,72)        */
+
+int         qdm_version(void);
+const char* qdm_last_error(void);
+/* fails with QDM_ERR_DEVICE unless `device` has compute capability 10.0 */
+int         qdm_device_check(int device);
+
+/* ------------------------------------------------------------------ (a) reductions */
+
+/* out[c] = max_r |x[r,c]|, x row-major [rows, cols] with row stride `ld` elements.
+ * Replaces `x.reshape(-1, C).abs().amax(dim=0)`  utils/calib_data.py:117-118 and
+ * `fc.weight.abs().max(dim=0)`                   quantize/quantizer_SQ.py:417-418.
+ * mode 0: out = colmax; mode 1: out = max(out, colmax) (running max,
+ * quantize/quantizer_SQ.py:1080-1084).  out has `dtype`.  Exact (max is order-free). */
+size_t qdm_colreduce_workspace_bytes(int64_t rows, int64_t cols);
+int qdm_colabsmax(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld,
+                  void* out, int mode, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out_sum[c] = sum_r |x[r,c]| accumulated in fp32 with a fixed reduction tree
+ * (deterministic run to run).  out_sum is fp32[cols]; the caller finishes
+ * `(sum / rows).to(dtype)` as quantize/quantizer.py:652-659 does. */
+int qdm_colabssum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld,
+                  float* out_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[r] = max_c |x[r,c]| (dtype), rows of `cols` contiguous elements.
+ * `w.abs().max(dim=-1)` quantize/fake_quant.py:89,114; cols may be tiny (conv kw). */
+int qdm_rowabsmax(const void* x, int dtype, int64_t rows, int64_t cols, void* out, void* stream);
+
+/* out[0] = max |x| over numel elements (dtype).  quantize/fake_quant.py:101,163. */
+size_t qdm_absmax_workspace_bytes(int64_t numel);
+int qdm_absmax(const void* x, int dtype, int64_t numel, void* out,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* AWQ weight statistic, quantize/quantizer.py:627-637:
+ *   w_scale = |W| / (groupmax(|W|) + 1e-6)   (per group of `group` along K, ops rounded in dtype)
+ *   out_sum[k] = sum_n w_scale[n,k]  in fp32 (fixed tree); caller divides by N and casts.
+ * W is row-major [n_rows, k_cols]; group must be 8*2^j <= 256 and divide k_cols. */
+int qdm_awq_wsum(const void* w, int dtype, int64_t n_rows, int64_t k_cols, int group,
+                 float* out_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[0] (double) = sum_i ( float( dtype(a[i] - b[i]) ) )^2, fixed tree.
+ * `(a - b).float().pow(2).sum()` quantize/quantizer.py:777. */
+size_t qdm_sqdiff_workspace_bytes(int64_t numel);
+int qdm_sqdiff_sum(const void* a, const void* b, int dtype, int64_t numel, double* out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ (b) quantize / pack */
+
+/* Per-group RTN.  w is [n_rows, k_cols] row-major, groups of `group` consecutive
+ * elements along K (group divides k_cols, multiple of 16 bytes).
+ *   flags & QDM_Q_ZERO_POINT : AwqQuantizer.pseudo_quantize_tensor, zero_point branch
+ *                              quantize/quantizer.py:172-182
+ *   flags == 0               : same function, symmetric branch  quantizer.py:183-190
+ *   flags & QDM_Q_NO_CLAMP   : quantize_weight_absmax            fake_quant.py:44-46,72
+ * Optional inputs (NULL to skip), each applied as its own rounded torch op:
+ *   pre_mul[k_cols]  : w <- w * pre_mul[k]         (fc.weight.mul_(scales_view), quantizer.py:727)
+ *   clip_max[n_rows*k_cols/group] : w <- clamp(w, -c, c) (scale.py:31, quantizer.py:845)
+ *   post_div[k_cols] : dq <- dq / post_div[k]      (quantizer.py:728-730)
+ * Optional outputs (NULL to skip):
+ *   dq     [n_rows,k_cols] dtype : fake-quantised weight (may alias w)
+ *   codes  [n_rows,k_cols] int8  : integer codes (0..2^b-1 with zero point, signed otherwise;
+ *                                   saturated to int8 when QDM_Q_NO_CLAMP)
+ *   scales [n_rows,k_cols/group] dtype, zeros [same] dtype (float-typed integers; zero-point only) */
+int qdm_quant_group(const void* w, int dtype, int64_t n_rows, int64_t k_cols, int group,
+                    int n_bits, unsigned flags,
+                    const void* pre_mul, const void* clip_max, const void* post_div,
+                    void* dq, int8_t* codes, void* scales, void* zeros, void* stream);
+
+/* Row-wise symmetric absmax RTN without clamping:
+ *   s = absmax_row.clamp(1e-5) / (2^(b-1)-1);  q = round(x / s);  dq = q * s
+ * quantize_weight_per_channel_absmax fake_quant.py:86-93 (rows = numel / last_dim) and
+ * quantize_activation_per_token_absmax fake_quant.py:109-118.
+ * Outputs optional: dq (dtype, may alias x), codes int8 (saturated), scales[rows] dtype. */
+int qdm_quant_rowwise(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
+                      void* dq, int8_t* codes, void* scales, void* stream);
+
+/* Whole-tensor symmetric absmax RTN, fake_quant.py:97-105,158-167.
+ * scale_out[0] (dtype) optional. */
+int qdm_quant_tensor(const void* x, int dtype, int64_t numel, int n_bits,
+                     void* dq, int8_t* codes, void* scale_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* AWQ GEMM int4 layout (utils/packing_utils.py:4-27,87-102; utils/quant_utils.py:10-39):
+ *   qweight[k, c] int32, nibble i = code of column 8c + {0,2,4,6,1,3,5,7}[i].
+ * codes_nk is int8 [n_rows, k_cols] (low 4 bits used) in nn.Linear orientation; the
+ * kernel transposes: qweight is [k_cols, n_rows/8].  n_rows % 8 == 0. */
+int qdm_pack_awq(const int8_t* codes_nk, int64_t n_rows, int64_t k_cols, int32_t* qweight, void* stream);
+/* inverse: qweight [k_rows, n_cols/8] -> codes_kn int8 [k_rows, n_cols] in natural column order */
+int qdm_unpack_awq(const int32_t* qweight, int64_t k_rows, int64_t n_cols, int8_t* codes_kn, void* stream);
+
+/* Fused zero-point W4 RTN + AWQ pack straight from the nn.Linear weight [n_rows,k_cols]:
+ *   qweight [k_cols, n_rows/8] int32, qzeros [k_cols/group, n_rows/8] int32,
+ *   scales_t [k_cols/group, n_rows] dtype   (quantizer.py:540-547 + WQLinear_GEMM.from_linear)
+ * group in {32,64,128}; n_rows % 64 == 0; k_cols % group == 0.  Optional dq as above. */
+int qdm_quant_pack_awq(const void* w, int dtype, int64_t n_rows, int64_t k_cols, int group,
+                       int32_t* qweight, int32_t* qzeros, void* scales_t, void* dq, void* stream);
+
+/* W_kn[k, n] = (q - z) * s in dtype (utils/packing_utils.py:87-102), out [k_rows, n_cols] */
+int qdm_dequant_awq(const int32_t* qweight, const int32_t* qzeros, const void* scales_t, int dtype,
+                    int64_t k_rows, int64_t n_cols, int group, void* out_kn, void* stream);
+
+/* ------------------------------------------------------------------ (c)(d) GEMMs (tcgen05) */
+
+/* y[M,N] = x[M,K] @ w[N,K]^T + bias, fp32 accumulate in TMEM, x/w/y/bias in dtype (f16|bf16).
+ * This is WxAxLinear.forward on fake-quant weights, quantize/fake_quant.py:223.
+ * K % 8 == 0, N % 8 == 0 (16-byte TMA strides).  bias may be NULL. */
+int qdm_gemm_f16(const void* x, const void* w, const void* bias, void* y, int dtype,
+                 int64_t M, int64_t N, int64_t K, void* stream);
+
+/* y[M,N] = x[M,K] @ dequant(qweight,qzeros,scales)[K,N] + bias; dequant inside the main loop.
+ * Same storage as WQLinear_GEMM (call sites quantize/quantizer.py:544-569):
+ *   qweight [K, N/8] int32, qzeros [K/group, N/8] int32, scales [K/group, N] dtype.
+ * N % 64 == 0, K % 64 == 0, group % 64 == 0. */
+int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                   const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
+                   void* stream);
+
+/* y[m,n] = (sum_k xq[m,k]*wq[n,k]) * sx[m] * sw[n] + bias[n]; int8 x int8 -> int32 in TMEM.
+ * xq [M,K] int8 (per-token codes, fake_quant.py:109-118), wq [N,K] int8 (per-channel codes,
+ * fake_quant.py:86-93), sx [M] / sw [N] fp32, bias/y in out_dtype.  K % 16 == 0, N % 8 == 0. */
+int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const float* sw,
+                  const void* bias, void* y, int out_dtype, int64_t M, int64_t N, int64_t K,
+                  void* stream);
+
+/* Host-buffer entry used for the end-to-end measurement: x_host/y_host are (pinned) HOST buffers,
+ * x_dev/y_dev device staging buffers of the same size owned by the caller; the call does
+ * H2D(x) -> qdm_gemm_w4a16 -> D2H(y) on `stream`. */
+int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight, const int32_t* qzeros,
+                        const void* scales, const void* bias, void* y_dev, void* y_host, int dtype,
+                        int64_t M, int64_t N, int64_t K, int group, void* stream);
+
+/* number of kernels launched by this library in the calling thread since the last reset */
+int64_t qdm_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QDM_H_ */
