@@ -106,24 +106,35 @@ int qdm_sqdiff_sum(const void* a, const void* b, int dtype, int64_t numel, doubl
  *   post_div[k_cols] : dq <- dq / post_div[k]      (quantizer.py:728-730)
  * Optional outputs (NULL to skip):
  *   dq     [n_rows,k_cols] dtype : fake-quantised weight (may alias w)
- *   codes  [n_rows,k_cols] int8  : integer codes (0..2^b-1 with zero point, signed otherwise;
- *                                   saturated to int8 when QDM_Q_NO_CLAMP)
+ *   codes  [n_rows,k_cols] 1 byte: integer codes; unsigned 0..2^b-1 with zero point, two's
+ *                                   complement otherwise (saturated to [-128,127] when QDM_Q_NO_CLAMP)
  *   scales [n_rows,k_cols/group] dtype, zeros [same] dtype (float-typed integers; zero-point only) */
 int qdm_quant_group(const void* w, int dtype, int64_t n_rows, int64_t k_cols, int group,
                     int n_bits, unsigned flags,
                     const void* pre_mul, const void* clip_max, const void* post_div,
                     void* dq, int8_t* codes, void* scales, void* zeros, void* stream);
 
-/* Row-wise symmetric absmax RTN without clamping:
+/* Row-wise RTN: one scale (and zero point) per row of `cols` contiguous elements; same `flags`
+ * as qdm_quant_group.  With QDM_Q_NO_CLAMP it is
  *   s = absmax_row.clamp(1e-5) / (2^(b-1)-1);  q = round(x / s);  dq = q * s
- * quantize_weight_per_channel_absmax fake_quant.py:86-93 (rows = numel / last_dim) and
- * quantize_activation_per_token_absmax fake_quant.py:109-118.
- * Outputs optional: dq (dtype, may alias x), codes int8 (saturated), scales[rows] dtype. */
-int qdm_quant_rowwise(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
-                      void* dq, int8_t* codes, void* scales, void* stream);
+ * = quantize_weight_per_channel_absmax fake_quant.py:86-93 (rows = numel / last_dim) and
+ *   quantize_activation_per_token_absmax fake_quant.py:109-118;
+ * with QDM_Q_ZERO_POINT / 0 it is pseudo_quantize_tensor with group_size <= 0 (quantizer.py:165-167).
+ * Outputs optional: dq (dtype, may alias x), codes int8, scales[rows] dtype, zeros[rows] dtype. */
+int qdm_quant_rowwise(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits, unsigned flags,
+                      void* dq, int8_t* codes, void* scales, void* zeros, void* stream);
+
+/* Per-token int8 activation codes, the A8 of W8A8: same arithmetic as
+ * quantize_activation_per_token_absmax (fake_quant.py:109-118) with n_bits = 8, but emits
+ * xq[rows, cols] int8 and sx[rows] fp32 (= the dtype-rounded scale) instead of q * s.
+ * smooth[cols] (dtype, optional): x is divided by it first (SmoothQuant activation side,
+ * quantize/quantizer_SQ.py:425-431 when the divide cannot be folded into a previous op). */
+int qdm_actquant_token_i8(const void* x, int dtype, int64_t rows, int64_t cols, const void* smooth,
+                          int8_t* xq, float* sx, void* stream);
 
 /* Whole-tensor symmetric absmax RTN, fake_quant.py:97-105,158-167.
  * scale_out[0] (dtype) optional. */
+size_t qdm_quant_tensor_workspace_bytes(int64_t numel);
 int qdm_quant_tensor(const void* x, int dtype, int64_t numel, int n_bits,
                      void* dq, int8_t* codes, void* scale_out,
                      void* workspace, size_t workspace_bytes, void* stream);
@@ -155,10 +166,15 @@ int qdm_dequant_awq(const int32_t* qweight, const int32_t* qzeros, const void* s
 int qdm_gemm_f16(const void* x, const void* w, const void* bias, void* y, int dtype,
                  int64_t M, int64_t N, int64_t K, void* stream);
 
+/* y[M,N] = x[M,K] @ w_kn[K,N] + bias: same as qdm_gemm_f16 with the weight stored [K, N]
+ * (the orientation dequantize_gemm returns, utils/packing_utils.py:87-102). */
+int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
+                    int64_t M, int64_t N, int64_t K, void* stream);
+
 /* y[M,N] = x[M,K] @ dequant(qweight,qzeros,scales)[K,N] + bias; dequant inside the main loop.
  * Same storage as WQLinear_GEMM (call sites quantize/quantizer.py:544-569):
  *   qweight [K, N/8] int32, qzeros [K/group, N/8] int32, scales [K/group, N] dtype.
- * N % 64 == 0, K % 64 == 0, group % 64 == 0. */
+ * N % 8 == 0, K % 64 == 0, group % 64 == 0 and group divides K. */
 int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
                    const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
                    void* stream);

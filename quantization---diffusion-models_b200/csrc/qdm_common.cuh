@@ -11,6 +11,13 @@
 // ---------------------------------------------------------------- error plumbing
 void qdm_set_error(const char* fmt, ...);
 void qdm_count_launch(int n = 1);
+int qdm_require_device();  // QDM_OK only on a cc-10.0 device (cached per device)
+
+#define QDM_DEVICE_GATE()                              \
+  do {                                                 \
+    int _g = qdm_require_device();                     \
+    if (_g != QDM_OK) return _g;                       \
+  } while (0)
 
 #define QDM_REQUIRE(cond, ...)                         \
   do {                                                 \

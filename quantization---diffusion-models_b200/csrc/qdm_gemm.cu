@@ -1,0 +1,622 @@
+// (c)(d) Quantized-linear GEMMs on the 5th-gen tensor cores: tcgen05.mma with TMEM accumulators,
+// TMA-fed operand tiles, mbarrier pipelines, persistent warp-specialised CTAs (one per SM).
+//
+//   G_F16     y = x[M,K] . w[N,K]^T            both operands by TMA, K-major SW128
+//             = WxAxLinear.forward on fake-quant weights            quantize/fake_quant.py:223
+//   G_F16_KN  y = x[M,K] . w_kn[K,N]           B by TMA in MN-major SW128 (dequantize_gemm output,
+//                                              utils/packing_utils.py:87-102)
+//   G_W4      y = x[M,K] . dequant(qweight,qzeros,scales)[K,N]
+//             AWQ int4 layout consumed as stored (utils/packing_utils.py:4-27): 8 dequant warps
+//             unpack nibble pairs (lop3 magic-number trick the [0,2,4,6,1,3,5,7] order exists for),
+//             apply (q - z) * s in the tensor dtype (bit-exact with dequantize_gemm) and write the
+//             MN-major SW128 B tile straight into the pipeline stage.
+//   G_I8      y = (xq[M,K] . wq[N,K]^T) * sx[m] * sw[n]   int8 x int8 -> int32 (kind::i8), the W8A8 of
+//             quantize_activation_per_token_absmax x quantize_weight_per_channel_absmax
+//             (quantize/fake_quant.py:86-93,109-118) with the dequant scales in the epilogue.
+//
+// Warp roles (CTA of 256 threads, 512 for G_W4):
+//   warp 0  lane 0 : TMA producer          warp 1 lane 0 : MMA issuer
+//   warp 2         : TMEM alloc / dealloc  warp 3        : idle
+//   warps 4-7      : epilogue (TMEM -> registers -> smem transpose -> coalesced 16-byte stores)
+//   warps 8-15     : int4 dequant producers (G_W4 only)
+#include "qdm_common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace {
+
+enum GemmKind { G_F16 = 0, G_F16_KN = 1, G_W4 = 2, G_I8 = 3 };
+
+constexpr int BLOCK_M = 128;
+constexpr int ROW_BYTES = 128;                 // one swizzle-128B row = one k-block of an operand row
+constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
+constexpr int EPI_COLS = 64;                   // accumulator columns per epilogue chunk
+constexpr int EPI_PITCH = EPI_COLS * 2 + 16;   // staging row pitch in bytes (2-byte outputs), conflict-free
+constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
+constexpr int NUM_DQ_WARPS = 8;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t polls = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++polls == 4096) t0 = clock64();
+    if (polls > 4096 && (polls & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  if (KIND == G_I8) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+// Instruction descriptor: c_format [4,6) | a_format [7,10) | b_format [10,13) | a_major 15 | b_major 16 |
+// N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int c_fmt, int ab_fmt, int b_mn_major, int M, int N) {
+  return (uint32_t(c_fmt) << 4) | (uint32_t(ab_fmt) << 7) | (uint32_t(ab_fmt) << 10) | (uint32_t(b_mn_major) << 16) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+struct GemmParams {
+  int M, N, K;
+  int group;                 // G_W4
+  const int32_t* qweight;    // G_W4  [K, N/8]
+  const int32_t* qzeros;     // G_W4  [K/group, N/8]
+  const void* scales;        // G_W4  [K/group, N] dtype
+  const void* bias;          // [N] out dtype or null
+  const float* sx;           // G_I8  [M]
+  const float* sw;           // G_I8  [N]
+  void* y;                   // [M, N] out dtype
+  int is_bf16;               // element / output type: 0 fp16, 1 bf16
+};
+
+template <int BLOCK_N, int KIND>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int STAGES = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int THREADS = (KIND == G_W4) ? 512 : 256;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int K_PER_BLOCK = (KIND == G_I8) ? 128 : 64;   // elements per k-block (128 bytes)
+  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS : 1;
+};
+
+template <int KIND, bool BF16>
+__device__ __forceinline__ uint32_t pack_out2(float a, float b) {
+  if (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+template <bool BF16>
+__device__ __forceinline__ void load8_as_float(const void* base, int64_t idx, bool ok, float* out) {
+  if (!base || !ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = 0.f;
+    return;
+  }
+  uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (BF16) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      out[2 * i] = __low2float(h);
+      out[2 * i + 1] = __high2float(h);
+    } else {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      out[2 * i] = __low2float(h);
+      out[2 * i + 1] = __high2float(h);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int BLOCK_N, int KIND, bool BF16>
+__global__ void __launch_bounds__(Cfg<BLOCK_N, KIND>::THREADS, 1)
+qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const GemmParams p) {
+  using C = Cfg<BLOCK_N, KIND>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // layout: [stages x (A | B)] [epilogue staging] [barriers] [tmem ptr]
+  const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (p.K + C::K_PER_BLOCK - 1) / C::K_PER_BLOCK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    if (KIND != G_W4) tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), C::FULL_COUNT);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          const int kc = kb * C::K_PER_BLOCK;
+          if (KIND == G_W4) {
+            mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
+            tma_load_2d(a_dst, &map_a, full_bar(stage), kc, m0);
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(a_dst, &map_a, full_bar(stage), kc, m0);
+            if (KIND == G_F16_KN) {
+#pragma unroll
+              for (int c = 0; c < BLOCK_N / 64; ++c)
+                tma_load_2d(b_dst + c * (64 * ROW_BYTES), &map_b, full_bar(stage), n0 + c * 64, kc);
+            } else {
+              tma_load_2d(b_dst, &map_b, full_bar(stage), kc, n0);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr bool B_MN = (KIND == G_F16_KN || KIND == G_W4);
+      constexpr uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, BLOCK_M, BLOCK_N)
+                                                : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte row
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024)
+                                     : make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma<KIND>(tmem_c, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== epilogue
+    const int ew = warp - 4;  // TMEM lane quarter this warp may read (warp % 4)
+    uint8_t* stg = smem_gen + STAGES * C::STAGE_BYTES + ew * EPI_WARP_BYTES;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint16_t* y = reinterpret_cast<uint16_t*>(p.y);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % m_tiles) * BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      float sxr = 1.f;
+      if (KIND == G_I8) sxr = (row < p.M) ? p.sx[row] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
+        const int nc = n0 + c * EPI_COLS;
+        if (nc >= p.N) break;
+        uint32_t v[EPI_COLS];
+        const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N + c * EPI_COLS;
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + 32, v + 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j8 = 0; j8 < EPI_COLS / 8; ++j8) {
+          const int n = nc + j8 * 8;
+          const bool ok = n < p.N;
+          float bias8[8];
+          load8_as_float<BF16>(p.bias, n, ok, bias8);
+          float f[8];
+          if (KIND == G_I8) {
+            float4 s0 = make_float4(0, 0, 0, 0), s1 = s0;
+            if (ok) {
+              s0 = *reinterpret_cast<const float4*>(p.sw + n);
+              s1 = *reinterpret_cast<const float4*>(p.sw + n + 4);
+            }
+            const float sw8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[i] = __fmaf_rn(__fmul_rn(float(int(v[j8 * 8 + i])), __fmul_rn(sxr, sw8[i])), 1.f, bias8[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j8 * 8 + i]) + bias8[i];
+          }
+          uint4 o;
+          o.x = pack_out2<KIND, BF16>(f[0], f[1]);
+          o.y = pack_out2<KIND, BF16>(f[2], f[3]);
+          o.z = pack_out2<KIND, BF16>(f[4], f[5]);
+          o.w = pack_out2<KIND, BF16>(f[6], f[7]);
+          *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + j8 * 16) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), seg = lane & 7;
+          const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_PITCH + seg * 16);
+          const int gm = m0 + ew * 32 + r, gn = nc + seg * 8;
+          if (gm < p.M && gn < p.N) *reinterpret_cast<uint4*>(y + int64_t(gm) * p.N + gn) = o;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (KIND == G_W4 && warp >= 8) {
+    // ===================================================== int4 dequant producers
+    constexpr int WPR = BLOCK_N / 8;            // packed words per k row of the tile
+    constexpr int ROWS_PER_PASS = 256 / WPR;    // k rows covered by the 256 dequant threads at once
+    constexpr int PASSES = 64 / ROWS_PER_PASS;
+    const int dt = threadIdx.x - 256;
+    const int wc = dt % WPR, kr = dt / WPR;
+    const int words_per_row = p.N / 8;
+    const uint32_t dst_off = uint32_t(wc >> 3) * (64 * ROW_BYTES);  // 64-column chunk of the MN-major tile
+    const uint32_t j16 = uint32_t(wc & 7);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t magic = BF16 ? 0x43004300u : 0x64006400u;  // 128.0 / 1024.0: q sits in the low mantissa bits
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile / m_tiles) * BLOCK_N;
+      const int wcol = n0 / 8 + wc;
+      const bool valid = wcol < words_per_row;
+      const int32_t* qcol = p.qweight + wcol;
+      uint32_t cur[PASSES], nxt[PASSES];
+      auto load_words = [&](int kb, uint32_t* w) {
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+          const int k = kb * 64 + kr + ps * ROWS_PER_PASS;
+          w[ps] = valid ? (uint32_t)__ldg(qcol + int64_t(k) * words_per_row) : 0u;
+        }
+      };
+      load_words(0, cur);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (kb + 1 < num_kb) load_words(kb + 1, nxt);
+        // per-group scale / zero for this thread's 8 output columns
+        const int g = (kb * 64) / p.group;
+        uint32_t zw = 0;
+        uint4 sv = make_uint4(0, 0, 0, 0);
+        if (valid) {
+          zw = (uint32_t)__ldg(p.qzeros + int64_t(g) * words_per_row + wcol);
+          sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.scales) + int64_t(g) * p.N + n0 + wc * 8));
+        }
+        uint32_t zp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) zp[q] = ((zw >> (4 * q)) & 0x000F000Fu) | magic;
+        const uint32_t sp[4] = {sv.x, sv.y, sv.z, sv.w};
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t b_dst = smem_base + stage * C::STAGE_BYTES + A_STAGE_BYTES + dst_off;
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) {
+          const int k = kr + ps * ROWS_PER_PASS;
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t t = ((cur[ps] >> (4 * q)) & 0x000F000Fu) | magic;  // {magic + q(col 2q), magic + q(col 2q+1)}
+            if (BF16) {
+              __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zp[q]));
+              d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&sp[q]));
+              o[q] = *reinterpret_cast<uint32_t*>(&d);
+            } else {
+              __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zp[q]));
+              d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));
+              o[q] = *reinterpret_cast<uint32_t*>(&d);
+            }
+          }
+          const uint32_t addr = b_dst + uint32_t(k) * ROW_BYTES + ((j16 ^ uint32_t(k & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) cur[ps] = nxt[ps];
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+std::mutex g_encode_mu;
+
+int get_encode_fn() {
+  std::lock_guard<std::mutex> lk(g_encode_mu);
+  if (g_encode) return QDM_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    qdm_set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return QDM_ERR_CUDA;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  return QDM_OK;
+}
+
+// 2-D row-major tensor [rows, cols] of `elem_bytes` elements; box = {box_cols, box_rows}, 128-byte swizzle.
+int make_map(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int box_cols, int box_rows) {
+  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    qdm_set_error("cuTensorMapEncodeTiled failed (%d) for [%lld, %lld] x %d B", (int)r, (long long)rows, (long long)cols, elem_bytes);
+    return QDM_ERR_CUDA;
+  }
+  return QDM_OK;
+}
+
+int pick_block_n(int64_t N) {
+  if (N <= 128) return 128;
+  const int64_t waste256 = (N + 255) / 256 * 256 - N;
+  return waste256 >= 128 ? 128 : 256;
+}
+
+template <int BLOCK_N, int KIND, bool BF16>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<BLOCK_N, KIND>;
+  auto kern = qdm_gemm_kernel<BLOCK_N, KIND, BF16>;
+  static bool attr_set = false;  // per instantiation; benign race (idempotent)
+  if (!attr_set) {
+    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < QDM_NUM_SMS ? tiles : QDM_NUM_SMS;
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
+template <int KIND>
+int dispatch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int block_n, cudaStream_t st) {
+  if (block_n == 128) {
+    return p.is_bf16 ? launch_gemm<128, KIND, true>(ma, mb, p, st) : launch_gemm<128, KIND, false>(ma, mb, p, st);
+  }
+  return p.is_bf16 ? launch_gemm<256, KIND, true>(ma, mb, p, st) : launch_gemm<256, KIND, false>(ma, mb, p, st);
+}
+
+int check_common(const char* fn, const void* x, const void* w, void* y, int dtype, int64_t M, int64_t N, int64_t K) {
+  QDM_REQUIRE(x && w && y, "%s: null pointer", fn);
+  QDM_REQUIRE(M > 0 && N > 0 && K > 0, "%s: empty problem M=%lld N=%lld K=%lld", fn, (long long)M, (long long)N, (long long)K);
+  QDM_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "%s: dimension too large", fn);
+  QDM_REQUIRE(dtype == QDM_F16 || dtype == QDM_BF16, "%s: dtype must be f16 or bf16", fn);
+  QDM_REQUIRE(N % 8 == 0, "%s: N=%lld must be a multiple of 8", fn, (long long)N);
+  QDM_REQUIRE(qdm_aligned16(x) && qdm_aligned16(w) && qdm_aligned16(y), "%s: operands must be 16-byte aligned", fn);
+  return QDM_OK;
+}
+
+}  // namespace
+
+extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void* y, int dtype,
+                            int64_t M, int64_t N, int64_t K, void* stream) {
+  int rc = check_common("qdm_gemm_f16", x, w, y, dtype, M, N, K);
+  if (rc) return rc;
+  QDM_REQUIRE(K % 8 == 0, "qdm_gemm_f16: K=%lld must be a multiple of 8", (long long)K);
+  QDM_REQUIRE(!bias || qdm_aligned16(bias), "qdm_gemm_f16: bias must be 16-byte aligned");
+  QDM_DEVICE_GATE();
+  if ((rc = get_encode_fn())) return rc;
+  const int bn = pick_block_n(N);
+  CUtensorMap ma, mb;
+  if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
+  if ((rc = make_map(&mb, w, 2, N, K, 64, bn))) return rc;
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
+  return dispatch_gemm<G_F16>(ma, mb, p, bn, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
+                               int64_t M, int64_t N, int64_t K, void* stream) {
+  int rc = check_common("qdm_gemm_f16_kn", x, w_kn, y, dtype, M, N, K);
+  if (rc) return rc;
+  QDM_REQUIRE(K % 8 == 0, "qdm_gemm_f16_kn: K=%lld must be a multiple of 8", (long long)K);
+  QDM_REQUIRE(!bias || qdm_aligned16(bias), "qdm_gemm_f16_kn: bias must be 16-byte aligned");
+  QDM_DEVICE_GATE();
+  if ((rc = get_encode_fn())) return rc;
+  const int bn = pick_block_n(N);
+  CUtensorMap ma, mb;
+  if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
+  if ((rc = make_map(&mb, w_kn, 2, K, N, 64, 64))) return rc;
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
+  return dispatch_gemm<G_F16_KN>(ma, mb, p, bn, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                              const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
+                              void* stream) {
+  int rc = check_common("qdm_gemm_w4a16", x, qweight, y, dtype, M, N, K);
+  if (rc) return rc;
+  QDM_REQUIRE(qzeros && scales, "qdm_gemm_w4a16: null qzeros/scales");
+  QDM_REQUIRE(K % 64 == 0, "qdm_gemm_w4a16: K=%lld must be a multiple of 64", (long long)K);
+  QDM_REQUIRE(group > 0 && group % 64 == 0 && K % group == 0,
+              "qdm_gemm_w4a16: group=%d must be a multiple of 64 dividing K=%lld", group, (long long)K);
+  QDM_REQUIRE(qdm_aligned16(scales) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w4a16: scales/bias must be 16-byte aligned");
+  QDM_DEVICE_GATE();
+  if ((rc = get_encode_fn())) return rc;
+  const int bn = pick_block_n(N);
+  CUtensorMap ma;
+  if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.group = group;
+  p.qweight = qweight; p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
+  return dispatch_gemm<G_W4>(ma, ma, p, bn, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const float* sw,
+                             const void* bias, void* y, int out_dtype, int64_t M, int64_t N, int64_t K,
+                             void* stream) {
+  int rc = check_common("qdm_gemm_w8a8", xq, wq, y, out_dtype, M, N, K);
+  if (rc) return rc;
+  QDM_REQUIRE(sx && sw, "qdm_gemm_w8a8: null scales");
+  QDM_REQUIRE(K % 16 == 0, "qdm_gemm_w8a8: K=%lld must be a multiple of 16", (long long)K);
+  QDM_REQUIRE(qdm_aligned16(sw) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w8a8: sw/bias must be 16-byte aligned");
+  QDM_DEVICE_GATE();
+  if ((rc = get_encode_fn())) return rc;
+  const int bn = pick_block_n(N);
+  CUtensorMap ma, mb;
+  if ((rc = make_map(&ma, xq, 1, M, K, 128, BLOCK_M))) return rc;
+  if ((rc = make_map(&mb, wq, 1, N, K, 128, bn))) return rc;
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.sx = sx; p.sw = sw; p.bias = bias; p.y = y; p.is_bf16 = out_dtype == QDM_BF16;
+  return dispatch_gemm<G_I8>(ma, mb, p, bn, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight, const int32_t* qzeros,
+                                   const void* scales, const void* bias, void* y_dev, void* y_host, int dtype,
+                                   int64_t M, int64_t N, int64_t K, int group, void* stream) {
+  QDM_REQUIRE(x_host && x_dev && y_dev && y_host, "qdm_gemm_w4a16_host: null pointer");
+  QDM_REQUIRE(M > 0 && N > 0 && K > 0, "qdm_gemm_w4a16_host: empty problem");
+  QDM_DEVICE_GATE();
+  cudaStream_t st = (cudaStream_t)stream;
+  QDM_CUDA_OK(cudaMemcpyAsync(x_dev, x_host, size_t(M) * K * 2, cudaMemcpyHostToDevice, st));
+  int rc = qdm_gemm_w4a16(x_dev, qweight, qzeros, scales, bias, y_dev, dtype, M, N, K, group, stream);
+  if (rc) return rc;
+  QDM_CUDA_OK(cudaMemcpyAsync(y_host, y_dev, size_t(M) * N * 2, cudaMemcpyDeviceToHost, st));
+  return QDM_OK;
+}

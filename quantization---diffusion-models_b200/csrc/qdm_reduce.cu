@@ -322,6 +322,7 @@ extern "C" int qdm_colabsmax(const void* x, int dtype, int64_t rows, int64_t col
   QDM_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "qdm_colabsmax: bad shape rows=%lld cols=%lld ld=%lld",
               (long long)rows, (long long)cols, (long long)ld);
   QDM_REQUIRE(mode == 0 || mode == 1, "qdm_colabsmax: mode must be 0 or 1");
+  QDM_DEVICE_GATE();
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, return (launch_col_reduce<T, COL_ABSMAX, T>((const T*)x, rows, cols, ld, (T*)out, mode,
                                                                        (float*)workspace, workspace_bytes, st)));
@@ -332,6 +333,7 @@ extern "C" int qdm_colabssum(const void* x, int dtype, int64_t rows, int64_t col
                              float* out_sum, void* workspace, size_t workspace_bytes, void* stream) {
   QDM_REQUIRE(x && out_sum && workspace, "qdm_colabssum: null pointer");
   QDM_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "qdm_colabssum: bad shape");
+  QDM_DEVICE_GATE();
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, return (launch_col_reduce<T, COL_ABSSUM, float>((const T*)x, rows, cols, ld, out_sum, 0,
                                                                            (float*)workspace, workspace_bytes, st)));
@@ -341,6 +343,7 @@ extern "C" int qdm_colabssum(const void* x, int dtype, int64_t rows, int64_t col
 extern "C" int qdm_rowabsmax(const void* x, int dtype, int64_t rows, int64_t cols, void* out, void* stream) {
   QDM_REQUIRE(x && out, "qdm_rowabsmax: null pointer");
   QDM_REQUIRE(rows > 0 && cols > 0, "qdm_rowabsmax: bad shape");
+  QDM_DEVICE_GATE();
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, {
     constexpr int V = ElemTraits<T>::kVec;
@@ -378,6 +381,7 @@ extern "C" int qdm_absmax(const void* x, int dtype, int64_t numel, void* out, vo
                           size_t workspace_bytes, void* stream) {
   QDM_REQUIRE(x && out && workspace, "qdm_absmax: null pointer");
   QDM_REQUIRE(numel > 0, "qdm_absmax: empty tensor");
+  QDM_DEVICE_GATE();
   return qdm_absmax_impl(x, dtype, numel, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -390,6 +394,7 @@ extern "C" int qdm_sqdiff_sum(const void* a, const void* b, int dtype, int64_t n
                               void* workspace, size_t workspace_bytes, void* stream) {
   QDM_REQUIRE(a && b && out && workspace, "qdm_sqdiff_sum: null pointer");
   QDM_REQUIRE(numel > 0, "qdm_sqdiff_sum: empty tensor");
+  QDM_DEVICE_GATE();
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, {
     constexpr int V = ElemTraits<T>::kVec;
@@ -410,6 +415,7 @@ extern "C" int qdm_awq_wsum(const void* w, int dtype, int64_t n_rows, int64_t k_
   QDM_REQUIRE(n_rows > 0 && k_cols > 0 && group > 0 && k_cols % group == 0,
               "qdm_awq_wsum: group %d must divide k_cols %lld", group, (long long)k_cols);
   QDM_REQUIRE(qdm_aligned16(w), "qdm_awq_wsum: weight must be 16-byte aligned");
+  QDM_DEVICE_GATE();
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, {
     constexpr int V = ElemTraits<T>::kVec;

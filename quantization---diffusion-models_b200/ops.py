@@ -1,0 +1,364 @@
+"""Torch-tensor front end of the C ABI (include/qdm.h).
+
+Every function takes CUDA tensors, allocates the outputs with torch (the library never
+allocates), passes raw device pointers plus the current CUDA stream, and maps return codes
+to the reference's exception types.  Nothing here computes anything in Python or torch:
+a CPU tensor, a missing library or a non-B200 device is an error, not a fallback.
+"""
+import torch
+
+from . import _lib
+from ._lib import QDM_BF16, QDM_F16, QDM_F32, QDM_Q_NO_CLAMP, QDM_Q_ZERO_POINT, check
+
+_DTYPES = {torch.float16: QDM_F16, torch.bfloat16: QDM_BF16, torch.float32: QDM_F32}
+_workspaces = {}
+
+
+def _dt(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise ValueError(f"unsupported dtype {t.dtype}; libqdm handles float16, bfloat16, float32")
+
+
+def _cuda(t, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
+    return t
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ws(device, nbytes):
+    """Grow-only per-device scratch buffer handed to the library as its workspace."""
+    key = (device.type, device.index)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def lib():
+    return _lib.load()
+
+
+def launch_count(reset=False):
+    return int(lib().qdm_launch_count(1 if reset else 0))
+
+
+# ------------------------------------------------------------------ (a) reductions
+def _as_2d(x):
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    return x2
+
+
+def colabsmax(x, out=None, running=False):
+    """|x|.reshape(-1, C).amax(0) -> [C] in x.dtype (utils/calib_data.py:117-118,
+    quantize/quantizer_SQ.py:417-418).  running=True folds into `out` (quantizer_SQ.py:1080-1084)."""
+    _cuda(x, "x")
+    x2 = _as_2d(x)
+    rows, cols = x2.shape
+    if out is None:
+        if running:
+            raise ValueError("running=True needs an existing `out`")
+        out = torch.empty(cols, dtype=x.dtype, device=x.device)
+    L = lib()
+    ws = _ws(x.device, L.qdm_colreduce_workspace_bytes(rows, cols))
+    with torch.cuda.device(x.device):
+        check(L.qdm_colabsmax(x2.data_ptr(), _dt(x2), rows, cols, x2.stride(0), out.data_ptr(),
+                              1 if running else 0, ws.data_ptr(), ws.numel(), _stream(x)))
+    return out
+
+
+def colabssum(x):
+    """sum over rows of |x| in fp32 with a fixed tree -> fp32 [C] (quantize/quantizer.py:652-657)."""
+    _cuda(x, "x")
+    x2 = _as_2d(x)
+    rows, cols = x2.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    L = lib()
+    ws = _ws(x.device, L.qdm_colreduce_workspace_bytes(rows, cols))
+    with torch.cuda.device(x.device):
+        check(L.qdm_colabssum(x2.data_ptr(), _dt(x2), rows, cols, x2.stride(0), out.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream(x)))
+    return out
+
+
+def rowabsmax(x):
+    """x.abs().max(dim=-1) over contiguous rows -> [rows] (quantize/fake_quant.py:89,114)."""
+    _cuda(x, "x")
+    x2 = x.contiguous().reshape(-1, x.shape[-1])
+    rows, cols = x2.shape
+    out = torch.empty(rows, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().qdm_rowabsmax(x2.data_ptr(), _dt(x2), rows, cols, out.data_ptr(), _stream(x)))
+    return out.reshape(x.shape[:-1])
+
+
+def absmax(x):
+    """x.abs().max() -> 0-dim tensor (quantize/fake_quant.py:101,163)."""
+    _cuda(x, "x")
+    xc = x.contiguous()
+    out = torch.empty((), dtype=x.dtype, device=x.device)
+    L = lib()
+    ws = _ws(x.device, L.qdm_absmax_workspace_bytes(xc.numel()))
+    with torch.cuda.device(x.device):
+        check(L.qdm_absmax(xc.data_ptr(), _dt(xc), xc.numel(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)))
+    return out
+
+
+def awq_wsum(w, group):
+    """sum_n |W|/(groupmax+1e-6) per input channel in fp32 (quantize/quantizer.py:627-637);
+    the caller divides by N and casts.  W is [N, K] contiguous."""
+    _cuda(w, "w")
+    wc = w.contiguous()
+    n, k = wc.shape
+    out = torch.empty(k, dtype=torch.float32, device=w.device)
+    L = lib()
+    ws = _ws(w.device, L.qdm_colreduce_workspace_bytes(n, k))
+    with torch.cuda.device(w.device):
+        check(L.qdm_awq_wsum(wc.data_ptr(), _dt(wc), n, k, int(group), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(w)))
+    return out
+
+
+def sqdiff_sum(a, b):
+    """(a - b).float().pow(2).sum() as a float64 0-dim tensor (quantize/quantizer.py:777)."""
+    _cuda(a, "a"), _cuda(b, "b")
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("sqdiff_sum: shape/dtype mismatch")
+    ac, bc = a.contiguous(), b.contiguous()
+    out = torch.empty((), dtype=torch.float64, device=a.device)
+    L = lib()
+    ws = _ws(a.device, L.qdm_sqdiff_workspace_bytes(ac.numel()))
+    with torch.cuda.device(a.device):
+        check(L.qdm_sqdiff_sum(ac.data_ptr(), bc.data_ptr(), _dt(ac), ac.numel(), out.data_ptr(),
+                               ws.data_ptr(), ws.numel(), _stream(a)))
+    return out
+
+
+# ------------------------------------------------------------------ (b) quantise / pack
+def _flags(zero_point, no_clamp):
+    if zero_point and no_clamp:
+        raise ValueError("zero_point and no_clamp are mutually exclusive")
+    return (QDM_Q_ZERO_POINT if zero_point else 0) | (QDM_Q_NO_CLAMP if no_clamp else 0)
+
+
+def quant_group(w, group, n_bits=4, zero_point=True, no_clamp=False, pre_mul=None, clip_max=None,
+                post_div=None, want_dq=True, want_codes=False, want_scales=True, out=None):
+    """Per-group RTN over the last dim (see qdm_quant_group in include/qdm.h).
+    Returns (dq, codes, scales, zeros); entries not requested are None.  `out` may alias `w`."""
+    _cuda(w, "w")
+    wc = w.contiguous()
+    k = wc.shape[-1]
+    n = wc.numel() // k
+    if group <= 0:
+        group = k
+    if k % group:
+        raise ValueError(f"group {group} must divide the last dim {k}")
+    G = k // group
+    dev, dt = w.device, w.dtype
+    for name, v in (("pre_mul", pre_mul), ("post_div", post_div)):
+        if v is not None and (v.numel() != k or v.dtype != dt):
+            raise ValueError(f"{name} must be a [{k}] tensor of dtype {dt}")
+    if clip_max is not None and (clip_max.numel() != n * G or clip_max.dtype != dt):
+        raise ValueError(f"clip_max must hold {n * G} values of dtype {dt}")
+    dq = (out if out is not None else torch.empty_like(wc)) if want_dq else None
+    codes = torch.empty(wc.shape, dtype=torch.uint8 if zero_point else torch.int8, device=dev) if want_codes else None
+    scales = torch.empty((n, G), dtype=dt, device=dev) if want_scales else None
+    zeros = torch.empty((n, G), dtype=dt, device=dev) if (want_scales and zero_point) else None
+    pm = pre_mul.contiguous() if pre_mul is not None else None
+    pd = post_div.contiguous() if post_div is not None else None
+    cm = clip_max.contiguous() if clip_max is not None else None
+    with torch.cuda.device(dev):
+        check(lib().qdm_quant_group(wc.data_ptr(), _dt(wc), n, k, int(group), int(n_bits), _flags(zero_point, no_clamp),
+                                    _ptr(pm), _ptr(cm), _ptr(pd), _ptr(dq), _ptr(codes), _ptr(scales), _ptr(zeros),
+                                    _stream(w)))
+    return dq, codes, scales, zeros
+
+
+def quant_rowwise(x, n_bits=8, zero_point=False, no_clamp=True, want_dq=True, want_codes=False, want_scales=False):
+    """One scale per row of the last dim (fake_quant.py:86-93,109-118)."""
+    _cuda(x, "x")
+    xc = x.contiguous()
+    cols = xc.shape[-1]
+    rows = xc.numel() // cols
+    dq = torch.empty_like(xc) if want_dq else None
+    codes = torch.empty(xc.shape, dtype=torch.uint8 if zero_point else torch.int8, device=x.device) if want_codes else None
+    scales = torch.empty(rows, dtype=x.dtype, device=x.device) if want_scales else None
+    zeros = torch.empty(rows, dtype=x.dtype, device=x.device) if (want_scales and zero_point) else None
+    with torch.cuda.device(x.device):
+        check(lib().qdm_quant_rowwise(xc.data_ptr(), _dt(xc), rows, cols, int(n_bits), _flags(zero_point, no_clamp),
+                                      _ptr(dq), _ptr(codes), _ptr(scales), _ptr(zeros), _stream(x)))
+    return dq, codes, scales, zeros
+
+
+def quant_tensor(x, n_bits=8, want_dq=True, want_codes=False):
+    """Whole-tensor absmax RTN (fake_quant.py:97-105,158-167). Returns (dq, codes, scale)."""
+    _cuda(x, "x")
+    xc = x.contiguous()
+    dq = torch.empty_like(xc) if want_dq else None
+    codes = torch.empty(xc.shape, dtype=torch.int8, device=x.device) if want_codes else None
+    scale = torch.empty((), dtype=x.dtype, device=x.device)
+    L = lib()
+    ws = _ws(x.device, L.qdm_quant_tensor_workspace_bytes(xc.numel()))
+    with torch.cuda.device(x.device):
+        check(L.qdm_quant_tensor(xc.data_ptr(), _dt(xc), xc.numel(), int(n_bits), _ptr(dq), _ptr(codes),
+                                 scale.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)))
+    return dq, codes, scale
+
+
+def actquant_token_i8(x, smooth=None):
+    """Per-token int8 codes + fp32 scales of x[..., K] -> (xq int8 [M, K], sx fp32 [M])."""
+    _cuda(x, "x")
+    x2 = x.contiguous().reshape(-1, x.shape[-1])
+    rows, cols = x2.shape
+    if smooth is not None and (smooth.numel() != cols or smooth.dtype != x.dtype):
+        raise ValueError(f"smooth must be a [{cols}] tensor of dtype {x.dtype}")
+    xq = torch.empty((rows, cols), dtype=torch.int8, device=x.device)
+    sx = torch.empty(rows, dtype=torch.float32, device=x.device)
+    sm = smooth.contiguous() if smooth is not None else None
+    with torch.cuda.device(x.device):
+        check(lib().qdm_actquant_token_i8(x2.data_ptr(), _dt(x2), rows, cols, _ptr(sm), xq.data_ptr(), sx.data_ptr(), _stream(x)))
+    return xq, sx
+
+
+def pack_awq(codes_nk):
+    """int codes [N, K] (nn.Linear orientation, low 4 bits) -> qweight int32 [K, N/8] in AWQ order."""
+    _cuda(codes_nk, "codes")
+    c = codes_nk.contiguous()
+    if c.dtype not in (torch.int8, torch.uint8):
+        raise ValueError("codes must be int8/uint8")
+    n, k = c.shape
+    if n % 8:
+        raise ValueError(f"N={n} must be a multiple of 8")
+    q = torch.empty((k, n // 8), dtype=torch.int32, device=c.device)
+    with torch.cuda.device(c.device):
+        check(lib().qdm_pack_awq(c.data_ptr(), n, k, q.data_ptr(), _stream(c)))
+    return q
+
+
+def unpack_awq(qweight):
+    """qweight int32 [K, N/8] -> codes int8 [K, N] in natural column order."""
+    _cuda(qweight, "qweight")
+    q = qweight.contiguous()
+    k, nw = q.shape
+    out = torch.empty((k, nw * 8), dtype=torch.int8, device=q.device)
+    with torch.cuda.device(q.device):
+        check(lib().qdm_unpack_awq(q.data_ptr(), k, nw * 8, out.data_ptr(), _stream(q)))
+    return out
+
+
+def quant_pack_awq(w, group, want_dq=False):
+    """W [N, K] -> (qweight [K, N/8] int32, qzeros [K/g, N/8] int32, scales [K/g, N] dtype, dq|None)."""
+    _cuda(w, "w")
+    wc = w.contiguous()
+    n, k = wc.shape
+    if group <= 0 or k % group:
+        raise ValueError(f"group {group} must divide K={k}")
+    qweight = torch.empty((k, n // 8), dtype=torch.int32, device=w.device)
+    qzeros = torch.empty((k // group, n // 8), dtype=torch.int32, device=w.device)
+    scales = torch.empty((k // group, n), dtype=w.dtype, device=w.device)
+    dq = torch.empty_like(wc) if want_dq else None
+    with torch.cuda.device(w.device):
+        check(lib().qdm_quant_pack_awq(wc.data_ptr(), _dt(wc), n, k, int(group), qweight.data_ptr(), qzeros.data_ptr(),
+                                       scales.data_ptr(), _ptr(dq), _stream(w)))
+    return qweight, qzeros, scales, dq
+
+
+def dequant_awq(qweight, qzeros, scales, group):
+    """(q - z) * s -> W_kn [K, N] in scales.dtype (utils/packing_utils.py:87-102)."""
+    _cuda(qweight, "qweight")
+    k, nw = qweight.shape
+    out = torch.empty((k, nw * 8), dtype=scales.dtype, device=qweight.device)
+    with torch.cuda.device(qweight.device):
+        check(lib().qdm_dequant_awq(qweight.contiguous().data_ptr(), qzeros.contiguous().data_ptr(),
+                                    scales.contiguous().data_ptr(), _dt(scales), k, nw * 8, int(group),
+                                    out.data_ptr(), _stream(qweight)))
+    return out
+
+
+# ------------------------------------------------------------------ (c)(d) GEMMs
+def _gemm_io(x, n_out, out_dtype=None):
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = torch.empty((x2.shape[0], n_out), dtype=out_dtype or x.dtype, device=x.device)
+    return x2, y
+
+
+def gemm_f16(x, w, bias=None):
+    """F.linear(x, w, bias) with w [N, K] (fake-quant weights, quantize/fake_quant.py:223)."""
+    _cuda(x, "x"), _cuda(w, "w")
+    if w.dtype != x.dtype:
+        raise ValueError("x and w must share a dtype")
+    x2, y = _gemm_io(x, w.shape[0])
+    wc = w.contiguous()
+    b = bias.to(x.dtype).contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        check(lib().qdm_gemm_f16(x2.data_ptr(), wc.data_ptr(), _ptr(b), y.data_ptr(), _dt(x2),
+                                 x2.shape[0], wc.shape[0], wc.shape[1], _stream(x)))
+    return y.reshape(*x.shape[:-1], w.shape[0])
+
+
+def gemm_f16_kn(x, w_kn, bias=None):
+    """x @ w_kn + bias with w_kn [K, N]."""
+    _cuda(x, "x"), _cuda(w_kn, "w_kn")
+    if w_kn.dtype != x.dtype:
+        raise ValueError("x and w must share a dtype")
+    x2, y = _gemm_io(x, w_kn.shape[1])
+    wc = w_kn.contiguous()
+    b = bias.to(x.dtype).contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        check(lib().qdm_gemm_f16_kn(x2.data_ptr(), wc.data_ptr(), _ptr(b), y.data_ptr(), _dt(x2),
+                                    x2.shape[0], wc.shape[1], wc.shape[0], _stream(x)))
+    return y.reshape(*x.shape[:-1], w_kn.shape[1])
+
+
+def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None):
+    """x @ dequant(qweight, qzeros, scales) + bias, AWQ GEMM layout (quantize/quantizer.py:544-569)."""
+    _cuda(x, "x"), _cuda(qweight, "qweight")
+    if scales.dtype != x.dtype:
+        raise ValueError("scales must have the activation dtype")
+    k, nw = qweight.shape
+    n = nw * 8
+    if x.shape[-1] != k:
+        raise ValueError(f"x has K={x.shape[-1]}, qweight has K={k}")
+    x2, y = _gemm_io(x, n)
+    b = bias.to(x.dtype).contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        check(lib().qdm_gemm_w4a16(x2.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(), _ptr(b),
+                                   y.data_ptr(), _dt(x2), x2.shape[0], n, k, int(group), _stream(x)))
+    return y.reshape(*x.shape[:-1], n)
+
+
+def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):
+    """(xq @ wq.T) * sx[:, None] * sw[None, :] + bias with int8 codes and fp32 scales."""
+    _cuda(xq, "xq"), _cuda(wq, "wq")
+    m, k = xq.shape
+    n = wq.shape[0]
+    y = torch.empty((m, n), dtype=out_dtype, device=xq.device)
+    b = bias.to(out_dtype).contiguous() if bias is not None else None
+    with torch.cuda.device(xq.device):
+        check(lib().qdm_gemm_w8a8(xq.data_ptr(), sx.data_ptr(), wq.data_ptr(), sw.data_ptr(), _ptr(b), y.data_ptr(),
+                                  _DTYPES[out_dtype], m, n, k, _stream(xq)))
+    return y
+
+
+def gemm_w4a16_host(x_host, x_dev, qweight, qzeros, scales, group, bias, y_dev, y_host):
+    """Host-buffer entry: pinned x_host -> device -> W4A16 GEMM -> pinned y_host, all on the current stream."""
+    k, nw = qweight.shape
+    m = x_host.numel() // k
+    with torch.cuda.device(x_dev.device):
+        check(lib().qdm_gemm_w4a16_host(x_host.data_ptr(), x_dev.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(),
+                                        scales.data_ptr(), _ptr(bias), y_dev.data_ptr(), y_host.data_ptr(),
+                                        _dt(x_dev), m, nw * 8, k, int(group), _stream(x_dev)))
+    return y_host

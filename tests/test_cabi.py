@@ -1,0 +1,49 @@
+"""CPU: libqdm.so loads, exports every symbol include/qdm.h declares, validates arguments before it
+touches a device, and refuses to compute without a B200 (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "qdm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qdm_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(qdm):
+    lib = qdm._lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"libqdm.so does not export {s}"
+    assert set(qdm._lib.SIGNATURES) == set(syms), set(qdm._lib.SIGNATURES) ^ set(syms)
+    assert lib.qdm_version() >= 100
+
+
+def test_argument_errors_map_to_reference_exception_types(qdm):
+    lib = qdm._lib.load()
+    # group must divide K -> QDM_ERR_INVALID -> ValueError (fake_quant.py:198,253 raise ValueError)
+    rc = lib.qdm_quant_group(1, 0, 4, 100, 64, 4, 1, None, None, None, None, None, None, None, None)
+    assert rc == qdm._lib.QDM_ERR_INVALID
+    with pytest.raises(ValueError, match="group"):
+        qdm._lib.check(rc)
+    rc = lib.qdm_gemm_w4a16(16, 16, 16, 16, None, 16, 0, 128, 128, 100, 64, None)
+    assert rc == qdm._lib.QDM_ERR_INVALID and "multiple of 64" in qdm._lib.last_error()
+    rc = lib.qdm_pack_awq(16, 12, 64, 16, None)
+    assert rc == qdm._lib.QDM_ERR_INVALID
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback(qdm):
+    lib = qdm._lib.load()
+    assert lib.qdm_device_check(0) == qdm._lib.QDM_ERR_DEVICE
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        qdm.ops.colabsmax(torch.randn(4, 8))
+    with pytest.raises(RuntimeError):
+        qdm._lib.check(lib.qdm_rowabsmax(16, 0, 4, 8, 16, None))

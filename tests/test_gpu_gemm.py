@@ -1,0 +1,99 @@
+"""GPU parity for kernels (c) W4A16 and (d) W8A8 (tcgen05/TMEM GEMMs) through the C ABI.
+
+Tolerance (north star): max |y - ref| / max |ref| <= 1e-2 with fp32 accumulation.  The reference
+output is the reference's own formulation on the same inputs: F.linear(x, W_fakequant, bias)
+(quantize/fake_quant.py:223) evaluated in fp32 on the dequantised weights."""
+import pytest
+import torch
+
+from _util import DT, max_rel_err
+
+import oracle.qdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-2
+
+
+def ref_linear(x, w_nk, bias=None):
+    y = x.float().cuda() @ w_nk.float().cuda().t()
+    if bias is not None:
+        y = y + bias.float().cuda()
+    return y.cpu()
+
+
+SHAPES = [(128, 128, 64), (256, 256, 128), (300, 320, 320), (1024, 2432, 2432), (77, 1280, 768), (4096, 640, 2560),
+          (1, 512, 256), (513, 72, 192)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_f16(qdm, dt, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DT[dt])
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DT[dt])
+    b = torch.randn(N, generator=g).to(DT[dt])
+    y = qdm.ops.gemm_f16(x.to(DEV), w.to(DEV), b.to(DEV))
+    assert max_rel_err(y, ref_linear(x, w, b)) <= TOL
+    y2 = qdm.ops.gemm_f16_kn(x.to(DEV), w.t().contiguous().to(DEV), None)
+    assert max_rel_err(y2, ref_linear(x, w)) <= TOL
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("M,N,K,group", [(128, 128, 128, 128), (256, 256, 256, 64), (300, 320, 320, 64),
+                                          (1024, 2432, 2432, 128), (77, 1280, 768, 128), (4096, 2560, 320, 64),
+                                          (1, 1024, 256, 128), (513, 72, 192, 64), (2048, 64, 2432, 128)])
+def test_gemm_w4a16(qdm, dt, M, N, K, group):
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DT[dt])
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DT[dt])
+    b = torch.randn(N, generator=g).to(DT[dt])
+    if N % 64 == 0:
+        qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(w.to(DEV), group, want_dq=True)
+        dq = dq.cpu()
+    else:
+        oq, oz, os_, dq = O.awq_from_linear(w, group, 4)
+        qweight, qzeros, scales = torch.from_numpy(oq).to(DEV), torch.from_numpy(oz).to(DEV), os_.to(DEV)
+    y = qdm.ops.gemm_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV))
+    assert y.shape == (M, N) and y.dtype == DT[dt]
+    assert max_rel_err(y, ref_linear(x, dq, b)) <= TOL
+    # same product through the decoded weight: the in-mainloop dequant is bit-identical to
+    # dequantize_gemm, so the two kernels may differ only by accumulation order
+    y_kn = qdm.ops.gemm_f16_kn(x.to(DEV), qdm.ops.dequant_awq(qweight, qzeros, scales, group), b.to(DEV))
+    assert max_rel_err(y, y_kn.cpu()) <= 2e-3
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (300, 320, 320), (1024, 1280, 1280), (4096, 5120, 640), (77, 1280, 2048),
+                                   (1, 256, 512), (200, 72, 144)])
+def test_gemm_w8a8(qdm, dt, M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g)
+    x[:, 3] *= 20
+    x = x.to(DT[dt])
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DT[dt])
+    b = torch.randn(N, generator=g).to(DT[dt])
+    xq, sx = qdm.ops.actquant_token_i8(x.to(DEV))
+    _, wq, sw, _ = qdm.ops.quant_rowwise(w.to(DEV), 8, want_dq=False, want_codes=True, want_scales=True)
+    y = qdm.ops.gemm_w8a8(xq, sx, wq, sw.float(), b.to(DEV), out_dtype=DT[dt])
+    # exact integer reference of the same codes
+    yi = (xq.cpu().double() @ wq.cpu().double().t()) * sx.cpu().double()[:, None] * sw.cpu().double()[None, :] + b.double()
+    assert max_rel_err(y, yi) <= 4e-3          # one rounding to the output dtype (bf16: 2^-8)
+    # the reference's fake-quant formulation (fake_quant.py:86-93,109-118,223)
+    assert max_rel_err(y, O.linear_w8a8_fake(x, w, b)) <= TOL
+
+
+def test_gemm_large_m_round_trip(qdm):
+    """BASELINE-size shape (SD1.5: M=65536, K=320) through a size-independent property: linearity.
+    y(x1 + x2) == y(x1) + y(x2) up to output rounding, and row permutation equivariance."""
+    M, N, K, group = 65536, 320, 320, 64
+    g = torch.Generator().manual_seed(1)
+    w = (torch.randn(N, K, generator=g) * 0.05).half().to(DEV)
+    qweight, qzeros, scales, _ = qdm.ops.quant_pack_awq(w, group)
+    x1 = torch.randn(M, K, generator=g).half().to(DEV)
+    perm = torch.randperm(M, generator=g).to(DEV)
+    y1 = qdm.ops.gemm_w4a16(x1, qweight, qzeros, scales, group)
+    yp = qdm.ops.gemm_w4a16(x1[perm].contiguous(), qweight, qzeros, scales, group)
+    assert torch.equal(yp, y1[perm])
+    y2 = qdm.ops.gemm_w4a16((x1 * 2).contiguous(), qweight, qzeros, scales, group)
+    assert torch.equal(y2.float(), y1.float() * 2)   # scaling by 2 is exact in fp16/fp32
