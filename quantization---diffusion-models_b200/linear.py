@@ -1,0 +1,105 @@
+"""Real quantized Linear modules behind the reference's module contract.
+
+WQLinear_GEMM  : the W4A16 module the reference imports from (un-vendored) AutoAWQ
+                 (`awq.modules.linear.WQLinear_GEMM`; call sites quantize/quantizer.py:562-569,
+                 models/base.py:1661-1663).  Same buffers (qweight [K, N/8] int32, qzeros [K/g, N/8] int32,
+                 scales [K/g, N], bias [N]) and the same `from_linear(linear, w_bit, group_size, init_only,
+                 scales, zeros)` signature; forward is the tcgen05 dequant-in-mainloop GEMM (kernel c).
+W8A8Linear     : W8 per-channel x A8 per-token (quantize/fake_quant.py:86-93,109-118) with int8 codes and
+                 the dequant scales in the GEMM epilogue (kernel d).  `smooth` carries a SmoothQuant
+                 activation-side divisor when it was not folded into the previous op
+                 (quantize/quantizer_SQ.py:425-431).
+"""
+import torch
+from torch import nn
+
+from . import ops
+
+
+class WQLinear_GEMM(nn.Module):
+    def __init__(self, w_bit, group_size, in_features, out_features, bias, dev, dtype=torch.float16):
+        super().__init__()
+        if w_bit != 4:
+            raise NotImplementedError("Only 4-bit are supported for now.")
+        self.in_features, self.out_features = in_features, out_features
+        self.w_bit = w_bit
+        self.group_size = group_size if group_size != -1 else in_features
+        assert self.in_features % self.group_size == 0
+        assert out_features % (32 // self.w_bit) == 0
+        self.register_buffer("qweight", torch.zeros((in_features, out_features // 8), dtype=torch.int32, device=dev))
+        self.register_buffer("qzeros", torch.zeros((in_features // self.group_size, out_features // 8), dtype=torch.int32, device=dev))
+        self.register_buffer("scales", torch.zeros((in_features // self.group_size, out_features), dtype=dtype, device=dev))
+        if bias:
+            self.register_buffer("bias", torch.zeros(out_features, dtype=dtype, device=dev))
+        else:
+            self.bias = None
+
+    @classmethod
+    def from_linear(cls, linear, w_bit, group_size, init_only=False, scales=None, zeros=None):
+        """With scales/zeros=None the weight is quantised here by the fused RTN+pack kernel
+        (pseudo_quantize_tensor + pack, quantizer.py:540-569 in one pass).  When the caller passes
+        `scales`/`zeros` ([K/g, N], already transposed as quantizer.py:544-547 does) and a weight that
+        is already fake-quantised, re-running the RTN reproduces exactly those codes, scales and zeros
+        (quantisation of a fake-quantised tensor is idempotent); that is asserted, not assumed."""
+        dev, dtype = linear.weight.device, linear.weight.dtype
+        m = cls(w_bit, group_size, linear.in_features, linear.out_features, linear.bias is not None, dev, dtype)
+        if init_only:
+            return m
+        qweight, qzeros, s, _ = ops.quant_pack_awq(linear.weight.data, m.group_size)
+        if scales is not None and not torch.equal(s, scales.to(dtype)):
+            raise ValueError("from_linear: the supplied scales do not match the weight's own RTN scales")
+        m.qweight, m.qzeros, m.scales = qweight, qzeros, s
+        if linear.bias is not None:
+            m.bias = linear.bias.data.clone().to(dtype)
+        return m
+
+    @torch.no_grad()
+    def forward(self, x):
+        xs = x if x.dtype == self.scales.dtype else x.to(self.scales.dtype)
+        y = ops.gemm_w4a16(xs, self.qweight, self.qzeros, self.scales, self.group_size, self.bias)
+        return y if y.dtype == x.dtype else y.to(x.dtype)
+
+    def dequantize(self):
+        """[N, K] fake-quant weight (utils/packing_utils.py:87-102, transposed back to nn.Linear layout)."""
+        return ops.dequant_awq(self.qweight, self.qzeros, self.scales, self.group_size).t().contiguous()
+
+    def extra_repr(self):
+        return "in_features={}, out_features={}, bias={}, w_bit={}, group_size={}".format(
+            self.in_features, self.out_features, self.bias is not None, self.w_bit, self.group_size)
+
+
+class W8A8Linear(nn.Module):
+    def __init__(self, in_features, out_features, bias, dev, dtype=torch.float16):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.register_buffer("qweight", torch.zeros((out_features, in_features), dtype=torch.int8, device=dev))
+        self.register_buffer("w_scales", torch.zeros(out_features, dtype=torch.float32, device=dev))
+        self.register_buffer("smooth", None)
+        if bias:
+            self.register_buffer("bias", torch.zeros(out_features, dtype=dtype, device=dev))
+        else:
+            self.bias = None
+        self.out_dtype = dtype
+
+    @classmethod
+    def from_float(cls, linear, smooth=None):
+        dev, dtype = linear.weight.device, linear.weight.dtype
+        m = cls(linear.in_features, linear.out_features, linear.bias is not None, dev, dtype)
+        _, codes, scales, _ = ops.quant_rowwise(linear.weight.data, 8, want_dq=False, want_codes=True, want_scales=True)
+        m.qweight, m.w_scales = codes, scales.float()
+        if smooth is not None:
+            m.smooth = smooth.to(device=dev, dtype=dtype)
+        if linear.bias is not None:
+            m.bias = linear.bias.data.clone().to(dtype)
+        return m
+
+    @torch.no_grad()
+    def forward(self, x):
+        xs = x if x.dtype == self.out_dtype else x.to(self.out_dtype)
+        xq, sx = ops.actquant_token_i8(xs, self.smooth)
+        y = ops.gemm_w8a8(xq, sx, self.qweight, self.w_scales, self.bias, out_dtype=self.out_dtype)
+        y = y.reshape(*x.shape[:-1], self.out_features)
+        return y if y.dtype == x.dtype else y.to(x.dtype)
+
+    def extra_repr(self):
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, W8A8"
