@@ -377,72 +377,124 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (KIND == G_W4 && warp >= 8) {
     // ===================================================== int4 dequant producers
+    // 256 threads; thread -> one packed word column `wc` (8 output columns) and k rows kr, kr+RPP, ...
+    // Global loads run two k-blocks ahead of the shared-memory writes and do not stop at tile
+    // boundaries (the prefetch cursor walks the same (tile, kb) sequence as every other role).
     constexpr int WPR = BLOCK_N / 8;            // packed words per k row of the tile
-    constexpr int ROWS_PER_PASS = 256 / WPR;    // k rows covered by the 256 dequant threads at once
-    constexpr int PASSES = 64 / ROWS_PER_PASS;
+    constexpr int RPP = 256 / WPR;              // k rows covered by the 256 dequant threads at once (8 or 16)
+    constexpr int PASSES = 64 / RPP;
+    constexpr int DIST = 2;                     // prefetch distance in k-blocks
     const int dt = threadIdx.x - 256;
     const int wc = dt % WPR, kr = dt / WPR;
     const int words_per_row = p.N / 8;
-    const uint32_t dst_off = uint32_t(wc >> 3) * (64 * ROW_BYTES);  // 64-column chunk of the MN-major tile
-    const uint32_t j16 = uint32_t(wc & 7);
+    // MN-major SW128 tile: 64-column chunk (wc>>3), k row stride 128 B, 16-byte slot (wc&7) ^ (k&7);
+    // RPP is a multiple of 8 so the swizzle term is the same for every pass.
+    const uint32_t thr_off = uint32_t(wc >> 3) * (64 * ROW_BYTES) + uint32_t(kr) * ROW_BYTES +
+                             ((uint32_t(wc & 7) ^ uint32_t(kr & 7)) << 4);
+
+    struct Pf {            // one prefetched k-block of this thread
+      uint32_t w[PASSES];  // packed weight words
+      uint32_t zw;         // packed zero points of the group
+      uint4 sv;            // 8 scales
+    };
+    Pf ring[DIST + 1];
+    int pf_tile = blockIdx.x, pf_kb = 0;  // prefetch cursor
+    auto prefetch = [&](Pf& f) {
+      const int n0 = (pf_tile / m_tiles) * BLOCK_N;
+      const int wcol = n0 / 8 + wc;
+      const bool valid = pf_tile < num_tiles && wcol < words_per_row;
+      f.zw = 0u;
+      f.sv = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = 0u;
+      if (valid) {
+        const int32_t* src = p.qweight + int64_t(pf_kb * 64 + kr) * words_per_row + wcol;
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = (uint32_t)__ldg(src + int64_t(ps * RPP) * words_per_row);
+        const int g = (pf_kb * 64) / p.group;
+        f.zw = (uint32_t)__ldg(p.qzeros + int64_t(g) * words_per_row + wcol);
+        f.sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.scales) + int64_t(g) * p.N + wcol * 8));
+      }
+      if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
+    };
+#pragma unroll
+    for (int d = 0; d < DIST; ++d) prefetch(ring[d]);
+
+    // constants kept in registers so that (x & mask) | magic is ONE lop3
+    uint32_t mask_lo = 0x000F000Fu, mask_hi = 0x00F000F0u;
+    uint32_t magic = BF16 ? 0x43004300u : 0x64006400u;  // 128.0 / 1024.0: the nibble lands in the low mantissa bits
+    asm volatile("" : "+r"(mask_lo), "+r"(mask_hi), "+r"(magic));
+    auto and_or = [](uint32_t a, uint32_t b, uint32_t c) {
+      uint32_t d;
+      asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));  // (a & b) | c
+      return d;
+    };
+
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t magic = BF16 ? 0x43004300u : 0x64006400u;  // 128.0 / 1024.0: q sits in the low mantissa bits
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n0 = (tile / m_tiles) * BLOCK_N;
-      const int wcol = n0 / 8 + wc;
-      const bool valid = wcol < words_per_row;
-      const int32_t* qcol = p.qweight + wcol;
-      uint32_t cur[PASSES], nxt[PASSES];
-      auto load_words = [&](int kb, uint32_t* w) {
-#pragma unroll
-        for (int ps = 0; ps < PASSES; ++ps) {
-          const int k = kb * 64 + kr + ps * ROWS_PER_PASS;
-          w[ps] = valid ? (uint32_t)__ldg(qcol + int64_t(k) * words_per_row) : 0u;
-        }
-      };
-      load_words(0, cur);
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (kb + 1 < num_kb) load_words(kb + 1, nxt);
-        // per-group scale / zero for this thread's 8 output columns
-        const int g = (kb * 64) / p.group;
-        uint32_t zw = 0;
-        uint4 sv = make_uint4(0, 0, 0, 0);
-        if (valid) {
-          zw = (uint32_t)__ldg(p.qzeros + int64_t(g) * words_per_row + wcol);
-          sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.scales) + int64_t(g) * p.N + n0 + wc * 8));
-        }
-        uint32_t zp[4];
+        prefetch(ring[DIST]);
+        const Pf& f = ring[0];
+        const uint32_t sp[4] = {f.sv.x, f.sv.y, f.sv.z, f.sv.w};
+        // zero-point operands of the exact (q - z) step, per nibble pair
+        uint32_t zsub[4];
+        if (BF16) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) zp[q] = ((zw >> (4 * q)) & 0x000F000Fu) | magic;
-        const uint32_t sp[4] = {sv.x, sv.y, sv.z, sv.w};
+          for (int q = 0; q < 4; ++q) zsub[q] = and_or(f.zw >> (4 * q), mask_lo, magic);        // 128 + z
+        } else {
+          const uint32_t zs = f.zw >> 8;
+          zsub[0] = and_or(f.zw, mask_lo, magic);                                                // 1024 + z
+          zsub[2] = and_or(zs, mask_lo, magic);
+          // high nibbles decode as 1024 + 16 z; (.)/16 = 64 + z exactly
+          const __half2 sixteenth = __float2half2_rn(0.0625f);
+          const uint32_t z1 = and_or(f.zw, mask_hi, magic), z3 = and_or(zs, mask_hi, magic);
+          __half2 h1 = __hmul2(*reinterpret_cast<const __half2*>(&z1), sixteenth);
+          __half2 h3 = __hmul2(*reinterpret_cast<const __half2*>(&z3), sixteenth);
+          zsub[1] = *reinterpret_cast<uint32_t*>(&h1);
+          zsub[3] = *reinterpret_cast<uint32_t*>(&h3);
+        }
         mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t b_dst = smem_base + stage * C::STAGE_BYTES + A_STAGE_BYTES + dst_off;
+        const uint32_t b_dst = smem_base + stage * C::STAGE_BYTES + A_STAGE_BYTES + thr_off;
 #pragma unroll
         for (int ps = 0; ps < PASSES; ++ps) {
-          const int k = kr + ps * ROWS_PER_PASS;
+          const uint32_t w = f.w[ps];
           uint32_t o[4];
+          if (BF16) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t t = ((cur[ps] >> (4 * q)) & 0x000F000Fu) | magic;  // {magic + q(col 2q), magic + q(col 2q+1)}
-            if (BF16) {
-              __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zp[q]));
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t t = and_or(w >> (4 * q), mask_lo, magic);  // {128 + q(col 2q), 128 + q(col 2q+1)}
+              __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zsub[q]));
               d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&sp[q]));
               o[q] = *reinterpret_cast<uint32_t*>(&d);
-            } else {
-              __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zp[q]));
-              d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));
+            }
+          } else {
+            const uint32_t ws = w >> 8;
+            const __half2 sixteenth = __float2half2_rn(0.0625f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t src = (q < 2) ? w : ws;
+              __half2 d;
+              if ((q & 1) == 0) {   // low nibble of each byte: 1024 + q, exact subtract
+                const uint32_t t = and_or(src, mask_lo, magic);
+                d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zsub[q]));
+              } else {              // high nibble: 1024 + 16 q; fma(., 1/16, -(64 + z)) = q - z exactly
+                const uint32_t t = and_or(src, mask_hi, magic);
+                d = __hfma2(*reinterpret_cast<const __half2*>(&t), sixteenth, __hneg2(*reinterpret_cast<const __half2*>(&zsub[q])));
+              }
+              d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));   // (q - z) * s, one rounding
               o[q] = *reinterpret_cast<uint32_t*>(&d);
             }
           }
-          const uint32_t addr = b_dst + uint32_t(k) * ROW_BYTES + ((j16 ^ uint32_t(k & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_dst + ps * (RPP * ROW_BYTES)), "r"(o[0]), "r"(o[1]),
+                       "r"(o[2]), "r"(o[3])
+                       : "memory");
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar(stage));
 #pragma unroll
-        for (int ps = 0; ps < PASSES; ++ps) cur[ps] = nxt[ps];
+        for (int d = 0; d < DIST; ++d) ring[d] = ring[d + 1];
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }

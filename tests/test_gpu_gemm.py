@@ -96,4 +96,5 @@ def test_gemm_large_m_round_trip(qdm):
     yp = qdm.ops.gemm_w4a16(x1[perm].contiguous(), qweight, qzeros, scales, group)
     assert torch.equal(yp, y1[perm])
     y2 = qdm.ops.gemm_w4a16((x1 * 2).contiguous(), qweight, qzeros, scales, group)
-    assert torch.equal(y2.float(), y1.float() * 2)   # scaling by 2 is exact in fp16/fp32
+    normal = y1.float().abs() >= 2.0 ** -13          # scaling by 2 is exact unless the fp16 output is subnormal
+    assert torch.equal(y2.float()[normal], (y1.float() * 2)[normal])
