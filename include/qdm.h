@@ -193,6 +193,10 @@ int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight,
                         const void* scales, const void* bias, void* y_dev, void* y_host, int dtype,
                         int64_t M, int64_t N, int64_t K, int group, void* stream);
 
+/* Tile-shape override for bring-up and A/B timing: 0 = heuristic, 1 = single-CTA tiles (128 x N),
+ * 2 = CTA-pair tiles (cta_group::2, 256 x N).  Process-wide; not part of the reference interface. */
+int qdm_set_gemm_mode(int ctas);
+
 /* number of kernels launched by this library in the calling thread since the last reset */
 int64_t qdm_launch_count(int reset);
 

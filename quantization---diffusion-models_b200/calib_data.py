@@ -1,0 +1,111 @@
+"""Calibration plumbing with the semantics of the reference's utils/calib_data.py (diffusion part):
+per-Linear activation hooks, deterministic calibration latents (seed 42) and the pipeline run loop.
+The per-call statistic is computed by the col-absmax reduction kernel (kernel a)."""
+import torch
+
+from . import ops
+
+
+class Mean_Max_Activation_Hook:
+    """utils/calib_data.py:105-124: per forward call, max over tokens of |x| per input channel.
+    `max_scales[step]` keeps one [C] vector per call exactly like the reference, so that
+    `mean_of_dict` (models/StableDiffusion1_x.py:104-112) reduces the same values in the same way."""
+
+    def __init__(self):
+        self.hook_handle = None
+        self.max_scales = {}
+        self.step = 0
+
+    def __call__(self, module, module_in, module_out):
+        self.max_scales[self.step] = ops.colabsmax(module_in[0])
+        self.step += 1
+
+    def clear(self):
+        self.max_scales = []
+
+
+class Running_Max_Activation_Hook:
+    """LLM-style statistic of quantize/quantizer_SQ.py:1077-1084: running max over calls, folded in place by
+    the kernel's running mode (no per-call tensors retained)."""
+
+    def __init__(self):
+        self.hook_handle = None
+        self.running = None
+        self.step = 0
+
+    def __call__(self, module, module_in, module_out):
+        x = module_in[0]
+        if self.running is None:
+            self.running = ops.colabsmax(x)
+        else:
+            ops.colabsmax(x, out=self.running, running=True)
+        self.step += 1
+
+
+class Input_Capture_Hook:
+    """Keeps the inputs of a Linear on the GPU (the reference caches them on the CPU, quantizer.py:1097-1100)."""
+
+    def __init__(self, max_tokens=None):
+        self.hook_handle = None
+        self.chunks = []
+        self.max_tokens = max_tokens
+
+    def __call__(self, module, module_in, module_out):
+        x = module_in[0].detach()
+        x = x.reshape(-1, x.shape[-1])
+        self.chunks.append(x)
+
+    def cat(self):
+        x = torch.cat(self.chunks, dim=0)
+        if self.max_tokens is not None and x.shape[0] > self.max_tokens:
+            x = x[:: x.shape[0] // self.max_tokens][: self.max_tokens].contiguous()
+        return x
+
+
+def apply_hook(module: torch.nn.Module, hook_cls=Mean_Max_Activation_Hook):
+    """utils/calib_data.py:216-224: one hook per nn.Linear, keyed by the name relative to `module`."""
+    hook_dictionary = {}
+    for name, submod in module.named_modules():
+        if isinstance(submod, torch.nn.Linear):
+            hook = hook_cls()
+            hook.hook_handle = submod.register_forward_hook(hook)
+            hook_dictionary[name] = hook
+    return hook_dictionary
+
+
+def remove_hooks(hook_d):
+    """utils/calib_data.py:247-249 (the reference iterates the dict itself and fails; `.items()` is meant)."""
+    for _, v in hook_d.items():
+        v.hook_handle.remove()
+
+
+def generate_latents(pipe, batch_size, device, generator):
+    """utils/calib_data.py:139-171: N(0,1) latents of the denoiser's input shape in the pipeline dtype."""
+    shape = (batch_size, pipe.latent_channels, pipe.latent_size, pipe.latent_size)
+    return torch.randn(shape, generator=generator, dtype=torch.float32).to(device=device, dtype=pipe.dtype)
+
+
+def get_calib_dataset_dm(model_pipeline, text_dataset, batch_size=4, n_samples=100, seed=42, device="cuda",
+                         split=None, text_column=None, cut_off_captions=200):
+    """utils/calib_data.py:174-213.  There is no network here, so `text_dataset` must be a list of prompts
+    (any hashable) -- the skeleton pipelines turn a prompt into a deterministic synthetic embedding."""
+    assert n_samples % batch_size == 0, "The batch_size, doesnt divide the dataset, choose an appropriate batch_size"
+    if isinstance(text_dataset, str):
+        prompts = [f"{text_dataset}#{i}" for i in range(n_samples)]   # stand-in captions (offline)
+    else:
+        prompts = list(text_dataset)
+    generator = torch.Generator().manual_seed(seed)
+    calib_data = []
+    for i in range(n_samples // batch_size):
+        prompt_batch = prompts[i * batch_size:(i + 1) * batch_size]
+        calib_data.append((prompt_batch, generate_latents(model_pipeline, batch_size, device, generator)))
+    return calib_data
+
+
+def run_calibration(pipeline, samples, callback=None, n_inference_steps=50, cfg=7.5):
+    """utils/calib_data.py:227-245."""
+    for i, sample in enumerate(samples):
+        if callback is not None:
+            callback.set_batch_num(i)
+        pipeline(prompt=sample[0], latents=sample[1], callback_on_step_end=callback,
+                 num_inference_steps=n_inference_steps, guidance_scale=cfg, num_images_per_prompt=1)

@@ -115,6 +115,71 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cluster / CTA-pair helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, polls = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++polls == 4096) t0 = clock64();
+    if (polls > 4096 && (polls & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();
+  }
+}
+// CTA-pair TMA load: data lands in THIS CTA's shared memory, completion bytes are counted on `bar`, a
+// shared::cluster address (the leader CTA's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  if (KIND == G_I8) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// commit to the same barrier offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
@@ -190,6 +255,195 @@ __device__ __forceinline__ void load8_as_float(const void* base, int64_t idx, bo
       __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
       out[2 * i] = __low2float(h);
       out[2 * i + 1] = __high2float(h);
+    }
+  }
+}
+
+// Drain one accumulator tile: this warp owns 32 TMEM lanes (= 32 output rows starting at `row0`) and walks the
+// BLOCK_N columns in chunks of 64: tcgen05.ld -> scale/bias -> pack -> padded smem transpose -> 16-byte stores
+// in which 8 lanes cover 128 contiguous bytes of one output row.
+template <int BLOCK_N, int KIND, bool BF16>
+__device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg, uint32_t taddr0, int row0, int n0, int lane) {
+  uint16_t* y = reinterpret_cast<uint16_t*>(p.y);
+  const int row = row0 + lane;
+  float sxr = 1.f;
+  if (KIND == G_I8) sxr = (row < p.M) ? p.sx[row] : 0.f;
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
+    const int nc = n0 + c * EPI_COLS;
+    if (nc >= p.N) break;
+    uint32_t v[EPI_COLS];
+    const uint32_t taddr = taddr0 + c * EPI_COLS;
+    tmem_ld32(taddr, v);
+    tmem_ld32(taddr + 32, v + 32);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j8 = 0; j8 < EPI_COLS / 8; ++j8) {
+      const int n = nc + j8 * 8;
+      const bool ok = n < p.N;
+      float bias8[8];
+      load8_as_float<BF16>(p.bias, n, ok, bias8);
+      float f[8];
+      if (KIND == G_I8) {
+        float4 s0 = make_float4(0, 0, 0, 0), s1 = s0;
+        if (ok) {
+          s0 = *reinterpret_cast<const float4*>(p.sw + n);
+          s1 = *reinterpret_cast<const float4*>(p.sw + n + 4);
+        }
+        const float sw8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          f[i] = __fmaf_rn(__fmul_rn(float(int(v[j8 * 8 + i])), __fmul_rn(sxr, sw8[i])), 1.f, bias8[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j8 * 8 + i]) + bias8[i];
+      }
+      uint4 o;
+      o.x = pack_out2<KIND, BF16>(f[0], f[1]);
+      o.y = pack_out2<KIND, BF16>(f[2], f[3]);
+      o.z = pack_out2<KIND, BF16>(f[4], f[5]);
+      o.w = pack_out2<KIND, BF16>(f[6], f[7]);
+      *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + j8 * 16) = o;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3), seg = lane & 7;
+      const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_PITCH + seg * 16);
+      const int gm = row0 + r, gn = nc + seg * 8;
+      if (gm < p.M && gn < p.N) *reinterpret_cast<uint4*>(y + int64_t(gm) * p.N + gn) = o;
+    }
+    __syncwarp();
+  }
+}
+
+// int4 dequant producers: 256 threads fill the MN-major SW128 B tile of NLOC columns for every (tile, k-block).
+// Thread -> one packed word column `wc` (8 output columns) and k rows kr, kr+RPP, ...  Global loads run two
+// k-blocks ahead of the shared-memory writes and do not stop at tile boundaries (the prefetch cursor walks the
+// same (tile, kb) sequence as every other role).  `tile_n` is the tile extent in N, `col_off` this CTA's column
+// offset inside the tile (0, or rank * NLOC in a CTA pair).  full barriers live at full_addr + 8*stage (a
+// shared::cluster address when CLUSTER), empty barriers at empty_addr + 8*stage (always local).
+template <int NLOC, bool BF16, int STAGES, int STAGE_BYTES, bool CLUSTER>
+__device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, int lane, int first_tile, int tile_stride,
+                                                 int num_tiles, int m_tiles, int num_kb, int tile_n, int col_off,
+                                                 uint32_t b_stage0, uint32_t empty_addr, uint32_t full_addr) {
+  constexpr int WPR = NLOC / 8;               // packed words per k row of this CTA's tile part
+  constexpr int RPP = 256 / WPR;              // k rows covered by the 256 dequant threads at once (multiple of 8)
+  constexpr int PASSES = 64 / RPP;
+  constexpr int DIST = 2;                     // prefetch distance in k-blocks
+  static_assert(RPP % 8 == 0 && PASSES >= 1, "tile part too narrow for 256 dequant threads");
+  const int wc = dt % WPR, kr = dt / WPR;
+  const int words_per_row = p.N / 8;
+  // MN-major SW128 tile: 64-column chunk (wc>>3), k row stride 128 B, 16-byte slot (wc&7) ^ (k&7);
+  // RPP is a multiple of 8 so the swizzle term is the same for every pass.
+  const uint32_t thr_off = uint32_t(wc >> 3) * (64 * ROW_BYTES) + uint32_t(kr) * ROW_BYTES +
+                           ((uint32_t(wc & 7) ^ uint32_t(kr & 7)) << 4);
+  struct Pf {            // one prefetched k-block of this thread
+    uint32_t w[PASSES];  // packed weight words
+    uint32_t zw;         // packed zero points of the group
+    uint4 sv;            // 8 scales
+  };
+  Pf ring[DIST + 1];
+  int pf_tile = first_tile, pf_kb = 0;  // prefetch cursor
+  auto prefetch = [&](Pf& f) {
+    const int wcol = ((pf_tile / m_tiles) * tile_n + col_off) / 8 + wc;
+    const bool valid = pf_tile < num_tiles && wcol < words_per_row;
+    f.zw = 0u;
+    f.sv = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = 0u;
+    if (valid) {
+      const int32_t* src = p.qweight + int64_t(pf_kb * 64 + kr) * words_per_row + wcol;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = (uint32_t)__ldg(src + int64_t(ps * RPP) * words_per_row);
+      const int g = (pf_kb * 64) / p.group;
+      f.zw = (uint32_t)__ldg(p.qzeros + int64_t(g) * words_per_row + wcol);
+      f.sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.scales) + int64_t(g) * p.N + wcol * 8));
+    }
+    if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += tile_stride; }
+  };
+#pragma unroll
+  for (int d = 0; d < DIST; ++d) prefetch(ring[d]);
+
+  // constants kept in registers so that (x & mask) | magic is ONE lop3
+  uint32_t mask_lo = 0x000F000Fu, mask_hi = 0x00F000F0u;
+  uint32_t magic = BF16 ? 0x43004300u : 0x64006400u;  // 128.0 / 1024.0: the nibble lands in the low mantissa bits
+  asm volatile("" : "+r"(mask_lo), "+r"(mask_hi), "+r"(magic));
+  auto and_or = [](uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));  // (a & b) | c
+    return d;
+  };
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
+    for (int kb = 0; kb < num_kb; ++kb) {
+      prefetch(ring[DIST]);
+      const Pf& f = ring[0];
+      const uint32_t sp[4] = {f.sv.x, f.sv.y, f.sv.z, f.sv.w};
+      // zero-point operands of the exact (q - z) step, per nibble pair
+      uint32_t zsub[4];
+      if (BF16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) zsub[q] = and_or(f.zw >> (4 * q), mask_lo, magic);        // 128 + z
+      } else {
+        const uint32_t zs = f.zw >> 8;
+        zsub[0] = and_or(f.zw, mask_lo, magic);                                                // 1024 + z
+        zsub[2] = and_or(zs, mask_lo, magic);
+        // high nibbles decode as 1024 + 16 z; (.)/16 = 64 + z exactly
+        const __half2 sixteenth = __float2half2_rn(0.0625f);
+        const uint32_t z1 = and_or(f.zw, mask_hi, magic), z3 = and_or(zs, mask_hi, magic);
+        __half2 h1 = __hmul2(*reinterpret_cast<const __half2*>(&z1), sixteenth);
+        __half2 h3 = __hmul2(*reinterpret_cast<const __half2*>(&z3), sixteenth);
+        zsub[1] = *reinterpret_cast<uint32_t*>(&h1);
+        zsub[3] = *reinterpret_cast<uint32_t*>(&h3);
+      }
+      mbar_wait(empty_addr + 8u * stage, phase ^ 1);
+      const uint32_t b_dst = b_stage0 + stage * STAGE_BYTES + thr_off;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const uint32_t w = f.w[ps];
+        uint32_t o[4];
+        if (BF16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t t = and_or(w >> (4 * q), mask_lo, magic);  // {128 + q(col 2q), 128 + q(col 2q+1)}
+            __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zsub[q]));
+            d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&sp[q]));
+            o[q] = *reinterpret_cast<uint32_t*>(&d);
+          }
+        } else {
+          const uint32_t ws = w >> 8;
+          const __half2 sixteenth = __float2half2_rn(0.0625f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t src = (q < 2) ? w : ws;
+            __half2 d;
+            if ((q & 1) == 0) {   // low nibble of each byte: 1024 + q, exact subtract
+              const uint32_t t = and_or(src, mask_lo, magic);
+              d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zsub[q]));
+            } else {              // high nibble: 1024 + 16 q; fma(., 1/16, -(64 + z)) = q - z exactly
+              const uint32_t t = and_or(src, mask_hi, magic);
+              d = __hfma2(*reinterpret_cast<const __half2*>(&t), sixteenth, __hneg2(*reinterpret_cast<const __half2*>(&zsub[q])));
+            }
+            d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));   // (q - z) * s, one rounding
+            o[q] = *reinterpret_cast<uint32_t*>(&d);
+          }
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_dst + ps * (RPP * ROW_BYTES)), "r"(o[0]), "r"(o[1]),
+                     "r"(o[2]), "r"(o[3])
+                     : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (CLUSTER) mbar_arrive_cluster(full_addr + 8u * stage);
+        else mbar_arrive(full_addr + 8u * stage);
+      }
+#pragma unroll
+      for (int d = 0; d < DIST; ++d) ring[d] = ring[d + 1];
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   }
 }
@@ -316,188 +570,21 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint8_t* stg = smem_gen + STAGES * C::STAGE_BYTES + ew * EPI_WARP_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint16_t* y = reinterpret_cast<uint16_t*>(p.y);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % m_tiles) * BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + ew * 32 + lane;
-      float sxr = 1.f;
-      if (KIND == G_I8) sxr = (row < p.M) ? p.sx[row] : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
-        const int nc = n0 + c * EPI_COLS;
-        if (nc >= p.N) break;
-        uint32_t v[EPI_COLS];
-        const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N + c * EPI_COLS;
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + 32, v + 32);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j8 = 0; j8 < EPI_COLS / 8; ++j8) {
-          const int n = nc + j8 * 8;
-          const bool ok = n < p.N;
-          float bias8[8];
-          load8_as_float<BF16>(p.bias, n, ok, bias8);
-          float f[8];
-          if (KIND == G_I8) {
-            float4 s0 = make_float4(0, 0, 0, 0), s1 = s0;
-            if (ok) {
-              s0 = *reinterpret_cast<const float4*>(p.sw + n);
-              s1 = *reinterpret_cast<const float4*>(p.sw + n + 4);
-            }
-            const float sw8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              f[i] = __fmaf_rn(__fmul_rn(float(int(v[j8 * 8 + i])), __fmul_rn(sxr, sw8[i])), 1.f, bias8[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j8 * 8 + i]) + bias8[i];
-          }
-          uint4 o;
-          o.x = pack_out2<KIND, BF16>(f[0], f[1]);
-          o.y = pack_out2<KIND, BF16>(f[2], f[3]);
-          o.z = pack_out2<KIND, BF16>(f[4], f[5]);
-          o.w = pack_out2<KIND, BF16>(f[6], f[7]);
-          *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + j8 * 16) = o;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3), seg = lane & 7;
-          const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_PITCH + seg * 16);
-          const int gm = m0 + ew * 32 + r, gn = nc + seg * 8;
-          if (gm < p.M && gn < p.N) *reinterpret_cast<uint4*>(y + int64_t(gm) * p.N + gn) = o;
-        }
-        __syncwarp();
-      }
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, stg, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+                                          m0 + ew * 32, n0, lane);
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (KIND == G_W4 && warp >= 8) {
     // ===================================================== int4 dequant producers
-    // 256 threads; thread -> one packed word column `wc` (8 output columns) and k rows kr, kr+RPP, ...
-    // Global loads run two k-blocks ahead of the shared-memory writes and do not stop at tile
-    // boundaries (the prefetch cursor walks the same (tile, kb) sequence as every other role).
-    constexpr int WPR = BLOCK_N / 8;            // packed words per k row of the tile
-    constexpr int RPP = 256 / WPR;              // k rows covered by the 256 dequant threads at once (8 or 16)
-    constexpr int PASSES = 64 / RPP;
-    constexpr int DIST = 2;                     // prefetch distance in k-blocks
-    const int dt = threadIdx.x - 256;
-    const int wc = dt % WPR, kr = dt / WPR;
-    const int words_per_row = p.N / 8;
-    // MN-major SW128 tile: 64-column chunk (wc>>3), k row stride 128 B, 16-byte slot (wc&7) ^ (k&7);
-    // RPP is a multiple of 8 so the swizzle term is the same for every pass.
-    const uint32_t thr_off = uint32_t(wc >> 3) * (64 * ROW_BYTES) + uint32_t(kr) * ROW_BYTES +
-                             ((uint32_t(wc & 7) ^ uint32_t(kr & 7)) << 4);
-
-    struct Pf {            // one prefetched k-block of this thread
-      uint32_t w[PASSES];  // packed weight words
-      uint32_t zw;         // packed zero points of the group
-      uint4 sv;            // 8 scales
-    };
-    Pf ring[DIST + 1];
-    int pf_tile = blockIdx.x, pf_kb = 0;  // prefetch cursor
-    auto prefetch = [&](Pf& f) {
-      const int n0 = (pf_tile / m_tiles) * BLOCK_N;
-      const int wcol = n0 / 8 + wc;
-      const bool valid = pf_tile < num_tiles && wcol < words_per_row;
-      f.zw = 0u;
-      f.sv = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = 0u;
-      if (valid) {
-        const int32_t* src = p.qweight + int64_t(pf_kb * 64 + kr) * words_per_row + wcol;
-#pragma unroll
-        for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = (uint32_t)__ldg(src + int64_t(ps * RPP) * words_per_row);
-        const int g = (pf_kb * 64) / p.group;
-        f.zw = (uint32_t)__ldg(p.qzeros + int64_t(g) * words_per_row + wcol);
-        f.sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.scales) + int64_t(g) * p.N + wcol * 8));
-      }
-      if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += gridDim.x; }
-    };
-#pragma unroll
-    for (int d = 0; d < DIST; ++d) prefetch(ring[d]);
-
-    // constants kept in registers so that (x & mask) | magic is ONE lop3
-    uint32_t mask_lo = 0x000F000Fu, mask_hi = 0x00F000F0u;
-    uint32_t magic = BF16 ? 0x43004300u : 0x64006400u;  // 128.0 / 1024.0: the nibble lands in the low mantissa bits
-    asm volatile("" : "+r"(mask_lo), "+r"(mask_hi), "+r"(magic));
-    auto and_or = [](uint32_t a, uint32_t b, uint32_t c) {
-      uint32_t d;
-      asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));  // (a & b) | c
-      return d;
-    };
-
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        prefetch(ring[DIST]);
-        const Pf& f = ring[0];
-        const uint32_t sp[4] = {f.sv.x, f.sv.y, f.sv.z, f.sv.w};
-        // zero-point operands of the exact (q - z) step, per nibble pair
-        uint32_t zsub[4];
-        if (BF16) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) zsub[q] = and_or(f.zw >> (4 * q), mask_lo, magic);        // 128 + z
-        } else {
-          const uint32_t zs = f.zw >> 8;
-          zsub[0] = and_or(f.zw, mask_lo, magic);                                                // 1024 + z
-          zsub[2] = and_or(zs, mask_lo, magic);
-          // high nibbles decode as 1024 + 16 z; (.)/16 = 64 + z exactly
-          const __half2 sixteenth = __float2half2_rn(0.0625f);
-          const uint32_t z1 = and_or(f.zw, mask_hi, magic), z3 = and_or(zs, mask_hi, magic);
-          __half2 h1 = __hmul2(*reinterpret_cast<const __half2*>(&z1), sixteenth);
-          __half2 h3 = __hmul2(*reinterpret_cast<const __half2*>(&z3), sixteenth);
-          zsub[1] = *reinterpret_cast<uint32_t*>(&h1);
-          zsub[3] = *reinterpret_cast<uint32_t*>(&h3);
-        }
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t b_dst = smem_base + stage * C::STAGE_BYTES + A_STAGE_BYTES + thr_off;
-#pragma unroll
-        for (int ps = 0; ps < PASSES; ++ps) {
-          const uint32_t w = f.w[ps];
-          uint32_t o[4];
-          if (BF16) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t t = and_or(w >> (4 * q), mask_lo, magic);  // {128 + q(col 2q), 128 + q(col 2q+1)}
-              __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zsub[q]));
-              d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&sp[q]));
-              o[q] = *reinterpret_cast<uint32_t*>(&d);
-            }
-          } else {
-            const uint32_t ws = w >> 8;
-            const __half2 sixteenth = __float2half2_rn(0.0625f);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t src = (q < 2) ? w : ws;
-              __half2 d;
-              if ((q & 1) == 0) {   // low nibble of each byte: 1024 + q, exact subtract
-                const uint32_t t = and_or(src, mask_lo, magic);
-                d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zsub[q]));
-              } else {              // high nibble: 1024 + 16 q; fma(., 1/16, -(64 + z)) = q - z exactly
-                const uint32_t t = and_or(src, mask_hi, magic);
-                d = __hfma2(*reinterpret_cast<const __half2*>(&t), sixteenth, __hneg2(*reinterpret_cast<const __half2*>(&zsub[q])));
-              }
-              d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));   // (q - z) * s, one rounding
-              o[q] = *reinterpret_cast<uint32_t*>(&d);
-            }
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_dst + ps * (RPP * ROW_BYTES)), "r"(o[0]), "r"(o[1]),
-                       "r"(o[2]), "r"(o[3])
-                       : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(stage));
-#pragma unroll
-        for (int d = 0; d < DIST; ++d) ring[d] = ring[d + 1];
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
+    w4_producer_loop<BLOCK_N, BF16, STAGES, C::STAGE_BYTES, false>(
+        p, threadIdx.x - 256, lane, blockIdx.x, gridDim.x, num_tiles, m_tiles, num_kb, BLOCK_N, 0,
+        smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, bar_base);
   }
 
   tc_fence_before();
@@ -505,6 +592,171 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- the CTA-pair kernel (cta_group::2)
+// Two CTAs of one cluster (one TPC) work on a 256 x BLOCK_N tile: CTA r holds A rows [128 r, 128 r + 128) and
+// the B columns [NLOC r, NLOC r + NLOC) (NLOC = BLOCK_N / 2) of every k-block in ITS shared memory; the leader
+// (rank 0) issues tcgen05.mma.cta_group::2 with M = 256 and each CTA's tensor core accumulates its 128 rows x
+// BLOCK_N columns in its own TMEM.  Per SM this halves the B operand -- and with it the int4 dequant work and
+// the shared-memory traffic -- per flop.  Barriers: `full` lives in the leader (TMA bytes of both CTAs and
+// the dequant warps of both CTAs arrive there), `empty`/`tmem_full` are signalled in both CTAs by multicast
+// commits, `tmem_empty` lives in the leader and collects the epilogue warps of both CTAs.
+template <int BLOCK_N, int KIND>
+struct Cfg2 {
+  static constexpr int NLOC = BLOCK_N / 2;
+  static constexpr int B_STAGE_BYTES = NLOC * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int STAGES = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int THREADS = (KIND == G_W4) ? 512 : 256;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int K_PER_BLOCK = (KIND == G_I8) ? 128 : 64;
+  static constexpr int FULL_COUNT = (KIND == G_W4) ? 2 + 2 * NUM_DQ_WARPS : 2;
+};
+
+template <int BLOCK_N, int KIND, bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<BLOCK_N, KIND>::THREADS, 1)
+qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+  using C = Cfg2<BLOCK_N, KIND>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int NLOC = C::NLOC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (p.K + C::K_PER_BLOCK - 1) / C::K_PER_BLOCK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    if (KIND != G_W4) tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), C::FULL_COUNT);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 8);   // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits and TMEM allocation of BOTH CTAs are visible before anything remote happens
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
+  const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs; each loads its own halves)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile % m_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M;
+        const int n0 = (tile / m_tiles) * BLOCK_N + int(rank) * NLOC;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          const uint32_t lf = leader_full0 + 8u * stage;
+          const int kc = kb * C::K_PER_BLOCK;
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (KIND == G_W4 ? A_STAGE_BYTES : C::STAGE_BYTES));
+          else mbar_arrive_cluster(lf);
+          tma_load_2d_pair(a_dst, &map_a, lf, kc, m0);
+          if (KIND != G_W4) tma_load_2d_pair(b_dst, &map_b, lf, kc, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr bool B_MN = (KIND == G_W4);
+      constexpr uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, 2 * BLOCK_M, BLOCK_N)
+                                                : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, 2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait_cluster(tmem_empty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024)
+                                     : make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_pair<KIND>(tmem_c, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit_pair(empty_bar(stage));
+          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== epilogue (each CTA drains its own 128 rows)
+    const int ew = warp - 4;
+    uint8_t* stg = smem_gen + STAGES * C::STAGE_BYTES + ew * EPI_WARP_BYTES;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile % m_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, stg, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+                                          m0 + ew * 32, n0, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (KIND == G_W4 && warp >= 8) {
+    // ===================================================== int4 dequant producers (each CTA: its NLOC columns)
+    w4_producer_loop<NLOC, BF16, STAGES, C::STAGE_BYTES, true>(
+        p, threadIdx.x - 256, lane, pair, num_pairs, num_tiles, m_tiles, num_kb, BLOCK_N, int(rank) * NLOC,
+        smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, leader_full0);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -565,8 +817,38 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
   return QDM_OK;
 }
 
+template <int BLOCK_N, int KIND, bool BF16>
+int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg2<BLOCK_N, KIND>;
+  auto kern = qdm_gemm2_kernel<BLOCK_N, KIND, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = m_tiles * n_tiles;
+  const int pairs = tiles < QDM_NUM_SMS / 2 ? tiles : QDM_NUM_SMS / 2;
+  kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
+// 0: heuristic, 1: force the single-CTA kernel, 2: force the CTA-pair kernel (bring-up / A-B timing)
+int g_force_ctas = 0;
+bool use_pair(const GemmParams& p) {
+  if (g_force_ctas == 1) return false;
+  if (g_force_ctas == 2) return true;
+  return p.M > BLOCK_M;   // a second 128-row half exists
+}
+
 template <int KIND>
-int dispatch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int block_n, cudaStream_t st) {
+int dispatch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int block_n, bool pair, cudaStream_t st) {
+  if (pair) {
+    if (block_n == 128)
+      return p.is_bf16 ? launch_gemm2<128, KIND, true>(ma, mb, p, st) : launch_gemm2<128, KIND, false>(ma, mb, p, st);
+    return p.is_bf16 ? launch_gemm2<256, KIND, true>(ma, mb, p, st) : launch_gemm2<256, KIND, false>(ma, mb, p, st);
+  }
   if (block_n == 128) {
     return p.is_bf16 ? launch_gemm<128, KIND, true>(ma, mb, p, st) : launch_gemm<128, KIND, false>(ma, mb, p, st);
   }
@@ -585,6 +867,12 @@ int check_common(const char* fn, const void* x, const void* w, void* y, int dtyp
 
 }  // namespace
 
+extern "C" int qdm_set_gemm_mode(int ctas) {
+  QDM_REQUIRE(ctas >= 0 && ctas <= 2, "qdm_set_gemm_mode: 0 (auto), 1 (single CTA) or 2 (CTA pair)");
+  g_force_ctas = ctas;
+  return QDM_OK;
+}
+
 extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void* y, int dtype,
                             int64_t M, int64_t N, int64_t K, void* stream) {
   int rc = check_common("qdm_gemm_f16", x, w, y, dtype, M, N, K);
@@ -596,10 +884,11 @@ extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void
   const int bn = pick_block_n(N);
   CUtensorMap ma, mb;
   if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
-  if ((rc = make_map(&mb, w, 2, N, K, 64, bn))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
-  return dispatch_gemm<G_F16>(ma, mb, p, bn, (cudaStream_t)stream);
+  const bool pair = use_pair(p);
+  if ((rc = make_map(&mb, w, 2, N, K, 64, pair ? bn / 2 : bn))) return rc;
+  return dispatch_gemm<G_F16>(ma, mb, p, bn, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
@@ -616,7 +905,7 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   if ((rc = make_map(&mb, w_kn, 2, K, N, 64, 64))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
-  return dispatch_gemm<G_F16_KN>(ma, mb, p, bn, (cudaStream_t)stream);
+  return dispatch_gemm<G_F16_KN>(ma, mb, p, bn, false, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
@@ -637,7 +926,7 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.group = group;
   p.qweight = qweight; p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
-  return dispatch_gemm<G_W4>(ma, ma, p, bn, (cudaStream_t)stream);
+  return dispatch_gemm<G_W4>(ma, ma, p, bn, use_pair(p), (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const float* sw,
@@ -653,10 +942,11 @@ extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq
   const int bn = pick_block_n(N);
   CUtensorMap ma, mb;
   if ((rc = make_map(&ma, xq, 1, M, K, 128, BLOCK_M))) return rc;
-  if ((rc = make_map(&mb, wq, 1, N, K, 128, bn))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.sx = sx; p.sw = sw; p.bias = bias; p.y = y; p.is_bf16 = out_dtype == QDM_BF16;
-  return dispatch_gemm<G_I8>(ma, mb, p, bn, (cudaStream_t)stream);
+  const bool pair = use_pair(p);
+  if ((rc = make_map(&mb, wq, 1, N, K, 128, pair ? bn / 2 : bn))) return rc;
+  return dispatch_gemm<G_I8>(ma, mb, p, bn, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight, const int32_t* qzeros,

@@ -1,0 +1,324 @@
+"""Top-level API with the reference's signatures for the quantized-linear path:
+`BaseAWQForDiffusion.quantize(tokenizer=None, quant_config={...}, quantType='awq'|'sq', quantUnet=..., ...)`
+(models/base.py:216-526) and `.generate(prompt, ..., lat=..., generator=...)` (models/base.py:829-850), plus the
+three adapters `StableDiffusion1_x`, `StableDiffusionXL`, `StableDiffusion3_5`
+(models/StableDiffusion1_x.py, StableDiffusionXL.py, StableDiffusion3_5.py).
+
+`from_pretrained` needs diffusers + a checkpoint, neither of which exists offline; `from_skeleton` builds the
+same module tree with random weights (skeletons.py).  `save_quantized` / `from_quantized` store the REAL packed
+tensors (qweight/qzeros/scales) -- SURVEY.md section 8(f) row 2 -- instead of fp16 fake-quant weights.
+"""
+import json
+import os
+from typing import Dict, List, Optional, Union
+
+import torch
+import torch.nn as nn
+
+from .calib_data import Input_Capture_Hook
+from .config import AwqConfig
+from .quantizer import AwqQuantizer
+from .quantizer_SQ import SqQuantizer
+from .scale import AdaLNShift
+from . import skeletons as sk
+
+
+class BaseAWQForDiffusion:
+    kind = None
+
+    def __init__(self, pipeline, model_type, is_quantized=False, config=None, quant_config=None):
+        """models/base.py:120-138."""
+        self.pipeline = pipeline
+        self.model_type, self.is_quantized, self.config = model_type, is_quantized, config or {}
+        self.quant_config: AwqConfig = quant_config or AwqConfig()
+        self.search_result = None
+        self.quantized_components = []
+        self.quantizer = None
+        self.calib_samples = None          # list of (prompts, latents); defaults to a small synthetic set
+        self.calib_steps = 4               # denoise steps per calibration batch for the AWQ capture pass
+        self.calib_max_tokens = 4096       # tokens kept per Linear input (subsampled evenly)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_pretrained(cls, model_path, model_type=None, torch_dtype=torch.float16, **kwargs):
+        raise RuntimeError("from_pretrained needs `diffusers` and a checkpoint; neither is available offline. "
+                           "Use from_skeleton() (random-init weights of the same architecture).")
+
+    @classmethod
+    def from_skeleton(cls, device="cuda", dtype=torch.float16, seed=42, **arch):
+        torch.manual_seed(seed)
+        den = cls.build_denoiser(**arch)
+        pipe = sk.SkeletonPipeline(cls.kind, den, device=device, dtype=dtype, latent_size=arch.get("latent_size"))
+        return cls(pipe, cls.kind, False, {"arch": arch}, AwqConfig())
+
+    def to(self, device):
+        return self.pipeline.to(device)
+
+    # ------------------------------------------------------------------ adapter surface (StableDiffusion1_x.py:39-102)
+    def denoiser(self):
+        return self.pipeline.unet if self.pipeline.unet is not None else self.pipeline.transformer
+
+    def get_model_layers_unet(self):
+        if self.pipeline.unet is None:
+            raise Exception("There is no UNet in this model")
+        return [list(self.pipeline.unet.named_children())]
+
+    def get_model_layers_transformers(self):
+        if self.pipeline.transformer is None:
+            raise Exception("There is no transformer in this model")
+        return [list(self.pipeline.transformer.named_children())]
+
+    def get_model_layers_te(self):
+        return []
+
+    def get_model_layers_vae(self):
+        return []
+
+    def get_root(self, component, idx):
+        return self.denoiser()
+
+    def get_unet(self):
+        return self.pipeline.unet
+
+    def get_transformer(self):
+        return self.pipeline.transformer
+
+    def get_pipeline(self):
+        return self.pipeline
+
+    def set_quantized_components(self, component):
+        self.quantized_components.append(component)
+
+    def get_debugModuleNames(self, **_):
+        return []
+
+    def get_scalingStates(self, **_):
+        return []
+
+    def get_projectionNames(self, **_):
+        return []
+
+    def mean_of_dict(self, act_dict):
+        """models/StableDiffusion1_x.py:104-112: mean over calls of the per-call maxima."""
+        return torch.mean(torch.stack(list(act_dict.values())), dim=0)
+
+    # ------------------------------------------------------------------ AWQ search support (new for diffusion)
+    def block_types(self):
+        return (sk.BasicTransformerBlock,)
+
+    def get_search_blocks(self):
+        return {n: m for n, m in self.denoiser().named_modules() if isinstance(m, self.block_types())}
+
+    get_smoothing_blocks = get_search_blocks   # models/StableDiffusion1_x.py:96-102
+
+    @staticmethod
+    def block_cost(block):
+        return sum(m.weight.numel() for m in block.modules() if isinstance(m, nn.Linear))
+
+    def default_calib_samples(self, n_batches=1, batch_size=2):
+        from .calib_data import get_calib_dataset_dm
+        return get_calib_dataset_dm(self.pipeline, "synthetic-captions", batch_size=batch_size,
+                                    n_samples=n_batches * batch_size, seed=42, device=self.pipeline.device)
+
+    @torch.no_grad()
+    def capture_block_inputs(self, block_names):
+        """One FP pass over the calibration set with a capture hook on every Linear of the requested blocks:
+        {block: {linear_name: X [n_tok, K]}} kept on the GPU (the FP activations of the un-quantised model,
+        as quantizer.py:1093-1141 collects them block by block)."""
+        blocks = self.get_search_blocks()
+        hooks = {}
+        for bn in block_names:
+            for ln, lin in blocks[bn].named_modules():
+                if isinstance(lin, nn.Linear):
+                    h = Input_Capture_Hook(self.calib_max_tokens)
+                    h.hook_handle = lin.register_forward_hook(h)
+                    hooks[(bn, ln)] = h
+        samples = self.calib_samples or self.default_calib_samples()
+        for prompts, latents in samples:
+            self.pipeline(prompt=prompts, latents=latents, num_inference_steps=self.calib_steps, guidance_scale=7.5)
+        feats = {bn: {} for bn in block_names}
+        for (bn, ln), h in hooks.items():
+            h.hook_handle.remove()
+            feats[bn][ln] = h.cat()
+        return feats
+
+    def get_layers_for_scaling(self, block, input_feat):
+        """Scaling groups of a BasicTransformerBlock: the two groups the reference's SmoothQuant
+        table has (StableDiffusion1_x.py:117-139) plus norm2 -> attn2.to_q.  Each group: prev_op, layers, inp,
+        module2inspect (the dict shape of the LLM adapters, e.g. models/llava.py:42-89)."""
+        class _Cat(nn.Module):
+            def __init__(self, ls):
+                super().__init__()
+                self.ls = nn.ModuleList(ls)
+
+            def forward(self, x):
+                return torch.cat([l(x) for l in self.ls], dim=-1)
+
+        qkv = [block.attn1.to_q, block.attn1.to_k, block.attn1.to_v]
+        return [
+            dict(prev_op=block.norm1, layers=qkv, inp=input_feat["attn1.to_q"], module2inspect=_Cat(qkv)),
+            dict(prev_op=block.norm2, layers=[block.attn2.to_q], inp=input_feat["attn2.to_q"]),
+            dict(prev_op=block.norm3, layers=[block.ff.net[0].proj], inp=input_feat["ff.net.0.proj"]),
+        ]
+
+    def get_layers_for_scaling_unet(self, module, hooks):
+        """models/StableDiffusion1_x.py:115-150 (SmoothQuant groups with their activation statistic)."""
+        return [
+            dict(prev_op=module.norm1, layers=[module.attn1.to_q, module.attn1.to_k, module.attn1.to_v],
+                 activations_max=[self.mean_of_dict(hooks[n].max_scales) for n in ('attn1.to_q', 'attn1.to_k', 'attn1.to_v')]),
+            dict(prev_op=module.norm3, layers=[module.ff.net[0].proj],
+                 activations_max=[self.mean_of_dict(hooks['ff.net.0.proj'].max_scales)]),
+        ]
+
+    # ------------------------------------------------------------------ models/base.py:216-526
+    @torch.no_grad()
+    def quantize(self, tokenizer=None, quant_config: Dict = {}, calib_data="pileval", split="train", text_column="text",
+                 duo_scaling=True, export_compatible=False, apply_clip=True, applyScale=True, quant_act=False,
+                 n_parallel_calib_samples=None, max_chunk_memory=1024 * 1024 * 1024, quantType="awq", quantUnet=True,
+                 quantTextEncoder=False, quantVAE=False, quantTransformer=False, codeBookQuantInd=False,
+                 debugSavePath="", debugPlot=False, calibrate=False, alpha=0.5, shard=None, **kwargs):
+        """Same call shape as the reference (first positional is `tokenizer`; the method is picked by `quantType`).
+        New keywords: `calibrate` (run the AWQ scale/clip search on the diffusion blocks), `alpha` (SmoothQuant),
+        `shard` = (rank, world) for the sharded search."""
+        quant_config = dict(quant_config)
+        if quant_act and quant_config.get('version', 'fake_act').lower() != 'fake_act':
+            quant_config['version'] = 'fake_act'
+        self.quant_config = AwqConfig.from_dict(quant_config)
+        qc = self.quant_config
+        common = dict(quantise_act=qc.quantize_act, weight_quant_conv_type=qc.weight_quant_conv_type,
+                      weight_quant_type=qc.weight_quant_type, act_quant_conv_type=qc.act_quant_conv_type,
+                      act_quant_conv_group_size=qc.act_quant_conv_group_size, w_bit=qc.w_bit, wv_bit=qc.wv_bit, a_bit=qc.a_bit,
+                      group_size=qc.q_group_size, zero_point=qc.zero_point, version=qc.version, calib_data=calib_data,
+                      split=split, text_column=text_column, duo_scaling=duo_scaling,
+                      modules_to_not_convert=qc.modules_to_not_convert, export_compatible=export_compatible,
+                      quant_act=quant_act, apply_clip=apply_clip, applyScale=applyScale,
+                      n_parallel_calib_samples=n_parallel_calib_samples, max_chunk_memory=max_chunk_memory,
+                      quantUnet=quantUnet and self.pipeline.unet is not None, quantTextEncoder=quantTextEncoder, quantVAE=quantVAE,
+                      quantTransformer=quantTransformer or (self.pipeline.transformer is not None and quantUnet),
+                      diffusion_model=True, codeBookQuantInd=codeBookQuantInd)
+        if quantType.lower() == 'awq':
+            self.quantizer = AwqQuantizer(self, None, None, calibrate=calibrate, **common)
+            if shard is not None and calibrate:
+                from .dist import sharded_search
+                results = sharded_search(self.quantizer, shard)
+                self.quantizer.apply_search_results(results)
+                self.quantizer.calibrate = False
+            self.quantizer.quantize(debugSavePath, debugPlot)
+        elif quantType.lower() == 'sq':
+            self.quantizer = SqQuantizer(self, None, None, alpha=alpha, **{**common, **kwargs})
+            self.quantizer.quantize(debugSavePath, debugPlot, samples=self.calib_samples)
+        else:
+            raise NotImplementedError("Only awq and sq are supported for now.")
+        self.is_quantized = True
+
+    # ------------------------------------------------------------------ models/base.py:829-850
+    @torch.no_grad()
+    def generate(self, prompt, height=512, width=512, num_inference_steps=50, guidance_scale=7.5, negative_prompt=None,
+                 num_images_per_prompt=1, generator=None, device="cpu", lat=None, output_type=None, **kwargs):
+        if self.pipeline is None:
+            raise RuntimeError("The diffusion pipeline is not loaded. Please use `from_pretrained` or `from_quantized` first.")
+        return self.pipeline(prompt=prompt, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+                             num_images_per_prompt=1, generator=generator, latents=lat, output_type=output_type)
+
+    # ------------------------------------------------------------------ packed checkpoint
+    def save_quantized(self, save_dir):
+        """models/base.py:530-582 re-thought: the denoiser state dict (packed int4 / int8 tensors for swapped
+        modules) + quantization_config + the list of quantised components."""
+        os.makedirs(save_dir, exist_ok=True)
+        torch.save(self.denoiser().state_dict(), os.path.join(save_dir, "denoiser.pt"))
+        kinds = {n: type(m).__name__ for n, m in self.denoiser().named_modules()
+                 if type(m).__name__ in ("WQLinear_GEMM", "W8A8Linear", "WxAxLinear", "WxAxConv2d")}
+        meta = {"model_type": self.model_type, "arch": self.config.get("arch", {}), "quantization_config": self.quant_config.to_transformers_dict(),
+                "quant_config": self.quant_config.to_dict(), "quant_components": self.quantized_components, "modules": kinds}
+        with open(os.path.join(save_dir, "quant_components.json"), "w") as f:
+            json.dump(meta, f, indent=1)
+
+    @classmethod
+    def from_quantized(cls, save_dir, device="cuda", dtype=torch.float16):
+        """models/base.py:736-826: rebuild the module tree, swap in `init_only` quantised modules, load the state."""
+        from .fake_quant import WxAxConv2d, WxAxLinear
+        from .linear import W8A8Linear, WQLinear_GEMM
+        from .module import get_op_by_name, set_op_by_name
+        from .fake_quant import _effective_group
+        with open(os.path.join(save_dir, "quant_components.json")) as f:
+            meta = json.load(f)
+        model = cls.from_skeleton(device=device, dtype=dtype, **meta["arch"])
+        model.quant_config = AwqConfig.from_dict(meta["quant_config"])
+        den = model.denoiser()
+        for name, kind in meta["modules"].items():
+            old = get_op_by_name(den, name)
+            if kind == "WQLinear_GEMM":
+                new = WQLinear_GEMM.from_linear(old, 4, _effective_group(old.in_features, model.quant_config.q_group_size), init_only=True)
+            elif kind == "W8A8Linear":
+                new = W8A8Linear(old.in_features, old.out_features, old.bias is not None, old.weight.device, dtype)
+            elif kind == "WxAxLinear":
+                new = WxAxLinear.from_float(old, init_only=True).to(old.weight.device)
+            else:
+                new = WxAxConv2d.from_float(old, init_only=True).to(old.weight.device)
+            set_op_by_name(den, name, new)
+        den.load_state_dict(torch.load(os.path.join(save_dir, "denoiser.pt"), map_location=device))
+        model.is_quantized = True
+        model.quantized_components = meta["quant_components"]
+        return model
+
+
+class StableDiffusion1_x(BaseAWQForDiffusion):
+    kind = "sd15"
+
+    @staticmethod
+    def build_denoiser(channels=(320, 640, 1280, 1280), depth=(1, 1, 1, 0), ctx_dim=768, heads=8, **_):
+        return sk.UNet2DConditionSkeleton(tuple(channels), tuple(depth), ctx_dim=ctx_dim, heads=heads)
+
+    def checkQuantStatus(self, quantUnet=True, quantTextEncoder=False, quantVAE=False, quantTransformer=True):
+        if quantTransformer:
+            raise Exception("There is no Transformer in this Diffusion Model")
+
+
+class StableDiffusionXL(BaseAWQForDiffusion):
+    kind = "sdxl"
+
+    @staticmethod
+    def build_denoiser(channels=(320, 640, 1280), depth=(0, 2, 10), ctx_dim=2048, head_dim=64, add_embed_in=2816, **_):
+        return sk.UNet2DConditionSkeleton(tuple(channels), tuple(depth), ctx_dim=ctx_dim, head_dim=head_dim, linear_proj=True,
+                                          add_embed_in=add_embed_in)
+
+
+class StableDiffusion3_5(BaseAWQForDiffusion):
+    kind = "sd3"
+
+    @staticmethod
+    def build_denoiser(layers=38, dim=2432, heads=38, in_ch=16, patch=2, ctx_in=4096, pooled=2048, **_):
+        return sk.MMDiTSkeleton(layers=layers, dim=dim, heads=heads, in_ch=in_ch, patch=patch, ctx_in=ctx_in, pooled=pooled)
+
+    def block_types(self):
+        return (sk.JointTransformerBlock,)
+
+    def get_layers_for_scaling(self, block, input_feat):
+        """JointTransformerBlock: the LayerNorms are non-affine and the affine comes from AdaLN modulation, so
+        1/s is folded into the shift / scale rows of norm1.linear (scale.py AdaLNShift)."""
+        class _Cat(nn.Module):
+            def __init__(self, ls):
+                super().__init__()
+                self.ls = nn.ModuleList(ls)
+
+            def forward(self, x):
+                return torch.cat([l(x) for l in self.ls], dim=-1)
+
+        d = block.attn.to_q.in_features
+        qkv = [block.attn.to_q, block.attn.to_k, block.attn.to_v]
+        add = [block.attn.add_q_proj, block.attn.add_k_proj, block.attn.add_v_proj]
+        groups = [
+            dict(prev_op=AdaLNShift(block.norm1.linear, slice(0, d), slice(d, 2 * d)), layers=qkv,
+                 inp=input_feat["attn.to_q"], module2inspect=_Cat(qkv)),
+            dict(prev_op=AdaLNShift(block.norm1_context.linear, slice(0, d), slice(d, 2 * d)), layers=add,
+                 inp=input_feat["attn.add_q_proj"], module2inspect=_Cat(add)),
+            dict(prev_op=AdaLNShift(block.norm1.linear, slice(3 * d, 4 * d), slice(4 * d, 5 * d)), layers=[block.ff.net[0].proj],
+                 inp=input_feat["ff.net.0.proj"]),
+        ]
+        if not block.context_pre_only:
+            groups.append(dict(prev_op=AdaLNShift(block.norm1_context.linear, slice(3 * d, 4 * d), slice(4 * d, 5 * d)),
+                               layers=[block.ff_context.net[0].proj], inp=input_feat["ff_context.net.0.proj"]))
+        return groups
+
+    def get_layers_for_scaling_unet(self, module, hooks):
+        raise NotImplementedError("SmoothQuant groups are defined for UNet BasicTransformerBlocks only (as in the reference)")

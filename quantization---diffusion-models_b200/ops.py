@@ -49,6 +49,11 @@ def lib():
     return _lib.load()
 
 
+def set_gemm_mode(ctas=0):
+    """0 = heuristic, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles; bring-up / A-B timing only."""
+    check(lib().qdm_set_gemm_mode(int(ctas)))
+
+
 def launch_count(reset=False):
     return int(lib().qdm_launch_count(1 if reset else 0))
 

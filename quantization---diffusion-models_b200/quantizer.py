@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's quantize/quantizer.py (class AwqQuantizer): same method names,
+argument meaning and results; the arithmetic runs in libqdm's sm_100a kernels.
+
+What differs from the reference, on purpose (SURVEY.md sections 0.4, 3.2, 3.5):
+  * the activation-aware scale/clip search is wired to the DIFFUSION branch (the reference hard-codes
+    `calibrate = False` there, quantizer.py:1050, and only searches for LLMs): the model adapter supplies
+    the transformer blocks, their captured inputs and `get_layers_for_scaling`;
+  * calibration inputs stay on the GPU (the reference caches them on the CPU, quantizer.py:1099, and restores
+    the weights from a CPU state dict 20 times per group, :703,743);
+  * Q(W*s)/s is ONE fused kernel writing into a scratch weight; the original weight is never touched, so
+    nothing has to be restored;
+  * the 20 losses stay on the device and the argmin costs one sync per group (the reference syncs per chunk
+    per ratio, :777);
+  * `_apply_quant` honours `bitWidth` (the reference ignores it, :540-542).
+(block, group) searches are independent, so `quantize()` can shard them over ranks: see dist.py.
+"""
+import logging
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .fake_quant import WxAxConv2d, WxAxLinear
+from .linear import WQLinear_GEMM
+from .module import (ModuleTraversal, append_str_prefix, exclude_layers_to_not_quantize, get_named_linears, get_op_name,
+                     set_op_by_name)
+from .scale import apply_clip, apply_scale
+
+
+class AwqQuantizer:
+    def __init__(self, awq_model, model=None, tokenizer=None, quantise_act=False, weight_quant_conv_type="per_channel",
+                 weight_quant_type="group", act_quant_conv_type="per_channel", act_quant_conv_group_size=1,
+                 w_bit=4, wv_bit=4, a_bit=16, group_size=128, zero_point=True, version="fake_act", calib_data=None,
+                 split="train", text_column="text", duo_scaling=True, modules_to_not_convert=None,
+                 export_compatible=False, quant_act=False, apply_clip=True, applyScale=True, samples=512,
+                 n_parallel_calib_samples=None, max_chunk_memory=1024 * 1024 * 1024, quantUnet=True,
+                 quantTextEncoder=False, quantVAE=False, quantTransformer=False, diffusion_model=True,
+                 codeBookQuantInd=False, calibrate=False, **unused_llm_flags) -> None:
+        """Keyword names follow quantizer.py:36-81; `calibrate` switches the activation-aware search on for
+        diffusion models (new).  LLM/VLM-only flags are accepted and ignored."""
+        self.awq_model, self.model, self.tokenizer = awq_model, model, tokenizer
+        self.w_bit, self.wv_bit, self.a_bit = w_bit, wv_bit, a_bit
+        self.quantise_act = quantise_act
+        self.weight_quant_conv_type, self.weight_quant_type = weight_quant_conv_type, weight_quant_type
+        self.act_quant_conv_type, self.act_quant_conv_group_size = act_quant_conv_type, act_quant_conv_group_size
+        self.group_size, self.zero_point, self.version = group_size, zero_point, version
+        self.calib_data, self.split, self.text_column = calib_data, split, text_column
+        self.duo_scaling = duo_scaling
+        self.export_compatible, self.quant_act = export_compatible, quant_act
+        self.apply_clip, self.applyScale = apply_clip, applyScale
+        self.n_parallel_calib_samples, self.max_chunk_memory = n_parallel_calib_samples, max_chunk_memory
+        self.modules_to_not_convert = modules_to_not_convert if modules_to_not_convert is not None else []
+        self.samples = samples
+        self.quantUnet, self.quantTextEncoder, self.quantVAE, self.quantTransformer = quantUnet, quantTextEncoder, quantVAE, quantTransformer
+        self.codeBookQuantInd, self.diffusion_model = codeBookQuantInd, diffusion_model
+        self.calibrate = calibrate
+        self.search_log = []   # (block name, prev_op name, layer names, best ratio, best loss) per group
+        if codeBookQuantInd:
+            raise NotImplementedError("codebook quantisation is outside the quantized-linear hot path")
+        if awq_model is not None:
+            self.modules, self.module_kwargs, self.inps = self.init_quant()
+        else:
+            self.modules, self.module_kwargs, self.inps = {}, [], []
+
+    MyTraversal = ModuleTraversal   # quantizer.py:142-159
+
+    # ------------------------------------------------------------------ quantizer.py:163-213
+    def pseudo_quantize_tensor(self, w: torch.Tensor, bitWidth=4):
+        """Per-group RTN; returns (w_fakequant, scales, zeros|None) exactly like quantizer.py:163-198."""
+        org_w_shape = w.shape
+        if self.group_size > 0:
+            assert org_w_shape[-1] % self.group_size == 0
+        else:
+            assert w.dim() == 2
+        dq, _, scales, zeros = ops.quant_group(w, self.group_size, bitWidth, zero_point=self.zero_point)
+        return dq.reshape(org_w_shape), scales.view(org_w_shape[0], -1), (zeros.view(org_w_shape[0], -1) if zeros is not None else None)
+
+    def pseudo_dequantize_tensor(self, w: nn.Linear, scales: torch.Tensor, zeros: Optional[torch.Tensor] = None):
+        """quantizer.py:200-213 (plain tensor algebra on integer-valued weights)."""
+        repeat_count = w.weight.data.shape[-1] // scales.shape[-1]
+        scales = scales.repeat(1, repeat_count).reshape(w.weight.data.shape)
+        if self.zero_point:
+            zeros = zeros.repeat(1, repeat_count).reshape(w.weight.data.shape)
+            return (w.weight.data - zeros) * scales
+        return w.weight.data * scales
+
+    # ------------------------------------------------------------------ init (quantizer.py:1049-1091, diffusion)
+    def init_quant(self):
+        modules = {"unet": [], "text_encoder": [], "vae": [], "transformer": []}
+        if self.quantUnet:
+            modules["unet"] = self.awq_model.get_model_layers_unet()
+        if self.quantTextEncoder:
+            modules["text_encoder"] = self.awq_model.get_model_layers_te()
+        if self.quantVAE:
+            modules["vae"] = self.awq_model.get_model_layers_vae()
+        if self.quantTransformer:
+            modules["transformer"] = self.awq_model.get_model_layers_transformers()
+        return modules, [], []
+
+    # ------------------------------------------------------------------ quantize (quantizer.py:386-425, diffusion)
+    @torch.no_grad()
+    def quantize(self, debugSavePath=None, debugPlot=False, shard=None):
+        """Diffusion branch.  With `calibrate` the activation-aware search (quantizer.py:216-385 transplanted to
+        UNet / MMDiT blocks) runs first: scales are folded (scale.py:37-84), clips applied (scale.py:25-34),
+        and only then every Linear / Conv2d is swapped.  `shard` = (rank, world) restricts the search to this
+        rank's blocks; dist.py gathers the results so every rank applies the identical list."""
+        if self.calibrate:
+            results = self.search(shard=shard)
+            self.apply_search_results(results)
+        for key in self.modules:
+            for k, module_list in enumerate(self.modules[key]):
+                root = self.awq_model.get_root(key, k)
+                self.awq_model.set_quantized_components(f"{key}_{k + 1}" if (len(self.modules[key]) > 1 and k > 0) else key)
+                for name, mod in module_list:
+                    if next(mod.parameters(), None) is None:
+                        continue
+                    traversal = self.MyTraversal()
+                    traversal.traverse(name, mod, root)
+                    layers = [(parent, n, l) for parent, n, l in traversal.get_lin_conv()
+                              if not any(key_ in n for key_ in self.modules_to_not_convert)]
+                    if self.version in ("gemm", "w8a8"):
+                        self._apply_quant_real(mod, layers, self.w_bit)
+                    else:
+                        self._apply_quant_fake_act(mod, layers, self.w_bit, debugStruct=None)
+
+    # ------------------------------------------------------------------ search over blocks (new orchestration)
+    @torch.no_grad()
+    def search(self, shard=None):
+        """Returns {block_name: {"scales": [(prev_op_name, layer_names, scales)], "clip": [(layer_name, max_val)]}}
+        for the blocks owned by this rank.  Blocks and their calibration inputs come from the adapter:
+        `get_search_blocks()` -> {name: block}, `capture_block_inputs(names)` -> {name: {linear_name: X}}
+        (inputs of every Linear of the block from one FP pass over the calibration set, kept on the GPU)."""
+        blocks = self.awq_model.get_search_blocks()
+        names = list(blocks)
+        if shard is not None:
+            from .dist import assign_blocks
+            names = assign_blocks(names, [self.awq_model.block_cost(blocks[n]) for n in names], shard[1])[shard[0]]
+        feats = self.awq_model.capture_block_inputs(names)
+        out = {}
+        for bname in names:
+            block = blocks[bname]
+            input_feat = feats[bname]
+            groups = self.awq_model.get_layers_for_scaling(block, input_feat)
+            scales_list = [self._search_best_scale(block, **g) for g in groups] if self.applyScale else []
+            res = {"scales": scales_list, "clip": []}
+            if self.apply_clip:
+                # the clip search runs on the SCALED weights and inputs (quantizer.py:312-336); do that on a view
+                # of the block and roll the weights back so the gathered results can be applied once everywhere
+                named = exclude_layers_to_not_quantize(get_named_linears(block), self.modules_to_not_convert)
+                backup = {n: l.weight.data.clone() for n, l in named.items()}
+                prev_backup = self._snapshot_prev_ops(block, scales_list)
+                apply_scale(block, scales_list, input_feat_dict=input_feat)
+                res["clip"] = self._search_best_clip(block, named, input_feat)
+                for n, l in named.items():
+                    l.weight.data = backup[n]
+                self._restore_prev_ops(prev_backup)
+            out[bname] = res
+            del feats[bname]
+        return out
+
+    def _snapshot_prev_ops(self, block, scales_list):
+        from .scale import AdaLNShift, resolve_prev_op
+        snap = []
+        for prev_name, _, _ in scales_list:
+            op = resolve_prev_op(block, prev_name)
+            target = op.linear if isinstance(op, AdaLNShift) else op
+            snap.append((target, {k: v.detach().clone() for k, v in target.state_dict().items()}))
+        return snap
+
+    @staticmethod
+    def _restore_prev_ops(snap):
+        for target, sd in snap:
+            target.load_state_dict(sd)
+
+    @torch.no_grad()
+    def apply_search_results(self, results):
+        blocks = self.awq_model.get_search_blocks()
+        for bname, res in results.items():
+            apply_scale(blocks[bname], res["scales"])
+            apply_clip(blocks[bname], res["clip"])
+
+    # ------------------------------------------------------------------ module swap (quantizer.py:491-577)
+    def _apply_quant_fake_act(self, module, named_linears, bitWidth, debugStruct=None, debug=False):
+        """quantizer.py:491-533 (diffusion branch): RTN fake-quant of every Linear / Conv2d, in place."""
+        for parent, name, layer in named_linears:
+            quantize_bmm_input = 'k_proj' in name or 'v_proj' in name or 'q_proj' in name
+            if isinstance(layer, torch.nn.Linear):
+                fake = WxAxLinear.from_float(layer, weight_quant=self.weight_quant_type, act_quant='per_token',
+                                             quantize_output=quantize_bmm_input, n_bits_W=bitWidth, n_bits_A=self.a_bit,
+                                             group_size_W=self.group_size, codeBookQuantInd=self.codeBookQuantInd)
+            elif isinstance(layer, torch.nn.Conv2d):
+                fake = WxAxConv2d.from_float(layer, weight_quant=self.weight_quant_conv_type, act_quant=self.act_quant_conv_type,
+                                             quantize_output=self.quantise_act, act_group_size=self.act_quant_conv_group_size,
+                                             n_bits_W=bitWidth, n_bits_A=self.a_bit, codeBookQuantInd=self.codeBookQuantInd)
+            else:
+                continue
+            setattr(parent, name, fake)
+
+    def _apply_quant_real(self, module, named_linears, bitWidth):
+        """version == 'gemm': the reference's `_apply_quant` (quantizer.py:535-577) with the real packed module --
+        pseudo_quantize_tensor + transpose + WQLinear_GEMM.from_linear fused into one RTN+pack kernel.
+        version == 'w8a8': int8 per-channel weights + per-token activations (fake_quant.py:86-93,109-118).
+        Conv2d layers keep the fake-quant path (their GEMM is cuDNN's)."""
+        from .fake_quant import _effective_group
+        from .linear import W8A8Linear
+        for parent, name, layer in named_linears:
+            if isinstance(layer, torch.nn.Linear):
+                if self.version == "w8a8":
+                    new = W8A8Linear.from_float(layer)
+                else:
+                    g = _effective_group(layer.in_features, self.group_size) if self.group_size > 0 else layer.in_features
+                    if g % 64 or layer.out_features % 8:   # shapes the W4A16 kernel does not tile stay fake-quant
+                        self._apply_quant_fake_act(module, [(parent, name, layer)], bitWidth)
+                        continue
+                    new = WQLinear_GEMM.from_linear(layer, bitWidth, g)
+                setattr(parent, name, new)
+            elif isinstance(layer, torch.nn.Conv2d):
+                self._apply_quant_fake_act(module, [(parent, name, layer)], 8 if self.version == "w8a8" else bitWidth)
+
+    def _apply_quant(self, module, named_linears: Dict[str, nn.Linear], bitWidth):
+        """quantizer.py:535-577 for a dict of named Linears (LLM-style call shape)."""
+        for name, linear_layer in named_linears.items():
+            if self.version != "gemm":
+                raise ValueError(f"Unknown version {self.version}")
+            q_linear = WQLinear_GEMM.from_linear(linear_layer, bitWidth, self.group_size)
+            set_op_by_name(module, name, q_linear)
+
+    # ------------------------------------------------------------------ quantizer.py:580-603
+    @torch.no_grad()
+    def _module_forward(self, x: torch.Tensor, module: torch.nn.Module, module_kwargs: Dict) -> torch.Tensor:
+        if self.n_parallel_calib_samples is None:
+            out = module(x, **module_kwargs)
+            return out[0] if isinstance(out, tuple) else out
+        outs = []
+        for xp in torch.split(x, self.n_parallel_calib_samples):
+            o = module(xp, **module_kwargs)
+            outs.append(o[0] if isinstance(o, tuple) else o)
+        return torch.cat(outs, dim=0)
+
+    # ------------------------------------------------------------------ quantizer.py:606-676
+    @torch.no_grad()
+    def _search_best_scale(self, module, prev_op, layers: List[nn.Linear], inp: torch.Tensor, module2inspect=None, kwargs={}):
+        if module2inspect is None:
+            assert len(layers) == 1
+            module2inspect = layers[0]
+        kwargs = {k: v for k, v in kwargs.items() if k != "use_cache"}
+        inp = inp.to(next(module2inspect.parameters()).device)
+        # [STEP 1] per-channel mean of the group-normalised weights (quantizer.py:627-637): fused kernel, fp32 sums
+        weight = torch.cat([m.weight for m in layers], dim=0)
+        w_mean = (ops.awq_wsum(weight, self.group_size if self.group_size > 0 else weight.shape[1]) / weight.shape[0]).to(weight.dtype)
+        # [STEP 2] per-channel mean |x| in fp32 (quantizer.py:642-659): one reduction kernel, no CPU round trip
+        n_tok = inp.numel() // inp.shape[-1]
+        x_mean = (ops.colabssum(inp) / n_tok).to(inp.dtype)
+        # [STEP 3] reference output
+        fp16_output = self._module_forward(inp, module2inspect, kwargs)
+        # [STEP 4] grid search
+        best_scales = self._compute_best_scale(inp, w_mean, x_mean, module2inspect, layers, fp16_output, kwargs)
+        from .scale import describe_prev_op
+        self.search_log.append((describe_prev_op(module, prev_op), self.last_best_ratio, float(self.last_losses.min().item())))
+        return (describe_prev_op(module, prev_op), tuple(get_op_name(module, m) for m in layers), best_scales)
+
+    # ------------------------------------------------------------------ quantizer.py:678-751
+    def _ratio_scales(self, x_mean, w_mean, ratio):
+        """quantizer.py:717-725: K-length vector algebra, left in torch on the device."""
+        if self.duo_scaling:
+            scales = (x_mean.pow(ratio) / (w_mean.pow(1 - ratio) + 1e-4)).clamp(min=1e-4)
+        else:
+            scales = x_mean.pow(ratio).clamp(min=1e-4).view(-1)
+        scales = scales / (scales.max() * scales.min()).sqrt()
+        scales[torch.isinf(scales)] = 1
+        scales[torch.isnan(scales)] = 1
+        return scales
+
+    @torch.no_grad()
+    def _compute_best_scale(self, x, w_mean, x_mean, module2inspect, linears2scale: List[nn.Linear], fp16_output, kwargs: Dict = {},
+                            ratios=None):
+        """L(s) = || Q(W * s) (s^-1 * X) - W * X ||; returns best_scales [K] on the device.
+        `ratios` restricts the grid (ratio-sharded search, dist.py); the loss vector is kept in `self.last_losses`."""
+        n_grid = 20
+        ratios = list(range(n_grid)) if ratios is None else list(ratios)
+        x_mean, w_mean = x_mean.view(-1), w_mean.view(-1)
+        org = [fc.weight.data for fc in linears2scale]
+        scratch = [torch.empty_like(w) for w in org]
+        losses = torch.full((n_grid,), float("inf"), dtype=torch.float64, device=x.device)
+        cand = {}
+        g = self.group_size
+        try:
+            for i in ratios:
+                scales = self._ratio_scales(x_mean, w_mean, i / n_grid)
+                cand[i] = scales
+                s_w = scales.to(org[0].dtype)
+                for fc, w, buf in zip(linears2scale, org, scratch):
+                    # Q(W * s) / s in one kernel (quantizer.py:727-730)
+                    ops.quant_group(w, g, 4, zero_point=self.zero_point, pre_mul=s_w, post_div=s_w, want_scales=False, out=buf)
+                    fc.weight.data = buf
+                int_w_output = self._module_forward(x, module2inspect, kwargs)
+                losses[i] = ops.sqdiff_sum(fp16_output, int_w_output) / fp16_output.numel()   # quantizer.py:754-783
+        finally:
+            for fc, w in zip(linears2scale, org):
+                fc.weight.data = w
+        losses = torch.where(torch.isnan(losses), torch.full_like(losses, float("inf")), losses)
+        self.last_losses = losses
+        best = int(torch.argmin(losses).item())   # first minimum == the reference's strict `<` (quantizer.py:739)
+        if not torch.isfinite(losses[best]) or best not in cand:
+            logging.debug(losses.tolist())
+            raise Exception
+        best_scales = cand[best]
+        assert torch.isnan(best_scales).sum() == 0, best_scales
+        self.last_best_ratio = best / n_grid
+        return best_scales.detach()
+
+    @torch.no_grad()
+    def _compute_loss(self, fp16_output, int_w_output, device=None):
+        """quantizer.py:754-783 -> python float."""
+        return (ops.sqdiff_sum(fp16_output, int_w_output) / fp16_output.numel()).item()
+
+    # ------------------------------------------------------------------ quantizer.py:786-863
+    @torch.no_grad()
+    def _search_best_clip(self, layer, named_linears, input_feat):
+        clip_list = []
+        avoid_clipping = ["q_", "k_", "query", "key", "Wqkv", "to_q", "to_k", "add_q_proj", "add_k_proj"]
+        for name in named_linears:
+            if any(a in name for a in avoid_clipping):   # inputs of the QK^T bmm are hard to clip precisely
+                continue
+            if name not in input_feat:
+                continue
+            clip_list.append((name, self._compute_best_clip(named_linears[name].weight, input_feat[name])))
+        return clip_list
+
+    @torch.no_grad()
+    def _compute_best_clip(self, w: torch.Tensor, input_feat: torch.Tensor, n_grid=20, max_shrink=0.5, n_sample_token=512):
+        """quantizer.py:805-863.  The per-group dot products sum_g x*w are one batched GEMM per out-row batch
+        ([G] x [co_b, g] x [g, n_tok]) instead of a co_b x n_tok x K broadcast product; Q(clamp(w)) is the fused
+        quantise kernel with `clip_max`.  The reference rounds every x*w product to fp16 before summing; the GEMM
+        keeps fp32 products, so err values agree to ~1e-3 relative and best_max can differ on near-ties."""
+        assert w.dim() == 2
+        co, ci = w.shape
+        gs = self.group_size if self.group_size > 0 else ci
+        G = ci // gs
+        x = input_feat.view(-1, input_feat.shape[-1])
+        x = x[:: max(1, x.shape[0] // n_sample_token)]
+        xg = x.reshape(-1, G, gs).permute(1, 2, 0).contiguous().float()      # [G, g, n_tok]
+        oc_batch = 256 if co % 256 == 0 else 64
+        assert co % oc_batch == 0
+        best_all = []
+        for b in range(co // oc_batch):
+            wb = w[b * oc_batch:(b + 1) * oc_batch].contiguous()             # [co_b, ci]
+            org_max = ops.rowabsmax(wb.reshape(-1, gs)).reshape(oc_batch, G)  # exact
+            best_max = org_max.clone()
+            min_errs = torch.full((oc_batch, G), 1e9, dtype=torch.float32, device=w.device)
+            org_out = torch.bmm(wb.reshape(oc_batch, G, gs).permute(1, 0, 2).float(), xg)   # [G, co_b, n_tok]
+            for i_s in range(int(max_shrink * n_grid)):
+                max_val = org_max * (1 - i_s / n_grid)
+                q_w = ops.quant_group(wb, gs, 4, zero_point=self.zero_point, clip_max=max_val.reshape(-1), want_scales=False)[0]
+                cur_out = torch.bmm(q_w.reshape(oc_batch, G, gs).permute(1, 0, 2).float(), xg)
+                err = (cur_out - org_out).pow(2).mean(dim=2).t()             # [co_b, G]
+                better = err < min_errs
+                min_errs[better] = err[better]
+                best_max[better] = max_val[better]
+            best_all.append(best_max)
+        return torch.cat(best_all, dim=0).unsqueeze(-1)                      # [co, G, 1]

@@ -22,6 +22,24 @@ class AdaLNShift:
         self.linear, self.rows_shift, self.rows_scale = linear, rows_shift, rows_scale
 
 
+def describe_prev_op(module, prev_op):
+    """name of a prev_op relative to `module`; AdaLN targets become a picklable tuple so that search results
+    can be gathered across ranks: ("adaln", linear_name, (shift rows), (scale rows))."""
+    from .module import get_op_name
+    if isinstance(prev_op, AdaLNShift):
+        return ("adaln", get_op_name(module, prev_op.linear), (prev_op.rows_shift.start, prev_op.rows_shift.stop),
+                (prev_op.rows_scale.start, prev_op.rows_scale.stop))
+    return get_op_name(module, prev_op) if isinstance(prev_op, nn.Module) else prev_op
+
+
+def resolve_prev_op(module, desc):
+    if isinstance(desc, str):
+        return get_op_by_name(module, desc)
+    if isinstance(desc, (tuple, list)) and len(desc) == 4 and desc[0] == "adaln":
+        return AdaLNShift(get_op_by_name(module, desc[1]), slice(*desc[2]), slice(*desc[3]))
+    return desc
+
+
 @torch.no_grad()
 def apply_clip(module, clip_list: Tuple[str, torch.Tensor]):
     """scale.py:25-34."""
@@ -36,7 +54,7 @@ def apply_clip(module, clip_list: Tuple[str, torch.Tensor]):
 def apply_scale(module, scales_list, input_feat_dict=None):
     """scale.py:37-84."""
     for prev_op_name, layer_names, scales in scales_list:
-        prev_op = get_op_by_name(module, prev_op_name) if isinstance(prev_op_name, str) else prev_op_name
+        prev_op = resolve_prev_op(module, prev_op_name)
         layers = [get_op_by_name(module, name) for name in layer_names]
         scales = scales.to(layers[0].weight.device)
         if isinstance(prev_op, AdaLNShift):

@@ -1,0 +1,431 @@
+"""Synthetic model skeletons (plain torch, random init) with the module NAMES and Linear/Conv SHAPES of the
+diffusers models the reference quantizes: SD1.5 / SDXL `UNet2DConditionModel` and the SD3.5-Large MMDiT
+(`SD3Transformer2DModel`).  `diffusers` is not installed here and there is no network for checkpoints, so
+these stand in for the real pipelines in calibration, parity and throughput runs (SURVEY.md section 7.7,
+Appendix A).  The reference's name-based logic (`attn1.to_q`, `ff.net.0.proj`, ...,
+models/StableDiffusion1_x.py:115-150) sees the same names.  Only the quantized-linear path is the product;
+attention, norms, convolutions and the sampler loop are library torch ops.
+"""
+import hashlib
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------ transformer pieces
+class Attention(nn.Module):
+    def __init__(self, dim, heads, ctx_dim=None, out_bias=True):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_v = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim, bias=out_bias), nn.Dropout(0.0)])
+
+    def forward(self, x, context=None):
+        c = x if context is None else context
+        b, t, d = x.shape
+        h = self.heads
+        q = self.to_q(x).view(b, t, h, d // h).transpose(1, 2)
+        k = self.to_k(c).view(b, c.shape[1], h, d // h).transpose(1, 2)
+        v = self.to_v(c).view(b, c.shape[1], h, d // h).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, t, d)
+        return self.to_out[1](self.to_out[0](o))
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        h, gate = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+
+class GELUProj(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out)
+
+    def forward(self, x):
+        return F.gelu(self.proj(x), approximate="tanh")
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, mult=4, geglu=True):
+        super().__init__()
+        act = GEGLU(dim, dim * mult) if geglu else GELUProj(dim, dim * mult)
+        self.net = nn.ModuleList([act, nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class BasicTransformerBlock(nn.Module):
+    """diffusers BasicTransformerBlock: norm1 -> attn1 (self), norm2 -> attn2 (cross), norm3 -> ff (GEGLU)."""
+
+    def __init__(self, dim, heads, ctx_dim):
+        super().__init__()
+        self.norm1, self.attn1 = nn.LayerNorm(dim), Attention(dim, heads)
+        self.norm2, self.attn2 = nn.LayerNorm(dim), Attention(dim, heads, ctx_dim)
+        self.norm3, self.ff = nn.LayerNorm(dim), FeedForward(dim)
+
+    def forward(self, x, context):
+        x = x + self.attn1(self.norm1(x))
+        x = x + self.attn2(self.norm2(x), context)
+        return x + self.ff(self.norm3(x))
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, ch, heads, ctx_dim, depth=1, linear_proj=False):
+        super().__init__()
+        self.linear_proj = linear_proj
+        self.norm = nn.GroupNorm(32, ch, eps=1e-6)
+        self.proj_in = nn.Linear(ch, ch) if linear_proj else nn.Conv2d(ch, ch, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(ch, heads, ctx_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(ch, ch) if linear_proj else nn.Conv2d(ch, ch, 1)
+
+    def forward(self, x, context):
+        b, c, h, w = x.shape
+        res = x
+        x = self.norm(x)
+        if self.linear_proj:
+            x = self.proj_in(x.permute(0, 2, 3, 1).reshape(b, h * w, c))
+        else:
+            x = self.proj_in(x).permute(0, 2, 3, 1).reshape(b, h * w, c)
+        for blk in self.transformer_blocks:
+            x = blk(x, context)
+        if self.linear_proj:
+            x = self.proj_out(x).reshape(b, h, w, c).permute(0, 3, 1, 2)
+        else:
+            x = self.proj_out(x.reshape(b, h, w, c).permute(0, 3, 1, 2))
+        return x + res
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, cin, cout, temb=1280):
+        super().__init__()
+        self.norm1, self.conv1 = nn.GroupNorm(32, cin, eps=1e-5), nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2, self.conv2 = nn.GroupNorm(32, cout, eps=1e-5), nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x, temb):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        h = self.conv2(F.silu(self.norm2(h)))
+        return h + (x if self.conv_shortcut is None else self.conv_shortcut(x))
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1, self.linear_2 = nn.Linear(cin, dim), nn.Linear(dim, dim)
+
+    def forward(self, x):
+        return self.linear_2(F.silu(self.linear_1(x)))
+
+
+def sinusoidal(t, dim, dtype):
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, device=t.device, dtype=torch.float32) / half)
+    a = t.float()[:, None] * freqs[None]
+    return torch.cat([a.cos(), a.sin()], dim=-1).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------ UNets
+class _Stage(nn.Module):
+    def __init__(self, resnets, attentions, sampler=None, up=False):
+        super().__init__()
+        self.resnets = nn.ModuleList(resnets)
+        self.attentions = nn.ModuleList(attentions) if attentions else None
+        if sampler is not None:
+            if up:
+                self.upsamplers = nn.ModuleList([sampler])
+            else:
+                self.downsamplers = nn.ModuleList([sampler])
+
+
+class _Sampler(nn.Module):
+    def __init__(self, ch, down):
+        super().__init__()
+        self.down = down
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2 if down else 1, padding=1)
+
+    def forward(self, x):
+        if not self.down:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+        return self.conv(x)
+
+
+class UNet2DConditionSkeleton(nn.Module):
+    """UNet2DConditionModel topology.  SD1.5: channels (320,640,1280,1280), 1 transformer layer per attention,
+    conv proj_in/out, ctx 768.  SDXL: channels (320,640,1280), transformer depth (0,2,10), linear proj_in/out,
+    ctx 2048, add_embedding."""
+
+    def __init__(self, channels=(320, 640, 1280, 1280), depth=(1, 1, 1, 0), ctx_dim=768, head_dim=None, heads=8,
+                 linear_proj=False, add_embed_in=None, in_ch=4, layers_per_block=2):
+        super().__init__()
+        temb = channels[0] * 4
+        self.channels = channels
+        self.conv_in = nn.Conv2d(in_ch, channels[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(channels[0], temb)
+        self.add_embedding = TimestepEmbedding(add_embed_in, temb) if add_embed_in else None
+        nh = lambda c: (c // head_dim) if head_dim else heads
+        mk_attn = lambda c, d: Transformer2DModel(c, nh(c), ctx_dim, d, linear_proj)
+        self.down_blocks = nn.ModuleList()
+        skip, cin = [channels[0]], channels[0]
+        for i, c in enumerate(channels):
+            res, att = [], []
+            for _ in range(layers_per_block):
+                res.append(ResnetBlock2D(cin, c, temb))
+                if depth[i]:
+                    att.append(mk_attn(c, depth[i]))
+                cin = c
+                skip.append(c)
+            last = i == len(channels) - 1
+            self.down_blocks.append(_Stage(res, att, None if last else _Sampler(c, True)))
+            if not last:
+                skip.append(c)
+        cm = channels[-1]
+        dm = max(depth) if linear_proj else 1
+        self.mid_block = _Stage([ResnetBlock2D(cm, cm, temb), ResnetBlock2D(cm, cm, temb)], [mk_attn(cm, dm)])
+        self.up_blocks = nn.ModuleList()
+        for i, c in reversed(list(enumerate(channels))):
+            res, att = [], []
+            for _ in range(layers_per_block + 1):
+                res.append(ResnetBlock2D(cin + skip.pop(), c, temb))
+                if depth[i]:
+                    att.append(mk_attn(c, depth[i]))
+                cin = c
+            self.up_blocks.append(_Stage(res, att, None if i == 0 else _Sampler(c, False), up=True))
+        self.conv_norm_out = nn.GroupNorm(32, channels[0], eps=1e-5)
+        self.conv_out = nn.Conv2d(channels[0], in_ch, 3, padding=1)
+
+    def forward(self, x, t, context, added=None):
+        temb = self.time_embedding(sinusoidal(t, self.channels[0], x.dtype))
+        if self.add_embedding is not None and added is not None:
+            temb = temb + self.add_embedding(added)
+        h = self.conv_in(x)
+        skips = [h]
+        for blk in self.down_blocks:
+            for j, r in enumerate(blk.resnets):
+                h = r(h, temb)
+                if blk.attentions is not None:
+                    h = blk.attentions[j](h, context)
+                skips.append(h)
+            if hasattr(blk, "downsamplers"):
+                h = blk.downsamplers[0](h)
+                skips.append(h)
+        h = self.mid_block.resnets[0](h, temb)
+        h = self.mid_block.attentions[0](h, context)
+        h = self.mid_block.resnets[1](h, temb)
+        for blk in self.up_blocks:
+            for j, r in enumerate(blk.resnets):
+                h = r(torch.cat([h, skips.pop()], dim=1), temb)
+                if blk.attentions is not None:
+                    h = blk.attentions[j](h, context)
+            if hasattr(blk, "upsamplers"):
+                h = blk.upsamplers[0](h)
+        return self.conv_out(F.silu(self.conv_norm_out(h)))
+
+
+def sd15_unet():
+    return UNet2DConditionSkeleton((320, 640, 1280, 1280), (1, 1, 1, 0), ctx_dim=768, heads=8)
+
+
+def sdxl_unet():
+    return UNet2DConditionSkeleton((320, 640, 1280), (0, 2, 10), ctx_dim=2048, head_dim=64, linear_proj=True,
+                                   add_embed_in=2816)
+
+
+# ------------------------------------------------------------------------------------------ SD3.5 MMDiT
+class AdaLayerNormZero(nn.Module):
+    def __init__(self, dim, n=6):
+        super().__init__()
+        self.linear = nn.Linear(dim, n * dim)
+        self.norm = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.n = n
+
+    def forward(self, x, emb):
+        parts = self.linear(F.silu(emb)).chunk(self.n, dim=1)
+        shift, scale = parts[0], parts[1]
+        return self.norm(x) * (1 + scale[:, None]) + shift[:, None], parts[2:]
+
+
+class JointAttention(nn.Module):
+    def __init__(self, dim, heads, context_pre_only):
+        super().__init__()
+        self.heads = heads
+        self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.add_q_proj, self.add_k_proj, self.add_v_proj = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+        self.to_add_out = None if context_pre_only else nn.Linear(dim, dim)
+
+    def forward(self, x, c):
+        b, t, d = x.shape
+        h = self.heads
+        sp = lambda y: y.view(b, -1, h, d // h).transpose(1, 2)
+        q = torch.cat([sp(self.to_q(x)), sp(self.add_q_proj(c))], dim=2)
+        k = torch.cat([sp(self.to_k(x)), sp(self.add_k_proj(c))], dim=2)
+        v = torch.cat([sp(self.to_v(x)), sp(self.add_v_proj(c))], dim=2)
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, -1, d)
+        xo, co = o[:, :t], o[:, t:]
+        return self.to_out[0](xo), (self.to_add_out(co) if self.to_add_out is not None else None)
+
+
+class JointTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, context_pre_only=False):
+        super().__init__()
+        self.context_pre_only = context_pre_only
+        self.norm1 = AdaLayerNormZero(dim, 6)
+        self.norm1_context = AdaLayerNormZero(dim, 2 if context_pre_only else 6)
+        self.attn = JointAttention(dim, heads, context_pre_only)
+        self.norm2 = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.ff = FeedForward(dim, 4, geglu=False)
+        if not context_pre_only:
+            self.norm2_context = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+            self.ff_context = FeedForward(dim, 4, geglu=False)
+
+    def forward(self, x, c, emb):
+        xn, (gate_msa, shift_mlp, scale_mlp, gate_mlp) = self.norm1(x, emb)
+        cn, cparts = self.norm1_context(c, emb)
+        xo, co = self.attn(xn, cn)
+        x = x + gate_msa[:, None] * xo
+        x = x + gate_mlp[:, None] * self.ff(self.norm2(x) * (1 + scale_mlp[:, None]) + shift_mlp[:, None])
+        if not self.context_pre_only:
+            c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = cparts
+            c = c + c_gate_msa[:, None] * co
+            c = c + c_gate_mlp[:, None] * self.ff_context(self.norm2_context(c) * (1 + c_scale_mlp[:, None]) + c_shift_mlp[:, None])
+        return x, c
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, in_ch, dim, patch):
+        super().__init__()
+        self.proj = nn.Conv2d(in_ch, dim, patch, stride=patch)
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)
+
+
+class _TimeTextEmbed(nn.Module):
+    def __init__(self, dim, pooled):
+        super().__init__()
+        self.timestep_embedder = TimestepEmbedding(256, dim)
+        self.text_embedder = TimestepEmbedding(pooled, dim)
+
+    def forward(self, t, pooled):
+        return self.timestep_embedder(sinusoidal(t, 256, pooled.dtype)) + self.text_embedder(pooled)
+
+
+class MMDiTSkeleton(nn.Module):
+    """SD3Transformer2DModel topology; SD3.5-Large: 38 blocks, D = 2432 (38 heads x 64), FF 9728, patch 2,
+    16 latent channels, joint_attention_dim 4096, pooled 2048."""
+
+    def __init__(self, layers=38, dim=2432, heads=38, in_ch=16, patch=2, ctx_in=4096, pooled=2048):
+        super().__init__()
+        self.patch, self.in_ch, self.dim = patch, in_ch, dim
+        self.pos_embed = _PatchEmbed(in_ch, dim, patch)
+        self.time_text_embed = _TimeTextEmbed(dim, pooled)
+        self.context_embedder = nn.Linear(ctx_in, dim)
+        self.transformer_blocks = nn.ModuleList(
+            [JointTransformerBlock(dim, heads, context_pre_only=(i == layers - 1)) for i in range(layers)])
+        self.norm_out = AdaLayerNormZero(dim, 2)
+        self.proj_out = nn.Linear(dim, patch * patch * in_ch)
+
+    def forward(self, x, t, context, pooled):
+        b, c, hh, ww = x.shape
+        emb = self.time_text_embed(t, pooled)
+        h = self.pos_embed(x)
+        ctx = self.context_embedder(context)
+        for blk in self.transformer_blocks:
+            h, ctx = blk(h, ctx, emb)
+        h, _ = self.norm_out(h, emb)
+        h = self.proj_out(h)
+        p = self.patch
+        h = h.view(b, hh // p, ww // p, p, p, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, hh, ww)
+        return h
+
+
+def sd35_large_mmdit(layers=38):
+    return MMDiTSkeleton(layers=layers)
+
+
+# ------------------------------------------------------------------------------------------ pipeline
+def _prompt_tensor(prompt, shape, device, dtype):
+    """deterministic synthetic embedding of a prompt string (no text encoder / tokenizer offline)"""
+    seed = int.from_bytes(hashlib.sha256(str(prompt).encode()).digest()[:8], "little") % (2 ** 63)
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g).to(device=device, dtype=dtype)
+
+
+class SkeletonPipeline:
+    """Stands in for the diffusers pipeline object the reference drives (`self.pipeline(prompt, latents=..,
+    num_inference_steps=50, guidance_scale=7.5)`, models/base.py:848, utils/calib_data.py:239-244):
+    classifier-free guidance doubles the batch; an Euler-style update walks `num_inference_steps` timesteps
+    from 999 to 0.  Returns the final latents (there is no VAE here)."""
+
+    def __init__(self, kind, denoiser, device="cuda", dtype=torch.float16, latent_size=None):
+        self.kind = kind
+        self.device, self.dtype = torch.device(device), dtype
+        denoiser.to(device=self.device, dtype=dtype).eval()
+        if kind == "sd3":
+            self.transformer, self.unet = denoiser, None
+            self.latent_channels, self.latent_size = 16, latent_size or 128
+            self.ctx_shape, self.pooled_dim = (333, 4096), 2048
+        else:
+            self.unet, self.transformer = denoiser, None
+            self.latent_channels = 4
+            self.latent_size = latent_size or (128 if kind == "sdxl" else 64)
+            self.ctx_shape = (77, 2048 if kind == "sdxl" else 768)
+            self.pooled_dim = 2816 if kind == "sdxl" else None
+
+    def to(self, *a, **k):
+        return self
+
+    def encode(self, prompts):
+        ctx = torch.stack([_prompt_tensor(p, self.ctx_shape, self.device, self.dtype) for p in prompts])
+        pooled = None
+        if self.pooled_dim:
+            pooled = torch.stack([_prompt_tensor(("pooled", p), (self.pooled_dim,), self.device, self.dtype) for p in prompts])
+        return ctx, pooled
+
+    @torch.no_grad()
+    def denoise(self, x, t, ctx, pooled):
+        if self.kind == "sd3":
+            return self.transformer(x, t, ctx, pooled)
+        return self.unet(x, t, ctx, pooled)
+
+    @torch.no_grad()
+    def __call__(self, prompt, latents=None, num_inference_steps=50, guidance_scale=7.5, callback_on_step_end=None,
+                 num_images_per_prompt=1, generator=None, output_type="latent", **_):
+        prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        b = len(prompts)
+        if latents is None:
+            latents = torch.randn((b, self.latent_channels, self.latent_size, self.latent_size), generator=generator,
+                                  dtype=torch.float32).to(self.device, self.dtype)
+        x = latents.to(self.device, self.dtype)
+        ctx, pooled = self.encode(prompts)
+        do_cfg = guidance_scale is not None and guidance_scale > 1.0
+        if do_cfg:
+            uctx, upooled = self.encode([""] * b)
+            ctx = torch.cat([uctx, ctx])
+            pooled = torch.cat([upooled, pooled]) if pooled is not None else None
+        ts = torch.linspace(999, 0, num_inference_steps, device=self.device)
+        dt = 1.0 / num_inference_steps
+        for i, t in enumerate(ts):
+            xin = torch.cat([x, x]) if do_cfg else x
+            eps = self.denoise(xin, t.expand(xin.shape[0]), ctx, pooled)
+            if do_cfg:
+                eu, ec = eps.chunk(2)
+                eps = eu + guidance_scale * (ec - eu)
+            x = (x.float() - dt * eps.float()).to(self.dtype)
+            if callback_on_step_end is not None:
+                callback_on_step_end(self, i, t, {"latents": x})
+        return x

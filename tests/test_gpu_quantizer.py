@@ -1,0 +1,203 @@
+"""GPU parity of the host-side quantizer mirror (AwqQuantizer / SqQuantizer / scale) against the
+reference-generated golden fixtures and the CPU oracle."""
+import importlib
+import types
+
+import pytest
+import torch
+
+from _util import DT, Golden, assert_bit_equal, max_rel_err
+
+import oracle.qdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PKG = "quantization---diffusion-models_b200"
+
+
+class Cat(torch.nn.Module):
+    def __init__(self, ls):
+        super().__init__()
+        self.ls = torch.nn.ModuleList(ls)
+
+    def forward(self, x):
+        return torch.cat([l(x) for l in self.ls], dim=-1)
+
+
+def make_quantizer(group, zp):
+    Q = importlib.import_module(PKG + ".quantizer").AwqQuantizer
+    return Q(None, group_size=group, zero_point=zp)
+
+
+def test_pseudo_quantize_tensor_method(qdm):
+    g = Golden("pseudo_quantize_tensor.npz")
+    for tag, dt, group, zp, bits in g.cases()[:12]:
+        q = make_quantizer(int(group), bool(int(zp)))
+        w, s, z = q.pseudo_quantize_tensor(g.get(tag + "_w").to(DEV), bitWidth=int(bits))
+        assert_bit_equal(w, g.get(tag + "_dq"), tag)
+        assert_bit_equal(s, g.get(tag + "_s"), tag)
+        if int(zp):
+            assert_bit_equal(z, g.get(tag + "_z"), tag)
+        else:
+            assert z is None
+
+
+def test_search_best_scale_and_clip_vs_reference(qdm):
+    """_search_best_scale / _compute_best_scale / _compute_best_clip on the toy LN -> q,k,v group the golden
+    fixture was generated from (reference run on CPU)."""
+    g = Golden("awq_search.npz")
+    for tag, dt, group, zp in g.cases():
+        x = g.get(tag + "_x").to(DEV)
+        lins = []
+        for i in range(3):
+            w, b = g.get(f"{tag}_w{i}"), g.get(f"{tag}_b{i}")
+            l = torch.nn.Linear(w.shape[1], w.shape[0], bias=True)
+            l.weight.data, l.bias.data = w.clone(), b.clone()
+            lins.append(l.to(DEV))
+        block = Cat(lins)
+        q = make_quantizer(int(group), bool(int(zp)))
+        w_before = [l.weight.data.clone() for l in lins]
+        prev, names, best = q._search_best_scale(block, lins[0], lins, x, module2inspect=block, kwargs={})
+        assert names == ("ls.0", "ls.1", "ls.2") and prev == "ls.0"
+        for l, wb in zip(lins, w_before):
+            assert torch.equal(l.weight.data, wb)           # originals untouched
+        want = g.get(tag + "_best")
+        # the 20 losses come from GEMMs with a different accumulation order than the reference's CPU run,
+        # so a near-tie may pick the neighbouring ratio: accept the reference's scales bit-exactly, or a
+        # choice whose oracle loss is within 0.5 % of the oracle's minimum
+        if not torch.equal(best.cpu(), want):
+            xs = g.get(tag + "_x")
+            ws = [g.get(f"{tag}_w{i}") for i in range(3)]
+            bs = [g.get(f"{tag}_b{i}") for i in range(3)]
+            fwd = lambda wl: torch.cat([torch.nn.functional.linear(xs, w, b) for w, b in zip(wl, bs)], dim=-1)
+            _, _, hist = O.awq_search_scale(xs, ws, fwd, int(group), bool(int(zp)))
+            assert hist[int(round(q.last_best_ratio * 20))] <= min(hist) * 1.005
+        # candidate scale vectors themselves are exact: ratio of the reference -> same vector
+        xm = (qdm.ops.colabssum(x) / (x.numel() // x.shape[-1])).to(x.dtype)
+        wm = (qdm.ops.awq_wsum(torch.cat([l.weight for l in lins]), int(group)) / (3 * 64)).to(x.dtype)
+        assert (xm.cpu() != g.get(tag + "_xmean")).float().mean() <= 0.02
+        assert (wm.cpu() != g.get(tag + "_wmean")).float().mean() <= 0.02
+        clip = q._compute_best_clip(lins[0].weight.data, x)
+        ref_clip = g.get(tag + "_clip")
+        assert clip.shape == ref_clip.shape
+        # batched-GEMM error sums vs the reference's fp16 broadcast products: same clip level for the bulk
+        agree = (clip.cpu() == ref_clip).float().mean().item()
+        assert agree >= 0.9, agree
+        assert ((clip.cpu().float() - ref_clip.float()).abs() <= 0.1 * ref_clip.float().abs() + 1e-6).all()
+
+
+def test_smooth_ln_fcs_vs_reference(qdm):
+    SQ = importlib.import_module(PKG + ".quantizer_SQ").SqQuantizer
+    cd = importlib.import_module(PKG + ".calib_data")
+    g = Golden("smoothquant.npz")
+    for tag, dt, alpha in g.cases():
+        C = g.get(tag + "_lnw").numel()
+        ln = torch.nn.LayerNorm(C)
+        ln.weight.data, ln.bias.data = g.get(tag + "_lnw").clone(), g.get(tag + "_lnb").clone()
+        ln = ln.to(DEV)
+        fcs = []
+        for i in range(3):
+            w = g.get(f"{tag}_w{i}")
+            fc = torch.nn.Linear(w.shape[1], w.shape[0], bias=False)
+            fc.weight.data = w.clone()
+            fcs.append(fc.to(DEV))
+        hook = cd.Mean_Max_Activation_Hook()
+        for c in range(3):
+            hook(None, (g.get(f"{tag}_x{c}").to(DEV),), None)
+            assert_bit_equal(hook.max_scales[c], g.get(f"{tag}_max{c}"), f"{tag} hook {c}")
+        act = torch.mean(torch.stack(list(hook.max_scales.values())), dim=0)
+        assert_bit_equal(act, g.get(tag + "_act"), f"{tag} act")
+        sq = SQ.__new__(SQ)
+        sq.smooth_ln_fcs(ln, fcs, act, alpha=float(alpha))
+        assert_bit_equal(ln.weight.data, g.get(tag + "_lnw_out"), f"{tag} ln.weight")
+        assert_bit_equal(ln.bias.data, g.get(tag + "_lnb_out"), f"{tag} ln.bias")
+        for i in range(3):
+            assert_bit_equal(fcs[i].weight.data, g.get(f"{tag}_w{i}_out"), f"{tag} fc{i}")
+
+
+def test_wxax_linear_vs_reference(qdm):
+    fq = importlib.import_module(PKG + ".fake_quant")
+    g = Golden("wxax_linear.npz")
+    for tag, dt, wq, bits, group in g.cases():
+        w, b, x = g.get(tag + "_w"), g.get(tag + "_b"), g.get(tag + "_x")
+        lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=True)
+        lin.weight.data, lin.bias.data = w.clone(), b.clone()
+        lin = lin.to(DEV)
+        m = fq.WxAxLinear.from_float(lin, weight_quant=wq, n_bits_W=int(bits), group_size_W=int(group))
+        assert_bit_equal(m.weight, g.get(tag + "_wq"), f"{tag} fake-quant weight")
+        y = m(x.to(DEV))
+        assert y.shape == g.get(tag + "_y").shape and y.dtype == x.dtype
+        assert max_rel_err(y, g.get(tag + "_y")) <= 1e-2
+    with pytest.raises(ValueError, match="Invalid weight_quant"):
+        fq.WxAxLinear.from_float(lin, weight_quant="nope")
+    with pytest.raises(ValueError, match="Invalid act_quant"):
+        fq.WxAxLinear(8, 8, act_quant="nope")
+
+
+def tiny_sd15(qdm):
+    M = importlib.import_module(PKG + ".models")
+    m = M.StableDiffusion1_x.from_skeleton(device=DEV, channels=(64, 128), depth=(1, 1), ctx_dim=64, heads=2, latent_size=16)
+    return M, m
+
+
+@pytest.mark.parametrize("version", ["fake_act", "gemm"])
+def test_quantize_awq_end_to_end(qdm, version):
+    """quantize('awq') on a small UNet skeleton: fake-quant weights equal the oracle's RTN of the original
+    weights; the real packed modules reproduce the fake-quant model's denoised latents (bf16-level tolerance)."""
+    M, model = tiny_sd15(qdm)
+    lat = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(1)).half().to(DEV)
+    orig = {n: mod.weight.data.clone().cpu() for n, mod in model.denoiser().named_modules() if isinstance(mod, torch.nn.Linear)}
+    model.quantize(quant_config={"zero_point": True, "q_group_size": 64, "w_bit": 4, "version": version}, quantType="awq")
+    den = model.denoiser()
+    kinds = {type(mod).__name__ for mod in den.modules()}
+    assert "Linear" not in kinds and "Conv2d" not in kinds
+    if version == "fake_act":
+        for n, w in orig.items():
+            got = dict(den.named_modules())[n].weight
+            assert_bit_equal(got, O.rtn_absmax_group(w, 4, 64)[0], n)
+    else:
+        assert "WQLinear_GEMM" in kinds
+        for n, w in orig.items():
+            mod = dict(den.named_modules())[n]
+            if type(mod).__name__ == "WQLinear_GEMM":
+                assert_bit_equal(mod.dequantize(), O.rtn_group(w, mod.group_size, True, 4)[0], n)
+    out = model.generate(["a", "b"], lat=lat, num_inference_steps=3)
+    assert out.shape == lat.shape and torch.isfinite(out).all()
+
+
+def test_awq_search_on_skeleton_and_sq_w8a8(qdm):
+    M, model = tiny_sd15(qdm)
+    model.calib_steps = 2
+    den = model.denoiser()
+    blk_name = next(iter(model.get_search_blocks()))
+    w0 = dict(den.named_modules())[blk_name + ".attn1.to_q"].weight.data.clone()
+    n1 = dict(den.named_modules())[blk_name + ".norm1"].weight.data.clone()
+    model.quantize(quant_config={"zero_point": True, "q_group_size": 64, "w_bit": 4, "version": "gemm"}, quantType="awq",
+                   calibrate=True)
+    log = model.quantizer.search_log
+    assert len(log) == 3 * len(model.get_search_blocks())          # 3 scaling groups per block
+    assert all(0.0 <= r < 1.0 for _, r, _ in log)
+    n1_after = dict(den.named_modules())[blk_name + ".norm1"].weight.data
+    assert not torch.equal(n1_after, n1) or all(r == 0.0 for _, r, _ in log)
+    lat = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(1)).half().to(DEV)
+    assert torch.isfinite(model.generate(["a", "b"], lat=lat, num_inference_steps=2)).all()
+    # SmoothQuant + real W8A8 modules
+    M2, model2 = tiny_sd15(qdm)
+    fp = model2.generate(["a", "b"], lat=lat, num_inference_steps=2).float()
+    model2.calib_samples = model2.default_calib_samples(1, 2)
+    model2.quantize(quant_config={"w_bit": 8, "version": "w8a8"}, quantType="sq", alpha=0.5, calib_num_infer_steps=2)
+    assert any(type(m).__name__ == "W8A8Linear" for m in model2.denoiser().modules())
+    q8 = model2.generate(["a", "b"], lat=lat, num_inference_steps=2).float()
+    assert torch.isfinite(q8).all()
+    assert ((q8 - fp).abs().max() / fp.abs().max()).item() < 0.1   # W8A8 stays close to the fp16 model
+
+
+def test_save_and_load_packed(qdm, tmp_path):
+    M, model = tiny_sd15(qdm)
+    model.quantize(quant_config={"q_group_size": 64, "w_bit": 4, "version": "gemm"}, quantType="awq")
+    lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(3)).half().to(DEV)
+    a = model.generate(["p"], lat=lat, num_inference_steps=2)
+    model.save_quantized(str(tmp_path))
+    again = M.StableDiffusion1_x.from_quantized(str(tmp_path), device=DEV)
+    b = again.generate(["p"], lat=lat, num_inference_steps=2)
+    assert torch.equal(a, b)

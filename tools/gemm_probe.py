@@ -19,6 +19,8 @@ CASES = [
     ("w4", "f16", 128, 128, 128, 128), ("w4", "f16", 128, 256, 256, 64), ("w4", "bf16", 300, 320, 320, 64),
     ("w4", "f16", 1024, 2432, 2432, 128), ("w4", "f16", 4096, 2560, 320, 64),
     ("w8", "f16", 128, 128, 128), ("w8", "f16", 300, 320, 320), ("w8", "bf16", 1024, 1280, 1280),
+    ("f16", "f16", 4096, 1280, 1280), ("w4", "f16", 8192, 1280, 1280, 128), ("w4", "bf16", 4096, 640, 2560, 128),
+    ("w8", "f16", 8192, 5120, 640), ("w4", "f16", 257, 256, 128, 128), ("w4", "f16", 65536, 320, 320, 64),
 ]
 
 
@@ -27,6 +29,7 @@ def run_one(kind, dt, M, N, K, group=128):
     q = importlib.import_module("quantization---diffusion-models_b200")
     dtype = {"f16": torch.float16, "bf16": torch.bfloat16}[dt]
     dev = "cuda:0"
+    q.ops.set_gemm_mode(int(os.environ.get("QDM_GEMM_MODE", "0")))
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(dtype).to(dev)
     w = (torch.randn(N, K, generator=g) * 0.05).to(dtype).to(dev)
