@@ -76,6 +76,9 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library is stale
         fn.restype = res
         fn.argtypes = args
+    mode = os.environ.get("QDM_GEMM_MODE")   # bring-up / A-B timing switch, see qdm_set_gemm_mode
+    if mode:
+        lib.qdm_set_gemm_mode(int(mode))
     _lib = lib
     return lib
 

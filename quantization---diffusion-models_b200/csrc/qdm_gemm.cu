@@ -130,24 +130,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive(cta_id) does.
+// A .release.cluster arrive compiles to MEMBAR.ALL.GPU and an .acquire.cluster wait to CCTL.IVALL; measured: they
+// halve the throughput of the CTA-pair kernel.  What is published here is shared memory of the ARRIVING CTA, already
+// made visible to its own async proxy by fence.proxy.async (or TMEM reads completed by tcgen05.wait::ld), and it is
+// consumed by that same SM's tensor core / by the leader's next tcgen05.mma, so CTA scope is sufficient.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, polls = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++polls == 4096) t0 = clock64();
-    if (polls > 4096 && (polls & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();
-  }
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // CTA-pair TMA load: data lands in THIS CTA's shared memory, completion bytes are counted on `bar`, a
 // shared::cluster address (the leader CTA's full barrier)
@@ -222,7 +211,7 @@ struct Cfg {
   static constexpr int THREADS = (KIND == G_W4) ? 512 : 256;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int K_PER_BLOCK = (KIND == G_I8) ? 128 : 64;   // elements per k-block (128 bytes)
-  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS : 1;
+  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS / 2 : 1;   // TMA + one producer group
 };
 
 template <int KIND, bool BF16>
@@ -317,50 +306,73 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg
   }
 }
 
-// int4 dequant producers: 256 threads fill the MN-major SW128 B tile of NLOC columns for every (tile, k-block).
-// Thread -> one packed word column `wc` (8 output columns) and k rows kr, kr+RPP, ...  Global loads run two
-// k-blocks ahead of the shared-memory writes and do not stop at tile boundaries (the prefetch cursor walks the
-// same (tile, kb) sequence as every other role).  `tile_n` is the tile extent in N, `col_off` this CTA's column
-// offset inside the tile (0, or rank * NLOC in a CTA pair).  full barriers live at full_addr + 8*stage (a
-// shared::cluster address when CLUSTER), empty barriers at empty_addr + 8*stage (always local).
+// int4 dequant producers.  The 8 producer warps form two groups of 128 threads that take alternate k-blocks
+// (group g fills pipeline iterations g, g+2, ...): the per-k-block overhead of a warp (cursor arithmetic,
+// barrier wait, proxy fence, arrive) is paid half as often and each warp has two MMA periods to hide the
+// latency of its dependent instruction chain.  A thread owns one packed word column `wc` (8 output columns) and
+// the k rows kr, kr+RPP, ... of the 64-row k-block, and writes the MN-major SW128 B tile of NLOC columns.
+// Global loads run DIST of the group's k-blocks ahead of the shared-memory writes and do not stop at tile
+// boundaries (the prefetch cursor walks the same (tile, kb) sequence as every other role).  `tile_n` is the tile
+// extent in N, `col_off` this CTA's column offset inside the tile (0, or rank * NLOC in a CTA pair).  full
+// barriers live at full_addr + 8*stage (a shared::cluster address when CLUSTER), empty barriers at
+// empty_addr + 8*stage (always local).
+constexpr int DQ_GROUPS = 2;
+constexpr int DQ_GROUP_THREADS = 32 * NUM_DQ_WARPS / DQ_GROUPS;   // 128
+
 template <int NLOC, bool BF16, int STAGES, int STAGE_BYTES, bool CLUSTER>
 __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, int lane, int first_tile, int tile_stride,
                                                  int num_tiles, int m_tiles, int num_kb, int tile_n, int col_off,
                                                  uint32_t b_stage0, uint32_t empty_addr, uint32_t full_addr) {
-  constexpr int WPR = NLOC / 8;               // packed words per k row of this CTA's tile part
-  constexpr int RPP = 256 / WPR;              // k rows covered by the 256 dequant threads at once (multiple of 8)
+  constexpr int WPR = NLOC / 8;                  // packed words per k row of this CTA's tile part
+  constexpr int RPP = DQ_GROUP_THREADS / WPR;    // k rows covered by one pass of the group
   constexpr int PASSES = 64 / RPP;
-  constexpr int DIST = 2;                     // prefetch distance in k-blocks
-  static_assert(RPP % 8 == 0 && PASSES >= 1, "tile part too narrow for 256 dequant threads");
-  const int wc = dt % WPR, kr = dt / WPR;
+  constexpr int DIST = 2;                        // prefetch distance, in k-blocks of this group
+  static_assert(RPP >= 1 && PASSES >= 1 && 64 % RPP == 0, "bad producer tiling");
+  const int grp = dt / DQ_GROUP_THREADS, tg = dt % DQ_GROUP_THREADS;
+  const int wc = tg % WPR, kr = tg / WPR;
   const int words_per_row = p.N / 8;
-  // MN-major SW128 tile: 64-column chunk (wc>>3), k row stride 128 B, 16-byte slot (wc&7) ^ (k&7);
-  // RPP is a multiple of 8 so the swizzle term is the same for every pass.
-  const uint32_t thr_off = uint32_t(wc >> 3) * (64 * ROW_BYTES) + uint32_t(kr) * ROW_BYTES +
-                           ((uint32_t(wc & 7) ^ uint32_t(kr & 7)) << 4);
+  const int gshift = 31 - __clz(p.group >> 6);   // group / 64 is a power of two (host-checked)
+  // MN-major SW128 tile: 64-column chunk (wc>>3), k row stride 128 B, 16-byte slot (wc&7) ^ (k&7)
+  const uint32_t chunk_off = uint32_t(wc >> 3) * (64 * ROW_BYTES);
+  auto row_off = [&](int ps) {
+    const uint32_t k = uint32_t(kr + ps * RPP);
+    return chunk_off + k * ROW_BYTES + ((uint32_t(wc & 7) ^ (k & 7)) << 4);
+  };
   struct Pf {            // one prefetched k-block of this thread
     uint32_t w[PASSES];  // packed weight words
     uint32_t zw;         // packed zero points of the group
     uint4 sv;            // 8 scales
   };
   Pf ring[DIST + 1];
-  int pf_tile = first_tile, pf_kb = 0;  // prefetch cursor
+  // prefetch cursor of this group: k-block `pf_kb` of tile `pf_tile`, word column pf_wcol
+  int pf_tile = first_tile, pf_kb = grp, pf_wcol = 0;
+  bool pf_valid = false;
+  auto enter_tile = [&]() {
+    pf_wcol = ((pf_tile / m_tiles) * tile_n + col_off) / 8 + wc;
+    pf_valid = pf_tile < num_tiles && pf_wcol < words_per_row;
+  };
+  auto normalise = [&]() {   // carry pf_kb into pf_tile
+    bool moved = false;
+    while (pf_kb >= num_kb) { pf_kb -= num_kb; pf_tile += tile_stride; moved = true; }
+    if (moved) enter_tile();
+  };
+  enter_tile();
+  normalise();
   auto prefetch = [&](Pf& f) {
-    const int wcol = ((pf_tile / m_tiles) * tile_n + col_off) / 8 + wc;
-    const bool valid = pf_tile < num_tiles && wcol < words_per_row;
     f.zw = 0u;
     f.sv = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = 0u;
-    if (valid) {
-      const int32_t* src = p.qweight + int64_t(pf_kb * 64 + kr) * words_per_row + wcol;
+    if (pf_valid) {
+      const int32_t* src = p.qweight + int64_t(pf_kb * 64 + kr) * words_per_row + pf_wcol;
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) f.w[ps] = (uint32_t)__ldg(src + int64_t(ps * RPP) * words_per_row);
-      const int g = (pf_kb * 64) / p.group;
-      f.zw = (uint32_t)__ldg(p.qzeros + int64_t(g) * words_per_row + wcol);
-      f.sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.scales) + int64_t(g) * p.N + wcol * 8));
+      const int64_t g = pf_kb >> gshift;
+      f.zw = (uint32_t)__ldg(p.qzeros + g * words_per_row + pf_wcol);
+      f.sv = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.scales) + g * p.N + pf_wcol * 8));
     }
-    if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += tile_stride; }
+    pf_kb += DQ_GROUPS;
+    normalise();
   };
 #pragma unroll
   for (int d = 0; d < DIST; ++d) prefetch(ring[d]);
@@ -375,75 +387,84 @@ __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, in
     return d;
   };
 
-  int stage = 0;
+  int stage = grp % STAGES;
   uint32_t phase = 0;
-  for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-    for (int kb = 0; kb < num_kb; ++kb) {
-      prefetch(ring[DIST]);
-      const Pf& f = ring[0];
-      const uint32_t sp[4] = {f.sv.x, f.sv.y, f.sv.z, f.sv.w};
-      // zero-point operands of the exact (q - z) step, per nibble pair
-      uint32_t zsub[4];
+  auto process = [&](const Pf& f) {
+    const uint32_t sp[4] = {f.sv.x, f.sv.y, f.sv.z, f.sv.w};
+    // zero-point operands of the exact (q - z) step, per nibble pair
+    uint32_t zsub[4];
+    if (BF16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) zsub[q] = and_or(f.zw >> (4 * q), mask_lo, magic);        // 128 + z
+    } else {
+      const uint32_t zs = f.zw >> 8;
+      zsub[0] = and_or(f.zw, mask_lo, magic);                                                // 1024 + z
+      zsub[2] = and_or(zs, mask_lo, magic);
+      // high nibbles decode as 1024 + 16 z; (.)/16 = 64 + z exactly
+      const __half2 sixteenth = __float2half2_rn(0.0625f);
+      const uint32_t z1 = and_or(f.zw, mask_hi, magic), z3 = and_or(zs, mask_hi, magic);
+      __half2 h1 = __hmul2(*reinterpret_cast<const __half2*>(&z1), sixteenth);
+      __half2 h3 = __hmul2(*reinterpret_cast<const __half2*>(&z3), sixteenth);
+      zsub[1] = *reinterpret_cast<uint32_t*>(&h1);
+      zsub[3] = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    mbar_wait(empty_addr + 8u * stage, phase ^ 1);
+    const uint32_t b_dst = b_stage0 + stage * STAGE_BYTES;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const uint32_t w = f.w[ps];
+      uint32_t o[4];
       if (BF16) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) zsub[q] = and_or(f.zw >> (4 * q), mask_lo, magic);        // 128 + z
-      } else {
-        const uint32_t zs = f.zw >> 8;
-        zsub[0] = and_or(f.zw, mask_lo, magic);                                                // 1024 + z
-        zsub[2] = and_or(zs, mask_lo, magic);
-        // high nibbles decode as 1024 + 16 z; (.)/16 = 64 + z exactly
-        const __half2 sixteenth = __float2half2_rn(0.0625f);
-        const uint32_t z1 = and_or(f.zw, mask_hi, magic), z3 = and_or(zs, mask_hi, magic);
-        __half2 h1 = __hmul2(*reinterpret_cast<const __half2*>(&z1), sixteenth);
-        __half2 h3 = __hmul2(*reinterpret_cast<const __half2*>(&z3), sixteenth);
-        zsub[1] = *reinterpret_cast<uint32_t*>(&h1);
-        zsub[3] = *reinterpret_cast<uint32_t*>(&h3);
-      }
-      mbar_wait(empty_addr + 8u * stage, phase ^ 1);
-      const uint32_t b_dst = b_stage0 + stage * STAGE_BYTES + thr_off;
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const uint32_t w = f.w[ps];
-        uint32_t o[4];
-        if (BF16) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t t = and_or(w >> (4 * q), mask_lo, magic);  // {128 + q(col 2q), 128 + q(col 2q+1)}
-            __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zsub[q]));
-            d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&sp[q]));
-            o[q] = *reinterpret_cast<uint32_t*>(&d);
-          }
-        } else {
-          const uint32_t ws = w >> 8;
-          const __half2 sixteenth = __float2half2_rn(0.0625f);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t src = (q < 2) ? w : ws;
-            __half2 d;
-            if ((q & 1) == 0) {   // low nibble of each byte: 1024 + q, exact subtract
-              const uint32_t t = and_or(src, mask_lo, magic);
-              d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zsub[q]));
-            } else {              // high nibble: 1024 + 16 q; fma(., 1/16, -(64 + z)) = q - z exactly
-              const uint32_t t = and_or(src, mask_hi, magic);
-              d = __hfma2(*reinterpret_cast<const __half2*>(&t), sixteenth, __hneg2(*reinterpret_cast<const __half2*>(&zsub[q])));
-            }
-            d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));   // (q - z) * s, one rounding
-            o[q] = *reinterpret_cast<uint32_t*>(&d);
-          }
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t t = and_or(w >> (4 * q), mask_lo, magic);  // {128 + q(col 2q), 128 + q(col 2q+1)}
+          __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zsub[q]));
+          d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&sp[q]));
+          o[q] = *reinterpret_cast<uint32_t*>(&d);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_dst + ps * (RPP * ROW_BYTES)), "r"(o[0]), "r"(o[1]),
-                     "r"(o[2]), "r"(o[3])
-                     : "memory");
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        if (CLUSTER) mbar_arrive_cluster(full_addr + 8u * stage);
-        else mbar_arrive(full_addr + 8u * stage);
-      }
+      } else {
+        const uint32_t ws = w >> 8;
+        const __half2 sixteenth = __float2half2_rn(0.0625f);
 #pragma unroll
-      for (int d = 0; d < DIST; ++d) ring[d] = ring[d + 1];
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t src = (q < 2) ? w : ws;
+          __half2 d;
+          if ((q & 1) == 0) {   // low nibble of each byte: 1024 + q, exact subtract
+            const uint32_t t = and_or(src, mask_lo, magic);
+            d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zsub[q]));
+          } else {              // high nibble: 1024 + 16 q; fma(., 1/16, -(64 + z)) = q - z exactly
+            const uint32_t t = and_or(src, mask_hi, magic);
+            d = __hfma2(*reinterpret_cast<const __half2*>(&t), sixteenth, __hneg2(*reinterpret_cast<const __half2*>(&zsub[q])));
+          }
+          d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));   // (q - z) * s, one rounding
+          o[q] = *reinterpret_cast<uint32_t*>(&d);
+        }
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_dst + row_off(ps)), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                   "r"(o[3])
+                   : "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (CLUSTER) mbar_arrive_cluster(full_addr + 8u * stage);
+      else mbar_arrive(full_addr + 8u * stage);
+    }
+    stage += DQ_GROUPS;
+    if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
+  };
+  // The ring is indexed with compile-time constants (loop unrolled by DIST + 1): rotating it with register
+  // copies would make every iteration wait for the loads it has just issued.
+  const int my_tiles = first_tile < num_tiles ? (num_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
+  const int total = my_tiles * num_kb;                       // pipeline iterations of this CTA
+  const int mine = (total - grp + DQ_GROUPS - 1) / DQ_GROUPS;  // ... of which this group fills `mine`
+  for (int it = 0; it < mine; it += DIST + 1) {
+#pragma unroll
+    for (int u = 0; u < DIST + 1; ++u) {
+      if (it + u < mine) {
+        prefetch(ring[(u + DIST) % (DIST + 1)]);
+        process(ring[u]);
+      }
     }
   }
 }
@@ -614,7 +635,8 @@ struct Cfg2 {
   static constexpr int THREADS = (KIND == G_W4) ? 512 : 256;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int K_PER_BLOCK = (KIND == G_I8) ? 128 : 64;
-  static constexpr int FULL_COUNT = (KIND == G_W4) ? 2 + 2 * NUM_DQ_WARPS : 2;
+  // leader's arrive.expect_tx (covers the TMA bytes of both CTAs) + the dequant warps of both CTAs
+  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS : 1;   // one producer group per CTA
 };
 
 template <int BLOCK_N, int KIND, bool BF16>
@@ -687,8 +709,9 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           const uint32_t lf = leader_full0 + 8u * stage;
           const int kc = kb * C::K_PER_BLOCK;
+          // the peer's TMA bytes land on the leader's barrier too; the peer itself does not arrive (its loads of
+          // phase n+1 cannot start before its `empty` barrier says the leader consumed phase n)
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (KIND == G_W4 ? A_STAGE_BYTES : C::STAGE_BYTES));
-          else mbar_arrive_cluster(lf);
           tma_load_2d_pair(a_dst, &map_a, lf, kc, m0);
           if (KIND != G_W4) tma_load_2d_pair(b_dst, &map_b, lf, kc, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -706,11 +729,11 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        mbar_wait_cluster(tmem_empty_bar(acc), acc_phase ^ 1);
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait_cluster(full_bar(stage), phase);
+          mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;

@@ -311,6 +311,8 @@ def gemm_f16(x, w, bias=None):
     _cuda(x, "x"), _cuda(w, "w")
     if w.dtype != x.dtype:
         raise ValueError("x and w must share a dtype")
+    if w.dim() != 2 or x.shape[-1] != w.shape[1]:
+        raise ValueError(f"shape mismatch: x[..., {x.shape[-1]}] @ w{tuple(w.shape)}^T")
     x2, y = _gemm_io(x, w.shape[0])
     wc = w.contiguous()
     b = bias.to(x.dtype).contiguous() if bias is not None else None
@@ -325,6 +327,8 @@ def gemm_f16_kn(x, w_kn, bias=None):
     _cuda(x, "x"), _cuda(w_kn, "w_kn")
     if w_kn.dtype != x.dtype:
         raise ValueError("x and w must share a dtype")
+    if w_kn.dim() != 2 or x.shape[-1] != w_kn.shape[0]:
+        raise ValueError(f"shape mismatch: x[..., {x.shape[-1]}] @ w_kn{tuple(w_kn.shape)}")
     x2, y = _gemm_io(x, w_kn.shape[1])
     wc = w_kn.contiguous()
     b = bias.to(x.dtype).contiguous() if bias is not None else None
@@ -356,6 +360,8 @@ def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):
     _cuda(xq, "xq"), _cuda(wq, "wq")
     m, k = xq.shape
     n = wq.shape[0]
+    if wq.shape[1] != k or sx.numel() != m or sw.numel() != n or sx.dtype != torch.float32 or sw.dtype != torch.float32:
+        raise ValueError(f"shape/dtype mismatch: xq{tuple(xq.shape)} wq{tuple(wq.shape)} sx{tuple(sx.shape)} sw{tuple(sw.shape)}")
     y = torch.empty((m, n), dtype=out_dtype, device=xq.device)
     b = bias.to(out_dtype).contiguous() if bias is not None else None
     with torch.cuda.device(xq.device):

@@ -375,16 +375,19 @@ class SkeletonPipeline:
         self.kind = kind
         self.device, self.dtype = torch.device(device), dtype
         denoiser.to(device=self.device, dtype=dtype).eval()
+        # conditioning widths are read off the module tree so that scaled-down skeletons work too
         if kind == "sd3":
             self.transformer, self.unet = denoiser, None
-            self.latent_channels, self.latent_size = 16, latent_size or 128
-            self.ctx_shape, self.pooled_dim = (333, 4096), 2048
+            self.latent_channels, self.latent_size = denoiser.in_ch, latent_size or 128
+            self.ctx_shape = (333, denoiser.context_embedder.in_features)
+            self.pooled_dim = denoiser.time_text_embed.text_embedder.linear_1.in_features
         else:
             self.unet, self.transformer = denoiser, None
-            self.latent_channels = 4
+            self.latent_channels = denoiser.conv_in.in_channels
             self.latent_size = latent_size or (128 if kind == "sdxl" else 64)
-            self.ctx_shape = (77, 2048 if kind == "sdxl" else 768)
-            self.pooled_dim = 2816 if kind == "sdxl" else None
+            ctx = next(m.attn2.to_k.in_features for m in denoiser.modules() if isinstance(m, BasicTransformerBlock))
+            self.ctx_shape = (77, ctx)
+            self.pooled_dim = denoiser.add_embedding.linear_1.in_features if denoiser.add_embedding is not None else None
 
     def to(self, *a, **k):
         return self
