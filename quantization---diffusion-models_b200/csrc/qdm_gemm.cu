@@ -191,6 +191,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int c_fmt, int ab_fmt, int b_m
 struct GemmParams {
   int M, N, K;
   int group;                 // G_W4
+  int tile_n;                // columns per output tile (multiple of 16, <= the BLOCK_N the kernel was built for)
   const int32_t* qweight;    // G_W4  [K, N/8]
   const int32_t* qzeros;     // G_W4  [K/group, N/8]
   const void* scales;        // G_W4  [K/group, N] dtype
@@ -254,13 +255,14 @@ __device__ __forceinline__ void load8_as_float(const void* base, int64_t idx, bo
 template <int BLOCK_N, int KIND, bool BF16>
 __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg, uint32_t taddr0, int row0, int n0, int lane) {
   uint16_t* y = reinterpret_cast<uint16_t*>(p.y);
+  const int n_end = min(n0 + p.tile_n, p.N);   // columns of this tile that exist
   const int row = row0 + lane;
   float sxr = 1.f;
   if (KIND == G_I8) sxr = (row < p.M) ? p.sx[row] : 0.f;
 #pragma unroll 1
   for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
     const int nc = n0 + c * EPI_COLS;
-    if (nc >= p.N) break;
+    if (nc >= n_end) break;
     uint32_t v[EPI_COLS];
     const uint32_t taddr = taddr0 + c * EPI_COLS;
     tmem_ld32(taddr, v);
@@ -269,7 +271,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg
 #pragma unroll
     for (int j8 = 0; j8 < EPI_COLS / 8; ++j8) {
       const int n = nc + j8 * 8;
-      const bool ok = n < p.N;
+      const bool ok = n < n_end;
       float bias8[8];
       load8_as_float<BF16>(p.bias, n, ok, bias8);
       float f[8];
@@ -300,7 +302,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg
       const int r = it * 4 + (lane >> 3), seg = lane & 7;
       const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_PITCH + seg * 16);
       const int gm = row0 + r, gn = nc + seg * 8;
-      if (gm < p.M && gn < p.N) *reinterpret_cast<uint4*>(y + int64_t(gm) * p.N + gn) = o;
+      if (gm < p.M && gn < n_end) *reinterpret_cast<uint4*>(y + int64_t(gm) * p.N + gn) = o;
     }
     __syncwarp();
   }
@@ -321,16 +323,17 @@ constexpr int DQ_GROUP_THREADS = 32 * NUM_DQ_WARPS / DQ_GROUPS;   // 128
 
 template <int NLOC, bool BF16, int STAGES, int STAGE_BYTES, bool CLUSTER>
 __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, int lane, int first_tile, int tile_stride,
-                                                 int num_tiles, int m_tiles, int num_kb, int tile_n, int col_off,
+                                                 int num_tiles, int n_tiles, int num_kb, int tile_n, int col_off, int nloc,
                                                  uint32_t b_stage0, uint32_t empty_addr, uint32_t full_addr) {
   constexpr int WPR = NLOC / 8;                  // packed words per k row of this CTA's tile part
   constexpr int RPP = DQ_GROUP_THREADS / WPR;    // k rows covered by one pass of the group
   constexpr int PASSES = 64 / RPP;
-  constexpr int DIST = 2;                        // prefetch distance, in k-blocks of this group
+  constexpr int DIST = 2;                        // ring depth - 1; loads run DIST + 1 group-k-blocks ahead
   static_assert(RPP >= 1 && PASSES >= 1 && 64 % RPP == 0, "bad producer tiling");
   const int grp = dt / DQ_GROUP_THREADS, tg = dt % DQ_GROUP_THREADS;
   const int wc = tg % WPR, kr = tg / WPR;
   const int words_per_row = p.N / 8;
+  const bool in_tile = wc * 8 < nloc;            // `nloc` <= NLOC columns of the tile part are in use
   const int gshift = 31 - __clz(p.group >> 6);   // group / 64 is a power of two (host-checked)
   // MN-major SW128 tile: 64-column chunk (wc>>3), k row stride 128 B, 16-byte slot (wc&7) ^ (k&7)
   const uint32_t chunk_off = uint32_t(wc >> 3) * (64 * ROW_BYTES);
@@ -348,8 +351,8 @@ __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, in
   int pf_tile = first_tile, pf_kb = grp, pf_wcol = 0;
   bool pf_valid = false;
   auto enter_tile = [&]() {
-    pf_wcol = ((pf_tile / m_tiles) * tile_n + col_off) / 8 + wc;
-    pf_valid = pf_tile < num_tiles && pf_wcol < words_per_row;
+    pf_wcol = ((pf_tile % n_tiles) * tile_n + col_off) / 8 + wc;
+    pf_valid = in_tile && pf_tile < num_tiles && pf_wcol < words_per_row;
   };
   auto normalise = [&]() {   // carry pf_kb into pf_tile
     bool moved = false;
@@ -375,7 +378,7 @@ __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, in
     normalise();
   };
 #pragma unroll
-  for (int d = 0; d < DIST; ++d) prefetch(ring[d]);
+  for (int d = 0; d < DIST + 1; ++d) prefetch(ring[d]);
 
   // constants kept in registers so that (x & mask) | magic is ONE lop3
   uint32_t mask_lo = 0x000F000Fu, mask_hi = 0x00F000F0u;
@@ -412,6 +415,7 @@ __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, in
     const uint32_t b_dst = b_stage0 + stage * STAGE_BYTES;
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) {
+      if (!in_tile) break;   // columns past the tile are never read by the MMA
       const uint32_t w = f.w[ps];
       uint32_t o[4];
       if (BF16) {
@@ -462,8 +466,10 @@ __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, in
 #pragma unroll
     for (int u = 0; u < DIST + 1; ++u) {
       if (it + u < mine) {
-        prefetch(ring[(u + DIST) % (DIST + 1)]);
+        // loads are issued AFTER the proxy fence of this k-block: the fence waits for every outstanding memory
+        // operation of the thread, prefetches included (measured as long-scoreboard stalls on FENCE.VIEW.ASYNC)
         process(ring[u]);
+        prefetch(ring[u]);   // ring[u] is free again: refill it with k-block it + u + DIST + 1
       }
     }
   }
@@ -491,7 +497,8 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tile_n = p.tile_n;
+  const int n_tiles = (p.N + tile_n - 1) / tile_n;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + C::K_PER_BLOCK - 1) / C::K_PER_BLOCK;
 
@@ -528,7 +535,7 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+        const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
@@ -538,11 +545,12 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
             tma_load_2d(a_dst, &map_a, full_bar(stage), kc, m0);
           } else {
-            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            // B bytes: tile_n rows of 128 B (K-major box), or ceil(tile_n / 64) boxes of 64 x 64 (MN-major)
+            const int kn_chunks = (tile_n + 63) / 64;
+            mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + (KIND == G_F16_KN ? kn_chunks * 64 : tile_n) * ROW_BYTES);
             tma_load_2d(a_dst, &map_a, full_bar(stage), kc, m0);
             if (KIND == G_F16_KN) {
-#pragma unroll
-              for (int c = 0; c < BLOCK_N / 64; ++c)
+              for (int c = 0; c < kn_chunks; ++c)
                 tma_load_2d(b_dst + c * (64 * ROW_BYTES), &map_b, full_bar(stage), n0 + c * 64, kc);
             } else {
               tma_load_2d(b_dst, &map_b, full_bar(stage), kc, n0);
@@ -556,8 +564,8 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===================================================== MMA issuer
     if (lane == 0) {
       constexpr bool B_MN = (KIND == G_F16_KN || KIND == G_W4);
-      constexpr uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, BLOCK_M, BLOCK_N)
-                                                : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, BLOCK_M, BLOCK_N);
+      const uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, BLOCK_M, tile_n)
+                                            : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, BLOCK_M, tile_n);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -592,7 +600,7 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % m_tiles) * BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+      const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
       epilogue_drain<BLOCK_N, KIND, BF16>(p, stg, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
@@ -604,7 +612,7 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (KIND == G_W4 && warp >= 8) {
     // ===================================================== int4 dequant producers
     w4_producer_loop<BLOCK_N, BF16, STAGES, C::STAGE_BYTES, false>(
-        p, threadIdx.x - 256, lane, blockIdx.x, gridDim.x, num_tiles, m_tiles, num_kb, BLOCK_N, 0,
+        p, threadIdx.x - 256, lane, blockIdx.x, gridDim.x, num_tiles, n_tiles, num_kb, tile_n, 0, tile_n,
         smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, bar_base);
   }
 
@@ -662,7 +670,8 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int tile_n = p.tile_n, nloc = p.tile_n / 2;   // this CTA holds `nloc` of the tile's B columns
+  const int n_tiles = (p.N + tile_n - 1) / tile_n;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (p.K + C::K_PER_BLOCK - 1) / C::K_PER_BLOCK;
 
@@ -701,8 +710,8 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile % m_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M;
-        const int n0 = (tile / m_tiles) * BLOCK_N + int(rank) * NLOC;
+        const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M;
+        const int n0 = (tile % n_tiles) * tile_n + int(rank) * nloc;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
@@ -711,7 +720,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int kc = kb * C::K_PER_BLOCK;
           // the peer's TMA bytes land on the leader's barrier too; the peer itself does not arrive (its loads of
           // phase n+1 cannot start before its `empty` barrier says the leader consumed phase n)
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (KIND == G_W4 ? A_STAGE_BYTES : C::STAGE_BYTES));
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (A_STAGE_BYTES + (KIND == G_W4 ? 0 : nloc * ROW_BYTES)));
           tma_load_2d_pair(a_dst, &map_a, lf, kc, m0);
           if (KIND != G_W4) tma_load_2d_pair(b_dst, &map_b, lf, kc, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -722,8 +731,8 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===================================================== MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
       constexpr bool B_MN = (KIND == G_W4);
-      constexpr uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, 2 * BLOCK_M, BLOCK_N)
-                                                : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, 2 * BLOCK_M, BLOCK_N);
+      const uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, 2 * BLOCK_M, tile_n)
+                                            : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, 2 * BLOCK_M, tile_n);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -758,7 +767,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m0 = (tile % m_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+      const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
       epilogue_drain<BLOCK_N, KIND, BF16>(p, stg, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
@@ -771,12 +780,14 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (KIND == G_W4 && warp >= 8) {
     // ===================================================== int4 dequant producers (each CTA: its NLOC columns)
     w4_producer_loop<NLOC, BF16, STAGES, C::STAGE_BYTES, true>(
-        p, threadIdx.x - 256, lane, pair, num_pairs, num_tiles, m_tiles, num_kb, BLOCK_N, int(rank) * NLOC,
+        p, threadIdx.x - 256, lane, pair, num_pairs, num_tiles, n_tiles, num_kb, tile_n, int(rank) * nloc, nloc,
         smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, leader_full0);
   }
 
   tc_fence_before();
-  cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers
+  // execution-only rendezvous (the peer may still be reading this CTA's operands / signalling its barriers): a
+  // relaxed arrive, so the epilogue warps do not sit in a MEMBAR.ALL.GPU behind their output stores
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
@@ -817,10 +828,26 @@ int make_map(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, in
   return QDM_OK;
 }
 
-int pick_block_n(int64_t N) {
-  if (N <= 128) return 128;
-  const int64_t waste256 = (N + 255) / 256 * 256 - N;
-  return waste256 >= 128 ? 128 : 256;
+// Tile width.  The kernels are built for up to 256 columns per tile; the width actually used is chosen per problem
+// so that the persistent grid is not left with a nearly empty last wave (80 tiles on 74 CTA pairs cost two full
+// waves).  Model per (tile, k-block), in cycles: tensor pipe 2*tn, shared-memory traffic (A written + read,
+// B written + read) 256 + tn for a CTA pair and 256 + 2*tn for a single CTA, plus a fixed per-tile cost.
+int choose_tile_n(int64_t M, int64_t N, bool pair) {
+  const int64_t rows = pair ? 2 * BLOCK_M : BLOCK_M, units = pair ? QDM_NUM_SMS / 2 : QDM_NUM_SMS;
+  const int64_t m_tiles = (M + rows - 1) / rows;
+  const int n_cap = int((N + 15) / 16 * 16);
+  int best = 256;
+  double best_cost = 1e300;
+  for (int tn = 256; tn >= 32; tn -= 16) {
+    if (tn > n_cap && tn != 256) continue;
+    const int t = tn > n_cap ? n_cap : tn;
+    const int64_t n_tiles = (N + t - 1) / t;
+    const int64_t waves = (m_tiles * n_tiles + units - 1) / units;
+    const double mma = 2.0 * t, smem = pair ? 256.0 + t : 256.0 + 2.0 * t;
+    const double cost = double(waves) * ((mma > smem ? mma : smem) + 64.0);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = t; }
+  }
+  return best;
 }
 
 template <int BLOCK_N, int KIND, bool BF16>
@@ -832,7 +859,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + p.tile_n - 1) / p.tile_n;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < QDM_NUM_SMS ? tiles : QDM_NUM_SMS;
   kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
@@ -849,7 +876,7 @@ int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams&
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (p.N + p.tile_n - 1) / p.tile_n;
   const int tiles = m_tiles * n_tiles;
   const int pairs = tiles < QDM_NUM_SMS / 2 ? tiles : QDM_NUM_SMS / 2;
   kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
@@ -866,15 +893,8 @@ bool use_pair(const GemmParams& p) {
 }
 
 template <int KIND>
-int dispatch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int block_n, bool pair, cudaStream_t st) {
-  if (pair) {
-    if (block_n == 128)
-      return p.is_bf16 ? launch_gemm2<128, KIND, true>(ma, mb, p, st) : launch_gemm2<128, KIND, false>(ma, mb, p, st);
-    return p.is_bf16 ? launch_gemm2<256, KIND, true>(ma, mb, p, st) : launch_gemm2<256, KIND, false>(ma, mb, p, st);
-  }
-  if (block_n == 128) {
-    return p.is_bf16 ? launch_gemm<128, KIND, true>(ma, mb, p, st) : launch_gemm<128, KIND, false>(ma, mb, p, st);
-  }
+int dispatch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, bool pair, cudaStream_t st) {
+  if (pair) return p.is_bf16 ? launch_gemm2<256, KIND, true>(ma, mb, p, st) : launch_gemm2<256, KIND, false>(ma, mb, p, st);
   return p.is_bf16 ? launch_gemm<256, KIND, true>(ma, mb, p, st) : launch_gemm<256, KIND, false>(ma, mb, p, st);
 }
 
@@ -904,14 +924,14 @@ extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void
   QDM_REQUIRE(!bias || qdm_aligned16(bias), "qdm_gemm_f16: bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  const int bn = pick_block_n(N);
   CUtensorMap ma, mb;
   if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
   const bool pair = use_pair(p);
-  if ((rc = make_map(&mb, w, 2, N, K, 64, pair ? bn / 2 : bn))) return rc;
-  return dispatch_gemm<G_F16>(ma, mb, p, bn, pair, (cudaStream_t)stream);
+  p.tile_n = choose_tile_n(M, N, pair);
+  if ((rc = make_map(&mb, w, 2, N, K, 64, pair ? p.tile_n / 2 : p.tile_n))) return rc;
+  return dispatch_gemm<G_F16>(ma, mb, p, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
@@ -922,13 +942,13 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   QDM_REQUIRE(!bias || qdm_aligned16(bias), "qdm_gemm_f16_kn: bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  const int bn = pick_block_n(N);
   CUtensorMap ma, mb;
   if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
   if ((rc = make_map(&mb, w_kn, 2, K, N, 64, 64))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
-  return dispatch_gemm<G_F16_KN>(ma, mb, p, bn, false, (cudaStream_t)stream);
+  p.tile_n = choose_tile_n(M, N, false);
+  return dispatch_gemm<G_F16_KN>(ma, mb, p, false, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
@@ -943,13 +963,14 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   QDM_REQUIRE(qdm_aligned16(scales) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w4a16: scales/bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  const int bn = pick_block_n(N);
   CUtensorMap ma;
   if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.group = group;
   p.qweight = qweight; p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
-  return dispatch_gemm<G_W4>(ma, ma, p, bn, use_pair(p), (cudaStream_t)stream);
+  const bool pair = use_pair(p);
+  p.tile_n = choose_tile_n(M, N, pair);
+  return dispatch_gemm<G_W4>(ma, ma, p, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const float* sw,
@@ -962,14 +983,14 @@ extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq
   QDM_REQUIRE(qdm_aligned16(sw) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w8a8: sw/bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  const int bn = pick_block_n(N);
   CUtensorMap ma, mb;
   if ((rc = make_map(&ma, xq, 1, M, K, 128, BLOCK_M))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.sx = sx; p.sw = sw; p.bias = bias; p.y = y; p.is_bf16 = out_dtype == QDM_BF16;
   const bool pair = use_pair(p);
-  if ((rc = make_map(&mb, wq, 1, N, K, 128, pair ? bn / 2 : bn))) return rc;
-  return dispatch_gemm<G_I8>(ma, mb, p, bn, pair, (cudaStream_t)stream);
+  p.tile_n = choose_tile_n(M, N, pair);
+  if ((rc = make_map(&mb, wq, 1, N, K, 128, pair ? p.tile_n / 2 : p.tile_n))) return rc;
+  return dispatch_gemm<G_I8>(ma, mb, p, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight, const int32_t* qzeros,
