@@ -199,13 +199,31 @@ def run_ours(args):
             ms = t.item()
         return ms
 
-    # ---- device-resident throughput
+    # ---- device-resident throughput.  The 184 launches of a step are captured once in a CUDA graph (the tensor
+    # maps are by-value kernel parameters, so the capture is exact) and replayed: per-launch host work (Python,
+    # ctypes, cuTensorMapEncodeTiled) would otherwise bound the short small-M launches.
+    run_step = step
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        run_step = graph.replay
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     q.ops.launch_count(reset=True)
-    ms = timed(step, args.steps, args.warmup)
-    launches = q.ops.launch_count() * args.steps // (args.steps + args.warmup)
+    ms = timed(run_step, args.steps, args.warmup)
+    launches = n_calls * args.steps   # one libqdm kernel per Linear call (checked against the library's counter below)
+    if graph is None:
+        assert q.ops.launch_count() == n_calls * (args.steps + args.warmup), q.ops.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms / args.steps
     value = world * flops_step / (ms_step * 1e-3) / 1e12
@@ -240,6 +258,7 @@ def run_ours(args):
         "config": {"workload": "sd15_unet_w4a16_linears_b8cfg", "reference_config": "SD1.5 UNet W4A16 AWQ group-128, 512x512 latents batch 8 (CFG -> B_eff 16)",
                    "linear_calls_per_step": n_calls, "distinct_shapes": len(layers), "tflop_per_step": flops_step / 1e12,
                    "group_size": "128 (64 where K=320)", "l2": "per-step working set (>1.5 GB of activations + 184 distinct weights) exceeds the 126 MB L2",
+                   "launch": "eager" if graph is None else "one CUDA graph of the step's 184 launches",
                    "parallelism": f"dp{world} (prompt-batched, no collective in the step)"},
         "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
@@ -324,6 +343,113 @@ def run_tables(args):
         json.dump({"peaks": peaks, "rows": rows}, f, indent=1)
 
 
+# ------------------------------------------------------------------------------------------ model-level modes
+def run_models(args):
+    """The other BASELINE.json metrics, on the synthetic skeletons (one JSON line each; not the driver contract):
+      --mode denoise : it/s of the 50-step style loop (CFG) with fp16 / W4A16 / W8A8 Linears, data parallel
+      --mode calib   : AWQ calibration (scale + clip search, quantise, pack) seconds per model, block-sharded
+      --mode rtn     : config 1, RTN W8 per-channel over every Linear / Conv weight of the SD1.5 UNet (GB/s)"""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M = importlib.import_module("quantization---diffusion-models_b200.models")
+    q = importlib.import_module("quantization---diffusion-models_b200")
+    cls = {"sd15": M.StableDiffusion1_x, "sdxl": M.StableDiffusionXL, "sd35": M.StableDiffusion3_5}[args.model]
+    arch = {"layers": args.blocks} if (args.model == "sd35" and args.blocks) else {}
+    batch = args.batch or {"sd15": 8, "sdxl": 4, "sd35": 1}[args.model]
+    t_build = time.perf_counter()
+    model = cls.from_skeleton(device=dev, **arch)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+
+    def sync_max(x):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return x
+
+    out = {"mode": args.mode, "model": args.model, "n_gpus": world, "batch_per_gpu": batch, "data": "synthetic, random-init skeleton",
+           "build_s": t_build}
+    if args.mode == "denoise":
+        cfgs = {"w4a16": {"zero_point": True, "q_group_size": 128, "w_bit": 4, "version": "gemm"}, "w8a8": {"w_bit": 8, "version": "w8a8"}}
+        if args.quant != "fp16":
+            model.quantize(quant_config=cfgs[args.quant], quantType="awq")
+        prompts = [f"prompt {rank}-{i}" for i in range(batch)]
+        lat = torch.randn(batch, model.pipeline.latent_channels, model.pipeline.latent_size, model.pipeline.latent_size,
+                          generator=torch.Generator().manual_seed(42 + rank)).to(dev, model.pipeline.dtype)
+        model.generate(prompts, lat=lat, num_inference_steps=2)
+        sync_max(0.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q.ops.launch_count(reset=True)
+        e0.record()
+        res = model.generate(prompts, lat=lat, num_inference_steps=args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = sync_max(e0.elapsed_time(e1) * 1e-3)
+        out.update({"metric": "denoise_it_per_s", "quant": args.quant, "steps": args.steps, "value": args.steps / sec,
+                    "images_it_per_s": world * batch * args.steps / sec, "seconds": sec, "finite": bool(torch.isfinite(res).all()),
+                    "libqdm_launches": q.ops.launch_count(), "scaling": "weak (prompt-batched data parallel, no collective in the loop)"})
+    elif args.mode == "calib":
+        model.calib_samples = model.default_calib_samples(args.calib_batches, batch)
+        model.calib_steps = args.calib_steps
+        sync_max(0.0)
+        t0 = time.perf_counter()
+        model.quantize(quant_config={"zero_point": True, "q_group_size": 128, "w_bit": 4, "version": "gemm"}, quantType="awq",
+                       calibrate=True, shard=(rank, world) if world > 1 else None)
+        torch.cuda.synchronize()
+        sec = sync_max(time.perf_counter() - t0)
+        chk, n_mod = 0, 0
+        for name, mod in model.denoiser().named_modules():
+            if type(mod).__name__ == "WQLinear_GEMM":
+                n_mod += 1
+                for t in (mod.qweight, mod.qzeros, mod.scales.view(torch.int16)):
+                    chk = (chk * 1000003 + int(t.to(torch.int64).sum().item()) + t.numel()) % (1 << 61)
+        out.update({"metric": "awq_calib_s_per_model", "value": sec, "blocks": len(model.get_search_blocks()), "groups_searched": len(model.quantizer.search_log),
+                    "packed_modules": n_mod, "codes_checksum": chk, "calib_batches": args.calib_batches, "calib_steps": args.calib_steps,
+                    "note": "checksum covers qweight/qzeros/scales of every packed Linear; identical across world sizes = bit-exact codes"})
+    else:  # rtn (config 1)
+        fq = importlib.import_module("quantization---diffusion-models_b200.fake_quant")
+        ws = [m.weight.data for m in model.denoiser().modules() if isinstance(m, (torch.nn.Linear, torch.nn.Conv2d))]
+        numel = sum(w.numel() for w in ws)
+        for w in ws[:4]:
+            fq.quantize_weight_per_channel_absmax(w, 8)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for w in ws:
+            fq.quantize_weight_per_channel_absmax(w, 8)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        import oracle.qdm_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        sample = [w.cpu() for w in ws[:: max(1, len(ws) // 24)]]
+        tc = time.perf_counter()
+        for w in sample:
+            O.rtn_rows(w, 8)
+        tc = time.perf_counter() - tc
+        cpu_numel = sum(w.numel() for w in sample)
+        out.update({"metric": "rtn_w8_per_channel_GBps", "value": 4.0 * numel / sec / 1e9, "tensors": len(ws), "params": numel, "seconds": sec,
+                    "bytes_model": "2 B read + 2 B written per weight (fake-quant output)",
+                    "cpu_baseline": {"value": 4.0 * cpu_numel / tc / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                                     "sample": f"{len(sample)} of {len(ws)} tensors, {cpu_numel / 1e6:.0f} M weights"}})
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,7 +459,17 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--layers", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn"])
+    ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl", "sd35"])
+    ap.add_argument("--quant", default="w4a16", choices=["fp16", "w4a16", "w8a8"])
+    ap.add_argument("--blocks", type=int, default=0, help="sd35: number of joint blocks (default 38)")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--calib-batches", type=int, default=1)
+    ap.add_argument("--calib-steps", type=int, default=2)
     args = ap.parse_args()
+    if args.mode != "linears":
+        return run_models(args)
     if args.impl == "reference":
         return run_reference(args)
     if args.sweep or args.layers:

@@ -174,7 +174,7 @@ int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, 
 /* y[M,N] = x[M,K] @ dequant(qweight,qzeros,scales)[K,N] + bias; dequant inside the main loop.
  * Same storage as WQLinear_GEMM (call sites quantize/quantizer.py:544-569):
  *   qweight [K, N/8] int32, qzeros [K/group, N/8] int32, scales [K/group, N] dtype.
- * N % 8 == 0, K % 64 == 0, group % 64 == 0 and group divides K. */
+ * N % 8 == 0, K % 64 == 0, group = 64 * 2^j dividing K.  M <= 128 runs single-CTA tiles, larger M CTA-pair tiles. */
 int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
                    const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
                    void* stream);

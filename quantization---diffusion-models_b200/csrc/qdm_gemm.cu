@@ -958,8 +958,8 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   if (rc) return rc;
   QDM_REQUIRE(qzeros && scales, "qdm_gemm_w4a16: null qzeros/scales");
   QDM_REQUIRE(K % 64 == 0, "qdm_gemm_w4a16: K=%lld must be a multiple of 64", (long long)K);
-  QDM_REQUIRE(group > 0 && group % 64 == 0 && K % group == 0,
-              "qdm_gemm_w4a16: group=%d must be a multiple of 64 dividing K=%lld", group, (long long)K);
+  QDM_REQUIRE(group > 0 && group % 64 == 0 && K % group == 0 && ((group / 64) & (group / 64 - 1)) == 0,
+              "qdm_gemm_w4a16: group=%d must be 64 * 2^j and divide K=%lld", group, (long long)K);
   QDM_REQUIRE(qdm_aligned16(scales) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w4a16: scales/bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
@@ -1006,3 +1006,4 @@ extern "C" int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_
   QDM_CUDA_OK(cudaMemcpyAsync(y_host, y_dev, size_t(M) * N * 2, cudaMemcpyDeviceToHost, st));
   return QDM_OK;
 }
+

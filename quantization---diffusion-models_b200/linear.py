@@ -53,11 +53,10 @@ class WQLinear_GEMM(nn.Module):
             m.bias = linear.bias.data.clone().to(dtype)
         return m
 
-    @torch.no_grad()
     def forward(self, x):
-        xs = x if x.dtype == self.scales.dtype else x.to(self.scales.dtype)
-        y = ops.gemm_w4a16(xs, self.qweight, self.qzeros, self.scales, self.group_size, self.bias)
-        return y if y.dtype == x.dtype else y.to(x.dtype)
+        if x.dtype == self.scales.dtype:
+            return ops.gemm_w4a16(x, self.qweight, self.qzeros, self.scales, self.group_size, self.bias)
+        return ops.gemm_w4a16(x.to(self.scales.dtype), self.qweight, self.qzeros, self.scales, self.group_size, self.bias).to(x.dtype)
 
     def dequantize(self):
         """[N, K] fake-quant weight (utils/packing_utils.py:87-102, transposed back to nn.Linear layout)."""

@@ -31,6 +31,24 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _guard(device):
+    """`with torch.cuda.device(d)` costs ~10 us per call; skip it when d is already current (the common case)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -78,7 +96,7 @@ def colabsmax(x, out=None, running=False):
         out = torch.empty(cols, dtype=x.dtype, device=x.device)
     L = lib()
     ws = _ws(x.device, L.qdm_colreduce_workspace_bytes(rows, cols))
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(L.qdm_colabsmax(x2.data_ptr(), _dt(x2), rows, cols, x2.stride(0), out.data_ptr(),
                               1 if running else 0, ws.data_ptr(), ws.numel(), _stream(x)))
     return out
@@ -92,7 +110,7 @@ def colabssum(x):
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
     L = lib()
     ws = _ws(x.device, L.qdm_colreduce_workspace_bytes(rows, cols))
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(L.qdm_colabssum(x2.data_ptr(), _dt(x2), rows, cols, x2.stride(0), out.data_ptr(),
                               ws.data_ptr(), ws.numel(), _stream(x)))
     return out
@@ -104,7 +122,7 @@ def rowabsmax(x):
     x2 = x.contiguous().reshape(-1, x.shape[-1])
     rows, cols = x2.shape
     out = torch.empty(rows, dtype=x.dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(lib().qdm_rowabsmax(x2.data_ptr(), _dt(x2), rows, cols, out.data_ptr(), _stream(x)))
     return out.reshape(x.shape[:-1])
 
@@ -116,7 +134,7 @@ def absmax(x):
     out = torch.empty((), dtype=x.dtype, device=x.device)
     L = lib()
     ws = _ws(x.device, L.qdm_absmax_workspace_bytes(xc.numel()))
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(L.qdm_absmax(xc.data_ptr(), _dt(xc), xc.numel(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)))
     return out
 
@@ -130,7 +148,7 @@ def awq_wsum(w, group):
     out = torch.empty(k, dtype=torch.float32, device=w.device)
     L = lib()
     ws = _ws(w.device, L.qdm_colreduce_workspace_bytes(n, k))
-    with torch.cuda.device(w.device):
+    with _guard(w.device):
         check(L.qdm_awq_wsum(wc.data_ptr(), _dt(wc), n, k, int(group), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(w)))
     return out
 
@@ -144,7 +162,7 @@ def sqdiff_sum(a, b):
     out = torch.empty((), dtype=torch.float64, device=a.device)
     L = lib()
     ws = _ws(a.device, L.qdm_sqdiff_workspace_bytes(ac.numel()))
-    with torch.cuda.device(a.device):
+    with _guard(a.device):
         check(L.qdm_sqdiff_sum(ac.data_ptr(), bc.data_ptr(), _dt(ac), ac.numel(), out.data_ptr(),
                                ws.data_ptr(), ws.numel(), _stream(a)))
     return out
@@ -183,7 +201,7 @@ def quant_group(w, group, n_bits=4, zero_point=True, no_clamp=False, pre_mul=Non
     pm = pre_mul.contiguous() if pre_mul is not None else None
     pd = post_div.contiguous() if post_div is not None else None
     cm = clip_max.contiguous() if clip_max is not None else None
-    with torch.cuda.device(dev):
+    with _guard(dev):
         check(lib().qdm_quant_group(wc.data_ptr(), _dt(wc), n, k, int(group), int(n_bits), _flags(zero_point, no_clamp),
                                     _ptr(pm), _ptr(cm), _ptr(pd), _ptr(dq), _ptr(codes), _ptr(scales), _ptr(zeros),
                                     _stream(w)))
@@ -200,7 +218,7 @@ def quant_rowwise(x, n_bits=8, zero_point=False, no_clamp=True, want_dq=True, wa
     codes = torch.empty(xc.shape, dtype=torch.uint8 if zero_point else torch.int8, device=x.device) if want_codes else None
     scales = torch.empty(rows, dtype=x.dtype, device=x.device) if want_scales else None
     zeros = torch.empty(rows, dtype=x.dtype, device=x.device) if (want_scales and zero_point) else None
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(lib().qdm_quant_rowwise(xc.data_ptr(), _dt(xc), rows, cols, int(n_bits), _flags(zero_point, no_clamp),
                                       _ptr(dq), _ptr(codes), _ptr(scales), _ptr(zeros), _stream(x)))
     return dq, codes, scales, zeros
@@ -215,7 +233,7 @@ def quant_tensor(x, n_bits=8, want_dq=True, want_codes=False):
     scale = torch.empty((), dtype=x.dtype, device=x.device)
     L = lib()
     ws = _ws(x.device, L.qdm_quant_tensor_workspace_bytes(xc.numel()))
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(L.qdm_quant_tensor(xc.data_ptr(), _dt(xc), xc.numel(), int(n_bits), _ptr(dq), _ptr(codes),
                                  scale.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)))
     return dq, codes, scale
@@ -231,7 +249,7 @@ def actquant_token_i8(x, smooth=None):
     xq = torch.empty((rows, cols), dtype=torch.int8, device=x.device)
     sx = torch.empty(rows, dtype=torch.float32, device=x.device)
     sm = smooth.contiguous() if smooth is not None else None
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(lib().qdm_actquant_token_i8(x2.data_ptr(), _dt(x2), rows, cols, _ptr(sm), xq.data_ptr(), sx.data_ptr(), _stream(x)))
     return xq, sx
 
@@ -246,7 +264,7 @@ def pack_awq(codes_nk):
     if n % 8:
         raise ValueError(f"N={n} must be a multiple of 8")
     q = torch.empty((k, n // 8), dtype=torch.int32, device=c.device)
-    with torch.cuda.device(c.device):
+    with _guard(c.device):
         check(lib().qdm_pack_awq(c.data_ptr(), n, k, q.data_ptr(), _stream(c)))
     return q
 
@@ -257,7 +275,7 @@ def unpack_awq(qweight):
     q = qweight.contiguous()
     k, nw = q.shape
     out = torch.empty((k, nw * 8), dtype=torch.int8, device=q.device)
-    with torch.cuda.device(q.device):
+    with _guard(q.device):
         check(lib().qdm_unpack_awq(q.data_ptr(), k, nw * 8, out.data_ptr(), _stream(q)))
     return out
 
@@ -279,7 +297,7 @@ def quant_pack_awq(w, group, want_dq=False):
     qzeros = torch.empty((k // group, n // 8), dtype=torch.int32, device=w.device)
     scales = torch.empty((k // group, n), dtype=w.dtype, device=w.device)
     dq = torch.empty_like(wc) if want_dq else None
-    with torch.cuda.device(w.device):
+    with _guard(w.device):
         check(lib().qdm_quant_pack_awq(wc.data_ptr(), _dt(wc), n, k, int(group), qweight.data_ptr(), qzeros.data_ptr(),
                                        scales.data_ptr(), _ptr(dq), _stream(w)))
     return qweight, qzeros, scales, dq
@@ -290,7 +308,7 @@ def dequant_awq(qweight, qzeros, scales, group):
     _cuda(qweight, "qweight")
     k, nw = qweight.shape
     out = torch.empty((k, nw * 8), dtype=scales.dtype, device=qweight.device)
-    with torch.cuda.device(qweight.device):
+    with _guard(qweight.device):
         check(lib().qdm_dequant_awq(qweight.contiguous().data_ptr(), qzeros.contiguous().data_ptr(),
                                     scales.contiguous().data_ptr(), _dt(scales), k, nw * 8, int(group),
                                     out.data_ptr(), _stream(qweight)))
@@ -316,7 +334,7 @@ def gemm_f16(x, w, bias=None):
     x2, y = _gemm_io(x, w.shape[0])
     wc = w.contiguous()
     b = bias.to(x.dtype).contiguous() if bias is not None else None
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(lib().qdm_gemm_f16(x2.data_ptr(), wc.data_ptr(), _ptr(b), y.data_ptr(), _dt(x2),
                                  x2.shape[0], wc.shape[0], wc.shape[1], _stream(x)))
     return y.reshape(*x.shape[:-1], w.shape[0])
@@ -332,27 +350,38 @@ def gemm_f16_kn(x, w_kn, bias=None):
     x2, y = _gemm_io(x, w_kn.shape[1])
     wc = w_kn.contiguous()
     b = bias.to(x.dtype).contiguous() if bias is not None else None
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         check(lib().qdm_gemm_f16_kn(x2.data_ptr(), wc.data_ptr(), _ptr(b), y.data_ptr(), _dt(x2),
                                     x2.shape[0], wc.shape[1], wc.shape[0], _stream(x)))
     return y.reshape(*x.shape[:-1], w_kn.shape[1])
 
 
 def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None):
-    """x @ dequant(qweight, qzeros, scales) + bias, AWQ GEMM layout (quantize/quantizer.py:544-569)."""
-    _cuda(x, "x"), _cuda(qweight, "qweight")
+    """x @ dequant(qweight, qzeros, scales) + bias, AWQ GEMM layout (quantize/quantizer.py:544-569).
+    This is the per-Linear hot call of a denoise step: the Python side is kept to the bare minimum."""
+    if not x.is_cuda or not qweight.is_cuda:
+        raise RuntimeError("gemm_w4a16 needs CUDA tensors: the B200 path has no CPU fallback")
     if scales.dtype != x.dtype:
         raise ValueError("scales must have the activation dtype")
     k, nw = qweight.shape
     n = nw * 8
     if x.shape[-1] != k:
         raise ValueError(f"x has K={x.shape[-1]}, qweight has K={k}")
-    x2, y = _gemm_io(x, n)
-    b = bias.to(x.dtype).contiguous() if bias is not None else None
-    with torch.cuda.device(x.device):
-        check(lib().qdm_gemm_w4a16(x2.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(), _ptr(b),
-                                   y.data_ptr(), _dt(x2), x2.shape[0], n, k, int(group), _stream(x)))
-    return y.reshape(*x.shape[:-1], n)
+    x2 = x.reshape(-1, k)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    m = x2.shape[0]
+    y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
+        bias = bias.to(x.dtype).contiguous()
+    L = _lib._lib or lib()
+    with _guard(x.device):
+        rc = L.qdm_gemm_w4a16(x2.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(),
+                              0 if bias is None else bias.data_ptr(), y.data_ptr(), _DTYPES[x.dtype], m, n, k, group,
+                              torch.cuda.current_stream(x.device).cuda_stream)
+    if rc:
+        check(rc)
+    return y.reshape(*x.shape[:-1], n) if x.dim() != 2 else y
 
 
 def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):
@@ -364,7 +393,7 @@ def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):
         raise ValueError(f"shape/dtype mismatch: xq{tuple(xq.shape)} wq{tuple(wq.shape)} sx{tuple(sx.shape)} sw{tuple(sw.shape)}")
     y = torch.empty((m, n), dtype=out_dtype, device=xq.device)
     b = bias.to(out_dtype).contiguous() if bias is not None else None
-    with torch.cuda.device(xq.device):
+    with _guard(xq.device):
         check(lib().qdm_gemm_w8a8(xq.data_ptr(), sx.data_ptr(), wq.data_ptr(), sw.data_ptr(), _ptr(b), y.data_ptr(),
                                   _DTYPES[out_dtype], m, n, k, _stream(xq)))
     return y
@@ -374,7 +403,7 @@ def gemm_w4a16_host(x_host, x_dev, qweight, qzeros, scales, group, bias, y_dev, 
     """Host-buffer entry: pinned x_host -> device -> W4A16 GEMM -> pinned y_host, all on the current stream."""
     k, nw = qweight.shape
     m = x_host.numel() // k
-    with torch.cuda.device(x_dev.device):
+    with _guard(x_dev.device):
         check(lib().qdm_gemm_w4a16_host(x_host.data_ptr(), x_dev.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(),
                                         scales.data_ptr(), _ptr(bias), y_dev.data_ptr(), y_host.data_ptr(),
                                         _dt(x_dev), m, nw * 8, k, int(group), _stream(x_dev)))

@@ -21,6 +21,8 @@ CASES = [
     ("w8", "f16", 128, 128, 128), ("w8", "f16", 300, 320, 320), ("w8", "bf16", 1024, 1280, 1280),
     ("f16", "f16", 4096, 1280, 1280), ("w4", "f16", 8192, 1280, 1280, 128), ("w4", "bf16", 4096, 640, 2560, 128),
     ("w8", "f16", 8192, 5120, 640), ("w4", "f16", 257, 256, 128, 128), ("w4", "f16", 65536, 320, 320, 64),
+    ("w4", "f16", 16, 1280, 1280, 128), ("w4", "bf16", 2, 14592, 2432, 128), ("w4", "f16", 1, 320, 1280, 128),
+    ("w4", "f16", 9, 1280, 320, 64), ("w4", "f16", 16, 72, 192, 64),
 ]
 
 

@@ -38,6 +38,33 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(3):
         fn()
+    if os.environ.get("QDM_ONE_GRAPH"):
+        # warm GPU-side time without host launch overhead: CUDA graph of 10 x (L2 flush, gemm) minus 10 x flush
+        def graph_ms(body):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                for _ in range(10):
+                    body()
+            g_.replay()
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g_.replay(); e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            return best / 10
+        t_both = graph_ms(lambda: (flush.zero_(), fn()))
+        t_flush = graph_ms(lambda: flush.zero_())
+        t = t_both - t_flush
+        print(f"{kind} M={M} N={N} K={K}: {t * 1e3:.1f} us GPU-side (graph, L2 flushed), {2.0 * M * N * K / t / 1e9:.0f} TFLOP/s")
+        return
     ts = []
     for _ in range(iters):
         flush.zero_()
