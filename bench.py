@@ -416,7 +416,7 @@ def run_models(args):
                 for t in (mod.qweight, mod.qzeros, mod.scales.view(torch.int16)):
                     chk = (chk * 1000003 + int(t.to(torch.int64).sum().item()) + t.numel()) % (1 << 61)
         out.update({"metric": "awq_calib_s_per_model", "value": sec, "blocks": len(model.get_search_blocks()), "groups_searched": len(model.quantizer.search_log),
-                    "packed_modules": n_mod, "codes_checksum": chk, "calib_batches": args.calib_batches, "calib_steps": args.calib_steps,
+                    "packed_modules": n_mod, "codes_checksum": chk, "phases": getattr(model.quantizer, "timings", None), "calib_batches": args.calib_batches, "calib_steps": args.calib_steps,
                     "note": "checksum covers qweight/qzeros/scales of every packed Linear; identical across world sizes = bit-exact codes"})
     else:  # rtn (config 1)
         fq = importlib.import_module("quantization---diffusion-models_b200.fake_quant")

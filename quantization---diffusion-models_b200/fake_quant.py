@@ -88,16 +88,18 @@ class WxAxLinear(nn.Module):
     forward = F.linear on the tcgen05 GEMM (kernel c/d family, qdm_gemm_f16)."""
 
     def __init__(self, in_features, out_features, bias=True, weight_quant='per_channel', act_quant='per_token',
-                 quantize_output=False, n_bits_A=16, q_act=False):
+                 quantize_output=False, n_bits_A=16, q_act=False, device=None):
+        """`device` (new): where the buffers are created; the reference fills them with CPU randn first
+        (fake_quant.py:179-183), which costs seconds on a UNet and is overwritten by from_float anyway."""
         super().__init__()
         self.scales = []
         self.inputs = []
         self.quantize_act = q_act
         self.in_features = in_features
         self.out_features = out_features
-        self.register_buffer('weight', torch.randn(out_features, in_features, dtype=torch.float16, requires_grad=False))
+        self.register_buffer('weight', torch.empty(out_features, in_features, dtype=torch.float16, device=device))
         if bias:
-            self.register_buffer('bias', torch.zeros(out_features, dtype=torch.float16, requires_grad=False))
+            self.register_buffer('bias', torch.zeros(out_features, dtype=torch.float16, device=device))
         else:
             self.register_buffer('bias', None)
         self.weight_quant_name = weight_quant
@@ -136,10 +138,9 @@ class WxAxLinear(nn.Module):
         assert isinstance(module, torch.nn.Linear)
         new_module = WxAxLinear(module.in_features, module.out_features, module.bias is not None,
                                 weight_quant=weight_quant, act_quant=act_quant, quantize_output=quantize_output,
-                                n_bits_A=n_bits_A)
+                                n_bits_A=n_bits_A, device=module.weight.device)
         if init_only:
             return new_module
-        new_module.to(module.weight.device)
         if weight_quant == 'per_channel':
             new_module.weight.data.copy_(quantize_weight_per_channel_absmax(module.weight.data, n_bits_W))
         elif weight_quant == 'per_tensor':
@@ -166,7 +167,8 @@ class WxAxConv2d(nn.Module):
     itself stays cuDNN (outside the north-star kernels a-d)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
-                 act_group_size=1, weight_quant='per_tensor', act_quant='per_token', quantize_output=False, n_bits_A=16):
+                 act_group_size=1, weight_quant='per_tensor', act_quant='per_token', quantize_output=False, n_bits_A=16,
+                 device=None):
         super().__init__()
         pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
         self.in_channels, self.out_channels = in_channels, out_channels
@@ -176,10 +178,10 @@ class WxAxConv2d(nn.Module):
         self.a_gs = act_group_size
         self.quantise_act = quantize_output
         assert in_channels % groups == 0
-        self.register_buffer('weight', torch.randn((out_channels, in_channels // groups, *self.kernel_size),
-                                                   dtype=torch.float16, requires_grad=False))
+        self.register_buffer('weight', torch.empty((out_channels, in_channels // groups, *self.kernel_size),
+                                                   dtype=torch.float16, device=device))
         if bias:
-            self.register_buffer('bias', torch.zeros(out_channels, dtype=torch.float16, requires_grad=False))
+            self.register_buffer('bias', torch.zeros(out_channels, dtype=torch.float16, device=device))
         else:
             self.register_buffer('bias', None)
         self.weight_quant_name = weight_quant
@@ -212,10 +214,10 @@ class WxAxConv2d(nn.Module):
         assert isinstance(module, torch.nn.Conv2d)
         new_module = cls(module.in_channels, module.out_channels, module.kernel_size, module.stride, module.padding,
                          module.dilation, module.groups, module.bias is not None, act_quant=act_quant,
-                         quantize_output=quantize_output, n_bits_A=n_bits_A, act_group_size=act_group_size)
+                         quantize_output=quantize_output, n_bits_A=n_bits_A, act_group_size=act_group_size,
+                         device=module.weight.device)
         if init_only:
             return new_module
-        new_module.to(module.weight.device)
         if weight_quant == 'per_channel':
             new_module.weight.data.copy_(quantize_weight_per_channel_absmax(module.weight.data, n_bits_W))
         elif weight_quant == 'per_tensor':

@@ -65,6 +65,13 @@ class AwqQuantizer:
 
     MyTraversal = ModuleTraversal   # quantizer.py:142-159
 
+    def _g(self, k):
+        """group size used for a K-wide layer: the configured one, shrunk by 32 until it divides K exactly as
+        the fake-quant path does (fake_quant.py:34-37; K = 320 -> 64).  The reference's AWQ branch would
+        assert instead (quantizer.py:166); diffusion widths need the fallback."""
+        from .fake_quant import _effective_group
+        return _effective_group(k, self.group_size) if self.group_size > 0 else k
+
     # ------------------------------------------------------------------ quantizer.py:163-213
     def pseudo_quantize_tensor(self, w: torch.Tensor, bitWidth=4):
         """Per-group RTN; returns (w_fakequant, scales, zeros|None) exactly like quantizer.py:163-198."""
@@ -136,14 +143,26 @@ class AwqQuantizer:
         if shard is not None:
             from .dist import assign_blocks
             names = assign_blocks(names, [self.awq_model.block_cost(blocks[n]) for n in names], shard[1])[shard[0]]
+        import time
+        tm = self.timings = {"capture_s": 0.0, "scale_search_s": 0.0, "clip_search_s": 0.0}
+
+        def lap(key, t0):
+            torch.cuda.synchronize()
+            tm[key] += time.perf_counter() - t0
+
+        t0 = time.perf_counter()
         feats = self.awq_model.capture_block_inputs(names)
+        lap("capture_s", t0)
         out = {}
         for bname in names:
             block = blocks[bname]
             input_feat = feats[bname]
             groups = self.awq_model.get_layers_for_scaling(block, input_feat)
+            t0 = time.perf_counter()
             scales_list = [self._search_best_scale(block, **g) for g in groups] if self.applyScale else []
+            lap("scale_search_s", t0)
             res = {"scales": scales_list, "clip": []}
+            t0 = time.perf_counter()
             if self.apply_clip:
                 # the clip search runs on the SCALED weights and inputs (quantizer.py:312-336); do that on a view
                 # of the block and roll the weights back so the gathered results can be applied once everywhere
@@ -155,6 +174,7 @@ class AwqQuantizer:
                 for n, l in named.items():
                     l.weight.data = backup[n]
                 self._restore_prev_ops(prev_backup)
+            lap("clip_search_s", t0)
             out[bname] = res
             del feats[bname]
         return out
@@ -248,7 +268,7 @@ class AwqQuantizer:
         inp = inp.to(next(module2inspect.parameters()).device)
         # [STEP 1] per-channel mean of the group-normalised weights (quantizer.py:627-637): fused kernel, fp32 sums
         weight = torch.cat([m.weight for m in layers], dim=0)
-        w_mean = (ops.awq_wsum(weight, self.group_size if self.group_size > 0 else weight.shape[1]) / weight.shape[0]).to(weight.dtype)
+        w_mean = (ops.awq_wsum(weight, self._g(weight.shape[1])) / weight.shape[0]).to(weight.dtype)
         # [STEP 2] per-channel mean |x| in fp32 (quantizer.py:642-659): one reduction kernel, no CPU round trip
         n_tok = inp.numel() // inp.shape[-1]
         x_mean = (ops.colabssum(inp) / n_tok).to(inp.dtype)
@@ -284,7 +304,7 @@ class AwqQuantizer:
         scratch = [torch.empty_like(w) for w in org]
         losses = torch.full((n_grid,), float("inf"), dtype=torch.float64, device=x.device)
         cand = {}
-        g = self.group_size
+        g = self._g(org[0].shape[1])
         try:
             for i in ratios:
                 scales = self._ratio_scales(x_mean, w_mean, i / n_grid)
@@ -336,13 +356,19 @@ class AwqQuantizer:
         keeps fp32 products, so err values agree to ~1e-3 relative and best_max can differ on near-ties."""
         assert w.dim() == 2
         co, ci = w.shape
-        gs = self.group_size if self.group_size > 0 else ci
+        gs = self._g(ci)
         G = ci // gs
         x = input_feat.view(-1, input_feat.shape[-1])
         x = x[:: max(1, x.shape[0] // n_sample_token)]
         xg = x.reshape(-1, G, gs).permute(1, 2, 0).contiguous().float()      # [G, g, n_tok]
-        oc_batch = 256 if co % 256 == 0 else 64
-        assert co % oc_batch == 0
+        # The reference walks out-rows in batches of 256 / 64 because its broadcast product needs
+        # co_b x n_tok x K temporaries (quantizer.py:827); rows are independent, and the batched-GEMM form only
+        # needs G x co_b x n_tok fp32, so the batch is as large as ~1 GB of temporaries allows.
+        assert co % (256 if co % 256 == 0 else 64) == 0
+        n_tok = xg.shape[2]
+        oc_batch = co
+        while oc_batch * G * n_tok * 4 > (1 << 30) and oc_batch % 2 == 0 and oc_batch > 64:
+            oc_batch //= 2
         best_all = []
         for b in range(co // oc_batch):
             wb = w[b * oc_batch:(b + 1) * oc_batch].contiguous()             # [co_b, ci]
