@@ -450,6 +450,62 @@ def run_models(args):
         dist.destroy_process_group()
 
 
+def run_kernels(args):
+    """--mode kernels: HBM roofline of the reduction (a) and quantise/pack (b) kernels on tensors larger than L2.
+    Bytes are the algorithmic ones of SURVEY.md section 8(d): elem*numel read + the outputs actually emitted."""
+    import torch
+    q = importlib.import_module("quantization---diffusion-models_b200")
+    dev = torch.device("cuda", 0)
+    peaks = measured_peaks()
+    g = torch.Generator(device=dev).manual_seed(0)
+    rows, cols = 65536, 2560                      # 335 MB fp16 activations (one SD1.5 ff.net.0 output)
+    x = torch.randn(rows, cols, generator=g, device=dev, dtype=torch.float16)
+    w = torch.randn(9728 * 4, 2432, generator=g, device=dev, dtype=torch.float16) * 0.02   # 4 SD3.5 ff weights, 189 MB
+    y = (x.float() + 0.01).half()
+    s_vec = (torch.rand(2432, generator=g, device=dev) + 0.5).half()
+    dq_out = torch.empty_like(w)
+
+    def t_ms(fn, iters=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    nx, nw = x.numel(), w.numel()
+    cases = [
+        ("a colabsmax (hook, calib_data.py:117)", lambda: q.ops.colabsmax(x), 2 * nx),
+        ("a colabssum (x_mean, quantizer.py:652)", lambda: q.ops.colabssum(x), 2 * nx),
+        ("a awq_wsum (w_mean, quantizer.py:627)", lambda: q.ops.awq_wsum(w, 128), 2 * nw),
+        ("a sqdiff_sum (loss, quantizer.py:777)", lambda: q.ops.sqdiff_sum(x, y), 4 * nx),
+        ("a rowabsmax", lambda: q.ops.rowabsmax(x), 2 * nx),
+        ("b quant_group zp g128 -> dq (quantizer.py:163)", lambda: q.ops.quant_group(w, 128, 4, True, want_scales=True, out=dq_out), 4 * nw + 4 * nw // 128),
+        ("b quant_group W*s, /s fused (quantizer.py:727)", lambda: q.ops.quant_group(w, 128, 4, True, pre_mul=s_vec, post_div=s_vec, want_scales=False, out=dq_out), 4 * nw),
+        ("b quant_group sym noclamp (fake_quant.py:21)", lambda: q.ops.quant_group(w, 128, 4, False, no_clamp=True, want_scales=False, out=dq_out), 4 * nw),
+        ("b quant_pack_awq (quantizer.py:540-569)", lambda: q.ops.quant_pack_awq(w, 128), 2 * nw + nw // 2 + 5 * nw // 256),
+        ("b quant_rowwise 8-bit (fake_quant.py:86)", lambda: q.ops.quant_rowwise(x, 8), 4 * nx),
+        ("b actquant_token_i8 (fake_quant.py:109)", lambda: q.ops.actquant_token_i8(x), 3 * nx + 4 * rows),
+        ("b dequant_awq (packing_utils.py:87)", None, 0),
+        ("ref torch copy_ (same bytes model: 2 B in + 2 B out)", lambda: dq_out.copy_(w), 4 * nw),
+    ]
+    qw, qz, sc, _ = q.ops.quant_pack_awq(w, 128)
+    cases[11] = ("b dequant_awq (packing_utils.py:87)", lambda: q.ops.dequant_awq(qw, qz, sc, 128), nw // 2 + 2 * nw + 5 * nw // 256)
+    rows_out = []
+    for name, fn, nbytes in cases:
+        ms = t_ms(fn)
+        r = {"kernel": name, "ms": ms, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks["hbm"]}
+        rows_out.append(r)
+        print(json.dumps(r), flush=True)
+    out = args.out or os.path.join(ROOT, "gpurun_out", "kernels_ab.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "w") as f:
+        json.dump({"peaks": peaks, "rows": rows_out}, f, indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -460,7 +516,7 @@ def main():
     ap.add_argument("--layers", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn"])
+    ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn", "kernels"])
     ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl", "sd35"])
     ap.add_argument("--quant", default="w4a16", choices=["fp16", "w4a16", "w8a8"])
     ap.add_argument("--blocks", type=int, default=0, help="sd35: number of joint blocks (default 38)")
@@ -468,6 +524,8 @@ def main():
     ap.add_argument("--calib-batches", type=int, default=1)
     ap.add_argument("--calib-steps", type=int, default=2)
     args = ap.parse_args()
+    if args.mode == "kernels":
+        return run_kernels(args)
     if args.mode != "linears":
         return run_models(args)
     if args.impl == "reference":
