@@ -197,6 +197,12 @@ int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight,
  * 2 = CTA-pair tiles (cta_group::2, 256 x N).  Process-wide; not part of the reference interface. */
 int qdm_set_gemm_mode(int ctas);
 
+/* Test hook (synchronous, allocates 16 bytes): sweeps EVERY (dividend, divisor) pair of 16-bit values of
+ * `dtype` (QDM_F16 | QDM_BF16) inside the window in which the quantise kernels replace IEEE division by a
+ * reciprocal + two FMAs, and compares against __fdiv_rn after the dtype rounding.
+ * out_host[0] = pairs tested, out_host[1] = pairs that differ (must be 0).  See csrc/qdm_common.cuh. */
+int qdm_selftest_fastdiv(int dtype, uint64_t* out_host);
+
 /* number of kernels launched by this library in the calling thread since the last reset */
 int64_t qdm_launch_count(int reset);
 

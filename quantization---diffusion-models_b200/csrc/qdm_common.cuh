@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <type_traits>
 #include "../../include/qdm.h"
 
 // ---------------------------------------------------------------- error plumbing
@@ -127,6 +128,53 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---------------------------------------------------------------- exact division without the IEEE slow path
+// torch divides fp16/bf16 tensors as rnd<T>(fp32 w / fp32 s) with a correctly rounded fp32 quotient.
+// `__fdiv_rn` per element costs a MUFU, ~8 FFMA, an FCHK and a divergent slow-path call, which makes the
+// quantise kernels issue-bound instead of HBM-bound.  With one reciprocal estimate r ~ 1/s per divisor,
+//   q0 = w * r;  e = fma(-q0, s, w) (exact remainder);  q = fma(e, r, q0)
+// gives rnd<T>(q) == rnd<T>(__fdiv_rn(w, s)) for EVERY pair of fp16 values, and for every pair of bf16
+// values with s in [2^-60, 2^60] and |w| <= 2^64 -- proven by exhaustion over all 2^31 pairs on the device
+// (qdm_selftest_fastdiv, run by tests/test_gpu_quant.py).  Outside that window (bf16 only: quotient
+// overflow, subnormal divisors) and for fp32 tensors the kernels take `__fdiv_rn`.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// KEEP_ZERO_SIGN: a zero dividend keeps the sign IEEE division gives it (fma(+0, r, -0) would lose it);
+// callers that fix the sign themselves or feed an integer add skip the two extra instructions.
+template <bool KEEP_ZERO_SIGN>
+__device__ __forceinline__ float div_by_rcp(float w, float s, float r) {
+  const float q0 = __fmul_rn(w, r);
+  const float e = __fmaf_rn(-q0, s, w);
+  const float q1 = __fmaf_rn(e, r, q0);
+  return (KEEP_ZERO_SIGN && w == 0.f) ? q0 : q1;
+}
+// may the divisor s (> 0) be used with div_by_rcp for dividends of magnitude <= amax?
+template <typename T>
+__device__ __forceinline__ bool fastdiv_ok(float s, float amax) {
+  if (std::is_same<T, __half>::value) return true;
+  if (std::is_same<T, float>::value) return false;
+  return s >= 0x1p-60f && s <= 0x1p50f && amax <= 0x1p50f;   // |q * s| <= 2^8 * 2^50 keeps post-division inside too
+}
+template <typename T, bool FAST, bool KEEP_ZERO_SIGN>
+__device__ __forceinline__ float div_T(float w, float s, float r) {
+  return FAST ? div_by_rcp<KEEP_ZERO_SIGN>(w, s, r) : __fdiv_rn(w, s);
+}
+// round-half-even to an integer.  16-bit dtypes: magic-number add (two FADD on the FMA pipe instead of an
+// FRND on the quarter-rate XU pipe), exact for |q| < 2^22 and order/sign/inf-preserving above, where every
+// caller clamps.  A zero result comes out as +0; callers that need torch.round's -0 copy the dividend's sign.
+template <typename T>
+__device__ __forceinline__ float rint_T(float q) {
+  if (std::is_same<T, float>::value) return rintf(q);
+  return __fadd_rn(__fadd_rn(q, 12582912.f), -12582912.f);
+}
+// low byte of a small integer held in a float (two's complement), without an F2I
+__device__ __forceinline__ uint32_t int_byte(float c) {
+  return __float_as_uint(__fadd_rn(c, 12582912.f)) & 0xffu;
 }
 
 // The RTN chain shared by every quantiser of the reference.  One call = the torch ops

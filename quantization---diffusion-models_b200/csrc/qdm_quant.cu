@@ -45,12 +45,151 @@ __device__ __forceinline__ int8_t code_to_i8(float q) {
 
 constexpr int kQThreads = 256;
 
+// One 16-byte vector of a group through the reference's op chain.  x[] already holds the prepared
+// (pre-multiplied / clipped) weights, (s, z) the group's parameters.  Writes the fake-quantised values
+// to o and the integer codes (as floats) to cq.  FAST selects the reciprocal division (see qdm_common.cuh).
+//   zero point: q = round(w/s); c = clamp(q + z, 0, max); dq = (c - z) * s      quantizer.py:177-182
+//     (q + z and c - z are sums of small integers, exact in every dtype; when q is too large for that
+//      both the rounded and the unrounded sum are far above max and clamp to it)
+//   symmetric:  q = round(w/s); c = clamp(q, min, max) [not for NO_CLAMP]; dq = c * s   quantizer.py:186-190
+template <typename T, int MODE, bool FAST, bool POST, bool POST_FAST>
+__device__ __forceinline__ void rtn_vec(const float (&x)[ElemTraits<T>::kVec], float s, float z,
+                                        float min_int, float max_int,
+                                        const float (&pd)[ElemTraits<T>::kVec], const float (&rpd)[ElemTraits<T>::kVec],
+                                        Vec16<T>& o, float (&cq)[ElemTraits<T>::kVec]) {
+  constexpr int V = ElemTraits<T>::kVec;
+  const float r = FAST ? rcp_approx(s) : 0.f;
+  const float lo = (MODE == Q_ZP) ? __fsub_rn(0.f, z) : min_int, hi = (MODE == Q_ZP) ? __fsub_rn(max_int, z) : max_int;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    float q = rint_T<T>(rnd<T>(div_T<T, FAST, false>(x[j], s, r)));
+    if (MODE != Q_ZP) q = copysignf(q, x[j]);    // torch.round keeps the sign of a zero result; s > 0
+    if (MODE != Q_SYM_NOCLAMP) q = fminf(fmaxf(q, lo), hi);
+    cq[j] = q;                                   // code - z (zero point) or the code itself
+    if (POST) {
+      const float v = rnd<T>(__fmul_rn(q, s));
+      o.v[j] = ElemTraits<T>::from_f(div_T<T, POST_FAST, MODE != Q_ZP>(v, pd[j], rpd[j]));
+    } else {
+      o.v[j] = ElemTraits<T>::from_f(__fmul_rn(q, s));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- fp16 (the reference dtype) packed path
+// Everything except the division itself runs on half2 pairs (two elements per lane-instruction):
+//   * x*pre_mul, clamp, min/max and q*s round exactly like "fp32 op, round to fp16" because the fp32
+//     results are exact (22-bit products, comparisons), so HMUL2/HMNMX2 give the same bits;
+//   * round-half-even is (q + 1536) - 1536 in fp16 (ulp 1 in [1024, 2048)): exact for |q| < 512, and above
+//     that still far outside every clamp range (unclamped codes never exceed 128);
+//   * the quotient is formed in fp32 (div_by_rcp) and packed back with one F2FP per pair.
+// About 7 instructions per element instead of 13; that is what moves these kernels from issue-bound to HBM-bound.
+struct H2x4 { __half2 h[4]; };
+
+__device__ __forceinline__ H2x4 as_h2x4(const Vec16<__half>& v) {
+  H2x4 r;
+  *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(&v);
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+
+// per-lane packed (max, min) [zero point] or (|.|max, -) [symmetric] of one vector
+template <int MODE>
+__device__ __forceinline__ void fold_h(const H2x4& x, __half2& m2, __half2& n2) {
+  if (MODE == Q_ZP) {
+    m2 = __hmax2(__hmax2(x.h[0], x.h[1]), __hmax2(x.h[2], x.h[3]));
+    n2 = __hmin2(__hmin2(x.h[0], x.h[1]), __hmin2(x.h[2], x.h[3]));
+  } else {
+    m2 = __hmax2(__hmax2(__habs2(x.h[0]), __habs2(x.h[1])), __hmax2(__habs2(x.h[2]), __habs2(x.h[3])));
+    n2 = m2;
+  }
+}
+// fold the two halves, then ONE butterfly over `lpg` adjacent lanes on the pair (max, -min): max of negated
+// minima is the negated minimum (negation is exact), so a single SHFL + HMNMX2 per step serves both.
+template <int MODE>
+__device__ __forceinline__ void reduce_h(__half2 m2, __half2 n2, int lpg, float& mx, float& mn) {
+  __half2 p;
+  if (MODE == Q_ZP) p = __halves2half2(__hmax(__low2half(m2), __high2half(m2)), __hneg(__hmin(__low2half(n2), __high2half(n2))));
+  else p = __hmax2(m2, __lowhigh2highlow(m2));
+  for (int o = 1; o < lpg; o <<= 1) p = __hmax2(p, __shfl_xor_sync(0xffffffffu, p, o));
+  mx = __low2float(p);
+  mn = (MODE == Q_ZP) ? -__high2float(p) : 0.f;
+}
+template <int MODE>
+__device__ __forceinline__ void minmax_h(const H2x4& x, int lpg, float& mx, float& mn) {
+  __half2 m2, n2;
+  fold_h<MODE>(x, m2, n2);
+  reduce_h<MODE>(m2, n2, lpg, mx, mn);
+}
+
+// group_params for fp16 with the reciprocal division (valid for every fp16 pair); also returns r ~ 1/s
+template <int MODE>
+__device__ __forceinline__ void group_params_h(float mx, float mn, float max_int, float r_max_int,
+                                               float& s, float& z, float& r) {
+  const float floor_c = rnd<__half>(1e-5f);
+  if (MODE == Q_ZP) {
+    const float d = fmaxf(rnd<__half>(__fsub_rn(mx, mn)), floor_c);
+    s = rnd<__half>(div_by_rcp<false>(d, max_int, r_max_int));
+    r = rcp_approx(s);
+    const float t = rint_T<__half>(rnd<__half>(div_by_rcp<false>(mn, s, r)));
+    z = fminf(fmaxf(-t, 0.f), max_int);
+  } else {
+    s = rnd<__half>(div_by_rcp<false>(fmaxf(mx, floor_c), max_int, r_max_int));
+    r = rcp_approx(s);
+    z = 0.f;
+  }
+}
+
+// the RTN chain on a packed vector; cq receives (code - z) [zero point] or the code, as exact fp16 integers
+template <int MODE, bool POST>
+__device__ __forceinline__ void rtn_vec_h(const H2x4& x, float s, float r, float z, float min_int, float max_int,
+                                          const float (&pd)[8], const float (&rpd)[8], H2x4& o, H2x4& cq) {
+  const __half2 s2 = __float2half2_rn(s);                      // s is an fp16 value: exact
+  const __half2 magic = __float2half2_rn(1536.f);
+  const __half2 lo2 = __float2half2_rn(MODE == Q_ZP ? __fsub_rn(0.f, z) : min_int);   // +0 when z == 0
+  const __half2 hi2 = __float2half2_rn(MODE == Q_ZP ? __fsub_rn(max_int, z) : max_int);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float2 xf = __half22float2(x.h[p]);
+    __half2 q = __floats2half2_rn(div_by_rcp<false>(xf.x, s, r), div_by_rcp<false>(xf.y, s, r));
+    q = __hsub2(__hadd2(q, magic), magic);
+    if (MODE != Q_ZP) q = bits_h2((h2_bits(q) & 0x7fff7fffu) | (h2_bits(x.h[p]) & 0x80008000u));  // sign of a zero result
+    if (MODE != Q_SYM_NOCLAMP) q = __hmin2(__hmax2(q, lo2), hi2);
+    cq.h[p] = q;
+    const __half2 v = __hmul2(q, s2);
+    if (POST) {
+      const float2 vf = __half22float2(v);
+      o.h[p] = __floats2half2_rn(div_by_rcp<MODE != Q_ZP>(vf.x, pd[2 * p], rpd[2 * p]),
+                                 div_by_rcp<MODE != Q_ZP>(vf.y, pd[2 * p + 1], rpd[2 * p + 1]));
+    } else {
+      o.h[p] = v;
+    }
+  }
+}
+
+// 8 code bytes from cq (adds z back for zero point; saturates symmetric codes to int8)
+template <int MODE>
+__device__ __forceinline__ uint2 code_bytes_h(const H2x4& cq, float z) {
+  const __half2 z2 = __float2half2_rn(z), magic = __float2half2_rn(1536.f);
+  uint32_t t[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    __half2 c = (MODE == Q_ZP) ? __hadd2(cq.h[p], z2)
+                               : __hmin2(__hmax2(cq.h[p], __float2half2_rn(-128.f)), __float2half2_rn(127.f));
+    t[p] = h2_bits(__hadd2(c, magic));                         // mantissa = 512 + c: low byte = c mod 256
+  }
+  return make_uint2(__byte_perm(t[0], t[1], 0x6420), __byte_perm(t[2], t[3], 0x6420));
+}
+
 // ---------------------------------------------------------------- power-of-two groups, vector path
-// The flattened tensor is a sequence of contiguous groups; a group is `lpg` adjacent lanes
-// (one 16-byte vector per lane), so group min/max is an xor-shuffle butterfly.
-template <typename T, int MODE>
+// W[n_rows, k_cols] is a sequence of contiguous groups; a group is `lpg` adjacent lanes (one 16-byte
+// vector per lane), so group min/max is an xor-shuffle butterfly.  Thread t owns vector column
+// t % vpr for rows t / vpr, + rows_per_pass, ...: the per-column vectors of the AWQ search
+// (pre_mul, post_div and its reciprocal) are loaded once per thread, and the next row's vector is
+// requested before the current one is processed (two 16-byte loads in flight per thread).
+template <typename T, int MODE, bool EXTRAS>
 __global__ void __launch_bounds__(kQThreads)
-quant_group_kernel(const T* __restrict__ w, int64_t n_vec, int64_t k_cols, int lpg,
+quant_group_kernel(const T* __restrict__ w, int n_rows, int vpr, int lpg_shift, int rows_per_pass,
                    float max_int, float min_int,
                    const T* __restrict__ pre_mul, const T* __restrict__ clip_max,
                    const T* __restrict__ post_div,
@@ -58,26 +197,94 @@ quant_group_kernel(const T* __restrict__ w, int64_t n_vec, int64_t k_cols, int l
                    T* __restrict__ scales, T* __restrict__ zeros) {
   constexpr int V = ElemTraits<T>::kVec;
   const int lane = threadIdx.x & 31;
-  const int64_t stride = int64_t(gridDim.x) * kQThreads;
-  for (int64_t base = int64_t(blockIdx.x) * kQThreads; base < n_vec; base += stride) {
-    const int64_t i = base + threadIdx.x;
-    const bool active = i < n_vec;
-    float x[V];
-    int64_t col = 0;
-    if (active) {
-      Vec16<T> v = ld_vec16_stream(w + i * V);
+  const int t = blockIdx.x * kQThreads + threadIdx.x;
+  const bool in_range = t < rows_per_pass * vpr;
+  const int cv = in_range ? t % vpr : 0;
+  const int row0 = in_range ? t / vpr : n_rows;
+  const int lpg = 1 << lpg_shift;
+  const int gpr = vpr >> lpg_shift;                // groups per row
+  float pm[V], pd[V], rpd[V];
+  H2x4 pmh;                                        // fp16 path keeps pre_mul packed
+  const float r_max_int = rcp_approx(max_int);
+  bool post_fast = true;
 #pragma unroll
-      for (int j = 0; j < V; ++j) x[j] = ElemTraits<T>::to_f(v.v[j]);
-      col = (i * V) % k_cols;
-      if (pre_mul) {
-        Vec16<T> pm = ld_vec16(pre_mul + col);
+  for (int j = 0; j < V; ++j) { pm[j] = 1.f; pd[j] = 1.f; rpd[j] = 1.f; }
 #pragma unroll
-        for (int j = 0; j < V; ++j) x[j] = rnd<T>(__fmul_rn(x[j], ElemTraits<T>::to_f(pm.v[j])));
+  for (int p = 0; p < 4; ++p) pmh.h[p] = __float2half2_rn(1.f);
+  if (EXTRAS) {
+    if (pre_mul) {
+      Vec16<T> a = ld_vec16(pre_mul + int64_t(cv) * V);
+#pragma unroll
+      for (int j = 0; j < V; ++j) pm[j] = ElemTraits<T>::to_f(a.v[j]);
+      if constexpr (std::is_same<T, __half>::value) pmh = as_h2x4(a);
+    }
+    if (post_div) {
+      Vec16<T> a = ld_vec16(post_div + int64_t(cv) * V);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        pd[j] = ElemTraits<T>::to_f(a.v[j]);
+        rpd[j] = rcp_approx(pd[j]);
+        post_fast = post_fast && fastdiv_ok<T>(pd[j], 0.f);
       }
-      if (clip_max) {
-        const float c = ElemTraits<T>::to_f(clip_max[i / lpg]);
+    }
+  }
+  Vec16<T> cur;
+  if (row0 < n_rows) cur = ld_vec16_stream(w + (int64_t(row0) * vpr + cv) * V);
+  for (int row = row0, base = 0; base < n_rows; base += rows_per_pass, row += rows_per_pass) {
+    const bool active = row < n_rows;               // `base` keeps the trip count warp-uniform for the shuffles
+    const int64_t i = int64_t(row) * vpr + cv;
+    Vec16<T> nxt;
+    if (row + rows_per_pass < n_rows && in_range) nxt = ld_vec16_stream(w + (i + int64_t(rows_per_pass) * vpr) * V);
+    if constexpr (std::is_same<T, __half>::value) {
+      H2x4 x;
+      if (active) {
+        x = as_h2x4(cur);
+        if (EXTRAS) {
+          if (pre_mul) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) x[j] = fminf(fmaxf(x[j], -c), c);
+            for (int p = 0; p < 4; ++p) x.h[p] = __hmul2(x.h[p], pmh.h[p]);
+          }
+          if (clip_max) {
+            const __half2 c2 = __half2half2(clip_max[int64_t(row) * gpr + (cv >> lpg_shift)]);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) x.h[p] = __hmin2(__hmax2(x.h[p], __hneg2(c2)), c2);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) x.h[p] = __float2half2_rn(0.f);
+      }
+      float mx, mn;
+      minmax_h<MODE>(x, lpg, mx, mn);
+      if (active) {
+        float s, z, r;
+        group_params_h<MODE>(mx, mn, max_int, r_max_int, s, z, r);
+        if ((lane & (lpg - 1)) == 0) {
+          const int64_t g = int64_t(row) * gpr + (cv >> lpg_shift);
+          if (scales) scales[g] = __float2half_rn(s);
+          if (zeros && MODE == Q_ZP) zeros[g] = __float2half_rn(z);
+        }
+        H2x4 o, cq;
+        if (EXTRAS && post_div) rtn_vec_h<MODE, true>(x, s, r, z, min_int, max_int, pd, rpd, o, cq);
+        else rtn_vec_h<MODE, false>(x, s, r, z, min_int, max_int, pd, rpd, o, cq);
+        if (dq) *reinterpret_cast<uint4*>(dq + i * V) = *reinterpret_cast<const uint4*>(&o);
+        if (codes) *reinterpret_cast<uint2*>(codes + i * V) = code_bytes_h<MODE>(cq, z);
+      }
+    } else {
+    float x[V];
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) x[j] = ElemTraits<T>::to_f(cur.v[j]);
+      if (EXTRAS) {
+        if (pre_mul) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) x[j] = rnd<T>(__fmul_rn(x[j], pm[j]));
+        }
+        if (clip_max) {
+          const float c = ElemTraits<T>::to_f(clip_max[int64_t(row) * gpr + (cv >> lpg_shift)]);
+#pragma unroll
+          for (int j = 0; j < V; ++j) x[j] = fminf(fmaxf(x[j], -c), c);
+        }
       }
     } else {
 #pragma unroll
@@ -97,34 +304,40 @@ quant_group_kernel(const T* __restrict__ w, int64_t n_vec, int64_t k_cols, int l
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (MODE == Q_ZP) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     }
-    if (!active) continue;
-    float s, z;
-    group_params<T, MODE>(mx, mn, max_int, s, z);
-    if ((lane & (lpg - 1)) == 0) {
-      const int64_t g = i / lpg;
-      if (scales) scales[g] = ElemTraits<T>::from_f(s);
-      if (zeros && MODE == Q_ZP) zeros[g] = ElemTraits<T>::from_f(z);
-    }
-    Vec16<T> o;
-    int8_t cb[V];
-    Vec16<T> pd;
-    if (post_div) pd = ld_vec16(post_div + col);
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float code;
-      float d = rtn_elem<T>(x[j], s, z, min_int, max_int, MODE == Q_ZP, MODE != Q_SYM_NOCLAMP, code);
-      if (post_div) d = rnd<T>(__fdiv_rn(d, ElemTraits<T>::to_f(pd.v[j])));
-      o.v[j] = ElemTraits<T>::from_f(d);
-      cb[j] = code_to_i8<MODE>(code);
-    }
-    if (dq) st_vec16(dq + i * V, o);
-    if (codes) {
-      if (V == 8) {
-        *reinterpret_cast<uint2*>(codes + i * V) = *reinterpret_cast<const uint2*>(cb);
+    if (active) {
+      float s, z;
+      group_params<T, MODE>(mx, mn, max_int, s, z);
+      if ((lane & (lpg - 1)) == 0) {
+        const int64_t g = int64_t(row) * gpr + (cv >> lpg_shift);
+        if (scales) scales[g] = ElemTraits<T>::from_f(s);
+        if (zeros && MODE == Q_ZP) zeros[g] = ElemTraits<T>::from_f(z);
+      }
+      float cq[V];
+      Vec16<T> o;
+      const float amax = (MODE == Q_ZP) ? fmaxf(fabsf(mx), fabsf(mn)) : mx;
+      const bool fast = fastdiv_ok<T>(s, amax);
+      if (EXTRAS && post_div) {
+        if (fast && post_fast) rtn_vec<T, MODE, true, true, true>(x, s, z, min_int, max_int, pd, rpd, o, cq);
+        else rtn_vec<T, MODE, false, true, false>(x, s, z, min_int, max_int, pd, rpd, o, cq);
       } else {
-        *reinterpret_cast<uint32_t*>(codes + i * V) = *reinterpret_cast<const uint32_t*>(cb);
+        if (fast) rtn_vec<T, MODE, true, false, false>(x, s, z, min_int, max_int, pd, rpd, o, cq);
+        else rtn_vec<T, MODE, false, false, false>(x, s, z, min_int, max_int, pd, rpd, o, cq);
+      }
+      if (dq) st_vec16(dq + i * V, o);
+      if (codes) {
+        uint32_t pk[V / 4];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float c = (MODE == Q_ZP) ? __fadd_rn(cq[j], z) : fminf(fmaxf(cq[j], -128.f), 127.f);
+          const uint32_t b = int_byte(c);
+          if ((j & 3) == 0) pk[j / 4] = b; else pk[j / 4] |= b << (8 * (j & 3));
+        }
+        if (V == 8) *reinterpret_cast<uint2*>(codes + i * V) = make_uint2(pk[0], pk[V / 4 - 1]);
+        else *reinterpret_cast<uint32_t*>(codes + i * V) = pk[0];
       }
     }
+    }
+    cur = nxt;
   }
 }
 
@@ -212,6 +425,115 @@ quant_rows_warp_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int6
   }
 }
 
+// Rows of up to 32*V*NV elements held in registers: one warp per row, every lane issues all of its
+// 16-byte loads up front (NV in flight), the row statistics come from a shuffle butterfly and the row is
+// quantised from registers -- one pass over HBM (elem read + outputs), unlike the two-pass kernel above.
+// I8OUT: emit int8 codes + fp32 scale (the A8 of W8A8) instead of the fake-quantised row.
+template <typename T, int MODE, int NV, bool I8OUT>
+__global__ void __launch_bounds__(kQThreads)
+quant_rows_reg_kernel(const T* __restrict__ x, int64_t rows, int cols, float max_int, float min_int,
+                      T* __restrict__ dq, int8_t* __restrict__ codes,
+                      T* __restrict__ scales, T* __restrict__ zeros, float* __restrict__ sx) {
+  constexpr int V = ElemTraits<T>::kVec;
+  const int lane = threadIdx.x & 31;
+  const int wpb = kQThreads / 32;
+  const float dummy[V] = {};
+  const float dummy8[8] = {};
+  for (int64_t row = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows;
+       row += int64_t(gridDim.x) * wpb) {
+    const T* p = x + row * cols;
+    Vec16<T> raw[NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+      const int e = (t * 32 + lane) * V;
+      if (e < cols) raw[t] = ld_vec16_stream(p + e);
+    }
+    if constexpr (std::is_same<T, __half>::value) {
+      __half2 m2 = __float2half2_rn((MODE == Q_ZP) ? -INFINITY : 0.f), n2 = __float2half2_rn(INFINITY);
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        if ((t * 32 + lane) * V < cols) {
+          __half2 a, b;
+          fold_h<MODE>(as_h2x4(raw[t]), a, b);
+          m2 = __hmax2(m2, a);
+          n2 = __hmin2(n2, b);
+        }
+      }
+      float mx, mn, s, z, r;
+      reduce_h<MODE>(m2, n2, 32, mx, mn);
+      group_params_h<MODE>(mx, mn, max_int, rcp_approx(max_int), s, z, r);
+      if (lane == 0) {
+        if (I8OUT) sx[row] = s;
+        if (scales) scales[row] = __float2half_rn(s);
+        if (zeros && MODE == Q_ZP) zeros[row] = __float2half_rn(z);
+      }
+      if (!dq && !codes) continue;
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int e = (t * 32 + lane) * V;
+        if (e < cols) {
+          H2x4 o, cq;
+          rtn_vec_h<MODE, false>(as_h2x4(raw[t]), s, r, z, min_int, max_int, dummy8, dummy8, o, cq);
+          if (dq) *reinterpret_cast<uint4*>(dq + row * cols + e) = *reinterpret_cast<const uint4*>(&o);
+          if (codes) *reinterpret_cast<uint2*>(codes + row * cols + e) = code_bytes_h<MODE>(cq, z);
+        }
+      }
+    } else {
+      float mx = (MODE == Q_ZP) ? -INFINITY : 0.f, mn = INFINITY;
+  #pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int e = (t * 32 + lane) * V;
+        if (e < cols) {
+  #pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float f = ElemTraits<T>::to_f(raw[t].v[j]);
+            if (MODE == Q_ZP) { mx = fmaxf(mx, f); mn = fminf(mn, f); } else mx = fmaxf(mx, fabsf(f));
+          }
+        }
+      }
+  #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (MODE == Q_ZP) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      float s, z;
+      group_params<T, MODE>(mx, mn, max_int, s, z);
+      if (lane == 0) {
+        if (I8OUT) sx[row] = s;
+        if (scales) scales[row] = ElemTraits<T>::from_f(s);
+        if (zeros && MODE == Q_ZP) zeros[row] = ElemTraits<T>::from_f(z);
+      }
+      if (!dq && !codes) continue;
+      const float amax = (MODE == Q_ZP) ? fmaxf(fabsf(mx), fabsf(mn)) : mx;
+      const bool fast = fastdiv_ok<T>(s, amax);
+  #pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        const int e = (t * 32 + lane) * V;
+        if (e < cols) {
+          float xv[V], cq[V];
+          Vec16<T> o;
+  #pragma unroll
+          for (int j = 0; j < V; ++j) xv[j] = ElemTraits<T>::to_f(raw[t].v[j]);
+          if (fast) rtn_vec<T, MODE, true, false, false>(xv, s, z, min_int, max_int, dummy, dummy, o, cq);
+          else rtn_vec<T, MODE, false, false, false>(xv, s, z, min_int, max_int, dummy, dummy, o, cq);
+          if (dq) st_vec16(dq + row * cols + e, o);
+          if (codes) {
+            uint32_t pk[V / 4];
+  #pragma unroll
+            for (int j = 0; j < V; ++j) {
+              float c = (MODE == Q_ZP) ? __fadd_rn(cq[j], z) : fminf(fmaxf(cq[j], -128.f), 127.f);
+              const uint32_t b = int_byte(c);
+              if ((j & 3) == 0) pk[j / 4] = b; else pk[j / 4] |= b << (8 * (j & 3));
+            }
+            if (V == 8) *reinterpret_cast<uint2*>(codes + row * cols + e) = make_uint2(pk[0], pk[V / 4 - 1]);
+            else *reinterpret_cast<uint32_t*>(codes + row * cols + e) = pk[0];
+          }
+        }
+      }
+    }
+  }
+}
+
 // One thread per row for tiny rows (conv weights viewed as [..., kw]: rows of 1..16 taps).
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kQThreads)
@@ -259,14 +581,19 @@ quant_flat_kernel(const T* __restrict__ x, int64_t numel, const T* __restrict__ 
   const int64_t tid = int64_t(blockIdx.x) * kQThreads + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * kQThreads;
   const int64_t nvec = vec_ok ? numel / V : 0;
+  const bool fast = fastdiv_ok<T>(s, ElemTraits<T>::to_f(absmax_dev[0]));
+  const float dummy[V] = {};
   for (int64_t i = tid; i < nvec; i += nthreads) {
     Vec16<T> v = ld_vec16_stream(x + i * V);
+    float xv[V], cq[V];
     Vec16<T> o;
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float code;
-      o.v[j] = ElemTraits<T>::from_f(rtn_elem<T>(ElemTraits<T>::to_f(v.v[j]), s, 0.f, 0.f, 0.f, false, false, code));
-      if (codes) codes[i * V + j] = code_to_i8<Q_SYM_NOCLAMP>(code);
+    for (int j = 0; j < V; ++j) xv[j] = ElemTraits<T>::to_f(v.v[j]);
+    if (fast) rtn_vec<T, Q_SYM_NOCLAMP, true, false, false>(xv, s, 0.f, 0.f, 0.f, dummy, dummy, o, cq);
+    else rtn_vec<T, Q_SYM_NOCLAMP, false, false, false>(xv, s, 0.f, 0.f, 0.f, dummy, dummy, o, cq);
+    if (codes) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) codes[i * V + j] = code_to_i8<Q_SYM_NOCLAMP>(cq[j]);
     }
     if (dq) st_vec16(dq + i * V, o);
   }
@@ -371,31 +698,83 @@ unpack_awq_kernel(const int32_t* __restrict__ qweight, int64_t n_words, int8_t* 
   }
 }
 
-// Fused zero-point RTN + AWQ pack.  Block tile: 64 out-rows x one group of K.
-// Phase 1 (lanes-per-group butterflies) leaves codes/scale/zero in shared memory,
-// phase 2 assembles the transposed int32 words.
+// Fused zero-point RTN + AWQ pack.  Block tile: kFuseTileN out-rows x one group of K.
+// Phase 1: every thread issues all of its 16-byte loads, group statistics by lanes-per-group butterflies,
+// the 8 k-consecutive 4-bit codes of a lane are packed into one word of shared memory.
+// Phase 2: a thread takes the 8 words of output word-column c (rows 8c + AWQ order) for one k-octet,
+// transposes the 8x8 nibble matrix in registers (3 butterfly stages) and stores 8 qweight words;
+// scales / zero points leave through shared memory as contiguous rows of the [G, N] outputs.
+constexpr int kFuseTileN = 128;
+
+__device__ __forceinline__ void nib_swap(uint32_t& a, uint32_t& b, int sh, uint32_t mask) {
+  const uint32_t t = ((a >> sh) ^ b) & mask;   // a = even member (keeps low blocks), b = odd member
+  b ^= t;
+  a ^= t << sh;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 quant_pack_awq_kernel(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, int group, float max_int,
                       int32_t* __restrict__ qweight, int32_t* __restrict__ qzeros,
                       T* __restrict__ scales_t, T* __restrict__ dq) {
   constexpr int V = ElemTraits<T>::kVec;
-  extern __shared__ uint8_t smem_raw[];
-  const int pitch = group + 4;
-  uint8_t* tile = smem_raw;                                  // [64][group + 4] codes
-  uint8_t* zsm = smem_raw + kPackTileN * pitch;              // [64] zero points
-  const int lpg = group / V;                                 // lanes per row of the tile
+  constexpr int kMaxPasses = kFuseTileN * 32 / 256;          // lpg <= 32
+  extern __shared__ uint32_t smem_w[];
+  const int lpg = group / V;                                 // lanes (vectors) per row of the tile
+  const int pitch = lpg + 1;
+  uint32_t* tile = smem_w;                                   // [kFuseTileN][lpg + 1] nibble-packed codes
+  T* ssm = reinterpret_cast<T*>(smem_w + kFuseTileN * pitch); // [kFuseTileN] scales
+  uint8_t* zsm = reinterpret_cast<uint8_t*>(ssm + kFuseTileN); // [kFuseTileN] zero points
   const int rows_per_pass = 256 / lpg;
-  const int64_t n0 = int64_t(blockIdx.y) * kPackTileN;
+  const int passes = kFuseTileN / rows_per_pass;
+  const int64_t n0 = int64_t(blockIdx.y) * kFuseTileN;
   const int64_t gi = blockIdx.x;                             // group index along K
   const int64_t k0 = gi * group;
-  const int sub = threadIdx.x % lpg;
-  for (int r = threadIdx.x / lpg; r < kPackTileN; r += rows_per_pass) {
-    const int64_t n = n0 + r;                                // n_rows % 64 == 0: always valid
-    Vec16<T> v = ld_vec16_stream(w + n * k_cols + k0 + sub * V);
+  const int sub = threadIdx.x % lpg, r0 = threadIdx.x / lpg;
+  const float r_max_int = rcp_approx(max_int);
+  Vec16<T> raw[kMaxPasses];
+#pragma unroll
+  for (int p = 0; p < kMaxPasses; ++p) {
+    const int64_t n = n0 + r0 + p * rows_per_pass;
+    if (p < passes && n < n_rows) raw[p] = ld_vec16_stream(w + n * k_cols + k0 + sub * V);
+  }
+#pragma unroll
+  for (int p = 0; p < kMaxPasses; ++p) {
+    if (p >= passes) break;                                  // uniform
+    const int r = r0 + p * rows_per_pass;
+    const int64_t n = n0 + r;
+    const bool valid = n < n_rows;
+    if constexpr (std::is_same<T, __half>::value) {
+      H2x4 x;
+      if (valid) x = as_h2x4(raw[p]);
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x.h[q] = __float2half2_rn(0.f);
+      }
+      float mx, mn, s, z, r_s;
+      minmax_h<Q_ZP>(x, lpg, mx, mn);
+      group_params_h<Q_ZP>(mx, mn, max_int, r_max_int, s, z, r_s);
+      if (sub == 0) {
+        ssm[r] = __float2half_rn(s);
+        zsm[r] = (uint8_t)int_byte(z);
+      }
+      H2x4 o, cq;
+      const float dummy8[8] = {};
+      rtn_vec_h<Q_ZP, false>(x, s, r_s, z, 0.f, max_int, dummy8, dummy8, o, cq);
+      // nibble j of the word = code of element j: codes sit in the mantissas of (c + 1536)
+      const __half2 z2 = __float2half2_rn(z), magic = __float2half2_rn(1536.f);
+      uint32_t pk = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t u = h2_bits(__hadd2(__hadd2(cq.h[q], z2), magic)) & 0x000F000Fu;
+        pk |= ((u | (u >> 12)) & 0xFFu) << (8 * q);
+      }
+      tile[r * pitch + sub] = pk;
+      if (dq && valid) *reinterpret_cast<uint4*>(dq + n * k_cols + k0 + sub * V) = *reinterpret_cast<const uint4*>(&o);
+    } else {
     float x[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) x[j] = ElemTraits<T>::to_f(v.v[j]);
+    for (int j = 0; j < V; ++j) x[j] = valid ? ElemTraits<T>::to_f(raw[p].v[j]) : 0.f;
     float mx = x[0], mn = x[0];
 #pragma unroll
     for (int j = 1; j < V; ++j) { mx = fmaxf(mx, x[j]); mn = fminf(mn, x[j]); }
@@ -406,58 +785,93 @@ quant_pack_awq_kernel(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, i
     float s, z;
     group_params<T, Q_ZP>(mx, mn, max_int, s, z);
     if (sub == 0) {
-      scales_t[gi * n_rows + n] = ElemTraits<T>::from_f(s);
-      zsm[r] = (uint8_t)__float2int_rn(z);
+      ssm[r] = ElemTraits<T>::from_f(s);
+      zsm[r] = (uint8_t)int_byte(z);
     }
+    float cq[V];
     Vec16<T> o;
+    const float dummy[V] = {};
+    if (fastdiv_ok<T>(s, fmaxf(fabsf(mx), fabsf(mn)))) rtn_vec<T, Q_ZP, true, false, false>(x, s, z, 0.f, max_int, dummy, dummy, o, cq);
+    else rtn_vec<T, Q_ZP, false, false, false>(x, s, z, 0.f, max_int, dummy, dummy, o, cq);
+    uint32_t pk = 0;
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float code;
-      o.v[j] = ElemTraits<T>::from_f(rtn_elem<T>(x[j], s, z, 0.f, max_int, true, true, code));
-      tile[r * pitch + sub * V + j] = (uint8_t)__float2int_rn(code);
+    for (int j = 0; j < V; ++j) pk |= (int_byte(__fadd_rn(cq[j], z)) & 0xFu) << (4 * j);   // V == 4 (fp32): low 4 nibbles
+    if (V == 8) {
+      tile[r * pitch + sub] = pk;
+    } else {                                                 // fp32: two lanes share one k-octet word
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, pk, 1);
+      if ((sub & 1) == 0) tile[r * pitch + (sub >> 1)] = pk | (other << 16);
     }
-    if (dq) st_vec16(dq + n * k_cols + k0 + sub * V, o);
+    if (dq && valid) st_vec16(dq + n * k_cols + k0 + sub * V, o);
   }
+    }
   __syncthreads();
   const int64_t words_per_row = n_rows / 8;
-  for (int idx = threadIdx.x; idx < group * 8; idx += 256) {
-    const int k = idx >> 3, c = idx & 7;
-    uint32_t word = 0;
+  const int octets = group / 8;                              // k-octets in the tile
+  constexpr int kWordCols = kFuseTileN / 8;                  // 16 packed words across the tile
+  for (int idx = threadIdx.x; idx < octets * kWordCols; idx += 256) {
+    const int kb = idx / kWordCols, c = idx % kWordCols;
+    if (n0 + 8 * c >= n_rows) continue;
+    uint32_t m[8];                                           // m[i] = row 8c + order[i]; nibble t = code at k = 8kb + t
 #pragma unroll
-    for (int i = 0; i < 8; ++i) word |= uint32_t(tile[(8 * c + kAwqOrder[i]) * pitch + k] & 0xF) << (4 * i);
-    qweight[(k0 + k) * words_per_row + n0 / 8 + c] = (int32_t)word;
+    for (int i = 0; i < 8; ++i) m[i] = tile[(8 * c + kAwqOrder[i]) * pitch + kb];
+    // 8x8 nibble transpose: afterwards m[t] nibble i = old m[i] nibble t
+    nib_swap(m[0], m[1], 4, 0x0F0F0F0Fu); nib_swap(m[2], m[3], 4, 0x0F0F0F0Fu);
+    nib_swap(m[4], m[5], 4, 0x0F0F0F0Fu); nib_swap(m[6], m[7], 4, 0x0F0F0F0Fu);
+    nib_swap(m[0], m[2], 8, 0x00FF00FFu); nib_swap(m[1], m[3], 8, 0x00FF00FFu);
+    nib_swap(m[4], m[6], 8, 0x00FF00FFu); nib_swap(m[5], m[7], 8, 0x00FF00FFu);
+    nib_swap(m[0], m[4], 16, 0x0000FFFFu); nib_swap(m[1], m[5], 16, 0x0000FFFFu);
+    nib_swap(m[2], m[6], 16, 0x0000FFFFu); nib_swap(m[3], m[7], 16, 0x0000FFFFu);
+    int32_t* dst = qweight + (k0 + 8 * kb) * words_per_row + n0 / 8 + c;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dst[t * words_per_row] = (int32_t)m[t];
   }
-  if (threadIdx.x < 8) {
+  const int rows_here = (n_rows - n0) < kFuseTileN ? int(n_rows - n0) : kFuseTileN;
+  if (threadIdx.x < kWordCols && 8 * int(threadIdx.x) < rows_here) {
     const int c = threadIdx.x;
     uint32_t word = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) word |= uint32_t(zsm[8 * c + kAwqOrder[i]] & 0xF) << (4 * i);
     qzeros[gi * words_per_row + n0 / 8 + c] = (int32_t)word;
   }
+  for (int r = threadIdx.x; r < rows_here; r += 256) scales_t[gi * n_rows + n0 + r] = ssm[r];
 }
 
-// W_kn[k, 8c + j] = (q - z) * s, one packed word (8 outputs, one 16-byte store for 2-byte T) per thread
+// W_kn[k, 8c + j] = (q - z) * s, one packed word (8 outputs, 16-byte scale load and store for 2-byte T)
+// per thread.  q - z is formed exactly in fp32 from the nibble without an I2F: the nibble is or-ed into the
+// mantissa of 2^23 and (2^23 + z) subtracted.
 template <typename T>
 __global__ void __launch_bounds__(256)
 dequant_awq_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
-                   const T* __restrict__ scales, int64_t k_rows, int64_t n_words, int group,
+                   const T* __restrict__ scales, uint32_t total_words, uint32_t n_words, uint32_t group,
                    T* __restrict__ out) {
-  const int64_t total = k_rows * n_words;
-  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < total; i += int64_t(gridDim.x) * 256) {
-    const int64_t k = i / n_words, c = i % n_words;
-    const uint32_t qw = (uint32_t)qweight[i];
-    const uint32_t zw = (uint32_t)qzeros[(k / group) * n_words + c];
-    const T* sp = scales + (k / group) * n_words * 8 + c * 8;
-    T o[8];
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total_words; i += gridDim.x * 256u) {
+    const uint32_t k = i / n_words, c = i - k * n_words;
+    const uint32_t g = k / group;
+    const uint32_t qw = (uint32_t)__ldg(qweight + i);
+    const uint32_t zw = (uint32_t)__ldg(qzeros + g * n_words + c);
+    const T* sp = scales + (int64_t(g) * n_words + c) * 8;
+    T* dst = out + int64_t(i) * 8;
+    T sv[8], o[8];
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(sv) = *reinterpret_cast<const uint4*>(sp);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sv[j] = sp[j];
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int q = (qw >> (4 * j)) & 0xF, z = (zw >> (4 * j)) & 0xF;
-      const int col = kAwqOrder[j];
-      o[col] = ElemTraits<T>::from_f(__fmul_rn(float(q - z), ElemTraits<T>::to_f(sp[col])));
+      const float qf = __uint_as_float(((qw >> (4 * j)) & 0xFu) | 0x4B000000u);
+      const float zf = __uint_as_float(((zw >> (4 * j)) & 0xFu) | 0x4B000000u);
+      const int col = 2 * (j & 3) + (j >> 2);                // AWQ order {0,2,4,6,1,3,5,7}[j]
+      o[col] = ElemTraits<T>::from_f(__fmul_rn(__fsub_rn(qf, zf), ElemTraits<T>::to_f(sv[col])));
     }
-    T* dst = out + k * n_words * 8 + c * 8;
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = o[j];
+      for (int j = 0; j < 8; ++j) dst[j] = o[j];
+    }
   }
 }
 
@@ -467,6 +881,34 @@ int grid_for(int64_t work_items, int per_block) {
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return int(b);
+}
+
+template <typename T, int MODE, bool I8OUT>
+int launch_rows_reg(const T* x, int64_t rows, int64_t cols, float max_int, float min_int,
+                    T* dq, int8_t* codes, T* scales, T* zeros, float* sx, cudaStream_t st) {
+  constexpr int V = ElemTraits<T>::kVec;
+  const int64_t nv = (cols + 32 * V - 1) / (32 * V);
+  // persistent grid: the CTAs the device holds at once (equal work per CTA, no partial last wave)
+#define QDM_ROWS_REG(NV)                                                                              \
+  do {                                                                                                \
+    static int occ = 0;                                                                               \
+    if (occ == 0) {                                                                                   \
+      QDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quant_rows_reg_kernel<T, MODE, NV, I8OUT>, kQThreads, 0)); \
+      if (occ < 1) occ = 1;                                                                           \
+    }                                                                                                 \
+    int64_t grid = (rows + kQThreads / 32 - 1) / (kQThreads / 32);                                    \
+    if (grid > int64_t(QDM_NUM_SMS) * occ) grid = int64_t(QDM_NUM_SMS) * occ;                         \
+    quant_rows_reg_kernel<T, MODE, NV, I8OUT><<<(unsigned)grid, kQThreads, 0, st>>>(x, rows, int(cols), max_int, min_int, \
+                                                                          dq, codes, scales, zeros, sx); \
+  } while (0)
+  if (nv <= 1) QDM_ROWS_REG(1);
+  else if (nv <= 2) QDM_ROWS_REG(2);
+  else if (nv <= 4) QDM_ROWS_REG(4);
+  else if (nv <= 8) QDM_ROWS_REG(8);
+  else QDM_ROWS_REG(16);
+#undef QDM_ROWS_REG
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
 }
 
 template <typename T, int MODE>
@@ -481,13 +923,39 @@ int launch_quant(const T* w, int64_t n_groups, int64_t group, int64_t k_period, 
                        (!post_div || qdm_aligned16(post_div)) &&
                        (!codes || (reinterpret_cast<uintptr_t>(codes) & 7u) == 0);
   const int64_t lpg = group / V;
-  if (aligned && group % V == 0 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && k_period % V == 0) {
-    const int64_t n_vec = numel / V;
-    quant_group_kernel<T, MODE><<<grid_for(n_vec, kQThreads), kQThreads, 0, st>>>(
-        w, n_vec, k_period, int(lpg), max_int, min_int, pre_mul, clip_max, post_div, dq, codes, scales, zeros);
-  } else if (group <= 16 && !pre_mul && !clip_max && !post_div) {
+  const int64_t n_rows = numel / k_period;
+  const bool extras = pre_mul || clip_max || post_div;
+  if (aligned && group % V == 0 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && n_rows < (int64_t(1) << 31) &&
+      k_period / V < (int64_t(1) << 20)) {
+    const int64_t vpr = k_period / V;
+    int lpg_shift = 0;
+    while ((int64_t(1) << lpg_shift) < lpg) ++lpg_shift;
+    // persistent grid = exactly the CTAs the device holds at once (no partial second wave), and whole
+    // passes so that every pass covers the same number of rows
+    static int occ_plain = 0, occ_extras = 0;
+    int& occ = extras ? occ_extras : occ_plain;
+    if (occ == 0) {
+      if (extras) QDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quant_group_kernel<T, MODE, true>, kQThreads, 0));
+      else QDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quant_group_kernel<T, MODE, false>, kQThreads, 0));
+      if (occ < 1) occ = 1;
+    }
+    const int64_t target_threads = int64_t(QDM_NUM_SMS) * occ * kQThreads;
+    int64_t r_max = target_threads / vpr;
+    if (r_max < 1) r_max = 1;
+    const int64_t passes = (n_rows + r_max - 1) / r_max;
+    const int64_t rpp = (n_rows + passes - 1) / passes;
+    const unsigned grid = (unsigned)((rpp * vpr + kQThreads - 1) / kQThreads);
+    if (extras)
+      quant_group_kernel<T, MODE, true><<<grid, kQThreads, 0, st>>>(
+          w, int(n_rows), int(vpr), lpg_shift, int(rpp), max_int, min_int, pre_mul, clip_max, post_div, dq, codes, scales, zeros);
+    else
+      quant_group_kernel<T, MODE, false><<<grid, kQThreads, 0, st>>>(
+          w, int(n_rows), int(vpr), lpg_shift, int(rpp), max_int, min_int, nullptr, nullptr, nullptr, dq, codes, scales, zeros);
+  } else if (group <= 16 && !extras) {
     quant_rows_thread_kernel<T, MODE><<<grid_for(n_groups, kQThreads), kQThreads, 0, st>>>(
         w, n_groups, int(group), max_int, min_int, dq, codes, scales, zeros);
+  } else if (aligned && !extras && group % V == 0 && group <= 32 * V * 16) {
+    return launch_rows_reg<T, MODE, false>(w, n_groups, group, max_int, min_int, dq, codes, scales, zeros, nullptr, st);
   } else {
     const int vec_ok = aligned && group % V == 0;
     quant_rows_warp_kernel<T, MODE><<<grid_for(n_groups, kQThreads / 32), kQThreads, 0, st>>>(
@@ -562,6 +1030,9 @@ extern "C" int qdm_actquant_token_i8(const void* x, int dtype, int64_t rows, int
   QDM_DISPATCH_DTYPE(dtype, {
     constexpr int V = ElemTraits<T>::kVec;
     const int vec_ok = qdm_aligned16(x) && cols % V == 0 && (reinterpret_cast<uintptr_t>(xq) & 7u) == 0;
+    if (vec_ok && !smooth && cols <= 32 * V * 16)
+      return (launch_rows_reg<T, Q_SYM_NOCLAMP, true>((const T*)x, rows, cols, 127.f, -128.f, nullptr, xq, nullptr,
+                                                      nullptr, sx, st));
     actquant_token_i8_kernel<T><<<grid_for(rows, kQThreads / 32), kQThreads, 0, st>>>(
         (const T*)x, rows, cols, (const T*)smooth, xq, sx, vec_ok);
     QDM_LAUNCH_CHECK();
@@ -624,17 +1095,17 @@ extern "C" int qdm_quant_pack_awq(const void* w, int dtype, int64_t n_rows, int6
   QDM_REQUIRE(w && qweight && qzeros && scales_t, "qdm_quant_pack_awq: null pointer");
   QDM_REQUIRE(n_rows > 0 && k_cols > 0 && group > 0 && k_cols % group == 0,
               "qdm_quant_pack_awq: group %d must divide k_cols %lld", group, (long long)k_cols);
-  QDM_REQUIRE(n_rows % kPackTileN == 0, "qdm_quant_pack_awq: n_rows %lld must be a multiple of 64", (long long)n_rows);
+  QDM_REQUIRE(n_rows % 8 == 0, "qdm_quant_pack_awq: n_rows %lld must be a multiple of 8", (long long)n_rows);
   QDM_REQUIRE(qdm_aligned16(w) && (!dq || qdm_aligned16(dq)), "qdm_quant_pack_awq: tensors must be 16-byte aligned");
   QDM_DEVICE_GATE();
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, {
     constexpr int V = ElemTraits<T>::kVec;
     const int lpg = group / V;
-    QDM_UNSUPPORTED(group % V == 0 && lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && group <= 256,
+    QDM_UNSUPPORTED(group % V == 0 && group >= 32 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && group <= 256,
                     "qdm_quant_pack_awq: group %d unsupported for this dtype", group);
-    dim3 grid((unsigned)(k_cols / group), (unsigned)(n_rows / kPackTileN));
-    const size_t smem = size_t(kPackTileN) * (group + 4) + kPackTileN;
+    dim3 grid((unsigned)(k_cols / group), (unsigned)((n_rows + kFuseTileN - 1) / kFuseTileN));
+    const size_t smem = size_t(kFuseTileN) * (lpg + 1) * 4 + size_t(kFuseTileN) * sizeof(T) + kFuseTileN;
     quant_pack_awq_kernel<T><<<grid, 256, smem, st>>>((const T*)w, n_rows, k_cols, group, 15.f, qweight, qzeros,
                                                       (T*)scales_t, (T*)dq);
     QDM_LAUNCH_CHECK();
@@ -647,13 +1118,61 @@ extern "C" int qdm_dequant_awq(const int32_t* qweight, const int32_t* qzeros, co
   QDM_REQUIRE(qweight && qzeros && scales_t && out_kn, "qdm_dequant_awq: null pointer");
   QDM_REQUIRE(k_rows > 0 && n_cols > 0 && n_cols % 8 == 0 && group > 0 && k_rows % group == 0,
               "qdm_dequant_awq: bad shape K=%lld N=%lld group=%d", (long long)k_rows, (long long)n_cols, group);
+  QDM_REQUIRE(qdm_aligned16(scales_t) && qdm_aligned16(out_kn), "qdm_dequant_awq: scales / out must be 16-byte aligned");
+  const int64_t total = k_rows * (n_cols / 8);
+  QDM_UNSUPPORTED(total < (int64_t(1) << 32) - 256 * int64_t(QDM_NUM_SMS) * 16, "qdm_dequant_awq: more than 2^32 packed words");
   QDM_DEVICE_GATE();
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, {
-    const int64_t total = k_rows * (n_cols / 8);
-    dequant_awq_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(qweight, qzeros, (const T*)scales_t, k_rows,
-                                                               n_cols / 8, group, (T*)out_kn);
+    dequant_awq_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(qweight, qzeros, (const T*)scales_t, (uint32_t)total,
+                                                               (uint32_t)(n_cols / 8), (uint32_t)group, (T*)out_kn);
     QDM_LAUNCH_CHECK();
   });
+  return QDM_OK;
+}
+
+// ---------------------------------------------------------------- self test of the reciprocal division
+namespace {
+template <typename T> struct BitsOf;
+template <> struct BitsOf<__half> {
+  static __device__ float f(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+  static constexpr int kMaxFinite = 0x7BFF;
+};
+template <> struct BitsOf<__nv_bfloat16> {
+  static __device__ float f(uint16_t b) { return __uint_as_float(uint32_t(b) << 16); }
+  static constexpr int kMaxFinite = 0x7F7F;
+};
+// block = one positive finite divisor (by bit pattern), threads sweep all 65536 dividend patterns
+template <typename T>
+__global__ void fastdiv_selftest_kernel(unsigned long long* out) {
+  const float s = BitsOf<T>::f(uint16_t(blockIdx.x + 1));
+  const float r = rcp_approx(s);
+  unsigned long long tested = 0, bad = 0;
+  for (int wb = threadIdx.x; wb < 65536; wb += blockDim.x) {
+    const float w = BitsOf<T>::f(uint16_t(wb));
+    if (!(fabsf(w) <= 3.4e38f)) continue;                      // inf / nan patterns
+    if (!fastdiv_ok<T>(s, fabsf(w))) continue;                 // outside the window the kernels use __fdiv_rn
+    ++tested;
+    const float ref = rnd<T>(__fdiv_rn(w, s)), got = rnd<T>(div_by_rcp<true>(w, s, r));
+    if (__float_as_uint(ref) != __float_as_uint(got)) ++bad;
+  }
+  atomicAdd(&out[0], tested);
+  if (bad) atomicAdd(&out[1], bad);
+}
+}  // namespace
+
+extern "C" int qdm_selftest_fastdiv(int dtype, uint64_t* out_host) {
+  QDM_REQUIRE(out_host, "qdm_selftest_fastdiv: null pointer");
+  QDM_REQUIRE(dtype == QDM_F16 || dtype == QDM_BF16, "qdm_selftest_fastdiv: dtype must be f16 or bf16");
+  QDM_DEVICE_GATE();
+  unsigned long long* d = nullptr;
+  QDM_CUDA_OK(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+  if (dtype == QDM_F16) fastdiv_selftest_kernel<__half><<<BitsOf<__half>::kMaxFinite, 256>>>(d);
+  else fastdiv_selftest_kernel<__nv_bfloat16><<<BitsOf<__nv_bfloat16>::kMaxFinite, 256>>>(d);
+  cudaError_t e = cudaMemcpy(out_host, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { qdm_set_error("qdm_selftest_fastdiv: %s", cudaGetErrorString(e)); return QDM_ERR_CUDA; }
+  qdm_count_launch();
   return QDM_OK;
 }

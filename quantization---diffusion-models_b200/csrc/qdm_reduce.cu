@@ -101,9 +101,10 @@ __global__ void col_reduce_stage2(const float* __restrict__ partial, int splits,
   out[c] = ElemTraits<TOut>::from_f(v);  // exact for absmax: v is a value of the input dtype
 }
 
-int col_splits(int64_t rows, int64_t col_blocks) {
-  // ~4 CTAs per SM in flight, at least 8 rows per CTA, at most 256 splits
-  int64_t want = (int64_t(QDM_NUM_SMS) * 4 + col_blocks - 1) / col_blocks;
+int col_splits(int64_t rows, int64_t col_blocks, int ctas_per_sm = 4) {
+  // ~ctas_per_sm CTAs per SM in flight, at least 8 rows per CTA, at most 256 splits
+  int64_t want = (int64_t(QDM_NUM_SMS) * ctas_per_sm) / col_blocks;
+  if (want < 1) want = 1;
   int64_t max_by_rows = (rows + kColWarps - 1) / kColWarps;
   int64_t s = want < max_by_rows ? want : max_by_rows;
   if (s < 1) s = 1;
@@ -219,12 +220,21 @@ sqdiff_stage1(const T* __restrict__ a, const T* __restrict__ b, int64_t numel,
   };
   if (vec_ok) {
     const int64_t nvec = numel / V;
-    for (int64_t i = tid; i < nvec; i += nthreads) {
+    int64_t i = tid;
+    for (; i + nthreads < nvec; i += 2 * nthreads) {           // four 16-byte loads in flight per thread
+      Vec16<T> va = ld_vec16_stream(a + i * V), vb = ld_vec16_stream(b + i * V);
+      Vec16<T> vc = ld_vec16_stream(a + (i + nthreads) * V), vd = ld_vec16_stream(b + (i + nthreads) * V);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc += term(va.v[j], vb.v[j]);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc += term(vc.v[j], vd.v[j]);
+    }
+    if (i < nvec) {
       Vec16<T> va = ld_vec16_stream(a + i * V), vb = ld_vec16_stream(b + i * V);
 #pragma unroll
       for (int j = 0; j < V; ++j) acc += term(va.v[j], vb.v[j]);
     }
-    for (int64_t i = nvec * V + tid; i < numel; i += nthreads) acc += term(a[i], b[i]);
+    for (int64_t i2 = nvec * V + tid; i2 < numel; i2 += nthreads) acc += term(a[i2], b[i2]);
   } else {
     for (int64_t i = tid; i < numel; i += nthreads) acc += term(a[i], b[i]);
   }
@@ -271,11 +281,11 @@ awq_wsum_stage1(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, int lan
   float acc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
-  for (int64_t r = int64_t(blockIdx.y) * kColWarps + warp; r < n_rows; r += int64_t(gridDim.y) * kColWarps) {
+  // one row of the group statistics + normalised accumulation; `have` is warp-uniform per row
+  auto row_step = [&](const Vec16<T>& v, bool have) {
     float a[V];
     float m = 0.f;
-    if (active) {
-      Vec16<T> v = ld_vec16_stream(w + r * k_cols + c0);
+    if (have && active) {
 #pragma unroll
       for (int i = 0; i < V; ++i) { a[i] = fabsf(ElemTraits<T>::to_f(v.v[i])); m = fmaxf(m, a[i]); }
     } else {
@@ -284,8 +294,23 @@ awq_wsum_stage1(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, int lan
     }
     for (int o = 1; o < lanes_per_group; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     const float denom = rnd<T>(__fadd_rn(m, 1e-6f));  // amax + 1e-6 (python scalar), rounded to dtype
+    if (fastdiv_ok<T>(denom, m)) {                    // reciprocal division, exact (qdm_common.cuh)
+      const float rd = rcp_approx(denom);
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] += rnd<T>(__fdiv_rn(a[i], denom));
+      for (int i = 0; i < V; ++i) acc[i] += rnd<T>(div_by_rcp<false>(a[i], denom, rd));
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += rnd<T>(__fdiv_rn(a[i], denom));
+    }
+  };
+  const int64_t step = int64_t(gridDim.y) * kColWarps;
+  for (int64_t r = int64_t(blockIdx.y) * kColWarps + warp; r < n_rows; r += 2 * step) {   // two loads in flight
+    const bool two = r + step < n_rows;
+    Vec16<T> va, vb;
+    if (active) va = ld_vec16_stream(w + r * k_cols + c0);
+    if (active && two) vb = ld_vec16_stream(w + (r + step) * k_cols + c0);
+    row_step(va, true);
+    if (two) row_step(vb, true);
   }
   __shared__ float sm[kColWarps][32 * V + 1];
 #pragma unroll
@@ -423,7 +448,7 @@ extern "C" int qdm_awq_wsum(const void* w, int dtype, int64_t n_rows, int64_t k_
     QDM_UNSUPPORTED(group % V == 0 && lpg >= 1 && lpg <= 32 && (lpg & (lpg - 1)) == 0,
                     "qdm_awq_wsum: group %d unsupported (need %d*2^j <= %d)", group, V, 32 * V);
     const int64_t col_blocks = (k_cols + 32 * V - 1) / (32 * V);
-    const int splits = col_splits(n_rows, col_blocks);
+    const int splits = col_splits(n_rows, col_blocks, 8);
     QDM_REQUIRE(workspace_bytes >= size_t(splits) * k_cols * sizeof(float), "qdm_awq_wsum: workspace too small");
     dim3 grid((unsigned)col_blocks, (unsigned)splits);
     awq_wsum_stage1<T><<<grid, kColThreads, 0, st>>>((const T*)w, n_rows, k_cols, lpg, (float*)workspace);

@@ -289,7 +289,7 @@ def quant_pack_awq(w, group, want_dq=False):
         raise ValueError(f"group {group} must divide K={k}")
     if n % 8:
         raise ValueError(f"N={n} must be a multiple of 8")
-    if n % 64 or group not in (32, 64, 128, 256) or (w.dtype == torch.float32 and group > 128):
+    if group not in (32, 64, 128, 256) or (w.dtype == torch.float32 and group > 128):
         # shapes the fused kernel does not tile: same result from the unfused kernels
         dq, codes, s, z = quant_group(wc, group, 4, zero_point=True, want_dq=want_dq, want_codes=True)
         return pack_awq(codes), pack_awq(z.to(torch.int8)), s.t().contiguous(), dq

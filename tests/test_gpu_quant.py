@@ -139,7 +139,8 @@ def test_actquant_token_i8(qdm, dt):
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
-@pytest.mark.parametrize("N,K,group", [(128, 256, 128), (192, 320, 64), (64, 128, 32), (2432, 2432, 128), (72, 192, 64)])
+@pytest.mark.parametrize("N,K,group", [(128, 256, 128), (192, 320, 64), (64, 128, 32), (2432, 2432, 128), (72, 192, 64),
+                                         (320, 320, 64), (8, 256, 256), (1288, 384, 128)])
 def test_quant_pack_awq_vs_oracle(qdm, dt, N, K, group):
     w = rand_w((N, K), DT[dt], 21)
     qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(w.to(DEV), group, want_dq=True)
@@ -152,6 +153,41 @@ def test_quant_pack_awq_vs_oracle(qdm, dt, N, K, group):
     deq = qdm.ops.dequant_awq(qweight, qzeros, scales, group)
     assert_bit_equal(deq, O.awq_dequant(oq, oz, os_, group), "dequant")
     assert_bit_equal(deq.t().contiguous(), odq, "dequant == fake-quant weight")
+
+
+def test_fastdiv_exhaustive(qdm):
+    """The quantise kernels divide by `reciprocal + two FMAs` instead of IEEE division.  The library sweeps every
+    (dividend, divisor) pair of 16-bit values inside the window where that path is taken and compares with
+    __fdiv_rn after the dtype rounding: 0 differences allowed (csrc/qdm_common.cuh)."""
+    import ctypes
+    for dt, min_pairs in ((qdm._lib.QDM_F16, 31743 * 63488), (qdm._lib.QDM_BF16, 6 * 10 ** 8)):
+        out = (ctypes.c_uint64 * 2)()
+        qdm._lib.check(qdm._lib.load().qdm_selftest_fastdiv(dt, ctypes.cast(out, ctypes.c_void_p)))
+        assert out[0] >= min_pairs, out[0]
+        assert out[1] == 0, f"{out[1]} of {out[0]} quotients differ from IEEE division"
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_quant_group_wide_range_and_signed_zero(qdm, dt):
+    """Rows whose groups sit far from the unit range (tiny, huge, constant, one-sided) and the sign of the zeros
+    torch.round produces in the symmetric modes: bit patterns, not just values, must match the oracle."""
+    g = torch.Generator().manual_seed(77)
+    w = torch.randn(64, 512, generator=g)
+    w[0] *= 1e-7; w[1] *= 5e3 if dt == "f16" else 1e30; w[2] = 1.0; w[3] = w[3].abs() + 5.0
+    w[4] *= 1e-3; w[5, ::2] = 0.0; w[6] = -1e-6; w[7] = (w[7].abs() * 1e4 + 1e4) if dt == "f16" else w[7] * 1e37
+    w[8, ::3] = -0.0; w[9] = 0.0; w[10] = -0.0
+    w = w.clamp(-6e4, 6e4).to(DT[dt]) if dt == "f16" else w.to(DT[dt])
+    for zp, nc in ((True, False), (False, False), (False, True)):
+        dq = qdm.ops.quant_group(w.to(DEV), 128, 4, zero_point=zp, no_clamp=nc)[0]
+        if nc:                                        # fake_quant.py:75 returns fp16 whatever the input dtype
+            dq, ref = dq.to(torch.float16), O.rtn_absmax_group(w, 4, 128)[0]
+        else:
+            ref = O.rtn_group(w, 128, zp, 4)[0]
+        dq = dq.cpu()
+        assert torch.equal(dq.isnan(), ref.isnan())
+        ok = ~ref.isnan()
+        a, b = dq.view(torch.int16)[ok], ref.view(torch.int16)[ok]
+        assert torch.equal(a, b), f"zp={zp} nc={nc}: {(a != b).sum().item()} bit patterns differ"
 
 
 # ------------------------------------------------------------------ (a) reductions
