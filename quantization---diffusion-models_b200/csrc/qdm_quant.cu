@@ -111,7 +111,14 @@ __device__ __forceinline__ void reduce_h(__half2 m2, __half2 n2, int lpg, float&
   __half2 p;
   if (MODE == Q_ZP) p = __halves2half2(__hmax(__low2half(m2), __high2half(m2)), __hneg(__hmin(__low2half(n2), __high2half(n2))));
   else p = __hmax2(m2, __lowhigh2highlow(m2));
-  for (int o = 1; o < lpg; o <<= 1) p = __hmax2(p, __shfl_xor_sync(0xffffffffu, p, o));
+  switch (lpg) {                                   // xor-butterfly steps commute: fall through from the widest
+    case 32: p = __hmax2(p, __shfl_xor_sync(0xffffffffu, p, 16));
+    case 16: p = __hmax2(p, __shfl_xor_sync(0xffffffffu, p, 8));
+    case 8: p = __hmax2(p, __shfl_xor_sync(0xffffffffu, p, 4));
+    case 4: p = __hmax2(p, __shfl_xor_sync(0xffffffffu, p, 2));
+    case 2: p = __hmax2(p, __shfl_xor_sync(0xffffffffu, p, 1));
+    default: break;
+  }
   mx = __low2float(p);
   mn = (MODE == Q_ZP) ? -__high2float(p) : 0.f;
 }
@@ -712,38 +719,38 @@ __device__ __forceinline__ void nib_swap(uint32_t& a, uint32_t& b, int sh, uint3
   a ^= t << sh;
 }
 
-template <typename T>
+template <typename T, int LPG>                               // LPG = lanes (16-byte vectors) per group row
 __global__ void __launch_bounds__(256)
-quant_pack_awq_kernel(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, int group, float max_int,
+quant_pack_awq_kernel(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, float max_int,
                       int32_t* __restrict__ qweight, int32_t* __restrict__ qzeros,
                       T* __restrict__ scales_t, T* __restrict__ dq) {
   constexpr int V = ElemTraits<T>::kVec;
-  constexpr int kMaxPasses = kFuseTileN * 32 / 256;          // lpg <= 32
-  extern __shared__ uint32_t smem_w[];
-  const int lpg = group / V;                                 // lanes (vectors) per row of the tile
-  const int pitch = lpg + 1;
-  uint32_t* tile = smem_w;                                   // [kFuseTileN][lpg + 1] nibble-packed codes
-  T* ssm = reinterpret_cast<T*>(smem_w + kFuseTileN * pitch); // [kFuseTileN] scales
-  uint8_t* zsm = reinterpret_cast<uint8_t*>(ssm + kFuseTileN); // [kFuseTileN] zero points
-  const int rows_per_pass = 256 / lpg;
-  const int passes = kFuseTileN / rows_per_pass;
+  constexpr int kGroup = LPG * V;
+  constexpr int kRowsPerPass = 256 / LPG;
+  constexpr int kPasses = kFuseTileN / kRowsPerPass;
+  constexpr int kPitch = LPG + 1;
+  constexpr int kOctets = kGroup / 8;                        // k-octets (packed words per row) in the tile
+  __shared__ uint32_t tile[kFuseTileN * kPitch];             // nibble-packed codes, one word per k-octet
+  __shared__ T ssm[kFuseTileN];                              // scales
+  __shared__ uint8_t zsm[kFuseTileN];                        // zero points
   const int64_t n0 = int64_t(blockIdx.y) * kFuseTileN;
   const int64_t gi = blockIdx.x;                             // group index along K
-  const int64_t k0 = gi * group;
-  const int sub = threadIdx.x % lpg, r0 = threadIdx.x / lpg;
+  const int64_t k0 = gi * kGroup;
+  const int sub = threadIdx.x % LPG, r0 = threadIdx.x / LPG;
+  const int rows_here = (n_rows - n0) < kFuseTileN ? int(n_rows - n0) : kFuseTileN;
   const float r_max_int = rcp_approx(max_int);
-  Vec16<T> raw[kMaxPasses];
+  const T* src = w + (n0 + r0) * k_cols + k0 + sub * V;
+  T* dst_dq = dq ? dq + (n0 + r0) * k_cols + k0 + sub * V : nullptr;
+  const int64_t pass_stride = int64_t(kRowsPerPass) * k_cols;
+  Vec16<T> raw[kPasses];
 #pragma unroll
-  for (int p = 0; p < kMaxPasses; ++p) {
-    const int64_t n = n0 + r0 + p * rows_per_pass;
-    if (p < passes && n < n_rows) raw[p] = ld_vec16_stream(w + n * k_cols + k0 + sub * V);
-  }
+  for (int p = 0; p < kPasses; ++p)
+    if (r0 + p * kRowsPerPass < rows_here) raw[p] = ld_vec16_stream(src + p * pass_stride);
 #pragma unroll
-  for (int p = 0; p < kMaxPasses; ++p) {
-    if (p >= passes) break;                                  // uniform
-    const int r = r0 + p * rows_per_pass;
-    const int64_t n = n0 + r;
-    const bool valid = n < n_rows;
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = r0 + p * kRowsPerPass;
+    const bool valid = r < rows_here;
+    uint32_t pk = 0;
     if constexpr (std::is_same<T, __half>::value) {
       H2x4 x;
       if (valid) x = as_h2x4(raw[p]);
@@ -752,7 +759,7 @@ quant_pack_awq_kernel(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, i
         for (int q = 0; q < 4; ++q) x.h[q] = __float2half2_rn(0.f);
       }
       float mx, mn, s, z, r_s;
-      minmax_h<Q_ZP>(x, lpg, mx, mn);
+      minmax_h<Q_ZP>(x, LPG, mx, mn);
       group_params_h<Q_ZP>(mx, mn, max_int, r_max_int, s, z, r_s);
       if (sub == 0) {
         ssm[r] = __float2half_rn(s);
@@ -761,60 +768,57 @@ quant_pack_awq_kernel(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, i
       H2x4 o, cq;
       const float dummy8[8] = {};
       rtn_vec_h<Q_ZP, false>(x, s, r_s, z, 0.f, max_int, dummy8, dummy8, o, cq);
-      // nibble j of the word = code of element j: codes sit in the mantissas of (c + 1536)
-      const __half2 z2 = __float2half2_rn(z), magic = __float2half2_rn(1536.f);
-      uint32_t pk = 0;
+      // nibble j of the word = code of element j: the codes sit in the mantissas of (c + 1536)
+      const __half2 zm = __float2half2_rn(__fadd_rn(z, 1536.f));
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t u = h2_bits(__hadd2(__hadd2(cq.h[q], z2), magic)) & 0x000F000Fu;
+        const uint32_t u = h2_bits(__hadd2(cq.h[q], zm)) & 0x000F000Fu;
         pk |= ((u | (u >> 12)) & 0xFFu) << (8 * q);
       }
-      tile[r * pitch + sub] = pk;
-      if (dq && valid) *reinterpret_cast<uint4*>(dq + n * k_cols + k0 + sub * V) = *reinterpret_cast<const uint4*>(&o);
+      if (dst_dq && valid) *reinterpret_cast<uint4*>(dst_dq + p * pass_stride) = *reinterpret_cast<const uint4*>(&o);
     } else {
-    float x[V];
+      float x[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) x[j] = valid ? ElemTraits<T>::to_f(raw[p].v[j]) : 0.f;
-    float mx = x[0], mn = x[0];
+      for (int j = 0; j < V; ++j) x[j] = valid ? ElemTraits<T>::to_f(raw[p].v[j]) : 0.f;
+      float mx = x[0], mn = x[0];
 #pragma unroll
-    for (int j = 1; j < V; ++j) { mx = fmaxf(mx, x[j]); mn = fminf(mn, x[j]); }
-    for (int o = 1; o < lpg; o <<= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      for (int j = 1; j < V; ++j) { mx = fmaxf(mx, x[j]); mn = fminf(mn, x[j]); }
+#pragma unroll
+      for (int o = 1; o < LPG; o <<= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      }
+      float s, z;
+      group_params<T, Q_ZP>(mx, mn, max_int, s, z);
+      if (sub == 0) {
+        ssm[r] = ElemTraits<T>::from_f(s);
+        zsm[r] = (uint8_t)int_byte(z);
+      }
+      float cq[V];
+      Vec16<T> o;
+      const float dummy[V] = {};
+      if (fastdiv_ok<T>(s, fmaxf(fabsf(mx), fabsf(mn)))) rtn_vec<T, Q_ZP, true, false, false>(x, s, z, 0.f, max_int, dummy, dummy, o, cq);
+      else rtn_vec<T, Q_ZP, false, false, false>(x, s, z, 0.f, max_int, dummy, dummy, o, cq);
+#pragma unroll
+      for (int j = 0; j < V; ++j) pk |= (int_byte(__fadd_rn(cq[j], z)) & 0xFu) << (4 * j);
+      if (dst_dq && valid) st_vec16(dst_dq + p * pass_stride, o);
     }
-    float s, z;
-    group_params<T, Q_ZP>(mx, mn, max_int, s, z);
-    if (sub == 0) {
-      ssm[r] = ElemTraits<T>::from_f(s);
-      zsm[r] = (uint8_t)int_byte(z);
-    }
-    float cq[V];
-    Vec16<T> o;
-    const float dummy[V] = {};
-    if (fastdiv_ok<T>(s, fmaxf(fabsf(mx), fabsf(mn)))) rtn_vec<T, Q_ZP, true, false, false>(x, s, z, 0.f, max_int, dummy, dummy, o, cq);
-    else rtn_vec<T, Q_ZP, false, false, false>(x, s, z, 0.f, max_int, dummy, dummy, o, cq);
-    uint32_t pk = 0;
-#pragma unroll
-    for (int j = 0; j < V; ++j) pk |= (int_byte(__fadd_rn(cq[j], z)) & 0xFu) << (4 * j);   // V == 4 (fp32): low 4 nibbles
     if (V == 8) {
-      tile[r * pitch + sub] = pk;
+      tile[r * kPitch + sub] = pk;
     } else {                                                 // fp32: two lanes share one k-octet word
       const uint32_t other = __shfl_xor_sync(0xffffffffu, pk, 1);
-      if ((sub & 1) == 0) tile[r * pitch + (sub >> 1)] = pk | (other << 16);
+      if ((sub & 1) == 0) tile[r * kPitch + (sub >> 1)] = pk | (other << 16);
     }
-    if (dq && valid) st_vec16(dq + n * k_cols + k0 + sub * V, o);
   }
-    }
   __syncthreads();
   const int64_t words_per_row = n_rows / 8;
-  const int octets = group / 8;                              // k-octets in the tile
   constexpr int kWordCols = kFuseTileN / 8;                  // 16 packed words across the tile
-  for (int idx = threadIdx.x; idx < octets * kWordCols; idx += 256) {
+  for (int idx = threadIdx.x; idx < kOctets * kWordCols; idx += 256) {
     const int kb = idx / kWordCols, c = idx % kWordCols;
-    if (n0 + 8 * c >= n_rows) continue;
+    if (8 * c >= rows_here) continue;
     uint32_t m[8];                                           // m[i] = row 8c + order[i]; nibble t = code at k = 8kb + t
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = tile[(8 * c + kAwqOrder[i]) * pitch + kb];
+    for (int i = 0; i < 8; ++i) m[i] = tile[(8 * c + 2 * (i & 3) + (i >> 2)) * kPitch + kb];
     // 8x8 nibble transpose: afterwards m[t] nibble i = old m[i] nibble t
     nib_swap(m[0], m[1], 4, 0x0F0F0F0Fu); nib_swap(m[2], m[3], 4, 0x0F0F0F0Fu);
     nib_swap(m[4], m[5], 4, 0x0F0F0F0Fu); nib_swap(m[6], m[7], 4, 0x0F0F0F0Fu);
@@ -826,12 +830,11 @@ quant_pack_awq_kernel(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, i
 #pragma unroll
     for (int t = 0; t < 8; ++t) dst[t * words_per_row] = (int32_t)m[t];
   }
-  const int rows_here = (n_rows - n0) < kFuseTileN ? int(n_rows - n0) : kFuseTileN;
   if (threadIdx.x < kWordCols && 8 * int(threadIdx.x) < rows_here) {
     const int c = threadIdx.x;
     uint32_t word = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) word |= uint32_t(zsm[8 * c + kAwqOrder[i]] & 0xF) << (4 * i);
+    for (int i = 0; i < 8; ++i) word |= uint32_t(zsm[8 * c + 2 * (i & 3) + (i >> 2)] & 0xF) << (4 * i);
     qzeros[gi * words_per_row + n0 / 8 + c] = (int32_t)word;
   }
   for (int r = threadIdx.x; r < rows_here; r += 256) scales_t[gi * n_rows + n0 + r] = ssm[r];
@@ -1090,6 +1093,19 @@ extern "C" int qdm_unpack_awq(const int32_t* qweight, int64_t k_rows, int64_t n_
   return QDM_OK;
 }
 
+namespace {
+template <typename T>
+void launch_pack(int lpg, dim3 grid, const T* w, int64_t n_rows, int64_t k_cols, int32_t* qweight, int32_t* qzeros,
+                 T* scales_t, T* dq, cudaStream_t st) {
+  switch (lpg) {
+    case 4: quant_pack_awq_kernel<T, 4><<<grid, 256, 0, st>>>(w, n_rows, k_cols, 15.f, qweight, qzeros, scales_t, dq); break;
+    case 8: quant_pack_awq_kernel<T, 8><<<grid, 256, 0, st>>>(w, n_rows, k_cols, 15.f, qweight, qzeros, scales_t, dq); break;
+    case 16: quant_pack_awq_kernel<T, 16><<<grid, 256, 0, st>>>(w, n_rows, k_cols, 15.f, qweight, qzeros, scales_t, dq); break;
+    default: quant_pack_awq_kernel<T, 32><<<grid, 256, 0, st>>>(w, n_rows, k_cols, 15.f, qweight, qzeros, scales_t, dq); break;
+  }
+}
+}  // namespace
+
 extern "C" int qdm_quant_pack_awq(const void* w, int dtype, int64_t n_rows, int64_t k_cols, int group,
                                   int32_t* qweight, int32_t* qzeros, void* scales_t, void* dq, void* stream) {
   QDM_REQUIRE(w && qweight && qzeros && scales_t, "qdm_quant_pack_awq: null pointer");
@@ -1102,12 +1118,10 @@ extern "C" int qdm_quant_pack_awq(const void* w, int dtype, int64_t n_rows, int6
   QDM_DISPATCH_DTYPE(dtype, {
     constexpr int V = ElemTraits<T>::kVec;
     const int lpg = group / V;
-    QDM_UNSUPPORTED(group % V == 0 && group >= 32 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && group <= 256,
+    QDM_UNSUPPORTED(group % V == 0 && group >= 32 && lpg >= 4 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && group <= 256,
                     "qdm_quant_pack_awq: group %d unsupported for this dtype", group);
     dim3 grid((unsigned)(k_cols / group), (unsigned)((n_rows + kFuseTileN - 1) / kFuseTileN));
-    const size_t smem = size_t(kFuseTileN) * (lpg + 1) * 4 + size_t(kFuseTileN) * sizeof(T) + kFuseTileN;
-    quant_pack_awq_kernel<T><<<grid, 256, smem, st>>>((const T*)w, n_rows, k_cols, group, 15.f, qweight, qzeros,
-                                                      (T*)scales_t, (T*)dq);
+    launch_pack<T>(lpg, grid, (const T*)w, n_rows, k_cols, qweight, qzeros, (T*)scales_t, (T*)dq, st);
     QDM_LAUNCH_CHECK();
   });
   return QDM_OK;

@@ -118,7 +118,7 @@ int launch_col_reduce(const T* x, int64_t rows, int64_t cols, int64_t ld, TOut* 
   constexpr int V = ElemTraits<T>::kVec;
   const bool vec_ok = (cols % V == 0) && (ld % V == 0) && qdm_aligned16(x);
   const int64_t col_blocks = vec_ok ? (cols + 32 * V - 1) / (32 * V) : (cols + 31) / 32;
-  const int splits = col_splits(rows, col_blocks);
+  const int splits = col_splits(rows, col_blocks, 8);
   QDM_REQUIRE(ws_bytes >= size_t(splits) * cols * sizeof(float),
               "column reduction workspace too small: %zu < %zu", ws_bytes,
               size_t(splits) * cols * sizeof(float));
@@ -251,11 +251,18 @@ sqdiff_stage1(const T* __restrict__ a, const T* __restrict__ b, int64_t numel,
   }
 }
 __global__ void sqdiff_stage2(const double* __restrict__ partial, int n, double* __restrict__ out) {
-  // single thread, fixed order: n <= a few hundred
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double v = 0.0;
-    for (int i = 0; i < n; ++i) v += partial[i];
-    out[0] = v;
+  // one CTA, fixed order: thread t folds partial[t], partial[t + 256], ..., then a fixed shuffle / shared tree
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = sm[0];
+    for (int w = 1; w < int(blockDim.x >> 5); ++w) t += sm[w];
+    out[0] = t;
   }
 }
 
@@ -283,6 +290,33 @@ awq_wsum_stage1(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, int lan
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
   // one row of the group statistics + normalised accumulation; `have` is warp-uniform per row
   auto row_step = [&](const Vec16<T>& v, bool have) {
+    if constexpr (std::is_same<T, __half>::value) {
+      // fp16: |w| and the group max stay packed (exact), the quotient is formed in fp32 and rounded once
+      __half2 a2[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        a2[p] = (have && active) ? __habs2(reinterpret_cast<const __half2*>(&v)[p]) : __float2half2_rn(0.f);
+      __half2 m2 = __hmax2(__hmax2(a2[0], a2[1]), __hmax2(a2[2], a2[3]));
+      m2 = __hmax2(m2, __lowhigh2highlow(m2));
+      switch (lanes_per_group) {
+        case 32: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 16));
+        case 16: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 8));
+        case 8: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 4));
+        case 4: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
+        case 2: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
+        default: break;
+      }
+      const float denom = rnd<T>(__fadd_rn(__low2float(m2), 1e-6f));
+      const float rd = rcp_approx(denom);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float2 af = __half22float2(a2[p]);
+        const float2 qf = __half22float2(__floats2half2_rn(div_by_rcp<false>(af.x, denom, rd), div_by_rcp<false>(af.y, denom, rd)));
+        acc[2 * p] += qf.x;
+        acc[2 * p + 1] += qf.y;
+      }
+      return;
+    }
     float a[V];
     float m = 0.f;
     if (have && active) {
@@ -428,7 +462,7 @@ extern "C" int qdm_sqdiff_sum(const void* a, const void* b, int dtype, int64_t n
     const bool vec_ok = qdm_aligned16(a) && qdm_aligned16(b);
     sqdiff_stage1<T><<<blocks, kFlatThreads, 0, st>>>((const T*)a, (const T*)b, numel, (double*)workspace, vec_ok);
     QDM_LAUNCH_CHECK();
-    sqdiff_stage2<<<1, 32, 0, st>>>((const double*)workspace, blocks, out);
+    sqdiff_stage2<<<1, 256, 0, st>>>((const double*)workspace, blocks, out);
     QDM_LAUNCH_CHECK();
   });
   return QDM_OK;
