@@ -118,7 +118,7 @@ int launch_col_reduce(const T* x, int64_t rows, int64_t cols, int64_t ld, TOut* 
   constexpr int V = ElemTraits<T>::kVec;
   const bool vec_ok = (cols % V == 0) && (ld % V == 0) && qdm_aligned16(x);
   const int64_t col_blocks = vec_ok ? (cols + 32 * V - 1) / (32 * V) : (cols + 31) / 32;
-  const int splits = col_splits(rows, col_blocks, 8);
+  const int splits = col_splits(rows, col_blocks, OP == COL_ABSMAX ? 8 : 4);
   QDM_REQUIRE(ws_bytes >= size_t(splits) * cols * sizeof(float),
               "column reduction workspace too small: %zu < %zu", ws_bytes,
               size_t(splits) * cols * sizeof(float));
