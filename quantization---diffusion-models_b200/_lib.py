@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_int, c_int64, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqdm.so")
+LIB_PATH = os.environ.get("QDM_LIB", os.path.join(_HERE, "libqdm.so"))   # QDM_LIB: debug builds (timeline tracing)
 
 QDM_OK = 0
 QDM_ERR_INVALID = -1

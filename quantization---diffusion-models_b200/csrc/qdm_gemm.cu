@@ -23,17 +23,35 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
+
+// Debug timeline (compile with -DQDM_TRACE, run with QDM_TRACE=1): every role of block 0 logs (tag, clock64) pairs.
+#ifdef QDM_TRACE
+#define TRC_DECL int trc_n = 0
+#define TRC(ptr, region, tag)                                            \
+  do {                                                                   \
+    if ((ptr) && blockIdx.x == 0 && trc_n < 1000) {                      \
+      long long* t_ = (ptr) + (region) * 2048 + 2 * trc_n;               \
+      t_[0] = (tag);                                                     \
+      t_[1] = clock64();                                                 \
+      ++trc_n;                                                           \
+    }                                                                    \
+  } while (0)
+#else
+#define TRC_DECL
+#define TRC(ptr, region, tag)
+#endif
 
 enum GemmKind { G_F16 = 0, G_F16_KN = 1, G_W4 = 2, G_I8 = 3 };
 
 constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;                 // one swizzle-128B row = one k-block of an operand row
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
-constexpr int EPI_COLS = 64;                   // accumulator columns per epilogue chunk
-constexpr int EPI_PITCH = EPI_COLS * 2 + 16;   // staging row pitch in bytes (2-byte outputs), conflict-free
-constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
+constexpr int EPI_COLS = 64;                   // accumulator columns per epilogue chunk = one 128-byte output row segment
+constexpr int EPI_STG_BYTES = 32 * 128;        // per-warp TMA-store staging: 32 rows x 128 B, SWIZZLE_128B
+constexpr int EPI_VEC_BYTES = 256 * 4;         // per-warp fp32 copy of the tile's bias (and of the W8A8 column scales)
 constexpr int NUM_DQ_WARPS = 8;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -48,8 +66,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
 // Bounded wait: a pipeline bug traps (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#define mbar_wait(bar, parity) mbar_wait_(bar, parity, __LINE__)
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity, int line) {
   uint32_t done = 0;
   uint32_t polls = 0;
   long long t0 = 0;
@@ -63,7 +85,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (done) break;
     if (++polls == 4096) t0 = clock64();
-    if (polls > 4096 && (polls & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();
+    if (polls > 4096 && (polls & 1023) == 0 && clock64() - t0 > 2000000000LL) {
+      printf("qdm mbar_wait timeout: line %d block %d thread %d bar 0x%x parity %u\n", line, blockIdx.x, threadIdx.x, bar, parity);
+#ifdef QDM_DEBUG_WAIT
+      return;
+#else
+      __trap();
+#endif
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -200,19 +229,46 @@ struct GemmParams {
   const float* sw;           // G_I8  [N]
   void* y;                   // [M, N] out dtype
   int is_bf16;               // element / output type: 0 fp16, 1 bf16
+  long long* trace;          // QDM_TRACE builds only: per-role (tag, clock64) event log of block 0
+};
+
+// Packed-int4 staging ring of the W4 kernels: per k-block the TMA producer drops the tile part's packed words
+// (64 k rows x NLOC/8 words), its NLOC scales and NLOC/8 zero-point words here; the dequant warps read them from
+// shared memory, so they never have global loads outstanding when they reach fence.proxy.async.
+constexpr int RAW_STAGES = 4;
+template <int NLOC>
+struct RawCfg {
+  // One raw stage = TWO k-blocks (128 k rows): a thread issues a TMA every ~250 cycles, so the packed operands must
+  // cost fewer than one TMA per k-block each (measured: 4 TMAs per k-block made the producer the bottleneck).
+  // TMA needs a 16-byte aligned box start: the word box starts at the tile part's first word rounded DOWN to a
+  // multiple of 4 words (32 columns) and is 4 words wider; the dequant threads add the remainder (0..3 words).
+  static constexpr int WPRX = NLOC / 8 + 4;            // words per staged k row
+  static constexpr int QW_BYTES = 128 * WPRX * 4;      // [128 k rows][WPRX]
+  static constexpr int SC_ROW_BYTES = NLOC * 2;        // up to 2 quantisation groups per stage (group 64)
+  static constexpr int SC_BYTES = 2 * SC_ROW_BYTES;
+  static constexpr int ZW_ROW_BYTES = WPRX * 4;
+  static constexpr int ZW_BYTES = 2 * ZW_ROW_BYTES;
+  static constexpr int BYTES = (QW_BYTES + SC_BYTES + ZW_BYTES + 127) / 128 * 128;
+  static_assert(QW_BYTES % 128 == 0 && SC_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
+  __host__ __device__ static constexpr int tx_bytes(int srows) { return QW_BYTES + srows * (SC_ROW_BYTES + ZW_ROW_BYTES); }
 };
 
 template <int BLOCK_N, int KIND>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-  static constexpr int STAGES = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * (EPI_STG_BYTES + EPI_VEC_BYTES * (KIND == G_I8 ? 2 : 1));
+  static constexpr int RAW_N = 2;            // raw stages in use (of the RAW_STAGES barrier slots)
+  static constexpr int RAW_BYTES = (KIND == G_W4) ? RAW_N * RawCfg<BLOCK_N>::BYTES : 0;
+  static constexpr int STAGES = (227 * 1024 - 2048 - EPI_BYTES - RAW_BYTES) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048 - EPI_BYTES - RAW_BYTES) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int THREADS = (KIND == G_W4) ? 512 : 256;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int K_PER_BLOCK = (KIND == G_I8) ? 128 : 64;   // elements per k-block (128 bytes)
-  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS / 2 : 1;   // TMA + one producer group
+  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS / 2 : 1;   // TMA + one producer group (global-load path)
+  static constexpr int RAW_GROUPS = 2;                                            // dequant groups of the raw-ring path
+  static constexpr int FULL_COUNT_RAW = 1 + NUM_DQ_WARPS / RAW_GROUPS;
+  static constexpr int RAW_EMPTY_COUNT = 2 * NUM_DQ_WARPS / RAW_GROUPS;           // the warps of the stage's two k-blocks
 };
 
 template <int KIND, bool BF16>
@@ -249,16 +305,48 @@ __device__ __forceinline__ void load8_as_float(const void* base, int64_t idx, bo
   }
 }
 
-// Drain one accumulator tile: this warp owns 32 TMEM lanes (= 32 output rows starting at `row0`) and walks the
-// BLOCK_N columns in chunks of 64: tcgen05.ld -> scale/bias -> pack -> padded smem transpose -> 16-byte stores
-// in which 8 lanes cover 128 contiguous bytes of one output row.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Drain one accumulator tile: this warp owns 32 TMEM lanes (= 32 output rows starting at `row0`) and walks the tile's
+// columns in chunks of 64.  Per chunk: tcgen05.ld -> scale / bias (fp32, from a per-warp shared copy staged once
+// per tile) -> pack -> SWIZZLE_128B staging -> ONE TMA store of the 32 x 64 box (rows past M are clipped by the
+// tensor map).  The store is asynchronous; the staging buffer is reclaimed by wait_group.read one chunk later.
+// Measured before this (padded transpose + 8 x (ld.shared, predicated st.global) per chunk, bias from global per
+// 8 columns): 5500 cycles per 128 x 160 tile part -- the critical path of every K <= 640 shape.
+// A trailing chunk narrower than 64 columns is written row-wise from registers.
 template <int BLOCK_N, int KIND, bool BF16>
-__device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg, uint32_t taddr0, int row0, int n0, int lane) {
+__device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtensorMap* map_y, uint32_t stg, float* vec_sm,
+                                               uint32_t taddr0, int row0, int n0, int lane) {
   uint16_t* y = reinterpret_cast<uint16_t*>(p.y);
   const int n_end = min(n0 + p.tile_n, p.N);   // columns of this tile that exist
   const int row = row0 + lane;
   float sxr = 1.f;
   if (KIND == G_I8) sxr = (row < p.M) ? p.sx[row] : 0.f;
+  {  // lane l stages columns n0 + 8 l .. + 8 (whole groups of 8 are inside or outside: N % 8 == 0, tile_n % 16 == 0)
+    const int n = n0 + lane * 8;
+    const bool ok = n < n_end;
+    float b8[8];
+    load8_as_float<BF16>(p.bias, n, ok, b8);
+    __syncwarp();   // every lane is done reading the previous tile's copy
+    *reinterpret_cast<float4*>(vec_sm + lane * 8) = make_float4(b8[0], b8[1], b8[2], b8[3]);
+    *reinterpret_cast<float4*>(vec_sm + lane * 8 + 4) = make_float4(b8[4], b8[5], b8[6], b8[7]);
+    if (KIND == G_I8) {
+      float4 s0 = make_float4(0, 0, 0, 0), s1 = s0;
+      if (ok) {
+        s0 = *reinterpret_cast<const float4*>(p.sw + n);
+        s1 = *reinterpret_cast<const float4*>(p.sw + n + 4);
+      }
+      *reinterpret_cast<float4*>(vec_sm + 256 + lane * 8) = s0;
+      *reinterpret_cast<float4*>(vec_sm + 256 + lane * 8 + 4) = s1;
+    }
+    __syncwarp();
+  }
 #pragma unroll 1
   for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
     const int nc = n0 + c * EPI_COLS;
@@ -267,20 +355,20 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg
     const uint32_t taddr = taddr0 + c * EPI_COLS;
     tmem_ld32(taddr, v);
     tmem_ld32(taddr + 32, v + 32);
+    const bool whole = nc + EPI_COLS <= n_end;
+    if (whole) {   // the previous store of this warp must have read the staging buffer before it is overwritten
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
     tmem_ld_wait();
 #pragma unroll
     for (int j8 = 0; j8 < EPI_COLS / 8; ++j8) {
-      const int n = nc + j8 * 8;
-      const bool ok = n < n_end;
-      float bias8[8];
-      load8_as_float<BF16>(p.bias, n, ok, bias8);
+      const int col = c * EPI_COLS + j8 * 8;     // column inside the tile
+      const float4 b0 = *reinterpret_cast<const float4*>(vec_sm + col), b1 = *reinterpret_cast<const float4*>(vec_sm + col + 4);
+      const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float f[8];
       if (KIND == G_I8) {
-        float4 s0 = make_float4(0, 0, 0, 0), s1 = s0;
-        if (ok) {
-          s0 = *reinterpret_cast<const float4*>(p.sw + n);
-          s1 = *reinterpret_cast<const float4*>(p.sw + n + 4);
-        }
+        const float4 s0 = *reinterpret_cast<const float4*>(vec_sm + 256 + col), s1 = *reinterpret_cast<const float4*>(vec_sm + 256 + col + 4);
         const float sw8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -294,17 +382,19 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint8_t* stg
       o.y = pack_out2<KIND, BF16>(f[2], f[3]);
       o.z = pack_out2<KIND, BF16>(f[4], f[5]);
       o.w = pack_out2<KIND, BF16>(f[6], f[7]);
-      *reinterpret_cast<uint4*>(stg + lane * EPI_PITCH + j8 * 16) = o;
+      if (whole) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + uint32_t(lane) * 128u + (uint32_t(j8 ^ (lane & 7)) << 4)),
+                     "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                     : "memory");
+      } else if (row < p.M && nc + j8 * 8 < n_end) {
+        *reinterpret_cast<uint4*>(y + int64_t(row) * p.N + nc + j8 * 8) = o;
+      }
     }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3), seg = lane & 7;
-      const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_PITCH + seg * 16);
-      const int gm = row0 + r, gn = nc + seg * 8;
-      if (gm < p.M && gn < n_end) *reinterpret_cast<uint4*>(y + int64_t(gm) * p.N + gn) = o;
+    if (whole) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(map_y, stg, nc, row0);
     }
-    __syncwarp();
   }
 }
 
@@ -475,25 +565,167 @@ __device__ __forceinline__ void w4_producer_loop(const GemmParams& p, int dt, in
   }
 }
 
+// int4 dequant from the TMA-staged raw ring (see RawCfg).  Same thread mapping and arithmetic as w4_producer_loop,
+// but the packed words, scales and zero points come from shared memory: nothing global is outstanding at the proxy
+// fence, so a k-block costs its own instructions instead of a memory round trip (measured with the loads in this
+// loop: 0.63 us per k-block on latency-bound shapes).  `total` = pipeline iterations of this CTA.
+template <int NLOC, bool BF16, int STAGES, int STAGE_BYTES, int RAW_N, int GROUPS, bool CLUSTER>
+__device__ __forceinline__ void w4_dequant_loop(int dt, int lane, int first_tile, int tile_stride, int num_tiles, int n_tiles,
+                                                int num_kb, int tile_n, int col_off, int nloc, int group, uint32_t b_stage0, uint32_t raw0,
+                                                uint32_t empty_addr, uint32_t full_addr, uint32_t raw_full_addr,
+                                                uint32_t raw_empty_addr, long long* trace) {
+  using R = RawCfg<NLOC>;
+  TRC_DECL;
+  constexpr int WPR = NLOC / 8;                  // packed words per k row of this CTA's tile part
+  constexpr int GROUP_THREADS = 32 * NUM_DQ_WARPS / GROUPS;   // GROUPS groups take k-blocks round robin: their
+                                                               // wait / fence / arrive latencies overlap GROUPS-fold
+  constexpr int RPP = GROUP_THREADS / WPR;       // k rows covered by one pass of the group
+  constexpr int PASSES = 64 / RPP;
+  static_assert(RPP >= 1 && PASSES >= 1 && 64 % RPP == 0, "bad producer tiling");
+  const int grp = dt / GROUP_THREADS, tg = dt % GROUP_THREADS;
+  const int wc = tg % WPR, kr = tg / WPR;
+  const bool in_tile = wc * 8 < nloc;            // `nloc` <= NLOC columns of the tile part are in use
+  const uint32_t chunk_off = uint32_t(wc >> 3) * (64 * ROW_BYTES);
+  auto row_off = [&](int ps) {
+    const uint32_t k = uint32_t(kr + ps * RPP);
+    return chunk_off + k * ROW_BYTES + ((uint32_t(wc & 7) ^ (k & 7)) << 4);
+  };
+  uint32_t mask_lo = 0x000F000Fu, mask_hi = 0x00F000F0u;
+  uint32_t magic = BF16 ? 0x43004300u : 0x64006400u;  // 128.0 / 1024.0: the nibble lands in the low mantissa bits
+  asm volatile("" : "+r"(mask_lo), "+r"(mask_hi), "+r"(magic));
+  auto and_or = [](uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));  // (a & b) | c
+    return d;
+  };
+  auto lds32 = [](uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+  };
+  static_assert((RAW_N & (RAW_N - 1)) == 0, "raw ring depth must be a power of two");
+  int stage = grp % STAGES;
+  uint32_t phase = 0;
+  const int my_tiles = first_tile < num_tiles ? (num_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
+  const int total = my_tiles * num_kb;                         // pipeline iterations of this CTA
+  const int rs_per_tile = (num_kb + 1) >> 1;                   // raw stages (k-block pairs) per tile
+  int tile = first_tile, kb = grp, tl = 0;                     // position of iteration `it`: tile, k-block, local tile count
+  for (int it = grp; it < total; it += GROUPS) {
+    while (kb >= num_kb) { kb -= num_kb; tile += tile_stride; ++tl; }
+    // word offset of this tile part inside the (aligned-down) staged box
+    const uint32_t shift = uint32_t(((tile % n_tiles) * tile_n + col_off) >> 3) & 3u;
+    const uint32_t half = uint32_t(kb & 1);                    // which k-block of the raw stage
+    const uint32_t srow = (group == 64) ? half : 0u;           // quantisation group row inside the stage
+    const int rseq = tl * rs_per_tile + (kb >> 1);             // raw stage sequence number of this CTA
+    const int rs = rseq & (RAW_N - 1);
+    const uint32_t rphase = uint32_t(rseq / RAW_N) & 1u;
+    const bool lone = (kb == num_kb - 1) && half == 0;         // odd K tail: this group is the stage's only consumer
+    const uint32_t w_off = (uint32_t((kr + half * 64) * R::WPRX + wc) + shift) * 4u;
+    kb += GROUPS;
+    const uint32_t raw = raw0 + uint32_t(rs) * R::BYTES;
+    mbar_wait(raw_full_addr + 8u * rs, rphase);
+    if (tg == 0) TRC(trace, 3 + grp, 1000000 + it);
+    uint32_t w[PASSES];
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) w[ps] = lds32(raw + w_off + uint32_t(ps * RPP * R::WPRX) * 4u);
+    const uint32_t zw = lds32(raw + R::QW_BYTES + R::SC_BYTES + srow * R::ZW_ROW_BYTES + (uint32_t(wc) + shift) * 4u);
+    uint32_t sp[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(sp[0]), "=r"(sp[1]), "=r"(sp[2]), "=r"(sp[3])
+                 : "r"(raw + R::QW_BYTES + srow * R::SC_ROW_BYTES + uint32_t(wc) * 16u));
+    uint32_t zsub[4];
+    if (BF16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) zsub[q] = and_or(zw >> (4 * q), mask_lo, magic);        // 128 + z
+    } else {
+      const uint32_t zs = zw >> 8;
+      zsub[0] = and_or(zw, mask_lo, magic);                                                // 1024 + z
+      zsub[2] = and_or(zs, mask_lo, magic);
+      const __half2 sixteenth = __float2half2_rn(0.0625f);   // high nibbles decode as 1024 + 16 z; /16 = 64 + z exactly
+      const uint32_t z1 = and_or(zw, mask_hi, magic), z3 = and_or(zs, mask_hi, magic);
+      __half2 h1 = __hmul2(*reinterpret_cast<const __half2*>(&z1), sixteenth);
+      __half2 h3 = __hmul2(*reinterpret_cast<const __half2*>(&z3), sixteenth);
+      zsub[1] = *reinterpret_cast<uint32_t*>(&h1);
+      zsub[3] = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    mbar_wait(empty_addr + 8u * stage, phase ^ 1);
+    if (tg == 0) TRC(trace, 3 + grp, 2000000 + it);
+    const uint32_t b_dst = b_stage0 + stage * STAGE_BYTES;
+    if (in_tile) {   // columns past the tile are never read by the MMA
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const uint32_t wv = w[ps];
+        uint32_t o[4];
+        if (BF16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t t = and_or(wv >> (4 * q), mask_lo, magic);  // {128 + q(col 2q), 128 + q(col 2q+1)}
+            __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zsub[q]));
+            d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&sp[q]));
+            o[q] = *reinterpret_cast<uint32_t*>(&d);
+          }
+        } else {
+          const uint32_t ws = wv >> 8;
+          const __half2 sixteenth = __float2half2_rn(0.0625f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t src = (q < 2) ? wv : ws;
+            __half2 d;
+            if ((q & 1) == 0) {   // low nibble of each byte: 1024 + q, exact subtract
+              const uint32_t t = and_or(src, mask_lo, magic);
+              d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zsub[q]));
+            } else {              // high nibble: 1024 + 16 q; fma(., 1/16, -(64 + z)) = q - z exactly
+              const uint32_t t = and_or(src, mask_hi, magic);
+              d = __hfma2(*reinterpret_cast<const __half2*>(&t), sixteenth, __hneg2(*reinterpret_cast<const __half2*>(&zsub[q])));
+            }
+            d = __hmul2(d, *reinterpret_cast<const __half2*>(&sp[q]));   // (q - z) * s, one rounding
+            o[q] = *reinterpret_cast<uint32_t*>(&d);
+          }
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_dst + row_off(ps)), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                     "r"(o[3])
+                     : "memory");
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (CLUSTER) mbar_arrive_cluster(full_addr + 8u * stage);
+      else mbar_arrive(full_addr + 8u * stage);
+      mbar_arrive_n(raw_empty_addr + 8u * rs, lone ? 2u : 1u);   // stands in for the absent second k-block's warps
+    }
+    if (tg == 0) TRC(trace, 3 + grp, 3000000 + it);
+    stage += GROUPS;
+    while (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
-template <int BLOCK_N, int KIND, bool BF16>
+// RAWT (G_W4 only): packed words / scales / zero points arrive by TMA (map_b = qweight, map_s, map_z) in the raw
+// ring; otherwise (N % 32 != 0: strides TMA cannot express) the dequant warps load them from global memory.
+template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
 __global__ void __launch_bounds__(Cfg<BLOCK_N, KIND>::THREADS, 1)
 qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const GemmParams p) {
+                const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_z,
+                const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
   using C = Cfg<BLOCK_N, KIND>;
+  using R = RawCfg<BLOCK_N>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // layout: [stages x (A | B)] [epilogue staging] [barriers] [tmem ptr]
+  // layout: [stages x (A | B)] [epilogue: 4 store stagings (1024-aligned), 4 fp32 vectors] [raw int4 ring] [barriers] [tmem ptr]
   const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + C::EPI_BYTES;
+  const uint32_t raw_base = epi_base + C::EPI_BYTES;
+  const uint32_t bar_base = raw_base + C::RAW_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  volatile uint32_t* tmem_ptr_smem =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * (2 * STAGES + 4));
+  auto raw_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+  auto raw_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + RAW_STAGES + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + C::RAW_BYTES + 8 * (2 * STAGES + 4 + 2 * RAW_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -504,16 +736,21 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
-    if (KIND != G_W4) tma_prefetch_desc(&map_b);
+    if (KIND != G_W4 || RAWT) tma_prefetch_desc(&map_b);
+    if (KIND == G_W4 && RAWT) { tma_prefetch_desc(&map_s); tma_prefetch_desc(&map_z); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), C::FULL_COUNT);
+      mbar_init(full_bar(s), (KIND == G_W4 && RAWT) ? C::FULL_COUNT_RAW : C::FULL_COUNT);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), 128);
+    }
+    for (int s = 0; s < RAW_STAGES; ++s) {
+      mbar_init(raw_full_bar(s), 1);
+      mbar_init(raw_empty_bar(s), C::RAW_EMPTY_COUNT);
     }
     fence_barrier_init();
   }
@@ -593,27 +830,58 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================================================== raw int4 producer: one stage = two k-blocks of packed B
+    if (KIND == G_W4 && RAWT && lane == 0) {
+      const int srows = p.group == 64 ? 2 : 1;                    // quantisation groups per 128 k rows
+      const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
+      const uint32_t tx = R::tx_bytes(srows);
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * tile_n;
+        for (int j = 0; 2 * j < num_kb; ++j) {
+          mbar_wait(raw_empty_bar(rs), rphase ^ 1);
+          const uint32_t raw = raw_base + uint32_t(rs) * R::BYTES;
+          const int grow = j * gdiv / gmul;                       // first group row of k rows [128 j, 128 j + 128)
+          mbar_expect_tx(raw_full_bar(rs), tx);
+          tma_load_2d(raw, &map_b, raw_full_bar(rs), (n0 >> 3) & ~3, j * 128);
+          tma_load_2d(raw + R::QW_BYTES, &map_s, raw_full_bar(rs), n0, grow);
+          tma_load_2d(raw + R::QW_BYTES + R::SC_BYTES, &map_z, raw_full_bar(rs), (n0 >> 3) & ~3, grow);
+          if (++rs == C::RAW_N) { rs = 0; rphase ^= 1; }
+        }
+      }
+    }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================== epilogue
     const int ew = warp - 4;  // TMEM lane quarter this warp may read (warp % 4)
-    uint8_t* stg = smem_gen + STAGES * C::STAGE_BYTES + ew * EPI_WARP_BYTES;
+    const uint32_t stg = epi_base + ew * EPI_STG_BYTES;
+    float* vec_sm = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4) * (KIND == G_I8 ? 2 : 1);
+    if (lane == 0) tma_prefetch_desc(&map_y);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_drain<BLOCK_N, KIND, BF16>(p, stg, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
                                           m0 + ew * 32, n0, lane);
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   } else if (KIND == G_W4 && warp >= 8) {
     // ===================================================== int4 dequant producers
-    w4_producer_loop<BLOCK_N, BF16, STAGES, C::STAGE_BYTES, false>(
-        p, threadIdx.x - 256, lane, blockIdx.x, gridDim.x, num_tiles, n_tiles, num_kb, tile_n, 0, tile_n,
-        smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, bar_base);
+    if (RAWT) {
+      w4_dequant_loop<BLOCK_N, BF16, STAGES, C::STAGE_BYTES, C::RAW_N, C::RAW_GROUPS, false>(
+          threadIdx.x - 256, lane, blockIdx.x, gridDim.x, num_tiles, n_tiles, num_kb, tile_n, 0, tile_n, p.group,
+          smem_base + A_STAGE_BYTES, raw_base, empty_bar(0), full_bar(0), raw_full_bar(0), raw_empty_bar(0), p.trace);
+    } else {
+      w4_producer_loop<BLOCK_N, BF16, STAGES, C::STAGE_BYTES, false>(
+          p, threadIdx.x - 256, lane, blockIdx.x, gridDim.x, num_tiles, n_tiles, num_kb, tile_n, 0, tile_n,
+          smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, bar_base);
+    }
   }
 
   tc_fence_before();
@@ -637,34 +905,44 @@ struct Cfg2 {
   static constexpr int NLOC = BLOCK_N / 2;
   static constexpr int B_STAGE_BYTES = NLOC * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-  static constexpr int STAGES = (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048 - EPI_BYTES) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int EPI_BYTES = 4 * (EPI_STG_BYTES + EPI_VEC_BYTES * (KIND == G_I8 ? 2 : 1));
+  static constexpr int RAW_N = 4;
+  static constexpr int RAW_BYTES = (KIND == G_W4) ? RAW_N * RawCfg<NLOC>::BYTES : 0;
+  static constexpr int STAGES = (227 * 1024 - 2048 - EPI_BYTES - RAW_BYTES) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - 2048 - EPI_BYTES - RAW_BYTES) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RAW_BYTES + EPI_BYTES + 1024 + 256;
   static constexpr int THREADS = (KIND == G_W4) ? 512 : 256;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
   static constexpr int K_PER_BLOCK = (KIND == G_I8) ? 128 : 64;
   // leader's arrive.expect_tx (covers the TMA bytes of both CTAs) + the dequant warps of both CTAs
-  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS : 1;   // one producer group per CTA
+  static constexpr int FULL_COUNT = (KIND == G_W4) ? 1 + NUM_DQ_WARPS : 1;   // one producer group per CTA (global-load path)
+  static constexpr int RAW_GROUPS = 4;
+  static constexpr int FULL_COUNT_RAW = 1 + 2 * NUM_DQ_WARPS / RAW_GROUPS;    // one group per CTA, two CTAs
+  static constexpr int RAW_EMPTY_COUNT = 2 * NUM_DQ_WARPS / RAW_GROUPS;
 };
 
-template <int BLOCK_N, int KIND, bool BF16>
+template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<BLOCK_N, KIND>::THREADS, 1)
 qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_z,
+                 const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
   using C = Cfg2<BLOCK_N, KIND>;
   constexpr int STAGES = C::STAGES;
   constexpr int NLOC = C::NLOC;
+  using R = RawCfg<NLOC>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + C::EPI_BYTES;
+  const uint32_t raw_base = epi_base + C::EPI_BYTES;
+  const uint32_t bar_base = raw_base + C::RAW_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  volatile uint32_t* tmem_ptr_smem =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * (2 * STAGES + 4));
+  auto raw_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+  auto raw_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + RAW_STAGES + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + C::RAW_BYTES + 8 * (2 * STAGES + 4 + 2 * RAW_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -677,16 +955,21 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
-    if (KIND != G_W4) tma_prefetch_desc(&map_b);
+    if (KIND != G_W4 || RAWT) tma_prefetch_desc(&map_b);
+    if (KIND == G_W4 && RAWT) { tma_prefetch_desc(&map_s); tma_prefetch_desc(&map_z); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), C::FULL_COUNT);
+      mbar_init(full_bar(s), (KIND == G_W4 && RAWT) ? C::FULL_COUNT_RAW : C::FULL_COUNT);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), 8);   // 4 epilogue warps x 2 CTAs
+    }
+    for (int s = 0; s < RAW_STAGES; ++s) {
+      mbar_init(raw_full_bar(s), 1);
+      mbar_init(raw_empty_bar(s), C::RAW_EMPTY_COUNT);
     }
     fence_barrier_init();
   }
@@ -709,11 +992,15 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      TRC_DECL;
+      int trc_it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M;
         const int n0 = (tile % n_tiles) * tile_n + int(rank) * nloc;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
+          TRC(p.trace, 0, 2000000 + trc_it);
+          ++trc_it;
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           const uint32_t lf = leader_full0 + 8u * stage;
@@ -737,12 +1024,17 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      TRC_DECL;
+      int trc_it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+        TRC(p.trace, 1, 1000000 + trc_it);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          TRC(p.trace, 1, 2000000 + trc_it);
+          ++trc_it;
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
@@ -760,28 +1052,68 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================================================== raw int4 producer (each CTA: its own packed columns)
+    if (KIND == G_W4 && RAWT && lane == 0) {
+      const int srows = p.group == 64 ? 2 : 1;
+      const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
+      const uint32_t tx = R::tx_bytes(srows);
+      int rs = 0;
+      uint32_t rphase = 0;
+      TRC_DECL;
+      int trc_it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n0 = (tile % n_tiles) * tile_n + int(rank) * nloc;
+        for (int j = 0; 2 * j < num_kb; ++j) {
+          mbar_wait(raw_empty_bar(rs), rphase ^ 1);
+          TRC(p.trace, 7, 1000000 + trc_it);
+          ++trc_it;
+          const uint32_t raw = raw_base + uint32_t(rs) * R::BYTES;
+          const int grow = j * gdiv / gmul;
+          mbar_expect_tx(raw_full_bar(rs), tx);
+          tma_load_2d(raw, &map_b, raw_full_bar(rs), (n0 >> 3) & ~3, j * 128);
+          tma_load_2d(raw + R::QW_BYTES, &map_s, raw_full_bar(rs), n0, grow);
+          tma_load_2d(raw + R::QW_BYTES + R::SC_BYTES, &map_z, raw_full_bar(rs), (n0 >> 3) & ~3, grow);
+          if (++rs == C::RAW_N) { rs = 0; rphase ^= 1; }
+        }
+      }
+    }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================== epilogue (each CTA drains its own 128 rows)
     const int ew = warp - 4;
-    uint8_t* stg = smem_gen + STAGES * C::STAGE_BYTES + ew * EPI_WARP_BYTES;
+    const uint32_t stg = epi_base + ew * EPI_STG_BYTES;
+    float* vec_sm = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4) * (KIND == G_I8 ? 2 : 1);
+    if (lane == 0) tma_prefetch_desc(&map_y);
     int acc = 0;
     uint32_t acc_phase = 0;
+    TRC_DECL;
+    int trc_it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
       mbar_wait(tmem_full_bar(acc), acc_phase);
+      if (threadIdx.x == 128) TRC(p.trace, 2, 1000000 + trc_it);
       tc_fence_after();
-      epilogue_drain<BLOCK_N, KIND, BF16>(p, stg, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
                                           m0 + ew * 32, n0, lane);
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 128) TRC(p.trace, 2, 2000000 + trc_it);
+      ++trc_it;
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   } else if (KIND == G_W4 && warp >= 8) {
     // ===================================================== int4 dequant producers (each CTA: its NLOC columns)
-    w4_producer_loop<NLOC, BF16, STAGES, C::STAGE_BYTES, true>(
-        p, threadIdx.x - 256, lane, pair, num_pairs, num_tiles, n_tiles, num_kb, tile_n, int(rank) * nloc, nloc,
-        smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, leader_full0);
+    if (RAWT) {
+      w4_dequant_loop<NLOC, BF16, STAGES, C::STAGE_BYTES, C::RAW_N, C::RAW_GROUPS, true>(
+          threadIdx.x - 256, lane, pair, num_pairs, num_tiles, n_tiles, num_kb, tile_n, int(rank) * nloc, nloc, p.group,
+          smem_base + A_STAGE_BYTES, raw_base, empty_bar(0), leader_full0, raw_full_bar(0), raw_empty_bar(0), p.trace);
+    } else {
+      w4_producer_loop<NLOC, BF16, STAGES, C::STAGE_BYTES, true>(
+          p, threadIdx.x - 256, lane, pair, num_pairs, num_tiles, n_tiles, num_kb, tile_n, int(rank) * nloc, nloc,
+          smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, leader_full0);
+    }
   }
 
   tc_fence_before();
@@ -813,14 +1145,16 @@ int get_encode_fn() {
 }
 
 // 2-D row-major tensor [rows, cols] of `elem_bytes` elements; box = {box_cols, box_rows}, 128-byte swizzle.
-int make_map(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int box_cols, int box_rows) {
-  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+int make_map(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int box_cols, int box_rows,
+             bool swizzle128 = true) {
+  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                               : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     qdm_set_error("cuTensorMapEncodeTiled failed (%d) for [%lld, %lld] x %d B", (int)r, (long long)rows, (long long)cols, elem_bytes);
     return QDM_ERR_CUDA;
@@ -850,10 +1184,16 @@ int choose_tile_n(int64_t M, int64_t N, bool pair) {
   return best;
 }
 
-template <int BLOCK_N, int KIND, bool BF16>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+struct Maps {
+  CUtensorMap a, b, s, z;   // b: B operand (or packed qweight), s / z: W4 scales / zero points (raw TMA path)
+  CUtensorMap y;            // output [M, N], 32 x 64 boxes for the epilogue's TMA stores
+  bool raw = false;
+};
+
+template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
+int launch_gemm(const Maps& m, const GemmParams& p, cudaStream_t st) {
   using C = Cfg<BLOCK_N, KIND>;
-  auto kern = qdm_gemm_kernel<BLOCK_N, KIND, BF16>;
+  auto kern = qdm_gemm_kernel<BLOCK_N, KIND, BF16, RAWT>;
   static bool attr_set = false;  // per instantiation; benign race (idempotent)
   if (!attr_set) {
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -862,15 +1202,15 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + p.tile_n - 1) / p.tile_n;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < QDM_NUM_SMS ? tiles : QDM_NUM_SMS;
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, p);
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
 
-template <int BLOCK_N, int KIND, bool BF16>
-int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
+int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
   using C = Cfg2<BLOCK_N, KIND>;
-  auto kern = qdm_gemm2_kernel<BLOCK_N, KIND, BF16>;
+  auto kern = qdm_gemm2_kernel<BLOCK_N, KIND, BF16, RAWT>;
   static bool attr_set = false;
   if (!attr_set) {
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -879,7 +1219,26 @@ int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams&
   const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (p.N + p.tile_n - 1) / p.tile_n;
   const int tiles = m_tiles * n_tiles;
   const int pairs = tiles < QDM_NUM_SMS / 2 ? tiles : QDM_NUM_SMS / 2;
-  kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+#ifdef QDM_TRACE
+  if (getenv("QDM_TRACE")) {
+    static long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(&tbuf, 8 * 2048 * sizeof(long long));
+    cudaMemset(tbuf, 0, 8 * 2048 * sizeof(long long));
+    GemmParams pt = p;
+    pt.trace = tbuf;
+    kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, pt);
+    cudaDeviceSynchronize();
+    static long long host[8 * 2048];
+    cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "QDMTRACE begin M=%d N=%d K=%d tile_n=%d\n", p.M, p.N, p.K, p.tile_n);
+    for (int r = 0; r < 8; ++r)
+      for (int i = 0; i < 1000 && host[r * 2048 + 2 * i]; ++i)
+        fprintf(stderr, "QDMTRACE %d %lld %lld\n", r, host[r * 2048 + 2 * i], host[r * 2048 + 2 * i + 1]);
+    QDM_LAUNCH_CHECK();
+    return QDM_OK;
+  }
+#endif
+  kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, p);
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
@@ -892,10 +1251,15 @@ bool use_pair(const GemmParams& p) {
   return p.M > BLOCK_M;   // a second 128-row half exists
 }
 
+template <int KIND, bool RAWT>
+int dispatch_gemm_r(const Maps& m, const GemmParams& p, bool pair, cudaStream_t st) {
+  if (pair) return p.is_bf16 ? launch_gemm2<256, KIND, true, RAWT>(m, p, st) : launch_gemm2<256, KIND, false, RAWT>(m, p, st);
+  return p.is_bf16 ? launch_gemm<256, KIND, true, RAWT>(m, p, st) : launch_gemm<256, KIND, false, RAWT>(m, p, st);
+}
 template <int KIND>
-int dispatch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, bool pair, cudaStream_t st) {
-  if (pair) return p.is_bf16 ? launch_gemm2<256, KIND, true>(ma, mb, p, st) : launch_gemm2<256, KIND, false>(ma, mb, p, st);
-  return p.is_bf16 ? launch_gemm<256, KIND, true>(ma, mb, p, st) : launch_gemm<256, KIND, false>(ma, mb, p, st);
+int dispatch_gemm(const Maps& m, const GemmParams& p, bool pair, cudaStream_t st) {
+  if (KIND == G_W4 && m.raw) return dispatch_gemm_r<KIND, KIND == G_W4>(m, p, pair, st);
+  return dispatch_gemm_r<KIND, false>(m, p, pair, st);
 }
 
 int check_common(const char* fn, const void* x, const void* w, void* y, int dtype, int64_t M, int64_t N, int64_t K) {
@@ -924,14 +1288,16 @@ extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void
   QDM_REQUIRE(!bias || qdm_aligned16(bias), "qdm_gemm_f16: bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  CUtensorMap ma, mb;
-  if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
+  Maps m;
+  if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
+  if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
   const bool pair = use_pair(p);
   p.tile_n = choose_tile_n(M, N, pair);
-  if ((rc = make_map(&mb, w, 2, N, K, 64, pair ? p.tile_n / 2 : p.tile_n))) return rc;
-  return dispatch_gemm<G_F16>(ma, mb, p, pair, (cudaStream_t)stream);
+  if ((rc = make_map(&m.b, w, 2, N, K, 64, pair ? p.tile_n / 2 : p.tile_n))) return rc;
+  m.s = m.a; m.z = m.a;
+  return dispatch_gemm<G_F16>(m, p, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
@@ -942,13 +1308,15 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   QDM_REQUIRE(!bias || qdm_aligned16(bias), "qdm_gemm_f16_kn: bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  CUtensorMap ma, mb;
-  if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
-  if ((rc = make_map(&mb, w_kn, 2, K, N, 64, 64))) return rc;
+  Maps m;
+  if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
+  if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
+  if ((rc = make_map(&m.b, w_kn, 2, K, N, 64, 64))) return rc;
+  m.s = m.a; m.z = m.a;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
   p.tile_n = choose_tile_n(M, N, false);
-  return dispatch_gemm<G_F16_KN>(ma, mb, p, false, (cudaStream_t)stream);
+  return dispatch_gemm<G_F16_KN>(m, p, false, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
@@ -963,14 +1331,26 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   QDM_REQUIRE(qdm_aligned16(scales) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w4a16: scales/bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  CUtensorMap ma;
-  if ((rc = make_map(&ma, x, 2, M, K, 64, BLOCK_M))) return rc;
+  Maps m;
+  if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
+  if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.group = group;
   p.qweight = qweight; p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
   const bool pair = use_pair(p);
   p.tile_n = choose_tile_n(M, N, pair);
-  return dispatch_gemm<G_W4>(ma, ma, p, pair, (cudaStream_t)stream);
+  m.b = m.a; m.s = m.a; m.z = m.a;
+  // packed operands by TMA when their row strides are multiples of 16 bytes (N % 32 == 0): boxes are always the
+  // full tile part the kernel was built for (columns past the tile are loaded and ignored, past N zero-filled)
+  m.raw = (N % 32 == 0) && qdm_aligned16(qzeros) && !getenv("QDM_W4_NO_TMA");   // env: A/B switch for bring-up
+  if (m.raw) {
+    const int nloc_max = pair ? 128 : 256, G = int(K / group);
+    const int srows = group == 64 ? 2 : 1;   // quantisation groups per raw stage (128 k rows)
+    if ((rc = make_map(&m.b, qweight, 4, K, N / 8, nloc_max / 8 + 4, 128, false))) return rc;
+    if ((rc = make_map(&m.s, scales, 2, G, N, nloc_max, srows, false))) return rc;
+    if ((rc = make_map(&m.z, qzeros, 4, G, N / 8, nloc_max / 8 + 4, srows, false))) return rc;
+  }
+  return dispatch_gemm<G_W4>(m, p, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const float* sw,
@@ -983,14 +1363,16 @@ extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq
   QDM_REQUIRE(qdm_aligned16(sw) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w8a8: sw/bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
-  CUtensorMap ma, mb;
-  if ((rc = make_map(&ma, xq, 1, M, K, 128, BLOCK_M))) return rc;
+  Maps m;
+  if ((rc = make_map(&m.a, xq, 1, M, K, 128, BLOCK_M))) return rc;
+  if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.sx = sx; p.sw = sw; p.bias = bias; p.y = y; p.is_bf16 = out_dtype == QDM_BF16;
   const bool pair = use_pair(p);
   p.tile_n = choose_tile_n(M, N, pair);
-  if ((rc = make_map(&mb, wq, 1, N, K, 128, pair ? p.tile_n / 2 : p.tile_n))) return rc;
-  return dispatch_gemm<G_I8>(ma, mb, p, pair, (cudaStream_t)stream);
+  if ((rc = make_map(&m.b, wq, 1, N, K, 128, pair ? p.tile_n / 2 : p.tile_n))) return rc;
+  m.s = m.a; m.z = m.a;
+  return dispatch_gemm<G_I8>(m, p, pair, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight, const int32_t* qzeros,

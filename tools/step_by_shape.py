@@ -1,0 +1,22 @@
+"""Aggregate gpurun_out/launches_step.csv (one bench step under ncu) by layer shape: python tools/step_by_shape.py [csv]"""
+import collections, csv, importlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sh = importlib.import_module("quantization---diffusion-models_b200.shapes")
+path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "launches_step.csv")
+rows = list(csv.reader(open(path)))
+hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
+dur = [float(r[ix["Metric Value"]]) for r in rows[hi + 1:] if len(r) == len(hdr) and r[ix["Metric Name"]] == "gpu__time_duration.sum"]
+order = []
+for name, m, n, k, c in sh.sd15_unet_linears():
+    order += [(m, n, k)] * c
+d = dur[-184:]
+agg = collections.OrderedDict()
+for s, t in zip(order, d):
+    a = agg.setdefault(s, [0, 0.0]); a[0] += 1; a[1] += t
+print(f"launches {len(dur)}; sum of the step's 184 launch durations: {sum(d) / 1e3:.1f} us")
+for (m, n, k), a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    g = sh.group_for(k); fl = 2 * m * n * k; by = sh.gemm_bytes_w4a16(m, n, k, g)
+    ideal = max(fl / 1410.2e12, by / 6455.9e9) * 1e6
+    print(f"{a[1] / 1e3:8.1f} us {a[0]:3d} x ({m:6d},{n:5d},{k:5d}) avg {a[1] / a[0] / 1e3:6.1f} us  roofline {ideal:6.1f} us  {fl / (a[1] / a[0] * 1e-9) / 1e12:7.1f} TFLOP/s")
