@@ -32,8 +32,8 @@ namespace {
 #define TRC_DECL int trc_n = 0
 #define TRC(ptr, region, tag)                                            \
   do {                                                                   \
-    if ((ptr) && blockIdx.x == 0 && trc_n < 1000) {                      \
-      long long* t_ = (ptr) + (region) * 2048 + 2 * trc_n;               \
+    if ((ptr) && blockIdx.x < 2 && trc_n < 1000) {                       \
+      long long* t_ = (ptr) + ((region) + 8 * blockIdx.x) * 2048 + 2 * trc_n; \
       t_[0] = (tag);                                                     \
       t_[1] = clock64();                                                 \
       ++trc_n;                                                           \
@@ -347,23 +347,19 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
     }
     __syncwarp();
   }
-#pragma unroll 1
-  for (int c = 0; c < BLOCK_N / EPI_COLS; ++c) {
-    const int nc = n0 + c * EPI_COLS;
-    if (nc >= n_end) break;
-    uint32_t v[EPI_COLS];
-    const uint32_t taddr = taddr0 + c * EPI_COLS;
-    tmem_ld32(taddr, v);
-    tmem_ld32(taddr + 32, v + 32);
+  // 32-column halves, double buffered in registers: the tcgen05.ld of half h + 1 is in flight while half h is
+  // converted (one ld + wait per half was 40 % of a chunk's time when issued back to back with its use)
+  auto process_half = [&](const uint32_t (&v)[32], int h) {
+    const int c = h >> 1, hh = h & 1;
+    const int nc = n0 + c * EPI_COLS;                       // first column of the 64-column chunk
     const bool whole = nc + EPI_COLS <= n_end;
-    if (whole) {   // the previous store of this warp must have read the staging buffer before it is overwritten
+    if (whole && hh == 0) {   // the previous store of this warp must have read the staging buffer before it is overwritten
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
     }
-    tmem_ld_wait();
 #pragma unroll
-    for (int j8 = 0; j8 < EPI_COLS / 8; ++j8) {
-      const int col = c * EPI_COLS + j8 * 8;     // column inside the tile
+    for (int j8 = 0; j8 < 4; ++j8) {
+      const int col = h * 32 + j8 * 8;                       // column inside the tile
       const float4 b0 = *reinterpret_cast<const float4*>(vec_sm + col), b1 = *reinterpret_cast<const float4*>(vec_sm + col + 4);
       const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float f[8];
@@ -383,17 +379,31 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
       o.z = pack_out2<KIND, BF16>(f[4], f[5]);
       o.w = pack_out2<KIND, BF16>(f[6], f[7]);
       if (whole) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + uint32_t(lane) * 128u + (uint32_t(j8 ^ (lane & 7)) << 4)),
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + uint32_t(lane) * 128u + (uint32_t((hh * 4 + j8) ^ (lane & 7)) << 4)),
                      "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
                      : "memory");
-      } else if (row < p.M && nc + j8 * 8 < n_end) {
-        *reinterpret_cast<uint4*>(y + int64_t(row) * p.N + nc + j8 * 8) = o;
+      } else if (row < p.M && n0 + col < n_end) {
+        *reinterpret_cast<uint4*>(y + int64_t(row) * p.N + n0 + col) = o;
       }
     }
-    if (whole) {
+    if (whole && hh == 1) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) tma_store_2d(map_y, stg, nc, row0);
+    }
+  };
+  const int n_halves = (n_end - n0 + 31) / 32;
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr0, va);
+#pragma unroll 1
+  for (int h = 0; h < n_halves; h += 2) {
+    tmem_ld_wait();
+    if (h + 1 < n_halves) tmem_ld32(taddr0 + (h + 1) * 32, vb);
+    process_half(va, h);
+    if (h + 1 < n_halves) {
+      tmem_ld_wait();
+      if (h + 2 < n_halves) tmem_ld32(taddr0 + (h + 2) * 32, va);
+      process_half(vb, h + 1);
     }
   }
 }
@@ -1222,16 +1232,16 @@ int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
 #ifdef QDM_TRACE
   if (getenv("QDM_TRACE")) {
     static long long* tbuf = nullptr;
-    if (!tbuf) cudaMalloc(&tbuf, 8 * 2048 * sizeof(long long));
-    cudaMemset(tbuf, 0, 8 * 2048 * sizeof(long long));
+    if (!tbuf) cudaMalloc(&tbuf, 16 * 2048 * sizeof(long long));
+    cudaMemset(tbuf, 0, 16 * 2048 * sizeof(long long));
     GemmParams pt = p;
     pt.trace = tbuf;
     kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, pt);
     cudaDeviceSynchronize();
-    static long long host[8 * 2048];
+    static long long host[16 * 2048];
     cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost);
     fprintf(stderr, "QDMTRACE begin M=%d N=%d K=%d tile_n=%d\n", p.M, p.N, p.K, p.tile_n);
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 16; ++r)
       for (int i = 0; i < 1000 && host[r * 2048 + 2 * i]; ++i)
         fprintf(stderr, "QDMTRACE %d %lld %lld\n", r, host[r * 2048 + 2 * i], host[r * 2048 + 2 * i + 1]);
     QDM_LAUNCH_CHECK();

@@ -13,7 +13,8 @@ for line in open(sys.argv[1]):
 ev.sort()
 t0 = ev[0][0]
 names = {0: "tma", 1: "mma", 2: "epi", 3: "dq0", 4: "dq1", 5: "dq2", 6: "dq3", 7: "raw"}
+names.update({k + 8: "P:" + v for k, v in list(names.items())})   # peer CTA (block 1); clocks of the two SMs are not aligned
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (0, 10 ** 9)
 for t, r, e, it in ev:
     if lo <= t - t0 <= hi:
-        print(f"{t - t0:8d}  {'        ' * r}{names[r]}.{e}#{it}")
+        print(f"{t - t0:8d}  {'      ' * r}{names[r]}.{e}#{it}")
