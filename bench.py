@@ -236,13 +236,47 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host_x.values())
     d2h = host_y.numel() * host_y.element_size()
 
-    def step_e2e():
-        for k, hx in host_x.items():
-            xs[k].copy_(hx, non_blocking=True)
-        y = step()
-        host_y.copy_(y, non_blocking=True)
+    # The step's inputs are staged on a copy stream in order of first use; the layer that first reads an input waits
+    # for that copy only, so H2D (382 MB over PCIe) overlaps the GEMMs of the inputs that have already landed.  The
+    # whole step -- 8 H2D copies, 184 WQLinear_GEMM.forward launches, the D2H read -- is one two-stream CUDA graph.
+    copy_stream = torch.cuda.Stream()
+    first_use = []
+    for _, _, key in mods:
+        if key not in first_use:
+            first_use.append(key)
 
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2)) / args.steps
+    def step_e2e():
+        cur = torch.cuda.current_stream()
+        copy_stream.wait_stream(cur)
+        evs = {}
+        with torch.cuda.stream(copy_stream):
+            for k in first_use:
+                xs[k].copy_(host_x[k], non_blocking=True)
+                evs[k] = torch.cuda.Event()
+                evs[k].record(copy_stream)
+        seen = set()
+        y = None
+        for _, mod, key in mods:
+            if key not in seen:
+                cur.wait_event(evs[key])
+                seen.add(key)
+            y = mod(xs[key])
+        host_y.copy_(y, non_blocking=True)
+        cur.wait_stream(copy_stream)
+
+    run_e2e = step_e2e
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step_e2e()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph_e2e = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_e2e):
+            step_e2e()
+        run_e2e = graph_e2e.replay
+    ms_e2e = timed(run_e2e, args.steps, max(1, args.warmup // 2)) / args.steps
     e2e_value = world * flops_step / (ms_e2e * 1e-3) / 1e12
 
     if rank != 0:
