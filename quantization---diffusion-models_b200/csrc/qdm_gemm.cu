@@ -313,17 +313,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Drain one accumulator tile: this warp owns 32 TMEM lanes (= 32 output rows starting at `row0`) and walks the tile's
-// columns in chunks of 64.  Per chunk: tcgen05.ld -> scale / bias (fp32, from a per-warp shared copy staged once
-// per tile) -> pack -> SWIZZLE_128B staging -> ONE TMA store of the 32 x 64 box (rows past M are clipped by the
-// tensor map).  The store is asynchronous; the staging buffer is reclaimed by wait_group.read one chunk later.
+// Drain (a share of) one accumulator tile: this warp owns 32 TMEM lanes (= 32 output rows starting at `row0`) and
+// takes the 64-column chunks c_first, c_first + c_step, ...  Per chunk: tcgen05.ld (32-column halves, double
+// buffered in registers so that the load of the next half is in flight while this one is converted) -> scale /
+// bias in fp32 from a per-warp shared copy staged once per tile -> pack -> shared staging -> TMA store:
+//   * whole chunk: ONE store of the 32 x 64 box from a SWIZZLE_128B staging tile (map_y);
+//   * trailing chunk narrower than 64 columns: one store per 16-column slice (map_y16, dense 32 x 32 B slices).
+// Rows past M and columns past N are clipped by the tensor maps.  The stores are asynchronous; the staging buffer
+// is reclaimed by wait_group.read when the next chunk needs it.
 // Measured before this (padded transpose + 8 x (ld.shared, predicated st.global) per chunk, bias from global per
-// 8 columns): 5500 cycles per 128 x 160 tile part -- the critical path of every K <= 640 shape.
-// A trailing chunk narrower than 64 columns is written row-wise from registers.
+// 8 columns, no load/convert overlap): 5500 cycles per 128 x 160 tile part -- the critical path of every K <= 640 shape.
 template <int BLOCK_N, int KIND, bool BF16>
-__device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtensorMap* map_y, uint32_t stg, float* vec_sm,
-                                               uint32_t taddr0, int row0, int n0, int lane) {
-  uint16_t* y = reinterpret_cast<uint16_t*>(p.y);
+__device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtensorMap* map_y, const CUtensorMap* map_y16,
+                                               uint32_t stg, float* vec_sm, uint32_t taddr0, int row0, int n0, int lane,
+                                               int c_first, int c_step) {
   const int n_end = min(n0 + p.tile_n, p.N);   // columns of this tile that exist
   const int row = row0 + lane;
   float sxr = 1.f;
@@ -347,13 +350,16 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
     }
     __syncwarp();
   }
-  // 32-column halves, double buffered in registers: the tcgen05.ld of half h + 1 is in flight while half h is
-  // converted (one ld + wait per half was 40 % of a chunk's time when issued back to back with its use)
+  auto halves_in = [&](int c) {   // 32-column halves of chunk c that hold columns of the tile
+    const int w = n_end - (n0 + c * EPI_COLS);
+    return w <= 0 ? 0 : (w > 32 ? 2 : 1);
+  };
   auto process_half = [&](const uint32_t (&v)[32], int h) {
     const int c = h >> 1, hh = h & 1;
     const int nc = n0 + c * EPI_COLS;                       // first column of the 64-column chunk
-    const bool whole = nc + EPI_COLS <= n_end;
-    if (whole && hh == 0) {   // the previous store of this warp must have read the staging buffer before it is overwritten
+    const int width = min(EPI_COLS, n_end - nc);            // columns of the chunk inside the tile
+    const bool whole = width == EPI_COLS;
+    if (hh == 0) {   // the previous stores of this warp must have read the staging buffer before it is overwritten
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
     }
@@ -378,33 +384,50 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
       o.y = pack_out2<KIND, BF16>(f[2], f[3]);
       o.z = pack_out2<KIND, BF16>(f[4], f[5]);
       o.w = pack_out2<KIND, BF16>(f[6], f[7]);
-      if (whole) {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + uint32_t(lane) * 128u + (uint32_t((hh * 4 + j8) ^ (lane & 7)) << 4)),
-                     "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
-                     : "memory");
-      } else if (row < p.M && n0 + col < n_end) {
-        *reinterpret_cast<uint4*>(y + int64_t(row) * p.N + n0 + col) = o;
-      }
+      const uint32_t g16 = uint32_t(hh * 4 + j8);            // 16-byte column group inside the chunk
+      const uint32_t dst = whole ? stg + uint32_t(lane) * 128u + ((g16 ^ uint32_t(lane & 7)) << 4)
+                                 : stg + (g16 >> 1) * 1024u + uint32_t(lane) * 32u + (g16 & 1u) * 16u;
+      if (whole || int(g16) * 8 < width)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
     }
-    if (whole && hh == 1) {
+    if (hh == halves_in(c) - 1) {   // chunk complete
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) tma_store_2d(map_y, stg, nc, row0);
+      if (lane == 0) {
+        if (whole) {
+          tma_store_2d(map_y, stg, nc, row0);
+        } else {
+          for (int sl = 0; sl * 16 < width; ++sl) tma_store_2d(map_y16, stg + uint32_t(sl) * 1024u, nc + sl * 16, row0);
+        }
+      }
     }
   };
-  const int n_halves = (n_end - n0 + 31) / 32;
+  // walk the halves of this warp's chunks with two register buffers
+  int c = c_first;
+  if (halves_in(c) == 0) return;
+  int h = 2 * c;
+  auto next_half = [&](int& hn, int& cn) {   // successor of half h of chunk c, or hn = -1
+    if ((h & 1) == 0 && halves_in(c) == 2) { hn = h + 1; cn = c; return; }
+    cn = c + c_step;
+    hn = (cn * EPI_COLS < BLOCK_N && halves_in(cn) > 0) ? 2 * cn : -1;
+  };
   uint32_t va[32], vb[32];
-  tmem_ld32(taddr0, va);
+  tmem_ld32(taddr0 + h * 32, va);
 #pragma unroll 1
-  for (int h = 0; h < n_halves; h += 2) {
+  for (;;) {
+    int hn, cn;
+    next_half(hn, cn);
     tmem_ld_wait();
-    if (h + 1 < n_halves) tmem_ld32(taddr0 + (h + 1) * 32, vb);
+    if (hn >= 0) tmem_ld32(taddr0 + hn * 32, vb);
     process_half(va, h);
-    if (h + 1 < n_halves) {
-      tmem_ld_wait();
-      if (h + 2 < n_halves) tmem_ld32(taddr0 + (h + 2) * 32, va);
-      process_half(vb, h + 1);
-    }
+    if (hn < 0) break;
+    h = hn; c = cn;
+    next_half(hn, cn);
+    tmem_ld_wait();
+    if (hn >= 0) tmem_ld32(taddr0 + hn * 32, va);
+    process_half(vb, h);
+    if (hn < 0) break;
+    h = hn; c = cn;
   }
 }
 
@@ -717,7 +740,7 @@ template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
 __global__ void __launch_bounds__(Cfg<BLOCK_N, KIND>::THREADS, 1)
 qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_z,
-                const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
+                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y16, const GemmParams p) {
   using C = Cfg<BLOCK_N, KIND>;
   using R = RawCfg<BLOCK_N>;
   constexpr int STAGES = C::STAGES;
@@ -867,15 +890,17 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int ew = warp - 4;  // TMEM lane quarter this warp may read (warp % 4)
     const uint32_t stg = epi_base + ew * EPI_STG_BYTES;
     float* vec_sm = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4) * (KIND == G_I8 ? 2 : 1);
-    if (lane == 0) tma_prefetch_desc(&map_y);
+    if (lane == 0) { tma_prefetch_desc(&map_y); tma_prefetch_desc(&map_y16); }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
-                                          m0 + ew * 32, n0, lane);
+      // the CTA's last tile is shared with the (by then idle) dequant warps: chunks 0, 3, ... stay here
+      const bool last = KIND == G_W4 && tile + int(gridDim.x) >= num_tiles;
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, &map_y16, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+                                          m0 + ew * 32, n0, lane, 0, last ? 3 : 1);
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -891,6 +916,21 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       w4_producer_loop<BLOCK_N, BF16, STAGES, C::STAGE_BYTES, false>(
           p, threadIdx.x - 256, lane, blockIdx.x, gridDim.x, num_tiles, n_tiles, num_kb, tile_n, 0, tile_n,
           smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, bar_base);
+    }
+    // ---- help drain the CTA's last tile: two more warp sets (TMEM lane quarter = warp % 4) take chunks 1, 4, ... and
+    // 2, 5, ...; staging lives in the pipeline stages, which are idle once the last accumulator is complete
+    const int my_tiles = int(blockIdx.x) < num_tiles ? (num_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+    if (my_tiles > 0) {
+      const int lt = my_tiles - 1, tile = int(blockIdx.x) + lt * int(gridDim.x);
+      const int acc = lt & 1, dw = warp - 8, ew = dw & 3, set = 1 + (dw >> 2);
+      const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
+      mbar_wait(tmem_full_bar(acc), uint32_t(lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t stg = smem_base + A_STAGE_BYTES + uint32_t(dw) * EPI_STG_BYTES;                    // B part of stage 0
+      float* vec_sm = reinterpret_cast<float*>(smem_gen + C::STAGE_BYTES + A_STAGE_BYTES) + dw * 256;   // B part of stage 1
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, &map_y16, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+                                          m0 + ew * 32, n0, lane, set, 3);
+      if (lane == 0) tma_store_wait_all();
     }
   }
 
@@ -934,7 +974,7 @@ template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<BLOCK_N, KIND>::THREADS, 1)
 qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_z,
-                 const __grid_constant__ CUtensorMap map_y, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y16, const GemmParams p) {
   using C = Cfg2<BLOCK_N, KIND>;
   constexpr int STAGES = C::STAGES;
   constexpr int NLOC = C::NLOC;
@@ -1093,7 +1133,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int ew = warp - 4;
     const uint32_t stg = epi_base + ew * EPI_STG_BYTES;
     float* vec_sm = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4) * (KIND == G_I8 ? 2 : 1);
-    if (lane == 0) tma_prefetch_desc(&map_y);
+    if (lane == 0) { tma_prefetch_desc(&map_y); tma_prefetch_desc(&map_y16); }
     int acc = 0;
     uint32_t acc_phase = 0;
     TRC_DECL;
@@ -1103,8 +1143,9 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(tmem_full_bar(acc), acc_phase);
       if (threadIdx.x == 128) TRC(p.trace, 2, 1000000 + trc_it);
       tc_fence_after();
-      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
-                                          m0 + ew * 32, n0, lane);
+      const bool last = KIND == G_W4 && tile + num_pairs >= num_tiles;   // shared with the dequant warps, see below
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, &map_y16, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+                                          m0 + ew * 32, n0, lane, 0, last ? 3 : 1);
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 128) TRC(p.trace, 2, 2000000 + trc_it);
@@ -1123,6 +1164,21 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       w4_producer_loop<NLOC, BF16, STAGES, C::STAGE_BYTES, true>(
           p, threadIdx.x - 256, lane, pair, num_pairs, num_tiles, n_tiles, num_kb, tile_n, int(rank) * nloc, nloc,
           smem_base + A_STAGE_BYTES, bar_base + 8u * STAGES, leader_full0);
+    }
+    // ---- help drain the pair's last tile (same scheme as the single-CTA kernel): the exposed tail of every launch
+    const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+    if (my_tiles > 0) {
+      const int lt = my_tiles - 1, tile = pair + lt * num_pairs;
+      const int acc = lt & 1, dw = warp - 8, ew = dw & 3, set = 1 + (dw >> 2);
+      const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
+      mbar_wait(tmem_full_bar(acc), uint32_t(lt >> 1) & 1u);
+      tc_fence_after();
+      // staging: B parts (16 KB each) of stages 0 and 1, fp32 vectors: B part of stage 2
+      const uint32_t stg = smem_base + uint32_t(dw >> 2) * C::STAGE_BYTES + A_STAGE_BYTES + uint32_t(dw & 3) * EPI_STG_BYTES;
+      float* vec_sm = reinterpret_cast<float*>(smem_gen + 2 * C::STAGE_BYTES + A_STAGE_BYTES) + dw * 256;
+      epilogue_drain<BLOCK_N, KIND, BF16>(p, &map_y, &map_y16, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N,
+                                          m0 + ew * 32, n0, lane, set, 3);
+      if (lane == 0) tma_store_wait_all();
     }
   }
 
@@ -1196,7 +1252,7 @@ int choose_tile_n(int64_t M, int64_t N, bool pair) {
 
 struct Maps {
   CUtensorMap a, b, s, z;   // b: B operand (or packed qweight), s / z: W4 scales / zero points (raw TMA path)
-  CUtensorMap y;            // output [M, N], 32 x 64 boxes for the epilogue's TMA stores
+  CUtensorMap y, y16;       // output [M, N]: 32 x 64 boxes (SWIZZLE_128B) and 32 x 16 slices (dense) for the epilogue's TMA stores
   bool raw = false;
 };
 
@@ -1212,7 +1268,7 @@ int launch_gemm(const Maps& m, const GemmParams& p, cudaStream_t st) {
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + p.tile_n - 1) / p.tile_n;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < QDM_NUM_SMS ? tiles : QDM_NUM_SMS;
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, p);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, m.y16, p);
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
@@ -1236,7 +1292,7 @@ int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
     cudaMemset(tbuf, 0, 16 * 2048 * sizeof(long long));
     GemmParams pt = p;
     pt.trace = tbuf;
-    kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, pt);
+    kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, m.y16, pt);
     cudaDeviceSynchronize();
     static long long host[16 * 2048];
     cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost);
@@ -1248,7 +1304,7 @@ int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
     return QDM_OK;
   }
 #endif
-  kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, p);
+  kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, m.y16, p);
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
@@ -1301,6 +1357,7 @@ extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void
   Maps m;
   if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
   if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
+  if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
   const bool pair = use_pair(p);
@@ -1321,6 +1378,7 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   Maps m;
   if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
   if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
+  if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
   if ((rc = make_map(&m.b, w_kn, 2, K, N, 64, 64))) return rc;
   m.s = m.a; m.z = m.a;
   GemmParams p{};
@@ -1344,6 +1402,7 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   Maps m;
   if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
   if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
+  if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.group = group;
   p.qweight = qweight; p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
@@ -1376,6 +1435,7 @@ extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq
   Maps m;
   if ((rc = make_map(&m.a, xq, 1, M, K, 128, BLOCK_M))) return rc;
   if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
+  if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.sx = sx; p.sw = sw; p.bias = bias; p.y = y; p.is_bf16 = out_dtype == QDM_BF16;
   const bool pair = use_pair(p);
