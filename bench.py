@@ -75,6 +75,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def step_traffic():
+    """DRAM bytes of one step (sum over its 184 launches) from the committed ncu launch list, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_traffic_r01.json")) as f:
+            return json.load(f)["dram_bytes_per_step"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def layer_list():
     shapes = importlib.import_module("quantization---diffusion-models_b200.shapes")
     return shapes, shapes.sd15_unet_linears(batch=8, cfg=True)
@@ -297,9 +306,12 @@ def run_ours(args):
         "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
-                     "kernel": "qdm_gemm_kernel<*, G_W4, fp16>", "peak_kind": "bf16 cuBLAS sustained, " + peaks["source"],
-                     "note": "2*M*N*K summed over the 184 launches / CUDA-event time of the step; 65 of the launches (K or N = 320) are HBM-bound shapes"},
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": step_traffic(),
+                     "kernel": "qdm_gemm2_kernel<256, G_W4, fp16, raw-TMA> (160 launches) + qdm_gemm_kernel (24 small-M launches)",
+                     "peak_kind": "bf16 cuBLAS sustained, " + peaks["source"],
+                     "note": "2*M*N*K summed over the step's 184 launches / CUDA-event time of the step (one CUDA graph); traffic = DRAM read+write "
+                             "bytes of the same 184 launches from the committed ncu launch list (profiles/step_traffic_r01.json; algorithmic bytes "
+                             "9.87 GB per step); 65 launches (K or N = 320) are HBM-bound shapes, per-shape roofline in profiles/README.md"},
         "clocks": clocks,
     }
     if world == 1:
@@ -321,18 +333,36 @@ def run_tables(args):
     peaks = measured_peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def time_fn(fn, iters=10):
-        for _ in range(3):
-            fn()
-        evs = []
-        for _ in range(iters):
-            flush.zero_()  # 256 MB write: evicts L2 between timed launches
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
-            evs.append((e0, e1))
+    def graph_ms(body, reps=10):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b) for a, b in evs)
-        return ts[len(ts) // 2]
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            for _ in range(reps):
+                body()
+        g_.replay()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g_.replay(); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / reps)
+        return best
+
+    flush_ms = graph_ms(lambda: flush.zero_())
+
+    def time_fn(fn):
+        """GPU-side time of one launch: a CUDA graph of 10 x (256 MB L2 flush, launch) minus the flushes alone, so that
+        neither host launch overhead (Python, ctypes, tensor-map encode) nor a warm L2 enters the number."""
+        def body():
+            flush.zero_()
+            fn()
+        return max(graph_ms(body) - flush_ms, 1e-4)
 
     if args.sweep:
         cases = []

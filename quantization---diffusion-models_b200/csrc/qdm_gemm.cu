@@ -1120,10 +1120,15 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ++trc_it;
           const uint32_t raw = raw_base + uint32_t(rs) * R::BYTES;
           const int grow = j * gdiv / gmul;
+#ifdef QDM_EXP_NORAW   // timing experiment only (wrong results): what do the raw TMA loads cost?
+          (void)raw; (void)grow; (void)tx;
+          mbar_arrive(raw_full_bar(rs));
+#else
           mbar_expect_tx(raw_full_bar(rs), tx);
           tma_load_2d(raw, &map_b, raw_full_bar(rs), (n0 >> 3) & ~3, j * 128);
           tma_load_2d(raw + R::QW_BYTES, &map_s, raw_full_bar(rs), n0, grow);
           tma_load_2d(raw + R::QW_BYTES + R::SC_BYTES, &map_z, raw_full_bar(rs), (n0 >> 3) & ~3, grow);
+#endif
           if (++rs == C::RAW_N) { rs = 0; rphase ^= 1; }
         }
       }
