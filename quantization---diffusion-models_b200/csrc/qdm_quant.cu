@@ -564,13 +564,18 @@ quant_rows_thread_kernel(const T* __restrict__ x, int64_t rows, int cols, float 
     group_params<T, MODE>(mx, mn, max_int, s, z);
     if (scales) scales[row] = ElemTraits<T>::from_f(s);
     if (zeros && MODE == Q_ZP) zeros[row] = ElemTraits<T>::from_f(z);
+    const float amax = (MODE == Q_ZP) ? fmaxf(fabsf(mx), fabsf(mn)) : mx;
+    const bool fast = fastdiv_ok<T>(s, amax);              // reciprocal division, see qdm_common.cuh
+    const float r = rcp_approx(s);
+    const float lo = (MODE == Q_ZP) ? __fsub_rn(0.f, z) : min_int, hi = (MODE == Q_ZP) ? __fsub_rn(max_int, z) : max_int;
 #pragma unroll
     for (int e = 0; e < kMaxCols; ++e) {
       if (e < cols) {
-        float code;
-        float d = rtn_elem<T>(v[e], s, z, min_int, max_int, MODE == Q_ZP, MODE != Q_SYM_NOCLAMP, code);
-        if (dq) dq[row * cols + e] = ElemTraits<T>::from_f(d);
-        if (codes) codes[row * cols + e] = code_to_i8<MODE>(code);
+        float q = rint_T<T>(rnd<T>(fast ? div_by_rcp<false>(v[e], s, r) : __fdiv_rn(v[e], s)));
+        if (MODE != Q_ZP) q = copysignf(q, v[e]);
+        if (MODE != Q_SYM_NOCLAMP) q = fminf(fmaxf(q, lo), hi);
+        if (dq) dq[row * cols + e] = ElemTraits<T>::from_f(__fmul_rn(q, s));
+        if (codes) codes[row * cols + e] = code_to_i8<MODE>(MODE == Q_ZP ? __fadd_rn(q, z) : q);
       }
     }
   }
