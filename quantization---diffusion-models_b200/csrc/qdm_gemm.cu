@@ -175,6 +175,14 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// CTA-pair TMA load multicast to the CTAs of `mask` (same CTA-relative destination offset in each); the completion
+// bytes of every destination CTA are counted on the barrier at `bar`'s offset in the leader (even rank) of THAT CTA's pair
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 template <int KIND>
 __device__ __forceinline__ void umma_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
   if (KIND == G_I8) {
@@ -191,10 +199,10 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_c, uint64_t da, uint64_t
         : "memory");
   }
 }
-// commit to the same barrier offset in both CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+// commit to the same barrier offset in the CTAs of `mask` (both CTAs of the pair; all four CTAs of a quad cluster)
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
+               "h"(mask)
                : "memory");
 }
 
@@ -970,8 +978,12 @@ struct Cfg2 {
   static constexpr int RAW_EMPTY_COUNT = 2 * NUM_DQ_WARPS / RAW_GROUPS;
 };
 
-template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<BLOCK_N, KIND>::THREADS, 1)
+// QUAD: clusters of FOUR CTAs = two pairs that work on the same 256 rows and on adjacent n-tiles.  The A operand is the
+// same for both pairs, so each CTA fetches only 64 of its 128 A rows and multicasts them to its counterpart in the other
+// pair: half the TMA rows per k-block per SM (the TMA engine serves ~1 row of 128 B per 3.3 cycles and was the limiter
+// of every W4 shape).  A stage may be refilled once BOTH pairs have consumed it (empty barriers count two commits).
+template <int BLOCK_N, int KIND, bool BF16, bool RAWT, bool QUAD>
+__global__ void __cluster_dims__(QUAD ? 4 : 2, 1, 1) __launch_bounds__(Cfg2<BLOCK_N, KIND>::THREADS, 1)
 qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_z,
                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y16, const GemmParams p) {
@@ -995,12 +1007,20 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + C::RAW_BYTES + 8 * (2 * STAGES + 4 + 2 * RAW_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();            // rank in the cluster: 0..1 (pair) or 0..3 (quad)
+  const uint32_t rank = crank & 1u;                    // role inside the CTA pair: 0 = leader
+  const int pgrp = QUAD ? int(crank >> 1) : 0;         // which pair of the quad
+  const uint32_t leader_crank = crank & ~1u;
   const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int tile_n = p.tile_n, nloc = p.tile_n / 2;   // this CTA holds `nloc` of the tile's B columns
-  const int n_tiles = (p.N + tile_n - 1) / tile_n;
+  // tile sequence of this pair: tiles pair, pair + num_pairs, ... of an [m_tiles, n_tiles] grid, n fastest.  In a quad the
+  // two pairs take the even / odd n-tiles of the same m-tile; n_tiles is rounded up to even (a tile past N loads zeros
+  // and stores nothing).
+  const int n_tiles_real = (p.N + tile_n - 1) / tile_n;
+  const int n_tiles = QUAD ? (n_tiles_real + 1) & ~1 : n_tiles_real;
   const int num_tiles = m_tiles * n_tiles;
+  const int cl = int(blockIdx.x) / (QUAD ? 4 : 2), num_cl = int(gridDim.x) / (QUAD ? 4 : 2);
+  const int pair = QUAD ? 2 * cl + pgrp : cl, num_pairs = QUAD ? 2 * num_cl : num_cl;
   const int num_kb = (p.K + C::K_PER_BLOCK - 1) / C::K_PER_BLOCK;
 
   if (warp == 0 && lane == 0) {
@@ -1011,7 +1031,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), (KIND == G_W4 && RAWT) ? C::FULL_COUNT_RAW : C::FULL_COUNT);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), QUAD ? 2 : 1);   // quad: both pairs' MMA issuers commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
@@ -1034,8 +1054,9 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   cluster_sync_all();   // barrier inits and TMEM allocation of BOTH CTAs are visible before anything remote happens
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
-  const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
+  const uint32_t leader_full0 = mapa_shared(full_bar(0), leader_crank);
+  const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), leader_crank);
+  const uint16_t pair_mask = uint16_t(3u << (2 * pgrp)), all_mask = QUAD ? uint16_t(0xF) : uint16_t(0x3);
 
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs; each loads its own halves)
@@ -1058,7 +1079,12 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           // the peer's TMA bytes land on the leader's barrier too; the peer itself does not arrive (its loads of
           // phase n+1 cannot start before its `empty` barrier says the leader consumed phase n)
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (A_STAGE_BYTES + (KIND == G_W4 ? 0 : nloc * ROW_BYTES)));
-          tma_load_2d_pair(a_dst, &map_a, lf, kc, m0);
+          if (QUAD) {   // my 64 of the 128 rows, to me and to my counterpart in the other pair
+            tma_load_2d_pair_mc(a_dst + uint32_t(pgrp) * (64 * ROW_BYTES), &map_a, lf, kc, m0 + pgrp * 64,
+                                uint16_t((1u << rank) | (1u << (rank + 2))));
+          } else {
+            tma_load_2d_pair(a_dst, &map_a, lf, kc, m0);
+          }
           if (KIND != G_W4) tma_load_2d_pair(b_dst, &map_b, lf, kc, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -1082,7 +1108,9 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
+#ifndef QDM_EXP_NOFULLWAIT   // timing experiment only (wrong results): the tensor pipe alone, operands never waited for
           mbar_wait(full_bar(stage), phase);
+#endif
           TRC(p.trace, 1, 2000000 + trc_it);
           ++trc_it;
           tc_fence_after();
@@ -1095,8 +1123,8 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                      : make_smem_desc(b_addr + k * 32, 16, 1024);
             umma_pair<KIND>(tmem_c, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit_pair(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc));
+          umma_commit_pair(empty_bar(stage), all_mask);
+          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc), pair_mask);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1237,8 +1265,13 @@ int make_map(CUtensorMap* map, const void* ptr, int elem_bytes, int64_t rows, in
 // so that the persistent grid is not left with a nearly empty last wave (80 tiles on 74 CTA pairs cost two full
 // waves).  Model per (tile, k-block), in cycles: tensor pipe 2*tn, shared-memory traffic (A written + read,
 // B written + read) 256 + tn for a CTA pair and 256 + 2*tn for a single CTA, plus a fixed per-tile cost.
-int choose_tile_n(int64_t M, int64_t N, bool pair) {
-  const int64_t rows = pair ? 2 * BLOCK_M : BLOCK_M, units = pair ? QDM_NUM_SMS / 2 : QDM_NUM_SMS;
+int g_quad_units = 32;   // resident quad clusters (a cluster must fit in one GPC); refined by the occupancy query at first launch
+
+// mode: 1 single CTA, 2 CTA pair, 4 quad cluster (two pairs on adjacent n-tiles sharing the A loads)
+int choose_tile_n(int64_t M, int64_t N, int mode, double* cost_out = nullptr) {
+  const bool pair = mode >= 2;
+  const int64_t rows = pair ? 2 * BLOCK_M : BLOCK_M;
+  const int64_t units = mode == 4 ? g_quad_units : pair ? QDM_NUM_SMS / 2 : QDM_NUM_SMS;
   const int64_t m_tiles = (M + rows - 1) / rows;
   const int n_cap = int((N + 15) / 16 * 16);
   int best = 256;
@@ -1246,12 +1279,16 @@ int choose_tile_n(int64_t M, int64_t N, bool pair) {
   for (int tn = 256; tn >= 32; tn -= 16) {
     if (tn > n_cap && tn != 256) continue;
     const int t = tn > n_cap ? n_cap : tn;
-    const int64_t n_tiles = (N + t - 1) / t;
+    int64_t n_tiles = (N + t - 1) / t;
+    if (mode == 4) n_tiles = (n_tiles + 1) / 2;          // a quad takes two n-tiles at a time
     const int64_t waves = (m_tiles * n_tiles + units - 1) / units;
-    const double mma = 2.0 * t, smem = pair ? 256.0 + t : 256.0 + 2.0 * t;
-    const double cost = double(waves) * ((mma > smem ? mma : smem) + 64.0);
+    // cycles per k-block: tensor pipe ~2 t; operand delivery (TMA rows: A 128 or 64 per CTA + packed rows) -- measured
+    // ~600 + t for a pair, ~350 + t expected for a quad
+    const double mma = 2.0 * t, feed = mode == 4 ? 350.0 + t : pair ? 256.0 + t : 256.0 + 2.0 * t;
+    const double cost = double(waves) * ((mma > feed ? mma : feed) + 64.0);
     if (cost < best_cost * 0.999) { best_cost = cost; best = t; }
   }
+  if (cost_out) *cost_out = best_cost;
   return best;
 }
 
@@ -1259,6 +1296,7 @@ struct Maps {
   CUtensorMap a, b, s, z;   // b: B operand (or packed qweight), s / z: W4 scales / zero points (raw TMA path)
   CUtensorMap y, y16;       // output [M, N]: 32 x 64 boxes (SWIZZLE_128B) and 32 x 16 slices (dense) for the epilogue's TMA stores
   bool raw = false;
+  bool quad = false;        // W4 raw path on quad clusters: the A map has 64-row boxes
 };
 
 template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
@@ -1278,18 +1316,41 @@ int launch_gemm(const Maps& m, const GemmParams& p, cudaStream_t st) {
   return QDM_OK;
 }
 
-template <int BLOCK_N, int KIND, bool BF16, bool RAWT>
+template <int BLOCK_N, int KIND, bool BF16, bool RAWT, bool QUAD>
 int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
   using C = Cfg2<BLOCK_N, KIND>;
-  auto kern = qdm_gemm2_kernel<BLOCK_N, KIND, BF16, RAWT>;
+  auto kern = qdm_gemm2_kernel<BLOCK_N, KIND, BF16, RAWT, QUAD>;
   static bool attr_set = false;
   if (!attr_set) {
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (p.N + p.tile_n - 1) / p.tile_n;
-  const int tiles = m_tiles * n_tiles;
-  const int pairs = tiles < QDM_NUM_SMS / 2 ? tiles : QDM_NUM_SMS / 2;
+  int pairs;
+  if (QUAD) {   // whole clusters of two pairs; a cluster must fit inside one GPC, so fewer than 148 / 4 may be resident
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(QDM_NUM_SMS / 4 * 4);
+      cfg.blockDim = dim3(C::THREADS);
+      cfg.dynamicSmemBytes = C::SMEM_BYTES;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = QDM_NUM_SMS / 4 - 5; }
+      max_clusters = n < QDM_NUM_SMS / 4 ? n : QDM_NUM_SMS / 4;
+      g_quad_units = max_clusters;
+      if (getenv("QDM_DEBUG")) fprintf(stderr, "qdm: %d quad clusters resident\n", max_clusters);
+    }
+    const int st_tiles = m_tiles * ((n_tiles + 1) / 2);
+    pairs = 2 * (st_tiles < max_clusters ? st_tiles : max_clusters);
+  } else {
+    const int tiles = m_tiles * n_tiles;
+    pairs = tiles < QDM_NUM_SMS / 2 ? tiles : QDM_NUM_SMS / 2;
+  }
 #ifdef QDM_TRACE
   if (getenv("QDM_TRACE")) {
     static long long* tbuf = nullptr;
@@ -1314,17 +1375,23 @@ int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
   return QDM_OK;
 }
 
-// 0: heuristic, 1: force the single-CTA kernel, 2: force the CTA-pair kernel (bring-up / A-B timing)
+// 0: heuristic, 1: force the single-CTA kernel, 2: force the CTA-pair kernel, 4: force quad clusters where the kernel
+// supports them (bring-up / A-B timing)
 int g_force_ctas = 0;
 bool use_pair(const GemmParams& p) {
   if (g_force_ctas == 1) return false;
-  if (g_force_ctas == 2) return true;
+  if (g_force_ctas >= 2) return true;
   return p.M > BLOCK_M;   // a second 128-row half exists
 }
 
 template <int KIND, bool RAWT>
 int dispatch_gemm_r(const Maps& m, const GemmParams& p, bool pair, cudaStream_t st) {
-  if (pair) return p.is_bf16 ? launch_gemm2<256, KIND, true, RAWT>(m, p, st) : launch_gemm2<256, KIND, false, RAWT>(m, p, st);
+  if (pair && m.quad) {
+    if (KIND == G_W4 && RAWT)   // the only instantiation built for quad clusters
+      return p.is_bf16 ? launch_gemm2<256, KIND, true, RAWT, KIND == G_W4 && RAWT>(m, p, st)
+                       : launch_gemm2<256, KIND, false, RAWT, KIND == G_W4 && RAWT>(m, p, st);
+  }
+  if (pair) return p.is_bf16 ? launch_gemm2<256, KIND, true, RAWT, false>(m, p, st) : launch_gemm2<256, KIND, false, RAWT, false>(m, p, st);
   return p.is_bf16 ? launch_gemm<256, KIND, true, RAWT>(m, p, st) : launch_gemm<256, KIND, false, RAWT>(m, p, st);
 }
 template <int KIND>
@@ -1346,7 +1413,7 @@ int check_common(const char* fn, const void* x, const void* w, void* y, int dtyp
 }  // namespace
 
 extern "C" int qdm_set_gemm_mode(int ctas) {
-  QDM_REQUIRE(ctas >= 0 && ctas <= 2, "qdm_set_gemm_mode: 0 (auto), 1 (single CTA) or 2 (CTA pair)");
+  QDM_REQUIRE(ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4, "qdm_set_gemm_mode: 0 (auto), 1 (single CTA), 2 (CTA pair) or 4 (quad cluster)");
   g_force_ctas = ctas;
   return QDM_OK;
 }
@@ -1366,7 +1433,7 @@ extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
   const bool pair = use_pair(p);
-  p.tile_n = choose_tile_n(M, N, pair);
+  p.tile_n = choose_tile_n(M, N, pair ? 2 : 1);
   if ((rc = make_map(&m.b, w, 2, N, K, 64, pair ? p.tile_n / 2 : p.tile_n))) return rc;
   m.s = m.a; m.z = m.a;
   return dispatch_gemm<G_F16>(m, p, pair, (cudaStream_t)stream);
@@ -1388,7 +1455,7 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   m.s = m.a; m.z = m.a;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
-  p.tile_n = choose_tile_n(M, N, false);
+  p.tile_n = choose_tile_n(M, N, 1);
   return dispatch_gemm<G_F16_KN>(m, p, false, (cudaStream_t)stream);
 }
 
@@ -1405,18 +1472,24 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
   Maps m;
-  if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
   if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
   if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.group = group;
   p.qweight = qweight; p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
   const bool pair = use_pair(p);
-  p.tile_n = choose_tile_n(M, N, pair);
-  m.b = m.a; m.s = m.a; m.z = m.a;
   // packed operands by TMA when their row strides are multiples of 16 bytes (N % 32 == 0): boxes are always the
   // full tile part the kernel was built for (columns past the tile are loaded and ignored, past N zero-filled)
   m.raw = (N % 32 == 0) && qdm_aligned16(qzeros) && !getenv("QDM_W4_NO_TMA");   // env: A/B switch for bring-up
+  double cost2 = 0, cost4 = 0;
+  p.tile_n = choose_tile_n(M, N, pair ? 2 : 1, &cost2);
+  if (pair && m.raw && g_force_ctas != 2) {   // quad clusters when the cost model prefers them (or when forced)
+    const int t4 = choose_tile_n(M, N, 4, &cost4);
+    (void)cost4;   // measured: no gain from the shared A loads (profiles/README.md), so quads run only when forced
+    if (g_force_ctas == 4) { m.quad = true; p.tile_n = t4; }
+  }
+  if ((rc = make_map(&m.a, x, 2, M, K, 64, m.quad ? BLOCK_M / 2 : BLOCK_M))) return rc;
+  m.b = m.a; m.s = m.a; m.z = m.a;
   if (m.raw) {
     const int nloc_max = pair ? 128 : 256, G = int(K / group);
     const int srows = group == 64 ? 2 : 1;   // quantisation groups per raw stage (128 k rows)
@@ -1444,7 +1517,7 @@ extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.sx = sx; p.sw = sw; p.bias = bias; p.y = y; p.is_bf16 = out_dtype == QDM_BF16;
   const bool pair = use_pair(p);
-  p.tile_n = choose_tile_n(M, N, pair);
+  p.tile_n = choose_tile_n(M, N, pair ? 2 : 1);
   if ((rc = make_map(&m.b, wq, 1, N, K, 128, pair ? p.tile_n / 2 : p.tile_n))) return rc;
   m.s = m.a; m.z = m.a;
   return dispatch_gemm<G_I8>(m, p, pair, (cudaStream_t)stream);
