@@ -646,7 +646,7 @@ __device__ __forceinline__ void w4_dequant_loop(int dt, int lane, int first_tile
   };
   static_assert((RAW_N & (RAW_N - 1)) == 0, "raw ring depth must be a power of two");
   int stage = grp % STAGES;
-  uint32_t phase = 0;
+  uint32_t phase = uint32_t(grp / STAGES) & 1u;                // more groups than stages: the first use may be a second lap
   const int my_tiles = first_tile < num_tiles ? (num_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
   const int total = my_tiles * num_kb;                         // pipeline iterations of this CTA
   const int rs_per_tile = (num_kb + 1) >> 1;                   // raw stages (k-block pairs) per tile
