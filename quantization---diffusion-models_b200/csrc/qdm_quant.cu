@@ -581,6 +581,64 @@ quant_rows_thread_kernel(const T* __restrict__ x, int64_t rows, int cols, float 
   }
 }
 
+// Tiny rows with vector traffic (conv weights viewed as [..., kw]: kw = 3 for the 3x3 convolutions that hold 70 % of
+// the SD1.5 UNet's weights, kw = 1 for the 1x1 ones).  A thread takes the smallest run of whole rows that is a whole
+// number of 16-byte vectors (COLS = 3: 8 rows = 3 vectors), so loads and stores are coalesced 16-byte accesses instead
+// of 2-byte ones.  Symmetric modes only (the per-channel path of fake_quant.py:86-93); outputs: dq and / or scales.
+template <typename T, int MODE, int COLS>
+__global__ void __launch_bounds__(kQThreads)
+quant_rows_tiny_kernel(const T* __restrict__ x, int64_t n_chunks, float max_int, float min_int,
+                       T* __restrict__ dq, T* __restrict__ scales) {
+  constexpr int V = ElemTraits<T>::kVec;
+  constexpr int G = (COLS % 8 == 0) ? 8 : (COLS % 4 == 0) ? 4 : (COLS % 2 == 0) ? 2 : 1;   // gcd(COLS, 8)
+  constexpr int GV = (V == 8) ? G : ((COLS % 4 == 0) ? 4 : (COLS % 2 == 0) ? 2 : 1);      // gcd(COLS, V)
+  constexpr int NVEC = COLS / GV;             // vectors per chunk
+  constexpr int R = V / GV;                   // rows per chunk
+  static_assert(NVEC * V == R * COLS, "chunk = whole rows = whole vectors");
+  (void)G;
+  const float floor_c = rnd<T>(1e-5f);
+  const float r_max_int = rcp_approx(max_int);
+  for (int64_t c = int64_t(blockIdx.x) * kQThreads + threadIdx.x; c < n_chunks; c += int64_t(gridDim.x) * kQThreads) {
+    float v[NVEC * V];
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      Vec16<T> a = ld_vec16_stream(x + (c * NVEC + i) * V);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[i * V + j] = ElemTraits<T>::to_f(a.v[j]);
+    }
+    float o[NVEC * V];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float mx = 0.f;
+#pragma unroll
+      for (int e = 0; e < COLS; ++e) mx = fmaxf(mx, fabsf(v[r * COLS + e]));
+      const float a = fmaxf(mx, floor_c);
+      const bool fast = fastdiv_ok<T>(max_int, a);
+      const float s = rnd<T>(fast ? div_by_rcp<false>(a, max_int, r_max_int) : __fdiv_rn(a, max_int));
+      if (scales) scales[c * R + r] = ElemTraits<T>::from_f(s);
+      const bool fast2 = fastdiv_ok<T>(s, mx);
+      const float rs = rcp_approx(s);
+#pragma unroll
+      for (int e = 0; e < COLS; ++e) {
+        const float w = v[r * COLS + e];
+        float q = rint_T<T>(rnd<T>(fast2 ? div_by_rcp<false>(w, s, rs) : __fdiv_rn(w, s)));
+        q = copysignf(q, w);
+        if (MODE != Q_SYM_NOCLAMP) q = fminf(fmaxf(q, min_int), max_int);
+        o[r * COLS + e] = __fmul_rn(q, s);
+      }
+    }
+    if (dq) {
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        Vec16<T> a;
+#pragma unroll
+        for (int j = 0; j < V; ++j) a.v[j] = ElemTraits<T>::from_f(o[i * V + j]);
+        st_vec16(dq + (c * NVEC + i) * V, a);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- whole-tensor scale
 template <typename T>
 __global__ void __launch_bounds__(kQThreads)
@@ -960,8 +1018,31 @@ int launch_quant(const T* w, int64_t n_groups, int64_t group, int64_t k_period, 
       quant_group_kernel<T, MODE, false><<<grid, kQThreads, 0, st>>>(
           w, int(n_rows), int(vpr), lpg_shift, int(rpp), max_int, min_int, nullptr, nullptr, nullptr, dq, codes, scales, zeros);
   } else if (group <= 16 && !extras) {
-    quant_rows_thread_kernel<T, MODE><<<grid_for(n_groups, kQThreads), kQThreads, 0, st>>>(
-        w, n_groups, int(group), max_int, min_int, dq, codes, scales, zeros);
+    // whole chunks of rows through the vector kernel (symmetric modes, no int8 codes), the remaining rows one per thread
+    int64_t done_rows = 0;
+    if (MODE != Q_ZP && !codes && aligned && group < V) {
+      const int gv = (group % 8 == 0 && V == 8) ? 8 : (group % 4 == 0) ? 4 : (group % 2 == 0) ? 2 : 1;
+      const int64_t rows_per_chunk = V / gv, n_chunks = n_groups / rows_per_chunk;
+      if (n_chunks > 0) {
+        const int grid = grid_for(n_chunks, kQThreads);
+        switch (group) {
+#define QDM_TINY(C) case C: quant_rows_tiny_kernel<T, MODE, C><<<grid, kQThreads, 0, st>>>(w, n_chunks, max_int, min_int, dq, scales); break;
+          QDM_TINY(1) QDM_TINY(2) QDM_TINY(3) QDM_TINY(4) QDM_TINY(5) QDM_TINY(6) QDM_TINY(7)
+#undef QDM_TINY
+          default: break;
+        }
+        QDM_LAUNCH_CHECK();
+        done_rows = n_chunks * rows_per_chunk;
+      }
+    }
+    if (done_rows < n_groups) {
+      const int64_t rest = n_groups - done_rows, off = done_rows * group;
+      quant_rows_thread_kernel<T, MODE><<<grid_for(rest, kQThreads), kQThreads, 0, st>>>(
+          w + off, rest, int(group), max_int, min_int, dq ? dq + off : nullptr, codes ? codes + off : nullptr,
+          scales ? scales + done_rows : nullptr, zeros ? zeros + done_rows : nullptr);
+    } else {
+      return QDM_OK;
+    }
   } else if (aligned && !extras && group % V == 0 && group <= 32 * V * 16) {
     return launch_rows_reg<T, MODE, false>(w, n_groups, group, max_int, min_int, dq, codes, scales, zeros, nullptr, st);
   } else {

@@ -101,7 +101,7 @@ def test_quant_group_search_fusions(qdm, dt):
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
-@pytest.mark.parametrize("shape", [(320, 1280), (64, 32, 3, 3), (7, 5, 1, 1), (33, 100), (4, 77, 320)])
+@pytest.mark.parametrize("shape", [(320, 1280), (64, 32, 3, 3), (7, 5, 1, 1), (33, 100), (4, 77, 320), (5, 3, 3, 3), (16, 4, 5, 5), (9, 6)])
 def test_rowwise_vs_oracle(qdm, dt, shape):
     x = rand_w(shape, DT[dt], 3, scale=1.0)
     dq, codes, s, _ = qdm.ops.quant_rowwise(x.to(DEV), 8, want_codes=True, want_scales=True)
@@ -111,6 +111,10 @@ def test_rowwise_vs_oracle(qdm, dt, shape):
     assert torch.equal(codes.cpu().to(torch.int32), oc.clamp(-128, 127).to(torch.int32))
     if dt == "f16":
         assert oc.abs().max() <= 127  # fp16 never reaches +-128 (DESIGN.md, 8-bit caveat)
+    # without integer codes the tiny-row shapes (conv kw = 3 / 1) take the vectorised kernel: same bits
+    dq2, _, s2, _ = qdm.ops.quant_rowwise(x.to(DEV), 8, want_scales=True)
+    assert torch.equal(dq2.cpu().view(torch.int16), odq.view(torch.int16)), "dq bits (no-codes path)"
+    assert_bit_equal(s2, os_.reshape(-1), "scales (no-codes path)")
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
