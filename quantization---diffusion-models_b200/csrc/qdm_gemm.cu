@@ -25,6 +25,10 @@
 #include <mutex>
 #include <stdlib.h>
 
+bool qdm_gemm_w4a16_smallm_fits(int64_t M, int64_t N, int64_t K);
+int qdm_gemm_w4a16_smallm(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* bias,
+                          void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int group, cudaStream_t st);
+
 namespace {
 
 // Debug timeline (compile with -DQDM_TRACE, run with QDM_TRACE=1): every role of block 0 logs (tag, clock64) pairs.
@@ -1470,6 +1474,10 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
               "qdm_gemm_w4a16: group=%d must be 64 * 2^j and divide K=%lld", group, (long long)K);
   QDM_REQUIRE(qdm_aligned16(scales) && (!bias || qdm_aligned16(bias)), "qdm_gemm_w4a16: scales/bias must be 16-byte aligned");
   QDM_DEVICE_GATE();
+  // M <= 32 and small weights: latency bound -> the mma.sync kernel of qdm_gemm_smallm.cu (g_force_ctas keeps the
+  // tcgen05 path reachable for A/B timing)
+  if (qdm_gemm_w4a16_smallm_fits(M, N, K) && g_force_ctas == 0 && !getenv("QDM_W4_NO_SMALLM"))
+    return qdm_gemm_w4a16_smallm(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);
   if ((rc = get_encode_fn())) return rc;
   Maps m;
   if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;

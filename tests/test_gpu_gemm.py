@@ -42,7 +42,8 @@ def test_gemm_f16(qdm, dt, M, N, K):
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("M,N,K,group", [(128, 128, 128, 128), (256, 256, 256, 64), (300, 320, 320, 64),
                                           (1024, 2432, 2432, 128), (77, 1280, 768, 128), (4096, 2560, 320, 64),
-                                          (1, 1024, 256, 128), (513, 72, 192, 64), (2048, 64, 2432, 128)])
+                                          (1, 1024, 256, 128), (513, 72, 192, 64), (2048, 64, 2432, 128),
+                                          (16, 1280, 1280, 128), (64, 320, 1280, 128), (33, 72, 192, 64), (2, 14592, 2432, 128), (48, 640, 320, 64)])
 def test_gemm_w4a16(qdm, dt, M, N, K, group):
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(DT[dt])
@@ -60,7 +61,8 @@ def test_gemm_w4a16(qdm, dt, M, N, K, group):
     # same product through the decoded weight: the in-mainloop dequant is bit-identical to
     # dequantize_gemm, so the two kernels may differ only by accumulation order
     y_kn = qdm.ops.gemm_f16_kn(x.to(DEV), qdm.ops.dequant_awq(qweight, qzeros, scales, group), b.to(DEV))
-    assert max_rel_err(y, y_kn.cpu()) <= 2e-3
+    # (one ulp of the output dtype at the largest magnitude: fp16 2^-11, bf16 2^-8)
+    assert max_rel_err(y, y_kn.cpu()) <= (2e-3 if dt == "f16" else 8e-3)
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
