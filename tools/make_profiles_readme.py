@@ -1,0 +1,56 @@
+"""Regenerate profiles/README.md from the committed JSON tables + the hand-written profiles/_notes.md."""
+import json, os
+R = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
+ab = json.load(open(os.path.join(R, "kernels_ab_r01.json")))
+sw = json.load(open(os.path.join(R, "gemm_sweep_r01.json")))
+ly = json.load(open(os.path.join(R, "gemm_layers_r01.json")))
+out = []
+A = out.append
+A("# profiles/ — round 1 evidence (B200, sm_100a)\n")
+A("All numbers were measured on the pool's B200 through `gpurun`; peaks are the driver-written `MEASURED_PEAKS.json`")
+A(f"(HBM copy {ab['peaks']['hbm']:.0f} GB/s, cuBLAS bf16 {ab['peaks']['bf16_burst']:.0f} TFLOP/s burst / {ab['peaks']['bf16_sustained']:.0f} sustained).")
+A("Timings: CUDA events on the launching stream after warm-up, GPU-side (launches replayed from a CUDA graph, a 256 MB")
+A("L2 flush between launches, flush time subtracted). ncu captures: `--set full --clock-control none --import-source on`;")
+A("their absolute times are cold-cache / serialised and are used for shares, stall reasons and DRAM bytes only.\n")
+A("## Files\n")
+A("| file | what |\n|---|---|")
+for f, w in [
+    ("launches_bench_step_r01.csv", "ncu launch list of one `bench.py` step (184 launches): duration + DRAM read/write bytes per launch (`tools/step_durations.sh`)"),
+    ("step_by_shape_r01.txt", "the same list aggregated by layer shape with the per-shape roofline (`tools/step_by_shape.py`)"),
+    ("step_traffic_r01.json", "DRAM bytes of the step = `roofline.traffic` of the bench line (6.4 GB measured vs 9.87 GB algorithmic: outputs of one launch are still in L2 when the next starts; no re-reads)"),
+    ("w4a16_gemm_4096x10240x1280_r01.txt", "ncu summary + top stalled SASS, W4A16 CTA-pair kernel, compute-bound shape"),
+    ("w4a16_gemm_4096x1280x1280_r01.txt", "same, mid shape (2 waves of 256x144 tiles)"),
+    ("w4a16_gemm_65536x320x320_r01.txt", "same, HBM-bound shape (K = N = 320)"),
+    ("w8a8_gemm_4096x10240x1280_r01.txt", "ncu summary, W8A8 (`kind::i8`) CTA-pair kernel"),
+    ("kernels_ab_ncu_r01.txt", "ncu summaries of the reduction (a) and quantise/pack (b) kernels on HBM-sized tensors (`tools/prof_ab.py`)"),
+    ("kernels_ab_r01.json", "`bench.py --mode kernels`: GB/s of every (a)/(b) kernel vs the measured HBM peak"),
+    ("gemm_sweep_r01.json", "`bench.py --sweep`: BASELINE config 5 (M 4096-65536, K,N 1536-6144): W4A16 vs our f16 tcgen05 vs cuBLAS vs W8A8"),
+    ("gemm_layers_r01.json", "`bench.py --layers`: every distinct Linear shape of the SD1.5 UNet step"),
+    ("timeline_roles_1232x1280x768_r01.txt", "role timeline (TMA / raw producer / 4 dequant groups / MMA / epilogue, clock64) of one CTA pair, `QDM_TRACE` build + `tools/trace_view.py`"),
+    ("timeline_inputs_320.txt, timeline_inputs_1280.txt", "per k-block: A-load issue, dequant arrival, MMA start (`tools/trace_inputs.py`) — the evidence that the MMA waits for the A tile, not for the dequant"),
+]:
+    A(f"| `{f}` | {w} |")
+A("\n## (a) reductions and (b) quantise / pack — HBM roofline\n")
+A("Tensors: activations 65536 x 2560 fp16 (335 MB), weights 38912 x 2432 fp16 (189 MB); bytes = algorithmic bytes of SURVEY.md §8(d).\n")
+A("| kernel | ms | GB/s | fraction of measured HBM peak |\n|---|---:|---:|---:|")
+for r in ab["rows"]:
+    A(f"| {r['kernel']} | {r['ms']:.4f} | {r['GBps']:.0f} | {r['frac_of_hbm_peak']:.2f} |")
+A("\nStart of the session: quant_group 0.33, fused W*s,/s 0.18, pack 0.24, rowwise 0.50, actquant 0.40, dequant 0.18, awq_wsum 0.15 —")
+A("all issue-bound on IEEE division (MUFU + FCHK + slow-path call per element), FRND/F2I on the XU pipe and 64-bit index")
+A("arithmetic. What changed: exact reciprocal division (2 FMA, exhaustively verified against `__fdiv_rn`), packed half2 chain,")
+A("register-resident rows, nibble-transpose pack, occupancy-sized persistent grids. ncu (kernels_ab_ncu_r01.txt): every one of these")
+A("kernels still issues at 65-75 % of peak — they remain instruction-limited below the HBM roofline, which is where the")
+A("remaining gap of quant_group (zero point), the fused search kernel, the pack and awq_wsum comes from.\n")
+A("## (c) W4A16 / (d) W8A8 GEMM — config 5 sweep (TFLOP/s, GPU-side)\n")
+A("| M | N | K | W4A16 | % of burst peak | % of sustained | our f16 tcgen05 | cuBLAS f16 | W8A8 |\n|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+for r in sw["rows"]:
+    w = r["w4a16"]["tflops"]
+    A(f"| {r['M']} | {r['N']} | {r['K']} | {w:.0f} | {100 * w / sw['peaks']['bf16_burst']:.0f} | {100 * w / sw['peaks']['bf16_sustained']:.0f} | {r['f16_tcgen05']['tflops']:.0f} | {r['cublas_f16']['tflops']:.0f} | {r.get('w8a8_gemm', {}).get('tflops', 0):.0f} |")
+A("\n## SD1.5 UNet step: every distinct Linear shape (GPU-side)\n")
+A("| M | N | K | W4A16 us | TFLOP/s | per-shape roofline TFLOP/s | fraction | our f16 | cuBLAS f16 | W8A8 |\n|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+for r in ly["rows"]:
+    w = r["w4a16"]
+    A(f"| {r['M']} | {r['N']} | {r['K']} | {w['ms'] * 1e3:.1f} | {w['tflops']:.1f} | {w['roof_tflops']:.0f} | {w['frac']:.2f} | {r['f16_tcgen05']['tflops']:.1f} | {r['cublas_f16']['tflops']:.1f} | {r.get('w8a8_gemm', {}).get('tflops', 0):.1f} |")
+A("")
+A(open(os.path.join(R, "_notes.md")).read())
+open(os.path.join(R, "README.md"), "w").write("\n".join(out))
