@@ -1229,6 +1229,207 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------- B-stationary CTA-pair kernel (W4, K <= 384)
+// For the K = 320 layers of the UNet (M = 65536 tokens: 40 of the step's 184 launches, 37 % of its time) a pair's B tile
+// part is tiny: K x nloc fp16 = 80 KB.  The generic kernel re-fetches and re-dequantises it for every one of the pair's
+// ~7-35 tiles and pays packed-operand TMA rows, dequant latency and a B stage per k-block for it.  Here every pair keeps
+// ONE n-tile (grid = n_tiles x floor(74 / n_tiles) pairs, so tile % n_tiles is constant per pair), dequantises its
+// K x nloc part once into shared memory, and then only streams A: 5 stages of 16 KB, one TMA box per k-block.  The
+// dequant warps become a second epilogue warp set after that (chunks alternate between the two sets), because with 5
+// k-blocks per tile the epilogue is as long as the main loop.
+struct CfgBS {
+  static constexpr int NLOC = 128;
+  static constexpr int A_STAGES = 5;
+  static constexpr int BST_KB = 6;                        // resident k-blocks: K <= 384
+  static constexpr int B_KB_BYTES = NLOC * ROW_BYTES;     // 16 KB per k-block
+  static constexpr int RAW_N = 2;                         // raw ring, used once; afterwards staging of epilogue set 1
+  static constexpr int RAW_BYTES = RAW_N * RawCfg<NLOC>::BYTES;
+  static constexpr int EPI_BYTES = 4 * (EPI_STG_BYTES + EPI_VEC_BYTES);
+  static_assert(RAW_BYTES >= EPI_BYTES, "epilogue set 1 stages in the raw ring");
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + BST_KB * B_KB_BYTES + EPI_BYTES + RAW_BYTES + 1024 + BAR_BYTES;
+  static constexpr int THREADS = 512;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int GROUPS = 4;
+};
+
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CfgBS::THREADS, 1)
+qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_z,
+                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y16, const GemmParams p) {
+  using C = CfgBS;
+  using R = RawCfg<C::NLOC>;
+  constexpr int SA = C::A_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // layout: [A stages] [resident B: BST_KB x 16 KB] [epilogue set 0] [raw ring / epilogue set 1] [barriers] [tmem ptr]
+  const uint32_t bst_base = smem_base + SA * A_STAGE_BYTES;
+  const uint32_t epi_base = bst_base + C::BST_KB * C::B_KB_BYTES;
+  const uint32_t raw_base = epi_base + C::EPI_BYTES;
+  const uint32_t bar_base = raw_base + C::RAW_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * SA + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 + a); };
+  auto raw_full_bar = [&](int s) { return bar_base + 8u * (2 * SA + 4 + s); };
+  auto raw_empty_bar = [&](int s) { return bar_base + 8u * (2 * SA + 4 + RAW_STAGES + s); };
+  auto bst_full_bar = [&](int kb) { return bar_base + 8u * (2 * SA + 4 + 2 * RAW_STAGES + kb); };
+  auto bst_free_bar = [&](int kb) { return bar_base + 8u * (2 * SA + 4 + 2 * RAW_STAGES + C::BST_KB + kb); };   // never completes
+  constexpr int kNumBars = 2 * SA + 4 + 2 * RAW_STAGES + 2 * C::BST_KB;
+  static_assert(8 * kNumBars + 8 <= C::BAR_BYTES, "barrier area");
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;   // num_pairs % n_tiles == 0 (host): fixed n-tile per pair
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int tile_n = p.tile_n, nloc = p.tile_n / 2;
+  const int n_tiles = (p.N + tile_n - 1) / tile_n;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / 64;
+  const int n_idx = pair % n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_s); tma_prefetch_desc(&map_z);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 16); }   // 2 sets x 4 warps x 2 CTAs
+    for (int s = 0; s < RAW_STAGES; ++s) { mbar_init(raw_full_bar(s), 1); mbar_init(raw_empty_bar(s), 2 * NUM_DQ_WARPS / C::GROUPS); }
+    for (int kb = 0; kb < C::BST_KB; ++kb) { mbar_init(bst_full_bar(kb), 2 * NUM_DQ_WARPS / C::GROUPS); mbar_init(bst_free_bar(kb), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
+  const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
+  const uint32_t leader_bst_full0 = mapa_shared(bst_full_bar(0), 0);
+
+  // one epilogue warp set: TMEM lane quarter = warp % 4, chunks `set`, set + 2, ...
+  auto epilogue_role = [&](int set, int ew, uint32_t stg, float* vec_sm) {
+    if (lane == 0) { tma_prefetch_desc(&map_y); tma_prefetch_desc(&map_y16); }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      epilogue_drain<256, G_W4, BF16>(p, &map_y, &map_y16, stg, vec_sm, tmem_base + (uint32_t(ew * 32) << 16) + acc * 256,
+                                      m0 + ew * 32, n0, lane, set, 2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer: A only
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * A_STAGE_BYTES);
+          tma_load_2d_pair(smem_base + stage * A_STAGE_BYTES, &map_a, leader_full0 + 8u * stage, kb * 64, m0);
+          if (++stage == SA) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 1, 2 * BLOCK_M, tile_n);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      bool first = true;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (first) mbar_wait(bst_full_bar(kb), 0);   // the resident B part of this k-block has been written (both CTAs)
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = bst_base + kb * C::B_KB_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024);
+            umma_pair<G_W4>(tmem_c, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit_pair(empty_bar(stage), 3);
+          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc), 3);
+          if (++stage == SA) { stage = 0; phase ^= 1; }
+        }
+        first = false;
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================== raw int4 producer: this pair's n-tile, once
+    if (lane == 0 && pair < num_tiles) {
+      const int srows = p.group == 64 ? 2 : 1;
+      const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
+      const uint32_t tx = R::tx_bytes(srows);
+      const int n0 = n_idx * tile_n + int(rank) * nloc;
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int j = 0; 2 * j < num_kb; ++j) {
+        mbar_wait(raw_empty_bar(rs), rphase ^ 1);
+        const uint32_t raw = raw_base + uint32_t(rs) * R::BYTES;
+        const int grow = j * gdiv / gmul;
+        mbar_expect_tx(raw_full_bar(rs), tx);
+        tma_load_2d(raw, &map_b, raw_full_bar(rs), (n0 >> 3) & ~3, j * 128);
+        tma_load_2d(raw + R::QW_BYTES, &map_s, raw_full_bar(rs), n0, grow);
+        tma_load_2d(raw + R::QW_BYTES + R::SC_BYTES, &map_z, raw_full_bar(rs), (n0 >> 3) & ~3, grow);
+        if (++rs == C::RAW_N) { rs = 0; rphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== epilogue set 0
+    const int ew = warp - 4;
+    epilogue_role(0, ew, epi_base + ew * EPI_STG_BYTES,
+                  reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4));
+  } else if (warp >= 8) {
+    // ===================================================== dequant once, then epilogue set 1 (warps 8-11)
+    if (pair < num_tiles) {
+      // one "tile" whose n index is n_idx: stage index == k-block, nothing ever has to be waited for on the B side
+      w4_dequant_loop<C::NLOC, BF16, C::BST_KB, C::B_KB_BYTES, C::RAW_N, C::GROUPS, true>(
+          threadIdx.x - 256, lane, n_idx, 1 << 20, n_idx + 1, 1 << 20, num_kb, tile_n, int(rank) * nloc, nloc, p.group,
+          bst_base, raw_base, bst_free_bar(0), leader_bst_full0, raw_full_bar(0), raw_empty_bar(0), p.trace);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // all dequant warps are done with the raw ring: it becomes staging
+    if (warp < 12) {
+      const int ew = warp - 8;
+      epilogue_role(1, ew, raw_base + ew * EPI_STG_BYTES,
+                    reinterpret_cast<float*>(smem_gen + (raw_base - smem_base) + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4));
+    }
+  }
+
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
 std::mutex g_encode_mu;
@@ -1379,6 +1580,19 @@ int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
   return QDM_OK;
 }
 
+template <bool BF16>
+int launch_bstat(const Maps& m, const GemmParams& p, int pairs, cudaStream_t st) {
+  auto kern = qdm_gemm2_bstat_kernel<BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBS::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<2 * pairs, CfgBS::THREADS, CfgBS::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, m.y16, p);
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
 // 0: heuristic, 1: force the single-CTA kernel, 2: force the CTA-pair kernel, 4: force quad clusters where the kernel
 // supports them (bring-up / A-B timing)
 int g_force_ctas = 0;
@@ -1504,6 +1718,15 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
     if ((rc = make_map(&m.b, qweight, 4, K, N / 8, nloc_max / 8 + 4, 128, false))) return rc;
     if ((rc = make_map(&m.s, scales, 2, G, N, nloc_max, srows, false))) return rc;
     if ((rc = make_map(&m.z, qzeros, 4, G, N / 8, nloc_max / 8 + 4, srows, false))) return rc;
+  }
+  // B-stationary pair kernel: small K (resident B fits), enough tiles per pair for the one-time dequant to pay off
+  if (pair && m.raw && !m.quad && g_force_ctas == 0 && K <= 64 * CfgBS::BST_KB && !getenv("QDM_W4_NO_BSTAT")) {
+    const int64_t m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + p.tile_n - 1) / p.tile_n;
+    const int64_t max_pairs = QDM_NUM_SMS / 2;
+    if (n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs) {
+      const int pairs = int(n_tiles * (max_pairs / n_tiles));   // multiple of n_tiles: every pair keeps one n-tile
+      return p.is_bf16 ? launch_bstat<true>(m, p, pairs, (cudaStream_t)stream) : launch_bstat<false>(m, p, pairs, (cudaStream_t)stream);
+    }
   }
   return dispatch_gemm<G_W4>(m, p, pair, (cudaStream_t)stream);
 }

@@ -43,7 +43,8 @@ def test_gemm_f16(qdm, dt, M, N, K):
 @pytest.mark.parametrize("M,N,K,group", [(128, 128, 128, 128), (256, 256, 256, 64), (300, 320, 320, 64),
                                           (1024, 2432, 2432, 128), (77, 1280, 768, 128), (4096, 2560, 320, 64),
                                           (1, 1024, 256, 128), (513, 72, 192, 64), (2048, 64, 2432, 128),
-                                          (16, 1280, 1280, 128), (64, 320, 1280, 128), (33, 72, 192, 64), (2, 14592, 2432, 128), (48, 640, 320, 64)])
+                                          (16, 1280, 1280, 128), (64, 320, 1280, 128), (33, 72, 192, 64), (2, 14592, 2432, 128), (48, 640, 320, 64),
+                                          (60000, 320, 320, 64), (30001, 2560, 320, 64), (40960, 416, 384, 128), (57344, 160, 64, 64)])
 def test_gemm_w4a16(qdm, dt, M, N, K, group):
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(DT[dt])
