@@ -148,6 +148,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- programmatic dependent launch: the next kernel of the stream may be scheduled while this one drains (its CTAs
+// start as SMs free up, its prologue overlaps our tail); it must not touch global memory before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cluster / CTA-pair helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -810,6 +815,8 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();   // everything above is on-chip set-up; from here on global memory of earlier kernels is read
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -1058,6 +1065,8 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   cluster_sync_all();   // barrier inits and TMEM allocation of BOTH CTAs are visible before anything remote happens
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t leader_full0 = mapa_shared(full_bar(0), leader_crank);
   const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), leader_crank);
   const uint16_t pair_mask = uint16_t(3u << (2 * pgrp)), all_mask = QUAD ? uint16_t(0xF) : uint16_t(0x3);
@@ -1312,6 +1321,8 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
   const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
   const uint32_t leader_bst_full0 = mapa_shared(bst_full_bar(0), 0);
@@ -1497,6 +1508,25 @@ int choose_tile_n(int64_t M, int64_t N, int mode, double* cost_out = nullptr) {
   return best;
 }
 
+// Launch with programmatic stream serialisation (see pdl_wait in the kernels); QDM_NO_PDL=1 launches plainly.
+template <typename Kern>
+cudaError_t launch_pdl(Kern kern, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, const CUtensorMap& a,
+                       const CUtensorMap& b, const CUtensorMap& s, const CUtensorMap& z, const CUtensorMap& y,
+                       const CUtensorMap& y16, const struct GemmParams& p) {
+  static const bool no_pdl = getenv("QDM_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, a, b, s, z, y, y16, p);
+}
+
 struct Maps {
   CUtensorMap a, b, s, z;   // b: B operand (or packed qweight), s / z: W4 scales / zero points (raw TMA path)
   CUtensorMap y, y16;       // output [M, N]: 32 x 64 boxes (SWIZZLE_128B) and 32 x 16 slices (dense) for the epilogue's TMA stores
@@ -1516,7 +1546,7 @@ int launch_gemm(const Maps& m, const GemmParams& p, cudaStream_t st) {
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + p.tile_n - 1) / p.tile_n;
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < QDM_NUM_SMS ? tiles : QDM_NUM_SMS;
-  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, m.y16, p);
+  QDM_CUDA_OK(launch_pdl(kern, (unsigned)grid, C::THREADS, C::SMEM_BYTES, st, m.a, m.b, m.s, m.z, m.y, m.y16, p));
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
@@ -1575,7 +1605,7 @@ int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
     return QDM_OK;
   }
 #endif
-  kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, m.y16, p);
+  QDM_CUDA_OK(launch_pdl(kern, (unsigned)(2 * pairs), C::THREADS, C::SMEM_BYTES, st, m.a, m.b, m.s, m.z, m.y, m.y16, p));
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
@@ -1588,7 +1618,7 @@ int launch_bstat(const Maps& m, const GemmParams& p, int pairs, cudaStream_t st)
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgBS::SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<2 * pairs, CfgBS::THREADS, CfgBS::SMEM_BYTES, st>>>(m.a, m.b, m.s, m.z, m.y, m.y16, p);
+  QDM_CUDA_OK(launch_pdl(kern, (unsigned)(2 * pairs), CfgBS::THREADS, CfgBS::SMEM_BYTES, st, m.a, m.b, m.s, m.z, m.y, m.y16, p));
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }

@@ -9,6 +9,7 @@
 // (q - z) * s is formed exactly as utils/packing_utils.py:87-102 does (integer difference, one rounding in the
 // tensor dtype), so the product differs from the large-M kernel only by accumulation order.
 #include "qdm_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -52,6 +53,8 @@ w4a16_smallm_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   extern __shared__ uint4 xs_raw[];                  // x staged once per CTA: [16 MT][K + 8] (pitch: conflict-free fragments)
   uint16_t* xs = reinterpret_cast<uint16_t*>(xs_raw);
   __shared__ float red[SM_WARPS][MT][4][32];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: nothing global is read before this
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wc = blockIdx.x;                        // packed word column: output columns 8 wc .. 8 wc + 7
   const int words_per_row = N >> 3;
@@ -163,8 +166,20 @@ int launch_one(dim3 grid, size_t smem, const void* x, const int32_t* qweight, co
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     smem_set = 200 * 1024;
   }
-  kern<<<grid, SM_WARPS * 32, smem, st>>>((const uint16_t*)x, (const uint32_t*)qweight, (const uint32_t*)qzeros,
-                                         (const uint16_t*)scales, (const uint16_t*)bias, (uint16_t*)y, M, N, K, group);
+  // programmatic stream serialisation, as for the tcgen05 kernels (the kernel waits before its first global access)
+  static const bool no_pdl = getenv("QDM_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(SM_WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  QDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const uint16_t*)x, (const uint32_t*)qweight, (const uint32_t*)qzeros,
+                                 (const uint16_t*)scales, (const uint16_t*)bias, (uint16_t*)y, M, N, K, group));
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
