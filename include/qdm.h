@@ -193,8 +193,16 @@ int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight,
                         const void* scales, const void* bias, void* y_dev, void* y_host, int dtype,
                         int64_t M, int64_t N, int64_t K, int group, void* stream);
 
+/* Optional workspace of the W4A16 GEMM (device memory owned by the caller, qdm_gemm_workspace_bytes() bytes, kept until
+ * replaced or cleared with NULL; one per device).  With it, problems whose whole-tile waves would leave CTA pairs idle
+ * (few tiles with a long K, a nearly empty last wave) run the stream-K kernel, which parks partial fp32 accumulators
+ * there; without it every problem runs the whole-tile kernels.  The call zeroes the flag area on `stream`.  GEMM calls
+ * that share a workspace must be ordered on one stream (the Python layer keeps one workspace per device). */
+size_t qdm_gemm_workspace_bytes(void);
+int qdm_gemm_set_workspace(void* workspace, size_t bytes, void* stream);
+
 /* Tile-shape override for bring-up and A/B timing: 0 = heuristic, 1 = single-CTA tiles (128 x N),
- * 2 = CTA-pair tiles (cta_group::2, 256 x N).  Process-wide; not part of the reference interface. */
+ * 2 = CTA-pair tiles (cta_group::2, 256 x N), 4 = quad clusters, 8 = stream-K.  Process-wide; not part of the reference interface. */
 int qdm_set_gemm_mode(int ctas);
 
 /* Test hook (synchronous, allocates 16 bytes): sweeps EVERY (dividend, divisor) pair of 16-bit values of

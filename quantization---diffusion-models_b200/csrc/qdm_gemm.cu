@@ -247,6 +247,8 @@ struct GemmParams {
   void* y;                   // [M, N] out dtype
   int is_bf16;               // element / output type: 0 fp16, 1 bf16
   long long* trace;          // QDM_TRACE builds only: per-role (tag, clock64) event log of block 0
+  float* sk_data;            // stream-K: partial accumulators, [pair][rank][128 rows][256] fp32
+  uint32_t* sk_flags;        // stream-K: [pair][rank][4 warps], 0 = empty, 1 = partial written (reset by its reader)
 };
 
 // Packed-int4 staging ring of the W4 kernels: per k-block the TMA producer drops the tile part's packed words
@@ -343,7 +345,11 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 template <int BLOCK_N, int KIND, bool BF16>
 __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtensorMap* map_y, const CUtensorMap* map_y16,
                                                uint32_t stg, float* vec_sm, uint32_t taddr0, int row0, int n0, int lane,
-                                               int c_first, int c_step) {
+                                               int c_first, int c_step, const float* part_row = nullptr, int n_parts = 0,
+                                               int64_t part_stride = 0) {
+  // stream-K: part_row + q * part_stride is this lane's entry in the q-th earlier partial accumulator of the tile (fp32,
+  // layout [half][16-byte chunk][128 rows], see qdm_gemm2_sk_kernel); the partials are added in slot order, so the
+  // result does not depend on timing
   const int n_end = min(n0 + p.tile_n, p.N);   // columns of this tile that exist
   const int row = row0 + lane;
   float sxr = 1.f;
@@ -371,7 +377,8 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
     const int w = n_end - (n0 + c * EPI_COLS);
     return w <= 0 ? 0 : (w > 32 ? 2 : 1);
   };
-  auto process_half = [&](const uint32_t (&v)[32], int h) {
+  auto process_half = [&](const uint32_t (&v)[32], int h, auto with_ex, const uint32_t (&ex)[32]) {
+    constexpr bool kEx = decltype(with_ex)::value;           // ex = fp32 bits to add (stream-K partial sums)
     const int c = h >> 1, hh = h & 1;
     const int nc = n0 + c * EPI_COLS;                       // first column of the 64-column chunk
     const int width = min(EPI_COLS, n_end - nc);            // columns of the chunk inside the tile
@@ -394,7 +401,8 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
           f[i] = __fmaf_rn(__fmul_rn(float(int(v[j8 * 8 + i])), __fmul_rn(sxr, sw8[i])), 1.f, bias8[i]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j8 * 8 + i]) + bias8[i];
+        for (int i = 0; i < 8; ++i)
+          f[i] = (kEx ? __uint_as_float(v[j8 * 8 + i]) + __uint_as_float(ex[j8 * 8 + i]) : __uint_as_float(v[j8 * 8 + i])) + bias8[i];
       }
       uint4 o;
       o.x = pack_out2<KIND, BF16>(f[0], f[1]);
@@ -429,6 +437,35 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
     hn = (cn * EPI_COLS < BLOCK_N && halves_in(cn) > 0) ? 2 * cn : -1;
   };
   uint32_t va[32], vb[32];
+  if (n_parts > 0) {
+    // stream-K final part: the second register buffer holds the sum of the earlier partials of the half (8 x 16-byte
+    // loads per part in flight together with the tcgen05.ld), added in slot order
+#pragma unroll 1
+    for (;;) {
+      tmem_ld32(taddr0 + h * 32, va);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) vb[i] = 0u;
+      for (int q = 0; q < n_parts; ++q) {
+        float4 t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = __ldcg(reinterpret_cast<const float4*>(part_row + q * part_stride) + (h * 8 + i) * 128);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          vb[4 * i] = __float_as_uint(__uint_as_float(vb[4 * i]) + t[i].x);
+          vb[4 * i + 1] = __float_as_uint(__uint_as_float(vb[4 * i + 1]) + t[i].y);
+          vb[4 * i + 2] = __float_as_uint(__uint_as_float(vb[4 * i + 2]) + t[i].z);
+          vb[4 * i + 3] = __float_as_uint(__uint_as_float(vb[4 * i + 3]) + t[i].w);
+        }
+      }
+      tmem_ld_wait();
+      process_half(va, h, std::true_type{}, vb);
+      int hn, cn;
+      next_half(hn, cn);
+      if (hn < 0) break;
+      h = hn; c = cn;
+    }
+    return;
+  }
   tmem_ld32(taddr0 + h * 32, va);
 #pragma unroll 1
   for (;;) {
@@ -436,13 +473,13 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
     next_half(hn, cn);
     tmem_ld_wait();
     if (hn >= 0) tmem_ld32(taddr0 + hn * 32, vb);
-    process_half(va, h);
+    process_half(va, h, std::false_type{}, va);
     if (hn < 0) break;
     h = hn; c = cn;
     next_half(hn, cn);
     tmem_ld_wait();
     if (hn >= 0) tmem_ld32(taddr0 + hn * 32, va);
-    process_half(vb, h);
+    process_half(vb, h, std::false_type{}, vb);
     if (hn < 0) break;
     h = hn; c = cn;
   }
@@ -623,7 +660,9 @@ template <int NLOC, bool BF16, int STAGES, int STAGE_BYTES, int RAW_N, int GROUP
 __device__ __forceinline__ void w4_dequant_loop(int dt, int lane, int first_tile, int tile_stride, int num_tiles, int n_tiles,
                                                 int num_kb, int tile_n, int col_off, int nloc, int group, uint32_t b_stage0, uint32_t raw0,
                                                 uint32_t empty_addr, uint32_t full_addr, uint32_t raw_full_addr,
-                                                uint32_t raw_empty_addr, long long* trace) {
+                                                uint32_t raw_empty_addr, long long* trace, int sk_u0 = -1, int sk_u1 = 0) {
+  // stream-K (sk_u0 >= 0): the CTA works on the k-block units [sk_u0, sk_u1) of the tile-major unit sequence, segment by
+  // segment from the LAST tile to the first (see qdm_gemm2_sk_kernel); first_tile / tile_stride / num_tiles are unused.
   using R = RawCfg<NLOC>;
   TRC_DECL;
   constexpr int WPR = NLOC / 8;                  // packed words per k row of this CTA's tile part
@@ -656,20 +695,45 @@ __device__ __forceinline__ void w4_dequant_loop(int dt, int lane, int first_tile
   static_assert((RAW_N & (RAW_N - 1)) == 0, "raw ring depth must be a power of two");
   int stage = grp % STAGES;
   uint32_t phase = uint32_t(grp / STAGES) & 1u;                // more groups than stages: the first use may be a second lap
+  const bool sk = sk_u0 >= 0;
   const int my_tiles = first_tile < num_tiles ? (num_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
-  const int total = my_tiles * num_kb;                         // pipeline iterations of this CTA
+  const int total = sk ? sk_u1 - sk_u0 : my_tiles * num_kb;    // pipeline iterations of this CTA
   const int rs_per_tile = (num_kb + 1) >> 1;                   // raw stages (k-block pairs) per tile
+  // stream-K geometry: first / last tile of the range, k-block bounds inside them, raw stages of the last tile's segment
+  const int sk_t0 = sk ? sk_u0 / num_kb : 0, sk_ka0 = sk ? sk_u0 - sk_t0 * num_kb : 0;
+  const int sk_t1 = sk ? (sk_u1 - 1) / num_kb : 0, sk_ke1 = sk ? (sk_u1 - 1) - sk_t1 * num_kb + 1 : 0;
   int tile = first_tile, kb = grp, tl = 0;                     // position of iteration `it`: tile, k-block, local tile count
   for (int it = grp; it < total; it += GROUPS) {
-    while (kb >= num_kb) { kb -= num_kb; tile += tile_stride; ++tl; }
+    int rseq;
+    bool lone;
+    if (sk) {
+      // iteration `it` counts k-blocks over the segments in REVERSE tile order (k ascending inside a segment)
+      // segment lengths: last tile first
+      int rem = it, t = sk_t1, ka, ke, rbase = 0;
+      for (;;) {
+        ka = (t == sk_t0) ? sk_ka0 : 0;
+        ke = (t == sk_t1) ? sk_ke1 : num_kb;
+        if (rem < ke - ka) break;
+        rem -= ke - ka;
+        rbase += ((ke - 1) >> 1) - (ka >> 1) + 1;
+        --t;
+      }
+      tile = t;
+      kb = ka + rem;
+      rseq = rbase + (kb >> 1) - (ka >> 1);
+      const int partner = kb ^ 1;
+      lone = !(partner >= ka && partner < ke);
+    } else {
+      while (kb >= num_kb) { kb -= num_kb; tile += tile_stride; ++tl; }
+      rseq = tl * rs_per_tile + (kb >> 1);                     // raw stage sequence number of this CTA
+      lone = (kb == num_kb - 1) && (kb & 1) == 0;              // odd K tail: this group is the stage's only consumer
+    }
     // word offset of this tile part inside the (aligned-down) staged box
     const uint32_t shift = uint32_t(((tile % n_tiles) * tile_n + col_off) >> 3) & 3u;
     const uint32_t half = uint32_t(kb & 1);                    // which k-block of the raw stage
     const uint32_t srow = (group == 64) ? half : 0u;           // quantisation group row inside the stage
-    const int rseq = tl * rs_per_tile + (kb >> 1);             // raw stage sequence number of this CTA
     const int rs = rseq & (RAW_N - 1);
     const uint32_t rphase = uint32_t(rseq / RAW_N) & 1u;
-    const bool lone = (kb == num_kb - 1) && half == 0;         // odd K tail: this group is the stage's only consumer
     const uint32_t w_off = (uint32_t((kr + half * 64) * R::WPRX + wc) + shift) * 4u;
     kb += GROUPS;
     const uint32_t raw = raw0 + uint32_t(rs) * R::BYTES;
@@ -1238,6 +1302,245 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------- stream-K CTA-pair kernel (W4)
+// The classic kernel gives every pair whole tiles: 80 tiles on 74 pairs cost two waves, and a 25-tile problem with a long
+// K runs on 25 pairs.  Here the work is the tile-major sequence of k-block units (tiles x K/64) and pair p takes the units
+// [p U / P, (p + 1) U / P): at most one tile is shared with the previous pair and one with the next.  A pair walks its
+// segments from its LAST tile to its first:
+//   * a segment that ends before the tile does (always the first one processed) leaves its fp32 accumulator in the pair's
+//     workspace slot and raises a flag per epilogue warp;
+//   * the segment that contains the tile's last k-block (processed last if it is a partial one) waits for the flags of the
+//     pairs that hold the tile's earlier parts, adds their partials in slot order (deterministic) and runs the normal epilogue.
+// Producers therefore publish early and consumers read late: nobody waits for long, and waits only go to lower pair
+// indices, so there is no cycle.  The flags are reset by their reader, so the protocol also holds under CUDA-graph replay.
+__device__ __forceinline__ void sk_wait_flag(const uint32_t* flag) {
+  uint32_t v = 0, polls = 0;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v != 0) break;
+    if (++polls == 4096) t0 = clock64();
+    if (polls > 4096 && (polls & 1023) == 0 && clock64() - t0 > 6000000000LL) __trap();
+  }
+}
+
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<256, G_W4>::THREADS, 1)
+qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_z,
+                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y16, const GemmParams p) {
+  using C = Cfg2<256, G_W4>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int NLOC = C::NLOC;
+  constexpr int BLOCK_N = 256;
+  using R = RawCfg<NLOC>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t raw_base = epi_base + C::EPI_BYTES;
+  const uint32_t bar_base = raw_base + C::RAW_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto raw_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+  auto raw_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + RAW_STAGES + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + STAGES * C::STAGE_BYTES + C::EPI_BYTES + C::RAW_BYTES + 8 * (2 * STAGES + 4 + 2 * RAW_STAGES));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int tile_n = p.tile_n, nloc = p.tile_n / 2;
+  const int n_tiles = (p.N + tile_n - 1) / tile_n;
+  const int num_kb = p.K / 64;
+  const long long units = (long long)m_tiles * n_tiles * num_kb;
+  const int u0 = int(units * pair / num_pairs), u1 = int(units * (pair + 1) / num_pairs);
+  // segments of [u0, u1) from the last tile to the first; f(tile, ka, ke): k-blocks [ka, ke) of `tile`
+  auto for_each_seg = [&](auto&& f) {
+    int u = u1;
+    while (u > u0) {
+      const int tile = (u - 1) / num_kb;
+      const int ke = (u - 1) - tile * num_kb + 1;
+      const int ka = (u - u0 >= ke) ? 0 : ke - (u - u0);
+      f(tile, ka, ke);
+      u -= ke - ka;
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_s); tma_prefetch_desc(&map_z);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), C::FULL_COUNT_RAW); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
+    for (int s = 0; s < RAW_STAGES; ++s) { mbar_init(raw_full_bar(s), 1); mbar_init(raw_empty_bar(s), C::RAW_EMPTY_COUNT); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
+  const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer: A
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for_each_seg([&](int tile, int ka, int ke) {
+        const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M;
+        for (int kb = ka; kb < ke; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * A_STAGE_BYTES);
+          tma_load_2d_pair(smem_base + stage * C::STAGE_BYTES, &map_a, leader_full0 + 8u * stage, kb * 64, m0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      });
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 1, 2 * BLOCK_M, tile_n);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for_each_seg([&](int, int ka, int ke) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
+        for (int kb = ka; kb < ke; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024);
+            umma_pair<G_W4>(tmem_c, da, db, idesc, (kb != ka) || (k != 0));
+          }
+          umma_commit_pair(empty_bar(stage), 3);
+          if (kb == ke - 1) umma_commit_pair(tmem_full_bar(acc), 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      });
+    }
+  } else if (warp == 3) {
+    // ===================================================== raw int4 producer
+    if (lane == 0) {
+      const int srows = p.group == 64 ? 2 : 1;
+      const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
+      const uint32_t tx = R::tx_bytes(srows);
+      int rs = 0;
+      uint32_t rphase = 0;
+      for_each_seg([&](int tile, int ka, int ke) {
+        const int n0 = (tile % n_tiles) * tile_n + int(rank) * nloc;
+        for (int j = ka >> 1; j <= (ke - 1) >> 1; ++j) {
+          mbar_wait(raw_empty_bar(rs), rphase ^ 1);
+          const uint32_t raw = raw_base + uint32_t(rs) * R::BYTES;
+          const int grow = j * gdiv / gmul;
+          mbar_expect_tx(raw_full_bar(rs), tx);
+          tma_load_2d(raw, &map_b, raw_full_bar(rs), (n0 >> 3) & ~3, j * 128);
+          tma_load_2d(raw + R::QW_BYTES, &map_s, raw_full_bar(rs), n0, grow);
+          tma_load_2d(raw + R::QW_BYTES + R::SC_BYTES, &map_z, raw_full_bar(rs), (n0 >> 3) & ~3, grow);
+          if (++rs == C::RAW_N) { rs = 0; rphase ^= 1; }
+        }
+      });
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== epilogue
+    const int ew = warp - 4;
+    const uint32_t stg = epi_base + ew * EPI_STG_BYTES;
+    float* vec_sm = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4);
+    if (lane == 0) { tma_prefetch_desc(&map_y); tma_prefetch_desc(&map_y16); }
+    constexpr int64_t kSlot = 2 * 128 * 256;                 // floats per pair slot
+    const int64_t my_row = int64_t(rank) * (128 * 64) + ew * 32 + lane;   // in 16-byte units: [rank][h][i][row]
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for_each_seg([&](int tile, int ka, int ke) {
+      const int m0 = (tile / n_tiles) * (2 * BLOCK_M) + int(rank) * BLOCK_M, n0 = (tile % n_tiles) * tile_n;
+      const uint32_t taddr0 = tmem_base + (uint32_t(ew * 32) << 16) + acc * BLOCK_N;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+#ifdef QDM_EXP_SK_NOFIX   // timing experiment only (wrong results): stream-K without parking / adding partials
+      if (false) {
+#else
+      if (ke < num_kb) {
+#endif
+        // ---- not the tile's last part: park the fp32 accumulator in this pair's slot and raise the flag
+        // slot layout [rank][half h][16-byte chunk i][128 rows]: a warp's store / load of chunk i covers 512 contiguous bytes
+        uint4* dst = reinterpret_cast<uint4*>(p.sk_data + int64_t(pair) * kSlot) + my_row;
+        const int n_halves = (min(tile_n, p.N - n0) + 31) / 32;
+        for (int h = 0; h < n_halves; ++h) {
+          uint32_t v[32];
+          tmem_ld32(taddr0 + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            __stcg(dst + (h * 8 + i) * 128, make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + (pair * 2 + int(rank)) * 4 + ew), "r"(1u) : "memory");
+      } else {
+        // ---- the tile's last part: earlier parts (if any) sit in the slots of the pairs pa .. pair - 1
+        int n_parts = 0;
+#if defined(QDM_EXP_SK_NOFIX) || defined(QDM_EXP_SK_NOREDUCE)
+        if (false) {
+#else
+        if (ka > 0) {
+#endif
+          const long long x0 = (long long)tile * num_kb;       // first unit of the tile; its owner is pa
+          int pa = int(x0 * num_pairs / units);
+          while (units * (pa + 1) / num_pairs <= x0) ++pa;
+          while (units * pa / num_pairs > x0) --pa;
+          n_parts = pair - pa;
+          if (lane == 0)
+            for (int q = pa; q < pair; ++q) sk_wait_flag(p.sk_flags + (q * 2 + int(rank)) * 4 + ew);
+          __syncwarp();
+        }
+        epilogue_drain<BLOCK_N, G_W4, BF16>(p, &map_y, &map_y16, stg, vec_sm, taddr0, m0 + ew * 32, n0, lane, 0, 1,
+                                            p.sk_data + int64_t(pair - n_parts) * kSlot + my_row * 4, n_parts, kSlot);
+        if (n_parts > 0) {   // every flag has exactly one reader warp: hand it back empty for the next launch / replay
+          __syncwarp();
+          if (lane == 0)
+            for (int q = pair - n_parts; q < pair; ++q) p.sk_flags[(q * 2 + int(rank)) * 4 + ew] = 0u;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    });
+    if (lane == 0) tma_store_wait_all();
+  } else if (warp >= 8) {
+    // ===================================================== int4 dequant
+    w4_dequant_loop<NLOC, BF16, STAGES, C::STAGE_BYTES, C::RAW_N, C::RAW_GROUPS, true>(
+        threadIdx.x - 256, lane, 0, 1, 0, n_tiles, num_kb, tile_n, int(rank) * nloc, nloc, p.group,
+        smem_base + A_STAGE_BYTES, raw_base, empty_bar(0), leader_full0, raw_full_bar(0), raw_empty_bar(0), p.trace, u0, u1);
+  }
+
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- B-stationary CTA-pair kernel (W4, K <= 384)
 // For the K = 320 layers of the UNet (M = 65536 tokens: 40 of the step's 184 launches, 37 % of its time) a pair's B tile
 // part is tiny: K x nloc fp16 = 80 KB.  The generic kernel re-fetches and re-dequantises it for every one of the pair's
@@ -1610,6 +1913,26 @@ int launch_gemm2(const Maps& m, const GemmParams& p, cudaStream_t st) {
   return QDM_OK;
 }
 
+// stream-K workspace (per device, set by qdm_gemm_set_workspace): [flags: 4 KB][74 pair slots x 2 x 128 x 256 fp32]
+constexpr size_t SK_FLAG_BYTES = 4096;
+constexpr size_t SK_SLOT_FLOATS = 2 * 128 * 256;
+constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + size_t(QDM_NUM_SMS / 2) * SK_SLOT_FLOATS * sizeof(float);
+void* g_sk_ws[64] = {};
+
+template <bool BF16>
+int launch_sk(const Maps& m, const GemmParams& p, int pairs, cudaStream_t st) {
+  using C = Cfg2<256, G_W4>;
+  auto kern = qdm_gemm2_sk_kernel<BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  QDM_CUDA_OK(launch_pdl(kern, (unsigned)(2 * pairs), C::THREADS, C::SMEM_BYTES, st, m.a, m.b, m.s, m.z, m.y, m.y16, p));
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
 template <bool BF16>
 int launch_bstat(const Maps& m, const GemmParams& p, int pairs, cudaStream_t st) {
   auto kern = qdm_gemm2_bstat_kernel<BF16>;
@@ -1660,8 +1983,22 @@ int check_common(const char* fn, const void* x, const void* w, void* y, int dtyp
 
 }  // namespace
 
+extern "C" size_t qdm_gemm_workspace_bytes(void) { return SK_WS_BYTES; }
+
+extern "C" int qdm_gemm_set_workspace(void* workspace, size_t bytes, void* stream) {
+  int dev = 0;
+  QDM_CUDA_OK(cudaGetDevice(&dev));
+  QDM_REQUIRE(dev >= 0 && dev < 64, "qdm_gemm_set_workspace: device index %d", dev);
+  if (!workspace) { g_sk_ws[dev] = nullptr; return QDM_OK; }
+  QDM_REQUIRE(bytes >= SK_WS_BYTES && qdm_aligned16(workspace), "qdm_gemm_set_workspace: need %zu bytes, 16-byte aligned", SK_WS_BYTES);
+  QDM_CUDA_OK(cudaMemsetAsync(workspace, 0, SK_FLAG_BYTES, (cudaStream_t)stream));   // all flags empty
+  g_sk_ws[dev] = workspace;
+  return QDM_OK;
+}
+
 extern "C" int qdm_set_gemm_mode(int ctas) {
-  QDM_REQUIRE(ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4, "qdm_set_gemm_mode: 0 (auto), 1 (single CTA), 2 (CTA pair) or 4 (quad cluster)");
+  QDM_REQUIRE(ctas == 0 || ctas == 1 || ctas == 2 || ctas == 4 || ctas == 8,
+              "qdm_set_gemm_mode: 0 (auto), 1 (single CTA), 2 (CTA pair), 4 (quad cluster) or 8 (stream-K)");
   g_force_ctas = ctas;
   return QDM_OK;
 }
@@ -1756,6 +2093,31 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
     if (n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs) {
       const int pairs = int(n_tiles * (max_pairs / n_tiles));   // multiple of n_tiles: every pair keeps one n-tile
       return p.is_bf16 ? launch_bstat<true>(m, p, pairs, (cudaStream_t)stream) : launch_bstat<false>(m, p, pairs, (cudaStream_t)stream);
+    }
+  }
+  // stream-K pair kernel: when whole-tile waves leave pairs idle (few tiles with a long K, or a nearly empty last wave).
+  // Cost model in cycles per k-block of a pair, measured: ~600 + tile_n; parking one partial accumulator and adding one
+  // back costs ~15000 cycles (8 us) per launch as measured, so stream-K wins for long-K problems with an awkward tile count
+  // (4096 x 1280 x 5120: 57 instead of 71 us) and loses for short ones (4096 x 1280 x 1280: 28.6 vs 23.1 us).
+  int dev = 0;
+  if (pair && m.raw && !m.quad && (g_force_ctas == 0 || g_force_ctas == 8) && !getenv("QDM_W4_NO_SK") &&
+      cudaGetDevice(&dev) == cudaSuccess && dev < 64 && g_sk_ws[dev]) {
+    const int64_t P = QDM_NUM_SMS / 2, m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_kb = K / 64;
+    const int64_t n_t = (N + 255) / 256;
+    const int tn = int(((N + n_t - 1) / n_t + 15) / 16 * 16);
+    const int64_t units = m_tiles * n_t * num_kb;
+    const int64_t pairs = units < P ? units : P;
+    const double sk_cost = double((units + pairs - 1) / pairs) * (600.0 + tn) + 15000.0;
+    const int64_t c_tiles = m_tiles * ((N + p.tile_n - 1) / p.tile_n);
+    const double classic_cost = double((c_tiles + P - 1) / P) * double(num_kb) * (600.0 + p.tile_n);
+    // a tile shared by three or more pairs would make its last part wait for several partials: only when every pair has
+    // at least one tile's worth of k-blocks
+    if (g_force_ctas == 8 || (units >= P * num_kb && sk_cost < 0.92 * classic_cost)) {
+      GemmParams ps = p;
+      ps.tile_n = tn;
+      ps.sk_flags = reinterpret_cast<uint32_t*>(g_sk_ws[dev]);
+      ps.sk_data = reinterpret_cast<float*>(reinterpret_cast<char*>(g_sk_ws[dev]) + SK_FLAG_BYTES);
+      return p.is_bf16 ? launch_sk<true>(m, ps, int(pairs), (cudaStream_t)stream) : launch_sk<false>(m, ps, int(pairs), (cudaStream_t)stream);
     }
   }
   return dispatch_gemm<G_W4>(m, p, pair, (cudaStream_t)stream);

@@ -356,6 +356,18 @@ def gemm_f16_kn(x, w_kn, bias=None):
     return y.reshape(*x.shape[:-1], w_kn.shape[1])
 
 
+_gemm_ws = {}   # device index -> stream-K workspace tensor (kept alive for the life of the process)
+
+
+def _set_gemm_workspace(L, device):
+    """One stream-K workspace per device (include/qdm.h: qdm_gemm_set_workspace); GEMM calls of a device are expected on
+    one stream at a time, as in the reference's single-stream execution."""
+    buf = torch.empty(int(L.qdm_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
+    with _guard(device):
+        check(L.qdm_gemm_set_workspace(buf.data_ptr(), buf.numel(), torch.cuda.current_stream(device).cuda_stream))
+    _gemm_ws[device.index] = buf
+
+
 def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None):
     """x @ dequant(qweight, qzeros, scales) + bias, AWQ GEMM layout (quantize/quantizer.py:544-569).
     This is the per-Linear hot call of a denoise step: the Python side is kept to the bare minimum."""
@@ -375,6 +387,8 @@ def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None):
     if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
         bias = bias.to(x.dtype).contiguous()
     L = _lib._lib or lib()
+    if x.device.index not in _gemm_ws:
+        _set_gemm_workspace(L, x.device)
     with _guard(x.device):
         rc = L.qdm_gemm_w4a16(x2.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(),
                               0 if bias is None else bias.data_ptr(), y.data_ptr(), _DTYPES[x.dtype], m, n, k, group,

@@ -101,3 +101,28 @@ def test_gemm_large_m_round_trip(qdm):
     y2 = qdm.ops.gemm_w4a16((x1 * 2).contiguous(), qweight, qzeros, scales, group)
     normal = y1.float().abs() >= 2.0 ** -13          # scaling by 2 is exact unless the fp16 output is subnormal
     assert torch.equal(y2.float()[normal], (y1.float() * 2)[normal])
+
+
+def test_gemm_w4a16_stream_k(qdm):
+    """Stream-K path (partial accumulators parked in the workspace, added back in slot order): forced on shapes whose
+    tiles are split between CTA pairs in every way (two-way and many-way splits, odd K tail, ragged M / N), called twice
+    so that the reader-reset flags are exercised; the result must equal the whole-tile kernel's within one output ulp and
+    be identical from call to call (deterministic reduction order)."""
+    g = torch.Generator().manual_seed(3)
+    try:
+        for M, N, K, group in [(4096, 1280, 1280, 128), (1232, 1280, 768, 128), (1024, 1280, 5120, 128), (513, 2560, 320, 64),
+                               (777, 96, 192, 64), (4096, 1280, 5120, 128)]:
+            x = torch.randn(M, K, generator=g).half().to(DEV)
+            w = (torch.randn(N, K, generator=g) * 0.05).half().to(DEV)
+            b = torch.randn(N, generator=g).half().to(DEV)
+            qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(w, group, want_dq=True)
+            qdm.ops.set_gemm_mode(2)
+            y_tiles = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+            qdm.ops.set_gemm_mode(8)
+            y1 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+            y2 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+            assert torch.equal(y1, y2), (M, N, K)
+            assert max_rel_err(y1, ref_linear(x.cpu(), dq.cpu(), b.cpu())) <= TOL
+            assert max_rel_err(y1, y_tiles.cpu()) <= 2e-3
+    finally:
+        qdm.ops.set_gemm_mode(0)
