@@ -307,7 +307,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_sustained"], "traffic": step_traffic(),
-                     "kernel": "qdm_gemm2_kernel<256, G_W4, fp16, raw-TMA> (160 launches) + w4a16_smallm_kernel (24 launches with M = 16)",
+                     "kernel": "W4A16 family: qdm_gemm2_kernel<256, G_W4, fp16, raw-TMA> (120 launches), qdm_gemm2_bstat_kernel (35, K = 320), "
+                               "qdm_gemm2_sk_kernel (5, stream-K), w4a16_smallm_kernel (24, M = 16)",
                      "peak_kind": "bf16 cuBLAS sustained, " + peaks["source"],
                      "note": "2*M*N*K summed over the step's 184 launches / CUDA-event time of the step (one CUDA graph); traffic = DRAM read+write "
                              "bytes of the same 184 launches from the committed ncu launch list (profiles/step_traffic_r01.json; algorithmic bytes "
