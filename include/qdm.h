@@ -70,6 +70,20 @@ int qdm_colabsmax(const void* x, int dtype, int64_t rows, int64_t cols, int64_t 
 int qdm_colabssum(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld,
                   float* out_sum, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One-pass hook statistic: ONE read of x[rows, cols] yields the per-call column
+ * |x| max and |x| sum, and folds them in place into the caller's running accumulators, replacing the per-call
+ * `abs().amax(0)` + retained `max_scales[step]` tensors of utils/calib_data.py:112-121 and the later
+ * `torch.mean(torch.stack(...))` of models/StableDiffusion1_x.py:104-112, and the chunked `abs().sum(0)` of
+ * quantize/quantizer.py:642-659.  Any of the three outputs may be NULL (not all):
+ *   out_max[c]    (dtype)  = colmax (max_mode 0) or max(out_max[c], colmax) (max_mode 1)
+ *   acc_maxsum[c] (double) += colmax            -> mean over calls of the per-call max = acc / n_calls
+ *   acc_abssum[c] (double) += sum_r |x[r,c]|     (per-call sum in fp32 by a fixed tree) -> x_mean = acc / n_rows
+ * Accumulators are updated by one thread per column in stream order: deterministic; the fp64 sum of fp16 maxima
+ * is exact (order-free), so it may also be all-reduced across data-parallel ranks without changing a bit. */
+size_t qdm_colstats_workspace_bytes(int64_t rows, int64_t cols);
+int qdm_colstats(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, void* out_max, int max_mode,
+                 double* acc_maxsum, double* acc_abssum, void* workspace, size_t workspace_bytes, void* stream);
+
 /* out[r] = max_c |x[r,c]| (dtype), rows of `cols` contiguous elements.
  * `w.abs().max(dim=-1)` quantize/fake_quant.py:89,114; cols may be tiny (conv kw). */
 int qdm_rowabsmax(const void* x, int dtype, int64_t rows, int64_t cols, void* out, void* stream);

@@ -257,3 +257,10 @@ def linear_w8a8_fake(x, w, bias=None):
     xq = rtn_rows(x.reshape(-1, x.shape[-1]), 8)[0]
     wq = rtn_rows(w, 8)[0]
     return linear_fake(xq, wq, bias).reshape(*x.shape[:-1], w.shape[0])
+
+
+# ------------------------------------------------------------------ A8  fake_quant.py:337-341
+def conv2d_fake(x, w_fake, bias=None, stride=1, padding=0):
+    """WxAxConv2d.forward with quantize_act=False: F.conv2d on fake-quant weights (fp32 math on CPU)."""
+    y = torch.nn.functional.conv2d(x.float(), w_fake.float(), None if bias is None else bias.float(), stride, padding)
+    return y.to(x.dtype)

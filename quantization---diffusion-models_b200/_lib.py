@@ -35,6 +35,8 @@ SIGNATURES = {
     "qdm_colreduce_workspace_bytes": (c_size_t, [_L, _L]),
     "qdm_colabsmax": (c_int, [_P, _I, _L, _L, _L, _P, _I, _P, _Z, _P]),
     "qdm_colabssum": (c_int, [_P, _I, _L, _L, _L, _P, _P, _Z, _P]),
+    "qdm_colstats_workspace_bytes": (c_size_t, [_L, _L]),
+    "qdm_colstats": (c_int, [_P, _I, _L, _L, _L, _P, _I, _P, _P, _P, _Z, _P]),
     "qdm_rowabsmax": (c_int, [_P, _I, _L, _L, _P, _P]),
     "qdm_absmax_workspace_bytes": (c_size_t, [_L]),
     "qdm_absmax": (c_int, [_P, _I, _L, _P, _P, _Z, _P]),

@@ -24,6 +24,69 @@ class Mean_Max_Activation_Hook:
         self.max_scales = []
 
 
+class AccumulatedMax:
+    """What `Fused_Mean_Max_Activation_Hook.max_scales` hands to `mean_of_dict`: the fp64 sum over calls of the
+    per-call column maxima plus the call count (instead of one retained [C] tensor per call)."""
+
+    def __init__(self, acc_maxsum, n_calls, dtype):
+        self.acc_maxsum, self.n_calls, self.dtype = acc_maxsum, n_calls, dtype
+
+    def __len__(self):
+        return self.n_calls
+
+    def mean_over_calls(self):
+        return (self.acc_maxsum / self.n_calls).to(self.dtype)
+
+
+class Fused_Mean_Max_Activation_Hook:
+    """the statistic of Mean_Max_Activation_Hook (utils/calib_data.py:105-124, mean over
+    calls of the per-call column |x| max) collected by ONE pass of the one-pass hook kernel (`qdm_colstats`) per
+    call, folded in place into fp64 accumulators on the GPU: no `max_scales[step]` tensors are retained, and the
+    same pass also maintains the running max (quantizer_SQ.py:1077-1084) and -- with `want_abssum` -- the
+    numerator of AWQ's x_mean (quantizer.py:642-659).  The fp64 sum of fp16 maxima is exact, so the mean is the
+    correctly rounded one: identical to the reference's `torch.mean(torch.stack(...))` except where the
+    reference's own fp32 summation order lands across a rounding boundary (<= 1 ulp; tests bound it)."""
+
+    def __init__(self, want_abssum=False):
+        self.hook_handle = None
+        self.want_abssum = want_abssum
+        self.acc_maxsum = None
+        self.acc_abssum = None
+        self.running_max = None
+        self.dtype = None
+        self.step = 0
+        self.rows = 0
+
+    def __call__(self, module, module_in, module_out):
+        x = module_in[0]
+        c = x.shape[-1]
+        first = self.acc_maxsum is None
+        if first:
+            self.dtype = x.dtype
+            self.acc_maxsum = torch.zeros(c, dtype=torch.float64, device=x.device)
+            self.running_max = torch.empty(c, dtype=x.dtype, device=x.device)
+            if self.want_abssum:
+                self.acc_abssum = torch.zeros(c, dtype=torch.float64, device=x.device)
+        ops.colstats(x, out_max=self.running_max, running=not first, acc_maxsum=self.acc_maxsum,
+                     acc_abssum=self.acc_abssum)
+        self.step += 1
+        self.rows += x.numel() // c
+
+    @property
+    def max_scales(self):
+        return AccumulatedMax(self.acc_maxsum, self.step, self.dtype)
+
+    def x_mean(self):
+        """mean over all tokens seen of |x| per channel, in the activation dtype (quantizer.py:652-659)."""
+        if self.acc_abssum is None:
+            raise RuntimeError("the hook was created without want_abssum=True")
+        return (self.acc_abssum / self.rows).to(self.dtype)
+
+    def clear(self):
+        self.acc_maxsum = self.acc_abssum = self.running_max = None
+        self.step = self.rows = 0
+
+
 class Running_Max_Activation_Hook:
     """LLM-style statistic of quantize/quantizer_SQ.py:1077-1084: running max over calls, folded in place by
     the kernel's running mode (no per-call tensors retained)."""

@@ -133,6 +133,116 @@ int launch_col_reduce(const T* x, int64_t rows, int64_t cols, int64_t ld, TOut* 
   return QDM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-pass calibration hook statistic (utils/calib_data.py:105-124):
+// column |x| max AND column |x| sum from a single read of x, folded in place into the caller's
+// running accumulators by the second stage -- nothing per call is retained on the host side.
+// Stage 1 is col_reduce_stage1 with both accumulators live (VEC = false: scalar columns).
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kColThreads)
+col_stats_stage1(const T* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                 float* __restrict__ pmax, float* __restrict__ psum) {
+  constexpr int V = VEC ? ElemTraits<T>::kVec : 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t(blockIdx.x) * 32 + lane) * V;
+  float amax[V], asum[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { amax[i] = 0.f; asum[i] = 0.f; }
+  if (c0 < cols) {
+    const int64_t row_step = int64_t(gridDim.y) * kColWarps;
+    int64_t r = int64_t(blockIdx.y) * kColWarps + warp;
+    if constexpr (VEC) {
+      for (; r + row_step < rows; r += 2 * row_step) {   // two loads in flight per thread
+        Vec16<T> a = ld_vec16_stream(x + r * ld + c0);
+        Vec16<T> b = ld_vec16_stream(x + (r + row_step) * ld + c0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float fa = fabsf(ElemTraits<T>::to_f(a.v[i])), fb = fabsf(ElemTraits<T>::to_f(b.v[i]));
+          amax[i] = fmaxf(amax[i], fmaxf(fa, fb));
+          asum[i] += fa + fb;
+        }
+      }
+      if (r < rows) {
+        Vec16<T> a = ld_vec16_stream(x + r * ld + c0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float fa = fabsf(ElemTraits<T>::to_f(a.v[i]));
+          amax[i] = fmaxf(amax[i], fa);
+          asum[i] += fa;
+        }
+      }
+    } else {
+      for (; r < rows; r += row_step) {
+        float fa = fabsf(ElemTraits<T>::to_f(x[r * ld + c0]));
+        amax[0] = fmaxf(amax[0], fa);
+        asum[0] += fa;
+      }
+    }
+  }
+  __shared__ float smx[kColWarps][32 * V + 1];
+  __shared__ float sms[kColWarps][32 * V + 1];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { smx[warp][lane * V + i] = amax[i]; sms[warp][lane * V + i] = asum[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * V; c += kColThreads) {
+    float m = smx[0][c], s = sms[0][c];
+#pragma unroll
+    for (int w = 1; w < kColWarps; ++w) { m = fmaxf(m, smx[w][c]); s += sms[w][c]; }
+    const int64_t col = int64_t(blockIdx.x) * 32 * V + c;
+    if (col < cols) {
+      pmax[int64_t(blockIdx.y) * cols + col] = m;
+      psum[int64_t(blockIdx.y) * cols + col] = s;
+    }
+  }
+}
+
+// Stage 2: fixed-order fold of the partials, then the in-place updates (one thread per column, launches are
+// stream-ordered, so the accumulators are deterministic): out_max = colmax | max(out_max, colmax);
+// acc_maxsum += colmax (the numerator of "mean over calls of the per-call max", StableDiffusion1_x.py:104-112);
+// acc_abssum += sum_r |x| (the numerator of x_mean, quantizer.py:642-659).  fp64 accumulators: a sum of fp16
+// values (multiples of 2^-24 below 2^16) is exact in fp64 up to 2^13 calls x 2^16, hence order-free.
+template <typename T>
+__global__ void col_stats_stage2(const float* __restrict__ pmax, const float* __restrict__ psum, int splits,
+                                 int64_t cols, T* __restrict__ out_max, int max_mode,
+                                 double* __restrict__ acc_maxsum, double* __restrict__ acc_abssum) {
+  const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float m = pmax[c], s = psum[c];
+  for (int k = 1; k < splits; ++k) {
+    m = fmaxf(m, pmax[int64_t(k) * cols + c]);
+    s += psum[int64_t(k) * cols + c];
+  }
+  if (acc_maxsum) acc_maxsum[c] += double(m);
+  if (acc_abssum) acc_abssum[c] += double(s);
+  if (out_max) {
+    if (max_mode == 1) m = fmaxf(m, ElemTraits<T>::to_f(out_max[c]));
+    out_max[c] = ElemTraits<T>::from_f(m);
+  }
+}
+
+template <typename T>
+int launch_col_stats(const T* x, int64_t rows, int64_t cols, int64_t ld, T* out_max, int max_mode,
+                     double* acc_maxsum, double* acc_abssum, float* ws, size_t ws_bytes, cudaStream_t st) {
+  constexpr int V = ElemTraits<T>::kVec;
+  const bool vec_ok = (cols % V == 0) && (ld % V == 0) && qdm_aligned16(x);
+  const int64_t col_blocks = vec_ok ? (cols + 32 * V - 1) / (32 * V) : (cols + 31) / 32;
+  const int splits = col_splits(rows, col_blocks, 4);
+  QDM_REQUIRE(ws_bytes >= 2 * size_t(splits) * cols * sizeof(float),
+              "qdm_colstats workspace too small: %zu < %zu", ws_bytes, 2 * size_t(splits) * cols * sizeof(float));
+  float* pmax = ws;
+  float* psum = ws + size_t(splits) * cols;
+  dim3 grid((unsigned)col_blocks, (unsigned)splits);
+  if (vec_ok)
+    col_stats_stage1<T, true><<<grid, kColThreads, 0, st>>>(x, rows, cols, ld, pmax, psum);
+  else
+    col_stats_stage1<T, false><<<grid, kColThreads, 0, st>>>(x, rows, cols, ld, pmax, psum);
+  QDM_LAUNCH_CHECK();
+  col_stats_stage2<T><<<(unsigned)((cols + 255) / 256), 256, 0, st>>>(pmax, psum, splits, cols, out_max, max_mode,
+                                                                      acc_maxsum, acc_abssum);
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
 // ------------------------------------------------------------------ row |x| max
 // warp per row for long rows
 template <typename T>
@@ -396,6 +506,25 @@ extern "C" int qdm_colabssum(const void* x, int dtype, int64_t rows, int64_t col
   cudaStream_t st = (cudaStream_t)stream;
   QDM_DISPATCH_DTYPE(dtype, return (launch_col_reduce<T, COL_ABSSUM, float>((const T*)x, rows, cols, ld, out_sum, 0,
                                                                            (float*)workspace, workspace_bytes, st)));
+  return QDM_OK;
+}
+
+extern "C" size_t qdm_colstats_workspace_bytes(int64_t rows, int64_t cols) {
+  return 2 * qdm_colreduce_workspace_bytes(rows, cols);
+}
+
+extern "C" int qdm_colstats(const void* x, int dtype, int64_t rows, int64_t cols, int64_t ld, void* out_max,
+                            int max_mode, double* acc_maxsum, double* acc_abssum, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  QDM_REQUIRE(x && workspace, "qdm_colstats: null pointer");
+  QDM_REQUIRE(out_max || acc_maxsum || acc_abssum, "qdm_colstats: no output requested");
+  QDM_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "qdm_colstats: bad shape rows=%lld cols=%lld ld=%lld",
+              (long long)rows, (long long)cols, (long long)ld);
+  QDM_REQUIRE(max_mode == 0 || max_mode == 1, "qdm_colstats: max_mode must be 0 or 1");
+  QDM_DEVICE_GATE();
+  cudaStream_t st = (cudaStream_t)stream;
+  QDM_DISPATCH_DTYPE(dtype, return (launch_col_stats<T>((const T*)x, rows, cols, ld, (T*)out_max, max_mode, acc_maxsum,
+                                                       acc_abssum, (float*)workspace, workspace_bytes, st)));
   return QDM_OK;
 }
 

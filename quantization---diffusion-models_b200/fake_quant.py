@@ -204,8 +204,21 @@ class WxAxConv2d(nn.Module):
         q_x = self.act_quant(x) if self.quantise_act else x
         w = self.weight if self.weight.dtype == q_x.dtype else self.weight.to(q_x.dtype)
         b = self.bias if (self.bias is None or self.bias.dtype == q_x.dtype) else self.bias.to(q_x.dtype)
-        y = torch.nn.functional.conv2d(q_x, w, b, self.stride, self.padding, self.dilation, self.groups)
+        if self._pointwise_gemm(q_x):
+            # 1x1 convolution = F.linear over channels: the tcgen05 GEMM on the [B*H*W, C] token view
+            # (SURVEY.md section 8(f) row 3); the result is the channels-last tensor cuDNN would return.
+            from .linear import nchw_as_tokens, tokens_as_nchw
+            n, _, h, wd = q_x.shape
+            y = tokens_as_nchw(ops.gemm_f16(nchw_as_tokens(q_x), w.reshape(self.out_channels, self.in_channels), b), n, h, wd)
+        else:
+            y = torch.nn.functional.conv2d(q_x, w, b, self.stride, self.padding, self.dilation, self.groups)
         return self.output_quant(y).to(x.dtype)
+
+    def _pointwise_gemm(self, x):
+        return (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0)
+                and self.dilation == (1, 1) and self.groups == 1 and x.dim() == 4 and x.is_cuda
+                and x.dtype in (torch.float16, torch.bfloat16)
+                and self.in_channels % 8 == 0 and self.out_channels % 8 == 0)
 
     @classmethod
     def from_float(cls, module, init_only=False, weight_quant='per_tensor', act_quant='per_tensor', act_group_size=1,

@@ -102,3 +102,69 @@ class W8A8Linear(nn.Module):
 
     def extra_repr(self):
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, W8A8"
+
+
+def is_pointwise_conv(conv):
+    """1x1, stride 1, no padding / dilation / groups: the convolution is `F.linear` over the channel dimension."""
+    one = lambda v: tuple(v) == (1, 1) if not isinstance(v, int) else v == 1
+    zero = lambda v: tuple(v) == (0, 0) if not isinstance(v, (int, str)) else v == 0
+    return one(conv.kernel_size) and one(conv.stride) and zero(conv.padding) and one(conv.dilation) and conv.groups == 1
+
+
+def nchw_as_tokens(x):
+    """[B, C, H, W] -> [B*H*W, C] row-major.  A view when x is channels-last in memory (what this module's own
+    output is, and what the transformer blocks after `proj_in` want anyway); one transpose copy otherwise."""
+    b, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(b * h * w, c)
+
+
+def tokens_as_nchw(y, b, h, w):
+    """[B*H*W, O] -> logical [B, O, H, W] with channels-last strides (no copy): the tensor `F.conv2d` returns for a
+    channels-last input."""
+    return y.view(b, h, w, y.shape[-1]).permute(0, 3, 1, 2)
+
+
+class QConv1x1(nn.Module):
+    """a pointwise `nn.Conv2d` (SD1.5 `proj_in` / `proj_out`, resnet shortcuts) is a
+    GEMM over channels, so its quantised replacement is the quantised Linear module on the [B*H*W, C] token view:
+    W4A16 -> WQLinear_GEMM (kernel c), W8A8 -> W8A8Linear (kernel d).  The reference only fake-quantises conv
+    weights and calls cuDNN (`WxAxConv2d`, fake_quant.py:263-398); 3x3 convolutions still do."""
+
+    def __init__(self, inner, in_channels, out_channels):
+        super().__init__()
+        self.inner = inner
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = self.stride = self.dilation = (1, 1)
+        self.padding = (0, 0)
+        self.groups = 1
+
+    @staticmethod
+    def _as_linear(conv):
+        lin = nn.Linear(conv.in_channels, conv.out_channels, bias=conv.bias is not None,
+                        device="meta", dtype=conv.weight.dtype)
+        lin.weight = nn.Parameter(conv.weight.data.reshape(conv.out_channels, conv.in_channels), requires_grad=False)
+        if conv.bias is not None:
+            lin.bias = nn.Parameter(conv.bias.data, requires_grad=False)
+        return lin
+
+    @classmethod
+    def from_conv_w4a16(cls, conv, w_bit, group_size):
+        if not is_pointwise_conv(conv):
+            raise ValueError("QConv1x1 needs a 1x1 / stride 1 / ungrouped convolution")
+        return cls(WQLinear_GEMM.from_linear(cls._as_linear(conv), w_bit, group_size), conv.in_channels, conv.out_channels)
+
+    @classmethod
+    def from_conv_w8a8(cls, conv, smooth=None):
+        if not is_pointwise_conv(conv):
+            raise ValueError("QConv1x1 needs a 1x1 / stride 1 / ungrouped convolution")
+        return cls(W8A8Linear.from_float(cls._as_linear(conv), smooth), conv.in_channels, conv.out_channels)
+
+    @torch.no_grad()
+    def forward(self, x):
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected [B, {self.in_channels}, H, W], got {tuple(x.shape)}")
+        b, _, h, w = x.shape
+        return tokens_as_nchw(self.inner(nchw_as_tokens(x)), b, h, w)
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, kernel_size=(1, 1)"

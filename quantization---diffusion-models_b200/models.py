@@ -99,7 +99,10 @@ class BaseAWQForDiffusion:
         return []
 
     def mean_of_dict(self, act_dict):
-        """models/StableDiffusion1_x.py:104-112: mean over calls of the per-call maxima."""
+        """models/StableDiffusion1_x.py:104-112: mean over calls of the per-call maxima.  The fused hook
+        (calib_data.Fused_Mean_Max_Activation_Hook) hands over the accumulated sum instead of a dict of tensors."""
+        if hasattr(act_dict, "mean_over_calls"):
+            return act_dict.mean_over_calls()
         return torch.mean(torch.stack(list(act_dict.values())), dim=0)
 
     # ------------------------------------------------------------------ AWQ search support (new for diffusion)
@@ -226,8 +229,14 @@ class BaseAWQForDiffusion:
         modules) + quantization_config + the list of quantised components."""
         os.makedirs(save_dir, exist_ok=True)
         torch.save(self.denoiser().state_dict(), os.path.join(save_dir, "denoiser.pt"))
-        kinds = {n: type(m).__name__ for n, m in self.denoiser().named_modules()
-                 if type(m).__name__ in ("WQLinear_GEMM", "W8A8Linear", "WxAxLinear", "WxAxConv2d")}
+        kinds, wrapped = {}, set()
+        for n, m in self.denoiser().named_modules():
+            k = type(m).__name__
+            if k == "QConv1x1":                      # pointwise conv on the GEMM kernels: record the inner module kind
+                kinds[n] = f"QConv1x1:{type(m.inner).__name__}"
+                wrapped.add(n + ".inner")
+            elif k in ("WQLinear_GEMM", "W8A8Linear", "WxAxLinear", "WxAxConv2d") and n not in wrapped:
+                kinds[n] = k
         meta = {"model_type": self.model_type, "arch": self.config.get("arch", {}), "quantization_config": self.quant_config.to_transformers_dict(),
                 "quant_config": self.quant_config.to_dict(), "quant_components": self.quantized_components, "modules": kinds}
         with open(os.path.join(save_dir, "quant_components.json"), "w") as f:
@@ -237,7 +246,7 @@ class BaseAWQForDiffusion:
     def from_quantized(cls, save_dir, device="cuda", dtype=torch.float16):
         """models/base.py:736-826: rebuild the module tree, swap in `init_only` quantised modules, load the state."""
         from .fake_quant import WxAxConv2d, WxAxLinear
-        from .linear import W8A8Linear, WQLinear_GEMM
+        from .linear import QConv1x1, W8A8Linear, WQLinear_GEMM
         from .module import get_op_by_name, set_op_by_name
         from .fake_quant import _effective_group
         with open(os.path.join(save_dir, "quant_components.json")) as f:
@@ -247,7 +256,15 @@ class BaseAWQForDiffusion:
         den = model.denoiser()
         for name, kind in meta["modules"].items():
             old = get_op_by_name(den, name)
-            if kind == "WQLinear_GEMM":
+            if kind.startswith("QConv1x1:"):
+                ci, co, dev = old.in_channels, old.out_channels, old.weight.device
+                if kind.endswith("WQLinear_GEMM"):
+                    inner = WQLinear_GEMM(4, _effective_group(ci, model.quant_config.q_group_size), ci, co,
+                                          old.bias is not None, dev, dtype)
+                else:
+                    inner = W8A8Linear(ci, co, old.bias is not None, dev, dtype)
+                new = QConv1x1(inner, ci, co)
+            elif kind == "WQLinear_GEMM":
                 new = WQLinear_GEMM.from_linear(old, 4, _effective_group(old.in_features, model.quant_config.q_group_size), init_only=True)
             elif kind == "W8A8Linear":
                 new = W8A8Linear(old.in_features, old.out_features, old.bias is not None, old.weight.device, dtype)

@@ -116,6 +116,30 @@ def colabssum(x):
     return out
 
 
+def colstats(x, out_max=None, running=False, acc_maxsum=None, acc_abssum=None):
+    """One read of x -> per-call column |x| max (into `out_max`, x.dtype; running=True folds max(out_max, .)),
+    `acc_maxsum += colmax` and `acc_abssum += sum_rows |x|` (float64 [C], updated in place).  The fused form of
+    the hook statistic (utils/calib_data.py:112-121 + StableDiffusion1_x.py:104-112) and of x_mean
+    (quantize/quantizer.py:642-659).  Pass only the outputs you need."""
+    _cuda(x, "x")
+    x2 = _as_2d(x)
+    rows, cols = x2.shape
+    if running and out_max is None:
+        raise ValueError("running=True needs an existing `out_max`")
+    if out_max is None and acc_maxsum is None and acc_abssum is None:
+        out_max = torch.empty(cols, dtype=x.dtype, device=x.device)
+    for name, t, dt in (("out_max", out_max, x.dtype), ("acc_maxsum", acc_maxsum, torch.float64),
+                        ("acc_abssum", acc_abssum, torch.float64)):
+        if t is not None and (t.dtype != dt or t.numel() != cols or not t.is_contiguous() or t.device != x.device):
+            raise ValueError(f"{name} must be a contiguous {dt} tensor of {cols} elements on {x.device}")
+    L = lib()
+    ws = _ws(x.device, L.qdm_colstats_workspace_bytes(rows, cols))
+    with _guard(x.device):
+        check(L.qdm_colstats(x2.data_ptr(), _dt(x2), rows, cols, x2.stride(0), _ptr(out_max), 1 if running else 0,
+                             _ptr(acc_maxsum), _ptr(acc_abssum), ws.data_ptr(), ws.numel(), _stream(x)))
+    return out_max
+
+
 def rowabsmax(x):
     """x.abs().max(dim=-1) over contiguous rows -> [rows] (quantize/fake_quant.py:89,114)."""
     _cuda(x, "x")

@@ -146,8 +146,11 @@ class AwqQuantizer:
         import time
         tm = self.timings = {"capture_s": 0.0, "scale_search_s": 0.0, "clip_search_s": 0.0}
 
+        on_gpu = next(self.awq_model.denoiser().parameters()).is_cuda
+
         def lap(key, t0):
-            torch.cuda.synchronize()
+            if on_gpu:
+                torch.cuda.synchronize()
             tm[key] += time.perf_counter() - t0
 
         t0 = time.perf_counter()
@@ -221,9 +224,10 @@ class AwqQuantizer:
         """version == 'gemm': the reference's `_apply_quant` (quantizer.py:535-577) with the real packed module --
         pseudo_quantize_tensor + transpose + WQLinear_GEMM.from_linear fused into one RTN+pack kernel.
         version == 'w8a8': int8 per-channel weights + per-token activations (fake_quant.py:86-93,109-118).
-        Conv2d layers keep the fake-quant path (their GEMM is cuDNN's)."""
+        1x1 Conv2d layers become QConv1x1 (the same kernels on the token view); other convolutions keep the
+        fake-quant path (their GEMM is cuDNN's)."""
         from .fake_quant import _effective_group
-        from .linear import W8A8Linear
+        from .linear import QConv1x1, W8A8Linear, is_pointwise_conv
         for parent, name, layer in named_linears:
             if isinstance(layer, torch.nn.Linear):
                 if self.version == "w8a8":
@@ -236,6 +240,16 @@ class AwqQuantizer:
                     new = WQLinear_GEMM.from_linear(layer, bitWidth, g)
                 setattr(parent, name, new)
             elif isinstance(layer, torch.nn.Conv2d):
+                # pointwise convolutions are GEMMs over channels: real packed modules on the token view
+                # (SURVEY.md section 8(f) row 3); everything else keeps the fake-quant weights + cuDNN.
+                g = _effective_group(layer.in_channels, self.group_size) if self.group_size > 0 else layer.in_channels
+                if is_pointwise_conv(layer) and layer.out_channels % 8 == 0 and layer.weight.dtype != torch.float32:
+                    if self.version == "w8a8" and layer.in_channels % 16 == 0:
+                        setattr(parent, name, QConv1x1.from_conv_w8a8(layer))
+                        continue
+                    if self.version != "w8a8" and g % 64 == 0:
+                        setattr(parent, name, QConv1x1.from_conv_w4a16(layer, bitWidth, g))
+                        continue
                 self._apply_quant_fake_act(module, [(parent, name, layer)], 8 if self.version == "w8a8" else bitWidth)
 
     def _apply_quant(self, module, named_linears: Dict[str, nn.Linear], bitWidth):

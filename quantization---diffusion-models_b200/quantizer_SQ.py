@@ -11,18 +11,19 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .calib_data import Mean_Max_Activation_Hook, apply_hook, get_calib_dataset_dm, run_calibration
+from .calib_data import Fused_Mean_Max_Activation_Hook, Mean_Max_Activation_Hook, apply_hook, get_calib_dataset_dm, run_calibration
 from .quantizer import AwqQuantizer
 
 
 class SqQuantizer(AwqQuantizer):
     def __init__(self, awq_model, *args, alpha=0.5, calib_n_samples=96, calib_batch_size=8, calib_num_infer_steps=50,
-                 calib_prompts="clip-benchmark/wds_mscoco_captions2017", **kwargs):
+                 calib_prompts="clip-benchmark/wds_mscoco_captions2017", fused_stats=False, **kwargs):
         """alpha / calibration-set knobs are explicit; everything else follows quantizer_SQ.py:35-140."""
         self.alpha = alpha
         self.calib_n_samples, self.calib_batch_size = calib_n_samples, calib_batch_size
         self.calib_num_infer_steps, self.calib_prompts = calib_num_infer_steps, calib_prompts
         self.smooth_log = {}
+        self.fused_stats = fused_stats   # one-pass in-place hook statistic (SURVEY 8(f) row 4) instead of per-call tensors
         super().__init__(awq_model, *args, **kwargs)
 
     # ------------------------------------------------------------------ quantizer_SQ.py:396-431
@@ -49,7 +50,8 @@ class SqQuantizer(AwqQuantizer):
 
     def apply_hooks_to_smoothing_blocks(self, blocks):
         """quantizer_SQ.py:1064-1070."""
-        return {name: apply_hook(block, Mean_Max_Activation_Hook) for name, block in blocks.items()}
+        hook_cls = Fused_Mean_Max_Activation_Hook if self.fused_stats else Mean_Max_Activation_Hook
+        return {name: apply_hook(block, hook_cls) for name, block in blocks.items()}
 
     # ------------------------------------------------------------------ quantizer_SQ.py:323-391
     @torch.no_grad()

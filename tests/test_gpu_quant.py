@@ -254,3 +254,54 @@ def test_empty_and_bad_inputs(qdm):
         qdm.ops.colabsmax(torch.zeros(0, 8, dtype=torch.float16, device=DEV))
     with pytest.raises(RuntimeError):
         qdm.ops.colabsmax(torch.zeros(4, 8, dtype=torch.float16))
+
+
+# ------------------------------------------------------------------ one-pass hook statistic
+@pytest.mark.parametrize("dt", ["f16", "bf16", "f32"])
+@pytest.mark.parametrize("rows,cols", [(4096, 2432), (77, 768), (1, 320), (1000, 20), (513, 1283)])
+def test_colstats_one_pass(qdm, dt, rows, cols):
+    """qdm_colstats: per-call max bit-exact, fp64 sum of the per-call maxima exact, |x| sum within fp32-tree error,
+    running max and accumulators folded in place over several calls, any subset of the outputs."""
+    g = torch.Generator().manual_seed(rows * 7 + cols)
+    calls = []
+    for c in range(3):
+        x = torch.randn(rows, cols, generator=g) * (1 + c)
+        x[:, cols // 3] *= 50
+        calls.append(x.to(DT[dt]))
+    acc_max = torch.zeros(cols, dtype=torch.float64, device=DEV)
+    acc_sum = torch.zeros(cols, dtype=torch.float64, device=DEV)
+    run = torch.empty(cols, dtype=DT[dt], device=DEV)
+    for c, x in enumerate(calls):
+        out = qdm.ops.colstats(x.to(DEV), out_max=run, running=c > 0, acc_maxsum=acc_max, acc_abssum=acc_sum)
+        assert out is run
+        # the per-call statistic alone, through the same kernel
+        assert_bit_equal(qdm.ops.colstats(x.to(DEV)), O.hook_colabsmax(x), f"per-call max {c}")
+    per_call = [O.hook_colabsmax(x) for x in calls]
+    assert_bit_equal(run, torch.stack(per_call).amax(0), "running max")
+    want_max = torch.stack(per_call).double().sum(0)
+    assert torch.equal(acc_max.cpu(), want_max), "fp64 sum of per-call maxima must be exact"
+    want_sum = sum(x.abs().double().sum(0) for x in calls)
+    assert ((acc_sum.cpu() - want_sum).abs() / want_sum.clamp_min(1e-30)).max().item() < 1e-5
+    # subsets of the outputs: only the |x| sum; only the max-sum
+    only = torch.zeros(cols, dtype=torch.float64, device=DEV)
+    assert qdm.ops.colstats(calls[0].to(DEV), acc_abssum=only) is None
+    assert ((only.cpu() - calls[0].abs().double().sum(0)).abs() / want_sum.clamp_min(1e-30)).max().item() < 1e-5
+    assert torch.equal(only.float().cpu(), qdm.ops.colabssum(calls[0].to(DEV)).cpu())   # same tree as qdm_colabssum
+    only.zero_()
+    qdm.ops.colstats(calls[1].to(DEV), acc_maxsum=only)
+    assert torch.equal(only.cpu(), per_call[1].double())
+
+
+def test_colstats_strided_and_bad_inputs(qdm):
+    x = torch.randn(64, 4, 96, generator=torch.Generator().manual_seed(5)).half()
+    assert_bit_equal(qdm.ops.colstats(x.to(DEV)), O.hook_colabsmax(x), "3-D input")
+    xs = x.to(DEV)[:, :, :40]                      # row stride 96, 40 columns: ld != cols
+    assert_bit_equal(qdm.ops.colstats(xs), O.hook_colabsmax(x[:, :, :40]), "strided rows")
+    with pytest.raises(ValueError):
+        qdm.ops.colstats(torch.zeros(0, 8, dtype=torch.float16, device=DEV))
+    with pytest.raises(ValueError):
+        qdm.ops.colstats(x.to(DEV), acc_maxsum=torch.zeros(96, dtype=torch.float32, device=DEV))
+    with pytest.raises(ValueError):
+        qdm.ops.colstats(x.to(DEV), running=True)
+    with pytest.raises(RuntimeError):
+        qdm.ops.colstats(x)

@@ -201,3 +201,116 @@ def test_save_and_load_packed(qdm, tmp_path):
     again = M.StableDiffusion1_x.from_quantized(str(tmp_path), device=DEV)
     b = again.generate(["p"], lat=lat, num_inference_steps=2)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ fused hook statistic
+def test_fused_hook_vs_reference(qdm):
+    """Fused_Mean_Max_Activation_Hook (one qdm_colstats pass per call, in-place fp64 accumulators) against the
+    reference-generated fixture of the per-call hook + mean_of_dict, and against the oracle's x_mean."""
+    cd = importlib.import_module(PKG + ".calib_data")
+    M = importlib.import_module(PKG + ".models")
+    g = Golden("smoothquant.npz")
+    for tag, dt, alpha in g.cases():
+        hook = cd.Fused_Mean_Max_Activation_Hook(want_abssum=True)
+        xs = [g.get(f"{tag}_x{c}") for c in range(3)]
+        for x in xs:
+            hook(None, (x.to(DEV),), None)
+        assert hook.step == 3 and len(hook.max_scales) == 3
+        act = M.BaseAWQForDiffusion.mean_of_dict(None, hook.max_scales)
+        ref = g.get(tag + "_act")
+        assert act.dtype == ref.dtype and act.shape == ref.shape
+        # exact fp64 sum -> correctly rounded mean; the reference's fp32 summation may sit 1 ulp away on a boundary
+        a, r = act.cpu().float(), ref.float()
+        assert (a != r).float().mean().item() <= 5e-3
+        assert ((a - r).abs() <= r.abs() * 2 ** -7).all()
+        assert_bit_equal(hook.running_max, torch.stack([g.get(f"{tag}_max{c}") for c in range(3)]).amax(0), f"{tag} running max")
+        xm, om = hook.x_mean().cpu(), O.awq_x_mean(torch.cat([x.reshape(-1, x.shape[-1]) for x in xs], 0))
+        assert (xm != om).float().mean().item() <= 5e-3
+        assert ((xm.float() - om.float()).abs() <= om.float().abs() * 2 ** -7).all()
+        hook.clear()
+        assert hook.step == 0 and hook.acc_maxsum is None
+
+
+def test_sq_fused_stats_same_model(qdm):
+    """quantize('sq') with the fused hook gives the same smoothing scales as the per-call hook (<= 1 ulp on a few
+    channels) and a finite W8A8 model."""
+    outs = []
+    for fused in (False, True):
+        M, model = tiny_sd15(qdm)
+        model.calib_samples = model.default_calib_samples(1, 2)
+        model.quantize(quant_config={"w_bit": 8, "version": "w8a8"}, quantType="sq", alpha=0.5, calib_num_infer_steps=2,
+                       fused_stats=fused)
+        outs.append(model.quantizer.smooth_log)
+    assert outs[0].keys() == outs[1].keys() and len(outs[0]) > 0
+    for k in outs[0]:
+        for a, b in zip(outs[0][k], outs[1][k]):
+            a, b = a.float().cpu(), b.float().cpu()
+            assert (a != b).float().mean().item() <= 2e-2
+            assert ((a - b).abs() <= b.abs() * 2 ** -6).all()
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) row 3: pointwise convolutions on the GEMM kernels
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("B,Cin,Cout,H", [(2, 320, 320, 16), (2, 640, 320, 8), (1, 64, 128, 5), (16, 320, 320, 64)])
+def test_pointwise_conv_on_gemm_kernels(qdm, dt, B, Cin, Cout, H):
+    fq = importlib.import_module(PKG + ".fake_quant")
+    L = importlib.import_module(PKG + ".linear")
+    g = torch.Generator().manual_seed(B + Cin + Cout + H)
+    conv = torch.nn.Conv2d(Cin, Cout, 1, bias=True)
+    conv.weight.data = (torch.randn(Cout, Cin, 1, 1, generator=g) * 0.05).to(DT[dt])
+    conv.bias.data = torch.randn(Cout, generator=g).to(DT[dt])
+    x = torch.randn(B, Cin, H, H, generator=g).to(DT[dt])
+    w0, b0 = conv.weight.data.clone(), conv.bias.data.clone()
+    conv = conv.to(DEV)
+    # (1) WxAxConv2d (fake-quant weight, fake_quant.py:263-398): weight bit-exact, forward through the f16 tcgen05 GEMM
+    for wq, bits in (("per_tensor", 8), ("per_channel", 8)):
+        m = fq.WxAxConv2d.from_float(conv, weight_quant=wq, n_bits_W=bits)
+        # RTN runs in the module's dtype, the WxAxConv2d buffer is fp16 (fake_quant.py:283)
+        wref = (O.rtn_tensor(w0, bits)[0] if wq == "per_tensor" else O.rtn_rows(w0, bits)[0]).reshape(w0.shape)
+        assert_bit_equal(m.weight, wref.half(), f"{wq} conv weight")
+        assert m._pointwise_gemm(x.to(DEV))
+        ref = O.conv2d_fake(x, m.weight.cpu(), b0)
+        for xin in (x.to(DEV), x.to(DEV).contiguous(memory_format=torch.channels_last)):
+            y = m(xin)
+            assert y.shape == ref.shape and y.dtype == x.dtype
+            assert max_rel_err(y, ref) <= 1e-2
+    # (2) real W4A16 module on the token view (kernel c) vs F.conv2d on the dequantised weight
+    group = 64
+    q4 = L.QConv1x1.from_conv_w4a16(conv, 4, group)
+    wdq = O.rtn_group(w0.reshape(Cout, Cin), group, True, 4)[0]
+    assert_bit_equal(q4.inner.dequantize(), wdq, "W4 conv codes")
+    y4 = q4(x.to(DEV))
+    assert y4.shape == (B, Cout, H, H) and y4.dtype == x.dtype
+    assert max_rel_err(y4, O.conv2d_fake(x, wdq.reshape(w0.shape), b0)) <= 1e-2
+    # (3) real W8A8 module (kernel d) vs the reference's fake-quant formulation on the token view
+    q8 = L.QConv1x1.from_conv_w8a8(conv)
+    y8 = q8(x.to(DEV))
+    tok = x.permute(0, 2, 3, 1).reshape(-1, Cin)
+    ref8 = O.linear_w8a8_fake(tok, w0.reshape(Cout, Cin), b0).reshape(B, H, H, Cout).permute(0, 3, 1, 2)
+    assert max_rel_err(y8, ref8) <= 1e-2
+    with pytest.raises(ValueError):
+        L.QConv1x1.from_conv_w4a16(torch.nn.Conv2d(Cin, Cout, 3, padding=1).to(DEV).to(DT[dt]), 4, group)
+    with pytest.raises(ValueError):
+        q4(x.to(DEV)[:, :8])
+
+
+def test_quantize_gemm_swaps_pointwise_convs(qdm, tmp_path):
+    """version='gemm' / 'w8a8': the skeleton's 1x1 convolutions (proj_in / proj_out / shortcuts) become QConv1x1 on the
+    GEMM kernels, 3x3 convolutions stay WxAxConv2d; the packed checkpoint round-trips them."""
+    for version, inner in (("gemm", "WQLinear_GEMM"), ("w8a8", "W8A8Linear")):
+        M, model = tiny_sd15(qdm)
+        lat = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(1)).half().to(DEV)
+        fp = model.generate(["a", "b"], lat=lat, num_inference_steps=2).float()
+        n_pw = sum(1 for m in model.denoiser().modules() if isinstance(m, torch.nn.Conv2d) and m.kernel_size == (1, 1))
+        assert n_pw > 0
+        model.quantize(quant_config={"q_group_size": 64, "w_bit": 4 if version == "gemm" else 8, "version": version}, quantType="awq")
+        mods = [m for m in model.denoiser().modules() if type(m).__name__ == "QConv1x1"]
+        assert len(mods) == n_pw and all(type(m.inner).__name__ == inner for m in mods)
+        assert any(type(m).__name__ == "WxAxConv2d" for m in model.denoiser().modules())
+        out = model.generate(["a", "b"], lat=lat, num_inference_steps=2)
+        assert torch.isfinite(out).all()
+        assert ((out.float() - fp).abs().max() / fp.abs().max()).item() < (0.5 if version == "gemm" else 0.1)
+        d = str(tmp_path / version)
+        model.save_quantized(d)
+        again = M.StableDiffusion1_x.from_quantized(d, device=DEV)
+        assert torch.equal(again.generate(["a", "b"], lat=lat, num_inference_steps=2), out)
