@@ -561,9 +561,13 @@ def run_kernels(args):
         return e0.elapsed_time(e1) / iters
 
     nx, nw = x.numel(), w.numel()
+    st_max = torch.zeros(cols, dtype=torch.float16, device=dev)
+    st_acc1, st_acc2 = (torch.zeros(cols, dtype=torch.float64, device=dev) for _ in range(2))
     cases = [
         ("a colabsmax (hook, calib_data.py:117)", lambda: q.ops.colabsmax(x), 2 * nx),
         ("a colabssum (x_mean, quantizer.py:652)", lambda: q.ops.colabssum(x), 2 * nx),
+        ("a colstats one pass: max, sum of maxima, |x| sum (calib_data.py:112-121)",
+         lambda: q.ops.colstats(x, out_max=st_max, running=True, acc_maxsum=st_acc1, acc_abssum=st_acc2), 2 * nx),
         ("a awq_wsum (w_mean, quantizer.py:627)", lambda: q.ops.awq_wsum(w, 128), 2 * nw),
         ("a sqdiff_sum (loss, quantizer.py:777)", lambda: q.ops.sqdiff_sum(x, y), 4 * nx),
         ("a rowabsmax", lambda: q.ops.rowabsmax(x), 2 * nx),
@@ -577,7 +581,7 @@ def run_kernels(args):
         ("ref torch copy_ (same bytes model: 2 B in + 2 B out)", lambda: dq_out.copy_(w), 4 * nw),
     ]
     qw, qz, sc, _ = q.ops.quant_pack_awq(w, 128)
-    cases[11] = ("b dequant_awq (packing_utils.py:87)", lambda: q.ops.dequant_awq(qw, qz, sc, 128), nw // 2 + 2 * nw + 5 * nw // 256)
+    cases[[c[0] for c in cases].index("b dequant_awq (packing_utils.py:87)")] = ("b dequant_awq (packing_utils.py:87)", lambda: q.ops.dequant_awq(qw, qz, sc, 128), nw // 2 + 2 * nw + 5 * nw // 256)
     rows_out = []
     for name, fn, nbytes in cases:
         ms = t_ms(fn)

@@ -1,5 +1,5 @@
 """One launch of every (a)/(b) kernel on an HBM-sized tensor, for `ncu --set full` (see profiles/).
-    ncu --set full --clock-control none -k regex:'quant_|awq_wsum_stage1|sqdiff_stage1|col_reduce_stage1|dequant_awq' ..."""
+    ncu --set full --clock-control none -k regex:'quant_|awq_wsum_stage1|sqdiff_stage1|col_reduce_stage1|col_stats_stage1|dequant_awq' ..."""
 import importlib
 import os
 import sys
@@ -15,6 +15,8 @@ w = torch.randn(9728 * 4, 2432, generator=g, device=dev, dtype=torch.float16) * 
 y = (x.float() + 0.01).half()
 s_vec = (torch.rand(2432, generator=g, device=dev) + 0.5).half()
 out = torch.empty_like(w)
+st_max = torch.zeros(2560, dtype=torch.float16, device=dev)
+st_acc, st_acc2 = (torch.zeros(2560, dtype=torch.float64, device=dev) for _ in range(2))
 for _ in range(2):
     q.ops.quant_group(w, 128, 4, True, want_scales=True, out=out)
     q.ops.quant_group(w, 128, 4, True, pre_mul=s_vec, post_div=s_vec, want_scales=False, out=out)
@@ -26,5 +28,6 @@ for _ in range(2):
     q.ops.awq_wsum(w, 128)
     q.ops.sqdiff_sum(x, y)
     q.ops.colabsmax(x)
+    q.ops.colstats(x, out_max=st_max, running=True, acc_maxsum=st_acc, acc_abssum=st_acc2)
 torch.cuda.synchronize()
 print("ok")
