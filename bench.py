@@ -594,6 +594,61 @@ def run_kernels(args):
         json.dump({"peaks": peaks, "rows": rows_out}, f, indent=1)
 
 
+def run_conv(args):
+    """--mode conv: the 3x3 convolutions of the SD1.5 UNet (batch 8 + CFG) as implicit GEMMs on kernels (c) / f16 against
+    cuDNN's fp16 conv2d on the same tensors.  TFLOP/s = 2 * B*H*W * N * 9C / t; every timed call includes the NHWC
+    zero-pad pass of our path; L2 flushed before every call."""
+    import torch
+    q = importlib.import_module("quantization---diffusion-models_b200")
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    B = 16
+    shapes = [(320, 320, 64), (640, 320, 64), (960, 320, 64), (640, 640, 32), (960, 640, 32), (1280, 640, 32), (1920, 640, 32),
+              (1280, 1280, 16), (1920, 1280, 16), (2560, 1280, 16), (1280, 1280, 8), (2560, 1280, 8)]
+
+    def t_ms(fn, iters=5):
+        for _ in range(2):
+            fn()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    rows = []
+    for C, N, H in shapes:
+        x = torch.randn(B, C, H, H, generator=g, device=dev, dtype=torch.float16)
+        x_cl = x.contiguous(memory_format=torch.channels_last)
+        w = torch.randn(N, C, 3, 3, generator=g, device=dev, dtype=torch.float16) * 0.03
+        w_cl = w.contiguous(memory_format=torch.channels_last)
+        b = torch.randn(N, generator=g, device=dev, dtype=torch.float16)
+        taps = q.ops.conv3x3_weight_taps(w)
+        grp = 128 if (9 * C) % 128 == 0 else 64
+        qw, qz, sc, _ = q.ops.quant_pack_awq(taps, grp)
+        flops = 2.0 * B * H * H * N * 9 * C
+        r = {"C": C, "N": N, "H": H, "gflop": flops / 1e9,
+             "cudnn_nchw_ms": t_ms(lambda: torch.nn.functional.conv2d(x, w, b, 1, 1)),
+             "cudnn_nhwc_ms": t_ms(lambda: torch.nn.functional.conv2d(x_cl, w_cl, b, 1, 1)),
+             "ours_f16_ms": t_ms(lambda: q.ops.conv3x3_f16(x_cl, taps, b)),
+             "ours_f16_from_nchw_ms": t_ms(lambda: q.ops.conv3x3_f16(x, taps, b)),
+             "ours_w4a16_ms": t_ms(lambda: q.ops.conv3x3_w4a16(x_cl, qw, qz, sc, grp, b))}
+        for k in list(r):
+            if k.endswith("_ms"):
+                r[k[:-3] + "_tflops"] = flops / r[k] / 1e9
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    out = args.out or os.path.join(ROOT, "gpurun_out", "conv3x3.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "w") as f:
+        json.dump({"batch": B, "rows": rows}, f, indent=1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -604,7 +659,7 @@ def main():
     ap.add_argument("--layers", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn", "kernels"])
+    ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn", "kernels", "conv"])
     ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl", "sd35"])
     ap.add_argument("--quant", default="w4a16", choices=["fp16", "w4a16", "w8a8"])
     ap.add_argument("--blocks", type=int, default=0, help="sd35: number of joint blocks (default 38)")
@@ -614,6 +669,8 @@ def main():
     args = ap.parse_args()
     if args.mode == "kernels":
         return run_kernels(args)
+    if args.mode == "conv":
+        return run_conv(args)
     if args.mode != "linears":
         return run_models(args)
     if args.impl == "reference":

@@ -200,6 +200,23 @@ int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const flo
                   const void* bias, void* y, int out_dtype, int64_t M, int64_t N, int64_t K,
                   void* stream);
 
+/* 3x3 / stride 1 / padding 1 convolution as an implicit GEMM on the same tcgen05 kernels (SURVEY.md section 8(f)
+ * row 3; replaces the cuDNN call of WxAxConv2d.forward, quantize/fake_quant.py:337-341, for these geometries).
+ *   x_pad [B, H+2, W+2, C]  NHWC activations with a one-pixel zero border (dtype f16/bf16), C % 64 == 0
+ *   w_tap [N, 9*C]          weight [N, C, 3, 3] permuted to (n, dy, dx, c), fake-quantised by the caller
+ *   y_pad [B, H+2, W+2, N]  NHWC output on the same padded grid: y_pad[b, h+1, w+1, :] is output pixel (h, w);
+ *                           the border positions are scratch (written, meaningless).
+ * One GEMM with M = B*(H+2)*(W+2), K = 9*C: the TMA producer fetches the A rows of tap (dy, dx) from rows shifted by
+ * (dy-1)*(W+2) + (dx-1); nothing is materialised (no im2col buffer).  N % 8 == 0. */
+int qdm_conv3x3_f16(const void* x_pad, const void* w_tap, const void* bias, void* y_pad, int dtype,
+                    int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream);
+
+/* Same convolution from packed int4 weights: qweight [9*C, N/8], qzeros [9*C/group, N/8], scales [9*C/group, N]
+ * are the AWQ GEMM layout (utils/packing_utils.py) of w_tap; group = 64 * 2^j dividing 9*C. */
+int qdm_conv3x3_w4a16(const void* x_pad, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                      const void* bias, void* y_pad, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
+                      int64_t N, int group, void* stream);
+
 /* Host-buffer entry used for the end-to-end measurement: x_host/y_host are (pinned) HOST buffers,
  * x_dev/y_dev device staging buffers of the same size owned by the caller; the call does
  * H2D(x) -> qdm_gemm_w4a16 -> D2H(y) on `stream`. */

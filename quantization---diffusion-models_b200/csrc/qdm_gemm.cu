@@ -247,6 +247,10 @@ struct GemmParams {
   void* y;                   // [M, N] out dtype
   int is_bf16;               // element / output type: 0 fp16, 1 bf16
   long long* trace;          // QDM_TRACE builds only: per-role (tag, clock64) event log of block 0
+  // 3x3 convolution as an implicit GEMM over a zero-padded NHWC grid (qdm_conv3x3_*): K = 9 * conv_cin, the A rows of
+  // k-block kb come from the activation rows shifted by conv_off[tap], tap = kb * 64 / conv_cin.  0 = plain GEMM.
+  int conv_cin;
+  int conv_off[9];
   float* sk_data;            // stream-K: partial accumulators, [pair][rank][128 rows][256] fp32
   uint32_t* sk_flags;        // stream-K: [pair][rank][4 warps], 0 = empty, 1 = partial written (reset by its reader)
 };
@@ -894,14 +898,20 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           const int kc = kb * C::K_PER_BLOCK;
+          int ka = kc, ma = m0;   // A coordinates: shifted rows / per-tap channel offset for the implicit-GEMM convolution
+          if (p.conv_cin) {
+            const int tap = kc / p.conv_cin;
+            ka = kc - tap * p.conv_cin;
+            ma = m0 + p.conv_off[tap];
+          }
           if (KIND == G_W4) {
             mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
-            tma_load_2d(a_dst, &map_a, full_bar(stage), kc, m0);
+            tma_load_2d(a_dst, &map_a, full_bar(stage), ka, ma);
           } else {
             // B bytes: tile_n rows of 128 B (K-major box), or ceil(tile_n / 64) boxes of 64 x 64 (MN-major)
             const int kn_chunks = (tile_n + 63) / 64;
             mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + (KIND == G_F16_KN ? kn_chunks * 64 : tile_n) * ROW_BYTES);
-            tma_load_2d(a_dst, &map_a, full_bar(stage), kc, m0);
+            tma_load_2d(a_dst, &map_a, full_bar(stage), ka, ma);
             if (KIND == G_F16_KN) {
               for (int c = 0; c < kn_chunks; ++c)
                 tma_load_2d(b_dst + c * (64 * ROW_BYTES), &map_b, full_bar(stage), n0 + c * 64, kc);
@@ -1159,6 +1169,9 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (QUAD) {   // my 64 of the 128 rows, to me and to my counterpart in the other pair
             tma_load_2d_pair_mc(a_dst + uint32_t(pgrp) * (64 * ROW_BYTES), &map_a, lf, kc, m0 + pgrp * 64,
                                 uint16_t((1u << rank) | (1u << (rank + 2))));
+          } else if (p.conv_cin) {   // implicit-GEMM convolution: tap-shifted rows, channel offset inside the tap
+            const int tap = kc / p.conv_cin;
+            tma_load_2d_pair(a_dst, &map_a, lf, kc - tap * p.conv_cin, m0 + p.conv_off[tap]);
           } else {
             tma_load_2d_pair(a_dst, &map_a, lf, kc, m0);
           }
@@ -1981,6 +1994,48 @@ int check_common(const char* fn, const void* x, const void* w, void* y, int dtyp
   return QDM_OK;
 }
 
+// 3x3 / stride 1 / pad 1 convolution on a zero-padded NHWC grid [B, H+2, W+2, C]: the output pixel stored at padded
+// position r = (b*(H+2) + h+1)*(W+2) + w+1 is sum over taps (dy, dx) of x_pad[r + (dy-1)*(W+2) + (dx-1), :] @ W[:, dy, dx, :]^T,
+// i.e. one GEMM with M = B*(H+2)*(W+2) rows, K = 9*C, whose A rows are shifted by a constant per tap.  Border rows of
+// the output grid are computed too (from wrapped-around neighbours) and are ignored by the caller; rows shifted out
+// of [0, M) are zero-filled by TMA.
+struct ConvGeom {
+  int64_t B, H, W, C;
+};
+int conv_check(const char* fn, const ConvGeom& g, int64_t N) {
+  QDM_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.C > 0 && N > 0, "%s: empty problem", fn);
+  QDM_REQUIRE(g.C % 64 == 0, "%s: C=%lld must be a multiple of 64 (one k-block never straddles two taps)", fn, (long long)g.C);
+  QDM_REQUIRE(g.B * (g.H + 2) * (g.W + 2) < (1LL << 31) && 9 * g.C < (1LL << 31), "%s: dimension too large", fn);
+  return QDM_OK;
+}
+void conv_fill(GemmParams* p, const ConvGeom& g) {
+  p->conv_cin = int(g.C);
+  for (int dy = 0; dy < 3; ++dy)
+    for (int dx = 0; dx < 3; ++dx) p->conv_off[dy * 3 + dx] = int((dy - 1) * (g.W + 2) + (dx - 1));
+}
+
+int gemm_f16_impl(const char* fn, const void* x, const void* w, const void* bias, void* y, int dtype, int64_t M, int64_t N,
+                  int64_t K, const ConvGeom* conv, cudaStream_t stream) {
+  int rc = check_common(fn, x, w, y, dtype, M, N, K);
+  if (rc) return rc;
+  QDM_REQUIRE(K % 8 == 0, "%s: K=%lld must be a multiple of 8", fn, (long long)K);
+  QDM_REQUIRE(!bias || qdm_aligned16(bias), "%s: bias must be 16-byte aligned", fn);
+  QDM_DEVICE_GATE();
+  if ((rc = get_encode_fn())) return rc;
+  Maps m;
+  if ((rc = make_map(&m.a, x, 2, M, conv ? conv->C : K, 64, BLOCK_M))) return rc;
+  if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
+  if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
+  GemmParams p{};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
+  if (conv) conv_fill(&p, *conv);
+  const bool pair = use_pair(p);
+  p.tile_n = choose_tile_n(M, N, pair ? 2 : 1);
+  if ((rc = make_map(&m.b, w, 2, N, K, 64, pair ? p.tile_n / 2 : p.tile_n))) return rc;
+  m.s = m.a; m.z = m.a;
+  return dispatch_gemm<G_F16>(m, p, pair, stream);
+}
+
 }  // namespace
 
 extern "C" size_t qdm_gemm_workspace_bytes(void) { return SK_WS_BYTES; }
@@ -2005,23 +2060,16 @@ extern "C" int qdm_set_gemm_mode(int ctas) {
 
 extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void* y, int dtype,
                             int64_t M, int64_t N, int64_t K, void* stream) {
-  int rc = check_common("qdm_gemm_f16", x, w, y, dtype, M, N, K);
+  return gemm_f16_impl("qdm_gemm_f16", x, w, bias, y, dtype, M, N, K, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_conv3x3_f16(const void* x_pad, const void* w_tap, const void* bias, void* y_pad, int dtype,
+                               int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream) {
+  const ConvGeom g{B, H, W, C};
+  int rc = conv_check("qdm_conv3x3_f16", g, N);
   if (rc) return rc;
-  QDM_REQUIRE(K % 8 == 0, "qdm_gemm_f16: K=%lld must be a multiple of 8", (long long)K);
-  QDM_REQUIRE(!bias || qdm_aligned16(bias), "qdm_gemm_f16: bias must be 16-byte aligned");
-  QDM_DEVICE_GATE();
-  if ((rc = get_encode_fn())) return rc;
-  Maps m;
-  if ((rc = make_map(&m.a, x, 2, M, K, 64, BLOCK_M))) return rc;
-  if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
-  if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
-  GemmParams p{};
-  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
-  const bool pair = use_pair(p);
-  p.tile_n = choose_tile_n(M, N, pair ? 2 : 1);
-  if ((rc = make_map(&m.b, w, 2, N, K, 64, pair ? p.tile_n / 2 : p.tile_n))) return rc;
-  m.s = m.a; m.z = m.a;
-  return dispatch_gemm<G_F16>(m, p, pair, (cudaStream_t)stream);
+  return gemm_f16_impl("qdm_conv3x3_f16", x_pad, w_tap, bias, y_pad, dtype, B * (H + 2) * (W + 2), N, 9 * C, &g,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
@@ -2044,9 +2092,9 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   return dispatch_gemm<G_F16_KN>(m, p, false, (cudaStream_t)stream);
 }
 
-extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
-                              const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
-                              void* stream) {
+static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                           const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
+                           const ConvGeom* conv, void* stream) {
   int rc = check_common("qdm_gemm_w4a16", x, qweight, y, dtype, M, N, K);
   if (rc) return rc;
   QDM_REQUIRE(qzeros && scales, "qdm_gemm_w4a16: null qzeros/scales");
@@ -2057,7 +2105,7 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   QDM_DEVICE_GATE();
   // M <= 32 and small weights: latency bound -> the mma.sync kernel of qdm_gemm_smallm.cu (g_force_ctas keeps the
   // tcgen05 path reachable for A/B timing)
-  if (qdm_gemm_w4a16_smallm_fits(M, N, K) && g_force_ctas == 0 && !getenv("QDM_W4_NO_SMALLM"))
+  if (!conv && qdm_gemm_w4a16_smallm_fits(M, N, K) && g_force_ctas == 0 && !getenv("QDM_W4_NO_SMALLM"))
     return qdm_gemm_w4a16_smallm(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);
   if ((rc = get_encode_fn())) return rc;
   Maps m;
@@ -2066,18 +2114,19 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   GemmParams p{};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.group = group;
   p.qweight = qweight; p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.y = y; p.is_bf16 = dtype == QDM_BF16;
+  if (conv) conv_fill(&p, *conv);   // only the whole-tile kernels below know about tap-shifted A rows
   const bool pair = use_pair(p);
   // packed operands by TMA when their row strides are multiples of 16 bytes (N % 32 == 0): boxes are always the
   // full tile part the kernel was built for (columns past the tile are loaded and ignored, past N zero-filled)
   m.raw = (N % 32 == 0) && qdm_aligned16(qzeros) && !getenv("QDM_W4_NO_TMA");   // env: A/B switch for bring-up
   double cost2 = 0, cost4 = 0;
   p.tile_n = choose_tile_n(M, N, pair ? 2 : 1, &cost2);
-  if (pair && m.raw && g_force_ctas != 2) {   // quad clusters when the cost model prefers them (or when forced)
+  if (pair && m.raw && g_force_ctas != 2 && !conv) {   // quad clusters when the cost model prefers them (or when forced)
     const int t4 = choose_tile_n(M, N, 4, &cost4);
     (void)cost4;   // measured: no gain from the shared A loads (profiles/README.md), so quads run only when forced
     if (g_force_ctas == 4) { m.quad = true; p.tile_n = t4; }
   }
-  if ((rc = make_map(&m.a, x, 2, M, K, 64, m.quad ? BLOCK_M / 2 : BLOCK_M))) return rc;
+  if ((rc = make_map(&m.a, x, 2, M, conv ? conv->C : K, 64, m.quad ? BLOCK_M / 2 : BLOCK_M))) return rc;
   m.b = m.a; m.s = m.a; m.z = m.a;
   if (m.raw) {
     const int nloc_max = pair ? 128 : 256, G = int(K / group);
@@ -2087,7 +2136,7 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
     if ((rc = make_map(&m.z, qzeros, 4, G, N / 8, nloc_max / 8 + 4, srows, false))) return rc;
   }
   // B-stationary pair kernel: small K (resident B fits), enough tiles per pair for the one-time dequant to pay off
-  if (pair && m.raw && !m.quad && g_force_ctas == 0 && K <= 64 * CfgBS::BST_KB && !getenv("QDM_W4_NO_BSTAT")) {
+  if (!conv && pair && m.raw && !m.quad && g_force_ctas == 0 && K <= 64 * CfgBS::BST_KB && !getenv("QDM_W4_NO_BSTAT")) {
     const int64_t m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + p.tile_n - 1) / p.tile_n;
     const int64_t max_pairs = QDM_NUM_SMS / 2;
     if (n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs) {
@@ -2100,7 +2149,7 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
   // back costs ~15000 cycles (8 us) per launch as measured, so stream-K wins for long-K problems with an awkward tile count
   // (4096 x 1280 x 5120: 57 instead of 71 us) and loses for short ones (4096 x 1280 x 1280: 28.6 vs 23.1 us).
   int dev = 0;
-  if (pair && m.raw && !m.quad && (g_force_ctas == 0 || g_force_ctas == 8) && !getenv("QDM_W4_NO_SK") &&
+  if (!conv && pair && m.raw && !m.quad && (g_force_ctas == 0 || g_force_ctas == 8) && !getenv("QDM_W4_NO_SK") &&
       cudaGetDevice(&dev) == cudaSuccess && dev < 64 && g_sk_ws[dev]) {
     const int64_t P = QDM_NUM_SMS / 2, m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_kb = K / 64;
     const int64_t n_t = (N + 255) / 256;
@@ -2121,6 +2170,22 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
     }
   }
   return dispatch_gemm<G_W4>(m, p, pair, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                              const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
+                              void* stream) {
+  return gemm_w4a16_impl(x, qweight, qzeros, scales, bias, y, dtype, M, N, K, group, nullptr, stream);
+}
+
+extern "C" int qdm_conv3x3_w4a16(const void* x_pad, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                                 const void* bias, void* y_pad, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
+                                 int64_t N, int group, void* stream) {
+  const ConvGeom g{B, H, W, C};
+  int rc = conv_check("qdm_conv3x3_w4a16", g, N);
+  if (rc) return rc;
+  return gemm_w4a16_impl(x_pad, qweight, qzeros, scales, bias, y_pad, dtype, B * (H + 2) * (W + 2), N, 9 * C, group, &g,
+                         stream);
 }
 
 extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const float* sw,

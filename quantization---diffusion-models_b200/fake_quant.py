@@ -210,9 +210,28 @@ class WxAxConv2d(nn.Module):
             from .linear import nchw_as_tokens, tokens_as_nchw
             n, _, h, wd = q_x.shape
             y = tokens_as_nchw(ops.gemm_f16(nchw_as_tokens(q_x), w.reshape(self.out_channels, self.in_channels), b), n, h, wd)
+        elif self.conv3x3_gemm and self._conv3x3_gemm(q_x):
+            # 3x3 / stride 1 / pad 1: one implicit GEMM over the zero-padded NHWC grid (qdm_conv3x3_f16)
+            y = ops.conv3x3_f16(q_x, self._taps(w), b)
         else:
             y = torch.nn.functional.conv2d(q_x, w, b, self.stride, self.padding, self.dilation, self.groups)
         return self.output_quant(y).to(x.dtype)
+
+    # implicit-GEMM 3x3 path (SURVEY.md section 8(f) row 3); class-level switch so that A/B timing against cuDNN is one line
+    conv3x3_gemm = True
+
+    def _conv3x3_gemm(self, x):
+        return (self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1)
+                and self.dilation == (1, 1) and self.groups == 1 and x.dim() == 4 and x.is_cuda
+                and x.dtype in (torch.float16, torch.bfloat16)
+                and self.in_channels % 64 == 0 and self.out_channels % 8 == 0)
+
+    def _taps(self, w):
+        """[N, 9C] tap-major copy of the (fake-quant) weight, rebuilt only when the weight buffer changes"""
+        key = (w.data_ptr(), w._version, w.dtype)
+        if getattr(self, "_taps_key", None) != key:
+            self._taps_cache, self._taps_key = ops.conv3x3_weight_taps(w), key
+        return self._taps_cache
 
     def _pointwise_gemm(self, x):
         return (self.kernel_size == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0)

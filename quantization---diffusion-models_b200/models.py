@@ -235,7 +235,7 @@ class BaseAWQForDiffusion:
             if k == "QConv1x1":                      # pointwise conv on the GEMM kernels: record the inner module kind
                 kinds[n] = f"QConv1x1:{type(m.inner).__name__}"
                 wrapped.add(n + ".inner")
-            elif k in ("WQLinear_GEMM", "W8A8Linear", "WxAxLinear", "WxAxConv2d") and n not in wrapped:
+            elif k in ("WQLinear_GEMM", "W8A8Linear", "WxAxLinear", "WxAxConv2d", "QConv3x3") and n not in wrapped:
                 kinds[n] = k
         meta = {"model_type": self.model_type, "arch": self.config.get("arch", {}), "quantization_config": self.quant_config.to_transformers_dict(),
                 "quant_config": self.quant_config.to_dict(), "quant_components": self.quantized_components, "modules": kinds}
@@ -246,7 +246,7 @@ class BaseAWQForDiffusion:
     def from_quantized(cls, save_dir, device="cuda", dtype=torch.float16):
         """models/base.py:736-826: rebuild the module tree, swap in `init_only` quantised modules, load the state."""
         from .fake_quant import WxAxConv2d, WxAxLinear
-        from .linear import QConv1x1, W8A8Linear, WQLinear_GEMM
+        from .linear import QConv1x1, QConv3x3, W8A8Linear, WQLinear_GEMM, conv_group
         from .module import get_op_by_name, set_op_by_name
         from .fake_quant import _effective_group
         with open(os.path.join(save_dir, "quant_components.json")) as f:
@@ -264,6 +264,8 @@ class BaseAWQForDiffusion:
                 else:
                     inner = W8A8Linear(ci, co, old.bias is not None, dev, dtype)
                 new = QConv1x1(inner, ci, co)
+            elif kind == "QConv3x3":
+                new = QConv3x3.from_conv(old, 4, conv_group(9 * old.in_channels, model.quant_config.q_group_size), init_only=True)
             elif kind == "WQLinear_GEMM":
                 new = WQLinear_GEMM.from_linear(old, 4, _effective_group(old.in_features, model.quant_config.q_group_size), init_only=True)
             elif kind == "W8A8Linear":

@@ -437,6 +437,63 @@ def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):
     return y
 
 
+# ------------------------------------------------------------------ 3x3 convolution as an implicit GEMM (SURVEY 8(f) row 3)
+def conv3x3_weight_taps(w):
+    """[N, C, 3, 3] -> [N, 9*C] in (n, dy, dx, c) order: the K axis of the implicit GEMM (tap-major, channels inside)."""
+    n, c, kh, kw = w.shape
+    if (kh, kw) != (3, 3):
+        raise ValueError(f"expected a 3x3 kernel, got {kh}x{kw}")
+    return w.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
+
+
+def _conv3x3_io(x, n_out):
+    _cuda(x, "x")
+    if x.dim() != 4:
+        raise ValueError(f"expected [B, C, H, W], got {tuple(x.shape)}")
+    b, c, h, w = x.shape
+    # NHWC with a one-pixel zero border, one pass (a pure copy when x is channels-last in memory)
+    x_pad = torch.nn.functional.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
+    y_pad = torch.empty((b, h + 2, w + 2, n_out), dtype=x.dtype, device=x.device)
+    return x_pad, y_pad, (b, h, w, c)
+
+
+def _conv3x3_out(y_pad, h, w):
+    """interior of the padded output grid as a logical [B, N, H, W] tensor (channels-last strides, no copy)"""
+    return y_pad[:, 1:h + 1, 1:w + 1, :].permute(0, 3, 1, 2)
+
+
+def conv3x3_f16(x, w_tap, bias=None):
+    """F.conv2d(x, w, bias, stride=1, padding=1) for a 3x3 kernel, w_tap = conv3x3_weight_taps(w) (fake-quant weights,
+    quantize/fake_quant.py:337-341), as one tcgen05 GEMM with tap-shifted A rows; C % 64 == 0, N % 8 == 0."""
+    _cuda(w_tap, "w_tap")
+    if w_tap.dtype != x.dtype or w_tap.dim() != 2 or w_tap.shape[1] != 9 * x.shape[1]:
+        raise ValueError(f"w_tap must be [N, {9 * x.shape[1]}] of dtype {x.dtype}")
+    x_pad, y_pad, (b, h, w, c) = _conv3x3_io(x, w_tap.shape[0])
+    wt = w_tap.contiguous()
+    bs = bias.to(x.dtype).contiguous() if bias is not None else None
+    with _guard(x.device):
+        check(lib().qdm_conv3x3_f16(x_pad.data_ptr(), wt.data_ptr(), _ptr(bs), y_pad.data_ptr(), _dt(x_pad),
+                                    b, h, w, c, wt.shape[0], _stream(x)))
+    return _conv3x3_out(y_pad, h, w)
+
+
+def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None):
+    """The same convolution from AWQ-packed int4 weights of w_tap (qweight [9C, N/8], qzeros / scales per group)."""
+    _cuda(qweight, "qweight")
+    n = scales.shape[1]
+    if scales.dtype != x.dtype:
+        raise ValueError("x and scales must share a dtype")
+    if qweight.shape[0] != 9 * x.shape[1] or qweight.shape[1] * 8 != n:
+        raise ValueError(f"qweight must be [{9 * x.shape[1]}, N/8]")
+    x_pad, y_pad, (b, h, w, c) = _conv3x3_io(x, n)
+    bs = bias.to(x.dtype).contiguous() if bias is not None else None
+    L = lib()
+    with _guard(x.device):
+        check(L.qdm_conv3x3_w4a16(x_pad.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(), _ptr(bs),
+                                  y_pad.data_ptr(), _dt(x_pad), b, h, w, c, n, int(group), _stream(x)))
+    return _conv3x3_out(y_pad, h, w)
+
+
 def gemm_w4a16_host(x_host, x_dev, qweight, qzeros, scales, group, bias, y_dev, y_host):
     """Host-buffer entry: pinned x_host -> device -> W4A16 GEMM -> pinned y_host, all on the current stream."""
     k, nw = qweight.shape

@@ -224,10 +224,10 @@ class AwqQuantizer:
         """version == 'gemm': the reference's `_apply_quant` (quantizer.py:535-577) with the real packed module --
         pseudo_quantize_tensor + transpose + WQLinear_GEMM.from_linear fused into one RTN+pack kernel.
         version == 'w8a8': int8 per-channel weights + per-token activations (fake_quant.py:86-93,109-118).
-        1x1 Conv2d layers become QConv1x1 (the same kernels on the token view); other convolutions keep the
-        fake-quant path (their GEMM is cuDNN's)."""
+        1x1 Conv2d layers become QConv1x1 (the same kernels on the token view), 3x3 / stride 1 / pad 1 layers QConv3x3
+        (kernel c as an implicit GEMM); other convolutions keep the fake-quant path."""
         from .fake_quant import _effective_group
-        from .linear import QConv1x1, W8A8Linear, is_pointwise_conv
+        from .linear import QConv1x1, QConv3x3, W8A8Linear, conv_group, is_conv3x3_gemm, is_pointwise_conv
         for parent, name, layer in named_linears:
             if isinstance(layer, torch.nn.Linear):
                 if self.version == "w8a8":
@@ -250,6 +250,11 @@ class AwqQuantizer:
                     if self.version != "w8a8" and g % 64 == 0:
                         setattr(parent, name, QConv1x1.from_conv_w4a16(layer, bitWidth, g))
                         continue
+                # 3x3 / stride 1 / pad 1: packed int4 weights on the implicit-GEMM form of kernel (c)
+                g3 = conv_group(9 * layer.in_channels, self.group_size)
+                if self.version == "gemm" and is_conv3x3_gemm(layer) and g3 and layer.weight.dtype != torch.float32:
+                    setattr(parent, name, QConv3x3.from_conv(layer, bitWidth, g3))
+                    continue
                 self._apply_quant_fake_act(module, [(parent, name, layer)], 8 if self.version == "w8a8" else bitWidth)
 
     def _apply_quant(self, module, named_linears: Dict[str, nn.Linear], bitWidth):

@@ -151,9 +151,26 @@ def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):
     return y.to(out_dtype)
 
 
+def conv3x3_weight_taps(w):
+    n, c, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
+
+
+def _taps_to_conv(w_tap, c):
+    return w_tap.reshape(w_tap.shape[0], 3, 3, c).permute(0, 3, 1, 2)
+
+
+def conv3x3_f16(x, w_tap, bias=None):
+    return O.conv2d_fake(x, _taps_to_conv(w_tap, x.shape[1]), bias, 1, 1)
+
+
+def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None):
+    return conv3x3_f16(x, dequant_awq(qweight, qzeros, scales, group).t(), bias)
+
+
 NAMES = ("colabsmax", "colabssum", "colstats", "rowabsmax", "absmax", "awq_wsum", "sqdiff_sum", "quant_group",
          "quant_rowwise", "quant_tensor", "actquant_token_i8", "quant_pack_awq", "dequant_awq", "pack_awq", "unpack_awq",
-         "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "gemm_w8a8")
+         "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16")
 
 
 @contextlib.contextmanager

@@ -126,3 +126,86 @@ def test_gemm_w4a16_stream_k(qdm):
             assert max_rel_err(y1, y_tiles.cpu()) <= 2e-3
     finally:
         qdm.ops.set_gemm_mode(0)
+
+
+# ------------------------------------------------------------------ 3x3 convolution as an implicit GEMM
+def ref_conv3x3(x, w, bias):
+    """F.conv2d in fp32 without TF32, on the GPU (the reference's own op, fake_quant.py:339, at full precision)."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = torch.nn.functional.conv2d(x.float().cuda(), w.float().cuda(), None if bias is None else bias.float().cuda(), 1, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    return y.cpu()
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("B,C,N,H,W", [(2, 64, 64, 8, 8), (2, 320, 320, 16, 16), (1, 128, 320, 5, 7), (3, 640, 1280, 8, 8),
+                                       (1, 64, 72, 3, 3), (4, 320, 640, 32, 32), (16, 320, 320, 64, 64)])
+def test_conv3x3_implicit_gemm(qdm, dt, B, C, N, H, W):
+    """qdm_conv3x3_f16 / qdm_conv3x3_w4a16 against F.conv2d(stride 1, padding 1) on the same (fake-quant) weights;
+    the last case is the full-size SD1.5 resnet convolution (batch 8 + CFG, 64 x 64 latents)."""
+    g = torch.Generator().manual_seed(B + C + N + H + W)
+    x = torch.randn(B, C, H, W, generator=g).to(DT[dt])
+    w = (torch.randn(N, C, 3, 3, generator=g) * 0.03).to(DT[dt])
+    b = torch.randn(N, generator=g).to(DT[dt])
+    taps = qdm.ops.conv3x3_weight_taps(w.to(DEV))
+    assert taps.shape == (N, 9 * C) and torch.equal(taps.cpu().reshape(N, 3, 3, C).permute(0, 3, 1, 2), w)
+    ref = ref_conv3x3(x, w, b)
+    for xin in (x.to(DEV), x.to(DEV).contiguous(memory_format=torch.channels_last)):
+        y = qdm.ops.conv3x3_f16(xin, taps, b.to(DEV))
+        assert y.shape == (B, N, H, W) and y.dtype == DT[dt]
+        assert max_rel_err(y, ref) <= TOL
+    assert max_rel_err(qdm.ops.conv3x3_f16(x.to(DEV), taps, None), ref_conv3x3(x, w, None)) <= TOL
+    # packed int4 weights of the tap-major matrix: codes bit-exact vs the oracle's RTN, conv within tolerance
+    group = 64
+    qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(taps, group, want_dq=True) if N % 64 == 0 else (None,) * 4
+    if qweight is None:
+        oq, oz, os_, dq = O.awq_from_linear(taps.cpu(), group, 4)
+        qweight, qzeros, scales = torch.from_numpy(oq).to(DEV), torch.from_numpy(oz).to(DEV), os_.to(DEV)
+    else:
+        assert torch.equal(dq.cpu(), O.rtn_group(taps.cpu(), group, True, 4)[0])
+        dq = dq.cpu()
+    w_dq = dq.reshape(N, 3, 3, C).permute(0, 3, 1, 2)
+    y4 = qdm.ops.conv3x3_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV))
+    assert y4.shape == (B, N, H, W) and y4.dtype == DT[dt]
+    assert max_rel_err(y4, ref_conv3x3(x, w_dq, b)) <= TOL
+
+
+def test_conv3x3_modules_and_bad_inputs(qdm):
+    import importlib
+    fq = importlib.import_module("quantization---diffusion-models_b200.fake_quant")
+    L = importlib.import_module("quantization---diffusion-models_b200.linear")
+    g = torch.Generator().manual_seed(11)
+    conv = torch.nn.Conv2d(128, 192, 3, padding=1)
+    conv.weight.data = (torch.randn(192, 128, 3, 3, generator=g) * 0.03).half()
+    conv.bias.data = torch.randn(192, generator=g).half()
+    x = torch.randn(2, 128, 12, 12, generator=g).half()
+    w0, b0 = conv.weight.data.clone(), conv.bias.data.clone()
+    conv = conv.to(DEV)
+    # WxAxConv2d: same fake-quant weight, implicit GEMM vs cuDNN (class switch)
+    m = fq.WxAxConv2d.from_float(conv, weight_quant="per_tensor", n_bits_W=8)
+    assert m._conv3x3_gemm(x.to(DEV))
+    y_gemm = m(x.to(DEV))
+    try:
+        fq.WxAxConv2d.conv3x3_gemm = False
+        y_cudnn = m(x.to(DEV))
+    finally:
+        fq.WxAxConv2d.conv3x3_gemm = True
+    assert max_rel_err(y_gemm, y_cudnn.cpu()) <= 2e-3
+    assert max_rel_err(y_gemm, O.conv2d_fake(x, m.weight.cpu(), b0, 1, 1)) <= TOL
+    # QConv3x3: packed weights, dequantize() returns the conv layout of the oracle's RTN
+    q = L.QConv3x3.from_conv(conv, 4, L.conv_group(9 * 128, 128))
+    assert q.group_size == 128
+    want = O.rtn_group(w0.permute(0, 2, 3, 1).reshape(192, -1), 128, True, 4)[0].reshape(192, 3, 3, 128).permute(0, 3, 1, 2)
+    assert torch.equal(q.dequantize().cpu(), want)
+    assert max_rel_err(q(x.to(DEV)), O.conv2d_fake(x, want, b0, 1, 1)) <= TOL
+    assert L.conv_group(9 * 320, 128) == 64 and L.conv_group(9 * 640, 128) == 128 and L.conv_group(9 * 64, 0) == 64
+    with pytest.raises(ValueError):
+        L.QConv3x3.from_conv(torch.nn.Conv2d(128, 192, 3, padding=1, stride=2).to(DEV).half(), 4, 64)
+    with pytest.raises(ValueError):
+        qdm.ops.conv3x3_f16(torch.zeros(1, 100, 4, 4, dtype=torch.float16, device=DEV),
+                            torch.zeros(8, 900, dtype=torch.float16, device=DEV))     # C % 64 != 0
+    with pytest.raises(ValueError):
+        qdm.ops.conv3x3_f16(x.to(DEV), torch.zeros(8, 64, dtype=torch.float16, device=DEV))

@@ -307,6 +307,7 @@ def test_quantize_gemm_swaps_pointwise_convs(qdm, tmp_path):
         mods = [m for m in model.denoiser().modules() if type(m).__name__ == "QConv1x1"]
         assert len(mods) == n_pw and all(type(m.inner).__name__ == inner for m in mods)
         assert any(type(m).__name__ == "WxAxConv2d" for m in model.denoiser().modules())
+        assert any(type(m).__name__ == "QConv3x3" for m in model.denoiser().modules()) == (version == "gemm")
         out = model.generate(["a", "b"], lat=lat, num_inference_steps=2)
         assert torch.isfinite(out).all()
         assert ((out.float() - fp).abs().max() / fp.abs().max()).item() < (0.5 if version == "gemm" else 0.1)

@@ -49,7 +49,12 @@ def test_swap_pointwise_convs_and_checkpoint(version, inner, tmp_path):
                        quantType="awq")
         mods = [m for m in model.denoiser().modules() if type(m).__name__ == "QConv1x1"]
         assert len(mods) == n_pw > 0 and all(type(m.inner).__name__ == inner for m in mods)
-        assert sum(1 for m in model.denoiser().modules() if type(m).__name__ == "WxAxConv2d") == n_33
+        # 3x3 / stride 1 / pad 1 convolutions with C % 64 == 0 carry packed int4 weights too (implicit-GEMM kernel c);
+        # conv_in (C = 4), conv_out and the stride-2 down-samplers keep fake-quant weights
+        n_q3 = sum(1 for m in model.denoiser().modules() if type(m).__name__ == "QConv3x3")
+        n_fake = sum(1 for m in model.denoiser().modules() if type(m).__name__ == "WxAxConv2d")
+        assert n_q3 + n_fake == n_33 and n_fake >= 2
+        assert (n_q3 > 0) == (version == "gemm")
         assert not any(isinstance(m, (torch.nn.Linear, torch.nn.Conv2d)) for m in model.denoiser().modules())
         out = model.generate(["a", "b"], lat=lat, num_inference_steps=2)
         assert torch.isfinite(out).all()
