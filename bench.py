@@ -596,8 +596,9 @@ def run_kernels(args):
 
 def run_conv(args):
     """--mode conv: the 3x3 convolutions of the SD1.5 UNet (batch 8 + CFG) as implicit GEMMs on kernels (c) / f16 against
-    cuDNN's fp16 conv2d on the same tensors.  TFLOP/s = 2 * B*H*W * N * 9C / t; every timed call includes the NHWC
-    zero-pad pass of our path; L2 flushed before every call."""
+    cuDNN's fp16 conv2d on the same tensors.  TFLOP/s = 2 * B*H*W * N * 9C / t.  `ours_*`: direct form (4-D TMA, no padded
+    copy) on channels-last input; `_from_nchw`: the same with the NCHW -> NHWC transpose pass inside the timed call;
+    `_padded_grid`: the fallback form with its zero-pad pass.  L2 flushed before every call."""
     import torch
     q = importlib.import_module("quantization---diffusion-models_b200")
     dev = torch.device("cuda", 0)
@@ -636,6 +637,7 @@ def run_conv(args):
              "cudnn_nchw_ms": t_ms(lambda: torch.nn.functional.conv2d(x, w, b, 1, 1)),
              "cudnn_nhwc_ms": t_ms(lambda: torch.nn.functional.conv2d(x_cl, w_cl, b, 1, 1)),
              "ours_f16_ms": t_ms(lambda: q.ops.conv3x3_f16(x_cl, taps, b)),
+             "ours_f16_padded_grid_ms": t_ms(lambda: q.ops.conv3x3_f16(x_cl, taps, b, padded=True)),
              "ours_f16_from_nchw_ms": t_ms(lambda: q.ops.conv3x3_f16(x, taps, b)),
              "ours_w4a16_ms": t_ms(lambda: q.ops.conv3x3_w4a16(x_cl, qw, qz, sc, grp, b))}
         for k in list(r):

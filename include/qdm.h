@@ -211,11 +211,25 @@ int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const flo
 int qdm_conv3x3_f16(const void* x_pad, const void* w_tap, const void* bias, void* y_pad, int dtype,
                     int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream);
 
+/* Direct form of the same convolution for geometries whose 128-row tiles are whole image rows
+ * (qdm_conv3x3_direct_ok(H, W) == 1: W divides 128 and 128/W divides H or is a multiple of H -- every power-of-two
+ * latent size up to 128 x 128):
+ *   x [B, H, W, C] NHWC, UNPADDED;  y [B, H, W, N] NHWC, every element valid.
+ * The activation sits behind a 4-D tensor map (c, w, h, image); tap (dy, dx) moves the box start by (dx-1, dy-1) and
+ * the TMA unit's out-of-bounds zero fill is the convolution's padding: no padded copy, no border rows, no im2col.
+ * Other geometries return QDM_ERR_UNSUPPORTED (use the padded-grid entry above). */
+int qdm_conv3x3_direct_ok(int64_t H, int64_t W);
+int qdm_conv3x3_nhwc_f16(const void* x, const void* w_tap, const void* bias, void* y, int dtype,
+                         int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream);
+
 /* Same convolution from packed int4 weights: qweight [9*C, N/8], qzeros [9*C/group, N/8], scales [9*C/group, N]
  * are the AWQ GEMM layout (utils/packing_utils.py) of w_tap; group = 64 * 2^j dividing 9*C. */
 int qdm_conv3x3_w4a16(const void* x_pad, const int32_t* qweight, const int32_t* qzeros, const void* scales,
                       const void* bias, void* y_pad, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
                       int64_t N, int group, void* stream);
+int qdm_conv3x3_nhwc_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                           const void* bias, void* y, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
+                           int64_t N, int group, void* stream);
 
 /* Host-buffer entry used for the end-to-end measurement: x_host/y_host are (pinned) HOST buffers,
  * x_dev/y_dev device staging buffers of the same size owned by the caller; the call does

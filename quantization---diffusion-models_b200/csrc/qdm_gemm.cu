@@ -110,6 +110,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4-D tiled load (channels, w, h, image) for the direct implicit-GEMM convolution: coordinates outside the tensor are
+// zero-filled, which IS the convolution's zero padding
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -184,6 +192,12 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // CTA-pair TMA load multicast to the CTAs of `mask` (same CTA-relative destination offset in each); the completion
 // bytes of every destination CTA are counted on the barrier at `bar`'s offset in the leader (even rank) of THAT CTA's pair
 __device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
@@ -251,6 +265,10 @@ struct GemmParams {
   // k-block kb come from the activation rows shifted by conv_off[tap], tap = kb * 64 / conv_cin.  0 = plain GEMM.
   int conv_cin;
   int conv_off[9];
+  // direct form (conv_w != 0): A is the UNPADDED NHWC tensor behind a 4-D tensor map (c, w, h, image); a 128-row tile is
+  // a box of whole image rows (W divides 128) and tap (dy, dx) shifts its (w, h) start by (dx-1, dy-1) -- the hardware's
+  // out-of-bounds zero fill is the padding, so there is neither a padded copy nor a wasted border row.
+  int conv_w, conv_h;
   float* sk_data;            // stream-K: partial accumulators, [pair][rank][128 rows][256] fp32
   uint32_t* sk_flags;        // stream-K: [pair][rank][4 warps], 0 = empty, 1 = partial written (reset by its reader)
 };
@@ -899,19 +917,28 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           const int kc = kb * C::K_PER_BLOCK;
           int ka = kc, ma = m0;   // A coordinates: shifted rows / per-tap channel offset for the implicit-GEMM convolution
+          int tap = 0;
           if (p.conv_cin) {
-            const int tap = kc / p.conv_cin;
+            tap = kc / p.conv_cin;
             ka = kc - tap * p.conv_cin;
             ma = m0 + p.conv_off[tap];
           }
+          auto load_a = [&]() {
+            if (p.conv_w) {
+              const int hrow = m0 / p.conv_w;
+              tma_load_4d(a_dst, &map_a, full_bar(stage), ka, tap % 3 - 1, hrow % p.conv_h + tap / 3 - 1, hrow / p.conv_h);
+            } else {
+              tma_load_2d(a_dst, &map_a, full_bar(stage), ka, ma);
+            }
+          };
           if (KIND == G_W4) {
             mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
-            tma_load_2d(a_dst, &map_a, full_bar(stage), ka, ma);
+            load_a();
           } else {
             // B bytes: tile_n rows of 128 B (K-major box), or ceil(tile_n / 64) boxes of 64 x 64 (MN-major)
             const int kn_chunks = (tile_n + 63) / 64;
             mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + (KIND == G_F16_KN ? kn_chunks * 64 : tile_n) * ROW_BYTES);
-            tma_load_2d(a_dst, &map_a, full_bar(stage), ka, ma);
+            load_a();
             if (KIND == G_F16_KN) {
               for (int c = 0; c < kn_chunks; ++c)
                 tma_load_2d(b_dst + c * (64 * ROW_BYTES), &map_b, full_bar(stage), n0 + c * 64, kc);
@@ -1171,7 +1198,12 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 uint16_t((1u << rank) | (1u << (rank + 2))));
           } else if (p.conv_cin) {   // implicit-GEMM convolution: tap-shifted rows, channel offset inside the tap
             const int tap = kc / p.conv_cin;
-            tma_load_2d_pair(a_dst, &map_a, lf, kc - tap * p.conv_cin, m0 + p.conv_off[tap]);
+            if (p.conv_w) {
+              const int hrow = m0 / p.conv_w;
+              tma_load_4d_pair(a_dst, &map_a, lf, kc - tap * p.conv_cin, tap % 3 - 1, hrow % p.conv_h + tap / 3 - 1, hrow / p.conv_h);
+            } else {
+              tma_load_2d_pair(a_dst, &map_a, lf, kc - tap * p.conv_cin, m0 + p.conv_off[tap]);
+            }
           } else {
             tma_load_2d_pair(a_dst, &map_a, lf, kc, m0);
           }
@@ -2001,15 +2033,47 @@ int check_common(const char* fn, const void* x, const void* w, void* y, int dtyp
 // of [0, M) are zero-filled by TMA.
 struct ConvGeom {
   int64_t B, H, W, C;
+  bool direct;   // unpadded NHWC input behind a 4-D tensor map (see GemmParams::conv_w)
 };
+// a 128-row tile must be a box of whole image rows: W divides 128 and the box is either a divisor of H image rows or a
+// whole number of images
+bool conv_direct_ok(int64_t H, int64_t W) {
+  if (W <= 0 || H <= 0 || W > 128 || 128 % W) return false;
+  const int64_t rows = 128 / W;
+  return rows <= H ? H % rows == 0 : rows % H == 0;
+}
+int make_map_nhwc(CUtensorMap* map, const void* ptr, const ConvGeom& g) {
+  const int64_t rows = 128 / g.W;
+  const int64_t bh = rows <= g.H ? rows : g.H, bb = rows <= g.H ? 1 : rows / g.H;
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)g.W, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    qdm_set_error("cuTensorMapEncodeTiled failed (%d) for NHWC [%lld, %lld, %lld, %lld]", (int)r, (long long)g.B, (long long)g.H,
+                  (long long)g.W, (long long)g.C);
+    return QDM_ERR_CUDA;
+  }
+  return QDM_OK;
+}
 int conv_check(const char* fn, const ConvGeom& g, int64_t N) {
   QDM_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.C > 0 && N > 0, "%s: empty problem", fn);
   QDM_REQUIRE(g.C % 64 == 0, "%s: C=%lld must be a multiple of 64 (one k-block never straddles two taps)", fn, (long long)g.C);
   QDM_REQUIRE(g.B * (g.H + 2) * (g.W + 2) < (1LL << 31) && 9 * g.C < (1LL << 31), "%s: dimension too large", fn);
+  if (g.direct && !conv_direct_ok(g.H, g.W)) {
+    qdm_set_error("%s: H=%lld W=%lld cannot be tiled by whole image rows (W must divide 128); use the padded-grid entry",
+                  fn, (long long)g.H, (long long)g.W);
+    return QDM_ERR_UNSUPPORTED;
+  }
   return QDM_OK;
 }
+int64_t conv_rows(const ConvGeom& g) { return g.direct ? g.B * g.H * g.W : g.B * (g.H + 2) * (g.W + 2); }
 void conv_fill(GemmParams* p, const ConvGeom& g) {
   p->conv_cin = int(g.C);
+  if (g.direct) { p->conv_w = int(g.W); p->conv_h = int(g.H); }
   for (int dy = 0; dy < 3; ++dy)
     for (int dx = 0; dx < 3; ++dx) p->conv_off[dy * 3 + dx] = int((dy - 1) * (g.W + 2) + (dx - 1));
 }
@@ -2023,7 +2087,9 @@ int gemm_f16_impl(const char* fn, const void* x, const void* w, const void* bias
   QDM_DEVICE_GATE();
   if ((rc = get_encode_fn())) return rc;
   Maps m;
-  if ((rc = make_map(&m.a, x, 2, M, conv ? conv->C : K, 64, BLOCK_M))) return rc;
+  if (conv && conv->direct) rc = make_map_nhwc(&m.a, x, *conv);
+  else rc = make_map(&m.a, x, 2, M, conv ? conv->C : K, 64, BLOCK_M);
+  if (rc) return rc;
   if ((rc = make_map(&m.y, y, 2, M, N, EPI_COLS, 32))) return rc;
   if ((rc = make_map(&m.y16, y, 2, M, N, 16, 32, false))) return rc;
   GemmParams p{};
@@ -2065,11 +2131,20 @@ extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void
 
 extern "C" int qdm_conv3x3_f16(const void* x_pad, const void* w_tap, const void* bias, void* y_pad, int dtype,
                                int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream) {
-  const ConvGeom g{B, H, W, C};
+  const ConvGeom g{B, H, W, C, false};
   int rc = conv_check("qdm_conv3x3_f16", g, N);
   if (rc) return rc;
-  return gemm_f16_impl("qdm_conv3x3_f16", x_pad, w_tap, bias, y_pad, dtype, B * (H + 2) * (W + 2), N, 9 * C, &g,
-                       (cudaStream_t)stream);
+  return gemm_f16_impl("qdm_conv3x3_f16", x_pad, w_tap, bias, y_pad, dtype, conv_rows(g), N, 9 * C, &g, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_conv3x3_direct_ok(int64_t H, int64_t W) { return conv_direct_ok(H, W) ? 1 : 0; }
+
+extern "C" int qdm_conv3x3_nhwc_f16(const void* x, const void* w_tap, const void* bias, void* y, int dtype,
+                                    int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream) {
+  const ConvGeom g{B, H, W, C, true};
+  int rc = conv_check("qdm_conv3x3_nhwc_f16", g, N);
+  if (rc) return rc;
+  return gemm_f16_impl("qdm_conv3x3_nhwc_f16", x, w_tap, bias, y, dtype, conv_rows(g), N, 9 * C, &g, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
@@ -2126,7 +2201,9 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
     (void)cost4;   // measured: no gain from the shared A loads (profiles/README.md), so quads run only when forced
     if (g_force_ctas == 4) { m.quad = true; p.tile_n = t4; }
   }
-  if ((rc = make_map(&m.a, x, 2, M, conv ? conv->C : K, 64, m.quad ? BLOCK_M / 2 : BLOCK_M))) return rc;
+  if (conv && conv->direct) rc = make_map_nhwc(&m.a, x, *conv);
+  else rc = make_map(&m.a, x, 2, M, conv ? conv->C : K, 64, m.quad ? BLOCK_M / 2 : BLOCK_M);
+  if (rc) return rc;
   m.b = m.a; m.s = m.a; m.z = m.a;
   if (m.raw) {
     const int nloc_max = pair ? 128 : 256, G = int(K / group);
@@ -2181,11 +2258,19 @@ extern "C" int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32
 extern "C" int qdm_conv3x3_w4a16(const void* x_pad, const int32_t* qweight, const int32_t* qzeros, const void* scales,
                                  const void* bias, void* y_pad, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
                                  int64_t N, int group, void* stream) {
-  const ConvGeom g{B, H, W, C};
+  const ConvGeom g{B, H, W, C, false};
   int rc = conv_check("qdm_conv3x3_w4a16", g, N);
   if (rc) return rc;
-  return gemm_w4a16_impl(x_pad, qweight, qzeros, scales, bias, y_pad, dtype, B * (H + 2) * (W + 2), N, 9 * C, group, &g,
-                         stream);
+  return gemm_w4a16_impl(x_pad, qweight, qzeros, scales, bias, y_pad, dtype, conv_rows(g), N, 9 * C, group, &g, stream);
+}
+
+extern "C" int qdm_conv3x3_nhwc_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                                      const void* bias, void* y, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
+                                      int64_t N, int group, void* stream) {
+  const ConvGeom g{B, H, W, C, true};
+  int rc = conv_check("qdm_conv3x3_nhwc_w4a16", g, N);
+  if (rc) return rc;
+  return gemm_w4a16_impl(x, qweight, qzeros, scales, bias, y, dtype, conv_rows(g), N, 9 * C, group, &g, stream);
 }
 
 extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq, const float* sw,

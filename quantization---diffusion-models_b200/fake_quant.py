@@ -8,6 +8,7 @@ Deviations from the reference, all deliberate:
     raises NotImplementedError;
   * WxAxLinear.forward does not evaluate `str(self)` per call (fake_quant.py:216-217).
 """
+import os
 from functools import partial
 
 import torch
@@ -218,7 +219,10 @@ class WxAxConv2d(nn.Module):
         return self.output_quant(y).to(x.dtype)
 
     # implicit-GEMM 3x3 path; class-level switch so that A/B timing against cuDNN is one line
-    conv3x3_gemm = True
+    # Off by default for the fake-quant module: with fp16 weights there is no memory to save and cuDNN's channels-last
+    # kernels are 15-25 % faster than the implicit GEMM (profiles/conv3x3_r01.json); QDM_CONV_GEMM=1 or setting the
+    # class attribute turns it on.  The packed-int4 module (linear.QConv3x3) always runs the implicit GEMM.
+    conv3x3_gemm = os.environ.get("QDM_CONV_GEMM", "0") == "1"
 
     def _conv3x3_gemm(self, x):
         return (self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1)

@@ -446,38 +446,49 @@ def conv3x3_weight_taps(w):
     return w.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
 
 
-def _conv3x3_io(x, n_out):
+def _conv3x3_io(x, n_out, padded=None):
+    """Returns (x_in, y_out, (b, h, w, c), direct).  direct (W divides 128, see qdm_conv3x3_direct_ok): x as unpadded
+    NHWC -- a free view when x is channels-last in memory, one transpose copy otherwise -- and a dense NHWC output.
+    Otherwise the padded-grid form: NHWC with a one-pixel zero border and an output on the same grid."""
     _cuda(x, "x")
     if x.dim() != 4:
         raise ValueError(f"expected [B, C, H, W], got {tuple(x.shape)}")
     b, c, h, w = x.shape
-    # NHWC with a one-pixel zero border, one pass (a pure copy when x is channels-last in memory)
-    x_pad = torch.nn.functional.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
-    y_pad = torch.empty((b, h + 2, w + 2, n_out), dtype=x.dtype, device=x.device)
-    return x_pad, y_pad, (b, h, w, c)
+    # measured (profiles/conv3x3_r01.json): the direct form wins for rows of >= 32 pixels (no padded copy, no border
+    # rows); for 16- and 8-pixel rows the 4-D boxes are fetched more slowly than they save and the padded grid wins
+    direct = (w >= 32 and bool(lib().qdm_conv3x3_direct_ok(h, w))) if padded is None else not padded
+    if direct:
+        x_in = x.permute(0, 2, 3, 1).contiguous()
+        y = torch.empty((b, h, w, n_out), dtype=x.dtype, device=x.device)
+    else:
+        x_in = torch.nn.functional.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
+        y = torch.empty((b, h + 2, w + 2, n_out), dtype=x.dtype, device=x.device)
+    return x_in, y, (b, h, w, c), direct
 
 
-def _conv3x3_out(y_pad, h, w):
-    """interior of the padded output grid as a logical [B, N, H, W] tensor (channels-last strides, no copy)"""
-    return y_pad[:, 1:h + 1, 1:w + 1, :].permute(0, 3, 1, 2)
+def _conv3x3_out(y, h, w, direct):
+    """logical [B, N, H, W] view of the NHWC result (channels-last memory format; dense in the direct form, the
+    interior of the padded grid otherwise)"""
+    return (y if direct else y[:, 1:h + 1, 1:w + 1, :]).permute(0, 3, 1, 2)
 
 
-def conv3x3_f16(x, w_tap, bias=None):
+def conv3x3_f16(x, w_tap, bias=None, padded=None):
     """F.conv2d(x, w, bias, stride=1, padding=1) for a 3x3 kernel, w_tap = conv3x3_weight_taps(w) (fake-quant weights,
-    quantize/fake_quant.py:337-341), as one tcgen05 GEMM with tap-shifted A rows; C % 64 == 0, N % 8 == 0."""
+    quantize/fake_quant.py:337-341), as one tcgen05 GEMM whose A rows are fetched per tap by TMA; C % 64 == 0,
+    N % 8 == 0.  `padded` forces the padded-grid (True) or direct (False) form; default: direct when the geometry allows."""
     _cuda(w_tap, "w_tap")
     if w_tap.dtype != x.dtype or w_tap.dim() != 2 or w_tap.shape[1] != 9 * x.shape[1]:
         raise ValueError(f"w_tap must be [N, {9 * x.shape[1]}] of dtype {x.dtype}")
-    x_pad, y_pad, (b, h, w, c) = _conv3x3_io(x, w_tap.shape[0])
+    x_in, y, (b, h, w, c), direct = _conv3x3_io(x, w_tap.shape[0], padded)
     wt = w_tap.contiguous()
     bs = bias.to(x.dtype).contiguous() if bias is not None else None
+    fn = lib().qdm_conv3x3_nhwc_f16 if direct else lib().qdm_conv3x3_f16
     with _guard(x.device):
-        check(lib().qdm_conv3x3_f16(x_pad.data_ptr(), wt.data_ptr(), _ptr(bs), y_pad.data_ptr(), _dt(x_pad),
-                                    b, h, w, c, wt.shape[0], _stream(x)))
-    return _conv3x3_out(y_pad, h, w)
+        check(fn(x_in.data_ptr(), wt.data_ptr(), _ptr(bs), y.data_ptr(), _dt(x_in), b, h, w, c, wt.shape[0], _stream(x)))
+    return _conv3x3_out(y, h, w, direct)
 
 
-def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None):
+def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
     """The same convolution from AWQ-packed int4 weights of w_tap (qweight [9C, N/8], qzeros / scales per group)."""
     _cuda(qweight, "qweight")
     n = scales.shape[1]
@@ -485,13 +496,13 @@ def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None):
         raise ValueError("x and scales must share a dtype")
     if qweight.shape[0] != 9 * x.shape[1] or qweight.shape[1] * 8 != n:
         raise ValueError(f"qweight must be [{9 * x.shape[1]}, N/8]")
-    x_pad, y_pad, (b, h, w, c) = _conv3x3_io(x, n)
+    x_in, y, (b, h, w, c), direct = _conv3x3_io(x, n, padded)
     bs = bias.to(x.dtype).contiguous() if bias is not None else None
-    L = lib()
+    fn = lib().qdm_conv3x3_nhwc_w4a16 if direct else lib().qdm_conv3x3_w4a16
     with _guard(x.device):
-        check(L.qdm_conv3x3_w4a16(x_pad.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(), _ptr(bs),
-                                  y_pad.data_ptr(), _dt(x_pad), b, h, w, c, n, int(group), _stream(x)))
-    return _conv3x3_out(y_pad, h, w)
+        check(fn(x_in.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(), _ptr(bs), y.data_ptr(),
+                 _dt(x_in), b, h, w, c, n, int(group), _stream(x)))
+    return _conv3x3_out(y, h, w, direct)
 
 
 def gemm_w4a16_host(x_host, x_dev, qweight, qzeros, scales, group, bias, y_dev, y_host):

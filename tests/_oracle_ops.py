@@ -160,11 +160,11 @@ def _taps_to_conv(w_tap, c):
     return w_tap.reshape(w_tap.shape[0], 3, 3, c).permute(0, 3, 1, 2)
 
 
-def conv3x3_f16(x, w_tap, bias=None):
+def conv3x3_f16(x, w_tap, bias=None, padded=None):
     return O.conv2d_fake(x, _taps_to_conv(w_tap, x.shape[1]), bias, 1, 1)
 
 
-def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None):
+def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
     return conv3x3_f16(x, dequant_awq(qweight, qzeros, scales, group).t(), bias)
 
 

@@ -142,7 +142,8 @@ def ref_conv3x3(x, w, bias):
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("B,C,N,H,W", [(2, 64, 64, 8, 8), (2, 320, 320, 16, 16), (1, 128, 320, 5, 7), (3, 640, 1280, 8, 8),
-                                       (1, 64, 72, 3, 3), (4, 320, 640, 32, 32), (16, 320, 320, 64, 64)])
+                                       (1, 64, 72, 3, 3), (4, 320, 640, 32, 32), (16, 320, 320, 64, 64), (1, 64, 64, 128, 128),
+                                       (5, 128, 64, 4, 4), (2, 64, 64, 16, 8), (1, 64, 128, 12, 16)])
 def test_conv3x3_implicit_gemm(qdm, dt, B, C, N, H, W):
     """qdm_conv3x3_f16 / qdm_conv3x3_w4a16 against F.conv2d(stride 1, padding 1) on the same (fake-quant) weights;
     the last case is the full-size SD1.5 resnet convolution (batch 8 + CFG, 64 x 64 latents)."""
@@ -153,10 +154,18 @@ def test_conv3x3_implicit_gemm(qdm, dt, B, C, N, H, W):
     taps = qdm.ops.conv3x3_weight_taps(w.to(DEV))
     assert taps.shape == (N, 9 * C) and torch.equal(taps.cpu().reshape(N, 3, 3, C).permute(0, 3, 1, 2), w)
     ref = ref_conv3x3(x, w, b)
+    direct_ok = bool(qdm.ops.lib().qdm_conv3x3_direct_ok(H, W))
+    assert direct_ok == (128 % W == 0 and ((128 // W) % H == 0 or H % (128 // W) == 0))
     for xin in (x.to(DEV), x.to(DEV).contiguous(memory_format=torch.channels_last)):
-        y = qdm.ops.conv3x3_f16(xin, taps, b.to(DEV))
-        assert y.shape == (B, N, H, W) and y.dtype == DT[dt]
-        assert max_rel_err(y, ref) <= TOL
+        for padded in ([True, False] if direct_ok else [True]):      # padded-grid form and direct 4-D TMA form
+            y = qdm.ops.conv3x3_f16(xin, taps, b.to(DEV), padded=padded)
+            assert y.shape == (B, N, H, W) and y.dtype == DT[dt]
+            assert max_rel_err(y, ref) <= TOL, (padded,)
+            if not padded:
+                assert y.is_contiguous(memory_format=torch.channels_last)
+    if not direct_ok:
+        with pytest.raises(RuntimeError, match="whole image rows"):
+            qdm.ops.conv3x3_f16(x.to(DEV), taps, None, padded=False)
     assert max_rel_err(qdm.ops.conv3x3_f16(x.to(DEV), taps, None), ref_conv3x3(x, w, None)) <= TOL
     # packed int4 weights of the tap-major matrix: codes bit-exact vs the oracle's RTN, conv within tolerance
     group = 64
@@ -168,9 +177,11 @@ def test_conv3x3_implicit_gemm(qdm, dt, B, C, N, H, W):
         assert torch.equal(dq.cpu(), O.rtn_group(taps.cpu(), group, True, 4)[0])
         dq = dq.cpu()
     w_dq = dq.reshape(N, 3, 3, C).permute(0, 3, 1, 2)
-    y4 = qdm.ops.conv3x3_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV))
-    assert y4.shape == (B, N, H, W) and y4.dtype == DT[dt]
-    assert max_rel_err(y4, ref_conv3x3(x, w_dq, b)) <= TOL
+    ref4 = ref_conv3x3(x, w_dq, b)
+    for padded in ([True, False] if direct_ok else [True]):
+        y4 = qdm.ops.conv3x3_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV), padded=padded)
+        assert y4.shape == (B, N, H, W) and y4.dtype == DT[dt]
+        assert max_rel_err(y4, ref4) <= TOL, (padded,)
 
 
 def test_conv3x3_modules_and_bad_inputs(qdm):
@@ -187,12 +198,17 @@ def test_conv3x3_modules_and_bad_inputs(qdm):
     # WxAxConv2d: same fake-quant weight, implicit GEMM vs cuDNN (class switch)
     m = fq.WxAxConv2d.from_float(conv, weight_quant="per_tensor", n_bits_W=8)
     assert m._conv3x3_gemm(x.to(DEV))
-    y_gemm = m(x.to(DEV))
+    default = fq.WxAxConv2d.conv3x3_gemm          # off unless QDM_CONV_GEMM=1 (cuDNN, as the reference)
     try:
+        fq.WxAxConv2d.conv3x3_gemm = True
+        qdm.ops.launch_count(reset=True)
+        y_gemm = m(x.to(DEV))
+        assert qdm.ops.launch_count() == 1         # the implicit GEMM really ran
         fq.WxAxConv2d.conv3x3_gemm = False
         y_cudnn = m(x.to(DEV))
+        assert qdm.ops.launch_count() == 1
     finally:
-        fq.WxAxConv2d.conv3x3_gemm = True
+        fq.WxAxConv2d.conv3x3_gemm = default
     assert max_rel_err(y_gemm, y_cudnn.cpu()) <= 2e-3
     assert max_rel_err(y_gemm, O.conv2d_fake(x, m.weight.cpu(), b0, 1, 1)) <= TOL
     # QConv3x3: packed weights, dequantize() returns the conv layout of the oracle's RTN
