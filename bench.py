@@ -330,6 +330,13 @@ def run_tables(args):
 
     q = importlib.import_module("quantization---diffusion-models_b200")
     shapes_mod, layers = layer_list()
+    if args.model == "sdxl":      # BASELINE config 3: SDXL UNet, 1024^2, batch 4 + CFG
+        layers = shapes_mod.sdxl_unet_linears(batch=4, cfg=True)
+    elif args.model == "sd35":    # BASELINE config 4: SD3.5-L MMDiT, 1024^2, batch 1
+        layers = shapes_mod.sd35_mmdit_linears(batch=1)
+    counts = {}
+    for _, m_, n_, k_, c_ in layers:
+        counts[(m_, n_, k_)] = counts.get((m_, n_, k_), 0) + c_
     dev = torch.device("cuda", 0)
     peaks = measured_peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -382,7 +389,7 @@ def run_tables(args):
         w = torch.randn(n, k, generator=g, device=dev, dtype=torch.float16) * 0.02
         qw, qz, sc, dq = q.ops.quant_pack_awq(w, grp, want_dq=True)
         flops = 2.0 * m * n * k
-        r = {"M": m, "N": n, "K": k, "group": grp}
+        r = {"M": m, "N": n, "K": k, "group": grp, "calls_per_step": counts.get((m, n, k), 1)}
         t = time_fn(lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp))
         by = shapes_mod.gemm_bytes_w4a16(m, n, k, grp)
         roof = min(peaks["bf16_burst"], by and flops / by * peaks["hbm"] / 1e3)
@@ -402,10 +409,25 @@ def run_tables(args):
         rows.append(r)
         print(json.dumps(r), flush=True)
         del x, w, qw, qz, sc, dq
-    out = args.out or os.path.join(ROOT, "gpurun_out", "gemm_sweep.json" if args.sweep else "gemm_layers.json")
+    summary = None
+    if not args.sweep:   # the whole Linear pass of one denoise step, every launch timed alone with a cold L2
+        tot_f = sum(2.0 * r["M"] * r["N"] * r["K"] * r["calls_per_step"] for r in rows)
+        summary = {"model": args.model, "tflop_per_step": tot_f / 1e12}
+        for key, sub in (("w4a16", "w4a16"), ("w8a8", "w8a8_gemm"), ("f16_tcgen05", "f16_tcgen05"), ("cublas_f16", "cublas_f16")):
+            if all(sub in r for r in rows):
+                ms = sum(r[sub]["ms"] * r["calls_per_step"] for r in rows)
+                summary[key] = {"ms_per_step": ms, "tflops": tot_f / ms / 1e9}
+        if all("w8a8_actquant" in r for r in rows):
+            ms = sum((r["w8a8_gemm"]["ms"] + r["w8a8_actquant"]["ms"]) * r["calls_per_step"] for r in rows)
+            summary["w8a8_with_actquant"] = {"ms_per_step": ms, "tflops": tot_f / ms / 1e9}
+        roof_ms = sum(2.0 * r["M"] * r["N"] * r["K"] / r["w4a16"]["roof_tflops"] / 1e9 * r["calls_per_step"] for r in rows)
+        summary["w4a16_per_shape_roofline"] = {"ms_per_step": roof_ms, "frac": roof_ms / summary["w4a16"]["ms_per_step"]}
+        print(json.dumps({"summary": summary}), flush=True)
+    name = "gemm_sweep.json" if args.sweep else ("gemm_layers.json" if args.model == "sd15" else f"gemm_layers_{args.model}.json")
+    out = args.out or os.path.join(ROOT, "gpurun_out", name)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as f:
-        json.dump({"peaks": peaks, "rows": rows}, f, indent=1)
+        json.dump({"peaks": peaks, "summary": summary, "rows": rows}, f, indent=1)
 
 
 # ------------------------------------------------------------------------------------------ model-level modes
