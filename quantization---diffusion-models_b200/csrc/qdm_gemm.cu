@@ -25,6 +25,9 @@
 #include <mutex>
 #include <stdlib.h>
 
+bool qdm_gemm_w4a16_skinny_fits(int64_t M, int64_t N, int64_t K);
+int qdm_gemm_w4a16_skinny(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* bias,
+                          void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int group, cudaStream_t st);
 bool qdm_gemm_w4a16_smallm_fits(int64_t M, int64_t N, int64_t K);
 int qdm_gemm_w4a16_smallm(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* bias,
                           void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int group, cudaStream_t st);
@@ -2180,6 +2183,9 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
   QDM_DEVICE_GATE();
   // M <= 32 and small weights: latency bound -> the mma.sync kernel of qdm_gemm_smallm.cu (g_force_ctas keeps the
   // tcgen05 path reachable for A/B timing)
+  // M <= 32: weight-bandwidth / latency bound -> the sector-wide cluster-split-K mma.sync kernel of qdm_gemm_skinny.cu
+  if (!conv && qdm_gemm_w4a16_skinny_fits(M, N, K) && g_force_ctas == 0 && !getenv("QDM_W4_NO_SKINNY"))
+    return qdm_gemm_w4a16_skinny(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);
   if (!conv && qdm_gemm_w4a16_smallm_fits(M, N, K) && g_force_ctas == 0 && !getenv("QDM_W4_NO_SMALLM"))
     return qdm_gemm_w4a16_smallm(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);
   if ((rc = get_encode_fn())) return rc;

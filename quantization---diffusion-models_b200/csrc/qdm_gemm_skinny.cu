@@ -1,0 +1,321 @@
+// (c'') W4A16 for M <= 32 rows, any weight size: the AdaLN / time-embedding / pooled-text projections of the diffusion
+// models (SD3.5: norm1.linear [14592, 2432] with M = batch, 75 calls per step; SDXL: M = 8; SD1.5: M = 16).  These are
+// bound by the packed-weight bandwidth (0.5 B per weight, every weight used once) and by latency, so the kernel is
+// built around the weight stream:
+//   * a warp-step is a [16 k rows x 64 columns] block of packed words: lane (nl = lane / 4, t = lane % 4) loads the word
+//     of column group nl (8 adjacent words = one 32-byte sector per row) from rows kk + 4 t + {0, 1, 2, 3} -- every
+//     sector it touches is fully used, 4 x U loads in flight per lane;
+//   * the weights are the A operand of mma.sync.m16n8k16 (W^T [16 columns x 16 k] times x^T [16 k x 8 rows]): which
+//     physical row / column plays which logical (n, k) of the fragment is free as long as A, B and the output agree, so
+//     the lane's four words ARE four A fragments (column pairs (2j, 2j+1) of its word, j = 0..3) without any shuffle:
+//     a[0] = column 2j, rows 4t, 4t+1;  a[1] = column 2j+1, same rows;  a[2], a[3] = rows 4t+2, 4t+3.  The x fragment is
+//     one 8-byte shared-memory load (x[m = nl][kk + 4t .. 4t+3]);
+//   * unpack: one byte permute pairs the same byte of two rows, one and-or drops the nibbles into the mantissa of 1024.0
+//     (fp16) / 128.0 (bf16), the packed subtract of (magic + z) gives the exact integer q - z and the packed multiply by
+//     the scale rounds once: bit-identical to dequantize_gemm (utils/packing_utils.py:87-102), ~1.1 instructions per weight;
+//   * K is split over the 8 warps of a CTA and over the CTAs of a thread-block CLUSTER (1, 2, 4 or 8, chosen so that
+//     every SM holds ~2 CTAs); partial sums are folded through shared memory inside the CTA and through distributed
+//     shared memory inside the cluster, both in a fixed order: deterministic, no workspace, no atomics.
+#include "qdm_common.cuh"
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int SK_WARPS = 8;
+constexpr int SK_U = 4;        // warp-steps whose packed words are requested together (16 loads in flight per lane)
+constexpr int SK_MAX_MT = 4;   // up to 32 rows of x (m8 tiles)
+
+template <bool BF16>
+__device__ __forceinline__ void mma_w_x(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (BF16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+
+// packed (v - zm) * s in the tensor dtype: v and zm hold magic + integer, so the difference is exact; one rounding
+template <bool BF16>
+__device__ __forceinline__ uint32_t sub_mul2(uint32_t v, uint32_t zm, uint32_t s) {
+  if (BF16) {
+    __nv_bfloat162 r = __hmul2(__hsub2(*reinterpret_cast<__nv_bfloat162*>(&v), *reinterpret_cast<__nv_bfloat162*>(&zm)),
+                               *reinterpret_cast<__nv_bfloat162*>(&s));
+    return *reinterpret_cast<uint32_t*>(&r);
+  } else {
+    __half2 r = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&v), *reinterpret_cast<__half2*>(&zm)), *reinterpret_cast<__half2*>(&s));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+}
+
+template <bool BF16, int MT>
+__global__ void __launch_bounds__(SK_WARPS * 32)
+w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__ qweight, const uint32_t* __restrict__ qzeros,
+                    const uint16_t* __restrict__ scales, const uint16_t* __restrict__ bias, uint16_t* __restrict__ y,
+                    int M, int N, int K, int group, int steps_per_cta) {
+  constexpr uint32_t MAGIC = BF16 ? 0x43004300u : 0x64006400u;   // 128.0 | 1024.0 in both halves
+  extern __shared__ uint4 sk_smem_raw[];
+  // [8 MT rows][k slice + 16] x slice, then the per-warp partial sums [warps][4 j][MT][4][32], then the CTA's sum
+  uint16_t* xs = reinterpret_cast<uint16_t*>(sk_smem_raw);
+  const int k_slice = steps_per_cta * 16;
+  const int pitch = k_slice + 16;
+  float* red = reinterpret_cast<float*>(xs + 8 * MT * pitch);
+  float* part = red + SK_WARPS * 4 * MT * 4 * 32;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: nothing global is read before this
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nl = lane >> 2, t = lane & 3;
+  const int words_per_row = N >> 3;
+  const int wc = int(blockIdx.x) * 8 + nl;              // this lane's packed word column (8 output columns)
+  const bool col_on = wc < words_per_row;
+  const int steps_total = K >> 4;
+  const int s_lo = crank * steps_per_cta;               // this CTA's k16 steps
+  const int s_hi = min(steps_total, s_lo + steps_per_cta);
+  const int n_steps = max(0, s_hi - s_lo);
+  const int spw = (n_steps + SK_WARPS - 1) / SK_WARPS;  // contiguous chunk per warp: the group changes rarely
+  const int w_lo = s_lo + warp * spw, w_hi = min(s_hi, w_lo + spw);
+
+  uint32_t w[SK_U][4];
+  auto load_words = [&](int s0) {
+#pragma unroll
+    for (int u = 0; u < SK_U; ++u) {
+      const bool on = col_on && (s0 + u) < w_hi;
+      const uint32_t* wp = qweight + int64_t(((s0 + u) << 4) + 4 * t) * words_per_row + wc;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[u][i] = on ? __ldg(wp + int64_t(i) * words_per_row) : 0u;
+    }
+  };
+  // first chunk of packed words and the first group's zero points / scales: in flight while x is staged
+  const int g_pre = (w_lo << 4) / group;
+  uint32_t zw_pre = 0u;
+  uint4 sv_pre = make_uint4(0, 0, 0, 0);
+  if (w_lo < w_hi) {
+    load_words(w_lo);
+    if (col_on) {
+      zw_pre = __ldg(qzeros + int64_t(g_pre) * words_per_row + wc);
+      sv_pre = __ldg(reinterpret_cast<const uint4*>(scales + int64_t(g_pre) * N + 8 * wc));
+    }
+  }
+
+  // stage this CTA's k slice of x (rows >= M are zeros)
+  {
+    const int vec_per_row = k_slice >> 3;
+    const int k0 = s_lo << 4;
+    for (int idx = threadIdx.x; idx < 8 * MT * vec_per_row; idx += SK_WARPS * 32) {
+      const int row = idx / vec_per_row, c8 = idx - row * vec_per_row;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row < M && k0 + c8 * 8 < K) v = __ldg(reinterpret_cast<const uint4*>(x + int64_t(row) * K + k0) + c8);
+      *reinterpret_cast<uint4*>(xs + row * pitch + c8 * 8) = v;
+    }
+  }
+  __syncthreads();
+
+  float acc[4][MT][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][m][i] = 0.f;
+
+  int g_cur = -1;
+  uint32_t zm[8], sc2[8];   // per column of this lane's word: (magic + z) and the scale, each duplicated into both halves
+  for (int s0 = w_lo; s0 < w_hi; s0 += SK_U) {
+    if (s0 != w_lo) load_words(s0);
+#pragma unroll
+    for (int u = 0; u < SK_U; ++u) {
+      const int st = s0 + u;
+      if (st >= w_hi) break;
+      const int kk = st << 4;
+      const int g = kk / group;                         // group % 16 == 0: a step never straddles two groups
+      if (g != g_cur) {
+        g_cur = g;
+        uint32_t zw = zw_pre;
+        uint4 sv = sv_pre;
+        if (col_on && g != g_pre) {
+          zw = __ldg(qzeros + int64_t(g) * words_per_row + wc);
+          sv = __ldg(reinterpret_cast<const uint4*>(scales + int64_t(g) * N + 8 * wc));
+        }
+        const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int nib = (c >> 1) + 4 * (c & 1);       // column c of a word sits in nibble {0,4,1,5,2,6,3,7}[c]
+          const uint32_t z = (zw >> (4 * nib)) & 0xFu;
+          zm[c] = MAGIC | z | (z << 16);
+          const uint32_t s16 = (c & 1) ? (sw[c >> 1] >> 16) : (sw[c >> 1] & 0xFFFFu);
+          sc2[c] = s16 | (s16 << 16);
+        }
+      }
+      // x fragment: rows kk + 4t .. 4t + 3 of x row nl (+ 8 per m-tile)
+      uint2 xb[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        xb[m] = *reinterpret_cast<const uint2*>(xs + (8 * m + nl) * pitch + (kk - (s_lo << 4)) + 4 * t);
+      // unpack: P = (byte b of row r, byte b of row r + 1) -> nibbles 2b (low) and 2b + 1 (high) of both rows
+      uint32_t a[4][4];
+#pragma unroll
+      for (int rp = 0; rp < 2; ++rp) {
+        const uint32_t r0 = w[u][2 * rp], r1 = w[u][2 * rp + 1];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t p = __byte_perm(r0, r1, 0x4400 + 0x1111 * b);   // bytes [r0.b, r0.b, r1.b, r1.b]
+          const uint32_t lo = (p & 0x000F000Fu) | MAGIC;            // nibble 2b     of (row r, row r + 1)
+          const uint32_t hi = ((p >> 4) & 0x000F000Fu) | MAGIC;     // nibble 2b + 1 of (row r, row r + 1)
+          // nibble n holds column order[n], order = {0,2,4,6,1,3,5,7}
+          const int c_lo = (2 * b < 4) ? 2 * (2 * b) : 2 * (2 * b - 4) + 1;
+          const int c_hi = (2 * b + 1 < 4) ? 2 * (2 * b + 1) : 2 * (2 * b + 1 - 4) + 1;
+          // column c = 2j (+1): fragment j = c / 2, register (c & 1) + 2 * rp
+          a[c_lo >> 1][(c_lo & 1) + 2 * rp] = sub_mul2<BF16>(lo, zm[c_lo], sc2[c_lo]);
+          a[c_hi >> 1][(c_hi & 1) + 2 * rp] = sub_mul2<BF16>(hi, zm[c_hi], sc2[c_hi]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mma_w_x<BF16>(acc[j][m], a[j], xb[m].x, xb[m].y);
+    }
+  }
+
+  // fold the warps' K chunks (fixed order), then the cluster's K slices (fixed order)
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) red[(((warp * 4 + j) * MT + m) * 4 + i) * 32 + lane] = acc[j][m][i];
+  __syncthreads();
+  constexpr int PER_LANE = 4 * MT * 4;
+  for (int e = warp; e < PER_LANE; e += SK_WARPS) {
+    float v = red[e * 32 + lane];
+#pragma unroll
+    for (int ww = 1; ww < SK_WARPS; ++ww) v += red[(ww * PER_LANE + e) * 32 + lane];
+    part[e * 32 + lane] = v;
+  }
+  cluster.sync();   // every CTA's `part` is complete and visible cluster-wide
+  if (crank == 0) {
+    // element e = (j * MT + m) * 4 + i of lane (nl, t): y[8 m + 2 t + (i & 1)][8 wc + 2 j + (i >> 1)]
+    for (int m = warp; m < MT; m += SK_WARPS) {
+      float out[2][8];   // [row 2t + h][column of the word]
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = (j * MT + m) * 4 + i;
+          float v = part[e * 32 + lane];
+          for (int r = 1; r < csize; ++r) v += cluster.map_shared_rank(part, r)[e * 32 + lane];
+          out[i & 1][2 * j + (i >> 1)] = v;
+        }
+      if (col_on) {
+        float bv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          bv[c] = 0.f;
+          if (bias) bv[c] = BF16 ? __bfloat162float(__ushort_as_bfloat16(bias[8 * wc + c])) : __half2float(__ushort_as_half(bias[8 * wc + c]));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = 8 * m + 2 * t + h;
+          if (row < M) {
+            uint32_t o[4];
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2) {
+              const float v0 = out[h][2 * c2] + bv[2 * c2], v1 = out[h][2 * c2 + 1] + bv[2 * c2 + 1];
+              if (BF16) { __nv_bfloat162 v = __floats2bfloat162_rn(v0, v1); o[c2] = *reinterpret_cast<uint32_t*>(&v); }
+              else { __half2 v = __floats2half2_rn(v0, v1); o[c2] = *reinterpret_cast<uint32_t*>(&v); }
+            }
+            *reinterpret_cast<uint4*>(y + int64_t(row) * N + 8 * wc) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+  cluster.sync();   // the other CTAs' shared memory stays alive until rank 0 has read it
+}
+
+size_t skinny_smem(int mt, int steps_per_cta) {
+  return size_t(8 * mt) * (steps_per_cta * 16 + 16) * 2 + size_t(SK_WARPS + 1) * 4 * mt * 4 * 32 * sizeof(float);
+}
+
+template <bool BF16, int MT>
+int skinny_launch(dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                  const void* bias, void* y, int M, int N, int K, int group, int steps_per_cta, cudaStream_t st) {
+  auto kern = w4a16_skinny_kernel<BF16, MT>;
+  static size_t smem_set = 0;   // per instantiation; grows monotonically
+  if (smem > 48 * 1024 && smem > smem_set) {
+    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = 200 * 1024;
+  }
+  static const bool no_pdl = getenv("QDM_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(SK_WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)ks; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 1 : 2;
+  QDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const uint16_t*)x, (const uint32_t*)qweight, (const uint32_t*)qzeros,
+                                 (const uint16_t*)scales, (const uint16_t*)bias, (uint16_t*)y, M, N, K, group, steps_per_cta));
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
+template <bool BF16>
+int skinny_mt(int mt, dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+              const void* bias, void* y, int M, int N, int K, int group, int spc, cudaStream_t st) {
+  switch (mt) {
+    case 1: return skinny_launch<BF16, 1>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
+    case 2: return skinny_launch<BF16, 2>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
+    case 3: return skinny_launch<BF16, 3>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
+    default: return skinny_launch<BF16, 4>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
+  }
+}
+
+// K split across the cluster: enough CTAs for ~2 per SM, at least one k16 step per warp, shared memory within bounds
+void skinny_plan(int64_t M, int64_t N, int64_t K, int* ks_out, int* spc_out, size_t* smem_out) {
+  const int mt = int((M + 7) / 8);
+  const int64_t col_blocks = (N + 63) / 64, steps = K / 16;
+  int ks = 1;
+  while (ks < 8 && col_blocks * ks < 2 * QDM_NUM_SMS && steps / (2 * ks) >= SK_WARPS) ks *= 2;
+  int spc = int((steps + ks - 1) / ks);
+  while (ks < 8 && skinny_smem(mt, spc) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
+  *ks_out = ks;
+  *spc_out = spc;
+  *smem_out = skinny_smem(mt, spc);
+}
+
+}  // namespace
+
+bool qdm_gemm_w4a16_skinny_fits(int64_t M, int64_t N, int64_t K) {
+  if (M > 8 * SK_MAX_MT || K % 16 || N % 8) return false;
+  int ks, spc;
+  size_t smem;
+  skinny_plan(M, N, K, &ks, &spc, &smem);
+  return smem <= 160 * 1024;
+}
+
+// called by qdm_gemm_w4a16 for M <= 32 (arguments already validated there)
+int qdm_gemm_w4a16_skinny(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* bias,
+                          void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int group, cudaStream_t st) {
+  int ks, spc;
+  size_t smem;
+  skinny_plan(M, N, K, &ks, &spc, &smem);
+  const int mt = int((M + 7) / 8);
+  dim3 grid((unsigned)((N + 63) / 64), (unsigned)ks);
+  return is_bf16 ? skinny_mt<true>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, st)
+                 : skinny_mt<false>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, st);
+}

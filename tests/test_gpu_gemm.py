@@ -44,7 +44,11 @@ def test_gemm_f16(qdm, dt, M, N, K):
                                           (1024, 2432, 2432, 128), (77, 1280, 768, 128), (4096, 2560, 320, 64),
                                           (1, 1024, 256, 128), (513, 72, 192, 64), (2048, 64, 2432, 128),
                                           (16, 1280, 1280, 128), (64, 320, 1280, 128), (33, 72, 192, 64), (2, 14592, 2432, 128), (48, 640, 320, 64),
-                                          (60000, 320, 320, 64), (30001, 2560, 320, 64), (40960, 416, 384, 128), (57344, 160, 64, 64)])
+                                          (60000, 320, 320, 64), (30001, 2560, 320, 64), (40960, 416, 384, 128), (57344, 160, 64, 64),
+                                          # M <= 32: the sector-wide cluster-split-K kernel (qdm_gemm_skinny.cu)
+                                          (8, 1280, 2816, 128), (1, 2432, 256, 128), (5, 72, 192, 64), (32, 640, 1280, 128),
+                                          (17, 320, 320, 64), (1, 14592, 2432, 128), (9, 8, 64, 64), (24, 1288, 1280, 128),
+                                          (3, 2432, 9728, 128), (16, 320, 1280, 256)])
 def test_gemm_w4a16(qdm, dt, M, N, K, group):
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(DT[dt])
@@ -225,3 +229,29 @@ def test_conv3x3_modules_and_bad_inputs(qdm):
                             torch.zeros(8, 900, dtype=torch.float16, device=DEV))     # C % 64 != 0
     with pytest.raises(ValueError):
         qdm.ops.conv3x3_f16(x.to(DEV), torch.zeros(8, 64, dtype=torch.float16, device=DEV))
+
+
+def test_gemm_w4a16_skinny_vs_other_kernels(qdm):
+    """M <= 32 runs the cluster-split-K mma.sync kernel: deterministic from call to call, and equal (up to accumulation
+    order) to the previous small-M kernel and to the tcgen05 kernel on the same packed weights."""
+    import os
+    g = torch.Generator().manual_seed(21)
+    for M, N, K, group in [(16, 1280, 1280, 128), (1, 4864, 2432, 128), (8, 1280, 320, 64), (31, 640, 1280, 128)]:
+        x = torch.randn(M, K, generator=g).half().to(DEV)
+        w = (torch.randn(N, K, generator=g) * 0.05).half().to(DEV)
+        b = torch.randn(N, generator=g).half().to(DEV)
+        qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(w, group, want_dq=True)
+        n0 = qdm.ops.launch_count(reset=True)
+        y1 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+        y2 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+        assert qdm.ops.launch_count() == 2 and torch.equal(y1, y2)
+        assert max_rel_err(y1, ref_linear(x.cpu(), dq.cpu(), b.cpu())) <= TOL
+        try:
+            os.environ["QDM_W4_NO_SKINNY"] = "1"
+            y_old = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+            os.environ["QDM_W4_NO_SMALLM"] = "1"
+            y_tc = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+        finally:
+            os.environ.pop("QDM_W4_NO_SKINNY", None)
+            os.environ.pop("QDM_W4_NO_SMALLM", None)
+        assert max_rel_err(y1, y_old.cpu()) <= 2e-3 and max_rel_err(y1, y_tc.cpu()) <= 2e-3
