@@ -26,6 +26,11 @@ for f, w in [
     ("kernels_ab_r01.json", "`bench.py --mode kernels`: GB/s of every (a)/(b) kernel vs the measured HBM peak"),
     ("gemm_sweep_r01.json", "`bench.py --sweep`: BASELINE config 5 (M 4096-65536, K,N 1536-6144): W4A16 vs our f16 tcgen05 vs cuBLAS vs W8A8"),
     ("gemm_layers_r01.json", "`bench.py --layers`: every distinct Linear shape of the SD1.5 UNet step"),
+    ("gemm_layers_sdxl_r01.json, gemm_layers_sd35_r01.json", "`bench.py --layers --model sdxl|sd35`: every distinct Linear shape of the SDXL UNet step (BASELINE config 3) and of the SD3.5-L MMDiT step (config 4), with calls per step and the whole-step totals"),
+    ("conv3x3_r01.json", "`bench.py --mode conv`: the 3x3 convolutions of the SD1.5 UNet as implicit GEMMs (direct 4-D TMA form, padded-grid form, W4A16) vs cuDNN NCHW / channels-last"),
+    ("conv3x3_w4a16_640x640x32_ncu_r01.txt", "ncu summary of the W4A16 CTA-pair kernel running a 3x3 convolution (640 -> 640 channels, 32 x 32, batch 16) through the 4-D tensor map"),
+    ("colstats_ncu_r01.txt", "ncu summary of the one-pass hook statistic kernel (`col_stats_stage1`)"),
+    ("denoise_conv_ab_r01.txt", "denoise loop it/s with packed 3x3 convolutions vs cuDNN (`QDM_CONV_GEMM` A/B)"),
     ("timeline_roles_1232x1280x768_r01.txt", "role timeline (TMA / raw producer / 4 dequant groups / MMA / epilogue, clock64) of one CTA pair, `QDM_TRACE` build + `tools/trace_view.py`"),
     ("timeline_inputs_320.txt, timeline_inputs_1280.txt", "per k-block: A-load issue, dequant arrival, MMA start (`tools/trace_inputs.py`) — the evidence that the MMA waits for the A tile, not for the dequant"),
 ]:
@@ -51,6 +56,28 @@ A("| M | N | K | W4A16 us | TFLOP/s | per-shape roofline TFLOP/s | fraction | ou
 for r in ly["rows"]:
     w = r["w4a16"]
     A(f"| {r['M']} | {r['N']} | {r['K']} | {w['ms'] * 1e3:.1f} | {w['tflops']:.1f} | {w['roof_tflops']:.0f} | {w['frac']:.2f} | {r['f16_tcgen05']['tflops']:.1f} | {r['cublas_f16']['tflops']:.1f} | {r.get('w8a8_gemm', {}).get('tflops', 0):.1f} |")
+for mdl, title in (("sdxl", "SDXL UNet step (config 3: 1024^2, batch 4 + CFG)"), ("sd35", "SD3.5-L MMDiT step (config 4: 1024^2, batch 1)")):
+    pth = os.path.join(R, f"gemm_layers_{mdl}_r01.json")
+    if not os.path.exists(pth):
+        continue
+    d = json.load(open(pth))
+    A(f"\n## {title}: every distinct Linear shape (GPU-side, cold L2 per launch)\n")
+    A("| M | N | K | calls / step | W4A16 us | TFLOP/s | fraction of per-shape roofline | our f16 | cuBLAS f16 | W8A8 |\n|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for r in d["rows"]:
+        w = r["w4a16"]
+        A(f"| {r['M']} | {r['N']} | {r['K']} | {r['calls_per_step']} | {w['ms'] * 1e3:.1f} | {w['tflops']:.1f} | {w['frac']:.2f} | {r['f16_tcgen05']['tflops']:.1f} | {r['cublas_f16']['tflops']:.1f} | {r.get('w8a8_gemm', {}).get('tflops', 0):.1f} |")
+    sm = d["summary"]
+    A(f"\nWhole Linear pass ({sm['tflop_per_step']:.1f} TFLOP): W4A16 {sm['w4a16']['ms_per_step']:.1f} ms = {sm['w4a16']['tflops']:.0f} TFLOP/s "
+      f"({sm['w4a16_per_shape_roofline']['frac']:.2f} of the per-shape roofline); W8A8 GEMMs {sm['w8a8']['tflops']:.0f} TFLOP/s "
+      f"({sm['w8a8_with_actquant']['tflops']:.0f} with the per-token quantiser); our f16 {sm['f16_tcgen05']['tflops']:.0f}; cuBLAS f16 {sm['cublas_f16']['tflops']:.0f}.")
+cv = os.path.join(R, "conv3x3_r01.json")
+if os.path.exists(cv):
+    d = json.load(open(cv))
+    A("\n## 3x3 convolutions of the SD1.5 UNet as implicit GEMMs (batch 16, fp16, ms per call, L2 flushed)\n")
+    A("| C_in | C_out | H = W | cuDNN NCHW | cuDNN channels-last | ours f16 direct | ours f16 padded grid | ours f16 from NCHW | ours W4A16 | ours f16 TFLOP/s |\n|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for r in d["rows"]:
+        A(f"| {r['C']} | {r['N']} | {r['H']} | {r['cudnn_nchw_ms']:.3f} | {r['cudnn_nhwc_ms']:.3f} | {r['ours_f16_ms']:.3f} | {r['ours_f16_padded_grid_ms']:.3f} | {r['ours_f16_from_nchw_ms']:.3f} | {r['ours_w4a16_ms']:.3f} | {r['ours_f16_tflops']:.0f} |")
+    A("\n(measured with the direct form forced for every size; `ops.conv3x3_*` now picks the padded grid below 32-pixel rows.)")
 A("")
 A(open(os.path.join(R, "_notes.md")).read())
 open(os.path.join(R, "README.md"), "w").write("\n".join(out))
