@@ -58,7 +58,7 @@ template <bool BF16, int MT>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__ qweight, const uint32_t* __restrict__ qzeros,
                     const uint16_t* __restrict__ scales, const uint16_t* __restrict__ bias, uint16_t* __restrict__ y,
-                    int M, int N, int K, int group, int steps_per_cta) {
+                    int M, int N, int K, int group, int steps_per_cta, int WN) {
   constexpr uint32_t MAGIC = BF16 ? 0x43004300u : 0x64006400u;   // 128.0 | 1024.0 in both halves
   extern __shared__ uint4 sk_smem_raw[];
   // [8 MT rows][k slice + 16] x slice, then the per-warp partial sums [warps][4 j][MT][4][32], then the CTA's sum
@@ -66,7 +66,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   const int k_slice = steps_per_cta * 16;
   const int pitch = k_slice + 16;
   float* red = reinterpret_cast<float*>(xs + 8 * MT * pitch);
-  float* part = red + SK_WARPS * 4 * MT * 4 * 32;
+  float* part = red + SK_WARPS * 4 * MT * 4 * 32;   // [WN column groups][4 j][MT][4][32]
 
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
@@ -76,14 +76,17 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nl = lane >> 2, t = lane & 3;
   const int words_per_row = N >> 3;
-  const int wc = int(blockIdx.x) * 8 + nl;              // this lane's packed word column (8 output columns)
+  // the CTA's 8 warps are WN column groups (64 columns each: WN x 32 contiguous bytes of every k row, so that DRAM and L2
+  // lines are used whole) times WK = 8 / WN slices of K
+  const int wn = warp % WN, wk = warp / WN, WK = SK_WARPS / WN;
+  const int wc = (int(blockIdx.x) * WN + wn) * 8 + nl;  // this lane's packed word column (8 output columns)
   const bool col_on = wc < words_per_row;
   const int steps_total = K >> 4;
   const int s_lo = crank * steps_per_cta;               // this CTA's k16 steps
   const int s_hi = min(steps_total, s_lo + steps_per_cta);
   const int n_steps = max(0, s_hi - s_lo);
-  const int spw = (n_steps + SK_WARPS - 1) / SK_WARPS;  // contiguous chunk per warp: the group changes rarely
-  const int w_lo = s_lo + warp * spw, w_hi = min(s_hi, w_lo + spw);
+  const int spw = (n_steps + WK - 1) / WK;              // contiguous chunk per warp: the group changes rarely
+  const int w_lo = s_lo + wk * spw, w_hi = min(s_hi, w_lo + spw);
 
   uint32_t w[SK_U][4];
   auto load_words = [&](int s0) {
@@ -195,60 +198,43 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
       for (int i = 0; i < 4; ++i) red[(((warp * 4 + j) * MT + m) * 4 + i) * 32 + lane] = acc[j][m][i];
   __syncthreads();
   constexpr int PER_LANE = 4 * MT * 4;
-  for (int e = warp; e < PER_LANE; e += SK_WARPS) {
-    float v = red[e * 32 + lane];
-#pragma unroll
-    for (int ww = 1; ww < SK_WARPS; ++ww) v += red[(ww * PER_LANE + e) * 32 + lane];
-    part[e * 32 + lane] = v;
+  for (int it = warp; it < WN * PER_LANE; it += SK_WARPS) {   // item = (column group, element): sum its WK slices
+    const int cg_ = it / PER_LANE, e = it - cg_ * PER_LANE;
+    float v = red[(cg_ * PER_LANE + e) * 32 + lane];          // warp index = k * WN + cg_
+    for (int k = 1; k < WK; ++k) v += red[((k * WN + cg_) * PER_LANE + e) * 32 + lane];
+    part[it * 32 + lane] = v;
   }
   cluster.sync();   // every CTA's `part` is complete and visible cluster-wide
-  if (crank == 0) {
-    // element e = (j * MT + m) * 4 + i of lane (nl, t): y[8 m + 2 t + (i & 1)][8 wc + 2 j + (i >> 1)]
-    for (int m = warp; m < MT; m += SK_WARPS) {
-      float out[2][8];   // [row 2t + h][column of the word]
+  // Reduce-scatter over the cluster: element e is folded by CTA e % csize (and one of its warps), which reads the csize
+  // partials through distributed shared memory -- all loads issued before the first add (a dependent chain of remote
+  // loads costs ~0.3 us each) -- adds them in rank order, adds the bias and stores.  Element e = (j * MT + m) * 4 + i of
+  // lane (nl, t) is y[8 m + 2 t + (i & 1)][8 wc + 2 j + (i >> 1)].
+  for (int it = crank + csize * warp; it < WN * PER_LANE; it += csize * SK_WARPS) {
+    float vals[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+    for (int r = 0; r < 8; ++r) vals[r] = (r < csize) ? cluster.map_shared_rank(part, r)[it * 32 + lane] : 0.f;
+    float v = vals[0];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = (j * MT + m) * 4 + i;
-          float v = part[e * 32 + lane];
-          for (int r = 1; r < csize; ++r) v += cluster.map_shared_rank(part, r)[e * 32 + lane];
-          out[i & 1][2 * j + (i >> 1)] = v;
-        }
-      if (col_on) {
-        float bv[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          bv[c] = 0.f;
-          if (bias) bv[c] = BF16 ? __bfloat162float(__ushort_as_bfloat16(bias[8 * wc + c])) : __half2float(__ushort_as_half(bias[8 * wc + c]));
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int row = 8 * m + 2 * t + h;
-          if (row < M) {
-            uint32_t o[4];
-#pragma unroll
-            for (int c2 = 0; c2 < 4; ++c2) {
-              const float v0 = out[h][2 * c2] + bv[2 * c2], v1 = out[h][2 * c2 + 1] + bv[2 * c2 + 1];
-              if (BF16) { __nv_bfloat162 v = __floats2bfloat162_rn(v0, v1); o[c2] = *reinterpret_cast<uint32_t*>(&v); }
-              else { __half2 v = __floats2half2_rn(v0, v1); o[c2] = *reinterpret_cast<uint32_t*>(&v); }
-            }
-            *reinterpret_cast<uint4*>(y + int64_t(row) * N + 8 * wc) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
+    for (int r = 1; r < 8; ++r) v += vals[r];
+    const int cg_ = it / PER_LANE, e = it - cg_ * PER_LANE;
+    const int i = e & 3, jm = e >> 2, m = jm % MT, j = jm / MT;
+    const int wco = (int(blockIdx.x) * WN + cg_) * 8 + nl;   // the word column this ITEM belongs to (not this warp's)
+    const int row = 8 * m + 2 * t + (i & 1), col = 8 * wco + 2 * j + (i >> 1);
+    if (wco < words_per_row && row < M) {
+      if (bias) v += BF16 ? __bfloat162float(__ushort_as_bfloat16(bias[col])) : __half2float(__ushort_as_half(bias[col]));
+      y[int64_t(row) * N + col] = BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
     }
   }
-  cluster.sync();   // the other CTAs' shared memory stays alive until rank 0 has read it
+  cluster.sync();   // every CTA's shared memory stays alive until its peers have read it
 }
 
-size_t skinny_smem(int mt, int steps_per_cta) {
-  return size_t(8 * mt) * (steps_per_cta * 16 + 16) * 2 + size_t(SK_WARPS + 1) * 4 * mt * 4 * 32 * sizeof(float);
+size_t skinny_smem(int mt, int steps_per_cta, int wn) {
+  return size_t(8 * mt) * (steps_per_cta * 16 + 16) * 2 + size_t(SK_WARPS + wn) * 4 * mt * 4 * 32 * sizeof(float);
 }
 
 template <bool BF16, int MT>
 int skinny_launch(dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
-                  const void* bias, void* y, int M, int N, int K, int group, int steps_per_cta, cudaStream_t st) {
+                  const void* bias, void* y, int M, int N, int K, int group, int steps_per_cta, int wn, cudaStream_t st) {
   auto kern = w4a16_skinny_kernel<BF16, MT>;
   static size_t smem_set = 0;   // per instantiation; grows monotonically
   if (smem > 48 * 1024 && smem > smem_set) {
@@ -269,53 +255,57 @@ int skinny_launch(dim3 grid, int ks, size_t smem, const void* x, const int32_t* 
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 1 : 2;
   QDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const uint16_t*)x, (const uint32_t*)qweight, (const uint32_t*)qzeros,
-                                 (const uint16_t*)scales, (const uint16_t*)bias, (uint16_t*)y, M, N, K, group, steps_per_cta));
+                                 (const uint16_t*)scales, (const uint16_t*)bias, (uint16_t*)y, M, N, K, group, steps_per_cta, wn));
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }
 
 template <bool BF16>
 int skinny_mt(int mt, dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
-              const void* bias, void* y, int M, int N, int K, int group, int spc, cudaStream_t st) {
+              const void* bias, void* y, int M, int N, int K, int group, int spc, int wn, cudaStream_t st) {
   switch (mt) {
-    case 1: return skinny_launch<BF16, 1>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
-    case 2: return skinny_launch<BF16, 2>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
-    case 3: return skinny_launch<BF16, 3>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
-    default: return skinny_launch<BF16, 4>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, st);
+    case 1: return skinny_launch<BF16, 1>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 2: return skinny_launch<BF16, 2>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 3: return skinny_launch<BF16, 3>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    default: return skinny_launch<BF16, 4>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
   }
 }
 
-// K split across the cluster: enough CTAs for ~2 per SM, at least one k16 step per warp, shared memory within bounds
-void skinny_plan(int64_t M, int64_t N, int64_t K, int* ks_out, int* spc_out, size_t* smem_out) {
+// Work split: WN = 4 column groups per CTA (128 contiguous bytes of every k row) when N is wide enough, K over the
+// remaining warps and over the cluster: enough CTAs for ~2 per SM, at least two k16 steps per warp, shared memory in bounds
+void skinny_plan(int64_t M, int64_t N, int64_t K, int* ks_out, int* spc_out, int* wn_out, size_t* smem_out) {
   const int mt = int((M + 7) / 8);
-  const int64_t col_blocks = (N + 63) / 64, steps = K / 16;
+  const int wn = N >= 256 ? 4 : (N >= 128 ? 2 : 1);
+  const int wk = SK_WARPS / wn;
+  const int64_t col_blocks = (N + 64 * wn - 1) / (64 * wn), steps = K / 16;
   int ks = 1;
-  while (ks < 8 && col_blocks * ks < 2 * QDM_NUM_SMS && steps / (2 * ks) >= SK_WARPS) ks *= 2;
+  while (ks < 8 && col_blocks * ks < 2 * QDM_NUM_SMS && steps / (2 * ks) >= 2 * wk) ks *= 2;
   int spc = int((steps + ks - 1) / ks);
-  while (ks < 8 && skinny_smem(mt, spc) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
+  while (ks < 8 && skinny_smem(mt, spc, wn) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
   *ks_out = ks;
   *spc_out = spc;
-  *smem_out = skinny_smem(mt, spc);
+  *wn_out = wn;
+  *smem_out = skinny_smem(mt, spc, wn);
 }
 
 }  // namespace
 
 bool qdm_gemm_w4a16_skinny_fits(int64_t M, int64_t N, int64_t K) {
   if (M > 8 * SK_MAX_MT || K % 16 || N % 8) return false;
-  int ks, spc;
+  int ks, spc, wn;
   size_t smem;
-  skinny_plan(M, N, K, &ks, &spc, &smem);
+  skinny_plan(M, N, K, &ks, &spc, &wn, &smem);
   return smem <= 160 * 1024;
 }
 
 // called by qdm_gemm_w4a16 for M <= 32 (arguments already validated there)
 int qdm_gemm_w4a16_skinny(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* bias,
                           void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int group, cudaStream_t st) {
-  int ks, spc;
+  int ks, spc, wn;
   size_t smem;
-  skinny_plan(M, N, K, &ks, &spc, &smem);
+  skinny_plan(M, N, K, &ks, &spc, &wn, &smem);
   const int mt = int((M + 7) / 8);
-  dim3 grid((unsigned)((N + 63) / 64), (unsigned)ks);
-  return is_bf16 ? skinny_mt<true>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, st)
-                 : skinny_mt<false>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, st);
+  dim3 grid((unsigned)((N + 64 * wn - 1) / (64 * wn)), (unsigned)ks);
+  return is_bf16 ? skinny_mt<true>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st)
+                 : skinny_mt<false>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st);
 }

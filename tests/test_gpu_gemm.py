@@ -45,10 +45,8 @@ def test_gemm_f16(qdm, dt, M, N, K):
                                           (1, 1024, 256, 128), (513, 72, 192, 64), (2048, 64, 2432, 128),
                                           (16, 1280, 1280, 128), (64, 320, 1280, 128), (33, 72, 192, 64), (2, 14592, 2432, 128), (48, 640, 320, 64),
                                           (60000, 320, 320, 64), (30001, 2560, 320, 64), (40960, 416, 384, 128), (57344, 160, 64, 64),
-                                          # M <= 32: the sector-wide cluster-split-K kernel (qdm_gemm_skinny.cu)
-                                          (8, 1280, 2816, 128), (1, 2432, 256, 128), (5, 72, 192, 64), (32, 640, 1280, 128),
-                                          (17, 320, 320, 64), (1, 14592, 2432, 128), (9, 8, 64, 64), (24, 1288, 1280, 128),
-                                          (3, 2432, 9728, 128), (16, 320, 1280, 256)])
+                                          # M <= 32 with more than 2 M weights: the sector-wide cluster-split-K kernel
+                                          (8, 1280, 2816, 128), (1, 14592, 2432, 128), (3, 2432, 9728, 128)])
 def test_gemm_w4a16(qdm, dt, M, N, K, group):
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(DT[dt])
@@ -231,27 +229,54 @@ def test_conv3x3_modules_and_bad_inputs(qdm):
         qdm.ops.conv3x3_f16(x.to(DEV), torch.zeros(8, 64, dtype=torch.float16, device=DEV))
 
 
+SKINNY_SHAPES = [(8, 1280, 2816, 128), (1, 2432, 256, 128), (5, 72, 192, 64), (32, 640, 1280, 128), (17, 320, 320, 64),
+                 (9, 8, 64, 64), (24, 1288, 1280, 128), (16, 320, 1280, 256), (16, 1280, 1280, 128), (1, 4864, 2432, 128)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("M,N,K,group", SKINNY_SHAPES)
+def test_gemm_w4a16_skinny_forced(qdm, dt, M, N, K, group):
+    """The cluster-split-K mma.sync kernel (qdm_gemm_skinny.cu) on every shape class it accepts -- ragged N (not a
+    multiple of 64 / 256), one k16 step per warp, 1..4 m-tiles, group 64 / 128 / 256 -- forced with QDM_W4_NO_SMALLM=1
+    (the dispatcher otherwise keeps the one-word-column kernel below ~2 M weights).  Deterministic call to call."""
+    import os
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DT[dt])
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DT[dt])
+    b = torch.randn(N, generator=g).to(DT[dt])
+    oq, oz, os_, dq = O.awq_from_linear(w, group, 4)
+    qweight, qzeros, scales = torch.from_numpy(oq).to(DEV), torch.from_numpy(oz).to(DEV), os_.to(DEV)
+    try:
+        os.environ["QDM_W4_NO_SMALLM"] = "1"
+        y1 = qdm.ops.gemm_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV))
+        y2 = qdm.ops.gemm_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV))
+    finally:
+        os.environ.pop("QDM_W4_NO_SMALLM", None)
+    assert y1.shape == (M, N) and y1.dtype == DT[dt] and torch.equal(y1, y2)
+    assert max_rel_err(y1, ref_linear(x, dq, b)) <= TOL
+    y_kn = qdm.ops.gemm_f16_kn(x.to(DEV), qdm.ops.dequant_awq(qweight, qzeros, scales, group), b.to(DEV))
+    assert max_rel_err(y1, y_kn.cpu()) <= (2e-3 if dt == "f16" else 8e-3)
+
+
 def test_gemm_w4a16_skinny_vs_other_kernels(qdm):
-    """M <= 32 runs the cluster-split-K mma.sync kernel: deterministic from call to call, and equal (up to accumulation
-    order) to the previous small-M kernel and to the tcgen05 kernel on the same packed weights."""
+    """The three W4A16 kernels an M <= 32 problem can take agree up to accumulation order on the same packed weights:
+    skinny (forced), the one-word-column small-M kernel (where it fits) and the tcgen05 kernel."""
     import os
     g = torch.Generator().manual_seed(21)
-    for M, N, K, group in [(16, 1280, 1280, 128), (1, 4864, 2432, 128), (8, 1280, 320, 64), (31, 640, 1280, 128)]:
+    for M, N, K, group in [(16, 1280, 1280, 128), (2, 14592, 2432, 128)]:
         x = torch.randn(M, K, generator=g).half().to(DEV)
         w = (torch.randn(N, K, generator=g) * 0.05).half().to(DEV)
         b = torch.randn(N, generator=g).half().to(DEV)
         qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(w, group, want_dq=True)
-        n0 = qdm.ops.launch_count(reset=True)
-        y1 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
-        y2 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
-        assert qdm.ops.launch_count() == 2 and torch.equal(y1, y2)
-        assert max_rel_err(y1, ref_linear(x.cpu(), dq.cpu(), b.cpu())) <= TOL
         try:
-            os.environ["QDM_W4_NO_SKINNY"] = "1"
-            y_old = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
             os.environ["QDM_W4_NO_SMALLM"] = "1"
-            y_tc = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)
+            y_sk = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)          # skinny
+            os.environ["QDM_W4_NO_SKINNY"] = "1"
+            y_tc = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)          # tcgen05
+            os.environ.pop("QDM_W4_NO_SMALLM", None)
+            y_sm = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)          # small-M where it fits, else tcgen05
         finally:
             os.environ.pop("QDM_W4_NO_SKINNY", None)
             os.environ.pop("QDM_W4_NO_SMALLM", None)
-        assert max_rel_err(y1, y_old.cpu()) <= 2e-3 and max_rel_err(y1, y_tc.cpu()) <= 2e-3
+        assert max_rel_err(y_sk, ref_linear(x.cpu(), dq.cpu(), b.cpu())) <= TOL
+        assert max_rel_err(y_sk, y_tc.cpu()) <= 2e-3 and max_rel_err(y_sk, y_sm.cpu()) <= 2e-3
