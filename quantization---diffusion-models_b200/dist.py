@@ -97,3 +97,44 @@ def sharded_search(quantizer, shard):
     # deterministic application order = model order
     order = list(quantizer.awq_model.get_search_blocks())
     return {k: merged[k] for k in order if k in merged}
+
+
+def allreduce_hook_stats(hook_dict):
+    """Data-parallel SmoothQuant calibration: every rank runs the FP model on its own share of the
+    calibration prompts with `calib_data.Fused_Mean_Max_Activation_Hook`s attached; this sums the hooks' fp64
+    accumulators (sum over calls of the per-call column max, |x| sum) and counters over the ranks and maxes the running
+    max, in place, so that every rank ends with the statistic of the whole calibration set.  The fp64 sum of fp16 maxima
+    is exact, hence independent of the reduction order NCCL picks: the smoothing scales -- and the quantised codes
+    -- are bit-identical for every world size.  `hook_dict`: {block: {linear: hook}} or {linear: hook}; one
+    all_reduce per tensor kind (flattened), not per hook."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return hook_dict
+    hooks = []
+    for v in hook_dict.values():
+        hooks += list(v.values()) if isinstance(v, dict) else [v]
+    hooks = [h for h in hooks if getattr(h, "acc_maxsum", None) is not None]
+    if not hooks:
+        return hook_dict
+    dev = hooks[0].acc_maxsum.device
+    comm_dev = dev if dist.get_backend() == "nccl" else torch.device("cpu")
+    sums = [h.acc_maxsum for h in hooks] + [h.acc_abssum for h in hooks if h.acc_abssum is not None]
+    flat = torch.cat([t.reshape(-1) for t in sums]).to(comm_dev)
+    counts = torch.tensor([[h.step, h.rows] for h in hooks], dtype=torch.int64, device=comm_dev).reshape(-1)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    off = 0
+    for t in sums:
+        t.copy_(flat[off:off + t.numel()].reshape(t.shape).to(t.device))
+        off += t.numel()
+    counts = counts.reshape(-1, 2).tolist()
+    for h, (step, rows) in zip(hooks, counts):
+        h.step, h.rows = int(step), int(rows)
+    # running max: max is exact in any order; reduce in fp32 (fp16 / bf16 -> fp32 -> back is exact)
+    rmax = torch.cat([h.running_max.reshape(-1).float() for h in hooks]).to(comm_dev)
+    dist.all_reduce(rmax, op=dist.ReduceOp.MAX)
+    off = 0
+    for h in hooks:
+        n = h.running_max.numel()
+        h.running_max.copy_(rmax[off:off + n].to(h.running_max.device, h.running_max.dtype))
+        off += n
+    return hook_dict

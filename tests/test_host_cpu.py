@@ -124,3 +124,69 @@ def test_sharded_awq_search_world2_equals_world1():
         assert state.keys() == want.keys()
         for k, v in want.items():
             assert (torch.from_numpy(state[k]) == v).all(), f"rank {rank}: {k} differs from the single-rank result"
+
+
+def _hook_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cd = importlib.import_module(PKG + ".calib_data")
+    d = importlib.import_module(PKG + ".dist")
+    g = torch.Generator().manual_seed(7)
+    calls = [torch.randn(12, 3, 40, generator=g).half() * (1 + c) for c in range(6)]
+    with patched_ops():
+        hooks = {"blk": {"to_q": cd.Fused_Mean_Max_Activation_Hook(want_abssum=True), "ff": cd.Fused_Mean_Max_Activation_Hook()}}
+        for c in range(rank, 6, world):          # this rank's share of the calibration calls
+            hooks["blk"]["to_q"](None, (calls[c],), None)
+            hooks["blk"]["ff"](None, (calls[c][..., :24].contiguous(),), None)
+        d.allreduce_hook_stats(hooks)
+    h = hooks["blk"]["to_q"]
+    q.put((rank, h.step, h.rows, h.max_scales.mean_over_calls().numpy(), h.x_mean().numpy(), h.running_max.numpy(),
+           hooks["blk"]["ff"].max_scales.mean_over_calls().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_hook_stats_allreduce_world2_is_exact():
+    """SURVEY 8(e), SmoothQuant statistics under data-parallel calibration: after one all_reduce of the fp64 accumulators
+    both ranks hold exactly the single-process statistic (the sum of fp16 maxima is exact in fp64, so order-free)."""
+    cd = importlib.import_module(PKG + ".calib_data")
+    g = torch.Generator().manual_seed(7)
+    calls = [torch.randn(12, 3, 40, generator=g).half() * (1 + c) for c in range(6)]
+    with patched_ops():
+        ref, ref_ff = cd.Fused_Mean_Max_Activation_Hook(want_abssum=True), cd.Fused_Mean_Max_Activation_Hook()
+        for x in calls:
+            ref(None, (x,), None)
+            ref_ff(None, (x[..., :24].contiguous(),), None)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_hook_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, step, rows, mean_max, x_mean, rmax, ff_mean in res:
+        assert step == 6 and rows == 6 * 36
+        assert (torch.from_numpy(mean_max) == ref.max_scales.mean_over_calls()).all()
+        assert (torch.from_numpy(rmax) == ref.running_max).all()
+        assert (torch.from_numpy(ff_mean) == ref_ff.max_scales.mean_over_calls()).all()
+        # |x| sums: per-call fp32 sums folded in fp64 -- the same addends on any rank split, added in a different
+        # order in fp64: equal to the last bit after rounding to fp16
+        assert (torch.from_numpy(x_mean) == ref.x_mean()).all()
+
+
+def test_conv_helpers():
+    L = importlib.import_module(PKG + ".linear")
+    C = torch.nn.Conv2d
+    assert L.is_pointwise_conv(C(8, 16, 1)) and not L.is_pointwise_conv(C(8, 16, 1, stride=2)) and not L.is_pointwise_conv(C(8, 16, 3, padding=1))
+    assert L.is_conv3x3_gemm(C(64, 16, 3, padding=1)) and not L.is_conv3x3_gemm(C(64, 16, 3, padding=1, stride=2))
+    assert not L.is_conv3x3_gemm(C(4, 320, 3, padding=1)) and not L.is_conv3x3_gemm(C(64, 16, 3)) and not L.is_conv3x3_gemm(C(64, 4, 3, padding=1))
+    assert not L.is_conv3x3_gemm(C(64, 64, 3, padding=1, groups=2)) and not L.is_conv3x3_gemm(C(64, 64, 3, padding="same"))
+    assert [L.conv_group(9 * c, 128) for c in (64, 320, 640, 960, 1280, 1920, 2560)] == [64, 64, 128, 64, 128, 128, 128]
+    x = torch.randn(2, 8, 3, 5)
+    t = L.nchw_as_tokens(x)
+    assert t.shape == (30, 8) and torch.equal(L.tokens_as_nchw(t, 2, 3, 5), x)
+    xc = x.contiguous(memory_format=torch.channels_last)
+    assert L.nchw_as_tokens(xc).data_ptr() == xc.data_ptr()          # a view, no copy
+    assert L.tokens_as_nchw(t, 2, 3, 5).is_contiguous(memory_format=torch.channels_last)
