@@ -315,3 +315,32 @@ def test_quantize_gemm_swaps_pointwise_convs(qdm, tmp_path):
         model.save_quantized(d)
         again = M.StableDiffusion1_x.from_quantized(d, device=DEV)
         assert torch.equal(again.generate(["a", "b"], lat=lat, num_inference_steps=2), out)
+
+
+def test_wxax_conv_vs_reference_fixture(qdm):
+    """WxAxConv2d against the reference-generated fixture (reference run on CPU, tools/gen_golden.py conv): the
+    fake-quant weight bit-exact, and the forward through each GEMM path -- 1x1 on the token view, 3x3 as an implicit
+    GEMM (padded grid for these ragged sizes, direct 4-D TMA form for the 8 x 8 one) -- within the GEMM tolerance."""
+    fq = importlib.import_module(PKG + ".fake_quant")
+    g = Golden("wxax_conv.npz")
+    default = fq.WxAxConv2d.conv3x3_gemm
+    try:
+        fq.WxAxConv2d.conv3x3_gemm = True
+        for tag, dt, wq, bits, ksz in g.cases():
+            w, b, x = g.get(tag + "_w"), g.get(tag + "_b"), g.get(tag + "_x")
+            conv = torch.nn.Conv2d(w.shape[1], w.shape[0], int(ksz), padding=int(ksz) // 2, bias=True)
+            conv.weight.data, conv.bias.data = w.clone(), b.clone()
+            conv = conv.to(DEV)
+            m = fq.WxAxConv2d.from_float(conv, weight_quant=wq, act_quant="per_tensor", n_bits_W=int(bits))
+            assert_bit_equal(m.weight, g.get(tag + "_wq"), f"{tag} fake-quant conv weight")
+            qdm.ops.launch_count(reset=True)
+            y = m(x.to(DEV))
+            assert qdm.ops.launch_count() == 1, "the convolution must run on the GEMM kernel, not cuDNN"
+            ref = g.get(tag + "_y")
+            assert y.shape == ref.shape and y.dtype == ref.dtype
+            assert max_rel_err(y, ref) <= 1e-2
+            if int(ksz) == 3 and x.shape[-1] == 8:
+                y_d = qdm.ops.conv3x3_f16(x.to(DEV), qdm.ops.conv3x3_weight_taps(m.weight), m.bias, padded=False)
+                assert max_rel_err(y_d, ref) <= 1e-2
+    finally:
+        fq.WxAxConv2d.conv3x3_gemm = default

@@ -122,3 +122,16 @@ def test_wxax_linear_matches_reference():
         ref = g.get(tag + "_y")
         # F.linear accumulates in a backend-dependent order: tolerance, not bit equality
         assert ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item() <= 2e-3
+
+
+def test_wxax_conv_matches_reference():
+    """A8: WxAxConv2d.from_float + forward of the reference (fake_quant.py:263-398), 1x1 and 3x3 / pad 1, vs the oracle."""
+    g = Golden("wxax_conv.npz")
+    for tag, dt, wq, bits, ksz in g.cases():
+        w, b, x = g.get(tag + "_w"), g.get(tag + "_b"), g.get(tag + "_x")
+        wf = (O.rtn_rows(w, int(bits))[0] if wq == "per_channel" else O.rtn_tensor(w, int(bits))[0]).reshape(w.shape)
+        assert_bit_equal(wf, g.get(tag + "_wq"), f"{tag} fake-quant conv weight")
+        y = O.conv2d_fake(x, wf, b, 1, int(ksz) // 2)
+        ref = g.get(tag + "_y")
+        assert y.shape == ref.shape
+        assert ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item() <= 2e-3

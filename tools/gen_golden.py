@@ -272,9 +272,38 @@ def main():
             i += 1
     d["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(OUT, "wxax_linear.npz"), **d)
+    gen_wxax_conv(r)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def gen_wxax_conv(r):
+    """A8 WxAxConv2d.from_float + forward (fake_quant.py:263-398) for the geometries the B200 path runs as GEMMs:
+    1x1 (pointwise) and 3x3 / stride 1 / padding 1, per_tensor and per_channel weights, fp16, reference on CPU."""
+    fq = r.fake_quant
+    d, cases, i = {}, [], 0
+    for ksz, cin, cout, hw in ((1, 64, 72, 6), (3, 64, 64, 8), (3, 128, 72, 5)):
+        for wq, bits in (("per_tensor", 8), ("per_channel", 8)):
+            g = torch.Generator().manual_seed(1200 + i)
+            conv = torch.nn.Conv2d(cin, cout, ksz, padding=ksz // 2, bias=True)
+            conv.weight.data = (torch.randn(cout, cin, ksz, ksz, generator=g) * 0.05)
+            conv.bias.data = torch.randn(cout, generator=g)
+            conv.to(torch.float16)
+            x = torch.randn(2, cin, hw, hw + (1 if ksz == 3 and hw == 5 else 0), generator=g).to(torch.float16)
+            m = fq.WxAxConv2d.from_float(conv, weight_quant=wq, act_quant="per_tensor", n_bits_W=bits)
+            y = m(x)
+            tag = f"c{i}"
+            enc(d, tag + "_w", conv.weight.data), enc(d, tag + "_b", conv.bias.data), enc(d, tag + "_x", x)
+            enc(d, tag + "_wq", m.weight), enc(d, tag + "_y", y)
+            cases.append(f"{tag},f16,{wq},{bits},{ksz}")
+            i += 1
+    d["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(OUT, "wxax_conv.npz"), **d)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "conv":   # only the convolution fixture (added later; the others are unchanged)
+        torch.set_grad_enabled(False)
+        gen_wxax_conv(ref_shim.ref())
+    else:
+        main()
