@@ -82,38 +82,39 @@ def test_sq_fused_hook_plumbing():
             assert ((a.float() - b.float()).abs() <= b.float().abs() * 2 ** -9).all()
 
 
-def _calibrated(shard):
-    M, model = tiny_sd15()
+def _calibrated(shard, kind="sd15"):
+    M, model = tiny_model(kind)
     model.calib_steps = 2
     model.quantize(quant_config={"zero_point": True, "q_group_size": 64, "w_bit": 4, "version": "gemm"}, quantType="awq",
                    calibrate=True, shard=shard)
     return model
 
 
-def _shard_worker(rank, world, port, q):
+def _shard_worker(rank, world, port, q, kind):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     with patched_ops():
-        model = _calibrated((rank, world))
+        model = _calibrated((rank, world), kind)
     q.put((rank, {k: v.numpy() for k, v in packed_state(model).items()}, len(model.quantizer.search_log)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_sharded_awq_search_world2_equals_world1():
+@pytest.mark.parametrize("kind", ["sd15", "sd35"])
+def test_sharded_awq_search_world2_equals_world1(kind):
     """blocks are searched on the rank that owns them, ONE gather exchanges {scales, clip}, every rank
     applies the identical list -> the packed codes / zeros / scales are bit-identical for world 1 and world 2, on
     both ranks, and each rank searched only its own blocks."""
     with patched_ops():
-        single = _calibrated(None)
+        single = _calibrated(None, kind)
     want = packed_state(single)
     n_groups = len(single.quantizer.search_log)
-    assert n_groups == 3 * len(single.get_search_blocks())
+    assert n_groups >= 3 * len(single.get_search_blocks())
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31000 + os.getpid() % 2000
-    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 31000 + os.getpid() % 2000 + (7 if kind == "sd35" else 0)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q, kind)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda t: t[0])
