@@ -2186,7 +2186,7 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
   // M <= 32: weight-bandwidth / latency bound.  Measured (profiles/README.md): the one-word-column kernel of
   // qdm_gemm_smallm.cu is as fast or faster up to ~2 M weights (16 x 1280 x 320: 4.7 vs 8.1 us, 16 x 1280 x 1280: 9.5 vs
   // 9.8 us); above that its sector over-fetch dominates and the sector-wide cluster-split-K kernel of qdm_gemm_skinny.cu
-  // wins (1 x 2432 x 2432: 9.7 vs 21.6 us; 1 x 14592 x 2432: 23.4 vs 32.6 us on the tcgen05 kernel).
+  // wins (1 x 2432 x 2432: 10 vs 21.6 us; 1 x 14592 x 2432: 18.1 vs 32.6 us on the tcgen05 kernel).
   const bool small_w = N * K <= (int64_t(1) << 21) && qdm_gemm_w4a16_smallm_fits(M, N, K) && !getenv("QDM_W4_NO_SMALLM");
   if (!conv && !small_w && qdm_gemm_w4a16_skinny_fits(M, N, K) && g_force_ctas == 0 && !getenv("QDM_W4_NO_SKINNY"))
     return qdm_gemm_w4a16_skinny(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);

@@ -4,7 +4,7 @@
 // built around the weight stream:
 //   * a warp-step is a [16 k rows x 64 columns] block of packed words: lane (nl = lane / 4, t = lane % 4) loads the word
 //     of column group nl (8 adjacent words = one 32-byte sector per row) from rows kk + 4 t + {0, 1, 2, 3} -- every
-//     sector it touches is fully used, 4 x U loads in flight per lane;
+//     sector it touches is fully used; two register buffers keep 16-32 loads in flight per lane;
 //   * the weights are the A operand of mma.sync.m16n8k16 (W^T [16 columns x 16 k] times x^T [16 k x 8 rows]): which
 //     physical row / column plays which logical (n, k) of the fragment is free as long as A, B and the output agree, so
 //     the lane's four words ARE four A fragments (column pairs (2j, 2j+1) of its word, j = 0..3) without any shuffle:
@@ -88,8 +88,10 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   const int spw = (n_steps + WK - 1) / WK;              // contiguous chunk per warp: the group changes rarely
   const int w_lo = s_lo + wk * spw, w_hi = min(s_hi, w_lo + spw);
 
-  uint32_t w[SK_U][4];
-  auto load_words = [&](int s0) {
+  // two register buffers of SK_U warp-steps each: the next chunk's words are requested before the current chunk is
+  // unpacked, so a warp always has 16-32 loads in flight instead of alternating between waiting and computing
+  uint32_t wa[SK_U][4], wb[SK_U][4];
+  auto load_words = [&](uint32_t (&w)[SK_U][4], int s0) {
 #pragma unroll
     for (int u = 0; u < SK_U; ++u) {
       const bool on = col_on && (s0 + u) < w_hi;
@@ -103,7 +105,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   uint32_t zw_pre = 0u;
   uint4 sv_pre = make_uint4(0, 0, 0, 0);
   if (w_lo < w_hi) {
-    load_words(w_lo);
+    load_words(wa, w_lo);
     if (col_on) {
       zw_pre = __ldg(qzeros + int64_t(g_pre) * words_per_row + wc);
       sv_pre = __ldg(reinterpret_cast<const uint4*>(scales + int64_t(g_pre) * N + 8 * wc));
@@ -133,8 +135,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
 
   int g_cur = -1;
   uint32_t zm[8], sc2[8];   // per column of this lane's word: (magic + z) and the scale, each duplicated into both halves
-  for (int s0 = w_lo; s0 < w_hi; s0 += SK_U) {
-    if (s0 != w_lo) load_words(s0);
+  auto do_chunk = [&](const uint32_t (&w)[SK_U][4], int s0) {
 #pragma unroll
     for (int u = 0; u < SK_U; ++u) {
       const int st = s0 + u;
@@ -187,6 +188,12 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
 #pragma unroll
         for (int m = 0; m < MT; ++m) mma_w_x<BF16>(acc[j][m], a[j], xb[m].x, xb[m].y);
     }
+  };
+  for (int s0 = w_lo; s0 < w_hi; s0 += 2 * SK_U) {        // wa holds chunk s0
+    if (s0 + SK_U < w_hi) load_words(wb, s0 + SK_U);
+    do_chunk(wa, s0);
+    if (s0 + 2 * SK_U < w_hi) load_words(wa, s0 + 2 * SK_U);
+    if (s0 + SK_U < w_hi) do_chunk(wb, s0 + SK_U);
   }
 
   // fold the warps' K chunks (fixed order), then the cluster's K slices (fixed order)
@@ -279,7 +286,10 @@ void skinny_plan(int64_t M, int64_t N, int64_t K, int* ks_out, int* spc_out, int
   const int wk = SK_WARPS / wn;
   const int64_t col_blocks = (N + 64 * wn - 1) / (64 * wn), steps = K / 16;
   int ks = 1;
-  while (ks < 8 && col_blocks * ks < 2 * QDM_NUM_SMS && steps / (2 * ks) >= 2 * wk) ks *= 2;
+  // every CTA resident at once (2 per SM up to 16 rows, 1 above: 124-126 vs 160-168 registers): a second wave would
+  // repeat the whole load / reduce latency chain
+  const int64_t resident = int64_t(mt <= 2 ? 2 : 1) * QDM_NUM_SMS;
+  while (ks < 8 && col_blocks * ks * 2 <= resident && steps / (2 * ks) >= 2 * wk) ks *= 2;
   int spc = int((steps + ks - 1) / ks);
   while (ks < 8 && skinny_smem(mt, spc, wn) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
   *ks_out = ks;
