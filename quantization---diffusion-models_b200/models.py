@@ -10,7 +10,7 @@ tensors (qweight/qzeros/scales) -- SURVEY.md section 8(f) row 2 -- instead of fp
 """
 import json
 import os
-from typing import Dict, List, Optional, Union
+from typing import Dict
 
 import torch
 import torch.nn as nn

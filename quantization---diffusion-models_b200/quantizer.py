@@ -23,7 +23,7 @@ import torch.nn as nn
 from . import ops
 from .fake_quant import WxAxConv2d, WxAxLinear
 from .linear import WQLinear_GEMM
-from .module import (ModuleTraversal, append_str_prefix, exclude_layers_to_not_quantize, get_named_linears, get_op_name,
+from .module import (ModuleTraversal, exclude_layers_to_not_quantize, get_named_linears, get_op_name,
                      set_op_by_name)
 from .scale import apply_clip, apply_scale
 

@@ -5,10 +5,7 @@ Deviations: `alpha` is a parameter (the reference hard-c
 quantizer_SQ.py:349 while BASELINE config 3 asks for 0.5); the NameError at :386 is not reproduced; adapters
 other than SD1.x provide smoothing blocks too; `version='w8a8'` swaps in real int8 modules (kernel d).
 """
-from typing import List
-
 import torch
-import torch.nn as nn
 
 from . import ops
 from .calib_data import Fused_Mean_Max_Activation_Hook, Mean_Max_Activation_Hook, apply_hook, get_calib_dataset_dm, run_calibration
