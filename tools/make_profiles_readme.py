@@ -31,6 +31,8 @@ for f, w in [
     ("conv3x3_w4a16_640x640x32_ncu_r01.txt", "ncu summary of the W4A16 CTA-pair kernel running a 3x3 convolution (640 -> 640 channels, 32 x 32, batch 16) through the 4-D tensor map"),
     ("colstats_ncu_r01.txt", "ncu summary of the one-pass hook statistic kernel (`col_stats_stage1`)"),
     ("denoise_conv_ab_r01.txt", "denoise loop it/s with packed 3x3 convolutions vs cuDNN (`QDM_CONV_GEMM` A/B)"),
+    ("wave_model_r01.txt", "`tools/wave_model.py`: tile / wave cost model of the CTA-pair kernel vs the measured per-shape tables, and what single-wave (wider) tiles would save"),
+    ("skinny_w4a16_times_r01.txt", "`tools/time_w4.py`: GPU-side times of the M <= 32 W4A16 kernel (final version)"),
     ("timeline_roles_1232x1280x768_r01.txt", "role timeline (TMA / raw producer / 4 dequant groups / MMA / epilogue, clock64) of one CTA pair, `QDM_TRACE` build + `tools/trace_view.py`"),
     ("timeline_inputs_320.txt, timeline_inputs_1280.txt", "per k-block: A-load issue, dequant arrival, MMA start (`tools/trace_inputs.py`) — the evidence that the MMA waits for the A tile, not for the dequant"),
 ]:
