@@ -47,3 +47,27 @@ def test_no_cpu_fallback(qdm):
         qdm.ops.colabsmax(torch.randn(4, 8))
     with pytest.raises(RuntimeError):
         qdm._lib.check(lib.qdm_rowabsmax(16, 0, 4, 8, 16, None))
+
+
+def test_new_entry_points_validate_arguments(qdm):
+    """qdm_colstats / qdm_conv3x3_*: argument errors are reported before a device is touched."""
+    lib, E = qdm._lib.load(), qdm._lib
+    # no output requested / bad shape / bad mode
+    assert lib.qdm_colstats(16, 0, 4, 8, 8, None, 0, None, None, 16, 1 << 20, None) == E.QDM_ERR_INVALID
+    assert "no output" in E.last_error()
+    assert lib.qdm_colstats(16, 0, 0, 8, 8, 16, 0, None, None, 16, 1 << 20, None) == E.QDM_ERR_INVALID
+    assert lib.qdm_colstats(16, 0, 4, 8, 8, 16, 2, None, None, 16, 1 << 20, None) == E.QDM_ERR_INVALID
+    assert lib.qdm_colstats_workspace_bytes(4096, 2432) == 2 * lib.qdm_colreduce_workspace_bytes(4096, 2432)
+    # convolution geometry: C must be a multiple of 64; the direct form needs rows that tile 128
+    assert lib.qdm_conv3x3_f16(16, 16, None, 16, 0, 1, 8, 8, 100, 64, None) == E.QDM_ERR_INVALID
+    assert "multiple of 64" in E.last_error()
+    assert lib.qdm_conv3x3_f16(16, 16, None, 16, 0, 0, 8, 8, 64, 64, None) == E.QDM_ERR_INVALID
+    rc = lib.qdm_conv3x3_nhwc_f16(16, 16, None, 16, 0, 1, 5, 7, 64, 64, None)
+    assert rc == E.QDM_ERR_UNSUPPORTED and "whole image rows" in E.last_error()
+    with pytest.raises(RuntimeError, match="whole image rows"):
+        E.check(rc)
+    ok = lambda h, w: bool(lib.qdm_conv3x3_direct_ok(h, w))
+    assert ok(64, 64) and ok(32, 32) and ok(16, 16) and ok(8, 8) and ok(128, 128) and ok(4, 4) and ok(16, 8)
+    assert not ok(96, 96) and not ok(5, 7) and not ok(12, 16) and not ok(256, 256) and not ok(0, 8)
+    # packed-weight convolution: the group must be 64 * 2^j dividing 9 C
+    assert lib.qdm_conv3x3_w4a16(16, 16, 16, 16, None, 16, 0, 1, 8, 8, 320, 64, 128, None) == E.QDM_ERR_INVALID
