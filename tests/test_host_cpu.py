@@ -262,3 +262,30 @@ def test_quantize_gemm_and_w8a8_on_other_adapters(kind, tmp_path):
         assert any(type(m).__name__ == "W8A8Linear" for m in m8.denoiser().modules())
         q8 = m8.generate(["a", "b"], lat=lat, num_inference_steps=1).float()
         assert torch.isfinite(q8).all() and ((q8 - fp).abs().max() / fp.abs().max()).item() < 0.2
+
+
+def test_packing_mirrors_on_reference_fixture():
+    """packing_utils / quant_utils mirrors (names and argument meaning of utils/packing_utils.py, utils/quant_utils.py)
+    against the reference-generated layout fixture: pack, unpack in packed order, order reversal, dequantize_gemm."""
+    from _util import Golden
+    pu = importlib.import_module(PKG + ".packing_utils")
+    qu = importlib.import_module(PKG + ".quant_utils")
+    g = Golden("awq_layout.npz")
+    codes, zeros = g.get("codes"), g.get("zeros")
+    qweight, qzeros, scales, deq = g.get("qweight"), g.get("qzeros"), g.get("scales"), g.get("deq")
+    gs = int(g.get("group"))
+    with patched_ops():
+        assert torch.equal(qu.pack_awq(codes), qweight) and torch.equal(qu.pack_awq(zeros), qzeros)
+        assert torch.equal(qu.unpack_awq(qweight).to(torch.int32), codes)
+        iw, iz = pu.unpack_awq(qweight, qzeros, 4)                 # still in packed nibble order, like the reference
+        assert not torch.equal(iw.to(torch.int32), codes)
+        iw, iz = pu.reverse_awq_order(iw, iz, 4)
+        assert torch.equal(iw.to(torch.int32) & 0xF, codes) and torch.equal(iz.to(torch.int32) & 0xF, zeros)
+        assert torch.equal(pu.dequantize_gemm(qweight, qzeros, scales, 4, gs), deq)
+        assert torch.equal(qu.dequantize(codes, scales, zeros, gs), deq.to(torch.float16))
+        with pytest.raises(NotImplementedError):
+            pu.dequantize_gemm(qweight, qzeros, scales, 8, gs)
+    x = torch.arange(32).view(2, 16)
+    assert torch.equal(qu.apply_order(qu.apply_order(x, "column", qu.AWQ_PACK_ORDER), "column", qu.REVERSE_AWQ_PACK_ORDER), x)
+    with pytest.raises(ValueError):
+        qu.apply_order(x, "diagonal")
