@@ -106,3 +106,40 @@ def test_wxax_conv_live(ref):
     eq(wf, m.weight, "fake-quant conv weight")
     y, want = O.conv2d_fake(x, wf, conv.bias.data, 1, 1), m(x)
     assert ((y.float() - want.float()).abs().max() / want.float().abs().max()).item() <= 2e-3
+
+
+# ------------------------------------------------------------------ host mirrors that are plain torch (no kernel): scale.py
+class _Toy(torch.nn.Module):
+    def __init__(self, g, dtype):
+        super().__init__()
+        C = 64
+        self.ln = torch.nn.LayerNorm(C)
+        self.q, self.k, self.v = (torch.nn.Linear(C, 48) for _ in range(3))
+        self.fc1, self.fc2 = torch.nn.Linear(C, 96), torch.nn.Linear(96, C)
+        for p in self.parameters():
+            p.data = torch.randn(p.shape, generator=g) * 0.1 + (1.0 if p.dim() == 1 and p.numel() == C else 0.0)
+        self.to(dtype)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_scale_and_clip_mirror_live(ref, dt):
+    """apply_scale (LayerNorm -> q,k,v and fc1 -> fc2) and apply_clip of the product's scale.py against the reference's
+    quantize/scale.py:25-153 on identical modules: every parameter bit-identical afterwards."""
+    import importlib
+    ours = importlib.import_module("quantization---diffusion-models_b200.scale")
+    mods = []
+    for _ in range(2):
+        mods.append(_Toy(torch.Generator().manual_seed(5), DT[dt]))
+    g = torch.Generator().manual_seed(6)
+    s_ln = (torch.rand(64, generator=g) + 0.5).to(DT[dt])
+    s_fc = (torch.rand(96, generator=g) + 0.5).to(DT[dt])
+    clip = (torch.rand(48, 2, 1, generator=g) * 0.1 + 0.02).to(DT[dt])
+    feats = [{"q": torch.randn(10, 64, generator=torch.Generator().manual_seed(7)).to(DT[dt])} for _ in range(2)]
+    scales_list = lambda: [("ln", ("q", "k", "v"), s_ln.clone()), ("fc1", ("fc2",), s_fc.clone())]
+    ref.scale.apply_scale(mods[0], scales_list(), input_feat_dict=feats[0])
+    ours.apply_scale(mods[1], scales_list(), input_feat_dict=feats[1])
+    ref.scale.apply_clip(mods[0], [("q", clip.clone())])
+    ours.apply_clip(mods[1], [("q", clip.clone())])
+    for (n, a), (_, b) in zip(mods[0].state_dict().items(), mods[1].state_dict().items()):
+        eq(b, a, n)
+    eq(feats[1]["q"], feats[0]["q"], "scaled input features")
