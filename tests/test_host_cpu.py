@@ -289,3 +289,47 @@ def test_packing_mirrors_on_reference_fixture():
     assert torch.equal(qu.apply_order(qu.apply_order(x, "column", qu.AWQ_PACK_ORDER), "column", qu.REVERSE_AWQ_PACK_ORDER), x)
     with pytest.raises(ValueError):
         qu.apply_order(x, "diagonal")
+
+
+def test_awq_search_host_logic_on_reference_fixture():
+    """AwqQuantizer._search_best_scale / _compute_best_scale / _compute_best_clip (the host orchestration: statistics,
+    20-point ratio grid, restore of the weights, first-minimum argmin, clip levels) against the reference-generated
+    search fixture, with the kernels stood in by the oracle."""
+    from _util import Golden
+    import oracle.qdm_oracle as O
+    Q = importlib.import_module(PKG + ".quantizer").AwqQuantizer
+
+    class Cat(torch.nn.Module):
+        def __init__(self, ls):
+            super().__init__()
+            self.ls = torch.nn.ModuleList(ls)
+
+        def forward(self, x):
+            return torch.cat([l(x) for l in self.ls], dim=-1)
+
+    g = Golden("awq_search.npz")
+    with patched_ops():
+        for tag, dt, group, zp in g.cases():
+            x = g.get(tag + "_x")
+            lins = []
+            for i in range(3):
+                w, b = g.get(f"{tag}_w{i}"), g.get(f"{tag}_b{i}")
+                l = torch.nn.Linear(w.shape[1], w.shape[0], bias=True)
+                l.weight.data, l.bias.data = w.clone(), b.clone()
+                lins.append(l)
+            block = Cat(lins)
+            q = Q(None, group_size=int(group), zero_point=bool(int(zp)))
+            before = [l.weight.data.clone() for l in lins]
+            prev, names, best = q._search_best_scale(block, lins[0], lins, x, module2inspect=block, kwargs={})
+            assert names == ("ls.0", "ls.1", "ls.2") and prev == "ls.0"
+            for l, wb in zip(lins, before):
+                assert torch.equal(l.weight.data, wb)                # originals restored
+            want = g.get(tag + "_best")
+            if not torch.equal(best, want):                          # near-tie between two ratios: loss within 0.5 %
+                ws, bs = [g.get(f"{tag}_w{i}") for i in range(3)], [g.get(f"{tag}_b{i}") for i in range(3)]
+                fwd = lambda wl: torch.cat([torch.nn.functional.linear(x, w, b) for w, b in zip(wl, bs)], dim=-1)
+                _, _, hist = O.awq_search_scale(x, ws, fwd, int(group), bool(int(zp)))
+                assert hist[int(round(q.last_best_ratio * 20))] <= min(hist) * 1.005
+            clip, ref_clip = q._compute_best_clip(lins[0].weight.data, x), g.get(tag + "_clip")
+            assert clip.shape == ref_clip.shape
+            assert (clip == ref_clip).float().mean().item() >= 0.97
