@@ -193,6 +193,37 @@ int qdm_gemm_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros,
                    const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
                    void* stream);
 
+/* Kernel-native copy of an AWQ weight for qdm_gemm_w4a16_rp ("repacked" weights; built once per weight, e.g. at module
+ * load -- the checkpoint / module buffers keep the utils/packing_utils.py layout).  Words, scales and zero points of
+ * 128 k rows x 16 output columns become one 1104-byte block, blocks of one k group are contiguous along N, so a CTA
+ * fetches everything it needs for 128 k rows of its tile part with ONE bulk copy of whole 128-byte lines instead of
+ * 64-128 short rows per k-block through three tensor maps.  blob: qdm_w4a16_repack_bytes(N, K) bytes, 16-byte aligned,
+ * owned by the caller.  N % 8 == 0, K % 64 == 0, group a multiple of 64 dividing K. */
+size_t qdm_w4a16_repack_bytes(int64_t N, int64_t K);
+int qdm_w4a16_repack(const int32_t* qweight, const int32_t* qzeros, const void* scales, int64_t N, int64_t K, int group,
+                     void* blob, size_t blob_bytes, void* stream);
+
+/* qdm_gemm_w4a16 with the repacked copy of the same weight in `blob` (may be NULL = plain qdm_gemm_w4a16).  Problems
+ * with M > 128 run the repacked-weight CTA-pair kernel: a pair owns 256 rows x one or two sub-tiles of <= 256 columns
+ * (two: all 512 TMEM columns as one accumulator set, the A operand amortised over twice the columns, mid-sized layers in
+ * one wave instead of two).  Small-M problems and the small-K B-stationary case read the AWQ tensors as before, so all
+ * four tensors must describe the same weight.  Results are identical to qdm_gemm_w4a16 up to fp32 summation order. */
+int qdm_gemm_w4a16_rp(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* blob,
+                      const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group, void* stream);
+
+/* Which kernel the calling thread's last W4A16 GEMM call launched, and its tile width in columns (tests assert the
+ * dispatch with this; not part of the reference interface). */
+#define QDM_GEMM_SINGLE  1 /* single-CTA tcgen05 tiles (M <= 128)              */
+#define QDM_GEMM_PAIR    2 /* CTA-pair tiles, AWQ tensors through tensor maps  */
+#define QDM_GEMM_BSTAT   3 /* B-stationary CTA-pair kernel (K <= 384)          */
+#define QDM_GEMM_STREAMK 4 /* stream-K CTA-pair kernel                         */
+#define QDM_GEMM_SKINNY  5 /* M <= 32, sector-wide cluster split-K (mma.sync)  */
+#define QDM_GEMM_SMALLM  6 /* M <= 32, small weights (mma.sync)                */
+#define QDM_GEMM_RP1     7 /* repacked weights, one sub-tile per pair          */
+#define QDM_GEMM_RP2     8 /* repacked weights, two sub-tiles per pair         */
+#define QDM_GEMM_QUAD    9 /* quad clusters (forced only)                      */
+int qdm_gemm_last_variant(int* tile_n);
+
 /* y[m,n] = (sum_k xq[m,k]*wq[n,k]) * sx[m] * sw[n] + bias[n]; int8 x int8 -> int32 in TMEM.
  * xq [M,K] int8 (per-token codes, fake_quant.py:109-118), wq [N,K] int8 (per-channel codes,
  * fake_quant.py:86-93), sx [M] / sw [N] fp32, bias/y in out_dtype.  K % 16 == 0, N % 8 == 0. */
@@ -247,7 +278,9 @@ size_t qdm_gemm_workspace_bytes(void);
 int qdm_gemm_set_workspace(void* workspace, size_t bytes, void* stream);
 
 /* Tile-shape override for bring-up and A/B timing: 0 = heuristic, 1 = single-CTA tiles (128 x N),
- * 2 = CTA-pair tiles (cta_group::2, 256 x N), 4 = quad clusters, 8 = stream-K.  Process-wide; not part of the reference interface. */
+ * 2 = CTA-pair tiles (cta_group::2, 256 x N), 4 = quad clusters, 8 = stream-K, 16 / 32 = repacked-weight kernel with one /
+ * two sub-tiles (+ (sub-tile width << 8) to pin the width), 64 = ignore the repacked copy.  Process-wide, test-only;
+ * not part of the reference interface. */
 int qdm_set_gemm_mode(int ctas);
 
 /* Test hook (synchronous, allocates 16 bytes): sweeps EVERY (dividend, divisor) pair of 16-bit values of

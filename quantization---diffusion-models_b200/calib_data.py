@@ -106,23 +106,36 @@ class Running_Max_Activation_Hook:
 
 
 class Input_Capture_Hook:
-    """Keeps the inputs of a Linear on the GPU (the reference caches them on the CPU, quantizer.py:1097-1100)."""
+    """Keeps the inputs of a Linear on the GPU (the reference caches them on the CPU, quantizer.py:1097-1100).
+    `per_call` bounds the rows kept per forward call (evenly strided subsample, copied, so the activation itself can be
+    freed): with per_call = max_tokens / total calls the memory of a capture pass is bounded by max_tokens rows per
+    Linear however long the calibration runs.  Chunks carry a global call id (`next_id`, set by the capture loop per
+    calibration batch) so that captures made data parallel can be merged in single-process order (dist.exchange_captures)."""
 
-    def __init__(self, max_tokens=None):
+    def __init__(self, max_tokens=None, per_call=None):
         self.hook_handle = None
-        self.chunks = []
+        self.chunks = []          # [(call_id, X[rows, K])]
         self.max_tokens = max_tokens
+        self.per_call = per_call
+        self.next_id = 0
 
     def __call__(self, module, module_in, module_out):
         x = module_in[0].detach()
         x = x.reshape(-1, x.shape[-1])
-        self.chunks.append(x)
+        if self.per_call is not None and x.shape[0] > self.per_call:
+            x = x[:: x.shape[0] // self.per_call][: self.per_call]
+        self.chunks.append((self.next_id, x.clone()))
+        self.next_id += 1
+
+    @staticmethod
+    def merge(chunks, max_tokens=None):
+        x = torch.cat([c for _, c in sorted(chunks, key=lambda t: t[0])], dim=0)
+        if max_tokens is not None and x.shape[0] > max_tokens:
+            x = x[:: x.shape[0] // max_tokens][:max_tokens].contiguous()
+        return x
 
     def cat(self):
-        x = torch.cat(self.chunks, dim=0)
-        if self.max_tokens is not None and x.shape[0] > self.max_tokens:
-            x = x[:: x.shape[0] // self.max_tokens][: self.max_tokens].contiguous()
-        return x
+        return self.merge(self.chunks, self.max_tokens)
 
 
 def apply_hook(module: torch.nn.Module, hook_cls=Mean_Max_Activation_Hook):

@@ -651,7 +651,8 @@ quant_flat_kernel(const T* __restrict__ x, int64_t numel, const T* __restrict__ 
   const int64_t tid = int64_t(blockIdx.x) * kQThreads + threadIdx.x;
   const int64_t nthreads = int64_t(gridDim.x) * kQThreads;
   const int64_t nvec = vec_ok ? numel / V : 0;
-  const bool fast = fastdiv_ok<T>(s, ElemTraits<T>::to_f(absmax_dev[0]));
+  // more than 8 bits (a_bit = 16, q_max = 32767): plain IEEE division, outside what the fast path was verified for
+  const bool fast = max_int <= 255.f && fastdiv_ok<T>(s, ElemTraits<T>::to_f(absmax_dev[0]));
   const float dummy[V] = {};
   for (int64_t i = tid; i < nvec; i += nthreads) {
     Vec16<T> v = ld_vec16_stream(x + i * V);
@@ -991,7 +992,10 @@ int launch_quant(const T* w, int64_t n_groups, int64_t group, int64_t k_period, 
   const int64_t lpg = group / V;
   const int64_t n_rows = numel / k_period;
   const bool extras = pre_mul || clip_max || post_div;
-  if (aligned && group % V == 0 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && n_rows < (int64_t(1) << 31) &&
+  // more than 8 bits (row-wise a_bit = 16, q_max = 32767): the packed fp16 chain's magic-number rounding and the reciprocal
+  // division were verified for small codes only, so these go through the op-by-op IEEE kernel at the end
+  const bool wide = max_int > 255.f;
+  if (!wide && aligned && group % V == 0 && lpg <= 32 && (lpg & (lpg - 1)) == 0 && n_rows < (int64_t(1) << 31) &&
       k_period / V < (int64_t(1) << 20)) {
     const int64_t vpr = k_period / V;
     int lpg_shift = 0;
@@ -1017,7 +1021,7 @@ int launch_quant(const T* w, int64_t n_groups, int64_t group, int64_t k_period, 
     else
       quant_group_kernel<T, MODE, false><<<grid, kQThreads, 0, st>>>(
           w, int(n_rows), int(vpr), lpg_shift, int(rpp), max_int, min_int, nullptr, nullptr, nullptr, dq, codes, scales, zeros);
-  } else if (group <= 16 && !extras) {
+  } else if (!wide && group <= 16 && !extras) {
     // whole chunks of rows through the vector kernel (symmetric modes, no int8 codes), the remaining rows one per thread
     int64_t done_rows = 0;
     if (MODE != Q_ZP && !codes && aligned && group < V) {
@@ -1043,7 +1047,7 @@ int launch_quant(const T* w, int64_t n_groups, int64_t group, int64_t k_period, 
     } else {
       return QDM_OK;
     }
-  } else if (aligned && !extras && group % V == 0 && group <= 32 * V * 16) {
+  } else if (!wide && aligned && !extras && group % V == 0 && group <= 32 * V * 16) {
     return launch_rows_reg<T, MODE, false>(w, n_groups, group, max_int, min_int, dq, codes, scales, zeros, nullptr, st);
   } else {
     const int vec_ok = aligned && group % V == 0;
@@ -1099,7 +1103,10 @@ extern "C" int qdm_quant_rowwise(const void* x, int dtype, int64_t rows, int64_t
                                  void* dq, int8_t* codes, void* scales, void* zeros, void* stream) {
   QDM_REQUIRE(x, "qdm_quant_rowwise: null input");
   QDM_REQUIRE(rows > 0 && cols > 0, "qdm_quant_rowwise: empty tensor [%lld, %lld]", (long long)rows, (long long)cols);
-  QDM_REQUIRE(n_bits >= 2 && n_bits <= 8, "qdm_quant_rowwise: n_bits %d outside [2, 8]", n_bits);
+  // up to 16 bits for the fake-quant output (the reference's default a_bit = 16, q_max = 32767: fake_quant.py:112);
+  // integer codes are one byte, so they exist for <= 8 bits only
+  QDM_REQUIRE(n_bits >= 2 && n_bits <= 16, "qdm_quant_rowwise: n_bits %d outside [2, 16]", n_bits);
+  QDM_REQUIRE(n_bits <= 8 || !codes, "qdm_quant_rowwise: int8 codes need n_bits <= 8 (got %d)", n_bits);
   QDM_REQUIRE((flags & ~(QDM_Q_ZERO_POINT | QDM_Q_NO_CLAMP)) == 0 &&
               (flags & (QDM_Q_ZERO_POINT | QDM_Q_NO_CLAMP)) != (QDM_Q_ZERO_POINT | QDM_Q_NO_CLAMP),
               "qdm_quant_rowwise: bad flags 0x%x", flags);
@@ -1134,7 +1141,8 @@ extern "C" int qdm_quant_tensor(const void* x, int dtype, int64_t numel, int n_b
                                 void* workspace, size_t workspace_bytes, void* stream) {
   QDM_REQUIRE(x && workspace, "qdm_quant_tensor: null pointer");
   QDM_REQUIRE(numel > 0, "qdm_quant_tensor: empty tensor");
-  QDM_REQUIRE(n_bits >= 2 && n_bits <= 8, "qdm_quant_tensor: n_bits %d outside [2, 8]", n_bits);
+  QDM_REQUIRE(n_bits >= 2 && n_bits <= 16, "qdm_quant_tensor: n_bits %d outside [2, 16]", n_bits);
+  QDM_REQUIRE(n_bits <= 8 || !codes, "qdm_quant_tensor: int8 codes need n_bits <= 8 (got %d)", n_bits);
   const size_t head = 256;  // absmax scalar lives at the start of the workspace
   QDM_REQUIRE(workspace_bytes >= head + qdm_absmax_workspace_bytes(numel), "qdm_quant_tensor: workspace too small");
   QDM_DEVICE_GATE();

@@ -90,7 +90,8 @@ def gather_results(local, device):
 
 
 def sharded_search(quantizer, shard):
-    """run quantizer.search on this rank's blocks and gather; every rank returns the full, identical result."""
+    """run quantizer.search on this rank's share (blocks, or ratios when there are fewer than 2 blocks per rank) and
+    gather; every rank returns the full, identical result."""
     local = quantizer.search(shard=shard)
     dev = next(quantizer.awq_model.denoiser().parameters()).device
     merged = gather_results(local, dev)
@@ -138,3 +139,81 @@ def allreduce_hook_stats(hook_dict):
         h.running_max.copy_(rmax[off:off + n].to(h.running_max.device, h.running_max.dtype))
         off += n
     return hook_dict
+
+
+# ------------------------------------------------------------------ data-parallel capture of the calibration inputs
+def owners_of(names, costs, world):
+    """(parts, ratio_split): the block -> rank assignment of the search.  With fewer than 2 blocks per rank the ratio grid
+    is split instead: every rank searches every block on its share of the 20 ratios."""
+    ratio_split = world > 1 and len(names) < 2 * world
+    return assign_blocks(names, costs, world), ratio_split
+
+
+def exchange_captures(caps, wanted_by, rank, world, device):
+    """Calibration batches are run data parallel (batch i on rank i % world); this hands every rank the captured Linear
+    inputs of the blocks it searches, from ALL batches.
+      caps      : {block: {linear: [(call_id, X[rows, K])]}} captured on this rank (call_id = global forward-call index)
+      wanted_by : {block: [ranks]} -- who needs the block's inputs (one owner, or every rank when the ratio grid is split)
+    Returns the same structure for the blocks `rank` wants, holding the chunks of every rank sorted by call_id, so the
+    concatenation is the one a single process would have built: search results do not depend on the world size.
+    One metadata all_gather_object + one batch of point-to-point copies (NCCL: grouped; gloo in the CPU tests)."""
+    mine = {b: {ln: list(ch) for ln, ch in lins.items()} for b, lins in caps.items() if rank in wanted_by.get(b, ())}
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return mine
+    meta = {b: {ln: [(cid, tuple(x.shape), str(x.dtype)) for cid, x in ch] for ln, ch in lins.items()} for b, lins in caps.items()}
+    metas = [None] * world
+    dist.all_gather_object(metas, meta)
+    comm_dev = device if dist.get_backend() == "nccl" else torch.device("cpu")
+    order = sorted(caps)   # identical module trees -> identical keys on every rank
+
+    def flat_for(dst):      # what this rank sends to dst: every chunk of the blocks dst wants, fixed order
+        parts = [x.reshape(-1) for b in order if dst in wanted_by.get(b, ()) for ln in caps[b] for _, x in caps[b][ln]]
+        return torch.cat(parts).to(comm_dev) if parts else None
+
+    ops, recv = [], {}
+    for peer in range(world):
+        if peer == rank:
+            continue
+        out = flat_for(peer)
+        if out is not None and out.numel():
+            ops.append(dist.P2POp(dist.isend, out, peer))
+        n, dt = 0, None
+        for b in order:
+            if rank in wanted_by.get(b, ()):
+                for ln, ch in metas[peer][b].items():
+                    for _, shape, dts in ch:
+                        n += shape[0] * shape[1]
+                        dt = getattr(torch, dts.split(".")[-1])
+        if n:
+            recv[peer] = torch.empty(n, dtype=dt, device=comm_dev)
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for peer, buf in recv.items():
+        off = 0
+        for b in order:
+            if rank not in wanted_by.get(b, ()):
+                continue
+            for ln, ch in metas[peer][b].items():
+                for cid, shape, _ in ch:
+                    n = shape[0] * shape[1]
+                    mine.setdefault(b, {}).setdefault(ln, []).append((cid, buf[off:off + n].reshape(shape).to(device)))
+                    off += n
+    for lins in mine.values():
+        for ln in lins:
+            lins[ln].sort(key=lambda t: t[0])
+    return mine
+
+
+def allreduce_min_losses(losses):
+    """ratio-split search: every rank filled its own ratios of the [groups, 20] loss table (inf elsewhere); ONE
+    all_reduce(MIN) completes it everywhere (the entries are disjoint, so MIN just merges them, bit for bit)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return losses
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(losses, op=dist.ReduceOp.MIN)
+        return losses
+    t = losses.cpu()
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return t.to(losses.device)

@@ -98,6 +98,7 @@ class WxAxLinear(nn.Module):
         self.quantize_act = q_act
         self.in_features = in_features
         self.out_features = out_features
+        self.n_bits_A, self.quantize_output = n_bits_A, quantize_output
         self.register_buffer('weight', torch.empty(out_features, in_features, dtype=torch.float16, device=device))
         if bias:
             self.register_buffer('bias', torch.zeros(out_features, dtype=torch.float16, device=device))
@@ -133,6 +134,11 @@ class WxAxLinear(nn.Module):
         return cls(module.in_features, module.out_features, module.bias is not None, act_quant=act_quant,
                    quantize_output=quantize_output, n_bits_A=n_bits_A)
 
+    @classmethod
+    def from_quant_args(cls, module, args):
+        """empty module with the recorded constructor arguments (weights come from the checkpoint's state dict)"""
+        return cls(module.in_features, module.out_features, module.bias is not None, device=module.weight.device, **args)
+
     @staticmethod
     def from_float(module, init_only=False, weight_quant='per_channel', act_quant='per_token', quantize_output=False,
                    n_bits_W=8, n_bits_A=16, group_size_W=0, codeBookQuantInd=False, debugPath=[], debug=False):
@@ -157,6 +163,12 @@ class WxAxLinear(nn.Module):
             new_module.bias.data.copy_(module.bias.data.to(new_module.weight.dtype))
         return new_module
 
+    def quant_args(self):
+        """constructor arguments that are not in the state dict: what a packed checkpoint must carry to rebuild this module
+        (models.save_quantized / from_quantized)"""
+        return {"weight_quant": self.weight_quant_name, "act_quant": self.act_quant_name, "quantize_output": self.quantize_output,
+                "n_bits_A": self.n_bits_A, "q_act": self.quantize_act}
+
     def __repr__(self):
         return (f'WxAxLinear({self.in_features}, {self.out_features}, bias={self.bias is not None}, '
                 f'weight_quant={self.weight_quant_name}, act_quant={self.act_quant_name}, '
@@ -178,6 +190,7 @@ class WxAxConv2d(nn.Module):
         self.groups = groups
         self.a_gs = act_group_size
         self.quantise_act = quantize_output
+        self.n_bits_A = n_bits_A
         assert in_channels % groups == 0
         self.register_buffer('weight', torch.empty((out_channels, in_channels // groups, *self.kernel_size),
                                                    dtype=torch.float16, device=device))
@@ -268,6 +281,16 @@ class WxAxConv2d(nn.Module):
         if module.bias is not None:
             new_module.bias.data.copy_(module.bias.data.to(new_module.weight.dtype))
         return new_module
+
+    def quant_args(self):
+        """constructor arguments that are not in the state dict (see WxAxLinear.quant_args)"""
+        return {"weight_quant": self.weight_quant_name, "act_quant": self.act_quant_name, "act_group_size": self.a_gs,
+                "quantize_output": self.quantise_act, "n_bits_A": self.n_bits_A}
+
+    @classmethod
+    def from_quant_args(cls, module, args):
+        return cls(module.in_channels, module.out_channels, module.kernel_size, module.stride, module.padding, module.dilation,
+                   module.groups, module.bias is not None, device=module.weight.device, **args)
 
     def __repr__(self):
         s = f'WxAxConv2d({self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}'

@@ -23,6 +23,7 @@ class WQLinear_GEMM(nn.Module):
             raise NotImplementedError("Only 4-bit are supported for now.")
         self.in_features, self.out_features = in_features, out_features
         self.w_bit = w_bit
+        self.repack = True   # keep a kernel-native copy of the weight for large-M calls (see _repacked)
         self.group_size = group_size if group_size != -1 else in_features
         assert self.in_features % self.group_size == 0
         assert out_features % (32 // self.w_bit) == 0
@@ -53,10 +54,25 @@ class WQLinear_GEMM(nn.Module):
             m.bias = linear.bias.data.clone().to(dtype)
         return m
 
+    def _repacked(self):
+        """Kernel-native copy of the weight for the tcgen05 GEMM (ops.w4a16_repack), built on first use and rebuilt when
+        the buffers are replaced (load_state_dict, .to()).  Not part of the state dict: checkpoints keep the AWQ layout
+        of utils/packing_utils.py only.  Costs 0.54 B / weight of device memory next to the 0.5 B / weight of qweight."""
+        key = (self.qweight.data_ptr(), self.qzeros.data_ptr(), self.scales.data_ptr(), self.qweight._version)
+        rp = self.__dict__.get("_rp")
+        if rp is None or rp[0] != key:
+            if self.group_size % 64 or self.in_features % 64:
+                rp = (key, None)   # shapes the repacked-weight kernel does not tile
+            else:
+                rp = (key, ops.w4a16_repack(self.qweight, self.qzeros, self.scales, self.group_size))
+            self.__dict__["_rp"] = rp
+        return rp[1]
+
     def forward(self, x):
+        blob = self._repacked() if self.repack else None
         if x.dtype == self.scales.dtype:
-            return ops.gemm_w4a16(x, self.qweight, self.qzeros, self.scales, self.group_size, self.bias)
-        return ops.gemm_w4a16(x.to(self.scales.dtype), self.qweight, self.qzeros, self.scales, self.group_size, self.bias).to(x.dtype)
+            return ops.gemm_w4a16(x, self.qweight, self.qzeros, self.scales, self.group_size, self.bias, blob)
+        return ops.gemm_w4a16(x.to(self.scales.dtype), self.qweight, self.qzeros, self.scales, self.group_size, self.bias, blob).to(x.dtype)
 
     def dequantize(self):
         """[N, K] fake-quant weight (utils/packing_utils.py:87-102, transposed back to nn.Linear layout)."""
@@ -102,6 +118,20 @@ class W8A8Linear(nn.Module):
 
     def extra_repr(self):
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}, W8A8"
+
+
+def w4a16_kernel_ok(in_features, out_features, group):
+    """Shapes qdm_gemm_w4a16 tiles -- the ONE predicate the module swap and the kernel share (csrc/qdm_gemm.cu,
+    gemm_w4a16_impl): K % 64 == 0, group = 64 * 2^j dividing K, N % 8 == 0.  Anything else (group_size = -1 on K = 320,
+    group 192, ...) stays on the fake-quant path instead of building a module whose forward would raise."""
+    j = group // 64 if group > 0 else 0
+    return (group > 0 and group % 64 == 0 and (j & (j - 1)) == 0 and in_features % group == 0
+            and in_features % 64 == 0 and out_features % 8 == 0)
+
+
+def w8a8_kernel_ok(in_features, out_features):
+    """qdm_gemm_w8a8: K % 16 == 0 (16-byte TMA rows of int8), N % 8 == 0."""
+    return in_features % 16 == 0 and out_features % 8 == 0
 
 
 def is_pointwise_conv(conv):

@@ -124,26 +124,41 @@ class BaseAWQForDiffusion:
                                     n_samples=n_batches * batch_size, seed=42, device=self.pipeline.device)
 
     @torch.no_grad()
-    def capture_block_inputs(self, block_names):
-        """One FP pass over the calibration set with a capture hook on every Linear of the requested blocks:
-        {block: {linear_name: X [n_tok, K]}} kept on the GPU (the FP activations of the un-quantised model,
-        as quantizer.py:1093-1141 collects them block by block)."""
+    def capture_block_inputs(self, block_names, shard=None, wanted_by=None):
+        """FP pass over the calibration set with a capture hook on every Linear of the requested blocks:
+        {block: {linear_name: X [n_tok, K]}} kept on the GPU (the FP activations of the un-quantised model, as
+        quantizer.py:1093-1141 collects them block by block), at most `calib_max_tokens` rows per Linear.
+        shard = (rank, world): the pass is DATA PARALLEL -- calibration batch i runs on rank i % world with hooks on every
+        block some rank searches (`wanted_by`: {block: [ranks]}), then dist.exchange_captures hands each rank the inputs
+        of `block_names` from all batches in single-process order.  A batch is always run whole by one rank, so every
+        forward has the shapes (and cuBLAS kernels) of the single-process run: captured inputs, and with them the
+        searched scales and packed codes, are identical for every world size."""
+        from .dist import exchange_captures
+        rank, world = shard if shard is not None else (0, 1)
         blocks = self.get_search_blocks()
+        samples = self.calib_samples or self.default_calib_samples()
+        per_call = -(-self.calib_max_tokens // max(1, len(samples) * self.calib_steps))   # ceil(max_tokens / total calls)
+        hook_blocks = list(wanted_by) if (world > 1 and wanted_by) else list(block_names)
         hooks = {}
-        for bn in block_names:
+        for bn in hook_blocks:
             for ln, lin in blocks[bn].named_modules():
                 if isinstance(lin, nn.Linear):
-                    h = Input_Capture_Hook(self.calib_max_tokens)
+                    h = Input_Capture_Hook(self.calib_max_tokens, per_call)
                     h.hook_handle = lin.register_forward_hook(h)
                     hooks[(bn, ln)] = h
-        samples = self.calib_samples or self.default_calib_samples()
-        for prompts, latents in samples:
+        for bi, (prompts, latents) in enumerate(samples):
+            if bi % world != rank:
+                continue
+            for h in hooks.values():
+                h.next_id = bi * self.calib_steps          # global index of this batch's first forward call
             self.pipeline(prompt=prompts, latents=latents, num_inference_steps=self.calib_steps, guidance_scale=7.5)
-        feats = {bn: {} for bn in block_names}
+        caps = {bn: {} for bn in hook_blocks}
         for (bn, ln), h in hooks.items():
             h.hook_handle.remove()
-            feats[bn][ln] = h.cat()
-        return feats
+            caps[bn][ln] = h.chunks
+        if world > 1:
+            caps = exchange_captures(caps, wanted_by or {bn: [rank] for bn in block_names}, rank, world, self.pipeline.device)
+        return {bn: {ln: Input_Capture_Hook.merge(ch, self.calib_max_tokens) for ln, ch in caps[bn].items()} for bn in block_names}
 
     def get_layers_for_scaling(self, block, input_feat):
         """Scaling groups of a BasicTransformerBlock: the two groups the reference's SmoothQuant
@@ -209,7 +224,7 @@ class BaseAWQForDiffusion:
             self.quantizer.quantize(debugSavePath, debugPlot)
         elif quantType.lower() == 'sq':
             self.quantizer = SqQuantizer(self, None, None, alpha=alpha, **{**common, **kwargs})
-            self.quantizer.quantize(debugSavePath, debugPlot, samples=self.calib_samples)
+            self.quantizer.quantize(debugSavePath, debugPlot, samples=self.calib_samples, shard=shard)
         else:
             raise NotImplementedError("Only awq and sq are supported for now.")
         self.is_quantized = True
@@ -233,10 +248,17 @@ class BaseAWQForDiffusion:
         for n, m in self.denoiser().named_modules():
             k = type(m).__name__
             if k == "QConv1x1":                      # pointwise conv on the GEMM kernels: record the inner module kind
-                kinds[n] = f"QConv1x1:{type(m.inner).__name__}"
+                kinds[n] = {"kind": f"QConv1x1:{type(m.inner).__name__}",
+                            "args": {"w_bit": getattr(m.inner, "w_bit", 8), "group_size": getattr(m.inner, "group_size", 0)}}
                 wrapped.add(n + ".inner")
-            elif k in ("WQLinear_GEMM", "W8A8Linear", "WxAxLinear", "WxAxConv2d", "QConv3x3") and n not in wrapped:
-                kinds[n] = k
+            elif k in ("WQLinear_GEMM", "QConv3x3") and n not in wrapped:
+                kinds[n] = {"kind": k, "args": {"w_bit": m.w_bit, "group_size": m.group_size}}
+            elif k == "W8A8Linear" and n not in wrapped:
+                kinds[n] = {"kind": k, "args": {}}
+            elif k in ("WxAxLinear", "WxAxConv2d"):
+                # everything the constructor needs that the state dict does not hold: activation / output quantisers,
+                # their bit width and group size (a model quantised with quantize_act=True must reload with it ON)
+                kinds[n] = {"kind": k, "args": m.quant_args()}
         meta = {"model_type": self.model_type, "arch": self.config.get("arch", {}), "quantization_config": self.quant_config.to_transformers_dict(),
                 "quant_config": self.quant_config.to_dict(), "quant_components": self.quantized_components, "modules": kinds}
         with open(os.path.join(save_dir, "quant_components.json"), "w") as f:
@@ -254,26 +276,31 @@ class BaseAWQForDiffusion:
         model = cls.from_skeleton(device=device, dtype=dtype, **meta["arch"])
         model.quant_config = AwqConfig.from_dict(meta["quant_config"])
         den = model.denoiser()
-        for name, kind in meta["modules"].items():
+        qg = model.quant_config.q_group_size
+        for name, entry in meta["modules"].items():
+            # entry: {"kind", "args"}; checkpoints written before the per-module arguments were recorded hold the kind only
+            kind, args = (entry["kind"], entry.get("args", {})) if isinstance(entry, dict) else (entry, None)
             old = get_op_by_name(den, name)
             if kind.startswith("QConv1x1:"):
                 ci, co, dev = old.in_channels, old.out_channels, old.weight.device
                 if kind.endswith("WQLinear_GEMM"):
-                    inner = WQLinear_GEMM(4, _effective_group(ci, model.quant_config.q_group_size), ci, co,
-                                          old.bias is not None, dev, dtype)
+                    g = args["group_size"] if args else _effective_group(ci, qg)
+                    inner = WQLinear_GEMM(args["w_bit"] if args else 4, g, ci, co, old.bias is not None, dev, dtype)
                 else:
                     inner = W8A8Linear(ci, co, old.bias is not None, dev, dtype)
                 new = QConv1x1(inner, ci, co)
             elif kind == "QConv3x3":
-                new = QConv3x3.from_conv(old, 4, conv_group(9 * old.in_channels, model.quant_config.q_group_size), init_only=True)
+                g = args["group_size"] if args else conv_group(9 * old.in_channels, qg)
+                new = QConv3x3.from_conv(old, args["w_bit"] if args else 4, g, init_only=True)
             elif kind == "WQLinear_GEMM":
-                new = WQLinear_GEMM.from_linear(old, 4, _effective_group(old.in_features, model.quant_config.q_group_size), init_only=True)
+                g = args["group_size"] if args else _effective_group(old.in_features, qg)
+                new = WQLinear_GEMM.from_linear(old, args["w_bit"] if args else 4, g, init_only=True)
             elif kind == "W8A8Linear":
                 new = W8A8Linear(old.in_features, old.out_features, old.bias is not None, old.weight.device, dtype)
             elif kind == "WxAxLinear":
-                new = WxAxLinear.from_float(old, init_only=True).to(old.weight.device)
+                new = (WxAxLinear.from_quant_args(old, args) if args else WxAxLinear.from_float(old, init_only=True)).to(old.weight.device)
             else:
-                new = WxAxConv2d.from_float(old, init_only=True).to(old.weight.device)
+                new = (WxAxConv2d.from_quant_args(old, args) if args else WxAxConv2d.from_float(old, init_only=True)).to(old.weight.device)
             set_op_by_name(den, name, new)
         den.load_state_dict(torch.load(os.path.join(save_dir, "denoiser.pt"), map_location=device))
         model.is_quantized = True
@@ -326,16 +353,27 @@ class StableDiffusion3_5(BaseAWQForDiffusion):
         d = block.attn.to_q.in_features
         qkv = [block.attn.to_q, block.attn.to_k, block.attn.to_v]
         add = [block.attn.add_q_proj, block.attn.add_k_proj, block.attn.add_v_proj]
+
+        def rows(norm, part):
+            """(shift rows, scale rows) of the modulation Linear that feed `part` ("attn" | "mlp"), by norm type:
+            AdaLayerNormZero chunks (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp); AdaLayerNormContinuous
+            -- norm1_context of the last, context_pre_only block -- chunks (scale, shift)."""
+            if isinstance(norm, sk.AdaLayerNormContinuous):
+                assert part == "attn"
+                return slice(d, 2 * d), slice(0, d)
+            o = 0 if part == "attn" else 3 * d
+            return slice(o, o + d), slice(o + d, o + 2 * d)
+
         groups = [
-            dict(prev_op=AdaLNShift(block.norm1.linear, slice(0, d), slice(d, 2 * d)), layers=qkv,
+            dict(prev_op=AdaLNShift(block.norm1.linear, *rows(block.norm1, "attn")), layers=qkv,
                  inp=input_feat["attn.to_q"], module2inspect=_Cat(qkv)),
-            dict(prev_op=AdaLNShift(block.norm1_context.linear, slice(0, d), slice(d, 2 * d)), layers=add,
+            dict(prev_op=AdaLNShift(block.norm1_context.linear, *rows(block.norm1_context, "attn")), layers=add,
                  inp=input_feat["attn.add_q_proj"], module2inspect=_Cat(add)),
-            dict(prev_op=AdaLNShift(block.norm1.linear, slice(3 * d, 4 * d), slice(4 * d, 5 * d)), layers=[block.ff.net[0].proj],
+            dict(prev_op=AdaLNShift(block.norm1.linear, *rows(block.norm1, "mlp")), layers=[block.ff.net[0].proj],
                  inp=input_feat["ff.net.0.proj"]),
         ]
         if not block.context_pre_only:
-            groups.append(dict(prev_op=AdaLNShift(block.norm1_context.linear, slice(3 * d, 4 * d), slice(4 * d, 5 * d)),
+            groups.append(dict(prev_op=AdaLNShift(block.norm1_context.linear, *rows(block.norm1_context, "mlp")),
                                layers=[block.ff_context.net[0].proj], inp=input_feat["ff_context.net.0.proj"]))
         return groups
 

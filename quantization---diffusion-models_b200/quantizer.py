@@ -139,16 +139,36 @@ class AwqQuantizer:
     def search(self, shard=None):
         """Returns {block_name: {"scales": [(prev_op_name, layer_names, scales)], "clip": [(layer_name, max_val)]}}
         for the blocks owned by this rank.  Blocks and their calibration inputs come from the adapter:
-        `get_search_blocks()` -> {name: block}, `capture_block_inputs(names)` -> {name: {linear_name: X}}
-        (inputs of every Linear of the block from one FP pass over the calibration set, kept on the GPU)."""
+        `get_search_blocks()` -> {name: block}, `capture_block_inputs(names, shard, wanted_by)` -> {name: {linear_name: X}}
+        (inputs of every Linear of the block from the FP passes over the calibration set, kept on the GPU).
+
+        shard = (rank, world), SURVEY.md section 8(e):
+          * the capture pass is data parallel over calibration batches (models.capture_block_inputs);
+          * with >= 2 blocks per rank, blocks are assigned to ranks (dist.assign_blocks) and a rank runs both phases -- scale
+            search over the full 20-point grid, then clip search on the scaled block -- for its blocks only;
+          * with fewer blocks the RATIO GRID is split instead (dist.split_ratios: 3,3,3,3,2,2,2,2 at world 8): every rank
+            evaluates its ratios for every group, ONE all_reduce(MIN) merges the [groups, 20] loss table, every rank takes
+            the same first minimum (the reference's strict `<`, quantizer.py:739); the clip phase is then shared out block
+            by block.
+        Every loss is computed by one GPU from the same inputs in both modes, so the results do not depend on the world size."""
+        import time
+        from .dist import allreduce_min_losses, owners_of, split_ratios
         blocks = self.awq_model.get_search_blocks()
         names = list(blocks)
-        if shard is not None:
-            from .dist import assign_blocks
-            names = assign_blocks(names, [self.awq_model.block_cost(blocks[n]) for n in names], shard[1])[shard[0]]
-        import time
-        tm = self.timings = {"capture_s": 0.0, "scale_search_s": 0.0, "clip_search_s": 0.0}
-
+        rank, world = shard if shard is not None else (0, 1)
+        ratios, wanted_by = None, None
+        mine = clip_mine = names
+        if world > 1:
+            parts, ratio_split = owners_of(names, [self.awq_model.block_cost(blocks[n]) for n in names], world)
+            if ratio_split:
+                ratios = split_ratios(20, world)[rank]
+                clip_mine = names[rank::world]
+                wanted_by = {n: list(range(world)) for n in names}
+            else:
+                mine = clip_mine = parts[rank]
+                wanted_by = {n: [r] for r, p in enumerate(parts) for n in p}
+        tm = self.timings = {"capture_s": 0.0, "scale_search_s": 0.0, "clip_search_s": 0.0, "mode": "ratio-split" if ratios is not None else "blocks",
+                             "blocks_searched": len(mine), "blocks_clipped": len(clip_mine)}
         on_gpu = next(self.awq_model.denoiser().parameters()).is_cuda
 
         def lap(key, t0):
@@ -157,32 +177,45 @@ class AwqQuantizer:
             tm[key] += time.perf_counter() - t0
 
         t0 = time.perf_counter()
-        feats = self.awq_model.capture_block_inputs(names)
+        feats = self.awq_model.capture_block_inputs(mine, shard=shard, wanted_by=wanted_by)
         lap("capture_s", t0)
+        # ---- phase A: scale search (loss tables), one collective when the ratio grid is split
+        t0 = time.perf_counter()
+        pending = {}
+        for bname in mine:
+            groups = self.awq_model.get_layers_for_scaling(blocks[bname], feats[bname]) if self.applyScale else []
+            pending[bname] = [self._scale_losses(blocks[bname], ratios=ratios, **g) for g in groups]
+        recs = [rec for bname in mine for rec in pending[bname]]
+        if ratios is not None and recs:
+            table = allreduce_min_losses(torch.stack([rec["losses"] for rec in recs]))
+            for i, rec in enumerate(recs):
+                rec["losses"] = table[i]
+        scales = {bname: [self._finish_scale(rec) for rec in pending[bname]] for bname in mine}
+        lap("scale_search_s", t0)
+        # ---- phase B: clip search on the scaled block
+        t0 = time.perf_counter()
         out = {}
-        for bname in names:
-            block = blocks[bname]
-            input_feat = feats[bname]
-            groups = self.awq_model.get_layers_for_scaling(block, input_feat)
-            t0 = time.perf_counter()
-            scales_list = [self._search_best_scale(block, **g) for g in groups] if self.applyScale else []
-            lap("scale_search_s", t0)
+        for bname in clip_mine:
+            block, input_feat, scales_list = blocks[bname], feats[bname], [r[:3] for r in scales[bname]]
             res = {"scales": scales_list, "clip": []}
-            t0 = time.perf_counter()
             if self.apply_clip:
-                # the clip search runs on the SCALED weights and inputs (quantizer.py:312-336); do that on a view
-                # of the block and roll the weights back so the gathered results can be applied once everywhere
-                named = exclude_layers_to_not_quantize(get_named_linears(block), self.modules_to_not_convert)
-                backup = {n: l.weight.data.clone() for n, l in named.items()}
+                # the clip search runs on the SCALED weights and inputs (quantizer.py:312-336); do that on the block itself
+                # and roll EVERY Linear back (apply_scale also folds into group members that are excluded from
+                # quantisation by modules_to_not_convert), so that the gathered results are applied exactly once everywhere
+                every = get_named_linears(block)
+                backup = {n: l.weight.data.clone() for n, l in every.items()}
                 prev_backup = self._snapshot_prev_ops(block, scales_list)
                 apply_scale(block, scales_list, input_feat_dict=input_feat)
+                named = exclude_layers_to_not_quantize(every, self.modules_to_not_convert)
                 res["clip"] = self._search_best_clip(block, named, input_feat)
-                for n, l in named.items():
+                for n, l in every.items():
                     l.weight.data = backup[n]
                 self._restore_prev_ops(prev_backup)
-            lap("clip_search_s", t0)
+            for prev, _, _, ratio, loss in scales[bname]:
+                self.search_log.append((prev, ratio, loss))
             out[bname] = res
             del feats[bname]
+        lap("clip_search_s", t0)
         return out
 
     def _snapshot_prev_ops(self, block, scales_list):
@@ -230,14 +263,18 @@ class AwqQuantizer:
         1x1 Conv2d layers become QConv1x1 (the same kernels on the token view), 3x3 / stride 1 / pad 1 layers QConv3x3
         (kernel c as an implicit GEMM); other convolutions keep the fake-quant path."""
         from .fake_quant import _effective_group
-        from .linear import QConv1x1, QConv3x3, W8A8Linear, conv_group, is_conv3x3_gemm, is_pointwise_conv
+        from .linear import (QConv1x1, QConv3x3, W8A8Linear, conv_group, is_conv3x3_gemm, is_pointwise_conv, w4a16_kernel_ok,
+                             w8a8_kernel_ok)
         for parent, name, layer in named_linears:
             if isinstance(layer, torch.nn.Linear):
                 if self.version == "w8a8":
+                    if not w8a8_kernel_ok(layer.in_features, layer.out_features):   # shapes kernel (d) does not tile stay fake-quant
+                        self._apply_quant_fake_act(module, [(parent, name, layer)], 8)
+                        continue
                     new = W8A8Linear.from_float(layer)
                 else:
                     g = _effective_group(layer.in_features, self.group_size) if self.group_size > 0 else layer.in_features
-                    if g % 64 or layer.out_features % 8:   # shapes the W4A16 kernel does not tile stay fake-quant
+                    if not w4a16_kernel_ok(layer.in_features, layer.out_features, g):   # e.g. group_size = -1 on K = 320
                         self._apply_quant_fake_act(module, [(parent, name, layer)], bitWidth)
                         continue
                     new = WQLinear_GEMM.from_linear(layer, bitWidth, g)
@@ -247,10 +284,10 @@ class AwqQuantizer:
                 # (SURVEY.md section 8(f) row 3); everything else keeps the fake-quant weights + cuDNN.
                 g = _effective_group(layer.in_channels, self.group_size) if self.group_size > 0 else layer.in_channels
                 if is_pointwise_conv(layer) and layer.out_channels % 8 == 0 and layer.weight.dtype != torch.float32:
-                    if self.version == "w8a8" and layer.in_channels % 16 == 0:
+                    if self.version == "w8a8" and w8a8_kernel_ok(layer.in_channels, layer.out_channels):
                         setattr(parent, name, QConv1x1.from_conv_w8a8(layer))
                         continue
-                    if self.version != "w8a8" and g % 64 == 0:
+                    if self.version != "w8a8" and w4a16_kernel_ok(layer.in_channels, layer.out_channels, g):
                         setattr(parent, name, QConv1x1.from_conv_w4a16(layer, bitWidth, g))
                         continue
                 # 3x3 / stride 1 / pad 1: packed int4 weights on the implicit-GEMM form of kernel (c)
@@ -283,7 +320,9 @@ class AwqQuantizer:
 
     # ------------------------------------------------------------------ quantizer.py:606-676
     @torch.no_grad()
-    def _search_best_scale(self, module, prev_op, layers: List[nn.Linear], inp: torch.Tensor, module2inspect=None, kwargs={}):
+    def _scale_losses(self, module, prev_op, layers: List[nn.Linear], inp: torch.Tensor, module2inspect=None, kwargs={}, ratios=None):
+        """Steps 1-4 of `_search_best_scale` up to the loss table: returns the group's record {prev, names, x_mean, w_mean,
+        losses [20] float64 on the device (inf where `ratios` left a grid point out)}."""
         if module2inspect is None:
             assert len(layers) == 1
             module2inspect = layers[0]
@@ -298,10 +337,28 @@ class AwqQuantizer:
         # [STEP 3] reference output
         fp16_output = self._module_forward(inp, module2inspect, kwargs)
         # [STEP 4] grid search
-        best_scales = self._compute_best_scale(inp, w_mean, x_mean, module2inspect, layers, fp16_output, kwargs)
+        losses = self._grid_losses(inp, w_mean, x_mean, module2inspect, layers, fp16_output, kwargs, ratios)
         from .scale import describe_prev_op
-        self.search_log.append((describe_prev_op(module, prev_op), self.last_best_ratio, float(self.last_losses.min().item())))
-        return (describe_prev_op(module, prev_op), tuple(get_op_name(module, m) for m in layers), best_scales)
+        return {"prev": describe_prev_op(module, prev_op), "names": tuple(get_op_name(module, m) for m in layers),
+                "x_mean": x_mean, "w_mean": w_mean, "losses": losses}
+
+    def _finish_scale(self, rec, n_grid=20):
+        """argmin of a (complete) loss table -> (prev_op_name, layer_names, best_scales, best_ratio, best_loss)."""
+        losses = rec["losses"]
+        best = int(torch.argmin(losses).item())   # first minimum == the reference's strict `<` (quantizer.py:739)
+        if not torch.isfinite(losses[best]):
+            logging.debug(losses.tolist())
+            raise Exception
+        best_scales = self._ratio_scales(rec["x_mean"].view(-1), rec["w_mean"].view(-1), best / n_grid)
+        assert torch.isnan(best_scales).sum() == 0, best_scales
+        self.last_losses, self.last_best_ratio = losses, best / n_grid
+        return (rec["prev"], rec["names"], best_scales.detach(), best / n_grid, float(losses[best].item()))
+
+    @torch.no_grad()
+    def _search_best_scale(self, module, prev_op, layers: List[nn.Linear], inp: torch.Tensor, module2inspect=None, kwargs={}):
+        prev, names, best_scales, ratio, loss = self._finish_scale(self._scale_losses(module, prev_op, layers, inp, module2inspect, kwargs))
+        self.search_log.append((prev, ratio, loss))
+        return (prev, names, best_scales)
 
     # ------------------------------------------------------------------ quantizer.py:678-751
     def _ratio_scales(self, x_mean, w_mean, ratio):
@@ -316,23 +373,19 @@ class AwqQuantizer:
         return scales
 
     @torch.no_grad()
-    def _compute_best_scale(self, x, w_mean, x_mean, module2inspect, linears2scale: List[nn.Linear], fp16_output, kwargs: Dict = {},
-                            ratios=None):
-        """L(s) = || Q(W * s) (s^-1 * X) - W * X ||; returns best_scales [K] on the device.
-        `ratios` restricts the grid (ratio-sharded search, dist.py); the loss vector is kept in `self.last_losses`."""
-        n_grid = 20
+    def _grid_losses(self, x, w_mean, x_mean, module2inspect, linears2scale: List[nn.Linear], fp16_output, kwargs: Dict = {},
+                     ratios=None, n_grid=20):
+        """L(s) = || Q(W * s) (s^-1 * X) - W * X || for the grid points in `ratios` (default: all 20) -> float64 [20]
+        on the device, inf elsewhere and where the loss is NaN."""
         ratios = list(range(n_grid)) if ratios is None else list(ratios)
         x_mean, w_mean = x_mean.view(-1), w_mean.view(-1)
         org = [fc.weight.data for fc in linears2scale]
         scratch = [torch.empty_like(w) for w in org]
         losses = torch.full((n_grid,), float("inf"), dtype=torch.float64, device=x.device)
-        cand = {}
         g = self._g(org[0].shape[1])
         try:
             for i in ratios:
-                scales = self._ratio_scales(x_mean, w_mean, i / n_grid)
-                cand[i] = scales
-                s_w = scales.to(org[0].dtype)
+                s_w = self._ratio_scales(x_mean, w_mean, i / n_grid).to(org[0].dtype)
                 for fc, w, buf in zip(linears2scale, org, scratch):
                     # Q(W * s) / s in one kernel (quantizer.py:727-730)
                     ops.quant_group(w, g, 4, zero_point=self.zero_point, pre_mul=s_w, post_div=s_w, want_scales=False, out=buf)
@@ -342,16 +395,14 @@ class AwqQuantizer:
         finally:
             for fc, w in zip(linears2scale, org):
                 fc.weight.data = w
-        losses = torch.where(torch.isnan(losses), torch.full_like(losses, float("inf")), losses)
-        self.last_losses = losses
-        best = int(torch.argmin(losses).item())   # first minimum == the reference's strict `<` (quantizer.py:739)
-        if not torch.isfinite(losses[best]) or best not in cand:
-            logging.debug(losses.tolist())
-            raise Exception
-        best_scales = cand[best]
-        assert torch.isnan(best_scales).sum() == 0, best_scales
-        self.last_best_ratio = best / n_grid
-        return best_scales.detach()
+        return torch.where(torch.isnan(losses), torch.full_like(losses, float("inf")), losses)
+
+    @torch.no_grad()
+    def _compute_best_scale(self, x, w_mean, x_mean, module2inspect, linears2scale: List[nn.Linear], fp16_output, kwargs: Dict = {},
+                            ratios=None):
+        """quantizer.py:678-751: returns best_scales [K] on the device; the loss vector is kept in `self.last_losses`."""
+        losses = self._grid_losses(x, w_mean, x_mean, module2inspect, linears2scale, fp16_output, kwargs, ratios)
+        return self._finish_scale({"prev": None, "names": (), "x_mean": x_mean, "w_mean": w_mean, "losses": losses})[2]
 
     @torch.no_grad()
     def _compute_loss(self, fp16_output, int_w_output, device=None):

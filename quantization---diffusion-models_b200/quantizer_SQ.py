@@ -52,7 +52,13 @@ class SqQuantizer(AwqQuantizer):
 
     # ------------------------------------------------------------------ quantizer_SQ.py:323-391
     @torch.no_grad()
-    def quantize(self, debugSavePath=None, debugPlot=False, samples=None):
+    def quantize(self, debugSavePath=None, debugPlot=False, samples=None, shard=None):
+        """shard = (rank, world): the calibration batches are run data parallel (batch i on rank i % world) with the fused
+        one-pass hooks, and ONE exact fp64 all_reduce of their accumulators (dist.allreduce_hook_stats) gives every rank
+        the statistic of the whole calibration set: smoothing scales and codes are identical for every world size."""
+        rank, world = shard if shard is not None else (0, 1)
+        if world > 1:
+            self.fused_stats = True   # per-call tensors cannot be merged across ranks; the fp64 accumulators can, exactly
         smoothing_blocks = self.awq_model.get_smoothing_blocks()
         hook_d = self.apply_hooks_to_smoothing_blocks(smoothing_blocks)
         pipe = self.awq_model.get_pipeline()
@@ -60,7 +66,10 @@ class SqQuantizer(AwqQuantizer):
             samples = get_calib_dataset_dm(model_pipeline=pipe, text_dataset=self.calib_prompts,
                                            batch_size=self.calib_batch_size, n_samples=self.calib_n_samples, seed=42,
                                            device=pipe.device, split="test", text_column="txt")
-        run_calibration(pipe, samples, None, self.calib_num_infer_steps)
+        run_calibration(pipe, samples[rank::world] if world > 1 else samples, None, self.calib_num_infer_steps)
+        if world > 1:
+            from .dist import allreduce_hook_stats
+            allreduce_hook_stats(hook_d)
         for block_name, block_module in smoothing_blocks.items():
             for group in self.awq_model.get_layers_for_scaling_unet(block_module, hook_d[block_name]):
                 s = self.smooth_ln_fcs(group['prev_op'], group['layers'], group['activations_max'][0], alpha=self.alpha)

@@ -258,6 +258,21 @@ class AdaLayerNormZero(nn.Module):
         return self.norm(x) * (1 + scale[:, None]) + shift[:, None], parts[2:]
 
 
+class AdaLayerNormContinuous(nn.Module):
+    """diffusers AdaLayerNormContinuous (the MMDiT's `norm_out` and the `norm1_context` of the last, context_pre_only
+    block): one modulation Linear [2D, D] whose output is chunked as (SCALE, SHIFT) -- the opposite order of
+    AdaLayerNormZero's (shift, scale, gate, ...)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.linear = nn.Linear(dim, 2 * dim)
+        self.norm = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+
+    def forward(self, x, emb):
+        scale, shift = self.linear(F.silu(emb)).chunk(2, dim=1)
+        return self.norm(x) * (1 + scale[:, None]) + shift[:, None], ()
+
+
 class JointAttention(nn.Module):
     def __init__(self, dim, heads, context_pre_only):
         super().__init__()
@@ -284,7 +299,7 @@ class JointTransformerBlock(nn.Module):
         super().__init__()
         self.context_pre_only = context_pre_only
         self.norm1 = AdaLayerNormZero(dim, 6)
-        self.norm1_context = AdaLayerNormZero(dim, 2 if context_pre_only else 6)
+        self.norm1_context = AdaLayerNormContinuous(dim) if context_pre_only else AdaLayerNormZero(dim, 6)
         self.attn = JointAttention(dim, heads, context_pre_only)
         self.norm2 = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
         self.ff = FeedForward(dim, 4, geglu=False)
@@ -336,7 +351,7 @@ class MMDiTSkeleton(nn.Module):
         self.context_embedder = nn.Linear(ctx_in, dim)
         self.transformer_blocks = nn.ModuleList(
             [JointTransformerBlock(dim, heads, context_pre_only=(i == layers - 1)) for i in range(layers)])
-        self.norm_out = AdaLayerNormZero(dim, 2)
+        self.norm_out = AdaLayerNormContinuous(dim)
         self.proj_out = nn.Linear(dim, patch * patch * in_ch)
 
     def forward(self, x, t, context, pooled):
