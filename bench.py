@@ -89,6 +89,26 @@ def layer_list():
     return shapes, shapes.sd15_unet_linears(batch=8, cfg=True)
 
 
+def per_shape_roofline_ms(shapes, layers, peaks):
+    """sum over the step's launches of max(flops / tensor peak, algorithmic bytes / HBM peak), in ms"""
+    tot = 0.0
+    for _, m, n, k, c in layers:
+        by = shapes.gemm_bytes_w4a16(m, n, k, shapes.group_for(k))
+        tot += c * max(2.0 * m * n * k / (peaks["bf16_burst"] * 1e12), by / (peaks["hbm"] * 1e9))
+    return tot * 1e3
+
+
+def workload_config(shapes, layers, world):
+    """`config` of the JSON line -- identical for the GPU arm and the reference arm (the reference arm times a bounded
+    sample of this workload; what the sample was is said in its `cpu_baseline.sample`)."""
+    return {"workload": "sd15_unet_w4a16_linears_b8cfg",
+            "reference_config": "SD1.5 UNet W4A16 AWQ group-128, 512x512 latents batch 8 (CFG -> B_eff 16)",
+            "linear_calls_per_step": sum(c for *_, c in layers), "distinct_shapes": len(layers),
+            "tflop_per_step": shapes.total_flops(layers) / 1e12, "group_size": "128 (64 where K=320)",
+            "l2": "per-step working set (>1.5 GB of activations + 184 distinct weights) exceeds the 126 MB L2",
+            "parallelism": f"dp{world} (prompt-batched, no collective in the step)"}
+
+
 # ------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference(sample_budget_s=20.0, steps=1, warmup=0):
     """The reference's CPU torch path for this workload: F.linear(x, W_fakequant, bias) in fp32 math on all
@@ -129,11 +149,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_reference(sample_budget_s=60.0, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    shapes, layers = layer_list()
+    cb = cpu_reference(sample_budget_s=120.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["passes"],
-            "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "sd15_unet_w4a16_linears_b8cfg", "sample": cb["sample"]},
+            "config": workload_config(shapes, layers, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -158,6 +179,156 @@ def build_layers(q, shapes, layers, dev, dtype):
             mods.append((name, lin.WQLinear_GEMM.from_linear(fl, 4, shapes.group_for(k)), (m, k)))
             del fl
     return xs, mods
+
+
+
+# ------------------------------------------------------------------------------------------ sub-records of the bench line
+def _graph_of(torch, fn):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def int8_dense_peak(torch, dev):
+    """Dense INT8 tensor-pipe peak of this GPU (BASELINE.md section 3 asks for a measured denominator of W8A8): cuBLASLt
+    int8 x int8 -> int32 through torch._int_mm on 8192^3, best of 10 (burst) -- the same protocol as MEASURED_PEAKS'
+    bf16 number.  None if the library path is unavailable."""
+    try:
+        n = 8192
+        a = torch.randint(-8, 8, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-8, 8, (n, n), dtype=torch.int8, device=dev).t().contiguous().t()   # column-major operand
+        for _ in range(3):
+            torch._int_mm(a, b)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / best / 1e9
+    except Exception:
+        return None
+
+
+def sub_w8a8(q, shapes, layers, dev, dtype, steps, warmup, timed):
+    """Kernel (d) on the same workload: every Linear call of the step through W8A8Linear.forward = per-token int8
+    quantiser (qdm_actquant_token_i8) + int8 tcgen05 GEMM with the dequant scales in the epilogue; one CUDA graph.
+    Also the GEMMs alone on pre-quantised activations, and the measured INT8 dense peak as the roofline denominator."""
+    import torch
+    lin = importlib.import_module("quantization---diffusion-models_b200.linear")
+    g = torch.Generator(device=dev).manual_seed(43)
+    xs, mods = {}, []
+    for name, m, n, k, cnt in layers:
+        if k % 16:
+            continue
+        if (m, k) not in xs:
+            xs[(m, k)] = torch.randn(m, k, generator=g, device=dev, dtype=dtype)
+        for _ in range(cnt):
+            fl = torch.nn.Linear(k, n, bias=True, device=dev, dtype=dtype)
+            fl.weight.data = torch.randn(n, k, generator=g, device=dev, dtype=dtype) * 0.02
+            mods.append((lin.W8A8Linear.from_float(fl), (m, k)))
+            del fl
+    flops = sum(2.0 * key[0] * mod.out_features * key[1] for mod, key in mods)
+
+    def step():
+        for mod, key in mods:
+            mod(xs[key])
+
+    pre = {key: q.ops.actquant_token_i8(x) for key, x in xs.items()}
+
+    def step_gemm_only():
+        for mod, key in mods:
+            xq, sx = pre[key]
+            q.ops.gemm_w8a8(xq, sx, mod.qweight, mod.w_scales, mod.bias, out_dtype=mod.out_dtype)
+
+    q.ops.launch_count(reset=True)
+    step()
+    launches = q.ops.launch_count()
+    ms = timed(_graph_of(torch, step).replay, steps, warmup) / steps
+    ms_g = timed(_graph_of(torch, step_gemm_only).replay, steps, warmup) / steps
+    peak = int8_dense_peak(torch, dev)
+    tf, tf_g = flops / ms / 1e9, flops / ms_g / 1e9
+    return {"tflops": tf, "ms_per_step": ms, "gemm_only_tflops": tf_g, "gemm_only_ms_per_step": ms_g, "launches_per_step": launches,
+            "tflop_per_step": flops / 1e12, "int8_dense_peak_tops": peak, "peak_how": "torch._int_mm (cuBLASLt int8) 8192^3, best of 10, this run",
+            "frac_of_int8_peak": (tf_g / peak) if peak else None,
+            "what": "W8A8Linear.forward over the step's Linear calls: qdm_actquant_token_i8 + qdm_gemm_w8a8 (quantize/fake_quant.py:86-118)"}
+
+
+def sub_denoise(args, dev, rank, world, sync_max):
+    """BASELINE config 2: SD1.5 UNet skeleton, W4A16 AWQ g128, 512^2 latents batch 8 + CFG, 50-step loop through generate();
+    prompt-batched data parallel, no collective in the loop.  it/s = denoise steps per second per replica."""
+    import torch
+    M = importlib.import_module("quantization---diffusion-models_b200.models")
+    q = importlib.import_module("quantization---diffusion-models_b200")
+    model = M.StableDiffusion1_x.from_skeleton(device=dev)
+    model.quantize(quant_config={"zero_point": True, "q_group_size": 128, "w_bit": 4, "version": "gemm"}, quantType="awq")
+    batch, steps = 8, 50
+    prompts = [f"prompt {rank}-{i}" for i in range(batch)]
+    lat = torch.randn(batch, 4, 64, 64, generator=torch.Generator().manual_seed(42 + rank)).to(dev, model.pipeline.dtype)
+    model.generate(prompts, lat=lat, num_inference_steps=2)
+    sync_max(0.0)
+    q.ops.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = model.generate(prompts, lat=lat, num_inference_steps=steps)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = sync_max(e0.elapsed_time(e1) * 1e-3)
+    out = {"it_per_s": steps / sec, "images_it_per_s": world * batch * steps / sec, "steps": steps, "batch_per_gpu": batch, "quant": "w4a16 g128",
+           "seconds": sec, "finite": bool(torch.isfinite(res).all()), "libqdm_launches": q.ops.launch_count(),
+           "model": "SD1.5 UNet skeleton (random init), packed Linears + 1x1 / 3x3 convolutions", "scaling": "weak (data parallel, no collective in the loop)"}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def sub_calib(args, dev, rank, world, sync_max, model_name="sd35", blocks=0, calib_batches=8, calib_steps=2):
+    """BASELINE config 4: AWQ calibration (capture, 20-point scale search, clip search, quantise + pack) of the SD3.5-Large
+    MMDiT skeleton (38 blocks, 8.05 G Linear parameters), sharded over the ranks: data-parallel capture, block-sharded
+    search, one gather.  codes_checksum covers qweight / qzeros / scales of every packed Linear: equal across world sizes
+    = bit-identical codes."""
+    import torch
+    M = importlib.import_module("quantization---diffusion-models_b200.models")
+    cls = {"sd15": M.StableDiffusion1_x, "sdxl": M.StableDiffusionXL, "sd35": M.StableDiffusion3_5}[model_name]
+    arch = {"layers": blocks} if (model_name == "sd35" and blocks) else {}
+    t0 = time.perf_counter()
+    model = cls.from_skeleton(device=dev, **arch)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    batch = {"sd15": 8, "sdxl": 4, "sd35": 1}[model_name]
+    model.calib_samples = model.default_calib_samples(calib_batches, batch)
+    model.calib_steps = calib_steps
+    sync_max(0.0)
+    t0 = time.perf_counter()
+    model.quantize(quant_config={"zero_point": True, "q_group_size": 128, "w_bit": 4, "version": "gemm"}, quantType="awq",
+                   calibrate=True, shard=(rank, world) if world > 1 else None)
+    torch.cuda.synchronize()
+    sec = sync_max(time.perf_counter() - t0)
+    chk, n_mod = 0, 0
+    for name, mod in model.denoiser().named_modules():
+        if type(mod).__name__ == "WQLinear_GEMM":
+            n_mod += 1
+            for t in (mod.qweight, mod.qzeros, mod.scales.view(torch.int16)):
+                chk = (chk * 1000003 + int(t.to(torch.int64).sum().item()) + t.numel()) % (1 << 61)
+    tm = dict(getattr(model.quantizer, "timings", {}) or {})
+    for k in ("capture_s", "scale_search_s", "clip_search_s"):
+        if k in tm:
+            tm[k] = sync_max(tm[k])
+    out = {"s_per_model": sec, "model": {"sd35": "SD3.5-Large MMDiT skeleton", "sd15": "SD1.5 UNet skeleton", "sdxl": "SDXL UNet skeleton"}[model_name],
+           "blocks": len(model.get_search_blocks()), "packed_modules": n_mod, "codes_checksum": chk, "phases_max_over_ranks": tm,
+           "calib_batches": calib_batches, "calib_steps": calib_steps, "calib_batch": batch, "world": world, "build_s": build_s,
+           "collectives": "capture exchange (P2P) + one all_gather of {scales, clip}" if world > 1 else "none"}
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -288,6 +459,39 @@ def run_ours(args):
     ms_e2e = timed(run_e2e, args.steps, max(1, args.warmup // 2)) / args.steps
     e2e_value = world * flops_step / (ms_e2e * 1e-3) / 1e12
 
+    # ---- the other BASELINE metrics as sub-records of the same line (every rank takes part: they shard / run data parallel)
+    def sync_max(x):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return x
+
+    variants = {}
+    for _, mod, key in mods:   # which kernel each Linear call of the step runs (dispatch is shape dependent)
+        mod(xs[key])
+        v, tile = q.ops.gemm_last_variant()
+        variants[v] = variants.get(v, 0) + 1
+    del graph, mods
+    if not args.no_graph:
+        del graph_e2e
+    torch.cuda.empty_cache()
+    extra = {}
+    if not args.no_extras:
+        for name, fn in (("w8a8", lambda: sub_w8a8(q, shapes, layers, dev, dtype, args.steps, args.warmup, timed)),
+                         ("denoise", lambda: sub_denoise(args, dev, rank, world, sync_max)),
+                         ("calib", lambda: sub_calib(args, dev, rank, world, sync_max, blocks=args.blocks))):
+            try:
+                extra[name] = fn()
+            except Exception as e:   # a sub-record must never take the headline metric down with it
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    raise
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -298,23 +502,24 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": "sd15_unet_w4a16_linears_b8cfg", "reference_config": "SD1.5 UNet W4A16 AWQ group-128, 512x512 latents batch 8 (CFG -> B_eff 16)",
-                   "linear_calls_per_step": n_calls, "distinct_shapes": len(layers), "tflop_per_step": flops_step / 1e12,
-                   "group_size": "128 (64 where K=320)", "l2": "per-step working set (>1.5 GB of activations + 184 distinct weights) exceeds the 126 MB L2",
-                   "launch": "eager" if graph is None else "one CUDA graph of the step's 184 launches",
-                   "parallelism": f"dp{world} (prompt-batched, no collective in the step)"},
+        "config": workload_config(shapes, layers, world),
+        "launch": "eager" if args.no_graph else "one CUDA graph of the step's 184 launches",
         "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": step_traffic(),
-                     "kernel": "W4A16 family: qdm_gemm2_kernel<256, G_W4, fp16, raw-TMA> (120 launches), qdm_gemm2_bstat_kernel (35, K = 320), "
-                               "qdm_gemm2_sk_kernel (5, stream-K), w4a16_smallm_kernel (24, M = 16)",
-                     "peak_kind": "bf16 cuBLAS sustained, " + peaks["source"],
+        # the timed region is short (0.1 s at full clocks, far below the power cap), so the honest denominator is the BURST
+        # cuBLAS bf16 peak; frac_sustained and the per-shape roofline (65 of the 184 launches are HBM-bound shapes) beside it
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_burst"], "traffic": step_traffic(),
+                     "frac_sustained_peak": achieved / peaks["bf16_sustained"],
+                     "frac_per_shape_roofline": per_shape_roofline_ms(shapes, layers, peaks) / ms_step,
+                     "kernel": "W4A16 family, launches per step by kernel: " + json.dumps(variants),
+                     "peak_kind": "bf16 cuBLAS burst, " + peaks["source"],
                      "note": "2*M*N*K summed over the step's 184 launches / CUDA-event time of the step (one CUDA graph); traffic = DRAM read+write "
-                             "bytes of the same 184 launches from the committed ncu launch list (profiles/step_traffic_r01.json; algorithmic bytes "
-                             "9.87 GB per step); 65 launches (K or N = 320) are HBM-bound shapes, per-shape roofline in profiles/README.md"},
+                             "bytes of the same 184 launches from the committed ncu launch list (algorithmic bytes 9.87 GB per step); "
+                             "frac_per_shape_roofline = sum over launches of max(flops / burst peak, algorithmic bytes / measured HBM) / step time"},
         "clocks": clocks,
     }
+    line.update(extra)
     if world == 1:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference(20.0).items() if k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
@@ -683,6 +888,7 @@ def main():
     ap.add_argument("--layers", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the w8a8 / denoise / calib sub-records of the line")
     ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn", "kernels", "conv"])
     ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl", "sd35"])
     ap.add_argument("--quant", default="w4a16", choices=["fp16", "w4a16", "w8a8"])

@@ -106,6 +106,22 @@ size_t qdm_sqdiff_workspace_bytes(int64_t numel);
 int qdm_sqdiff_sum(const void* a, const void* b, int dtype, int64_t numel, double* out,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* AWQ clip search, AwqQuantizer._compute_best_clip (quantize/quantizer.py:805-863), one call per Linear:
+ *   for every out-row r and group g:  org = max |w[r, g]|;  for i in 0 .. int(max_shrink * n_grid) - 1:
+ *     max_i = org * (1 - i / n_grid);  q_i = pseudo_quantize(clamp(w[r, g], -max_i, max_i))   (bit-exact RTN chain)
+ *     err_i = mean_t ( sum_k x[t, g, k] * (q_i[k] - w[r, g, k]) )^2
+ *   best_max[r, g] = max_i of the FIRST minimal err_i (strict <, :851).
+ * The reference forms co_b x n_tok x K products eleven times per batch of rows; here err_i = d^T C_g d with the group's
+ * g x g Gram matrix C_g = X_g^T X_g / n_tok (built once per call in `workspace`, fp32) -- no temporaries, g^2 instead of
+ * n_tok * g multiply-adds per (row, group, level).  x: [n_tok, ci] rows of `ld_x` elements (the caller passes the token
+ * subsample of :822-823 as a strided view), w: [co, ci] row-major, best_max: [co, ci / group] dtype.
+ * group in {64, 128}; flags: QDM_Q_ZERO_POINT or 0; n_bits 2..8.  The quadratic form is fp32 whereas the reference
+ * rounds products and sums to fp16, so near-ties may resolve to the neighbouring level (tests bound agreement and loss). */
+size_t qdm_awq_clip_workspace_bytes(int64_t ci, int group);
+int qdm_awq_clip_search(const void* w, int dtype, int64_t co, int64_t ci, int group, int n_bits, unsigned flags,
+                        const void* x, int64_t n_tok, int64_t ld_x, int n_grid, float max_shrink,
+                        void* best_max, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ (b) quantize / pack */
 
 /* Per-group RTN.  w is [n_rows, k_cols] row-major, groups of `group` consecutive

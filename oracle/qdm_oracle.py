@@ -97,6 +97,19 @@ def rtn_nchw_channel(t, n_bits=8):
     return (t / s).round().mul(s).to(t.dtype)
 
 
+def rtn_nchw_patch(t, group_size=128, n_bits=8):
+    """quantize_activation_per_channel_group_absmax, fake_quant.py:134-153: one scale per (n, c, square spatial patch);
+    the patch edge shrinks by 2 until it divides H and W (:140-141)."""
+    n, c, h, w = t.shape
+    while h % group_size != 0 or w % group_size != 0:
+        group_size -= 2
+    g = group_size
+    p = t.reshape(n, c, h // g, g, w // g, g).permute(0, 1, 2, 4, 3, 5)            # [N, C, H/g, W/g, g, g] (the unfold view)
+    s = torch.amax(p.abs(), dim=(4, 5), keepdim=True).clamp(min=1e-5) / (2 ** (n_bits - 1) - 1)
+    q = p.div(s).round().mul(s)
+    return q.permute(0, 1, 2, 4, 3, 5).reshape(n, c, h, w).to(t.dtype)
+
+
 # ------------------------------------------------------------------ A15 int4 AWQ GEMM layout
 def awq_pack(codes_kn):
     """codes [K, N] (0..15) -> int32 [K, N/8]; nibble i of a word = column 8c + AWQ_ORDER[i]
@@ -190,7 +203,10 @@ def awq_search_scale(x, weights, forward, group_size=128, zero_point=True, n_bit
 
 
 # ------------------------------------------------------------------ A11 quantizer.py:805-863
-def awq_search_clip(w, x, group_size=128, zero_point=True, n_bits=4, n_grid=20, max_shrink=0.5, n_sample_token=512):
+def awq_search_clip(w, x, group_size=128, zero_point=True, n_bits=4, n_grid=20, max_shrink=0.5, n_sample_token=512,
+                    return_levels=False):
+    """return_levels: also ([levels, co, G] candidate max values, [levels, co, G] errors) as the reference computes them
+    (tests use them to judge a near-tie: is the level another implementation picked as good as the best one?)."""
     co = w.shape[0]
     gs = group_size if group_size > 0 else w.shape[1]
     x = x.view(-1, x.shape[-1]).reshape(1, -1, w.shape[1] // gs, gs)
@@ -198,13 +214,14 @@ def awq_search_clip(w, x, group_size=128, zero_point=True, n_bits=4, n_grid=20, 
     w4 = w.reshape(co, 1, -1, gs)
     bs = 256 if co % 256 == 0 else 64
     assert co % bs == 0
-    outs = []
+    outs, lv_max, lv_err = [], [], []
     for b in range(co // bs):
         wb = w4[b * bs:(b + 1) * bs]
         org_max = wb.abs().amax(dim=-1, keepdim=True)
         best_max = org_max.clone()
         min_errs = torch.ones_like(org_max) * 1e9
         org_out = (x * wb).sum(dim=-1)
+        ms, es = [], []
         for i_s in range(int(max_shrink * n_grid)):
             max_val = org_max * (1 - i_s / n_grid)
             cur = torch.clamp(wb, -max_val, max_val)
@@ -213,8 +230,13 @@ def awq_search_clip(w, x, group_size=128, zero_point=True, n_bits=4, n_grid=20, 
             better = err < min_errs
             min_errs[better] = err[better]
             best_max[better] = max_val[better]
+            ms.append(max_val.squeeze(1).squeeze(-1)), es.append(err.squeeze(1).squeeze(-1))
         outs.append(best_max)
-    return torch.cat(outs, dim=0).squeeze(1)
+        lv_max.append(torch.stack(ms)), lv_err.append(torch.stack(es))
+    best = torch.cat(outs, dim=0).squeeze(1)
+    if return_levels:
+        return best, torch.cat(lv_max, dim=1), torch.cat(lv_err, dim=1)
+    return best
 
 
 def apply_clip(w, max_val):

@@ -43,6 +43,8 @@ SIGNATURES = {
     "qdm_awq_wsum": (c_int, [_P, _I, _L, _L, _I, _P, _P, _Z, _P]),
     "qdm_sqdiff_workspace_bytes": (c_size_t, [_L]),
     "qdm_sqdiff_sum": (c_int, [_P, _P, _I, _L, _P, _P, _Z, _P]),
+    "qdm_awq_clip_workspace_bytes": (c_size_t, [_L, _I]),
+    "qdm_awq_clip_search": (c_int, [_P, _I, _L, _L, _I, _I, _U, _P, _L, _L, _I, ctypes.c_float, _P, _P, _Z, _P]),
     "qdm_quant_group": (c_int, [_P, _I, _L, _L, _I, _I, _U, _P, _P, _P, _P, _P, _P, _P, _P]),
     "qdm_quant_rowwise": (c_int, [_P, _I, _L, _L, _I, _U, _P, _P, _P, _P, _P]),
     "qdm_quant_tensor_workspace_bytes": (c_size_t, [_L]),

@@ -1551,12 +1551,26 @@ int g_force_ctas = 0;
 int g_force_tile = 0;   // with 16 / 32: sub-tile width override (multiple of 32), 0 = cost model
 bool g_no_rp = false;   // mode 64: the heuristics of the non-repacked kernels, as if no blob had been passed
 
-// Repacked-weight kernel (qdm_gemm_w4rp.cu): pick the number of sub-tiles per CTA pair and their width.  Cycles per
-// k-block of a pair: tensor pipe 2 W (W = subs * sub_n columns), operand delivery ~430 (the A box: 128 rows per CTA)
-// + ~0.5 W (blob bytes); a single-buffered wide tile (subs = 2) adds its epilogue to every tile, a double-buffered one
-// only to the last.  Tiles past N cost like full ones, so waste shows up through the wave count.
-void choose_rp(int64_t M, int64_t N, int64_t K, int* subs_out, int* sub_n_out, double* cost_out) {
+// Repacked-weight kernel (qdm_gemm_w4rp.cu): when is it taken, and with which tile?  Measured (profiles/README.md, round 2):
+// reading the packed operand as one bulk copy per tile part instead of three tensor-map loads does not change the
+// k-block period (the pipeline is bound by shared-memory traffic: A written + read, B written by the dequant warps + read),
+// so the one-sub-tile form ties with the AWQ-tensor kernel; the two-sub-tile form (256 x up to 512 columns, all of TMEM
+// as ONE accumulator set) wins exactly when it turns a two-wave problem into ONE wave -- 4096 x 1280 x 1280: 144 tiles of
+// 256 x 144 on 74 pairs -> 64 tiles of 256 x 320, 23.2 -> 20.5 us; 4096 x 1280 x 5120: 60.8 (stream-K) -> 53.9 us -- and
+// loses when two or more waves remain (its epilogue does not overlap the next tile's main loop).  Forced modes (16 / 32)
+// keep a cost model over all widths for A/B timing.
+bool choose_rp(int64_t M, int64_t N, int64_t K, int* subs_out, int* sub_n_out) {
   const int64_t P = QDM_NUM_SMS / 2, m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_kb = K / 64;
+  if (g_force_ctas == 0) {
+    const int tn_old = choose_tile_n(M, N, 2);
+    if (m_tiles * ((N + tn_old - 1) / tn_old) <= P) return false;          // already one wave of whole tiles
+    for (int sn = 32; sn <= 256; sn += 32) {                                // narrowest two-sub-tile width that is one wave
+      const int W = 2 * sn;
+      if (W - sn >= N) break;
+      if (m_tiles * ((N + W - 1) / W) <= P) { *subs_out = 2; *sub_n_out = sn; return true; }
+    }
+    return false;
+  }
   double best = 1e300;
   int bs = 1, bn = 256;
   for (int subs = 1; subs <= 2; ++subs) {
@@ -1575,8 +1589,9 @@ void choose_rp(int64_t M, int64_t N, int64_t K, int* subs_out, int* sub_n_out, d
     }
   }
   *subs_out = bs; *sub_n_out = bn;
-  if (cost_out) *cost_out = best;
+  return true;
 }
+
 bool use_pair(const GemmParams& p) {
   if (g_force_ctas == 1) return false;
   if (g_force_ctas >= 2 && g_force_ctas <= 8) return true;
@@ -1791,9 +1806,8 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
       const int64_t m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + tn - 1) / tn, max_pairs = QDM_NUM_SMS / 2;
       bstat = n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs;
     }
-    if (!bstat) {
-      int subs = 1, sub_n = 256;
-      choose_rp(M, N, K, &subs, &sub_n, nullptr);
+    int subs = 1, sub_n = 256;
+    if (!bstat && choose_rp(M, N, K, &subs, &sub_n)) {
       note_variant(subs == 2 ? QDM_GEMM_RP2 : QDM_GEMM_RP1, subs * sub_n);
       return qdm_w4rp_gemm(x, blob, bias, y, dtype == QDM_BF16, M, N, K, subs, sub_n, (cudaStream_t)stream);
     }

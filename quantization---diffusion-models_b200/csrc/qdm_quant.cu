@@ -1058,6 +1058,143 @@ int launch_quant(const T* w, int64_t n_groups, int64_t group, int64_t k_period, 
   return QDM_OK;
 }
 
+
+// ---------------------------------------------------------------- AWQ clip search (quantize/quantizer.py:805-863)
+// For every (out-row, group) the reference tries 10 shrink levels max_i = org_max * (1 - i/20), quantises the clamped
+// group and keeps the level with the smallest  err_i = mean_tok ( sum_k x[t,k] q_i[k]  -  sum_k x[t,k] w[k] )^2 .
+// It materialises co_b x n_tok x K products eleven times per batch of rows.  By linearity
+//     err_i = d_i^T C d_i ,   d_i = q_i - w ,   C = X_g^T X_g / n_tok   (the group's g x g Gram matrix, fp32),
+// and C does not depend on the out-row: one small pass over the sampled activations builds all G Gram matrices
+// (group_gram_kernel), and the search itself (awq_clip_kernel) then costs g^2 FMAs per (row, group, level) instead of
+// n_tok * g -- 4x fewer for n_tok = 512, g = 128 -- with no temporaries at all.  Q_i is the bit-exact RTN chain of this
+// file; the quadratic form is fp32 (the reference rounds products and sums to fp16, so near-ties may pick the
+// neighbouring level: tests bound the agreement and the loss ratio).
+//
+// awq_clip_kernel: CTA = one group (its Gram matrix in shared memory, transposed access C[k][j] is conflict free since C is
+// symmetric) x a range of out-rows; warp = one row at a time, lane = E = g / 32 consecutive k.  Phase 1 computes the ten
+// d_i (kept in registers and written k-major to a per-warp shared tile), phase 2 accumulates y_i = C d_i for all ten
+// levels at once (per k: one 16-byte load of C, three broadcast loads of d, 10 E FMAs), phase 3 reduces d_i . y_i.
+constexpr int kClipLevels = 10;
+constexpr int kClipDPad = 12;        // floats per k row of the per-warp d tile (10 levels + pad: 16-byte aligned rows)
+constexpr int kClipWarps = 8;
+
+template <typename T, int GS>
+__global__ void __launch_bounds__(256)
+group_gram_kernel(const T* __restrict__ x, int64_t n_tok, int64_t ld, float* __restrict__ gram) {
+  // grid (G, GS / 16): block = group g, 16 rows a of its Gram matrix; thread = (a, 8 columns b)
+  constexpr int CH = 32;                             // tokens staged per step
+  __shared__ float xs[CH][GS + 1];
+  const int g = blockIdx.x, a = blockIdx.y * 16 + (threadIdx.x >> 4), b0 = (threadIdx.x & 15) * (GS / 16);
+  float acc[GS / 16];
+#pragma unroll
+  for (int j = 0; j < GS / 16; ++j) acc[j] = 0.f;
+  for (int64_t t0 = 0; t0 < n_tok; t0 += CH) {
+    for (int i = threadIdx.x; i < CH * GS; i += 256) {
+      const int tt = i / GS, c = i % GS;
+      xs[tt][c] = (t0 + tt < n_tok) ? ElemTraits<T>::to_f(x[(t0 + tt) * ld + int64_t(g) * GS + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int tt = 0; tt < CH; ++tt) {
+      const float xa = xs[tt][a];
+#pragma unroll
+      for (int j = 0; j < GS / 16; ++j) acc[j] = __fmaf_rn(xa, xs[tt][b0 + j], acc[j]);
+    }
+    __syncthreads();
+  }
+  const float inv = 1.f / float(n_tok);
+#pragma unroll
+  for (int j = 0; j < GS / 16; ++j) gram[(int64_t(g) * GS + a) * GS + b0 + j] = acc[j] * inv;
+}
+
+template <typename T, int GS, bool ZP>
+__global__ void __launch_bounds__(32 * kClipWarps)
+awq_clip_kernel(const T* __restrict__ w, int64_t co, int64_t ci, const float* __restrict__ gram, float max_int, float min_int,
+                int n_grid, int n_levels, int rows_per_cta, T* __restrict__ best_max) {
+  constexpr int E = GS / 32;
+  extern __shared__ float clip_smem[];
+  float* C = clip_smem;                                       // [GS][GS]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dT = clip_smem + GS * GS + warp * (GS * kClipDPad);  // [GS][kClipDPad], this warp's
+  const int g = blockIdx.x, G = int(ci / GS);
+  for (int i = threadIdx.x; i < GS * GS / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(C)[i] = reinterpret_cast<const float4*>(gram + int64_t(g) * GS * GS)[i];
+  __syncthreads();
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_cta, r1 = min(co, r0 + rows_per_cta);
+  for (int64_t r = r0 + warp; r < r1; r += kClipWarps) {
+    float wv[E];
+    {
+      const T* p = w + r * ci + int64_t(g) * GS + lane * E;
+#pragma unroll
+      for (int e = 0; e < E; ++e) wv[e] = ElemTraits<T>::to_f(p[e]);
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) amax = fmaxf(amax, fabsf(wv[e]));
+    amax = warp_max(amax);                                    // org_max_val (quantizer.py:833), exact
+    float d_own[kClipLevels][E], maxv[kClipLevels];
+#pragma unroll
+    for (int i = 0; i < kClipLevels; ++i) {
+      // max_val = org_max_val * (1 - i_s / n_grid): dtype tensor x python float = fp32 product rounded to the dtype
+      const float mv = rnd<T>(__fmul_rn(amax, float(1.0 - double(i) / double(n_grid))));
+      maxv[i] = mv;
+      float c[E], mx = ZP ? -INFINITY : 0.f, mn = INFINITY;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        c[e] = fminf(fmaxf(wv[e], -mv), mv);                  // torch.clamp(w, min_val, max_val)
+        if (ZP) { mx = fmaxf(mx, c[e]); mn = fminf(mn, c[e]); } else mx = fmaxf(mx, fabsf(c[e]));
+      }
+      mx = warp_max(mx);
+      if (ZP) mn = -warp_max(-mn);
+      float s, z;
+      group_params<T, ZP ? Q_ZP : Q_SYM>(mx, mn, max_int, s, z);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float code;
+        const float q = rtn_elem<T>(c[e], s, z, ZP ? 0.f : min_int, max_int, ZP, true, code);
+        d_own[i][e] = (i < n_levels) ? q - wv[e] : 0.f;
+        dT[(lane * E + e) * kClipDPad + i] = d_own[i][e];
+      }
+    }
+    __syncwarp();
+    float y[kClipLevels][E];
+#pragma unroll
+    for (int i = 0; i < kClipLevels; ++i)
+#pragma unroll
+      for (int e = 0; e < E; ++e) y[i][e] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < GS; ++k) {
+      float cv[E];
+      if (E == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(C + k * GS + lane * 4);
+        cv[0] = t.x; cv[1] = t.y; cv[2] = t.z; cv[E - 1] = t.w;
+      } else {
+        const float2 t = *reinterpret_cast<const float2*>(C + k * GS + lane * 2);
+        cv[0] = t.x; cv[E - 1] = t.y;
+      }
+      const float4 d0 = *reinterpret_cast<const float4*>(dT + k * kClipDPad);
+      const float4 d1 = *reinterpret_cast<const float4*>(dT + k * kClipDPad + 4);
+      const float2 d2 = *reinterpret_cast<const float2*>(dT + k * kClipDPad + 8);
+      const float dk[kClipLevels] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y};
+#pragma unroll
+      for (int i = 0; i < kClipLevels; ++i)
+#pragma unroll
+        for (int e = 0; e < E; ++e) y[i][e] = __fmaf_rn(cv[e], dk[i], y[i][e]);
+    }
+    float best = amax, min_err = INFINITY;                    // min_errs = ones * 1e9 is +inf in fp16 (quantizer.py:836)
+#pragma unroll
+    for (int i = 0; i < kClipLevels; ++i) {
+      float err = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) err = __fmaf_rn(y[i][e], d_own[i][e], err);
+      err = warp_sum(err);
+      if (i < n_levels && err < min_err) { min_err = err; best = maxv[i]; }   // strict <: the first minimum (quantizer.py:851)
+    }
+    if (lane == 0) best_max[r * G + g] = ElemTraits<T>::from_f(best);
+    __syncwarp();   // the d tile is rewritten by the next row
+  }
+}
+
 template <typename T>
 int dispatch_mode(unsigned flags, const T* w, int64_t n_groups, int64_t group, int64_t k_period, int n_bits,
                   const T* pre_mul, const T* clip_max, const T* post_div,
@@ -1282,5 +1419,61 @@ extern "C" int qdm_selftest_fastdiv(int dtype, uint64_t* out_host) {
   cudaFree(d);
   if (e != cudaSuccess) { qdm_set_error("qdm_selftest_fastdiv: %s", cudaGetErrorString(e)); return QDM_ERR_CUDA; }
   qdm_count_launch();
+  return QDM_OK;
+}
+
+extern "C" size_t qdm_awq_clip_workspace_bytes(int64_t ci, int group) {
+  if (ci <= 0 || group <= 0 || ci % group) return 0;
+  return size_t(ci / group) * size_t(group) * size_t(group) * sizeof(float);
+}
+
+extern "C" int qdm_awq_clip_search(const void* w, int dtype, int64_t co, int64_t ci, int group, int n_bits, unsigned flags,
+                                   const void* x, int64_t n_tok, int64_t ld_x, int n_grid, float max_shrink,
+                                   void* best_max, void* workspace, size_t workspace_bytes, void* stream) {
+  QDM_REQUIRE(w && x && best_max && workspace, "qdm_awq_clip_search: null pointer");
+  QDM_REQUIRE(co > 0 && ci > 0 && n_tok > 0 && ld_x >= ci, "qdm_awq_clip_search: empty problem");
+  QDM_REQUIRE(dtype == QDM_F16 || dtype == QDM_BF16, "qdm_awq_clip_search: dtype must be f16 or bf16");
+  QDM_REQUIRE((group == 64 || group == 128) && ci % group == 0, "qdm_awq_clip_search: group %d must be 64 or 128 and divide ci=%lld",
+              group, (long long)ci);
+  QDM_REQUIRE(n_bits >= 2 && n_bits <= 8, "qdm_awq_clip_search: n_bits %d outside [2, 8]", n_bits);
+  QDM_REQUIRE((flags & ~QDM_Q_ZERO_POINT) == 0, "qdm_awq_clip_search: bad flags 0x%x", flags);
+  const int n_levels = int(max_shrink * float(n_grid));
+  QDM_REQUIRE(n_grid > 0 && n_levels >= 1 && n_levels <= kClipLevels, "qdm_awq_clip_search: %d shrink levels (1..%d supported)", n_levels, kClipLevels);
+  QDM_REQUIRE(workspace_bytes >= qdm_awq_clip_workspace_bytes(ci, group) && qdm_aligned16(workspace), "qdm_awq_clip_search: workspace too small");
+  QDM_DEVICE_GATE();
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool zp = (flags & QDM_Q_ZERO_POINT) != 0;
+  const float max_int = zp ? float((1 << n_bits) - 1) : float((1 << (n_bits - 1)) - 1);
+  const float min_int = zp ? 0.f : -float(1 << (n_bits - 1));
+  const int G = int(ci / group);
+  float* gram = static_cast<float*>(workspace);
+  // rows per CTA: enough CTAs to fill the device (2 per SM), whole multiples of the warp count
+  int64_t rows_per_cta = (co * G + 2 * QDM_NUM_SMS - 1) / (2 * QDM_NUM_SMS);
+  rows_per_cta = (rows_per_cta + kClipWarps - 1) / kClipWarps * kClipWarps;
+  if (rows_per_cta < kClipWarps) rows_per_cta = kClipWarps;
+  if (rows_per_cta > co) rows_per_cta = (co + kClipWarps - 1) / kClipWarps * kClipWarps;
+  const dim3 grid(unsigned(G), unsigned((co + rows_per_cta - 1) / rows_per_cta));
+#define QDM_CLIP(TT, GSZ, ZPB)                                                                                         \
+  do {                                                                                                                 \
+    group_gram_kernel<TT, GSZ><<<dim3(unsigned(G), GSZ / 16), 256, 0, st>>>((const TT*)x, n_tok, ld_x, gram);          \
+    QDM_LAUNCH_CHECK();                                                                                                \
+    const size_t smem = size_t(GSZ) * GSZ * 4 + size_t(kClipWarps) * GSZ * kClipDPad * 4;                              \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      QDM_CUDA_OK(cudaFuncSetAttribute(awq_clip_kernel<TT, GSZ, ZPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    awq_clip_kernel<TT, GSZ, ZPB><<<grid, 32 * kClipWarps, smem, st>>>((const TT*)w, co, ci, gram, max_int, min_int, n_grid, \
+                                                                      n_levels, int(rows_per_cta), (TT*)best_max);    \
+    QDM_LAUNCH_CHECK();                                                                                                \
+  } while (0)
+  if (dtype == QDM_F16) {
+    if (group == 128) { if (zp) QDM_CLIP(__half, 128, true); else QDM_CLIP(__half, 128, false); }
+    else { if (zp) QDM_CLIP(__half, 64, true); else QDM_CLIP(__half, 64, false); }
+  } else {
+    if (group == 128) { if (zp) QDM_CLIP(__nv_bfloat16, 128, true); else QDM_CLIP(__nv_bfloat16, 128, false); }
+    else { if (zp) QDM_CLIP(__nv_bfloat16, 64, true); else QDM_CLIP(__nv_bfloat16, 64, false); }
+  }
+#undef QDM_CLIP
   return QDM_OK;
 }

@@ -46,8 +46,21 @@ class BaseAWQForDiffusion:
 
     @classmethod
     def from_skeleton(cls, device="cuda", dtype=torch.float16, seed=42, **arch):
+        """Random-init weights of the architecture.  On a CUDA device the modules are created there directly in `dtype`
+        (the full SD3.5-L skeleton is 8 G parameters: initialising it on the host in fp32 takes minutes and 32 GB); the
+        CUDA generator is seeded, so every rank of a multi-GPU run builds the identical model."""
         torch.manual_seed(seed)
-        den = cls.build_denoiser(**arch)
+        dev = torch.device(device)
+        if dev.type == "cuda":
+            old = torch.get_default_dtype()
+            torch.set_default_dtype(dtype)
+            try:
+                with torch.device(dev):
+                    den = cls.build_denoiser(**arch)
+            finally:
+                torch.set_default_dtype(old)
+        else:
+            den = cls.build_denoiser(**arch)
         pipe = sk.SkeletonPipeline(cls.kind, den, device=device, dtype=dtype, latent_size=arch.get("latent_size"))
         return cls(pipe, cls.kind, False, {"arch": arch}, AwqConfig())
 

@@ -192,6 +192,25 @@ def sqdiff_sum(a, b):
     return out
 
 
+def awq_clip_search(w, x, group, n_bits=4, zero_point=True, n_grid=20, max_shrink=0.5):
+    """AwqQuantizer._compute_best_clip (quantize/quantizer.py:805-863) for one Linear: w [co, ci], x [n_tok, ci] (the
+    already subsampled tokens; a strided view is fine) -> best_max [co, ci / group, 1] in w.dtype.  One Gram pass over x
+    + one search kernel (include/qdm.h: qdm_awq_clip_search)."""
+    _cuda(w, "w"), _cuda(x, "x")
+    if w.dim() != 2 or x.dim() != 2 or x.shape[1] != w.shape[1] or x.dtype != w.dtype or x.stride(1) != 1:
+        raise ValueError(f"awq_clip_search: w{tuple(w.shape)} / x{tuple(x.shape)} must be 2-D with the same K and dtype")
+    wc = w.contiguous()
+    co, ci = wc.shape
+    out = torch.empty((co, ci // group), dtype=w.dtype, device=w.device)
+    L = lib()
+    ws = _ws(w.device, L.qdm_awq_clip_workspace_bytes(ci, int(group)))
+    with _guard(w.device):
+        check(L.qdm_awq_clip_search(wc.data_ptr(), _dt(wc), co, ci, int(group), int(n_bits), QDM_Q_ZERO_POINT if zero_point else 0,
+                                    x.data_ptr(), x.shape[0], x.stride(0), int(n_grid), float(max_shrink), out.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), _stream(w)))
+    return out.unsqueeze(-1)
+
+
 # ------------------------------------------------------------------ (b) quantise / pack
 def _flags(zero_point, no_clamp):
     if zero_point and no_clamp:

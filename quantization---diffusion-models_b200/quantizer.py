@@ -424,16 +424,21 @@ class AwqQuantizer:
 
     @torch.no_grad()
     def _compute_best_clip(self, w: torch.Tensor, input_feat: torch.Tensor, n_grid=20, max_shrink=0.5, n_sample_token=512):
-        """quantizer.py:805-863.  The per-group dot products sum_g x*w are one batched GEMM per out-row batch
-        ([G] x [co_b, g] x [g, n_tok]) instead of a co_b x n_tok x K broadcast product; Q(clamp(w)) is the fused
-        quantise kernel with `clip_max`.  The reference rounds every x*w product to fp16 before summing; the GEMM
-        keeps fp32 products, so err values agree to ~1e-3 relative and best_max can differ on near-ties."""
+        """quantizer.py:805-863.  Groups of 64 / 128 in fp16 / bf16 (every diffusion layer) run the clip-search kernel.
+        Other group sizes keep the batched-GEMM form below: the per-group dot products sum_g x*w as one batched GEMM per
+        out-row batch ([G] x [co_b, g] x [g, n_tok]) instead of a co_b x n_tok x K broadcast product, Q(clamp(w)) by the
+        fused quantise kernel with `clip_max`.  The reference rounds every x*w product to fp16 before summing; both forms
+        keep fp32 products, so err values agree to ~1e-3 relative and best_max can differ on near-ties."""
         assert w.dim() == 2
         co, ci = w.shape
         gs = self._g(ci)
         G = ci // gs
         x = input_feat.view(-1, input_feat.shape[-1])
         x = x[:: max(1, x.shape[0] // n_sample_token)]
+        if gs in (64, 128) and w.dtype in (torch.float16, torch.bfloat16) and x.dtype == w.dtype:
+            # the search kernel (SURVEY.md section 8(f) row 1): err = d^T C d with the group's Gram matrix C, shrink levels
+            # quantised on the fly, no [G, co, n_tok] temporaries (include/qdm.h: qdm_awq_clip_search)
+            return ops.awq_clip_search(w, x, gs, 4, self.zero_point, n_grid, max_shrink)
         xg = x.reshape(-1, G, gs).permute(1, 2, 0).contiguous().float()      # [G, g, n_tok]
         # The reference walks out-rows in batches of 256 / 64 because its broadcast product needs
         # co_b x n_tok x K temporaries (quantizer.py:827); rows are independent, and the batched-GEMM form only

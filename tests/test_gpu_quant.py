@@ -58,6 +58,22 @@ def test_golden_fake_quant(qdm):
         assert_bit_equal(got, want, f"{tag} {kind}")
 
 
+def test_golden_activation_quantisers_round2(qdm):
+    """quantize_activation_per_channel_group_absmax (fake_quant.py:134-153: per (n, c, patch), incl. the `group_size -= 2`
+    fallback) and the 16-bit per-token / per-tensor / per-(n, c) forms (the reference's default a_bit = 16: q_max = 32767)
+    against the reference-generated fixture, bit for bit."""
+    import importlib
+    fq = importlib.import_module("quantization---diffusion-models_b200.fake_quant")
+    g = Golden("act_quant.npz")
+    for tag, kind, dt, gs, bits in g.cases():
+        x, want = g.get(tag + "_x").to(DEV), g.get(tag + "_y")
+        got = {"patch": lambda: fq.quantize_activation_per_channel_group_absmax(x, group_size=int(gs), n_bits=int(bits)),
+               "token": lambda: fq.quantize_activation_per_token_absmax(x, int(bits)),
+               "tensor": lambda: fq.quantize_activation_per_tensor_absmax(x, int(bits)),
+               "nchw": lambda: fq.quantize_activation_per_channel_absmax(x, int(bits))}[kind]()
+        assert_bit_equal(got, want, f"{tag} {kind} {dt}")
+
+
 def test_golden_awq_layout(qdm):
     g = Golden("awq_layout.npz")
     codes_kn = g.get("codes").to(torch.int8)

@@ -75,15 +75,29 @@ def test_search_best_scale_and_clip_vs_reference(qdm):
         # candidate scale vectors themselves are exact: ratio of the reference -> same vector
         xm = (qdm.ops.colabssum(x) / (x.numel() // x.shape[-1])).to(x.dtype)
         wm = (qdm.ops.awq_wsum(torch.cat([l.weight for l in lins]), int(group)) / (3 * 64)).to(x.dtype)
-        assert (xm.cpu() != g.get(tag + "_xmean")).float().mean() <= 0.02
-        assert (wm.cpu() != g.get(tag + "_wmean")).float().mean() <= 0.02
+        # fp32 fixed-tree sums vs the reference's CPU summation order: the 16-bit mean may sit 1 ulp away on a rounding
+        # boundary, on at most 0.5 % of the channels
+        for got, want_m in ((xm, g.get(tag + "_xmean")), (wm, g.get(tag + "_wmean"))):
+            got = got.cpu()
+            assert (got != want_m).float().mean() <= 0.005
+            assert ((got.float() - want_m.float()).abs() <= want_m.float().abs() * 2.0 ** (-7 if dt == "bf16" else -10)).all()
+        # clip search kernel (err = d^T C d in fp32) vs the reference's fp16 broadcast products: the same clip level for
+        # >= 99 % of the (row, group) pairs, and wherever it differs the level picked is as good as the reference's best
+        # BY THE REFERENCE'S OWN ERROR (a near-tie, not a mistake)
         clip = q._compute_best_clip(lins[0].weight.data, x)
         ref_clip = g.get(tag + "_clip")
         assert clip.shape == ref_clip.shape
-        # batched-GEMM error sums vs the reference's fp16 broadcast products: same clip level for the bulk
-        agree = (clip.cpu() == ref_clip).float().mean().item()
-        assert agree >= 0.9, agree
-        assert ((clip.cpu().float() - ref_clip.float()).abs() <= 0.1 * ref_clip.float().abs() + 1e-6).all()
+        same = clip.cpu() == ref_clip
+        assert same.float().mean().item() >= 0.99, same.float().mean().item()
+        w0, xs_ = g.get(f"{tag}_w0"), g.get(tag + "_x")
+        best, lv_max, lv_err = O.awq_search_clip(w0, xs_, int(group), bool(int(zp)), return_levels=True)
+        assert torch.equal(best, ref_clip)                                   # the oracle reproduces the fixture
+        ours = clip.cpu().squeeze(-1)
+        picked = (lv_max == ours.unsqueeze(0)).float().argmax(0)             # our level index per (row, group)
+        assert (lv_max.gather(0, picked.unsqueeze(0)).squeeze(0) == ours).all()   # always one of the ten candidates
+        err_ours = lv_err.float().gather(0, picked.unsqueeze(0)).squeeze(0)
+        err_best = lv_err.float().min(0).values
+        assert (err_ours <= err_best * 1.005 + 1e-7).all(), ((err_ours / err_best.clamp_min(1e-12)).max().item())
 
 
 def test_smooth_ln_fcs_vs_reference(qdm):
@@ -142,8 +156,9 @@ def tiny_sd15(qdm):
 
 @pytest.mark.parametrize("version", ["fake_act", "gemm"])
 def test_quantize_awq_end_to_end(qdm, version):
-    """quantize('awq') on a small UNet skeleton: fake-quant weights equal the oracle's RTN of the original
-    weights; the real packed modules reproduce the fake-quant model's denoised latents (bf16-level tolerance)."""
+    """quantize('awq') on a small UNet skeleton: fake-quant weights equal the oracle's RTN of the original weights, the
+    packed modules dequantise to the oracle's zero-point RTN, and the swapped model denoises to finite latents (latent
+    PARITY against torch on the same weights: test_denoised_latents_match_torch_on_the_same_fake_quant_weights)."""
     M, model = tiny_sd15(qdm)
     lat = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(1)).half().to(DEV)
     orig = {n: mod.weight.data.clone().cpu() for n, mod in model.denoiser().named_modules() if isinstance(mod, torch.nn.Linear)}
@@ -163,6 +178,67 @@ def test_quantize_awq_end_to_end(qdm, version):
                 assert_bit_equal(mod.dequantize(), O.rtn_group(w, mod.group_size, True, 4)[0], n)
     out = model.generate(["a", "b"], lat=lat, num_inference_steps=3)
     assert out.shape == lat.shape and torch.isfinite(out).all()
+
+
+def _torch_twin(model):
+    """The same quantised model with every libqdm GEMM module replaced by the torch op on ITS OWN fake-quant weights:
+    WQLinear_GEMM -> nn.Linear(dequantize()), QConv1x1 / QConv3x3 -> nn.Conv2d(dequantize()).  This is the reference's
+    formulation of the quantised model (fake-quant weights + F.linear / F.conv2d: fake_quant.py:223,339)."""
+    import copy
+    from torch import nn
+    mod_py = importlib.import_module(PKG + ".module")
+    twin = copy.deepcopy(model)
+    den = twin.denoiser()
+    done = []
+    for name, m in list(den.named_modules()):
+        kind = type(m).__name__
+        if any(name.startswith(d + ".") for d in done):
+            continue                                   # the inner module of an already replaced QConv1x1
+        if kind == "WQLinear_GEMM":
+            new = nn.Linear(m.in_features, m.out_features, bias=m.bias is not None, device=DEV, dtype=m.scales.dtype)
+            new.weight.data = m.dequantize()
+        elif kind == "QConv1x1" and type(m.inner).__name__ == "WQLinear_GEMM":
+            new = nn.Conv2d(m.in_channels, m.out_channels, 1, bias=m.inner.bias is not None, device=DEV, dtype=m.inner.scales.dtype)
+            new.weight.data = m.inner.dequantize().reshape(m.out_channels, m.in_channels, 1, 1)
+            m = m.inner
+        elif kind == "QConv3x3":
+            new = nn.Conv2d(m.in_channels, m.out_channels, 3, padding=1, bias=m.bias is not None, device=DEV, dtype=m.scales.dtype)
+            new.weight.data = m.dequantize()
+        else:
+            continue
+        if m.bias is not None:
+            new.bias.data = m.bias.clone()
+        mod_py.set_op_by_name(den, name, new)
+        done.append(name)
+    assert not any(type(m).__name__ in ("WQLinear_GEMM", "QConv1x1", "QConv3x3") for m in den.modules())
+    return twin
+
+
+@pytest.mark.parametrize("kind", ["sd15", "sd35"])
+def test_denoised_latents_match_torch_on_the_same_fake_quant_weights(qdm, kind):
+    """North star: 'GEMM and denoised-latent outputs within 1e-2'.  The W4A16 model (packed int4 Linears -- and, for the
+    UNet, 1x1 / 3x3 convolutions -- on the tcgen05 kernels) against the SAME model evaluated by torch (cuBLAS / cuDNN fp16)
+    on the dequantised weights, over a multi-step CFG denoise loop: max |latent - ref| / max |ref| <= 1e-2."""
+    M = importlib.import_module(PKG + ".models")
+    if kind == "sd15":   # real widths (320 / 640 / 1280, ctx 768), one transformer block per attention, 32 x 32 latents
+        model = M.StableDiffusion1_x.from_skeleton(device=DEV, latent_size=32)
+        lat = torch.randn(2, 4, 32, 32, generator=torch.Generator().manual_seed(11)).half().to(DEV)
+    else:                # 4 MMDiT blocks at the real width (2432, FF 9728), 32 x 32 latents -> 256 image + 333 text tokens
+        model = M.StableDiffusion3_5.from_skeleton(device=DEV, layers=4, latent_size=32)
+        lat = torch.randn(2, 16, 32, 32, generator=torch.Generator().manual_seed(11)).half().to(DEV)
+    model.quantize(quant_config={"zero_point": True, "q_group_size": 128, "w_bit": 4, "version": "gemm"}, quantType="awq")
+    assert any(type(m).__name__ == "WQLinear_GEMM" for m in model.denoiser().modules())
+    twin = _torch_twin(model)
+    qdm.ops.launch_count(reset=True)
+    out = model.generate(["a", "b"], lat=lat, num_inference_steps=4)
+    assert qdm.ops.launch_count() > 100                                       # the packed modules really ran libqdm kernels
+    qdm.ops.launch_count(reset=True)
+    ref = twin.generate(["a", "b"], lat=lat, num_inference_steps=4)
+    n_twin = qdm.ops.launch_count()
+    assert torch.isfinite(out).all() and torch.isfinite(ref).all()
+    err = ((out.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
+    assert err <= 1e-2, err
+    assert n_twin < 100                                                       # ... and the twin did not (fake-quant convs only)
 
 
 def test_awq_search_on_skeleton_and_sq_w8a8(qdm):

@@ -333,3 +333,65 @@ def test_awq_search_host_logic_on_reference_fixture():
             clip, ref_clip = q._compute_best_clip(lins[0].weight.data, x), g.get(tag + "_clip")
             assert clip.shape == ref_clip.shape
             assert (clip == ref_clip).float().mean().item() >= 0.97
+
+
+def test_calibrate_with_modules_to_not_convert_scales_once():
+    """a scaling-group member excluded from quantisation (modules_to_not_convert=['to_k']) is still scaled by
+    apply_scale during the clip phase; it must be rolled back like every other Linear so that apply_search_results
+    scales it exactly ONCE.  With scales applied once and no quantisation of that layer, weight == original * s."""
+    with patched_ops():
+        M, model = tiny_sd15()
+        model.calib_steps = 1
+        blocks = model.get_search_blocks()
+        bname = next(iter(blocks))
+        to_k = blocks[bname].attn1.to_k
+        w0 = to_k.weight.data.clone()
+        Q = importlib.import_module(PKG + ".quantizer").AwqQuantizer
+        quant = Q(model, None, None, group_size=64, zero_point=True, version="gemm", calibrate=True, apply_clip=True,
+                  modules_to_not_convert=["to_k"])
+        results = quant.search()
+        assert torch.equal(to_k.weight.data, w0)                      # search leaves every weight as it found it
+        s = next(sc for prev, names, sc in results[bname]["scales"] if "attn1.to_k" in names)
+        quant.apply_search_results(results)
+        assert torch.equal(to_k.weight.data, w0 * s.view(1, -1).to(w0.dtype))
+        assert all("to_k" not in name for name, _ in results[bname]["clip"])
+
+
+def test_non_tileable_groups_fall_back_to_fake_quant():
+    """group_size = -1 (per-channel: g = K = 64 * 5 for K = 320) or 192 cannot run on the W4A16 kernel
+    (g must be 64 * 2^j): the swap must keep those layers on the fake-quant path instead of building a module whose
+    forward raises."""
+    L = importlib.import_module(PKG + ".linear")
+    assert L.w4a16_kernel_ok(320, 320, 64) and L.w4a16_kernel_ok(2432, 9728, 128) and L.w4a16_kernel_ok(1024, 8, 256)
+    assert not L.w4a16_kernel_ok(320, 320, 320) and not L.w4a16_kernel_ok(384, 64, 192) and not L.w4a16_kernel_ok(64, 12, 64)
+    assert not L.w4a16_kernel_ok(96, 64, 96) and not L.w4a16_kernel_ok(128, 64, 0)
+    assert L.w8a8_kernel_ok(320, 8) and not L.w8a8_kernel_ok(72, 8) and not L.w8a8_kernel_ok(64, 12)
+    with patched_ops():
+        M = importlib.import_module(PKG + ".models")
+        model = M.StableDiffusion1_x.from_skeleton(device="cpu", channels=(320,), depth=(1,), ctx_dim=64, heads=2, latent_size=8)
+        model.quantize(quant_config={"q_group_size": -1, "w_bit": 4, "version": "gemm"}, quantType="awq")
+        kinds = [type(m).__name__ for m in model.denoiser().modules()]
+        assert "WxAxLinear" in kinds                                   # K = 320 per-channel: fake-quant fallback
+        lat = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(2)).half()
+        assert torch.isfinite(model.generate(["p"], lat=lat, num_inference_steps=1)).all()
+
+
+def test_fake_act_checkpoint_keeps_activation_quantisers(tmp_path):
+    """quantize_act / a_bit / per-group conv activations are constructor arguments, not state: the packed
+    checkpoint must carry them, or a model quantised with activation quantisation ON reloads with it OFF."""
+    with patched_ops():
+        M, model = tiny_sd15()
+        lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(3)).half()
+        model.quantize(quant_config={"q_group_size": 64, "w_bit": 8, "a_bit": 8, "version": "fake_act", "quantize_act": True,
+                                     "act_quant_conv_type": "per_group", "act_quant_conv_group_size": 4}, quantType="awq")
+        convs = [m for m in model.denoiser().modules() if type(m).__name__ == "WxAxConv2d"]
+        assert convs and all(c.quantise_act and c.act_quant_name == "per_group" and c.a_gs == 4 and c.n_bits_A == 8 for c in convs)
+        out = model.generate(["p"], lat=lat, num_inference_steps=1)
+        model.save_quantized(str(tmp_path))
+        again = M.StableDiffusion1_x.from_quantized(str(tmp_path), device="cpu")
+        convs2 = [m for m in again.denoiser().modules() if type(m).__name__ == "WxAxConv2d"]
+        assert len(convs2) == len(convs)
+        assert all(c.quantise_act and c.act_quant_name == "per_group" and c.a_gs == 4 and c.n_bits_A == 8 for c in convs2)
+        lins2 = [m for m in again.denoiser().modules() if type(m).__name__ == "WxAxLinear"]
+        assert lins2 and all(l.n_bits_A == 8 for l in lins2)
+        assert torch.equal(again.generate(["p"], lat=lat, num_inference_steps=1), out)

@@ -43,6 +43,20 @@ def test_fake_quant_functions_match_reference():
     assert kinds == {"group", "channel", "token", "tensor", "nchw"}
 
 
+def test_activation_quantisers_round2_fixture():
+    """act_quant.npz (tools/gen_golden.py acts): the NCHW per-patch quantiser (fake_quant.py:134-153) and the 16-bit
+    forms of the per-token / per-tensor / per-(n, c) quantisers the reference's default a_bit = 16 reaches."""
+    g = Golden("act_quant.npz")
+    kinds = set()
+    for tag, kind, dt, gs, bits in g.cases():
+        x, want = g.get(tag + "_x"), g.get(tag + "_y")
+        kinds.add(kind)
+        got = {"patch": lambda: O.rtn_nchw_patch(x, int(gs), int(bits)), "token": lambda: O.rtn_rows(x, int(bits))[0],
+               "tensor": lambda: O.rtn_tensor(x, int(bits))[0], "nchw": lambda: O.rtn_nchw_channel(x, int(bits))}[kind]()
+        assert_bit_equal(got, want, f"{tag} {kind} {dt}")
+    assert kinds == {"patch", "token", "tensor", "nchw"}
+
+
 def test_group_fallback():
     assert O.effective_group(320, 128) == 64      # fake_quant.py:34-37
     assert O.effective_group(2432, 128) == 128

@@ -301,9 +301,48 @@ def gen_wxax_conv(r):
     np.savez_compressed(os.path.join(OUT, "wxax_conv.npz"), **d)
 
 
+def gen_act_quant(r):
+    """A6 / A5 activation fake quantisers that the first fixtures did not cover: the NCHW per-(n, c, patch) quantiser
+    (fake_quant.py:134-153, incl. its `group_size -= 2` fallback) and the 16-bit forms the reference's default
+    a_bit = 16 reaches (q_max = 32767, fake_quant.py:109-118,158-167)."""
+    import contextlib
+    import io
+    fq = r.fake_quant
+    d, cases, i = {}, [], 0
+    for dt in ("f16", "bf16"):
+        for shape, gs in (((2, 6, 16, 16), 8), ((1, 5, 12, 12), 4), ((2, 3, 16, 16), 128), ((1, 4, 24, 24), 10)):
+            g = torch.Generator().manual_seed(1300 + i)
+            x = torch.randn(shape, generator=g)
+            x[:, 1] *= 25.0
+            x[0, 0, :4, :4] = 0.0                       # an all-zero patch -> clamp(min=1e-5) path
+            x = x.to(DT[dt])
+            with contextlib.redirect_stdout(io.StringIO()):   # the reference prints the group size it settled on
+                y = fq.quantize_activation_per_channel_group_absmax(x, group_size=gs, n_bits=8)
+            tag = f"g{i}"
+            enc(d, tag + "_x", x), enc(d, tag + "_y", y)
+            cases.append(f"{tag},patch,{dt},{gs},8")
+            i += 1
+        for kind, bits in (("token", 16), ("token", 12), ("tensor", 16), ("nchw", 16)):
+            g = torch.Generator().manual_seed(1300 + i)
+            x = torch.randn((3, 7, 40) if kind != "nchw" else (2, 5, 6, 6), generator=g) * 3.0
+            x[..., 3] *= 30.0
+            x = x.to(DT[dt])
+            fn = {"token": fq.quantize_activation_per_token_absmax, "tensor": fq.quantize_activation_per_tensor_absmax,
+                  "nchw": fq.quantize_activation_per_channel_absmax}[kind]
+            tag = f"g{i}"
+            enc(d, tag + "_x", x), enc(d, tag + "_y", fn(x, n_bits=bits))
+            cases.append(f"{tag},{kind},{dt},0,{bits}")
+            i += 1
+    d["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(OUT, "act_quant.npz"), **d)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "conv":   # only the convolution fixture (added later; the others are unchanged)
         torch.set_grad_enabled(False)
         gen_wxax_conv(ref_shim.ref())
+    elif len(sys.argv) > 1 and sys.argv[1] == "acts":  # only the activation-quantiser fixture (round 2)
+        torch.set_grad_enabled(False)
+        gen_act_quant(ref_shim.ref())
     else:
         main()

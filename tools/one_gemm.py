@@ -23,6 +23,10 @@ def main():
     if kind == "w4":
         qw, qz, sc, _ = q.ops.quant_pack_awq(w, grp)
         fn = lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp)
+    elif kind == "w4rp":   # repacked-weight kernel; QDM_GEMM_MODE = 16 | 32 (+ width << 8) pins the form
+        qw, qz, sc, _ = q.ops.quant_pack_awq(w, grp)
+        blob = q.ops.w4a16_repack(qw, qz, sc, grp)
+        fn = lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp, None, blob)
     elif kind == "f16":
         fn = lambda: q.ops.gemm_f16(x, w)
     elif kind == "f16_kn":
