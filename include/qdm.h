@@ -227,6 +227,19 @@ int qdm_w4a16_repack(const int32_t* qweight, const int32_t* qzeros, const void* 
 int qdm_gemm_w4a16_rp(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* blob,
                       const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group, void* stream);
 
+/* Second kernel-native form, for the kernel that feeds the dequantised WEIGHTS to the tensor core as its A operand from
+ * tensor memory (output channels on the 128 TMEM lanes, tokens along the MMA N dimension; the weights never touch shared
+ * memory): per (k-block, output channel) 8 words whose nibble order along k is {0,2,4,6,1,3,5,7} -- one lop3 gives the
+ * half2 (k, k+1) of one TMEM cell -- followed by one (scale, zero-point-as-dtype-value) pair per (k-block, channel).
+ * blob: qdm_w4a16_repack_ts_bytes(N, K) bytes (0.56 B / weight).  qdm_gemm_w4a16_plan takes both forms (either may be
+ * NULL) next to the AWQ tensors and picks the kernel per problem. */
+size_t qdm_w4a16_repack_ts_bytes(int64_t N, int64_t K);
+int qdm_w4a16_repack_ts(const int32_t* qweight, const int32_t* qzeros, const void* scales, int dtype, int64_t N, int64_t K,
+                        int group, void* blob, size_t blob_bytes, void* stream);
+int qdm_gemm_w4a16_plan(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* blob_rp,
+                        const void* blob_ts, const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
+                        void* stream);
+
 /* Which kernel the calling thread's last W4A16 GEMM call launched, and its tile width in columns (tests assert the
  * dispatch with this; not part of the reference interface). */
 #define QDM_GEMM_SINGLE  1 /* single-CTA tcgen05 tiles (M <= 128)              */
@@ -238,6 +251,7 @@ int qdm_gemm_w4a16_rp(const void* x, const int32_t* qweight, const int32_t* qzer
 #define QDM_GEMM_RP1     7 /* repacked weights, one sub-tile per pair          */
 #define QDM_GEMM_RP2     8 /* repacked weights, two sub-tiles per pair         */
 #define QDM_GEMM_QUAD    9 /* quad clusters (forced only)                      */
+#define QDM_GEMM_TS     10 /* weights as the A operand from tensor memory      */
 int qdm_gemm_last_variant(int* tile_n);
 
 /* y[m,n] = (sum_k xq[m,k]*wq[n,k]) * sx[m] * sw[n] + bias[n]; int8 x int8 -> int32 in TMEM.

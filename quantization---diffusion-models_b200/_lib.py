@@ -63,6 +63,9 @@ SIGNATURES = {
     "qdm_w4a16_repack": (c_int, [_P, _P, _P, _L, _L, _I, _P, _Z, _P]),
     "qdm_gemm_w4a16_rp": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _L, _L, _I, _P]),
     "qdm_gemm_last_variant": (c_int, [_P]),
+    "qdm_w4a16_repack_ts_bytes": (c_size_t, [_L, _L]),
+    "qdm_w4a16_repack_ts": (c_int, [_P, _P, _P, _I, _L, _L, _I, _P, _Z, _P]),
+    "qdm_gemm_w4a16_plan": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _L, _L, _I, _P]),
     "qdm_conv3x3_f16": (c_int, [_P, _P, _P, _P, _I, _L, _L, _L, _L, _L, _P]),
     "qdm_conv3x3_w4a16": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _L, _L, _L, _L, _I, _P]),
     "qdm_conv3x3_direct_ok": (c_int, [_L, _L]),

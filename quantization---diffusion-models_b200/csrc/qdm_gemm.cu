@@ -28,6 +28,8 @@ int qdm_gemm_w4a16_skinny(const void* x, const int32_t* qweight, const int32_t* 
                           void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int group, cudaStream_t st);
 int qdm_w4rp_gemm(const void* x, const void* blob, const void* bias, void* y, int is_bf16, int64_t M, int64_t N, int64_t K,
                   int subs, int sub_n, cudaStream_t st);
+int qdm_w4ts_gemm(const void* x, const void* blob, const void* bias, void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int tile_t,
+                  cudaStream_t st);
 bool qdm_gemm_w4a16_smallm_fits(int64_t M, int64_t N, int64_t K);
 int qdm_gemm_w4a16_smallm(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales, const void* bias,
                           void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int group, cudaStream_t st);
@@ -1595,6 +1597,7 @@ bool choose_rp(int64_t M, int64_t N, int64_t K, int* subs_out, int* sub_n_out) {
 bool use_pair(const GemmParams& p) {
   if (g_force_ctas == 1) return false;
   if (g_force_ctas >= 2 && g_force_ctas <= 8) return true;
+  if (g_force_ctas == 128) return p.M > BLOCK_M;
   return p.M > BLOCK_M;   // a second 128-row half exists
 }
 
@@ -1717,10 +1720,10 @@ extern "C" int qdm_gemm_set_workspace(void* workspace, size_t bytes, void* strea
 
 extern "C" int qdm_set_gemm_mode(int ctas) {
   const int mode = ctas & 0xff, tile = ctas >> 8;   // bits 8.. : sub-tile width override of the repacked-weight kernel
-  QDM_REQUIRE(mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8 || mode == 16 || mode == 32 || mode == 64,
+  QDM_REQUIRE(mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8 || mode == 16 || mode == 32 || mode == 64 || mode == 128,
               "qdm_set_gemm_mode: 0 (auto), 1 (single CTA), 2 (CTA pair), 4 (quad cluster), 8 (stream-K), 16 / 32 (repacked weights, "
               "one / two sub-tiles) or 64 (no repacked weights)");
-  QDM_REQUIRE(tile == 0 || (tile % 32 == 0 && tile <= 256), "qdm_set_gemm_mode: sub-tile width %d must be a multiple of 32 <= 256", tile);
+  QDM_REQUIRE(tile == 0 || (tile % 16 == 0 && tile <= 256), "qdm_set_gemm_mode: tile width %d must be a multiple of 16 <= 256", tile);
   g_force_ctas = mode == 64 ? 0 : mode;
   g_no_rp = mode == 64;
   g_force_tile = tile;
@@ -1770,9 +1773,27 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   return dispatch_gemm<G_F16_KN>(m, p, false, (cudaStream_t)stream);
 }
 
+// TS kernel (qdm_gemm_w4ts.cu): tokens per tile.  A pair owns 256 output channels x T tokens; T is any multiple of 16 <= 256,
+// chosen so that the last wave is not nearly empty.  Cycles per k-block: tensor pipe 2 T; the dequant sets deliver one A
+// stage (128 channels x 64 k per CTA) per ~300 cycles, whatever T is.
+int choose_ts_tile(int64_t M, int64_t N, int64_t K, double* cost_out) {
+  const int64_t P = QDM_NUM_SMS / 2, n_blks = (N + 255) / 256, num_kb = K / 64;
+  int best = 256;
+  double best_cost = 1e300;
+  for (int t = 256; t >= 32; t -= 32) {   // multiples of 32: the epilogue stores 32-token boxes
+    if (g_force_tile && t != g_force_tile) continue;
+    const int64_t tiles = n_blks * ((M + t - 1) / t), waves = (tiles + P - 1) / P;
+    const double perkb = (2.0 * t > 300.0 ? 2.0 * t : 300.0) + 40.0;
+    const double cost = double(waves) * (double(num_kb) * perkb + 600.0 + 6.0 * t);   // + the tile's exposed epilogue
+    if (cost < best_cost * 0.999) { best_cost = cost; best = t; }
+  }
+  if (cost_out) *cost_out = best_cost;
+  return best;
+}
+
 static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
                            const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K, int group,
-                           const ConvGeom* conv, void* stream, const void* blob = nullptr) {
+                           const ConvGeom* conv, void* stream, const void* blob = nullptr, const void* blob_ts = nullptr) {
   int rc = check_common("qdm_gemm_w4a16", x, qweight, y, dtype, M, N, K);
   if (rc) return rc;
   QDM_REQUIRE(qzeros && scales, "qdm_gemm_w4a16: null qzeros/scales");
@@ -1796,6 +1817,12 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
   if (!conv && qdm_gemm_w4a16_smallm_fits(M, N, K) && g_force_ctas == 0 && !opt.no_smallm) {
     note_variant(QDM_GEMM_SMALLM, 0);
     return qdm_gemm_w4a16_smallm(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);
+  }
+  // Weights as the TMEM A operand (forced only until its dispatch rule is calibrated: mode 128)
+  if (blob_ts && !conv && g_force_ctas == 128 && K >= 128 && M >= 16) {
+    const int t = choose_ts_tile(M, N, K, nullptr);
+    note_variant(QDM_GEMM_TS, t);
+    return qdm_w4ts_gemm(x, blob_ts, bias, y, dtype == QDM_BF16, M, N, K, t, (cudaStream_t)stream);
   }
   // Repacked weights: every CTA-pair problem except the small-K / many-tile ones the B-stationary kernel keeps
   // (K >= 192: the last-tile helpers' barrier-parity argument needs >= 3 k-blocks per tile, see qdm_gemm_w4rp.cu)
@@ -1892,6 +1919,12 @@ extern "C" int qdm_gemm_w4a16_rp(const void* x, const int32_t* qweight, const in
                                  const void* blob, const void* bias, void* y, int dtype, int64_t M, int64_t N, int64_t K,
                                  int group, void* stream) {
   return gemm_w4a16_impl(x, qweight, qzeros, scales, bias, y, dtype, M, N, K, group, nullptr, stream, blob);
+}
+
+extern "C" int qdm_gemm_w4a16_plan(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                                   const void* blob_rp, const void* blob_ts, const void* bias, void* y, int dtype, int64_t M,
+                                   int64_t N, int64_t K, int group, void* stream) {
+  return gemm_w4a16_impl(x, qweight, qzeros, scales, bias, y, dtype, M, N, K, group, nullptr, stream, blob_rp, blob_ts);
 }
 
 extern "C" int qdm_gemm_last_variant(int* tile_n) {

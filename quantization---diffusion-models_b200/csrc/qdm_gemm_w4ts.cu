@@ -1,0 +1,525 @@
+// (c) W4A16 GEMM with the WEIGHTS as the tensor-core A operand in TENSOR MEMORY (the "TS" path):
+//     y^T[N, M] = dequant(qweight, qzeros, scales)^T[N, K] . x^T[K, M]        (N output channels, M tokens)
+//
+// Why.  In the other W4 kernels the dequantised B tile travels through shared memory: the dequant warps write 16 KB per
+// k-block with st.shared, the tensor core reads it back, next to the A tile written by TMA and read by the tensor core
+// and the packed operand staged in between -- ~73 KB of shared-memory traffic per k-block per SM against 64 KB for a
+// plain fp16 GEMM, and measured k-block periods of 850-960 cycles against 512 cycles of tensor-pipe time
+// (profiles/README.md, round 2: both kernels sit at ~60 % of their shared-memory-port minimum).  tcgen05.mma can take
+// its A operand from TMEM.  With the roles swapped -- output channels on the 128 TMEM lanes, tokens along the MMA N
+// dimension -- the dequantised weights go registers -> TMEM (tcgen05.st) and never touch shared memory:
+//   * shared memory only carries the activations (16 KB written by TMA + read by the tensor core per k-block per SM:
+//     half of what an fp16 GEMM needs);
+//   * a dequant thread owns ONE output channel (its TMEM lane) and the 64 k of a k-block: one scale and one zero point
+//     per thread per k-block, 8 packed words -> 32 half2 registers -> one tcgen05.st.32x32b.x32;
+//   * the packed operand is read straight from global memory into registers (a kernel-native copy of the AWQ tensors
+//     built once by qdm_w4a16_repack_ts: per (k-block, channel) 8 words whose nibble order along k is the AWQ order
+//     [0,2,4,6,1,3,5,7], so that one lop3 yields the half2 (k, k+1) = one 32-bit TMEM cell; a warp reads 1 KB
+//     contiguous), prefetched three k-blocks ahead in registers.
+// Dequant arithmetic is unchanged: (q - z) exact in the 16-bit type (magic-number trick), * s with one rounding --
+// bit-identical to dequantize_gemm (utils/packing_utils.py:87-102).
+//
+// Tile: a CTA pair owns 256 output channels (128 TMEM lanes per CTA) x T <= 256 tokens (cta_group::2, M = 256, N = T).
+// TMEM per CTA: columns [0, 256) fp32 accumulator, [256, 512) the A ring: 4 stages of 64 columns (128 k as 64 half2);
+// shared memory: 6 stages of 32 KB of activations.
+// A pipeline stage is K = 128 (two k-blocks): the single MMA-issuing thread pays ~250 cycles of serial latency per
+// barrier wait (measured), so it gets ONE full / empty barrier pair per stage and 8 tcgen05.mma per wait.
+// Roles (16 warps): warp 0 TMA producer of x (each CTA T/2 token rows), warp 1 MMA issuer (leader CTA), warp 2 TMEM
+// allocator, warps 4-7 epilogue (TMEM -> registers -> +bias -> 16-bit -> 64-byte row segments of y[tokens, channels]),
+// warps 8-11 / 12-15 two dequant sets taking even / odd k-blocks (A stage = k-block % 8, so every stage belongs to one set).
+#include "qdm_gemm_dev.cuh"
+#include <stdlib.h>
+
+using namespace qdmg;
+
+namespace {
+
+constexpr int TS_KB = 2;                       // k-blocks (64 k) per pipeline stage: K = 128 per stage
+constexpr int TS_NS = 4;                       // weight stages in TMEM (64 columns each)
+constexpr int TS_NXS = 6;                      // activation stages in shared memory (32 KB each): the L2 -> SM latency under load
+                                               // is 3000-5000 cycles (measured), i.e. more than 4 stages of tensor-pipe time
+constexpr int TS_STAGE_BYTES = TS_KB * A_STAGE_BYTES;
+constexpr int TS_A_COL0 = 256;                 // first TMEM column of the A ring
+constexpr int TS_A_COLS = TS_KB * 32;          // TMEM columns of one A stage (64 k as 32 half2 per k-block)
+constexpr int TS_DIST = 2;                     // packed words are prefetched this many of a set's stages ahead
+constexpr int TS_EPI_BYTES = 12 * 2048;        // per draining warp (4 epilogue + 8 dequant): one staging tile of 32 tokens x 32 channels x 2 B
+constexpr int TS_BAR_BYTES = 512;
+constexpr int TS_SMEM_BYTES = TS_NXS * TS_STAGE_BYTES + TS_EPI_BYTES + 1024 + TS_BAR_BYTES;
+constexpr int TS_THREADS = 512;
+
+// ---------------------------------------------------------------- one-time repack
+// words[kb][n][8]: nibble i of word j = code of k = 64 kb + 8 j + {0,2,4,6,1,3,5,7}[i] of output channel n
+// sz[kb][n]      : low 16 bits = scale (dtype bits) of the k-block's group, high 16 bits = zero point as a dtype value
+template <bool BF16>
+__global__ void __launch_bounds__(256) w4ts_repack_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
+                                                          const uint16_t* __restrict__ scales, int N, int K, int group,
+                                                          uint32_t* __restrict__ words, uint32_t* __restrict__ sz) {
+  const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;   // (kb, n)
+  const int kbs = K / 64;
+  if (idx >= int64_t(kbs) * N) return;
+  const int kb = int(idx / N), n = int(idx % N);
+  const int words_per_row = N / 8;
+  const int pos = ((n & 7) >> 1) + ((n & 1) << 2);   // nibble of column n inside its AWQ word: order [0,2,4,6,1,3,5,7]
+  const int shift = 4 * pos;
+  uint32_t out[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int k = kb * 64 + 8 * j + t;
+      const uint32_t code = (uint32_t(qweight[int64_t(k) * words_per_row + (n >> 3)]) >> shift) & 0xFu;
+      const int nib = (t >> 1) + ((t & 1) << 2);     // k even -> nibbles 0..3, k odd -> nibbles 4..7
+      w |= code << (4 * nib);
+    }
+    out[j] = w;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(words + idx * 8);
+  dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  const int64_t g = (int64_t(kb) * 64) / group;
+  const uint32_t z = (uint32_t(qzeros[g * words_per_row + (n >> 3)]) >> shift) & 0xFu;
+  uint32_t zbits;
+  if (BF16) { __nv_bfloat16 h = __float2bfloat16_rn(float(z)); zbits = *reinterpret_cast<uint16_t*>(&h); }
+  else { __half h = __float2half_rn(float(z)); zbits = *reinterpret_cast<uint16_t*>(&h); }
+  sz[idx] = uint32_t(scales[g * N + n]) | (zbits << 16);
+}
+
+// ---------------------------------------------------------------- PTX: TMEM store, A-from-TMEM MMA
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+      "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+      "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] . B[smem]; both CTAs of the pair hold their 128 rows of A at the same TMEM address
+__device__ __forceinline__ void umma_pair_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+struct TsParams {
+  int M, N, K;                 // tokens, output channels, reduction
+  int tile_t;                  // tokens per tile (multiple of 16, <= 256)
+  const uint32_t* words;       // [K/64][N][8]
+  const uint32_t* sz;          // [K/64][N]
+  const void* bias;            // [N] dtype or null
+  void* y;                     // [M, N] dtype
+  long long* trace;            // QDM_TRACE builds only
+};
+
+// ---------------------------------------------------------------- the kernel
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TS_THREADS, 1)
+qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const TsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = smem_base + TS_NXS * TS_STAGE_BYTES;
+  const uint32_t bar_base = epi_base + TS_EPI_BYTES;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // ONE full barrier per stage: the MMA issuer is a single thread whose barrier waits are serial latency (measured: ~250
+  // cycles per wait on a barrier that is already complete), so a stage costs it one wait.  full[g % 6] collects, for
+  // global stage g, the leader's expect_tx (TMA bytes of both CTAs) and the 4 dequant warps of the stage's set in both
+  // CTAs.  The stage is released by two multicast commits: x_empty[g % 6] (awaited by the TMA producers) and
+  // a_empty[g % 4] (awaited by the dequant set that owns the TMEM slot).  6 and 4 are even, so a slot of either ring
+  // always belongs to the same dequant set: nobody skips a phase of a barrier it waits on.
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto x_empty_bar = [&](int s) { return bar_base + 8u * (TS_NXS + s); };
+  auto a_empty_bar = [&](int s) { return bar_base + 8u * (2 * TS_NXS + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * TS_NXS + TS_NS);
+  const uint32_t tmem_empty_bar = tmem_full_bar + 8u;
+  static_assert(8 * (2 * TS_NXS + TS_NS + 2) + 8 <= TS_BAR_BYTES, "barrier area");
+  static_assert(TS_NXS % 2 == 0 && TS_NS % 2 == 0, "ring slots must keep their dequant set");
+  static_assert(TS_A_COL0 + TS_NS * TS_A_COLS <= 512, "TMEM columns");
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * TS_NXS + TS_NS + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = int(blockIdx.x) >> 1, num_pairs = int(gridDim.x) >> 1;
+  const int T = p.tile_t, th = T >> 1;                              // tokens per tile, per CTA
+  const int n_blks = (p.N + 255) / 256, m_blks = (p.M + T - 1) / T;
+  const int num_tiles = n_blks * m_blks;                           // tile = n_blk * m_blks + m_blk: token blocks fastest, so
+  const int num_kb = p.K / 64;                                     // concurrently running pairs share a weight slab in L2
+  const int num_st = (num_kb + TS_KB - 1) / TS_KB;                 // pipeline stages per tile (the last may hold one k-block)
+  const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_y); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TS_NXS; ++s) { mbar_init(full_bar(s), 9); mbar_init(x_empty_bar(s), 1); }   // 1 + 4 dequant warps x 2 CTAs
+    for (int s = 0; s < TS_NS; ++s) mbar_init(a_empty_bar(s), 1);
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 24);                                                         // 12 draining warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr_smem))),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
+  const uint32_t leader_tmem_empty = mapa_shared(tmem_empty_bar, 0);
+
+  // One warp's share of a tile's epilogue: TMEM lane quarter ew (32 output channels), the 32-token chunks c_first,
+  // c_first + c_step, ...: tcgen05.ld -> + bias -> 16 bit -> shared staging [token][channel] (64-byte rows) -> one TMA store
+  // of the 32 x 32 box per chunk (clipped at N and M by the tensor map).  Three warps share a lane quarter -- the epilogue
+  // warp and the two dequant warps with the same warp % 4 -- and take every third chunk each.
+  auto epilogue_share = [&](int tl, int ew, int c_first, int c_step, uint32_t stg) {
+    const int tile = pair + tl * num_pairs;
+    const int n0 = (tile / m_blks) * 256 + int(rank) * 128 + ew * 32;     // this warp's 32 channels
+    const int m0 = (tile % m_blks) * T;
+    const int n = n0 + lane;
+    float bias = 0.f;
+    if (p.bias && n < p.N) {
+      if (BF16) bias = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+      else bias = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+    }
+    mbar_wait(tmem_full_bar, uint32_t(tl) & 1u);
+    tc_fence_after();
+    const int t_end = min(T, p.M - m0);
+    for (int c = 32 * c_first; c < t_end; c += 32 * c_step) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(c), v);
+      tmem_ld_wait();
+      if (lane == 0) tma_store_wait_read();                            // this warp's previous store has read the staging tile
+      __syncwarp();
+      if (n0 < p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float f = __uint_as_float(v[j]) + bias;
+          uint16_t h;
+          if (BF16) { __nv_bfloat16 bb = __float2bfloat16_rn(f); h = *reinterpret_cast<uint16_t*>(&bb); }
+          else { __half bb = __float2half_rn(f); h = *reinterpret_cast<uint16_t*>(&bb); }
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(stg + uint32_t(j) * 64u + uint32_t(lane) * 2u), "h"(h) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&map_y, stg, n0, m0 + c);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer: x, this CTA's half of the tile's tokens
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      TRC_DECL;
+      int trc_it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile % m_blks) * T + int(rank) * th;
+        for (int st = 0; st < num_st; ++st) {
+          mbar_wait(x_empty_bar(stage), phase ^ 1);
+          TRC(p.trace, 0, 2000000 + trc_it);
+          ++trc_it;
+          // boxes are always 128 rows (rows past this CTA's T/2 are loaded and ignored, past M zero-filled)
+          const int nk = min(TS_KB, num_kb - st * TS_KB);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * nk * A_STAGE_BYTES);
+          for (int j = 0; j < nk; ++j)
+            tma_load_2d_pair(smem_base + stage * TS_STAGE_BYTES + j * A_STAGE_BYTES, &map_x, leader_full0 + 8u * stage,
+                             (st * TS_KB + j) * 64, m0);
+          if (++stage == TS_NXS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 0, 2 * BLOCK_M, T);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      TRC_DECL;
+      int trc_it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tmem_empty_bar, acc_phase ^ 1);
+        TRC(p.trace, 1, 1000000 + trc_it);
+        tc_fence_after();
+        for (int st = 0; st < num_st; ++st) {
+          mbar_wait(full_bar(stage), phase);
+          TRC(p.trace, 1, 2000000 + trc_it);
+          ++trc_it;
+          tc_fence_after();
+          const int nk = min(TS_KB, num_kb - st * TS_KB);
+          for (int j = 0; j < nk; ++j) {
+            const uint32_t b_addr = smem_base + stage * TS_STAGE_BYTES + j * A_STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // 4 x 16 k: 8 TMEM columns of A, 32 bytes of every x row
+              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_pair_ts(tmem_base, tmem_base + uint32_t(TS_A_COL0 + as * TS_A_COLS + j * 32 + k * 8), db, idesc, (st | j | k) != 0);
+            }
+          }
+          umma_commit_pair(a_empty_bar(as), 3);
+          umma_commit_pair(x_empty_bar(stage), 3);
+          TRC(p.trace, 1, 3000000 + trc_it - 1);
+          if (st == num_st - 1) umma_commit_pair(tmem_full_bar, 3);
+          if (++stage == TS_NXS) { stage = 0; phase ^= 1; }
+          if (++as == TS_NS) as = 0;
+        }
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================== epilogue: lanes = output channels, columns = tokens
+    const int ew = warp - 4;
+    for (int tl = 0; tl < my_tiles; ++tl) epilogue_share(tl, ew, 0, 3, epi_base + uint32_t(ew) * 2048u);
+    if (lane == 0) tma_store_wait_all();
+  } else if (warp >= 8) {
+    // ===================================================== dequant: registers -> TMEM
+    const int set = (warp - 8) >> 2, q = warp & 3;                       // TMEM lane quarter = warp % 4
+    uint32_t mask_lo = 0x000F000Fu, mask_hi = 0x00F000F0u;
+    uint32_t magic = BF16 ? 0x43004300u : 0x64006400u;
+    asm volatile("" : "+r"(mask_lo), "+r"(mask_hi), "+r"(magic));
+    auto and_or = [](uint32_t a, uint32_t b, uint32_t c) {
+      uint32_t d;
+      asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // (a & b) | c
+      return d;
+    };
+    struct Pf { uint4 w0, w1; uint32_t sz; };   // one k-block of this thread's channel: 8 packed words, (scale, zero)
+    Pf ring[TS_DIST][TS_KB];
+    const int total = my_tiles * num_st;                                 // stages of this pair, global sequence
+    const int mine = (total - set + 1) / 2;                              // ... of which this set takes every other one
+    // prefetch cursor: the set's next stage to load = global stage pf_g = (pf_tl, pf_st)
+    int pf_g = set, pf_tl = 0, pf_st = set;
+    while (pf_st >= num_st) { pf_st -= num_st; ++pf_tl; }
+    auto prefetch = [&](Pf (&f)[TS_KB]) {
+#pragma unroll
+      for (int j = 0; j < TS_KB; ++j) { f[j].w0 = make_uint4(0, 0, 0, 0); f[j].w1 = f[j].w0; f[j].sz = 0; }
+      if (pf_g < total) {
+        const int tile = pair + pf_tl * num_pairs;
+        const int n = (tile / m_blks) * 256 + int(rank) * 128 + q * 32 + lane;
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < TS_KB; ++j) {
+            const int kb = pf_st * TS_KB + j;
+            if (kb < num_kb) {
+              const int64_t idx = int64_t(kb) * p.N + n;
+              const uint4* src = reinterpret_cast<const uint4*>(p.words + idx * 8);
+              f[j].w0 = __ldg(src);
+              f[j].w1 = __ldg(src + 1);
+              f[j].sz = __ldg(p.sz + idx);
+            }
+          }
+        }
+      }
+      pf_g += 2; pf_st += 2;
+      while (pf_st >= num_st) { pf_st -= num_st; ++pf_tl; }
+    };
+#pragma unroll
+    for (int d = 0; d < TS_DIST; ++d) prefetch(ring[d]);
+    auto unpack = [&](const Pf& f, uint32_t (&o)[32]) {
+      const uint32_t s2 = (f.sz & 0xFFFFu) * 0x10001u;                   // (s, s)
+      const uint32_t zz = (f.sz >> 16) * 0x10001u;                       // (z, z) as dtype values
+      uint32_t zlo, zhi = 0;
+      if (BF16) {
+        const __nv_bfloat162 m = __float2bfloat162_rn(128.f);
+        __nv_bfloat162 t = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&zz), m);   // 128 + z, exact
+        zlo = *reinterpret_cast<uint32_t*>(&t);
+      } else {
+        __half2 t = __hadd2(*reinterpret_cast<const __half2*>(&zz), __float2half2_rn(1024.f));   // 1024 + z
+        __half2 u = __hadd2(*reinterpret_cast<const __half2*>(&zz), __float2half2_rn(64.f));     // 64 + z
+        zlo = *reinterpret_cast<uint32_t*>(&t);
+        zhi = *reinterpret_cast<uint32_t*>(&u);
+      }
+      const uint32_t wsrc[8] = {f.w0.x, f.w0.y, f.w0.z, f.w0.w, f.w1.x, f.w1.y, f.w1.z, f.w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t wv = wsrc[j];
+        if (BF16) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t t = and_or(wv >> (4 * c), mask_lo, magic);    // {128 + q(k = 8j + 2c), 128 + q(k + 1)}
+            __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&t), *reinterpret_cast<const __nv_bfloat162*>(&zlo));
+            d = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&s2));
+            o[4 * j + c] = *reinterpret_cast<uint32_t*>(&d);
+          }
+        } else {
+          const uint32_t ws = wv >> 8;
+          const __half2 sixteenth = __float2half2_rn(0.0625f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t src = (c < 2) ? wv : ws;
+            __half2 d;
+            if ((c & 1) == 0) {   // nibbles c, c + 4 -> 1024 + q, exact subtract
+              const uint32_t t = and_or(src, mask_lo, magic);
+              d = __hsub2(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&zlo));
+            } else {              // 1024 + 16 q; fma(., 1/16, -(64 + z)) = q - z exactly
+              const uint32_t t = and_or(src, mask_hi, magic);
+              d = __hfma2(*reinterpret_cast<const __half2*>(&t), sixteenth, __hneg2(*reinterpret_cast<const __half2*>(&zhi)));
+            }
+            d = __hmul2(d, *reinterpret_cast<const __half2*>(&s2));      // (q - z) * s, one rounding
+            o[4 * j + c] = *reinterpret_cast<uint32_t*>(&d);
+          }
+        }
+      }
+    };
+    int as = set % TS_NS, fs = set % TS_NXS;                            // TMEM slot, full-barrier slot of the set's next stage
+    uint32_t aph = uint32_t(set / TS_NS) & 1u;
+    int done_g = set - 2, epi_tl = 0;                                    // last stage processed (global), next tile to drain
+    TRC_DECL;
+    int trc_it = 0;
+    auto process = [&](const Pf (&f)[TS_KB]) {
+      uint32_t o[32];
+      if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 1000000 + trc_it);
+      unpack(f[0], o);
+      mbar_wait(a_empty_bar(as), aph ^ 1);
+      if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 2000000 + trc_it);
+      tc_fence_after();
+      const uint32_t a_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(TS_A_COL0 + as * TS_A_COLS);
+      tmem_st32(a_addr, o);
+#pragma unroll
+      for (int j = 1; j < TS_KB; ++j) {
+        tmem_st_wait();                                                  // o is reused
+        unpack(f[j], o);
+        tmem_st32(a_addr + uint32_t(j) * 32u, o);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_full0 + 8u * fs);
+      if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 3000000 + trc_it);
+      ++trc_it;
+      as += 2;
+      if (as >= TS_NS) { as -= TS_NS; aph ^= 1; }
+      fs += 2;
+      if (fs >= TS_NXS) fs -= TS_NXS;
+      // drain this warp's share of a finished tile once the set is one stage into a LATER tile: its next weights are
+      // already in TMEM (the restart after the epilogue does not wait for them), and the tile it drains has long been
+      // dequantised completely, so waiting for its accumulator cannot deadlock
+      done_g += 2;
+      while (epi_tl < done_g / num_st) {
+        epilogue_share(epi_tl, q, 1 + set, 3, epi_base + uint32_t(4 + set * 4 + q) * 2048u);
+        ++epi_tl;
+      }
+    };
+    for (int it = 0; it < mine; it += TS_DIST) {
+#pragma unroll
+      for (int u = 0; u < TS_DIST; ++u) {
+        if (it + u < mine) {
+          process(ring[u]);
+          prefetch(ring[u]);
+        }
+      }
+    }
+    for (; epi_tl < my_tiles; ++epi_tl) epilogue_share(epi_tl, q, 1 + set, 3, epi_base + uint32_t(4 + set * 4 + q) * 2048u);
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+template <bool BF16>
+int launch_ts(const CUtensorMap& mx, const CUtensorMap& my, const TsParams& p, cudaStream_t st) {
+  auto kern = qdm_w4ts_kernel<BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t tiles = int64_t((p.N + 255) / 256) * ((p.M + p.tile_t - 1) / p.tile_t);
+  const int pairs = int(tiles < QDM_NUM_SMS / 2 ? tiles : QDM_NUM_SMS / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(2 * pairs));
+  cfg.blockDim = dim3(TS_THREADS);
+  cfg.dynamicSmemBytes = TS_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+#ifdef QDM_TRACE
+  if (getenv("QDM_TRACE")) {   // debug build only: per-role clock64 timeline of the first CTA pair (tools/trace_view.py)
+    static long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(&tbuf, 16 * 2048 * sizeof(long long));
+    cudaMemset(tbuf, 0, 16 * 2048 * sizeof(long long));
+    TsParams pt = p;
+    pt.trace = tbuf;
+    kern<<<2 * pairs, TS_THREADS, TS_SMEM_BYTES, st>>>(mx, my, pt);
+    cudaDeviceSynchronize();
+    static long long host[16 * 2048];
+    cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "QDMTRACE begin M=%d N=%d K=%d tile_t=%d (TS)\n", p.M, p.N, p.K, p.tile_t);
+    for (int r = 0; r < 16; ++r)
+      for (int i = 0; i < 1000 && host[r * 2048 + 2 * i]; ++i)
+        fprintf(stderr, "QDMTRACE %d %lld %lld\n", r, host[r * 2048 + 2 * i], host[r * 2048 + 2 * i + 1]);
+    QDM_LAUNCH_CHECK();
+    return QDM_OK;
+  }
+#endif
+  QDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, p));
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
+}  // namespace
+
+// layout of the TS blob: [words: K/64 x N x 32 bytes][sz: K/64 x N x 4 bytes]
+extern "C" size_t qdm_w4a16_repack_ts_bytes(int64_t N, int64_t K) {
+  if (N <= 0 || K <= 0 || K % 64) return 0;
+  return size_t(K / 64) * size_t(N) * 36;
+}
+
+extern "C" int qdm_w4a16_repack_ts(const int32_t* qweight, const int32_t* qzeros, const void* scales, int dtype, int64_t N, int64_t K,
+                                   int group, void* blob, size_t blob_bytes, void* stream) {
+  QDM_REQUIRE(qweight && qzeros && scales && blob, "qdm_w4a16_repack_ts: null pointer");
+  QDM_REQUIRE(dtype == QDM_F16 || dtype == QDM_BF16, "qdm_w4a16_repack_ts: dtype must be f16 or bf16");
+  QDM_REQUIRE(N > 0 && K > 0 && N % 8 == 0 && K % 64 == 0 && N < (1LL << 31) && K < (1LL << 31),
+              "qdm_w4a16_repack_ts: N=%lld must be a multiple of 8 and K=%lld of 64", (long long)N, (long long)K);
+  QDM_REQUIRE(group > 0 && group % 64 == 0 && K % group == 0, "qdm_w4a16_repack_ts: group=%d must be a multiple of 64 dividing K", group);
+  QDM_REQUIRE(blob_bytes >= qdm_w4a16_repack_ts_bytes(N, K) && qdm_aligned16(blob), "qdm_w4a16_repack_ts: blob needs %zu bytes, 16-byte aligned",
+              qdm_w4a16_repack_ts_bytes(N, K));
+  QDM_DEVICE_GATE();
+  const int64_t items = (K / 64) * N;
+  uint32_t* words = static_cast<uint32_t*>(blob);
+  uint32_t* sz = words + items * 8;
+  const unsigned grid = unsigned((items + 255) / 256);
+  if (dtype == QDM_BF16)
+    w4ts_repack_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(qweight, qzeros, static_cast<const uint16_t*>(scales), int(N), int(K), group, words, sz);
+  else
+    w4ts_repack_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(qweight, qzeros, static_cast<const uint16_t*>(scales), int(N), int(K), group, words, sz);
+  QDM_LAUNCH_CHECK();
+  return QDM_OK;
+}
+
+// Called by the W4A16 dispatcher (qdm_gemm.cu) once it has picked the TS path with `tile_t` tokens per tile.
+int qdm_w4ts_gemm(const void* x, const void* blob, const void* bias, void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int tile_t,
+                  cudaStream_t st) {
+  QDM_REQUIRE(blob && qdm_aligned16(blob), "qdm_gemm_w4a16_ts: the repacked weight must be 16-byte aligned");
+  QDM_REQUIRE(tile_t >= 32 && tile_t <= 256 && tile_t % 32 == 0, "qdm_gemm_w4a16_ts: bad token tile %d", tile_t);
+  QDM_REQUIRE(K % 64 == 0 && N % 8 == 0, "qdm_gemm_w4a16_ts: shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  int rc = get_encode_fn();
+  if (rc) return rc;
+  CUtensorMap mx, my;
+  if ((rc = make_map(&mx, x, 2, M, K, 64, BLOCK_M))) return rc;            // 64 k x 128 token rows, SWIZZLE_128B
+  if ((rc = make_map(&my, y, 2, M, N, 32, 32, false))) return rc;         // 32 channels x 32 tokens, dense
+  TsParams p{};
+  p.M = int(M); p.N = int(N); p.K = int(K); p.tile_t = tile_t; p.bias = bias; p.y = y;
+  p.words = static_cast<const uint32_t*>(blob);
+  p.sz = p.words + (K / 64) * N * 8;
+  return is_bf16 ? launch_ts<true>(mx, my, p, st) : launch_ts<false>(mx, my, p, st);
+}

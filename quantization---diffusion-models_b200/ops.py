@@ -411,7 +411,7 @@ def _set_gemm_workspace(L, device):
     _gemm_ws[device.index] = buf
 
 
-GEMM_VARIANTS = {1: "single", 2: "pair", 3: "bstat", 4: "streamk", 5: "skinny", 6: "smallm", 7: "rp1", 8: "rp2", 9: "quad"}
+GEMM_VARIANTS = {1: "single", 2: "pair", 3: "bstat", 4: "streamk", 5: "skinny", 6: "smallm", 7: "rp1", 8: "rp2", 9: "quad", 10: "ts"}
 
 
 def gemm_last_variant():
@@ -438,7 +438,23 @@ def w4a16_repack(qweight, qzeros, scales, group):
     return blob
 
 
-def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None):
+def w4a16_repack_ts(qweight, qzeros, scales, group):
+    """Kernel-native copy of an AWQ weight for the TMEM-A kernel (include/qdm.h: qdm_w4a16_repack_ts) -> uint8 blob."""
+    _cuda(qweight, "qweight")
+    k, nw = qweight.shape
+    n = nw * 8
+    if tuple(qzeros.shape) != (k // group, nw) or tuple(scales.shape) != (k // group, n):
+        raise ValueError(f"qzeros{tuple(qzeros.shape)} / scales{tuple(scales.shape)} do not match qweight{tuple(qweight.shape)}, group {group}")
+    L = lib()
+    nbytes = int(L.qdm_w4a16_repack_ts_bytes(n, k))
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=qweight.device)
+    with _guard(qweight.device):
+        check(L.qdm_w4a16_repack_ts(qweight.contiguous().data_ptr(), qzeros.contiguous().data_ptr(), scales.contiguous().data_ptr(),
+                                    _dt(scales), n, k, int(group), blob.data_ptr(), nbytes, _stream(qweight)))
+    return blob
+
+
+def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=None):
     """x @ dequant(qweight, qzeros, scales) + bias, AWQ GEMM layout (quantize/quantizer.py:544-569).
     `blob` = w4a16_repack(...) of the same weight routes M > 128 problems to the repacked-weight kernel.
     This is the per-Linear hot call of a denoise step: the Python side is kept to the bare minimum."""
@@ -461,9 +477,10 @@ def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None):
     if x.device.index not in _gemm_ws:
         _set_gemm_workspace(L, x.device)
     with _guard(x.device):
-        rc = L.qdm_gemm_w4a16_rp(x2.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(),
-                                 0 if blob is None else blob.data_ptr(), 0 if bias is None else bias.data_ptr(), y.data_ptr(),
-                                 _DTYPES[x.dtype], m, n, k, group, torch.cuda.current_stream(x.device).cuda_stream)
+        rc = L.qdm_gemm_w4a16_plan(x2.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(),
+                                   0 if blob is None else blob.data_ptr(), 0 if blob_ts is None else blob_ts.data_ptr(),
+                                   0 if bias is None else bias.data_ptr(), y.data_ptr(),
+                                   _DTYPES[x.dtype], m, n, k, group, torch.cuda.current_stream(x.device).cuda_stream)
     if rc:
         check(rc)
     return y.reshape(*x.shape[:-1], n) if x.dim() != 2 else y

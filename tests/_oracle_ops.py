@@ -148,7 +148,7 @@ def w4a16_repack(qweight, qzeros, scales, group):
     return torch.zeros(16, dtype=torch.uint8)        # the kernel-native copy only exists on the device
 
 
-def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None):
+def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=None):
     return _linear(x, dequant_awq(qweight, qzeros, scales, group).t(), bias)
 
 

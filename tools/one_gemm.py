@@ -27,6 +27,10 @@ def main():
         qw, qz, sc, _ = q.ops.quant_pack_awq(w, grp)
         blob = q.ops.w4a16_repack(qw, qz, sc, grp)
         fn = lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp, None, blob)
+    elif kind == "w4ts":   # TMEM-A kernel; QDM_GEMM_MODE = 128 (+ tokens per tile << 8)
+        qw, qz, sc, _ = q.ops.quant_pack_awq(w, grp)
+        bts = q.ops.w4a16_repack_ts(qw, qz, sc, grp)
+        fn = lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp, None, None, bts)
     elif kind == "f16":
         fn = lambda: q.ops.gemm_f16(x, w)
     elif kind == "f16_kn":
