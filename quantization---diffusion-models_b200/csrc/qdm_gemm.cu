@@ -1773,18 +1773,19 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   return dispatch_gemm<G_F16_KN>(m, p, false, (cudaStream_t)stream);
 }
 
-// TS kernel (qdm_gemm_w4ts.cu): tokens per tile.  A pair owns 256 output channels x T tokens; T is any multiple of 16 <= 256,
-// chosen so that the last wave is not nearly empty.  Cycles per k-block: tensor pipe 2 T; the dequant sets deliver one A
-// stage (128 channels x 64 k per CTA) per ~300 cycles, whatever T is.
+// TS kernel (qdm_gemm_w4ts.cu): tokens per tile.  A pair owns 256 output channels x T tokens, T a multiple of 32 <= 192.
+// Per tile a CTA moves K/64 x (64 T + 4608) bytes from L2 (its T/2 token rows + 128 channels of packed weights) at
+// ~39 B/clk/SM (the measured L2 -> SM rate with every SM pulling) against 2 T cycles of tensor-pipe time per k-block; the
+// epilogue is hidden (two accumulator buffers).  T is chosen so that the last wave is not nearly empty.
 int choose_ts_tile(int64_t M, int64_t N, int64_t K, double* cost_out) {
   const int64_t P = QDM_NUM_SMS / 2, n_blks = (N + 255) / 256, num_kb = K / 64;
-  int best = 256;
+  int best = 192;
   double best_cost = 1e300;
-  for (int t = 256; t >= 32; t -= 32) {   // multiples of 32: the epilogue stores 32-token boxes
+  for (int t = 192; t >= 32; t -= 32) {   // multiples of 32: the epilogue stores 32-token boxes
     if (g_force_tile && t != g_force_tile) continue;
     const int64_t tiles = n_blks * ((M + t - 1) / t), waves = (tiles + P - 1) / P;
-    const double perkb = (2.0 * t > 300.0 ? 2.0 * t : 300.0) + 40.0;
-    const double cost = double(waves) * (double(num_kb) * perkb + 600.0 + 6.0 * t);   // + the tile's exposed epilogue
+    const double mma = 2.0 * t, l2 = (64.0 * t + 4608.0) / 39.0;
+    const double cost = double(waves) * (double(num_kb) * ((mma > l2 ? mma : l2) + 30.0) + 800.0);
     if (cost < best_cost * 0.999) { best_cost = cost; best = t; }
   }
   if (cost_out) *cost_out = best_cost;
@@ -1818,11 +1819,29 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
     note_variant(QDM_GEMM_SMALLM, 0);
     return qdm_gemm_w4a16_smallm(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);
   }
-  // Weights as the TMEM A operand (forced only until its dispatch rule is calibrated: mode 128)
-  if (blob_ts && !conv && g_force_ctas == 128 && K >= 128 && M >= 16) {
+  // Weights as the TMEM A operand (qdm_gemm_w4ts.cu).  Measured against the kernels below (profiles/README.md, round 2):
+  // it wins by 10-20 % wherever the problem is a few waves of tiles -- 8192 x 1280 x 1280: 29.5 vs 34.8 us, 4096 x 2432 x 2432:
+  // 46.6 vs 56.1, 4096 x 1280 x 1280: 20.5 vs 24.0, the text-token shapes 1232 x 1280 x 768: 8.4 vs 10.4 and 333 x 2432 x 2432:
+  // 17.9 vs 20.7 (any multiple of 32 tokens per tile, a hidden epilogue, no shared-memory round trip of the weights) --
+  // and ties or loses by ~5 % on the many-wave shapes (4096 x 10240 x 1280: 93 vs 88 us), where both sit at the same
+  // ~54 % tensor-pipe utilisation; K <= 384 with many tiles stays on the B-stationary kernel.
+  if (blob_ts && !conv && K >= 128 && M > 32 && (g_force_ctas == 128 || (g_force_ctas == 0 && !g_no_rp && !opt.no_rp))) {
+    bool take = g_force_ctas == 128;
     const int t = choose_ts_tile(M, N, K, nullptr);
-    note_variant(QDM_GEMM_TS, t);
-    return qdm_w4ts_gemm(x, blob_ts, bias, y, dtype == QDM_BF16, M, N, K, t, (cudaStream_t)stream);
+    if (!take) {
+      const int64_t tiles = ((N + 255) / 256) * ((M + t - 1) / t);
+      bool bstat = false;
+      if (K <= 64 * CfgBS::BST_KB && N % 32 == 0 && M > BLOCK_M && !opt.no_bstat && !opt.no_tma) {
+        const int tn = choose_tile_n(M, N, 2);
+        const int64_t m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + tn - 1) / tn, max_pairs = QDM_NUM_SMS / 2;
+        bstat = n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs;
+      }
+      take = !bstat && K >= 256 && tiles <= 6 * (QDM_NUM_SMS / 2);
+    }
+    if (take) {
+      note_variant(QDM_GEMM_TS, t);
+      return qdm_w4ts_gemm(x, blob_ts, bias, y, dtype == QDM_BF16, M, N, K, t, (cudaStream_t)stream);
+    }
   }
   // Repacked weights: every CTA-pair problem except the small-K / many-tile ones the B-stationary kernel keeps
   // (K >= 192: the last-tile helpers' barrier-parity argument needs >= 3 k-blocks per tile, see qdm_gemm_w4rp.cu)

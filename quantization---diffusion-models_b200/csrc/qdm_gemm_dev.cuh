@@ -75,6 +75,20 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity, int li
     }
   }
 }
+// Non-blocking phase test: 1 if the phase with this parity has completed.  The MMA issuer PEEKS at the next stage's barrier
+// before issuing the current stage's tcgen05.mma: the result is consumed only after those are queued, so the ~250 cycles
+// of barrier latency overlap tensor-pipe work instead of idling it once per stage.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -19,14 +19,15 @@
 // Dequant arithmetic is unchanged: (q - z) exact in the 16-bit type (magic-number trick), * s with one rounding --
 // bit-identical to dequantize_gemm (utils/packing_utils.py:87-102).
 //
-// Tile: a CTA pair owns 256 output channels (128 TMEM lanes per CTA) x T <= 256 tokens (cta_group::2, M = 256, N = T).
-// TMEM per CTA: columns [0, 256) fp32 accumulator, [256, 512) the A ring: 4 stages of 64 columns (128 k as 64 half2);
-// shared memory: 6 stages of 32 KB of activations.
+// Tile: a CTA pair owns 256 output channels (128 TMEM lanes per CTA) x T <= 192 tokens (cta_group::2, M = 256, N = T).
+// TMEM per CTA (512 columns): TWO fp32 accumulators of DW columns (the epilogue of tile t overlaps the main loop of tile
+// t + 1 -- measured on the single-buffered first version: 5700 of 18400 cycles per tile were the exposed epilogue) and the
+// weight ring in the rest: DW = 128 -> 4 stages of 64 columns (128 k as 64 half2), DW = 192 -> 2 stages.
 // A pipeline stage is K = 128 (two k-blocks): the single MMA-issuing thread pays ~250 cycles of serial latency per
-// barrier wait (measured), so it gets ONE full / empty barrier pair per stage and 8 tcgen05.mma per wait.
+// barrier wait (measured), so it gets ONE full barrier per stage and 8 tcgen05.mma per wait.
 // Roles (16 warps): warp 0 TMA producer of x (each CTA T/2 token rows), warp 1 MMA issuer (leader CTA), warp 2 TMEM
-// allocator, warps 4-7 epilogue (TMEM -> registers -> +bias -> 16-bit -> 64-byte row segments of y[tokens, channels]),
-// warps 8-11 / 12-15 two dequant sets taking even / odd k-blocks (A stage = k-block % 8, so every stage belongs to one set).
+// allocator, warps 4-7 epilogue (TMEM -> registers -> +bias -> 16 bit -> shared [32 tokens][128 channels] -> one TMA store
+// of 256-byte rows per 32 tokens), warps 8-11 / 12-15 two dequant sets taking even / odd stages.
 #include "qdm_gemm_dev.cuh"
 #include <stdlib.h>
 
@@ -34,18 +35,34 @@ using namespace qdmg;
 
 namespace {
 
+#ifndef TS_ORDER
+#define TS_ORDER 0   // 0: token blocks fastest (pairs share a weight slab), 1: channel blocks fastest (pairs share a token tile)
+#endif
+#define TS_NBLK(tile) (TS_ORDER ? (tile) % n_blks : (tile) / m_blks)
+#define TS_MBLK(tile) (TS_ORDER ? (tile) / n_blks : (tile) % m_blks)
 constexpr int TS_KB = 2;                       // k-blocks (64 k) per pipeline stage: K = 128 per stage
-constexpr int TS_NS = 4;                       // weight stages in TMEM (64 columns each)
-constexpr int TS_NXS = 6;                      // activation stages in shared memory (32 KB each): the L2 -> SM latency under load
-                                               // is 3000-5000 cycles (measured), i.e. more than 4 stages of tensor-pipe time
-constexpr int TS_STAGE_BYTES = TS_KB * A_STAGE_BYTES;
-constexpr int TS_A_COL0 = 256;                 // first TMEM column of the A ring
-constexpr int TS_A_COLS = TS_KB * 32;          // TMEM columns of one A stage (64 k as 32 half2 per k-block)
-constexpr int TS_DIST = 2;                     // packed words are prefetched this many of a set's stages ahead
-constexpr int TS_EPI_BYTES = 12 * 2048;        // per draining warp (4 epilogue + 8 dequant): one staging tile of 32 tokens x 32 channels x 2 B
+constexpr int TS_DIST = 1;                     // packed words are prefetched this many of a set's stages ahead (one set stage = two
+                                               // pipeline stages of lead time; the registers go to the unpacked values instead)
 constexpr int TS_BAR_BYTES = 512;
-constexpr int TS_SMEM_BYTES = TS_NXS * TS_STAGE_BYTES + TS_EPI_BYTES + 1024 + TS_BAR_BYTES;
 constexpr int TS_THREADS = 512;
+
+// DW = TMEM columns of ONE accumulator buffer = most tokens per tile.  Two buffers (the epilogue of tile t overlaps the
+// main loop of tile t + 1) + the weight ring share the 512 columns: DW = 128 -> 4 weight stages, DW = 192 -> 2.
+template <int DW>
+struct CfgTS {
+  static constexpr int NS = (512 - 2 * DW) / 64;             // weight stages in TMEM (64 columns = 128 k each)
+  static constexpr int A_COL0 = 2 * DW;
+  static constexpr int KB_BYTES = DW * 64;                   // one k-block of activations: DW / 2 token rows x 128 B
+  static constexpr int X_STAGE_BYTES = TS_KB * KB_BYTES;
+  // activation stages in shared memory: deeper than the weight ring -- the L2 -> SM latency under load is 3000-5000
+  // cycles (measured), several stages of tensor-pipe time
+  static constexpr int NXS = DW == 128 ? 8 : 6;
+  static constexpr int EPI_BYTES = 2 * 32 * 256;             // two staging tiles [32 tokens][128 channels] x 2 B
+  static constexpr int SMEM_BYTES = NXS * X_STAGE_BYTES + EPI_BYTES + 1024 + TS_BAR_BYTES;
+  static_assert(NS >= 2 && NS % 2 == 0 && NXS % 2 == 0, "ring slots must keep their dequant set");
+  static_assert(8 * (2 * NXS + NS + 4) + 8 <= TS_BAR_BYTES, "barrier area");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
 
 // ---------------------------------------------------------------- one-time repack
 // words[kb][n][8]: nibble i of word j = code of k = 64 kb + 8 j + {0,2,4,6,1,3,5,7}[i] of output channel n
@@ -119,29 +136,28 @@ struct TsParams {
 };
 
 // ---------------------------------------------------------------- the kernel
-template <bool BF16>
+template <int DW, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TS_THREADS, 1)
 qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const TsParams p) {
+  using C = CfgTS<DW>;
+  constexpr int NS = C::NS, NXS = C::NXS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + TS_NXS * TS_STAGE_BYTES;
-  const uint32_t bar_base = epi_base + TS_EPI_BYTES;
+  const uint32_t epi_base = smem_base + NXS * C::X_STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_BYTES;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   // ONE full barrier per stage: the MMA issuer is a single thread whose barrier waits are serial latency (measured: ~250
-  // cycles per wait on a barrier that is already complete), so a stage costs it one wait.  full[g % 6] collects, for
+  // cycles per wait even on a complete barrier), so a stage of K = 128 costs it one wait.  full[g % NXS] collects, for
   // global stage g, the leader's expect_tx (TMA bytes of both CTAs) and the 4 dequant warps of the stage's set in both
-  // CTAs.  The stage is released by two multicast commits: x_empty[g % 6] (awaited by the TMA producers) and
-  // a_empty[g % 4] (awaited by the dequant set that owns the TMEM slot).  6 and 4 are even, so a slot of either ring
+  // CTAs.  The stage is released by two multicast commits: x_empty[g % NXS] (awaited by the TMA producers) and
+  // a_empty[g % NS] (awaited by the dequant set that owns the TMEM slot).  NXS and NS are even, so a slot of either ring
   // always belongs to the same dequant set: nobody skips a phase of a barrier it waits on.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto x_empty_bar = [&](int s) { return bar_base + 8u * (TS_NXS + s); };
-  auto a_empty_bar = [&](int s) { return bar_base + 8u * (2 * TS_NXS + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * TS_NXS + TS_NS);
-  const uint32_t tmem_empty_bar = tmem_full_bar + 8u;
-  static_assert(8 * (2 * TS_NXS + TS_NS + 2) + 8 <= TS_BAR_BYTES, "barrier area");
-  static_assert(TS_NXS % 2 == 0 && TS_NS % 2 == 0, "ring slots must keep their dequant set");
-  static_assert(TS_A_COL0 + TS_NS * TS_A_COLS <= 512, "TMEM columns");
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * TS_NXS + TS_NS + 2));
+  auto x_empty_bar = [&](int s) { return bar_base + 8u * (NXS + s); };
+  auto a_empty_bar = [&](int s) { return bar_base + 8u * (2 * NXS + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * NXS + NS + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * NXS + NS + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * NXS + NS + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -155,10 +171,9 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_y); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TS_NXS; ++s) { mbar_init(full_bar(s), 9); mbar_init(x_empty_bar(s), 1); }   // 1 + 4 dequant warps x 2 CTAs
-    for (int s = 0; s < TS_NS; ++s) mbar_init(a_empty_bar(s), 1);
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, 24);                                                         // 12 draining warps x 2 CTAs
+    for (int s = 0; s < NXS; ++s) { mbar_init(full_bar(s), 9); mbar_init(x_empty_bar(s), 1); }   // 1 + 4 dequant warps x 2 CTAs
+    for (int s = 0; s < NS; ++s) mbar_init(a_empty_bar(s), 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }   // 4 epilogue warps x 2 CTAs
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -175,49 +190,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
-  const uint32_t leader_tmem_empty = mapa_shared(tmem_empty_bar, 0);
-
-  // One warp's share of a tile's epilogue: TMEM lane quarter ew (32 output channels), the 32-token chunks c_first,
-  // c_first + c_step, ...: tcgen05.ld -> + bias -> 16 bit -> shared staging [token][channel] (64-byte rows) -> one TMA store
-  // of the 32 x 32 box per chunk (clipped at N and M by the tensor map).  Three warps share a lane quarter -- the epilogue
-  // warp and the two dequant warps with the same warp % 4 -- and take every third chunk each.
-  auto epilogue_share = [&](int tl, int ew, int c_first, int c_step, uint32_t stg) {
-    const int tile = pair + tl * num_pairs;
-    const int n0 = (tile / m_blks) * 256 + int(rank) * 128 + ew * 32;     // this warp's 32 channels
-    const int m0 = (tile % m_blks) * T;
-    const int n = n0 + lane;
-    float bias = 0.f;
-    if (p.bias && n < p.N) {
-      if (BF16) bias = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
-      else bias = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
-    }
-    mbar_wait(tmem_full_bar, uint32_t(tl) & 1u);
-    tc_fence_after();
-    const int t_end = min(T, p.M - m0);
-    for (int c = 32 * c_first; c < t_end; c += 32 * c_step) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(c), v);
-      tmem_ld_wait();
-      if (lane == 0) tma_store_wait_read();                            // this warp's previous store has read the staging tile
-      __syncwarp();
-      if (n0 < p.N) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float f = __uint_as_float(v[j]) + bias;
-          uint16_t h;
-          if (BF16) { __nv_bfloat16 bb = __float2bfloat16_rn(f); h = *reinterpret_cast<uint16_t*>(&bb); }
-          else { __half bb = __float2half_rn(f); h = *reinterpret_cast<uint16_t*>(&bb); }
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(stg + uint32_t(j) * 64u + uint32_t(lane) * 2u), "h"(h) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) tma_store_2d(&map_y, stg, n0, m0 + c);
-      }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
-  };
+  const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
 
   if (warp == 0) {
     // ===================================================== TMA producer: x, this CTA's half of the tile's tokens
@@ -226,19 +199,19 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       uint32_t phase = 0;
       TRC_DECL;
       int trc_it = 0;
+      const uint32_t kb_bytes = uint32_t(th) * ROW_BYTES;               // the tensor map's box is th token rows x 64 k
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile % m_blks) * T + int(rank) * th;
+        const int m0 = TS_MBLK(tile) * T + int(rank) * th;
         for (int st = 0; st < num_st; ++st) {
           mbar_wait(x_empty_bar(stage), phase ^ 1);
           TRC(p.trace, 0, 2000000 + trc_it);
           ++trc_it;
-          // boxes are always 128 rows (rows past this CTA's T/2 are loaded and ignored, past M zero-filled)
           const int nk = min(TS_KB, num_kb - st * TS_KB);
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * nk * A_STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * uint32_t(nk) * kb_bytes);   // rows past M are zero-filled and counted
           for (int j = 0; j < nk; ++j)
-            tma_load_2d_pair(smem_base + stage * TS_STAGE_BYTES + j * A_STAGE_BYTES, &map_x, leader_full0 + 8u * stage,
+            tma_load_2d_pair(smem_base + stage * C::X_STAGE_BYTES + j * C::KB_BYTES, &map_x, leader_full0 + 8u * stage,
                              (st * TS_KB + j) * 64, m0);
-          if (++stage == TS_NXS) { stage = 0; phase ^= 1; }
+          if (++stage == NXS) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -247,42 +220,94 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 0, 2 * BLOCK_M, T);
       int stage = 0, as = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t phase = 0;
       TRC_DECL;
       int trc_it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        mbar_wait(tmem_empty_bar, acc_phase ^ 1);
+      uint32_t ready = 0;                                                // has the peek already seen this stage's barrier complete?
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(tmem_empty_bar(acc), (uint32_t(tl >> 1) & 1u) ^ 1u);
         TRC(p.trace, 1, 1000000 + trc_it);
         tc_fence_after();
+        const uint32_t tmem_c = tmem_base + uint32_t(acc * DW);
         for (int st = 0; st < num_st; ++st) {
-          mbar_wait(full_bar(stage), phase);
+          if (!ready) mbar_wait(full_bar(stage), phase);
           TRC(p.trace, 1, 2000000 + trc_it);
           ++trc_it;
           tc_fence_after();
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == NXS) { nstage = 0; nphase ^= 1; }
+          const uint32_t ready_next = mbar_test(full_bar(nstage), nphase);   // consumed after this stage's MMAs are queued
           const int nk = min(TS_KB, num_kb - st * TS_KB);
           for (int j = 0; j < nk; ++j) {
-            const uint32_t b_addr = smem_base + stage * TS_STAGE_BYTES + j * A_STAGE_BYTES;
+            const uint32_t b_addr = smem_base + stage * C::X_STAGE_BYTES + j * C::KB_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {   // 4 x 16 k: 8 TMEM columns of A, 32 bytes of every x row
               const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_pair_ts(tmem_base, tmem_base + uint32_t(TS_A_COL0 + as * TS_A_COLS + j * 32 + k * 8), db, idesc, (st | j | k) != 0);
+              umma_pair_ts(tmem_c, tmem_base + uint32_t(C::A_COL0 + as * 64 + j * 32 + k * 8), db, idesc, (st | j | k) != 0);
             }
           }
           umma_commit_pair(a_empty_bar(as), 3);
           umma_commit_pair(x_empty_bar(stage), 3);
           TRC(p.trace, 1, 3000000 + trc_it - 1);
-          if (st == num_st - 1) umma_commit_pair(tmem_full_bar, 3);
-          if (++stage == TS_NXS) { stage = 0; phase ^= 1; }
-          if (++as == TS_NS) as = 0;
+          if (st == num_st - 1) umma_commit_pair(tmem_full_bar(acc), 3);
+          stage = nstage; phase = nphase;
+          ready = ready_next;
+          if (++as == NS) as = 0;
         }
-        acc_phase ^= 1;
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================== epilogue: lanes = output channels, columns = tokens
+    // The four warps (one per TMEM lane quarter = 32 channels each) fill ONE staging tile [32 tokens][128 channels]
+    // (256-byte rows: a quarter of the TMA rows that per-warp 64-byte boxes need) and warp 4 stores it with one TMA
+    // store per 32 tokens; two staging tiles alternate.  The whole epilogue overlaps the next tile's main loop.
     const int ew = warp - 4;
-    for (int tl = 0; tl < my_tiles; ++tl) epilogue_share(tl, ew, 0, 3, epi_base + uint32_t(ew) * 2048u);
-    if (lane == 0) tma_store_wait_all();
+    TRC_DECL;
+    int trc_it = 0;
+    uint32_t chunk = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int tile = pair + tl * num_pairs, acc = tl & 1;
+      const int n0 = TS_NBLK(tile) * 256 + int(rank) * 128;               // this CTA's 128 channels
+      const int m0 = TS_MBLK(tile) * T;
+      const int n = n0 + ew * 32 + lane;
+      float bias = 0.f;
+      if (p.bias && n < p.N) {
+        if (BF16) bias = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
+        else bias = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
+      }
+      mbar_wait(tmem_full_bar(acc), uint32_t(tl >> 1) & 1u);
+      if (threadIdx.x == 128) TRC(p.trace, 2, 1000000 + trc_it);
+      tc_fence_after();
+      const int t_end = min(T, p.M - m0);
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * DW);
+      for (int c = 0; c < t_end; c += 32, ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(taddr + uint32_t(c), v);
+        const uint32_t stg = epi_base + (chunk & 1u) * 8192u;
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store of two chunks ago has read this tile
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float f = __uint_as_float(v[j]) + bias;
+          uint16_t h;
+          if (BF16) { __nv_bfloat16 bb = __float2bfloat16_rn(f); h = *reinterpret_cast<uint16_t*>(&bb); }
+          else { __half bb = __float2half_rn(f); h = *reinterpret_cast<uint16_t*>(&bb); }
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(stg + uint32_t(j) * 256u + uint32_t(ew * 32 + lane) * 2u), "h"(h) : "memory");
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128 && n0 < p.N) tma_store_2d(&map_y, stg, n0, m0 + c);   // 128 channels x 32 tokens, clipped at N and M
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (threadIdx.x == 128) TRC(p.trace, 2, 2000000 + trc_it);
+      ++trc_it;
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
+    }
+    if (threadIdx.x == 128) tma_store_wait_all();
   } else if (warp >= 8) {
     // ===================================================== dequant: registers -> TMEM
     const int set = (warp - 8) >> 2, q = warp & 3;                       // TMEM lane quarter = warp % 4
@@ -306,7 +331,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int j = 0; j < TS_KB; ++j) { f[j].w0 = make_uint4(0, 0, 0, 0); f[j].w1 = f[j].w0; f[j].sz = 0; }
       if (pf_g < total) {
         const int tile = pair + pf_tl * num_pairs;
-        const int n = (tile / m_blks) * 256 + int(rank) * 128 + q * 32 + lane;
+        const int n = TS_NBLK(tile) * 256 + int(rank) * 128 + q * 32 + lane;
         if (n < p.N) {
 #pragma unroll
           for (int j = 0; j < TS_KB; ++j) {
@@ -372,26 +397,24 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
       }
     };
-    int as = set % TS_NS, fs = set % TS_NXS;                            // TMEM slot, full-barrier slot of the set's next stage
-    uint32_t aph = uint32_t(set / TS_NS) & 1u;
-    int done_g = set - 2, epi_tl = 0;                                    // last stage processed (global), next tile to drain
+    int as = set % NS, fs = set % NXS;                                   // TMEM slot, full-barrier slot of the set's next stage
+    uint32_t aph = uint32_t(set / NS) & 1u;
     TRC_DECL;
     int trc_it = 0;
     auto process = [&](const Pf (&f)[TS_KB]) {
-      uint32_t o[32];
+      // BOTH k-blocks are unpacked before the TMEM slot is waited for: with a two-slot weight ring (DW = 192) the slot
+      // frees only when the MMAs two stages back have finished, and everything after the wait is exposed latency
+      // (measured: 780 cycles from slot-free to arrive when the second k-block was unpacked after the wait)
+      uint32_t o[TS_KB][32];
       if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 1000000 + trc_it);
-      unpack(f[0], o);
+#pragma unroll
+      for (int j = 0; j < TS_KB; ++j) unpack(f[j], o[j]);
       mbar_wait(a_empty_bar(as), aph ^ 1);
       if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 2000000 + trc_it);
       tc_fence_after();
-      const uint32_t a_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(TS_A_COL0 + as * TS_A_COLS);
-      tmem_st32(a_addr, o);
+      const uint32_t a_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(C::A_COL0 + as * 64);
 #pragma unroll
-      for (int j = 1; j < TS_KB; ++j) {
-        tmem_st_wait();                                                  // o is reused
-        unpack(f[j], o);
-        tmem_st32(a_addr + uint32_t(j) * 32u, o);
-      }
+      for (int j = 0; j < TS_KB; ++j) tmem_st32(a_addr + uint32_t(j) * 32u, o[j]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -399,17 +422,9 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 3000000 + trc_it);
       ++trc_it;
       as += 2;
-      if (as >= TS_NS) { as -= TS_NS; aph ^= 1; }
+      if (as >= NS) { as -= NS; aph ^= 1; }
       fs += 2;
-      if (fs >= TS_NXS) fs -= TS_NXS;
-      // drain this warp's share of a finished tile once the set is one stage into a LATER tile: its next weights are
-      // already in TMEM (the restart after the epilogue does not wait for them), and the tile it drains has long been
-      // dequantised completely, so waiting for its accumulator cannot deadlock
-      done_g += 2;
-      while (epi_tl < done_g / num_st) {
-        epilogue_share(epi_tl, q, 1 + set, 3, epi_base + uint32_t(4 + set * 4 + q) * 2048u);
-        ++epi_tl;
-      }
+      if (fs >= NXS) fs -= NXS;
     };
     for (int it = 0; it < mine; it += TS_DIST) {
 #pragma unroll
@@ -420,8 +435,6 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
       }
     }
-    for (; epi_tl < my_tiles; ++epi_tl) epilogue_share(epi_tl, q, 1 + set, 3, epi_base + uint32_t(4 + set * 4 + q) * 2048u);
-    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -432,26 +445,17 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
 }
 
-template <bool BF16>
+template <int DW, bool BF16>
 int launch_ts(const CUtensorMap& mx, const CUtensorMap& my, const TsParams& p, cudaStream_t st) {
-  auto kern = qdm_w4ts_kernel<BF16>;
+  using C = CfgTS<DW>;
+  auto kern = qdm_w4ts_kernel<DW, BF16>;
   static bool attr_set = false;
   if (!attr_set) {
-    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+    QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int64_t tiles = int64_t((p.N + 255) / 256) * ((p.M + p.tile_t - 1) / p.tile_t);
   const int pairs = int(tiles < QDM_NUM_SMS / 2 ? tiles : QDM_NUM_SMS / 2);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(unsigned(2 * pairs));
-  cfg.blockDim = dim3(TS_THREADS);
-  cfg.dynamicSmemBytes = TS_SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr.val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
 #ifdef QDM_TRACE
   if (getenv("QDM_TRACE")) {   // debug build only: per-role clock64 timeline of the first CTA pair (tools/trace_view.py)
     static long long* tbuf = nullptr;
@@ -459,7 +463,7 @@ int launch_ts(const CUtensorMap& mx, const CUtensorMap& my, const TsParams& p, c
     cudaMemset(tbuf, 0, 16 * 2048 * sizeof(long long));
     TsParams pt = p;
     pt.trace = tbuf;
-    kern<<<2 * pairs, TS_THREADS, TS_SMEM_BYTES, st>>>(mx, my, pt);
+    kern<<<2 * pairs, TS_THREADS, C::SMEM_BYTES, st>>>(mx, my, pt);
     cudaDeviceSynchronize();
     static long long host[16 * 2048];
     cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost);
@@ -471,6 +475,16 @@ int launch_ts(const CUtensorMap& mx, const CUtensorMap& my, const TsParams& p, c
     return QDM_OK;
   }
 #endif
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(2 * pairs));
+  cfg.blockDim = dim3(TS_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
   QDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, p));
   QDM_LAUNCH_CHECK();
   return QDM_OK;
@@ -510,16 +524,17 @@ extern "C" int qdm_w4a16_repack_ts(const int32_t* qweight, const int32_t* qzeros
 int qdm_w4ts_gemm(const void* x, const void* blob, const void* bias, void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int tile_t,
                   cudaStream_t st) {
   QDM_REQUIRE(blob && qdm_aligned16(blob), "qdm_gemm_w4a16_ts: the repacked weight must be 16-byte aligned");
-  QDM_REQUIRE(tile_t >= 32 && tile_t <= 256 && tile_t % 32 == 0, "qdm_gemm_w4a16_ts: bad token tile %d", tile_t);
+  QDM_REQUIRE(tile_t >= 32 && tile_t <= 192 && tile_t % 32 == 0, "qdm_gemm_w4a16_ts: bad token tile %d", tile_t);
   QDM_REQUIRE(K % 64 == 0 && N % 8 == 0, "qdm_gemm_w4a16_ts: shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   int rc = get_encode_fn();
   if (rc) return rc;
   CUtensorMap mx, my;
-  if ((rc = make_map(&mx, x, 2, M, K, 64, BLOCK_M))) return rc;            // 64 k x 128 token rows, SWIZZLE_128B
-  if ((rc = make_map(&my, y, 2, M, N, 32, 32, false))) return rc;         // 32 channels x 32 tokens, dense
+  if ((rc = make_map(&mx, x, 2, M, K, 64, tile_t / 2))) return rc;        // 64 k x (T / 2) token rows per CTA, SWIZZLE_128B
+  if ((rc = make_map(&my, y, 2, M, N, 128, 32, false))) return rc;        // 128 channels x 32 tokens, dense 256-byte rows
   TsParams p{};
   p.M = int(M); p.N = int(N); p.K = int(K); p.tile_t = tile_t; p.bias = bias; p.y = y;
   p.words = static_cast<const uint32_t*>(blob);
   p.sz = p.words + (K / 64) * N * 8;
-  return is_bf16 ? launch_ts<true>(mx, my, p, st) : launch_ts<false>(mx, my, p, st);
+  if (tile_t <= 128) return is_bf16 ? launch_ts<128, true>(mx, my, p, st) : launch_ts<128, false>(mx, my, p, st);
+  return is_bf16 ? launch_ts<192, true>(mx, my, p, st) : launch_ts<192, false>(mx, my, p, st);
 }

@@ -55,24 +55,24 @@ class WQLinear_GEMM(nn.Module):
         return m
 
     def _repacked(self):
-        """Kernel-native copy of the weight for the tcgen05 GEMM (ops.w4a16_repack), built on first use and rebuilt when
-        the buffers are replaced (load_state_dict, .to()).  Not part of the state dict: checkpoints keep the AWQ layout
-        of utils/packing_utils.py only.  Costs 0.54 B / weight of device memory next to the 0.5 B / weight of qweight."""
+        """Kernel-native copy of the weight for the tensor-memory-A GEMM (ops.w4a16_repack_ts), built on first use and rebuilt
+        when the buffers are replaced (load_state_dict, .to()).  Not part of the state dict: checkpoints keep the AWQ layout
+        of utils/packing_utils.py only.  Costs 0.56 B / weight of device memory next to the 0.5 B / weight of qweight."""
         key = (self.qweight.data_ptr(), self.qzeros.data_ptr(), self.scales.data_ptr(), self.qweight._version)
         rp = self.__dict__.get("_rp")
         if rp is None or rp[0] != key:
             if self.group_size % 64 or self.in_features % 64:
-                rp = (key, None)   # shapes the repacked-weight kernel does not tile
+                rp = (key, None)   # shapes the kernel does not tile
             else:
-                rp = (key, ops.w4a16_repack(self.qweight, self.qzeros, self.scales, self.group_size))
+                rp = (key, ops.w4a16_repack_ts(self.qweight, self.qzeros, self.scales, self.group_size))
             self.__dict__["_rp"] = rp
         return rp[1]
 
     def forward(self, x):
         blob = self._repacked() if self.repack else None
         if x.dtype == self.scales.dtype:
-            return ops.gemm_w4a16(x, self.qweight, self.qzeros, self.scales, self.group_size, self.bias, blob)
-        return ops.gemm_w4a16(x.to(self.scales.dtype), self.qweight, self.qzeros, self.scales, self.group_size, self.bias, blob).to(x.dtype)
+            return ops.gemm_w4a16(x, self.qweight, self.qzeros, self.scales, self.group_size, self.bias, None, blob)
+        return ops.gemm_w4a16(x.to(self.scales.dtype), self.qweight, self.qzeros, self.scales, self.group_size, self.bias, None, blob).to(x.dtype)
 
     def dequantize(self):
         """[N, K] fake-quant weight (utils/packing_utils.py:87-102, transposed back to nn.Linear layout)."""

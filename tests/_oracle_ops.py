@@ -148,6 +148,9 @@ def w4a16_repack(qweight, qzeros, scales, group):
     return torch.zeros(16, dtype=torch.uint8)        # the kernel-native copy only exists on the device
 
 
+w4a16_repack_ts = w4a16_repack
+
+
 def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=None):
     return _linear(x, dequant_awq(qweight, qzeros, scales, group).t(), bias)
 
@@ -178,7 +181,7 @@ def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
 
 NAMES = ("colabsmax", "colabssum", "colstats", "rowabsmax", "absmax", "awq_wsum", "sqdiff_sum", "quant_group",
          "quant_rowwise", "quant_tensor", "actquant_token_i8", "quant_pack_awq", "dequant_awq", "pack_awq", "unpack_awq",
-         "awq_clip_search", "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16")
+         "awq_clip_search", "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "w4a16_repack_ts", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16")
 
 
 @contextlib.contextmanager

@@ -56,8 +56,8 @@ def expected_variants(M, N, K):
     if M <= 32:
         return {"skinny", "smallm"}
     if M <= 128:
-        return {"single"}
-    return {"pair", "bstat", "streamk", "rp2"}
+        return {"single", "ts"}
+    return {"pair", "bstat", "streamk", "ts"}
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
@@ -81,9 +81,11 @@ def test_w4a16_baseline_shape(qdm, model, M, N, K, dt):
     err = rel_err_gpu(y, ref)
     assert err <= TOL, (variant, tile, err)
     assert torch.isfinite(y).all()
-    # the two-wave layers that one wave of 256 x 320 tiles covers must actually take the wide-tile kernel
-    if (M, N, K) in ((4096, 1280, 1280), (4096, 1280, 5120)):
-        assert variant == "rp2" and tile == 320, (variant, tile)
+    # the few-wave layers must take the tensor-memory-A kernel, the many-wave / small-K ones the others
+    if (M, N, K) in ((4096, 1280, 1280), (8192, 1280, 1280), (4096, 2432, 2432), (1232, 1280, 768), (333, 2432, 2432)):
+        assert variant == "ts", (variant, tile)
+    if (M, N, K) in ((4096, 10240, 1280), (65536, 320, 320), (65536, 2560, 320)):
+        assert variant in ("pair", "bstat"), (variant, tile)
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
@@ -193,3 +195,47 @@ def test_w4a16_repack_layout(qdm):
                 z_pad[:N // 8] = qzeros[kk // group]
                 assert torch.equal(sc[a, :, h].reshape(-1), s_pad)
                 assert torch.equal(zw[a, :, h].reshape(-1), z_pad)
+
+
+TS_CASES = [(256, 256, 128, 128), (300, 320, 320, 64), (777, 520, 448, 64), (4096, 1280, 1280, 128), (1232, 1280, 768, 128),
+            (333, 2432, 2432, 128), (4096, 64, 2432, 128), (8192, 640, 2560, 128), (129, 72, 256, 128), (200, 8, 128, 128),
+            (64, 1280, 320, 64), (4096, 2560, 320, 64), (616, 1280, 2048, 256), (1000, 40, 192, 64)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("M,N,K,group", TS_CASES)
+def test_w4a16_tmem_a_kernel(qdm, M, N, K, group, dt):
+    """The kernel that feeds the dequantised weights to tcgen05.mma as its A operand from tensor memory (output channels on
+    the TMEM lanes, tokens along N), at every token-tile width, against the fp32 reference and against the kernels that
+    read the AWQ tensors (same dequantised values: only the fp32 summation order may differ, <= one output ulp at the
+    largest magnitude); ragged M / N / K-tail shapes included; twice for determinism."""
+    import oracle.qdm_oracle as O
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DT[dt]).to(DEV)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DT[dt])
+    b = torch.randn(N, generator=g).to(DT[dt]).to(DEV)
+    if N % 64 == 0:
+        qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(w.to(DEV), group, want_dq=True)
+    else:
+        oq, oz, os_, dq = O.awq_from_linear(w, group, 4)
+        qweight, qzeros, scales, dq = torch.from_numpy(oq).to(DEV), torch.from_numpy(oz).to(DEV), os_.to(DEV), dq.to(DEV)
+    bts = qdm.ops.w4a16_repack_ts(qweight, qzeros, scales, group)
+    ref = ref_linear_gpu(x, dq, b)
+    ulp = 2e-3 if dt == "f16" else 8e-3
+    try:
+        qdm.ops.set_gemm_mode(64)                            # the AWQ-tensor kernels
+        y_awq = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b, None, bts)
+        assert qdm.ops.gemm_last_variant()[0] != "ts"
+        for width in (0, 32, 64, 96, 128, 160, 192):
+            qdm.ops.set_gemm_mode(128 | (width << 8))
+            y1 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b, None, bts)
+            variant, tile = qdm.ops.gemm_last_variant()
+            assert variant == "ts" and (width == 0 or tile == width), (variant, tile)
+            y2 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, None, None, bts)      # also without bias
+            y3 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b, None, bts)
+            assert torch.equal(y1, y3), width                # deterministic
+            assert rel_err_gpu(y1, ref) <= TOL, width
+            assert rel_err_gpu(y1, y_awq.float()) <= ulp, width
+            assert rel_err_gpu(y2, ref - b.float()) <= TOL, width
+    finally:
+        qdm.ops.set_gemm_mode(0)
