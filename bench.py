@@ -595,7 +595,9 @@ def run_tables(args):
         qw, qz, sc, dq = q.ops.quant_pack_awq(w, grp, want_dq=True)
         flops = 2.0 * m * n * k
         r = {"M": m, "N": n, "K": k, "group": grp, "calls_per_step": counts.get((m, n, k), 1)}
-        t = time_fn(lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp))
+        bts = q.ops.w4a16_repack_ts(qw, qz, sc, grp)     # the kernel-native copy WQLinear_GEMM keeps (dispatch as in the module)
+        t = time_fn(lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp, None, None, bts))
+        r["w4a16_kernel"] = list(q.ops.gemm_last_variant())
         by = shapes_mod.gemm_bytes_w4a16(m, n, k, grp)
         roof = min(peaks["bf16_burst"], by and flops / by * peaks["hbm"] / 1e3)
         r["w4a16"] = {"ms": t, "tflops": flops / t / 1e9, "gbs": by / t / 1e6, "roof_tflops": roof, "frac": flops / t / 1e9 / roof}
@@ -613,7 +615,7 @@ def run_tables(args):
             r["w8a8_actquant"] = {"ms": t2, "gbs": 3.0 * m * k / t2 / 1e6}
         rows.append(r)
         print(json.dumps(r), flush=True)
-        del x, w, qw, qz, sc, dq
+        del x, w, qw, qz, sc, dq, bts
     summary = None
     if not args.sweep:   # the whole Linear pass of one denoise step, every launch timed alone with a cold L2
         tot_f = sum(2.0 * r["M"] * r["N"] * r["K"] * r["calls_per_step"] for r in rows)

@@ -1532,10 +1532,13 @@ int launch_bstat(const Maps& m, const GemmParams& p, int pairs, cudaStream_t st)
 // Bring-up / A-B switches.  The environment is read ONCE (first GEMM call of the process), never in the per-call path.
 struct W4Opts {
   bool no_smallm, no_skinny, no_tma, no_bstat, no_sk, no_rp;
+  int ts_waves, ts_fit;   // A/B knobs of the TS dispatch rule (QDM_W4_TS_WAVES, QDM_W4_TS_FIT), read once
   W4Opts()
       : no_smallm(getenv("QDM_W4_NO_SMALLM") != nullptr), no_skinny(getenv("QDM_W4_NO_SKINNY") != nullptr),
         no_tma(getenv("QDM_W4_NO_TMA") != nullptr), no_bstat(getenv("QDM_W4_NO_BSTAT") != nullptr),
-        no_sk(getenv("QDM_W4_NO_SK") != nullptr), no_rp(getenv("QDM_W4_NO_RP") != nullptr) {}
+        no_sk(getenv("QDM_W4_NO_SK") != nullptr), no_rp(getenv("QDM_W4_NO_RP") != nullptr),
+        ts_waves(getenv("QDM_W4_TS_WAVES") ? atoi(getenv("QDM_W4_TS_WAVES")) : 6),
+        ts_fit(getenv("QDM_W4_TS_FIT") ? atoi(getenv("QDM_W4_TS_FIT")) : 11) {}
 };
 const W4Opts& w4_opts() {
   static const W4Opts o;
@@ -1836,7 +1839,9 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
         const int64_t m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + tn - 1) / tn, max_pairs = QDM_NUM_SMS / 2;
         bstat = n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs;
       }
-      take = !bstat && K >= 256 && tiles <= 6 * (QDM_NUM_SMS / 2);
+      // 256-channel blocks: N = 640 (2.5 blocks) or 320 would idle a fifth or more of the MMA rows and dequant warps
+      const bool fits_n = ((N + 255) / 256) * 256 * 10 <= int64_t(N) * opt.ts_fit;
+      take = !bstat && fits_n && K >= 256 && tiles <= int64_t(opt.ts_waves) * (QDM_NUM_SMS / 2);
     }
     if (take) {
       note_variant(QDM_GEMM_TS, t);

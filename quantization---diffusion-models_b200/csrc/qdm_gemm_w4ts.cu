@@ -56,7 +56,13 @@ struct CfgTS {
   static constexpr int X_STAGE_BYTES = TS_KB * KB_BYTES;
   // activation stages in shared memory: deeper than the weight ring -- the L2 -> SM latency under load is 3000-5000
   // cycles (measured), several stages of tensor-pipe time
-  static constexpr int NXS = DW == 128 ? 8 : 6;
+#ifndef TS_NXS192
+#define TS_NXS192 6
+#endif
+#ifndef TS_NXS128
+#define TS_NXS128 8
+#endif
+  static constexpr int NXS = DW == 128 ? TS_NXS128 : TS_NXS192;
   static constexpr int EPI_BYTES = 2 * 32 * 256;             // two staging tiles [32 tokens][128 channels] x 2 B
   static constexpr int SMEM_BYTES = NXS * X_STAGE_BYTES + EPI_BYTES + 1024 + TS_BAR_BYTES;
   static_assert(NS >= 2 && NS % 2 == 0 && NXS % 2 == 0, "ring slots must keep their dequant set");
