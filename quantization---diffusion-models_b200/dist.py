@@ -156,49 +156,48 @@ def exchange_captures(caps, wanted_by, rank, world, device):
       wanted_by : {block: [ranks]} -- who needs the block's inputs (one owner, or every rank when the ratio grid is split)
     Returns the same structure for the blocks `rank` wants, holding the chunks of every rank sorted by call_id, so the
     concatenation is the one a single process would have built: search results do not depend on the world size.
-    One metadata all_gather_object + one batch of point-to-point copies (NCCL: grouped; gloo in the CPU tests)."""
+    One metadata all_gather_object + one all_gather per block (NCCL; gloo in the CPU tests)."""
     mine = {b: {ln: list(ch) for ln, ch in lins.items()} for b, lins in caps.items() if rank in wanted_by.get(b, ())}
     if world == 1 or not (dist.is_available() and dist.is_initialized()):
         return mine
     meta = {b: {ln: [(cid, tuple(x.shape), str(x.dtype)) for cid, x in ch] for ln, ch in lins.items()} for b, lins in caps.items()}
     metas = [None] * world
     dist.all_gather_object(metas, meta)
-    comm_dev = device if dist.get_backend() == "nccl" else torch.device("cpu")
-    order = sorted(caps)   # identical module trees -> identical keys on every rank
-
-    def flat_for(dst):      # what this rank sends to dst: every chunk of the blocks dst wants, fixed order
-        parts = [x.reshape(-1) for b in order if dst in wanted_by.get(b, ()) for ln in caps[b] for _, x in caps[b][ln]]
-        return torch.cat(parts).to(comm_dev) if parts else None
-
-    ops, recv = [], {}
-    for peer in range(world):
-        if peer == rank:
+    nccl = dist.get_backend() == "nccl"
+    comm_dev = device if nccl else torch.device("cpu")
+    # One all_gather per block over the communicator's collective channels (NVLS / ring over NVSwitch), not point-to-point
+    # sends: the first send/recv between two ranks makes NCCL open a new peer connection -- measured 1.7 s at world 4 and
+    # ~8 s at world 8 for 56 pairs, against ~30 ms to move the ~10 GB of SD3.5-L captures through all_gather -- and in
+    # ratio-split mode every rank wants every block anyway.  A block's gather buffer is dropped at once by non-owners.
+    for b in sorted(caps):   # identical module trees -> identical keys and order on every rank
+        sizes = [sum(sh[0] * sh[1] for ch in metas[r][b].values() for _, sh, _ in ch) for r in range(world)]
+        n_max = max(sizes)
+        if n_max == 0:
             continue
-        out = flat_for(peer)
-        if out is not None and out.numel():
-            ops.append(dist.P2POp(dist.isend, out, peer))
-        n, dt = 0, None
-        for b in order:
-            if rank in wanted_by.get(b, ()):
-                for ln, ch in metas[peer][b].items():
-                    for _, shape, dts in ch:
-                        n += shape[0] * shape[1]
-                        dt = getattr(torch, dts.split(".")[-1])
-        if n:
-            recv[peer] = torch.empty(n, dtype=dt, device=comm_dev)
-            ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    for peer, buf in recv.items():
-        off = 0
-        for b in order:
-            if rank not in wanted_by.get(b, ()):
+        dts = {d for r in range(world) for ch in metas[r][b].values() for _, _, d in ch}
+        assert len(dts) == 1, f"captures of block {b} have mixed dtypes {dts}"
+        dt = getattr(torch, dts.pop().split(".")[-1])
+        send = torch.zeros(n_max, dtype=dt, device=comm_dev)
+        parts = [x.reshape(-1) for ch in caps[b].values() for _, x in ch]
+        if parts:
+            send[: sizes[rank]] = torch.cat(parts).to(comm_dev)
+        if nccl:
+            recv = torch.empty(world * n_max, dtype=dt, device=comm_dev)
+            dist.all_gather_into_tensor(recv, send)
+            bufs = [recv[r * n_max:(r + 1) * n_max] for r in range(world)]
+        else:
+            bufs = [torch.empty(n_max, dtype=dt) for _ in range(world)]
+            dist.all_gather(bufs, send)
+        if rank not in wanted_by.get(b, ()):
+            continue
+        for peer in range(world):
+            if peer == rank:
                 continue
+            off = 0
             for ln, ch in metas[peer][b].items():
                 for cid, shape, _ in ch:
                     n = shape[0] * shape[1]
-                    mine.setdefault(b, {}).setdefault(ln, []).append((cid, buf[off:off + n].reshape(shape).to(device)))
+                    mine.setdefault(b, {}).setdefault(ln, []).append((cid, bufs[peer][off:off + n].reshape(shape).to(device)))
                     off += n
     for lins in mine.values():
         for ln in lins:

@@ -159,6 +159,10 @@ class BaseAWQForDiffusion:
                     h = Input_Capture_Hook(self.calib_max_tokens, per_call)
                     h.hook_handle = lin.register_forward_hook(h)
                     hooks[(bn, ln)] = h
+        import time
+        on_gpu = torch.device(self.pipeline.device).type == "cuda"
+        sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+        t0 = time.perf_counter()
         for bi, (prompts, latents) in enumerate(samples):
             if bi % world != rank:
                 continue
@@ -169,8 +173,12 @@ class BaseAWQForDiffusion:
         for (bn, ln), h in hooks.items():
             h.hook_handle.remove()
             caps[bn][ln] = h.chunks
+        sync()
+        t1 = time.perf_counter()
         if world > 1:
             caps = exchange_captures(caps, wanted_by or {bn: [rank] for bn in block_names}, rank, world, self.pipeline.device)
+            sync()
+        self.capture_timings = {"capture_forward_s": t1 - t0, "capture_exchange_s": time.perf_counter() - t1}
         return {bn: {ln: Input_Capture_Hook.merge(ch, self.calib_max_tokens) for ln, ch in caps[bn].items()} for bn in block_names}
 
     def get_layers_for_scaling(self, block, input_feat):

@@ -179,6 +179,7 @@ class AwqQuantizer:
         t0 = time.perf_counter()
         feats = self.awq_model.capture_block_inputs(mine, shard=shard, wanted_by=wanted_by)
         lap("capture_s", t0)
+        tm.update(getattr(self.awq_model, "capture_timings", {}))
         # ---- phase A: scale search (loss tables), one collective when the ratio grid is split
         t0 = time.perf_counter()
         pending = {}
