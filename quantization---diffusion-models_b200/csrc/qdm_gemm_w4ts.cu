@@ -123,12 +123,67 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] . B[smem]; both CTAs of the pair hold their 128 rows of A at the same TMEM address
-__device__ __forceinline__ void umma_pair_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_c), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
-      : "memory");
+// One pipeline stage for the issuing thread: NKB x 4 tcgen05.mma (K = 16 each) with the NEXT stage's barrier tested at the
+// top and its predicate read (selp) only after the last MMA.  Measured with the QDM_TRACE timeline (profiles/README.md,
+// round 2): a barrier test costs the thread ~290 cycles when its result is consumed at once, each MMA ~80 cycles when its
+// shared-memory descriptor is rebuilt from the address (five dependent uniform-datapath instructions), a commit ~170 --
+// 1270 cycles of serial issue per K = 128 stage against 768 cycles of tensor-pipe work at 192 tokens.  Here the test's
+// latency overlaps the MMAs, and every descriptor is the previous one plus 2 (32 bytes >> 4) in the low word.
+template <int NKB>
+__device__ __forceinline__ uint32_t ts_issue_stage(uint32_t tmem_c, uint32_t tmem_a, uint32_t desc_lo, uint32_t desc_lo_step,
+                                                   uint32_t desc_hi, uint32_t idesc, uint32_t accum, uint32_t next_bar,
+                                                   uint32_t next_parity) {
+  uint32_t done;
+  if (NKB == 2) {
+    asm volatile(
+        "{\n\t.reg .pred pa, pt, pd, pe;\n\t.reg .b64 d;\n\t.reg .b32 lo, ta;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pd, [%8], %9;\n\t"
+        "setp.ne.b32 pa, %7, 0;\n\t"
+        "setp.eq.b32 pt, %7, %7;\n\t"
+        "mov.b64 d, {%3, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [%2], d, %6, pa;\n\t"
+        "add.u32 lo, %3, 2;\n\tadd.u32 ta, %2, 8;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "add.u32 lo, %3, 4;\n\tadd.u32 ta, %2, 16;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "add.u32 lo, %3, 6;\n\tadd.u32 ta, %2, 24;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pe, [%8], %9;\n\t"   // second look, ~300 cycles later
+        "add.u32 lo, %3, %4;\n\tadd.u32 ta, %2, 32;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "add.u32 lo, lo, 2;\n\tadd.u32 ta, %2, 40;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "add.u32 lo, lo, 2;\n\tadd.u32 ta, %2, 48;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "add.u32 lo, lo, 2;\n\tadd.u32 ta, %2, 56;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "or.pred pd, pd, pe;\n\t"
+        "selp.u32 %0, 1, 0, pd;\n\t}"
+        : "=r"(done)
+        : "r"(tmem_c), "r"(tmem_a), "r"(desc_lo), "r"(desc_lo_step), "r"(desc_hi), "r"(idesc), "r"(accum), "r"(next_bar),
+          "r"(next_parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pa, pt, pd;\n\t.reg .b64 d;\n\t.reg .b32 lo, ta;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pd, [%8], %9;\n\t"
+        "setp.ne.b32 pa, %7, 0;\n\t"
+        "setp.eq.b32 pt, %7, %7;\n\t"
+        "mov.b64 d, {%3, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [%2], d, %6, pa;\n\t"
+        "add.u32 lo, %3, 2;\n\tadd.u32 ta, %2, 8;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "add.u32 lo, %3, 4;\n\tadd.u32 ta, %2, 16;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "add.u32 lo, %3, 6;\n\tadd.u32 ta, %2, 24;\n\tmov.b64 d, {lo, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d, %6, pt;\n\t"
+        "selp.u32 %0, 1, 0, pd;\n\t}"
+        : "=r"(done)
+        : "r"(tmem_c), "r"(tmem_a), "r"(desc_lo), "r"(desc_lo_step), "r"(desc_hi), "r"(idesc), "r"(accum), "r"(next_bar),
+          "r"(next_parity)
+        : "memory");
+  }
+  return done;
 }
 
 struct TsParams {
@@ -155,12 +210,11 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   // ONE full barrier per stage: the MMA issuer is a single thread whose barrier waits are serial latency (measured: ~250
   // cycles per wait even on a complete barrier), so a stage of K = 128 costs it one wait.  full[g % NXS] collects, for
   // global stage g, the leader's expect_tx (TMA bytes of both CTAs) and the 4 dequant warps of the stage's set in both
-  // CTAs.  The stage is released by two multicast commits: x_empty[g % NXS] (awaited by the TMA producers) and
-  // a_empty[g % NS] (awaited by the dequant set that owns the TMEM slot).  NXS and NS are even, so a slot of either ring
-  // always belongs to the same dequant set: nobody skips a phase of a barrier it waits on.
+  // CTAs.  The stage is released by ONE multicast commit (a commit costs the issuer ~170 cycles): x_empty[g % NXS], awaited
+  // by the TMA producers (x slot g % NXS) and by the dequant set that writes TMEM slot g % NS next, i.e. for stage g + NS.
+  // NXS and NS are even, so a slot of either ring always belongs to the same dequant set.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto x_empty_bar = [&](int s) { return bar_base + 8u * (NXS + s); };
-  auto a_empty_bar = [&](int s) { return bar_base + 8u * (2 * NXS + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * NXS + NS + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * NXS + NS + 2 + a); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + (bar_base - smem_base) + 8 * (2 * NXS + NS + 4));
@@ -178,7 +232,6 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_y); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NXS; ++s) { mbar_init(full_bar(s), 9); mbar_init(x_empty_bar(s), 1); }   // 1 + 4 dequant warps x 2 CTAs
-    for (int s = 0; s < NS; ++s) mbar_init(a_empty_bar(s), 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }   // 4 epilogue warps x 2 CTAs
     fence_barrier_init();
   }
@@ -237,25 +290,27 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + uint32_t(acc * DW);
         for (int st = 0; st < num_st; ++st) {
+#ifndef TS_MMA_SPIN
           if (!ready) mbar_wait(full_bar(stage), phase);
-          TRC(p.trace, 1, 2000000 + trc_it);
+#else
+          if (!ready) mbar_spin(full_bar(stage), phase);
+#endif
+          TRC(p.trace, 1, (ready ? 2000000 : 9000000) + trc_it);    // 9 = the stage was not yet complete at the peek: waited
           ++trc_it;
           tc_fence_after();
           int nstage = stage + 1;
           uint32_t nphase = phase;
           if (nstage == NXS) { nstage = 0; nphase ^= 1; }
-          const uint32_t ready_next = mbar_test(full_bar(nstage), nphase);   // consumed after this stage's MMAs are queued
           const int nk = min(TS_KB, num_kb - st * TS_KB);
-          for (int j = 0; j < nk; ++j) {
-            const uint32_t b_addr = smem_base + stage * C::X_STAGE_BYTES + j * C::KB_BYTES;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {   // 4 x 16 k: 8 TMEM columns of A, 32 bytes of every x row
-              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_pair_ts(tmem_c, tmem_base + uint32_t(C::A_COL0 + as * 64 + j * 32 + k * 8), db, idesc, (st | j | k) != 0);
-            }
-          }
-          umma_commit_pair(a_empty_bar(as), 3);
-          umma_commit_pair(x_empty_bar(stage), 3);
+          const uint64_t db = make_smem_desc(smem_base + stage * C::X_STAGE_BYTES, 16, 1024);
+          const uint32_t ta = tmem_base + uint32_t(C::A_COL0 + as * 64);
+          // the next stage's barrier is tested inside the block (top) and its result read after the stage's last MMA
+          const uint32_t ready_next =
+              nk == 2 ? ts_issue_stage<2>(tmem_c, ta, uint32_t(db), uint32_t(C::KB_BYTES >> 4), uint32_t(db >> 32), idesc, uint32_t(st != 0),
+                                          full_bar(nstage), nphase)
+                      : ts_issue_stage<1>(tmem_c, ta, uint32_t(db), 0u, uint32_t(db >> 32), idesc, uint32_t(st != 0), full_bar(nstage), nphase);
+          TRC(p.trace, 1, 7000000 + trc_it - 1);
+          umma_commit_pair(x_empty_bar(stage), 3);   // the stage's x slot AND its TMEM weight slot: one commit, two kinds of waiters
           TRC(p.trace, 1, 3000000 + trc_it - 1);
           if (st == num_st - 1) umma_commit_pair(tmem_full_bar(acc), 3);
           stage = nstage; phase = nphase;
@@ -404,10 +459,10 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     };
     int as = set % NS, fs = set % NXS;                                   // TMEM slot, full-barrier slot of the set's next stage
-    uint32_t aph = uint32_t(set / NS) & 1u;
+    int wg = set - NS;                                                   // the global stage whose MMAs last read that TMEM slot
     TRC_DECL;
     int trc_it = 0;
-    auto process = [&](const Pf (&f)[TS_KB]) {
+    auto process = [&](Pf (&f)[TS_KB]) {
       // BOTH k-blocks are unpacked before the TMEM slot is waited for: with a two-slot weight ring (DW = 192) the slot
       // frees only when the MMAs two stages back have finished, and everything after the wait is exposed latency
       // (measured: 780 cycles from slot-free to arrive when the second k-block was unpacked after the wait)
@@ -415,7 +470,14 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 1000000 + trc_it);
 #pragma unroll
       for (int j = 0; j < TS_KB; ++j) unpack(f[j], o[j]);
-      mbar_wait(a_empty_bar(as), aph ^ 1);
+#ifndef TS_LATE_PREFETCH
+      // the packed words are dead once unpacked: load the set's NEXT stage into the same registers now, so the loads fly
+      // while this stage waits for its TMEM slot, stores and arrives
+      prefetch(f);
+#endif
+      // slot free = the MMAs of stage wg = g - NS are complete = phase wg / NXS of that stage's release barrier.  The phase
+      // after it needs this very stage to be consumed first (NXS > NS), so the waiter never sees the barrier two phases on.
+      if (wg >= 0) mbar_wait(x_empty_bar(wg % NXS), uint32_t(wg / NXS) & 1u);
       if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 2000000 + trc_it);
       tc_fence_after();
       const uint32_t a_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(C::A_COL0 + as * 64);
@@ -428,7 +490,8 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 3000000 + trc_it);
       ++trc_it;
       as += 2;
-      if (as >= NS) { as -= NS; aph ^= 1; }
+      if (as >= NS) as -= NS;
+      wg += 2;
       fs += 2;
       if (fs >= NXS) fs -= NXS;
     };
@@ -437,7 +500,9 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int u = 0; u < TS_DIST; ++u) {
         if (it + u < mine) {
           process(ring[u]);
+#ifdef TS_LATE_PREFETCH
           prefetch(ring[u]);
+#endif
         }
       }
     }

@@ -36,7 +36,13 @@ def main():
         rows = list(csv.reader(io.StringIO(src)))
         hdr = rows[1]
         ix = {h: i for i, h in enumerate(hdr)}
-        data = [r for r in rows[2:] if len(r) == len(hdr)]
+        data = [r for r in rows[2:] if len(r) == len(hdr) and (r[ix["# Samples"]] or "0").isdigit()]   # several launches repeat the header
+        uniq, seen = [], set()
+        for r in data:          # the page lists an instruction once per launch of the report: keep the first
+            if tuple(r) not in seen:
+                seen.add(tuple(r))
+                uniq.append(r)
+        data = uniq
         tot = sum(int(r[ix["# Samples"]] or 0) for r in data) or 1
         print("\n## top sampled SASS instructions (share of warp-stall samples, dominant stall reasons)")
         stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]

@@ -1,5 +1,6 @@
-"""Aggregate gpurun_out/launches_step.csv (one bench step under ncu) by layer shape: python tools/step_by_shape.py [csv]"""
-import collections, csv, importlib, os, sys
+"""Aggregate gpurun_out/launches_step.csv (one bench step under ncu) by layer shape:
+    python tools/step_by_shape.py [csv] [step_traffic.json]      (the JSON is what bench.py's roofline.traffic reads)"""
+import collections, csv, importlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sh = importlib.import_module("quantization---diffusion-models_b200.shapes")
@@ -20,3 +21,19 @@ for (m, n, k), a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     g = sh.group_for(k); fl = 2 * m * n * k; by = sh.gemm_bytes_w4a16(m, n, k, g)
     ideal = max(fl / 1410.2e12, by / 6455.9e9) * 1e6
     print(f"{a[1] / 1e3:8.1f} us {a[0]:3d} x ({m:6d},{n:5d},{k:5d}) avg {a[1] / a[0] / 1e3:6.1f} us  roofline {ideal:6.1f} us  {fl / (a[1] / a[0] * 1e-9) / 1e12:7.1f} TFLOP/s")
+
+if len(sys.argv) > 2:
+    body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    def col(metric):
+        return [float(r[ix["Metric Value"]]) for r in body if r[ix["Metric Name"]] == metric][-184:]
+    rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+    unit = {r[ix["Metric Name"]]: r[ix["Metric Unit"]] for r in body}
+    mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd_b, wr_b = sum(rd) * mul[unit["dram__bytes_read.sum"]], sum(wr) * mul[unit["dram__bytes_write.sum"]]
+    names = [r[ix["Kernel Name"]] for r in body if r[ix["Metric Name"]] == "gpu__time_duration.sum"][-184:]
+    alg = sum(c * sh.gemm_bytes_w4a16(m, n, k, sh.group_for(k)) for _, m, n, k, c in sh.sd15_unet_linears())
+    json.dump({"source": os.path.basename(path) + " (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+                         "--clock-control none, one eager bench step, 184 launches)",
+               "kernels": dict(collections.Counter(n.split("(")[0] for n in names)),
+               "dram_bytes_read_per_step": rd_b, "dram_bytes_write_per_step": wr_b, "dram_bytes_per_step": rd_b + wr_b,
+               "algorithmic_bytes_per_step": float(alg), "sum_launch_durations_us": sum(d) / 1e3}, open(sys.argv[2], "w"), indent=1)
