@@ -1532,13 +1532,12 @@ int launch_bstat(const Maps& m, const GemmParams& p, int pairs, cudaStream_t st)
 // Bring-up / A-B switches.  The environment is read ONCE (first GEMM call of the process), never in the per-call path.
 struct W4Opts {
   bool no_smallm, no_skinny, no_tma, no_bstat, no_sk, no_rp;
-  int ts_waves, ts_fit;   // A/B knobs of the TS dispatch rule (QDM_W4_TS_WAVES, QDM_W4_TS_FIT), read once
+  int ts_waves;           // A/B knob of the TS dispatch rule (QDM_W4_TS_WAVES: largest tile count in waves), read once
   W4Opts()
       : no_smallm(getenv("QDM_W4_NO_SMALLM") != nullptr), no_skinny(getenv("QDM_W4_NO_SKINNY") != nullptr),
         no_tma(getenv("QDM_W4_NO_TMA") != nullptr), no_bstat(getenv("QDM_W4_NO_BSTAT") != nullptr),
         no_sk(getenv("QDM_W4_NO_SK") != nullptr), no_rp(getenv("QDM_W4_NO_RP") != nullptr),
-        ts_waves(getenv("QDM_W4_TS_WAVES") ? atoi(getenv("QDM_W4_TS_WAVES")) : 6),
-        ts_fit(getenv("QDM_W4_TS_FIT") ? atoi(getenv("QDM_W4_TS_FIT")) : 11) {}
+        ts_waves(getenv("QDM_W4_TS_WAVES") ? atoi(getenv("QDM_W4_TS_WAVES")) : 1000000) {}
 };
 const W4Opts& w4_opts() {
   static const W4Opts o;
@@ -1822,12 +1821,13 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
     note_variant(QDM_GEMM_SMALLM, 0);
     return qdm_gemm_w4a16_smallm(x, qweight, qzeros, scales, bias, y, dtype == QDM_BF16, M, N, K, group, (cudaStream_t)stream);
   }
-  // Weights as the TMEM A operand (qdm_gemm_w4ts.cu).  Measured against the kernels below (profiles/README.md, round 2):
-  // it wins by 10-20 % wherever the problem is a few waves of tiles -- 8192 x 1280 x 1280: 29.5 vs 34.8 us, 4096 x 2432 x 2432:
-  // 46.6 vs 56.1, 4096 x 1280 x 1280: 20.5 vs 24.0, the text-token shapes 1232 x 1280 x 768: 8.4 vs 10.4 and 333 x 2432 x 2432:
-  // 17.9 vs 20.7 (any multiple of 32 tokens per tile, a hidden epilogue, no shared-memory round trip of the weights) --
-  // and ties or loses by ~5 % on the many-wave shapes (4096 x 10240 x 1280: 93 vs 88 us), where both sit at the same
-  // ~54 % tensor-pipe utilisation; K <= 384 with many tiles stays on the B-stationary kernel.
+  // Weights as the TMEM A operand (qdm_gemm_w4ts.cu).  Measured against the kernels below over every Linear shape of the
+  // three denoisers (profiles/ts_models_r02.txt): it wins by 10-45 % on 27 of 31 shapes with M > 32 -- 4096 x 10240 x 1280:
+  // 79.4 vs 89.2 us (cuBLAS f16 79.4), 4096 x 2432 x 2432: 41.5 vs 56.3, 8192 x 1280 x 1280: 26.1 vs 33.7, the text-token
+  // shapes 333 x 2432 x 9728: 44.6 vs 63.9 and 1232 x 1280 x 768: 9.0 vs 11.3 (any multiple of 32 tokens per tile, a hidden
+  // epilogue, no shared-memory round trip of the weights, one barrier test + one commit per K = 128 on the issuing thread).
+  // It loses where K <= 384 with many tiles (the B-stationary kernel dequantises each weight once per CTA, not once per
+  // tile: 65536 x 320 x 320 25.2 vs 31.8) and where N = 320 leaves most of a 256-channel block empty.
   if (blob_ts && !conv && K >= 128 && M > 32 && (g_force_ctas == 128 || (g_force_ctas == 0 && !g_no_rp && !opt.no_rp))) {
     bool take = g_force_ctas == 128;
     const int t = choose_ts_tile(M, N, K, nullptr);
@@ -1839,9 +1839,10 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
         const int64_t m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + tn - 1) / tn, max_pairs = QDM_NUM_SMS / 2;
         bstat = n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs;
       }
-      // 256-channel blocks: N = 640 (2.5 blocks) or 320 would idle a fifth or more of the MMA rows and dequant warps
-      const bool fits_n = ((N + 255) / 256) * 256 * 10 <= int64_t(N) * opt.ts_fit;
-      take = !bstat && fits_n && K >= 256 && tiles <= int64_t(opt.ts_waves) * (QDM_NUM_SMS / 2);
+      // 256-channel blocks: N = 320 idles 3/8 of the MMA rows and dequant warps of its second block; with many token tiles
+      // (M >= 16384) the AWQ-tensor kernel's 160-wide tiles win there (65536 x 320 x 1280: 68.8 vs 76.1 us); N = 640 ties
+      const bool wasteful = ((N + 255) / 256) * 256 * 4 > int64_t(N) * 5 && M >= 16384;
+      take = !bstat && !wasteful && tiles <= int64_t(opt.ts_waves) * (QDM_NUM_SMS / 2);
     }
     if (take) {
       note_variant(QDM_GEMM_TS, t);

@@ -19,9 +19,22 @@ namespace qdmg {
       ++trc_n;                                                           \
     }                                                                    \
   } while (0)
+// wall-clock companion (ns): two TRCG events around a region give the SM clock the region actually ran at
+#define TRCG(ptr, region, tag)                                           \
+  do {                                                                   \
+    if ((ptr) && blockIdx.x < 2 && trc_n < 1000) {                       \
+      long long* t_ = (ptr) + ((region) + 8 * blockIdx.x) * 2048 + 2 * trc_n; \
+      unsigned long long g_;                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_));             \
+      t_[0] = (tag);                                                     \
+      t_[1] = (long long)g_;                                             \
+      ++trc_n;                                                           \
+    }                                                                    \
+  } while (0)
 #else
 #define TRC_DECL
 #define TRC(ptr, region, tag)
+#define TRCG(ptr, region, tag)
 #endif
 
 enum GemmKind { G_F16 = 0, G_F16_KN = 1, G_W4 = 2, G_I8 = 3 };

@@ -62,10 +62,10 @@ struct CfgTS {
 #ifndef TS_NXS128
 #define TS_NXS128 8
 #endif
-  static constexpr int NXS = DW == 128 ? TS_NXS128 : TS_NXS192;
+  static constexpr int NXS = DW <= 160 ? TS_NXS128 : TS_NXS192;
   static constexpr int EPI_BYTES = 2 * 32 * 256;             // two staging tiles [32 tokens][128 channels] x 2 B
   static constexpr int SMEM_BYTES = NXS * X_STAGE_BYTES + EPI_BYTES + 1024 + TS_BAR_BYTES;
-  static_assert(NS >= 2 && NS % 2 == 0 && NXS % 2 == 0, "ring slots must keep their dequant set");
+  static_assert(NS >= 2 && NXS > NS, "the dequant sets wait on the release barrier of the stage NS back: it must still be the x ring's current phase");
   static_assert(8 * (2 * NXS + NS + 4) + 8 <= TS_BAR_BYTES, "barrier area");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
@@ -266,8 +266,13 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           TRC(p.trace, 0, 2000000 + trc_it);
           ++trc_it;
           const int nk = min(TS_KB, num_kb - st * TS_KB);
+#ifdef TS_NO_X   // timing experiment only (wrong results): no activation loads at all
+          if (rank == 0) mbar_arrive(full_bar(stage));
+          for (int j = 0; j < 0; ++j)
+#else
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * uint32_t(nk) * kb_bytes);   // rows past M are zero-filled and counted
           for (int j = 0; j < nk; ++j)
+#endif
             tma_load_2d_pair(smem_base + stage * C::X_STAGE_BYTES + j * C::KB_BYTES, &map_x, leader_full0 + 8u * stage,
                              (st * TS_KB + j) * 64, m0);
           if (++stage == NXS) { stage = 0; phase ^= 1; }
@@ -296,6 +301,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (!ready) mbar_spin(full_bar(stage), phase);
 #endif
           TRC(p.trace, 1, (ready ? 2000000 : 9000000) + trc_it);    // 9 = the stage was not yet complete at the peek: waited
+          if ((trc_it & 15) == 0) TRCG(p.trace, 1, 10000000 + trc_it);
           ++trc_it;
           tc_fence_after();
           int nstage = stage + 1;
@@ -390,7 +396,11 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     auto prefetch = [&](Pf (&f)[TS_KB]) {
 #pragma unroll
       for (int j = 0; j < TS_KB; ++j) { f[j].w0 = make_uint4(0, 0, 0, 0); f[j].w1 = f[j].w0; f[j].sz = 0; }
+#ifdef TS_NO_W    // timing experiment only (wrong results): no packed-weight loads
+      if (false) {
+#else
       if (pf_g < total) {
+#endif
         const int tile = pair + pf_tl * num_pairs;
         const int n = TS_NBLK(tile) * 256 + int(rank) * 128 + q * 32 + lane;
         if (n < p.N) {
@@ -607,5 +617,6 @@ int qdm_w4ts_gemm(const void* x, const void* blob, const void* bias, void* y, in
   p.words = static_cast<const uint32_t*>(blob);
   p.sz = p.words + (K / 64) * N * 8;
   if (tile_t <= 128) return is_bf16 ? launch_ts<128, true>(mx, my, p, st) : launch_ts<128, false>(mx, my, p, st);
+  if (tile_t <= 160) return is_bf16 ? launch_ts<160, true>(mx, my, p, st) : launch_ts<160, false>(mx, my, p, st);
   return is_bf16 ? launch_ts<192, true>(mx, my, p, st) : launch_ts<192, false>(mx, my, p, st);
 }

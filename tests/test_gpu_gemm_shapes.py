@@ -81,10 +81,12 @@ def test_w4a16_baseline_shape(qdm, model, M, N, K, dt):
     err = rel_err_gpu(y, ref)
     assert err <= TOL, (variant, tile, err)
     assert torch.isfinite(y).all()
-    # the few-wave layers must take the tensor-memory-A kernel, the many-wave / small-K ones the others
-    if (M, N, K) in ((4096, 1280, 1280), (8192, 1280, 1280), (4096, 2432, 2432), (1232, 1280, 768), (333, 2432, 2432)):
+    # the module's dispatch: the tensor-memory-A kernel everywhere except small K with many tiles (B-stationary kernel) and
+    # N = 320 with many token tiles (AWQ-tensor kernel)
+    if (M, N, K) in ((4096, 1280, 1280), (8192, 1280, 1280), (4096, 2432, 2432), (1232, 1280, 768), (333, 2432, 2432), (4096, 10240, 1280),
+                     (4096, 9728, 2432), (16384, 5120, 640)):
         assert variant == "ts", (variant, tile)
-    if (M, N, K) in ((4096, 10240, 1280), (65536, 320, 320), (65536, 2560, 320)):
+    if (M, N, K) in ((65536, 320, 320), (65536, 2560, 320), (65536, 320, 1280)):
         assert variant in ("pair", "bstat"), (variant, tile)
 
 

@@ -24,7 +24,15 @@ def main():
         tiles = [0, 192, 160, 128, 64, 32]
     elif what == "quick":
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (4096, 9728, 2432), (1232, 1280, 768), (16384, 640, 640)]
-        tiles = [0, 192, 128]
+        tiles = [0, 192, 160, 128]
+    elif what == "models":   # every distinct Linear shape (M > 32) of the three denoisers
+        seen = []
+        for layers in (S.sd15_unet_linears(batch=8, cfg=True), S.sdxl_unet_linears(batch=4, cfg=True), S.sd35_mmdit_linears(batch=1)):
+            for _, m_, n_, k_, _ in layers:
+                if m_ > 32 and (m_, n_, k_) not in seen:
+                    seen.append((m_, n_, k_))
+        cases = seen
+        tiles = [0, 192, 160, 128, 96, 64]
     else:
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (16384, 640, 640), (4096, 1280, 5120), (8192, 1280, 1280),
                  (4096, 2432, 2432), (4096, 9728, 2432), (1232, 1280, 768), (333, 2432, 2432), (65536, 2560, 320), (65536, 320, 320)]
