@@ -491,25 +491,25 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      uint32_t ready = 0;   // did the peek inside the previous k-block already see this stage full?
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          if (!ready) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per 128-byte row
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024)
-                                     : make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma<KIND>(tmem_c, da, db, idesc, (kb | k) != 0);
-          }
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
+          const uint64_t da = make_smem_desc(a_addr, 16, 1024);   // 4 x 32 bytes of K per 128-byte row inside the block
+          const uint64_t db = B_MN ? make_smem_desc(b_addr, 64 * ROW_BYTES, 1024) : make_smem_desc(b_addr, 16, 1024);
+          ready = issue_kblock_ss<KIND, false>(tmem_c, da, db, B_MN ? 128u : 2u, idesc, uint32_t(kb != 0), full_bar(nstage), nphase);
           umma_commit(empty_bar(stage));
           if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          stage = nstage; phase = nphase;
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -706,6 +706,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs; each loads its own halves)
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       TRC_DECL;
@@ -755,30 +756,29 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t acc_phase = 0;
       TRC_DECL;
       int trc_it = 0;
+      uint32_t ready = 0;   // did the peek inside the previous k-block already see this stage full?
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
         TRC(p.trace, 1, 1000000 + trc_it);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-#ifndef QDM_EXP_NOFULLWAIT   // timing experiment only (wrong results): the tensor pipe alone, operands never waited for
-          mbar_wait(full_bar(stage), phase);
-#endif
-          TRC(p.trace, 1, 2000000 + trc_it);
+          if (!ready) mbar_wait(full_bar(stage), phase);
+          TRC(p.trace, 1, (ready ? 2000000 : 9000000) + trc_it);
           ++trc_it;
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024)
-                                     : make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_pair<KIND>(tmem_c, da, db, idesc, (kb | k) != 0);
-          }
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
+          const uint64_t da = make_smem_desc(a_addr, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(b_addr, 64 * ROW_BYTES, 1024) : make_smem_desc(b_addr, 16, 1024);
+          // the next stage's barrier is tested inside the block; its result is read after the fourth MMA
+          ready = issue_kblock_ss<KIND, true>(tmem_c, da, db, B_MN ? 128u : 2u, idesc, uint32_t(kb != 0), full_bar(nstage), nphase);
           umma_commit_pair(empty_bar(stage), all_mask);
           if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc), pair_mask);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          stage = nstage; phase = nphase;
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -816,6 +816,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================== epilogue (each CTA drains its own 128 rows)
+    pdl_wait();
     const int ew = warp - 4;
     const uint32_t stg = epi_base + ew * EPI_STG_BYTES;
     float* vec_sm = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4) * (KIND == G_I8 ? 2 : 1);
@@ -967,13 +968,15 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
-  pdl_wait();
+  // only the roles that touch memory of EARLIER kernels wait (TMA producer: activations; epilogue: output buffer, W8A8 row
+  // scales, stream-K partials); packed weights / scales / zeros are constants and are fetched while the previous kernel drains
   const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
   const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
 
   if (warp == 0) {
     // ===================================================== TMA producer: A
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for_each_seg([&](int tile, int ka, int ke) {
@@ -991,25 +994,24 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 1, 2 * BLOCK_M, tile_n);
       int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t phase = 0, acc_phase = 0, ready = 0;
       for_each_seg([&](int, int ka, int ke) {
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + acc * BLOCK_N;
         for (int kb = ka; kb < ke; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          if (!ready) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024);
-            umma_pair<G_W4>(tmem_c, da, db, idesc, (kb != ka) || (k != 0));
-          }
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
+          ready = issue_kblock_ss<G_W4, true>(tmem_c, make_smem_desc(a_addr, 16, 1024), make_smem_desc(b_addr, 64 * ROW_BYTES, 1024), 128u,
+                                              idesc, uint32_t(kb != ka), full_bar(nstage), nphase);
           umma_commit_pair(empty_bar(stage), 3);
           if (kb == ke - 1) umma_commit_pair(tmem_full_bar(acc), 3);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          stage = nstage; phase = nphase;
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       });
@@ -1038,6 +1040,7 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================================================== epilogue
+    pdl_wait();
     const int ew = warp - 4;
     const uint32_t stg = epi_base + ew * EPI_STG_BYTES;
     float* vec_sm = reinterpret_cast<float*>(smem_gen + STAGES * C::STAGE_BYTES + 4 * EPI_STG_BYTES) + ew * (EPI_VEC_BYTES / 4);
@@ -1127,8 +1130,14 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // k-blocks per tile the epilogue is as long as the main loop.
 struct CfgBS {
   static constexpr int NLOC = 128;
-  static constexpr int A_STAGES = 5;
-  static constexpr int BST_KB = 6;                        // resident k-blocks: K <= 384
+#ifndef QDM_BS_ASTAGES
+#define QDM_BS_ASTAGES 5
+#endif
+#ifndef QDM_BS_KB
+#define QDM_BS_KB 6
+#endif
+  static constexpr int A_STAGES = QDM_BS_ASTAGES;
+  static constexpr int BST_KB = QDM_BS_KB;                // resident k-blocks: K <= 384
   static constexpr int B_KB_BYTES = NLOC * ROW_BYTES;     // 16 KB per k-block
   static constexpr int RAW_N = 2;                         // raw ring, used once; afterwards staging of epilogue set 1
   static constexpr int RAW_BYTES = RAW_N * RawCfg<NLOC>::BYTES;
@@ -1201,13 +1210,15 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
-  pdl_wait();
+  // only the roles that touch memory of EARLIER kernels wait (TMA producer: activations; epilogue: output buffer, W8A8 row
+  // scales, stream-K partials); packed weights / scales / zeros are constants and are fetched while the previous kernel drains
   const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
   const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
   const uint32_t leader_bst_full0 = mapa_shared(bst_full_bar(0), 0);
 
   // one epilogue warp set: TMEM lane quarter = warp % 4, chunks `set`, set + 2, ...
   auto epilogue_role = [&](int set, int ew, uint32_t stg, float* vec_sm) {
+    pdl_wait();
     if (lane == 0) { tma_prefetch_desc(&map_y); tma_prefetch_desc(&map_y16); }
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -1228,6 +1239,7 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   if (warp == 0) {
     // ===================================================== TMA producer: A only
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -1245,7 +1257,7 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 1, 2 * BLOCK_M, tile_n);
       int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      uint32_t phase = 0, acc_phase = 0, ready = 0;
       bool first = true;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
@@ -1253,19 +1265,18 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const uint32_t tmem_c = tmem_base + acc * 256;
         for (int kb = 0; kb < num_kb; ++kb) {
           if (first) mbar_wait(bst_full_bar(kb), 0);   // the resident B part of this k-block has been written (both CTAs)
-          mbar_wait(full_bar(stage), phase);
+          if (!ready) mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * A_STAGE_BYTES;
           const uint32_t b_addr = bst_base + kb * C::B_KB_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(b_addr + k * 2048, 64 * ROW_BYTES, 1024);
-            umma_pair<G_W4>(tmem_c, da, db, idesc, (kb | k) != 0);
-          }
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == SA) { nstage = 0; nphase ^= 1; }
+          ready = issue_kblock_ss<G_W4, true>(tmem_c, make_smem_desc(a_addr, 16, 1024), make_smem_desc(b_addr, 64 * ROW_BYTES, 1024), 128u,
+                                              idesc, uint32_t(kb != 0), full_bar(nstage), nphase);
           umma_commit_pair(empty_bar(stage), 3);
           if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc), 3);
-          if (++stage == SA) { stage = 0; phase ^= 1; }
+          stage = nstage; phase = nphase;
         }
         first = false;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

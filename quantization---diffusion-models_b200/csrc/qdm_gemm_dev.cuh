@@ -234,6 +234,46 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_c, uint64_t da, uint64_t
         : "memory");
   }
 }
+// One k-block (4 MMAs over a 128-byte operand row) for the issuing thread, shared-memory operands (SS form).  Why one asm
+// block: measured on the issuing thread (QDM_TRACE timeline, profiles/README.md round 2) a barrier test costs ~290 cycles
+// when its predicate is read at once, an MMA ~80 cycles when its two descriptors are rebuilt from addresses, a commit ~170
+// -- ~870 cycles of serial issue per k-block against 512 cycles of tensor-pipe work at N = 256, so the thread, not the
+// tensor pipe, set the pace of every kernel.  Here the NEXT stage's barrier is tested first and its predicate read after the
+// fourth MMA (the latency overlaps the MMAs), and each descriptor is the previous one plus a constant in the low word
+// (a: 32 bytes >> 4; b: 32 bytes >> 4 K-major, 2048 bytes >> 4 MN-major).  Returns 1 if the next stage was already full.
+template <int KIND, bool PAIR>
+__device__ __forceinline__ uint32_t issue_kblock_ss(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t b_step, uint32_t idesc,
+                                                   uint32_t accum, uint32_t next_bar, uint32_t next_parity) {
+  uint32_t done;
+#define QDM_KBLOCK_ASM(MMA)                                                                                          \
+  asm volatile(                                                                                                      \
+      "{\n\t.reg .pred pa, pt, pd;\n\t.reg .b64 xa, xb;\n\t.reg .b32 la, lb;\n\t"                                  \
+      "mbarrier.test_wait.parity.shared::cta.b64 pd, [%9], %10;\n\t"                                                 \
+      "setp.ne.b32 pa, %8, 0;\n\t"                                                                                   \
+      "setp.eq.b32 pt, %8, %8;\n\t"                                                                                  \
+      "mov.b64 xa, {%2, %3};\n\tmov.b64 xb, {%4, %5};\n\t"                                                          \
+      MMA " [%1], xa, xb, %7, pa;\n\t"                                                                               \
+      "add.u32 la, %2, 2;\n\tadd.u32 lb, %4, %6;\n\tmov.b64 xa, {la, %3};\n\tmov.b64 xb, {lb, %5};\n\t"            \
+      MMA " [%1], xa, xb, %7, pt;\n\t"                                                                               \
+      "add.u32 la, la, 2;\n\tadd.u32 lb, lb, %6;\n\tmov.b64 xa, {la, %3};\n\tmov.b64 xb, {lb, %5};\n\t"            \
+      MMA " [%1], xa, xb, %7, pt;\n\t"                                                                               \
+      "add.u32 la, la, 2;\n\tadd.u32 lb, lb, %6;\n\tmov.b64 xa, {la, %3};\n\tmov.b64 xb, {lb, %5};\n\t"            \
+      MMA " [%1], xa, xb, %7, pt;\n\t"                                                                               \
+      "selp.u32 %0, 1, 0, pd;\n\t}"                                                                                  \
+      : "=r"(done)                                                                                                   \
+      : "r"(tmem_c), "r"(uint32_t(da)), "r"(uint32_t(da >> 32)), "r"(uint32_t(db)), "r"(uint32_t(db >> 32)), "r"(b_step),  \
+        "r"(idesc), "r"(accum), "r"(next_bar), "r"(next_parity)                                                      \
+      : "memory")
+  if (PAIR) {
+    if (KIND == G_I8) QDM_KBLOCK_ASM("tcgen05.mma.cta_group::2.kind::i8");
+    else QDM_KBLOCK_ASM("tcgen05.mma.cta_group::2.kind::f16");
+  } else {
+    if (KIND == G_I8) QDM_KBLOCK_ASM("tcgen05.mma.cta_group::1.kind::i8");
+    else QDM_KBLOCK_ASM("tcgen05.mma.cta_group::1.kind::f16");
+  }
+#undef QDM_KBLOCK_ASM
+  return done;
+}
 // commit to the same barrier offset in the CTAs of `mask` (both CTAs of the pair; all four CTAs of a quad cluster)
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -454,7 +494,11 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
     if (hh == halves_in(c) - 1) {   // chunk complete
       fence_proxy_async();
       __syncwarp();
+#ifdef QDM_EXP_NOSTORE   // timing experiment only (no output): what the epilogue's TMA stores cost
+      if (false) {
+#else
       if (lane == 0) {
+#endif
         if (whole) {
           tma_store_2d(map_y, stg, nc, row0);
         } else {

@@ -70,8 +70,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
 
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: nothing global is read before this
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nl = lane >> 2, t = lane & 3;
@@ -112,6 +111,9 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
     }
   }
 
+  // the loads above are constants (packed words, zeros, scales): they fly while the previous kernel drains; x and y belong
+  // to earlier kernels and are not touched before this wait
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // stage this CTA's k slice of x (rows >= M are zeros)
   {
     const int vec_per_row = k_slice >> 3;

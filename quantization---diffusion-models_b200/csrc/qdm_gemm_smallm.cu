@@ -53,8 +53,7 @@ w4a16_smallm_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   extern __shared__ uint4 xs_raw[];                  // x staged once per CTA: [16 MT][K + 8] (pitch: conflict-free fragments)
   uint16_t* xs = reinterpret_cast<uint16_t*>(xs_raw);
   __shared__ float red[SM_WARPS][MT][4][32];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: nothing global is read before this
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wc = blockIdx.x;                        // packed word column: output columns 8 wc .. 8 wc + 7
   const int words_per_row = N >> 3;
@@ -83,7 +82,8 @@ w4a16_smallm_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
       sc[u] = on ? __ldg(scales + int64_t(g) * N + 8 * wc + nl) : uint16_t(0);
     }
   };
-  load_chunk(s_begin);
+  load_chunk(s_begin);   // constants (packed words, zeros, scales): fetched while the previous kernel drains
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // x and y belong to earlier kernels: nothing of theirs is touched before this
   {
     const int vec_per_row = K >> 3;
     for (int idx = threadIdx.x; idx < 16 * MT * vec_per_row; idx += SM_WARPS * 32) {

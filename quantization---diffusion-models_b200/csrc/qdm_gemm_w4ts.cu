@@ -246,14 +246,18 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: the next kernel may start its set-up now.  Only the roles that touch memory an EARLIER
+  // kernel produces or still reads wait for it -- the TMA producer (activations) and the epilogue (the output buffer may be
+  // an earlier kernel's input).  The dequant warps read constants (packed weights, scales, zeros), so their first loads --
+  // a cold HBM round trip -- overlap the previous kernel's tail instead of following it.
   pdl_launch_dependents();
-  pdl_wait();
   const uint32_t leader_full0 = mapa_shared(full_bar(0), 0);
   const uint32_t leader_tmem_empty0 = mapa_shared(tmem_empty_bar(0), 0);
 
   if (warp == 0) {
     // ===================================================== TMA producer: x, this CTA's half of the tile's tokens
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       TRC_DECL;
@@ -326,6 +330,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       }
     }
   } else if (warp >= 4 && warp < 8) {
+    pdl_wait();
     // ===================================================== epilogue: lanes = output channels, columns = tokens
     // The four warps (one per TMEM lane quarter = 32 channels each) fill ONE staging tile [32 tokens][128 channels]
     // (256-byte rows: a quarter of the TMA rows that per-warp 64-byte boxes need) and warp 4 stores it with one TMA
