@@ -569,8 +569,9 @@ int launch_ts(const CUtensorMap& mx, const CUtensorMap& my, const TsParams& p, c
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("QDM_NO_PDL") != nullptr;   // A/B switch, read once
   cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   QDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, my, p));
   QDM_LAUNCH_CHECK();
   return QDM_OK;
