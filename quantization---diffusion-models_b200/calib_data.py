@@ -112,24 +112,42 @@ class Input_Capture_Hook:
     Linear however long the calibration runs.  Chunks carry a global call id (`next_id`, set by the capture loop per
     calibration batch) so that captures made data parallel can be merged in single-process order (dist.exchange_captures)."""
 
-    def __init__(self, max_tokens=None, per_call=None):
+    def __init__(self, max_tokens=None, per_call=None, arena=None):
         self.hook_handle = None
         self.chunks = []          # [(call_id, X[rows, K])]
         self.max_tokens = max_tokens
         self.per_call = per_call
         self.next_id = 0
+        # optional pre-allocated [rows, K] buffer (a slice of ONE arena per capture pass, models.capture_block_inputs): the
+        # kept rows are copied into consecutive slices of it instead of a fresh allocation per call -- thousands of small
+        # allocations interleaved with the forward's temporaries cost ~2 s of cudaMalloc on the 38-block SD3.5-L pass
+        self.arena = arena
+        self.used = 0
 
     def __call__(self, module, module_in, module_out):
         x = module_in[0].detach()
         x = x.reshape(-1, x.shape[-1])
         if self.per_call is not None and x.shape[0] > self.per_call:
             x = x[:: x.shape[0] // self.per_call][: self.per_call]
-        self.chunks.append((self.next_id, x.clone()))
+        if self.arena is not None and self.used + x.shape[0] <= self.arena.shape[0] and x.dtype == self.arena.dtype:
+            dst = self.arena[self.used:self.used + x.shape[0]]
+            dst.copy_(x)
+            self.used += x.shape[0]
+            self.chunks.append((self.next_id, dst))
+        else:
+            self.chunks.append((self.next_id, x.clone()))
         self.next_id += 1
 
     @staticmethod
     def merge(chunks, max_tokens=None):
-        x = torch.cat([c for _, c in sorted(chunks, key=lambda t: t[0])], dim=0)
+        cs = [c for _, c in sorted(chunks, key=lambda t: t[0])]
+        adjacent = all(a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype and a.shape[1] == b.shape[1] and
+                       a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr() and
+                       a.storage_offset() + a.numel() == b.storage_offset() for a, b in zip(cs, cs[1:]))
+        if len(cs) > 1 and adjacent:      # consecutive slices of one arena: the concatenation already exists
+            x = cs[0].new_empty(0).set_(cs[0].untyped_storage(), cs[0].storage_offset(), (sum(c.shape[0] for c in cs), cs[0].shape[1]))
+        else:
+            x = torch.cat(cs, dim=0) if len(cs) > 1 else cs[0]
         if max_tokens is not None and x.shape[0] > max_tokens:
             x = x[:: x.shape[0] // max_tokens][:max_tokens].contiguous()
         return x

@@ -157,9 +157,8 @@ def exchange_captures(caps, wanted_by, rank, world, device):
     Returns the same structure for the blocks `rank` wants, holding the chunks of every rank sorted by call_id, so the
     concatenation is the one a single process would have built: search results do not depend on the world size.
     One metadata all_gather_object + one all_gather per block (NCCL; gloo in the CPU tests)."""
-    mine = {b: {ln: list(ch) for ln, ch in lins.items()} for b, lins in caps.items() if rank in wanted_by.get(b, ())}
     if world == 1 or not (dist.is_available() and dist.is_initialized()):
-        return mine
+        return {b: {ln: sorted(ch, key=lambda t: t[0]) for ln, ch in lins.items()} for b, lins in caps.items() if rank in wanted_by.get(b, ())}
     meta = {b: {ln: [(cid, tuple(x.shape), str(x.dtype)) for cid, x in ch] for ln, ch in lins.items()} for b, lins in caps.items()}
     metas = [None] * world
     dist.all_gather_object(metas, meta)
@@ -167,41 +166,56 @@ def exchange_captures(caps, wanted_by, rank, world, device):
     comm_dev = device if nccl else torch.device("cpu")
     # One all_gather per block over the communicator's collective channels (NVLS / ring over NVSwitch), not point-to-point
     # sends: the first send/recv between two ranks makes NCCL open a new peer connection -- measured 1.7 s at world 4 and
-    # ~8 s at world 8 for 56 pairs, against ~30 ms to move the ~10 GB of SD3.5-L captures through all_gather -- and in
-    # ratio-split mode every rank wants every block anyway.  A block's gather buffer is dropped at once by non-owners.
-    for b in sorted(caps):   # identical module trees -> identical keys and order on every rank
-        sizes = [sum(sh[0] * sh[1] for ch in metas[r][b].values() for _, sh, _ in ch) for r in range(world)]
-        n_max = max(sizes)
+    # ~8 s at world 8 for 56 pairs, against ~40 ms to move the ~10 GB of SD3.5-L captures through all_gather -- and in
+    # ratio-split mode every rank wants every block anyway.  Memory: ONE send and ONE receive buffer (largest block) reused
+    # for every block, ONE output arena for everything this rank keeps; chunks are copied into the arena in call order,
+    # so the later merge is a view (fresh per-Linear allocations cost ~1 s of cudaMalloc per 14 GB).
+    order = sorted(caps)   # identical module trees -> identical keys and order on every rank
+    sizes = {b: [sum(sh[0] * sh[1] for ch in metas[r][b].values() for _, sh, _ in ch) for r in range(world)] for b in order}
+    dts = {d for r in range(world) for b in order for ch in metas[r][b].values() for _, _, d in ch}
+    if not dts:
+        return {b: {} for b in order if rank in wanted_by.get(b, ())}
+    assert len(dts) == 1, f"captures have mixed dtypes {dts}"
+    dt = getattr(torch, dts.pop().split(".")[-1])
+    n_cap = max(max(v) for v in sizes.values())
+    send = torch.zeros(n_cap, dtype=dt, device=comm_dev)
+    recv = torch.empty(world * n_cap, dtype=dt, device=comm_dev) if nccl else None
+    arena = torch.empty(sum(sum(sizes[b]) for b in order if rank in wanted_by.get(b, ())), dtype=dt, device=device)
+    pos = 0
+    mine = {}
+    for b in order:
+        n_max = max(sizes[b])
         if n_max == 0:
             continue
-        dts = {d for r in range(world) for ch in metas[r][b].values() for _, _, d in ch}
-        assert len(dts) == 1, f"captures of block {b} have mixed dtypes {dts}"
-        dt = getattr(torch, dts.pop().split(".")[-1])
-        send = torch.zeros(n_max, dtype=dt, device=comm_dev)
         parts = [x.reshape(-1) for ch in caps[b].values() for _, x in ch]
         if parts:
-            send[: sizes[rank]] = torch.cat(parts).to(comm_dev)
+            flat = torch.cat(parts)
+            send[: flat.numel()].copy_(flat)
         if nccl:
-            recv = torch.empty(world * n_max, dtype=dt, device=comm_dev)
-            dist.all_gather_into_tensor(recv, send)
+            dist.all_gather_into_tensor(recv[: world * n_max], send[:n_max])
             bufs = [recv[r * n_max:(r + 1) * n_max] for r in range(world)]
         else:
             bufs = [torch.empty(n_max, dtype=dt) for _ in range(world)]
-            dist.all_gather(bufs, send)
+            dist.all_gather(bufs, send[:n_max].clone())
         if rank not in wanted_by.get(b, ()):
             continue
+        entries = {}          # linear -> [(call id, peer, offset in the peer's buffer, shape)]
         for peer in range(world):
-            if peer == rank:
-                continue
             off = 0
             for ln, ch in metas[peer][b].items():
                 for cid, shape, _ in ch:
-                    n = shape[0] * shape[1]
-                    mine.setdefault(b, {}).setdefault(ln, []).append((cid, bufs[peer][off:off + n].reshape(shape).to(device)))
-                    off += n
-    for lins in mine.values():
-        for ln in lins:
-            lins[ln].sort(key=lambda t: t[0])
+                    entries.setdefault(ln, []).append((cid, peer, off, shape))
+                    off += shape[0] * shape[1]
+        mine[b] = {}
+        for ln in metas[rank][b] if metas[rank][b] else entries:
+            chunks = []
+            for cid, peer, off, shape in sorted(entries.get(ln, ())):
+                n = shape[0] * shape[1]
+                dst = arena[pos:pos + n].view(shape)
+                dst.copy_(bufs[peer][off:off + n].view(shape))
+                pos += n
+                chunks.append((cid, dst))
+            mine[b][ln] = chunks
     return mine
 
 

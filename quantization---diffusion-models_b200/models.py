@@ -146,20 +146,27 @@ class BaseAWQForDiffusion:
         of `block_names` from all batches in single-process order.  A batch is always run whole by one rank, so every
         forward has the shapes (and cuBLAS kernels) of the single-process run: captured inputs, and with them the
         searched scales and packed codes, are identical for every world size."""
+        import time
         from .dist import exchange_captures
+        t_in = time.perf_counter()
         rank, world = shard if shard is not None else (0, 1)
         blocks = self.get_search_blocks()
         samples = self.calib_samples or self.default_calib_samples()
         per_call = -(-self.calib_max_tokens // max(1, len(samples) * self.calib_steps))   # ceil(max_tokens / total calls)
         hook_blocks = list(wanted_by) if (world > 1 and wanted_by) else list(block_names)
         hooks = {}
-        for bn in hook_blocks:
-            for ln, lin in blocks[bn].named_modules():
-                if isinstance(lin, nn.Linear):
-                    h = Input_Capture_Hook(self.calib_max_tokens, per_call)
-                    h.hook_handle = lin.register_forward_hook(h)
-                    hooks[(bn, ln)] = h
-        import time
+        n_local = sum(1 for bi in range(len(samples)) if bi % world == rank) * self.calib_steps   # forward calls this rank runs
+        lins = [(bn, ln, lin) for bn in hook_blocks for ln, lin in blocks[bn].named_modules() if isinstance(lin, nn.Linear)]
+        # ONE arena for every kept row of this pass (upper bound per_call rows per call and Linear), sliced per hook
+        par = next(self.denoiser().parameters())
+        rows = n_local * per_call
+        arena = torch.empty(sum(rows * lin.in_features for _, _, lin in lins), dtype=par.dtype, device=par.device) if lins else None
+        off = 0
+        for bn, ln, lin in lins:
+            h = Input_Capture_Hook(self.calib_max_tokens, per_call, arena=arena[off:off + rows * lin.in_features].view(rows, lin.in_features))
+            off += rows * lin.in_features
+            h.hook_handle = lin.register_forward_hook(h)
+            hooks[(bn, ln)] = h
         on_gpu = torch.device(self.pipeline.device).type == "cuda"
         sync = torch.cuda.synchronize if on_gpu else (lambda: None)
         t0 = time.perf_counter()
@@ -178,8 +185,12 @@ class BaseAWQForDiffusion:
         if world > 1:
             caps = exchange_captures(caps, wanted_by or {bn: [rank] for bn in block_names}, rank, world, self.pipeline.device)
             sync()
-        self.capture_timings = {"capture_forward_s": t1 - t0, "capture_exchange_s": time.perf_counter() - t1}
-        return {bn: {ln: Input_Capture_Hook.merge(ch, self.calib_max_tokens) for ln, ch in caps[bn].items()} for bn in block_names}
+        t2 = time.perf_counter()
+        out = {bn: {ln: Input_Capture_Hook.merge(ch, self.calib_max_tokens) for ln, ch in caps[bn].items()} for bn in block_names}
+        sync()
+        self.capture_timings = {"capture_hooks_s": t0 - t_in, "capture_forward_s": t1 - t0, "capture_exchange_s": t2 - t1,
+                                "capture_merge_s": time.perf_counter() - t2}
+        return out
 
     def get_layers_for_scaling(self, block, input_feat):
         """Scaling groups of a BasicTransformerBlock: the two groups the reference's SmoothQuant

@@ -115,9 +115,19 @@ class AwqQuantizer:
         UNet / MMDiT blocks) runs first: scales are folded (scale.py:37-84), clips applied (scale.py:25-34),
         and only then every Linear / Conv2d is swapped.  `shard` = (rank, world) restricts the search to this
         rank's blocks; dist.py gathers the results so every rank applies the identical list."""
+        import time
+        on_gpu = next(self.awq_model.denoiser().parameters()).is_cuda
+
+        def now():
+            if on_gpu:
+                torch.cuda.synchronize()
+            return time.perf_counter()
         if self.calibrate:
             results = self.search(shard=shard)
+            t0 = now()
             self.apply_search_results(results)
+            self.timings["apply_s"] = now() - t0
+        t0 = now()
         for key in self.modules:
             for k, module_list in enumerate(self.modules[key]):
                 root = self.awq_model.get_root(key, k)
@@ -133,6 +143,8 @@ class AwqQuantizer:
                         self._apply_quant_real(mod, layers, self.w_bit)
                     else:
                         self._apply_quant_fake_act(mod, layers, self.w_bit, debugStruct=None)
+        if getattr(self, "timings", None) is not None:
+            self.timings["swap_pack_s"] = now() - t0
 
     # ------------------------------------------------------------------ search over blocks (new orchestration)
     @torch.no_grad()
