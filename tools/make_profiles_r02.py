@@ -1,0 +1,79 @@
+"""Regenerate profiles/ROUND2.md from the committed round-2 tables + the hand-written notes below."""
+import json
+import os
+
+R = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
+
+
+def load(name):
+    with open(os.path.join(R, name)) as f:
+        return json.load(f)
+
+
+def rows_of(d):
+    return d["rows"] if isinstance(d, dict) else d
+
+
+out = []
+A = out.append
+A("# profiles/ — round 2 evidence (B200, sm_100a)\n")
+A("Same method as round 1 (`README.md`): CUDA events on the launching stream, GPU-side (CUDA graph of 10 x (256 MB L2 flush, launch)")
+A("minus the flushes alone) for per-shape numbers; the bench line is one CUDA graph of the step's 184 launches. ncu captures:")
+A("`--set full --clock-control none --import-source on`, absolute times cold-cache / serialised (shares and stall reasons only).\n")
+A("## Files (round 2)\n")
+A("| file | what |\n|---|---|")
+for f, w in [
+    ("bench_line_r02_n8.json", "`bench.py --gpus 8` (torchrun, NCCL): the full line incl. W8A8, denoise and the 38-block SD3.5-L calibration sub-records"),
+    ("bench_line_r02_a.json", "the first round-2 line (before the TS kernel), kept for the history below"),
+    ("launches_bench_step_r02.csv, step_by_shape_r02.txt, step_traffic_r02.json", "ncu launch list of one eager bench step (184 launches: duration, DRAM read / write bytes), aggregated by shape; `step_traffic` is what `bench.py` reports as `roofline.traffic` (`tools/step_durations.sh`, `tools/step_by_shape.py`)"),
+    ("w4a16_ts_4096x2432x2432_r02.txt, w4a16_ts_4096x1280x1280_r02.txt, w4a16_ts_1232x1280x768_r02.txt", "ncu summary + top stalled SASS of the tensor-memory-A W4A16 kernel (`qdm_w4ts_kernel`): compute-bound, two-wave and text-token shapes"),
+    ("awq_clip_9728x2432_r02.txt", "ncu summary of the clip-search kernels (`group_gram_kernel`, `awq_clip_kernel`) on the SD3.5-L ff.net.0.proj weight"),
+    ("gemm_layers_r02.json, gemm_layers_sdxl_r02.json, gemm_layers_sd35_r02.json", "`bench.py --layers [--model sdxl|sd35]` through `WQLinear_GEMM.forward` (module dispatch, kernel recorded per shape)"),
+    ("ts_models_r02.txt", "`tools/ts_probe.py models`: every Linear shape with M > 32 of the three denoisers: AWQ-tensor kernels vs cuBLAS f16 vs the TS kernel at 5 token-tile widths"),
+    ("calib_scaling_r02.json", "`bench.py --mode calib --model sd35 --calib-batches 8` at 1 / 2 / 4 / 8 GPUs: seconds per model, phase times (max over ranks), codes checksum"),
+    ("topo_8gpu_box_r02.txt", "`nvidia-smi topo -m` + `lscpu` of the 8-GPU box (one NUMA node, 32 vCPUs: what bounds the end-to-end leg at N = 8)"),
+]:
+    A(f"| `{f}` | {w} |")
+
+n8 = load("bench_line_r02_n8.json")
+A("\n## Bench line history (SD1.5 UNet step, 184 W4A16 Linear calls, 3.73 TFLOP)\n")
+A("| state | ms / step | TFLOP/s | fraction of burst bf16 peak (1697.6) |\n|---|---:|---:|---:|")
+for name, ms in [("round 1 final", 5.198), ("round 2 start (shape-parity work, clip kernel, no GEMM change)", 5.20), ("RP kernel (per-tile repack, 2 sub-tiles) for one-wave shapes", 5.04),
+                 ("TS kernel, first dispatch (few-wave + text-token shapes)", 4.907), ("TS kernel: issuer rewritten (peeks inside one asm block, one commit per stage), TS default", 4.610),
+                 ("role-local PDL waits (weights fetched while the previous kernel drains)", 4.580), (f"8 GPUs, same build (per-GPU step; aggregate {n8['value']:.0f} TFLOP/s)", n8["ms_per_step"])]:
+    A(f"| {name} | {ms:.3f} | {3732.3 / ms:.0f} | {3.7323 / ms / 1.6976:.2f} |")
+
+A("\n## W4A16 per shape, module dispatch (us, cold L2) — SD1.5 / SDXL / SD3.5-L\n")
+r1 = {"sd15": "gemm_layers_r01.json", "sdxl": "gemm_layers_sdxl_r01.json", "sd35": "gemm_layers_sd35_r01.json"}
+r2 = {"sd15": "gemm_layers_r02.json", "sdxl": "gemm_layers_sdxl_r02.json", "sd35": "gemm_layers_sd35_r02.json"}
+for m in ("sd15", "sdxl", "sd35"):
+    a, b = rows_of(load(r1[m])), rows_of(load(r2[m]))
+    old = {(r["M"], r["N"], r["K"]): r for r in a}
+    A(f"\n### {m}\n")
+    A("| M | N | K | calls | kernel (tile) | round 1 | round 2 | cuBLAS f16 | W8A8 GEMM |\n|---:|---:|---:|---:|---|---:|---:|---:|---:|")
+    t1 = t2 = tc = 0.0
+    for r in b:
+        k = (r["M"], r["N"], r["K"])
+        o = old.get(k)
+        c = r["calls_per_step"]
+        t2 += c * r["w4a16"]["ms"]
+        tc += c * r["cublas_f16"]["ms"]
+        t1 += c * (o["w4a16"]["ms"] if o else r["w4a16"]["ms"])
+        A(f"| {k[0]} | {k[1]} | {k[2]} | {c} | {r['w4a16_kernel'][0]} ({r['w4a16_kernel'][1]}) | {(o['w4a16']['ms'] * 1e3 if o else float('nan')):.1f} | {r['w4a16']['ms'] * 1e3:.1f} | {r['cublas_f16']['ms'] * 1e3:.1f} | {r['w8a8_gemm']['ms'] * 1e3:.1f} |")
+    A(f"\nwhole Linear pass: round 1 {t1 * 1e3:.0f} us -> round 2 {t2 * 1e3:.0f} us; cuBLAS f16 on the fake-quant weights {tc * 1e3:.0f} us.")
+
+c = load("calib_scaling_r02.json")
+A("\n## AWQ calibration of the SD3.5-Large skeleton (BASELINE config 4), sharded\n")
+A("| GPUs | s / model | capture (FP forwards) | exchange | scale search | clip search | swap + pack | codes checksum |\n|---:|---:|---:|---:|---:|---:|---:|---|")
+for n in ("1", "2", "4", "8"):
+    p = c[n]["phases"]
+    A(f"| {n} | {c[n]['s_per_model']:.2f} | {p.get('capture_forward_s', 0):.2f} | {p.get('capture_exchange_s', 0):.3f} | {p['scale_search_s']:.2f} | {p['clip_search_s']:.2f} | {p.get('swap_pack_s', 0):.2f} | {c[n]['codes_checksum']} |")
+A("\n" + c["how"] + ". Round 1 measured 6 of the 38 blocks only. The checksum covers `qweight`, `qzeros`, `scales` of all 536 packed")
+A("Linears: identical at every world size. History at 1 GPU: 9.5 s (clip search in torch) -> 6.3 s (clip-search kernel: clip phase")
+A("4.0 -> 0.8 s) -> 4.0 s (capture into one arena: ~2 s of `cudaMalloc` for thousands of per-call clones gone). At 8 GPUs the")
+A("first version of the capture exchange (grouped point-to-point sends) cost 8.4 s of NCCL peer-connection set-up; one `all_gather`")
+A("per block over the already-connected collective channels moves the same ~10 GB in 0.08-0.13 s.\n")
+
+A(open(os.path.join(R, "_notes_r02.md")).read())
+open(os.path.join(R, "ROUND2.md"), "w").write("\n".join(out) + "\n")
+print("wrote profiles/ROUND2.md")

@@ -7,6 +7,7 @@ ly = json.load(open(os.path.join(R, "gemm_layers_r01.json")))
 out = []
 A = out.append
 A("# profiles/ — round 1 evidence (B200, sm_100a)\n")
+A("**Round 2 evidence (TS kernel, clip-search kernel, sharded calibration at 1-8 GPUs, per-model tables): `ROUND2.md`.**\n")
 A("All numbers were measured on the pool's B200 through `gpurun`; peaks are the driver-written `MEASURED_PEAKS.json`")
 A(f"(HBM copy {ab['peaks']['hbm']:.0f} GB/s, cuBLAS bf16 {ab['peaks']['bf16_burst']:.0f} TFLOP/s burst / {ab['peaks']['bf16_sustained']:.0f} sustained).")
 A("Timings: CUDA events on the launching stream after warm-up, GPU-side (launches replayed from a CUDA graph, a 256 MB")
