@@ -275,7 +275,6 @@ class BaseAWQForDiffusion:
         """models/base.py:530-582 re-thought: the denoiser state dict (packed int4 / int8 tensors for swapped
         modules) + quantization_config + the list of quantised components."""
         os.makedirs(save_dir, exist_ok=True)
-        torch.save(self.denoiser().state_dict(), os.path.join(save_dir, "denoiser.pt"))
         kinds, wrapped = {}, set()
         for n, m in self.denoiser().named_modules():
             k = type(m).__name__
@@ -295,6 +294,17 @@ class BaseAWQForDiffusion:
                 "quant_config": self.quant_config.to_dict(), "quant_components": self.quantized_components, "modules": kinds}
         with open(os.path.join(save_dir, "quant_components.json"), "w") as f:
             json.dump(meta, f, indent=1)
+        # the weights as safetensors (models/base.py:566-582 writes `model.safetensors` the same way): packed int32 / int8
+        # tensors keep their dtype; the Hugging Face `quantization_config` (models/_config.py:97-107) also travels in the
+        # file's metadata, so the file alone says how to read it.  Tensors that share storage are written once per name.
+        from safetensors.torch import save_file
+        state, seen = {}, set()
+        for k, v in self.denoiser().state_dict().items():
+            v = v.detach().contiguous()
+            state[k] = v.clone() if (v.numel() and v.data_ptr() in seen) else v
+            seen.add(v.data_ptr())
+        save_file(state, os.path.join(save_dir, "model.safetensors"),
+                  metadata={"format": "pt", "quantization_config": json.dumps(meta["quantization_config"]), "model_type": str(self.model_type)})
 
     @classmethod
     def from_quantized(cls, save_dir, device="cuda", dtype=torch.float16):
@@ -334,7 +344,12 @@ class BaseAWQForDiffusion:
             else:
                 new = (WxAxConv2d.from_quant_args(old, args) if args else WxAxConv2d.from_float(old, init_only=True)).to(old.weight.device)
             set_op_by_name(den, name, new)
-        den.load_state_dict(torch.load(os.path.join(save_dir, "denoiser.pt"), map_location=device))
+        st_path = os.path.join(save_dir, "model.safetensors")
+        if os.path.exists(st_path):
+            from safetensors.torch import load_file
+            den.load_state_dict(load_file(st_path, device=str(device)))
+        else:   # checkpoints written before the safetensors format
+            den.load_state_dict(torch.load(os.path.join(save_dir, "denoiser.pt"), map_location=device))
         model.is_quantized = True
         model.quantized_components = meta["quant_components"]
         return model

@@ -454,7 +454,7 @@ def w4a16_repack_ts(qweight, qzeros, scales, group):
     return blob
 
 
-def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=None):
+def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=None, out=None):
     """x @ dequant(qweight, qzeros, scales) + bias, AWQ GEMM layout (quantize/quantizer.py:544-569).
     `blob` = w4a16_repack(...) of the same weight routes M > 128 problems to the repacked-weight kernel.
     This is the per-Linear hot call of a denoise step: the Python side is kept to the bare minimum."""
@@ -470,7 +470,12 @@ def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=
     if not x2.is_contiguous():
         x2 = x2.contiguous()
     m = x2.shape[0]
-    y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    if out is None:
+        y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    else:   # caller-owned output (a [M, N] contiguous view): no allocation in the call
+        if out.shape != (m, n) or out.dtype != x.dtype or not out.is_contiguous() or out.device != x.device:
+            raise ValueError(f"out must be a contiguous [{m}, {n}] {x.dtype} tensor on {x.device}")
+        y = out
     if bias is not None and (bias.dtype != x.dtype or not bias.is_contiguous()):
         bias = bias.to(x.dtype).contiguous()
     L = _lib._lib or lib()

@@ -151,8 +151,9 @@ def w4a16_repack(qweight, qzeros, scales, group):
 w4a16_repack_ts = w4a16_repack
 
 
-def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=None):
-    return _linear(x, dequant_awq(qweight, qzeros, scales, group).t(), bias)
+def gemm_w4a16(x, qweight, qzeros, scales, group, bias=None, blob=None, blob_ts=None, out=None):
+    y = _linear(x, dequant_awq(qweight, qzeros, scales, group).t(), bias)
+    return y if out is None else out.copy_(y.reshape(out.shape))
 
 
 def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):

@@ -241,3 +241,36 @@ def test_w4a16_tmem_a_kernel(qdm, M, N, K, group, dt):
             assert rel_err_gpu(y2, ref - b.float()) <= TOL, width
     finally:
         qdm.ops.set_gemm_mode(0)
+
+
+@pytest.mark.parametrize("case", [(300, 512, 256, 0, True), (1232, 1280, 768, 0, True), (4096, 320, 320, 0, True), (333, 2432, 2432, 0, True),
+                                  (512, 640, 640, 2, False), (65536, 320, 320, 0, False), (4096, 1280, 2560, 8, False), (100, 256, 128, 1, False),
+                                  (16, 1280, 320, 0, True), (1, 4864, 2432, 0, True), (129, 72, 256, 0, True)])
+def test_w4a16_writes_only_its_output(qdm, case):
+    """Own bounds check (compute-sanitizer is closed on this pool, profiles/sanitizer_r02.txt): every kernel family writes
+    into a caller-owned [M, N] view in the middle of a sentinel-filled buffer; the guard rows before and after must survive
+    and the result must still match the fp32 reference (a column overrun would land in the next row)."""
+    M, N, K, mode, ts = case
+    g = torch.Generator(device=DEV).manual_seed(11 * M + N + K)
+    grp = shapes.group_for(K)
+    x = torch.randn(M, K, generator=g, device=DEV, dtype=torch.float16)
+    w = (torch.randn(N, K, generator=g, device=DEV) * 0.05).half()
+    b = torch.randn(N, generator=g, device=DEV).half()
+    if N % 64 == 0:
+        qw, qz, sc, dq = qdm.ops.quant_pack_awq(w, grp, want_dq=True)
+    else:
+        import oracle.qdm_oracle as O
+        oq, oz, os_, dq = O.awq_from_linear(w.cpu(), grp, 4)
+        qw, qz, sc, dq = torch.from_numpy(oq).to(DEV), torch.from_numpy(oz).to(DEV), os_.to(DEV), dq.to(DEV)
+    bts = qdm.ops.w4a16_repack_ts(qw, qz, sc, grp) if ts else None
+    guard = 8
+    big = torch.full((M + 2 * guard, N), 12345.0, dtype=torch.float16, device=DEV)
+    out = big[guard:guard + M]
+    qdm.ops.set_gemm_mode(mode)
+    try:
+        y = qdm.ops.gemm_w4a16(x, qw, qz, sc, grp, b, None, bts, out=out)
+    finally:
+        qdm.ops.set_gemm_mode(0)
+    assert y.data_ptr() == out.data_ptr()
+    assert bool((big[:guard] == 12345.0).all()) and bool((big[guard + M:] == 12345.0).all()), qdm.ops.gemm_last_variant()
+    assert rel_err_gpu(y, ref_linear_gpu(x, dq, b)) <= TOL, qdm.ops.gemm_last_variant()

@@ -60,6 +60,14 @@ def test_swap_pointwise_convs_and_checkpoint(version, inner, tmp_path):
         assert torch.isfinite(out).all()
         assert ((out.float() - fp).abs().max() / fp.abs().max()).item() < (0.5 if version == "gemm" else 0.1)
         model.save_quantized(str(tmp_path))
+        # the checkpoint is a safetensors file whose metadata carries the Hugging Face quantization_config (models/base.py:530-582)
+        import json
+        from safetensors import safe_open
+        with safe_open(str(tmp_path / "model.safetensors"), framework="pt") as f:
+            qc = json.loads(f.metadata()["quantization_config"])
+            keys = set(f.keys())
+        assert qc["quant_method"] == "awq" and qc["bits"] == (4 if version == "gemm" else 8) and "group_size" in qc
+        assert keys == set(model.denoiser().state_dict().keys())
         again = M.StableDiffusion1_x.from_quantized(str(tmp_path), device="cpu")
         for k, v in packed_state(model).items():
             assert torch.equal(v, again.denoiser().state_dict()[k]), k
