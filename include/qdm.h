@@ -292,13 +292,6 @@ int qdm_conv3x3_nhwc_w4a16(const void* x, const int32_t* qweight, const int32_t*
                            const void* bias, void* y, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
                            int64_t N, int group, void* stream);
 
-/* Host-buffer entry used for the end-to-end measurement: x_host/y_host are (pinned) HOST buffers,
- * x_dev/y_dev device staging buffers of the same size owned by the caller; the call does
- * H2D(x) -> qdm_gemm_w4a16 -> D2H(y) on `stream`. */
-int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight, const int32_t* qzeros,
-                        const void* scales, const void* bias, void* y_dev, void* y_host, int dtype,
-                        int64_t M, int64_t N, int64_t K, int group, void* stream);
-
 /* Optional workspace of the W4A16 GEMM (device memory owned by the caller, qdm_gemm_workspace_bytes() bytes, kept until
  * replaced or cleared with NULL; one per device).  With it, problems whose whole-tile waves would leave CTA pairs idle
  * (few tiles with a long K, a nearly empty last wave) run the stream-K kernel, which parks partial fp32 accumulators

@@ -74,7 +74,6 @@ SIGNATURES = {
     "qdm_selftest_fastdiv": (c_int, [_I, _P]),
     "qdm_gemm_workspace_bytes": (c_size_t, []),
     "qdm_gemm_set_workspace": (c_int, [_P, _Z, _P]),
-    "qdm_gemm_w4a16_host": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _L, _L, _I, _P]),
 }
 
 _lib = None

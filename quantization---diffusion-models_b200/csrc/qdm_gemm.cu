@@ -2009,17 +2009,3 @@ extern "C" int qdm_gemm_w8a8(const int8_t* xq, const float* sx, const int8_t* wq
   return dispatch_gemm<G_I8>(m, p, pair, (cudaStream_t)stream);
 }
 
-extern "C" int qdm_gemm_w4a16_host(const void* x_host, void* x_dev, const int32_t* qweight, const int32_t* qzeros,
-                                   const void* scales, const void* bias, void* y_dev, void* y_host, int dtype,
-                                   int64_t M, int64_t N, int64_t K, int group, void* stream) {
-  QDM_REQUIRE(x_host && x_dev && y_dev && y_host, "qdm_gemm_w4a16_host: null pointer");
-  QDM_REQUIRE(M > 0 && N > 0 && K > 0, "qdm_gemm_w4a16_host: empty problem");
-  QDM_DEVICE_GATE();
-  cudaStream_t st = (cudaStream_t)stream;
-  QDM_CUDA_OK(cudaMemcpyAsync(x_dev, x_host, size_t(M) * K * 2, cudaMemcpyHostToDevice, st));
-  int rc = qdm_gemm_w4a16(x_dev, qweight, qzeros, scales, bias, y_dev, dtype, M, N, K, group, stream);
-  if (rc) return rc;
-  QDM_CUDA_OK(cudaMemcpyAsync(y_host, y_dev, size_t(M) * N * 2, cudaMemcpyDeviceToHost, st));
-  return QDM_OK;
-}
-

@@ -572,14 +572,3 @@ def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
         check(fn(x_in.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(), _ptr(bs), y.data_ptr(),
                  _dt(x_in), b, h, w, c, n, int(group), _stream(x)))
     return _conv3x3_out(y, h, w, direct)
-
-
-def gemm_w4a16_host(x_host, x_dev, qweight, qzeros, scales, group, bias, y_dev, y_host):
-    """Host-buffer entry: pinned x_host -> device -> W4A16 GEMM -> pinned y_host, all on the current stream."""
-    k, nw = qweight.shape
-    m = x_host.numel() // k
-    with _guard(x_dev.device):
-        check(lib().qdm_gemm_w4a16_host(x_host.data_ptr(), x_dev.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(),
-                                        scales.data_ptr(), _ptr(bias), y_dev.data_ptr(), y_host.data_ptr(),
-                                        _dt(x_dev), m, nw * 8, k, int(group), _stream(x_dev)))
-    return y_host
