@@ -1736,7 +1736,7 @@ extern "C" int qdm_set_gemm_mode(int ctas) {
   QDM_REQUIRE(mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 8 || mode == 16 || mode == 32 || mode == 64 || mode == 128,
               "qdm_set_gemm_mode: 0 (auto), 1 (single CTA), 2 (CTA pair), 4 (quad cluster), 8 (stream-K), 16 / 32 (repacked weights, "
               "one / two sub-tiles) or 64 (no repacked weights)");
-  QDM_REQUIRE(tile == 0 || (tile % 16 == 0 && tile <= 256), "qdm_set_gemm_mode: tile width %d must be a multiple of 16 <= 256", tile);
+  QDM_REQUIRE(tile == 0 || (tile % 16 == 0 && tile <= 384), "qdm_set_gemm_mode: tile width %d must be a multiple of 16 <= 384", tile);
   g_force_ctas = mode == 64 ? 0 : mode;
   g_no_rp = mode == 64;
   g_force_tile = tile;
@@ -1786,19 +1786,24 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
   return dispatch_gemm<G_F16_KN>(m, p, false, (cudaStream_t)stream);
 }
 
-// TS kernel (qdm_gemm_w4ts.cu): tokens per tile.  A pair owns 256 output channels x T tokens, T a multiple of 32 <= 192.
-// Per tile a CTA moves K/64 x (64 T + 4608) bytes from L2 (its T/2 token rows + 128 channels of packed weights) at
-// ~39 B/clk/SM (the measured L2 -> SM rate with every SM pulling) against 2 T cycles of tensor-pipe time per k-block; the
-// epilogue is hidden (two accumulator buffers).  T is chosen so that the last wave is not nearly empty.
+// Token-tile width of the TS kernel (qdm_gemm_w4ts.cu).  Cost model fitted to the per-shape measurements of
+// profiles/ts_models_r02.txt (cycles at the ~1.65 GHz the SMs run at inside these kernels; it reproduces 14 of the measured
+// shapes to ~7 %): a K = 128 stage costs 700 + 2 T cycles with two alternating tiles of T <= 192 tokens (issue-bound below
+// T = 192: barrier test, commit and eight ~55-cycle MMA issues per stage; 600 per tile for fill / drain), and 8 Ts + 60 with
+// ONE wide tile of two sub-tiles of Ts = T / 2 tokens (sixteen MMAs per stage: tensor-pipe-bound), whose epilogue
+// (1800 + 14 T cycles) is not overlapped.  Wide tiles win where they remove a wave (4096 x 1280 x 5120: 41.4 vs 52.2 us,
+// 16384 x 640 x 2560: 54.6 vs 62.5) or the main loop is long (K >= 2432); a 5 % margin keeps the overlapped form on ties.
 int choose_ts_tile(int64_t M, int64_t N, int64_t K, double* cost_out) {
-  const int64_t P = QDM_NUM_SMS / 2, n_blks = (N + 255) / 256, num_kb = K / 64;
+  const int64_t P = QDM_NUM_SMS / 2, n_blks = (N + 255) / 256, num_st = (K / 64 + 1) / 2;
   int best = 192;
   double best_cost = 1e300;
-  for (int t = 192; t >= 32; t -= 32) {   // multiples of 32: the epilogue stores 32-token boxes
+  for (int t = 384; t >= 32; t -= 32) {   // multiples of 32: the epilogue stores 32-token boxes; > 192: two sub-tiles (WIDE)
     if (g_force_tile && t != g_force_tile) continue;
+    const bool wide = t > 192;
+    if (wide && t % 64 != 0) continue;
     const int64_t tiles = n_blks * ((M + t - 1) / t), waves = (tiles + P - 1) / P;
-    const double mma = 2.0 * t, l2 = (64.0 * t + 4608.0) / 39.0;
-    const double cost = double(waves) * (double(num_kb) * ((mma > l2 ? mma : l2) + 30.0) + 800.0);
+    double cost = wide ? double(waves) * (double(num_st) * (8.0 * (t / 2) + 60.0) + 1800.0 + 14.0 * t) / 0.95
+                       : double(waves) * (double(num_st) * (700.0 + 2.0 * t) + 600.0);
     if (cost < best_cost * 0.999) { best_cost = cost; best = t; }
   }
   if (cost_out) *cost_out = best_cost;

@@ -48,12 +48,17 @@ constexpr int TS_THREADS = 512;
 
 // DW = TMEM columns of ONE accumulator buffer = most tokens per tile.  Two buffers (the epilogue of tile t overlaps the
 // main loop of tile t + 1) + the weight ring share the 512 columns: DW = 128 -> 4 weight stages, DW = 192 -> 2.
-template <int DW>
+// WIDE: the two accumulator buffers are the two halves ("sub-tiles") of ONE tile of up to 2 DW tokens instead of two
+// alternating tiles: every weight stage feeds 16 MMAs instead of 8 (the issuing thread's fixed cost per stage -- barrier
+// test, commit -- and the dequant work are amortised over twice the tokens), at the price of an epilogue that no longer
+// overlaps the next tile's main loop.  Taken where it removes a wave of tiles or the main loop is long (qdm_gemm.cu).
+template <int DW, bool WIDE = false>
 struct CfgTS {
   static constexpr int NS = (512 - 2 * DW) / 64;             // weight stages in TMEM (64 columns = 128 k each)
   static constexpr int A_COL0 = 2 * DW;
   static constexpr int KB_BYTES = DW * 64;                   // one k-block of activations: DW / 2 token rows x 128 B
-  static constexpr int X_STAGE_BYTES = TS_KB * KB_BYTES;
+  static constexpr int SUBS = WIDE ? 2 : 1;
+  static constexpr int X_STAGE_BYTES = TS_KB * SUBS * KB_BYTES;   // [k-block][sub-tile][DW / 2 rows x 128 B]
   // activation stages in shared memory: deeper than the weight ring -- the L2 -> SM latency under load is 3000-5000
   // cycles (measured), several stages of tensor-pipe time
 #ifndef TS_NXS192
@@ -62,7 +67,7 @@ struct CfgTS {
 #ifndef TS_NXS128
 #define TS_NXS128 8
 #endif
-  static constexpr int NXS = DW <= 160 ? TS_NXS128 : TS_NXS192;
+  static constexpr int NXS = WIDE ? (DW == 128 ? 5 : DW == 160 ? 4 : 3) : (DW <= 160 ? TS_NXS128 : TS_NXS192);
   static constexpr int EPI_BYTES = 2 * 32 * 256;             // two staging tiles [32 tokens][128 channels] x 2 B
   static constexpr int SMEM_BYTES = NXS * X_STAGE_BYTES + EPI_BYTES + 1024 + TS_BAR_BYTES;
   static_assert(NS >= 2 && NXS > NS, "the dequant sets wait on the release barrier of the stage NS back: it must still be the x ring's current phase");
@@ -186,6 +191,37 @@ __device__ __forceinline__ uint32_t ts_issue_stage(uint32_t tmem_c, uint32_t tme
   return done;
 }
 
+// WIDE tiles: one k-block (4 x K 16) for BOTH accumulators = 8 MMAs; the next stage's barrier is tested first and its
+// predicate read after the last MMA of the block (the caller ORs the two k-blocks' results).
+__device__ __forceinline__ uint32_t ts_issue_kblock_wide(uint32_t tmem_c0, uint32_t tmem_c1, uint32_t tmem_a, uint32_t desc_lo0,
+                                                        uint32_t desc_lo1, uint32_t desc_hi, uint32_t idesc, uint32_t accum,
+                                                        uint32_t next_bar, uint32_t next_parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred pa, pt, pd;\n\t.reg .b64 d0, d1;\n\t.reg .b32 l0, l1, ta;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pd, [%9], %10;\n\t"
+      "setp.ne.b32 pa, %8, 0;\n\t"
+      "setp.eq.b32 pt, %8, %8;\n\t"
+      "mov.b64 d0, {%4, %6};\n\tmov.b64 d1, {%5, %6};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [%3], d0, %7, pa;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%2], [%3], d1, %7, pa;\n\t"
+      "add.u32 l0, %4, 2;\n\tadd.u32 l1, %5, 2;\n\tadd.u32 ta, %3, 8;\n\tmov.b64 d0, {l0, %6};\n\tmov.b64 d1, {l1, %6};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d0, %7, pt;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%2], [ta], d1, %7, pt;\n\t"
+      "add.u32 l0, %4, 4;\n\tadd.u32 l1, %5, 4;\n\tadd.u32 ta, %3, 16;\n\tmov.b64 d0, {l0, %6};\n\tmov.b64 d1, {l1, %6};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d0, %7, pt;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%2], [ta], d1, %7, pt;\n\t"
+      "add.u32 l0, %4, 6;\n\tadd.u32 l1, %5, 6;\n\tadd.u32 ta, %3, 24;\n\tmov.b64 d0, {l0, %6};\n\tmov.b64 d1, {l1, %6};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%1], [ta], d0, %7, pt;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%2], [ta], d1, %7, pt;\n\t"
+      "selp.u32 %0, 1, 0, pd;\n\t}"
+      : "=r"(done)
+      : "r"(tmem_c0), "r"(tmem_c1), "r"(tmem_a), "r"(desc_lo0), "r"(desc_lo1), "r"(desc_hi), "r"(idesc), "r"(accum), "r"(next_bar),
+        "r"(next_parity)
+      : "memory");
+  return done;
+}
+
 struct TsParams {
   int M, N, K;                 // tokens, output channels, reduction
   int tile_t;                  // tokens per tile (multiple of 16, <= 256)
@@ -197,10 +233,10 @@ struct TsParams {
 };
 
 // ---------------------------------------------------------------- the kernel
-template <int DW, bool BF16>
+template <int DW, bool BF16, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TS_THREADS, 1)
 qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const TsParams p) {
-  using C = CfgTS<DW>;
+  using C = CfgTS<DW, WIDE>;
   constexpr int NS = C::NS, NXS = C::NXS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -222,7 +258,9 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = int(blockIdx.x) >> 1, num_pairs = int(gridDim.x) >> 1;
-  const int T = p.tile_t, th = T >> 1;                              // tokens per tile, per CTA
+  const int T = p.tile_t;                                          // tokens per tile
+  const int Ts = WIDE ? T >> 1 : T;                                // ... per accumulator (sub-tile): the MMA's N
+  const int th = Ts >> 1;                                          // token rows of one TMA box = per CTA and sub-tile
   const int n_blks = (p.N + 255) / 256, m_blks = (p.M + T - 1) / T;
   const int num_tiles = n_blks * m_blks;                           // tile = n_blk * m_blks + m_blk: token blocks fastest, so
   const int num_kb = p.K / 64;                                     // concurrently running pairs share a weight slab in L2
@@ -264,7 +302,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       int trc_it = 0;
       const uint32_t kb_bytes = uint32_t(th) * ROW_BYTES;               // the tensor map's box is th token rows x 64 k
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = TS_MBLK(tile) * T + int(rank) * th;
+        const int m0 = TS_MBLK(tile) * T + int(rank) * th;   // sub-tile s adds s * Ts: an accumulator's columns are consecutive tokens
         for (int st = 0; st < num_st; ++st) {
           mbar_wait(x_empty_bar(stage), phase ^ 1);
           TRC(p.trace, 0, 2000000 + trc_it);
@@ -274,11 +312,11 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           if (rank == 0) mbar_arrive(full_bar(stage));
           for (int j = 0; j < 0; ++j)
 #else
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * uint32_t(nk) * kb_bytes);   // rows past M are zero-filled and counted
-          for (int j = 0; j < nk; ++j)
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * uint32_t(nk * C::SUBS) * kb_bytes);   // rows past M are zero-filled and counted
+          for (int j = 0; j < nk * C::SUBS; ++j)
 #endif
             tma_load_2d_pair(smem_base + stage * C::X_STAGE_BYTES + j * C::KB_BYTES, &map_x, leader_full0 + 8u * stage,
-                             (st * TS_KB + j) * 64, m0);
+                             (st * TS_KB + j / C::SUBS) * 64, m0 + (j % C::SUBS) * Ts);
           if (++stage == NXS) { stage = 0; phase ^= 1; }
         }
       }
@@ -286,15 +324,15 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 0, 2 * BLOCK_M, T);
+      const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 0, 2 * BLOCK_M, Ts);
       int stage = 0, as = 0;
       uint32_t phase = 0;
       TRC_DECL;
       int trc_it = 0;
       uint32_t ready = 0;                                                // has the peek already seen this stage's barrier complete?
       for (int tl = 0; tl < my_tiles; ++tl) {
-        const int acc = tl & 1;
-        mbar_wait(tmem_empty_bar(acc), (uint32_t(tl >> 1) & 1u) ^ 1u);
+        const int acc = WIDE ? 0 : (tl & 1);      // WIDE: both buffers belong to this tile; one full / empty barrier pair
+        mbar_wait(tmem_empty_bar(acc), (uint32_t(WIDE ? tl : (tl >> 1)) & 1u) ^ 1u);
         TRC(p.trace, 1, 1000000 + trc_it);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + uint32_t(acc * DW);
@@ -315,10 +353,20 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const uint64_t db = make_smem_desc(smem_base + stage * C::X_STAGE_BYTES, 16, 1024);
           const uint32_t ta = tmem_base + uint32_t(C::A_COL0 + as * 64);
           // the next stage's barrier is tested inside the block (top) and its result read after the stage's last MMA
-          const uint32_t ready_next =
-              nk == 2 ? ts_issue_stage<2>(tmem_c, ta, uint32_t(db), uint32_t(C::KB_BYTES >> 4), uint32_t(db >> 32), idesc, uint32_t(st != 0),
-                                          full_bar(nstage), nphase)
-                      : ts_issue_stage<1>(tmem_c, ta, uint32_t(db), 0u, uint32_t(db >> 32), idesc, uint32_t(st != 0), full_bar(nstage), nphase);
+          uint32_t ready_next;
+          if (WIDE) {
+            constexpr uint32_t KBD = uint32_t(C::KB_BYTES >> 4);   // descriptor units of one [sub-tile] box
+            ready_next = ts_issue_kblock_wide(tmem_c, tmem_c + uint32_t(DW), ta, uint32_t(db), uint32_t(db) + KBD, uint32_t(db >> 32), idesc,
+                                              uint32_t(st != 0), full_bar(nstage), nphase);
+            if (nk == 2)
+              ready_next |= ts_issue_kblock_wide(tmem_c, tmem_c + uint32_t(DW), ta + 32u, uint32_t(db) + 2u * KBD, uint32_t(db) + 3u * KBD,
+                                                 uint32_t(db >> 32), idesc, 1u, full_bar(nstage), nphase);
+          } else {
+            ready_next =
+                nk == 2 ? ts_issue_stage<2>(tmem_c, ta, uint32_t(db), uint32_t(C::KB_BYTES >> 4), uint32_t(db >> 32), idesc, uint32_t(st != 0),
+                                            full_bar(nstage), nphase)
+                        : ts_issue_stage<1>(tmem_c, ta, uint32_t(db), 0u, uint32_t(db >> 32), idesc, uint32_t(st != 0), full_bar(nstage), nphase);
+          }
           TRC(p.trace, 1, 7000000 + trc_it - 1);
           umma_commit_pair(x_empty_bar(stage), 3);   // the stage's x slot AND its TMEM weight slot: one commit, two kinds of waiters
           TRC(p.trace, 1, 3000000 + trc_it - 1);
@@ -340,20 +388,22 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     int trc_it = 0;
     uint32_t chunk = 0;
     for (int tl = 0; tl < my_tiles; ++tl) {
-      const int tile = pair + tl * num_pairs, acc = tl & 1;
+      const int tile = pair + tl * num_pairs, acc = WIDE ? 0 : (tl & 1);
       const int n0 = TS_NBLK(tile) * 256 + int(rank) * 128;               // this CTA's 128 channels
-      const int m0 = TS_MBLK(tile) * T;
+      const int m_tile = TS_MBLK(tile) * T;
       const int n = n0 + ew * 32 + lane;
       float bias = 0.f;
       if (p.bias && n < p.N) {
         if (BF16) bias = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n]);
         else bias = __half2float(reinterpret_cast<const __half*>(p.bias)[n]);
       }
-      mbar_wait(tmem_full_bar(acc), uint32_t(tl >> 1) & 1u);
+      mbar_wait(tmem_full_bar(acc), uint32_t(WIDE ? tl : (tl >> 1)) & 1u);
       if (threadIdx.x == 128) TRC(p.trace, 2, 1000000 + trc_it);
       tc_fence_after();
-      const int t_end = min(T, p.M - m0);
-      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * DW);
+      for (int sub = 0; sub < C::SUBS; ++sub) {
+      const int m0 = m_tile + sub * Ts;                                   // first token of this accumulator
+      const int t_end = min(Ts, p.M - m0);
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t((WIDE ? sub : acc) * DW);
       for (int c = 0; c < t_end; c += 32, ++chunk) {
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c), v);
@@ -372,6 +422,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 128 && n0 < p.N) tma_store_2d(&map_y, stg, n0, m0 + c);   // 128 channels x 32 tokens, clipped at N and M
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -531,10 +582,10 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   }
 }
 
-template <int DW, bool BF16>
+template <int DW, bool BF16, bool WIDE = false>
 int launch_ts(const CUtensorMap& mx, const CUtensorMap& my, const TsParams& p, cudaStream_t st) {
-  using C = CfgTS<DW>;
-  auto kern = qdm_w4ts_kernel<DW, BF16>;
+  using C = CfgTS<DW, WIDE>;
+  auto kern = qdm_w4ts_kernel<DW, BF16, WIDE>;
   static bool attr_set = false;
   if (!attr_set) {
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -611,17 +662,24 @@ extern "C" int qdm_w4a16_repack_ts(const int32_t* qweight, const int32_t* qzeros
 int qdm_w4ts_gemm(const void* x, const void* blob, const void* bias, void* y, int is_bf16, int64_t M, int64_t N, int64_t K, int tile_t,
                   cudaStream_t st) {
   QDM_REQUIRE(blob && qdm_aligned16(blob), "qdm_gemm_w4a16_ts: the repacked weight must be 16-byte aligned");
-  QDM_REQUIRE(tile_t >= 32 && tile_t <= 192 && tile_t % 32 == 0, "qdm_gemm_w4a16_ts: bad token tile %d", tile_t);
+  // tile_t <= 192: two alternating tiles of tile_t tokens; 256 / 320 / 384: ONE tile of two sub-tiles of tile_t / 2 tokens (WIDE)
+  const bool wide = tile_t > 192;
+  QDM_REQUIRE(tile_t >= 32 && tile_t <= 384 && tile_t % (wide ? 64 : 32) == 0, "qdm_gemm_w4a16_ts: bad token tile %d", tile_t);
   QDM_REQUIRE(K % 64 == 0 && N % 8 == 0, "qdm_gemm_w4a16_ts: shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   int rc = get_encode_fn();
   if (rc) return rc;
   CUtensorMap mx, my;
-  if ((rc = make_map(&mx, x, 2, M, K, 64, tile_t / 2))) return rc;        // 64 k x (T / 2) token rows per CTA, SWIZZLE_128B
+  if ((rc = make_map(&mx, x, 2, M, K, 64, wide ? tile_t / 4 : tile_t / 2))) return rc;   // 64 k x token rows per CTA (and sub-tile), SWIZZLE_128B
   if ((rc = make_map(&my, y, 2, M, N, 128, 32, false))) return rc;        // 128 channels x 32 tokens, dense 256-byte rows
   TsParams p{};
   p.M = int(M); p.N = int(N); p.K = int(K); p.tile_t = tile_t; p.bias = bias; p.y = y;
   p.words = static_cast<const uint32_t*>(blob);
   p.sz = p.words + (K / 64) * N * 8;
+  if (wide) {
+    if (tile_t <= 256) return is_bf16 ? launch_ts<128, true, true>(mx, my, p, st) : launch_ts<128, false, true>(mx, my, p, st);
+    if (tile_t <= 320) return is_bf16 ? launch_ts<160, true, true>(mx, my, p, st) : launch_ts<160, false, true>(mx, my, p, st);
+    return is_bf16 ? launch_ts<192, true, true>(mx, my, p, st) : launch_ts<192, false, true>(mx, my, p, st);
+  }
   if (tile_t <= 128) return is_bf16 ? launch_ts<128, true>(mx, my, p, st) : launch_ts<128, false>(mx, my, p, st);
   if (tile_t <= 160) return is_bf16 ? launch_ts<160, true>(mx, my, p, st) : launch_ts<160, false>(mx, my, p, st);
   return is_bf16 ? launch_ts<192, true>(mx, my, p, st) : launch_ts<192, false>(mx, my, p, st);

@@ -86,6 +86,10 @@ def test_w4a16_baseline_shape(qdm, model, M, N, K, dt):
     if (M, N, K) in ((4096, 1280, 1280), (8192, 1280, 1280), (4096, 2432, 2432), (1232, 1280, 768), (333, 2432, 2432), (4096, 10240, 1280),
                      (4096, 9728, 2432), (16384, 5120, 640)):
         assert variant == "ts", (variant, tile)
+    if (M, N, K) in ((4096, 1280, 5120), (4096, 2432, 9728), (16384, 640, 2560)):   # one wave less / long main loop: wide tile
+        assert variant == "ts" and tile > 192, (variant, tile)
+    if (M, N, K) in ((4096, 10240, 1280), (16384, 5120, 640), (8192, 1280, 1280)):   # many waves, short K: overlapped epilogue
+        assert variant == "ts" and tile <= 192, (variant, tile)
     if (M, N, K) in ((65536, 320, 320), (65536, 2560, 320), (65536, 320, 1280)):
         assert variant in ("pair", "bstat"), (variant, tile)
 
@@ -228,7 +232,7 @@ def test_w4a16_tmem_a_kernel(qdm, M, N, K, group, dt):
         qdm.ops.set_gemm_mode(64)                            # the AWQ-tensor kernels
         y_awq = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b, None, bts)
         assert qdm.ops.gemm_last_variant()[0] != "ts"
-        for width in (0, 32, 64, 96, 128, 160, 192):
+        for width in (0, 32, 64, 96, 128, 160, 192, 256, 320, 384):   # > 192: one wide tile of two sub-tiles
             qdm.ops.set_gemm_mode(128 | (width << 8))
             y1 = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b, None, bts)
             variant, tile = qdm.ops.gemm_last_variant()

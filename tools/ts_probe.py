@@ -21,10 +21,10 @@ def main():
     if what == "check":
         cases = [(256, 256, 128), (256, 256, 256), (512, 512, 512), (300, 320, 320), (777, 520, 448), (4096, 1280, 1280), (1232, 1280, 768),
                  (333, 2432, 2432), (4096, 64, 2432), (8192, 640, 2560), (129, 72, 256), (200, 8, 128)]
-        tiles = [0, 192, 160, 128, 64, 32]
+        tiles = [0, 384, 320, 256, 192, 128, 64]
     elif what == "quick":
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (4096, 9728, 2432), (1232, 1280, 768), (16384, 640, 640)]
-        tiles = [0, 192, 160, 128]
+        tiles = [0, 320, 192]
     elif what == "models":   # every distinct Linear shape (M > 32) of the three denoisers
         seen = []
         for layers in (S.sd15_unet_linears(batch=8, cfg=True), S.sdxl_unet_linears(batch=4, cfg=True), S.sd35_mmdit_linears(batch=1)):
@@ -32,7 +32,7 @@ def main():
                 if m_ > 32 and (m_, n_, k_) not in seen:
                     seen.append((m_, n_, k_))
         cases = seen
-        tiles = [0, 192, 160, 128, 96, 64]
+        tiles = [0]
     else:
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (16384, 640, 640), (4096, 1280, 5120), (8192, 1280, 1280),
                  (4096, 2432, 2432), (4096, 9728, 2432), (1232, 1280, 768), (333, 2432, 2432), (65536, 2560, 320), (65536, 320, 320)]
