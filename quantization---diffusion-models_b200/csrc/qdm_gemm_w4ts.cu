@@ -68,7 +68,11 @@ struct CfgTS {
 #define TS_NXS128 8
 #endif
   static constexpr int NXS = WIDE ? (DW == 128 ? 5 : DW == 160 ? 4 : 3) : (DW <= 160 ? TS_NXS128 : TS_NXS192);
-  static constexpr int EPI_BYTES = 2 * 32 * 256;             // two staging tiles [32 tokens][128 channels] x 2 B
+#ifndef TS_EPI_TILES
+#define TS_EPI_TILES 2
+#endif
+  static constexpr int EPI_TILES = TS_EPI_TILES;
+  static constexpr int EPI_BYTES = EPI_TILES * 32 * 256;     // staging tiles [32 tokens][128 channels] x 2 B
   static constexpr int SMEM_BYTES = NXS * X_STAGE_BYTES + EPI_BYTES + 1024 + TS_BAR_BYTES;
   static_assert(NS >= 2 && NXS > NS, "the dequant sets wait on the release barrier of the stage NS back: it must still be the x ring's current phase");
   static_assert(8 * (2 * NXS + NS + 4) + 8 <= TS_BAR_BYTES, "barrier area");
@@ -407,8 +411,8 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int c = 0; c < t_end; c += 32, ++chunk) {
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c), v);
-        const uint32_t stg = epi_base + (chunk & 1u) * 8192u;
-        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store of two chunks ago has read this tile
+        const uint32_t stg = epi_base + (chunk % uint32_t(C::EPI_TILES)) * 8192u;
+        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::EPI_TILES - 1) : "memory");   // the store of EPI_TILES chunks ago has read this tile
         asm volatile("bar.sync 1, 128;" ::: "memory");
         tmem_ld_wait();
 #pragma unroll
