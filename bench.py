@@ -276,15 +276,24 @@ def sub_denoise(args, dev, rank, world, sync_max):
     lat = torch.randn(batch, 4, 64, 64, generator=torch.Generator().manual_seed(42 + rank)).to(dev, model.pipeline.dtype)
     model.generate(prompts, lat=lat, num_inference_steps=2)
     sync_max(0.0)
-    q.ops.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    res = model.generate(prompts, lat=lat, num_inference_steps=steps)
-    e1.record()
-    torch.cuda.synchronize()
-    sec = sync_max(e0.elapsed_time(e1) * 1e-3)
+
+    def timed_loop(graph):
+        model.generate(prompts, lat=lat, num_inference_steps=2, cuda_graph=graph)   # warm-up (captures the step when graph)
+        sync_max(0.0)
+        q.ops.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = model.generate(prompts, lat=lat, num_inference_steps=steps, cuda_graph=graph)
+        e1.record()
+        torch.cuda.synchronize()
+        return sync_max(e0.elapsed_time(e1) * 1e-3), r, q.ops.launch_count()
+
+    sec_eager, res_eager, launches = timed_loop(False)
+    sec, res, _ = timed_loop(True)
     out = {"it_per_s": steps / sec, "images_it_per_s": world * batch * steps / sec, "steps": steps, "batch_per_gpu": batch, "quant": "w4a16 g128",
-           "seconds": sec, "finite": bool(torch.isfinite(res).all()), "libqdm_launches": q.ops.launch_count(),
+           "seconds": sec, "finite": bool(torch.isfinite(res).all()), "it_per_s_eager": steps / sec_eager,
+           "graph_equals_eager": bool(torch.equal(res, res_eager)), "libqdm_launches_per_step": launches // steps,
+           "how": "generate(..., cuda_graph=True): every denoiser call replayed from one CUDA graph (skeletons.SkeletonPipeline._graph_step); it_per_s_eager = the same loop launched eagerly",
            "model": "SD1.5 UNet skeleton (random init), packed Linears + 1x1 / 3x3 convolutions", "scaling": "weak (data parallel, no collective in the loop)"}
     del model
     torch.cuda.empty_cache()

@@ -230,6 +230,8 @@ class BaseAWQForDiffusion:
         """Same call shape as the reference (first positional is `tokenizer`; the method is picked by `quantType`).
         New keywords: `calibrate` (run the AWQ scale/clip search on the diffusion blocks), `alpha` (SmoothQuant),
         `shard` = (rank, world) for the sharded search."""
+        if hasattr(self.pipeline, "invalidate_graphs"):
+            self.pipeline.invalidate_graphs()          # captured denoise steps point at the modules about to be replaced
         quant_config = dict(quant_config)
         if quant_act and quant_config.get('version', 'fake_act').lower() != 'fake_act':
             quant_config['version'] = 'fake_act'
@@ -264,11 +266,12 @@ class BaseAWQForDiffusion:
     # ------------------------------------------------------------------ models/base.py:829-850
     @torch.no_grad()
     def generate(self, prompt, height=512, width=512, num_inference_steps=50, guidance_scale=7.5, negative_prompt=None,
-                 num_images_per_prompt=1, generator=None, device="cpu", lat=None, output_type=None, **kwargs):
+                 num_images_per_prompt=1, generator=None, device="cpu", lat=None, output_type=None, cuda_graph=False, **kwargs):
+        """models/base.py:829-850.  `cuda_graph=True` replays each denoiser call from a CUDA graph (skeletons.SkeletonPipeline)."""
         if self.pipeline is None:
             raise RuntimeError("The diffusion pipeline is not loaded. Please use `from_pretrained` or `from_quantized` first.")
         return self.pipeline(prompt=prompt, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
-                             num_images_per_prompt=1, generator=generator, latents=lat, output_type=output_type)
+                             num_images_per_prompt=1, generator=generator, latents=lat, output_type=output_type, cuda_graph=cuda_graph)
 
     # ------------------------------------------------------------------ packed checkpoint (SURVEY.md 8f-2)
     def save_quantized(self, save_dir):

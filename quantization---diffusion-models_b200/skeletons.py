@@ -407,6 +407,41 @@ class SkeletonPipeline:
     def to(self, *a, **k):
         return self
 
+    def invalidate_graphs(self):
+        """drop the captured denoise steps (the module tree or its buffers changed: quantize(), from_quantized())"""
+        self._graphs = {}
+
+    def _graph_step(self, xin, t, ctx, pooled):
+        """One denoiser call replayed from a CUDA graph (captured once per input signature after two eager warm-up calls,
+        which also build the kernel-native weight copies of the packed Linears).  The ~280 libqdm launches and ~1000 torch
+        ops of an SD1.5 step cost more host time (Python, ctypes, tensor-map encodes) than GPU time when launched eagerly;
+        replaying removes all of it.  Inputs are copied into the graph's static buffers; forward hooks do not run inside a
+        replay, so calibration passes never take this path."""
+        key = (tuple(xin.shape), tuple(ctx.shape), None if pooled is None else tuple(pooled.shape), xin.dtype)
+        ent = getattr(self, "_graphs", {}).get(key)
+        if ent is None:
+            sx, st, sc = xin.clone(), t.clone(), ctx.clone()
+            sp = None if pooled is None else pooled.clone()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.denoise(sx, st, sc, sp)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.denoise(sx, st, sc, sp)
+            ent = (g, sx, st, sc, sp, out)
+            if not hasattr(self, "_graphs"):
+                self._graphs = {}
+            self._graphs[key] = ent
+        g, sx, st, sc, sp, out = ent
+        sx.copy_(xin); st.copy_(t); sc.copy_(ctx)
+        if sp is not None:
+            sp.copy_(pooled)
+        g.replay()
+        return out
+
     def encode(self, prompts):
         ctx = torch.stack([_prompt_tensor(p, self.ctx_shape, self.device, self.dtype) for p in prompts])
         pooled = None
@@ -422,8 +457,9 @@ class SkeletonPipeline:
 
     @torch.no_grad()
     def __call__(self, prompt, latents=None, num_inference_steps=50, guidance_scale=7.5, callback_on_step_end=None,
-                 num_images_per_prompt=1, generator=None, output_type="latent", **_):
+                 num_images_per_prompt=1, generator=None, output_type="latent", cuda_graph=False, **_):
         prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        cuda_graph = bool(cuda_graph) and self.device.type == "cuda"
         b = len(prompts)
         if latents is None:
             latents = torch.randn((b, self.latent_channels, self.latent_size, self.latent_size), generator=generator,
@@ -439,7 +475,8 @@ class SkeletonPipeline:
         dt = 1.0 / num_inference_steps
         for i, t in enumerate(ts):
             xin = torch.cat([x, x]) if do_cfg else x
-            eps = self.denoise(xin, t.expand(xin.shape[0]), ctx, pooled)
+            tt = t.expand(xin.shape[0])
+            eps = self._graph_step(xin, tt, ctx, pooled) if cuda_graph else self.denoise(xin, tt, ctx, pooled)
             if do_cfg:
                 eu, ec = eps.chunk(2)
                 eps = eu + guidance_scale * (ec - eu)

@@ -391,6 +391,11 @@ def test_quantize_gemm_swaps_pointwise_convs(qdm, tmp_path):
         model.save_quantized(d)
         again = M.StableDiffusion1_x.from_quantized(d, device=DEV)
         assert torch.equal(again.generate(["a", "b"], lat=lat, num_inference_steps=2), out)
+        # the denoise step replayed from a CUDA graph gives the same latents as the eager loop, also after a re-quantisation
+        # has replaced the modules the first capture pointed at (quantize() drops the captured graphs)
+        assert torch.equal(again.generate(["a", "b"], lat=lat, num_inference_steps=2, cuda_graph=True), out)
+        assert torch.equal(again.generate(["c", "d"], lat=lat, num_inference_steps=3, cuda_graph=True),
+                           again.generate(["c", "d"], lat=lat, num_inference_steps=3))
 
 
 def test_wxax_conv_vs_reference_fixture(qdm):
