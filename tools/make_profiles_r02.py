@@ -23,6 +23,9 @@ A("`--set full --clock-control none --import-source on`, absolute times cold-cac
 A("## Files (round 2)\n")
 A("| file | what |\n|---|---|")
 for f, w in [
+    ("bench_line_r02.json", "`bench.py` at 1 GPU, final build: the full line (W4A16 step, e2e, roofline, clocks, W8A8 / denoise / calibration sub-records, CPU baseline)"),
+    ("ts_models_wide_r02.txt, ts_models_auto_r02.txt", "`tools/ts_probe.py models`: wide (256 / 320 / 384) vs narrow token tiles per shape, and what the module's cost model picks"),
+    ("sanitizer_r02.txt", "compute-sanitizer is closed on this pool; what stands in for it"),
     ("bench_line_r02_n8.json", "`bench.py --gpus 8` (torchrun, NCCL): the full line incl. W8A8, denoise and the 38-block SD3.5-L calibration sub-records"),
     ("bench_line_r02_a.json", "the first round-2 line (before the TS kernel), kept for the history below"),
     ("launches_bench_step_r02.csv, step_by_shape_r02.txt, step_traffic_r02.json", "ncu launch list of one eager bench step (184 launches: duration, DRAM read / write bytes), aggregated by shape; `step_traffic` is what `bench.py` reports as `roofline.traffic` (`tools/step_durations.sh`, `tools/step_by_shape.py`)"),
@@ -40,7 +43,9 @@ A("\n## Bench line history (SD1.5 UNet step, 184 W4A16 Linear calls, 3.73 TFLOP)
 A("| state | ms / step | TFLOP/s | fraction of burst bf16 peak (1697.6) |\n|---|---:|---:|---:|")
 for name, ms in [("round 1 final", 5.198), ("round 2 start (shape-parity work, clip kernel, no GEMM change)", 5.20), ("RP kernel (per-tile repack, 2 sub-tiles) for one-wave shapes", 5.04),
                  ("TS kernel, first dispatch (few-wave + text-token shapes)", 4.907), ("TS kernel: issuer rewritten (peeks inside one asm block, one commit per stage), TS default", 4.610),
-                 ("role-local PDL waits (weights fetched while the previous kernel drains)", 4.580), (f"8 GPUs, same build (per-GPU step; aggregate {n8['value']:.0f} TFLOP/s)", n8["ms_per_step"])]:
+                 ("role-local PDL waits (weights fetched while the previous kernel drains)", 4.580),
+                 ("wide tiles (two sub-tiles, 16 MMAs per weight stage) where the fitted cost model prefers them; `bench_line_r02.json`", load("bench_line_r02.json")["ms_per_step"]),
+                 (f"8 GPUs, build before the wide tiles (per-GPU step; aggregate {n8['value']:.0f} TFLOP/s)", n8["ms_per_step"])]:
     A(f"| {name} | {ms:.3f} | {3732.3 / ms:.0f} | {3.7323 / ms / 1.6976:.2f} |")
 
 A("\n## W4A16 per shape, module dispatch (us, cold L2) — SD1.5 / SDXL / SD3.5-L\n")
