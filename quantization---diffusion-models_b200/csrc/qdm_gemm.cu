@@ -437,7 +437,7 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -483,7 +483,7 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr bool B_MN = (KIND == G_F16_KN || KIND == G_W4);
       const uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, BLOCK_M, tile_n)
                                             : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, BLOCK_M, tile_n);
@@ -516,7 +516,7 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 3) {
     // ===================================================== raw int4 producer: one stage = two k-blocks of packed B
-    if (KIND == G_W4 && RAWT && lane == 0) {
+    if (KIND == G_W4 && RAWT && elect_one()) {
       const int srows = p.group == 64 ? 2 : 1;                    // quantisation groups per 128 k rows
       const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
       const uint32_t tx = R::tx_bytes(srows);
@@ -705,7 +705,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs; each loads its own halves)
-    if (lane == 0) {
+    if (elect_one()) {
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
@@ -746,7 +746,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr bool B_MN = (KIND == G_W4);
       const uint32_t idesc = (KIND == G_I8) ? make_idesc(2, 1, 0, 2 * BLOCK_M, tile_n)
                                             : make_idesc(1, BF16 ? 1 : 0, B_MN ? 1 : 0, 2 * BLOCK_M, tile_n);
@@ -785,7 +785,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 3) {
     // ===================================================== raw int4 producer (each CTA: its own packed columns)
-    if (KIND == G_W4 && RAWT && lane == 0) {
+    if (KIND == G_W4 && RAWT && elect_one()) {
       const int srows = p.group == 64 ? 2 : 1;
       const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
       const uint32_t tx = R::tx_bytes(srows);
@@ -975,7 +975,7 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     // ===================================================== TMA producer: A
-    if (lane == 0) {
+    if (elect_one()) {
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
@@ -991,7 +991,7 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 1, 2 * BLOCK_M, tile_n);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, ready = 0;
@@ -1018,7 +1018,7 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 3) {
     // ===================================================== raw int4 producer
-    if (lane == 0) {
+    if (elect_one()) {
       const int srows = p.group == 64 ? 2 : 1;
       const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
       const uint32_t tx = R::tx_bytes(srows);
@@ -1238,7 +1238,7 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
   if (warp == 0) {
     // ===================================================== TMA producer: A only
-    if (lane == 0) {
+    if (elect_one()) {
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
@@ -1254,7 +1254,7 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 1, 2 * BLOCK_M, tile_n);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, ready = 0;
@@ -1284,7 +1284,7 @@ qdm_gemm2_bstat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
   } else if (warp == 3) {
     // ===================================================== raw int4 producer: this pair's n-tile, once
-    if (lane == 0 && pair < num_tiles) {
+    if (pair < num_tiles && elect_one()) {
       const int srows = p.group == 64 ? 2 : 1;
       const int gdiv = p.group < 128 ? 128 / p.group : 1, gmul = p.group > 128 ? p.group / 128 : 1;
       const uint32_t tx = R::tx_bytes(srows);
@@ -1787,12 +1787,12 @@ extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias
 }
 
 // Token-tile width of the TS kernel (qdm_gemm_w4ts.cu).  Cost model fitted to the per-shape measurements of
-// profiles/ts_models_r02.txt (cycles at the ~1.65 GHz the SMs run at inside these kernels; it reproduces 14 of the measured
-// shapes to ~7 %): a K = 128 stage costs 700 + 2 T cycles with two alternating tiles of T <= 192 tokens (issue-bound below
-// T = 192: barrier test, commit and eight ~55-cycle MMA issues per stage; 600 per tile for fill / drain), and 8 Ts + 60 with
-// ONE wide tile of two sub-tiles of Ts = T / 2 tokens (sixteen MMAs per stage: tensor-pipe-bound), whose epilogue
-// (1800 + 14 T cycles) is not overlapped.  Wide tiles win where they remove a wave (4096 x 1280 x 5120: 41.4 vs 52.2 us,
-// 16384 x 640 x 2560: 54.6 vs 62.5) or the main loop is long (K >= 2432); a 5 % margin keeps the overlapped form on ties.
+// profiles/ts_models_wide_r02.txt (cycles at the ~1.65 GHz the SMs run at inside these kernels; it reproduces the measured
+// shapes to ~8 %): a K = 128 stage costs 450 + 2.25 T cycles with two alternating tiles of T <= 192 tokens (883 at T = 192
+// against 768 cycles of tensor-pipe work; 600 per tile for fill / drain), and 8 Ts + 60 with ONE wide tile of two
+// sub-tiles of Ts = T / 2 tokens (sixteen MMAs per stage: tensor-pipe-bound), whose epilogue (1800 + 14 T cycles) is not
+// overlapped.  Wide tiles win where they remove a wave on a long main loop (4096 x 1280 x 5120: 41.1 vs 47.6 us); a 5 %
+// margin keeps the overlapped form on ties.
 int choose_ts_tile(int64_t M, int64_t N, int64_t K, double* cost_out) {
   const int64_t P = QDM_NUM_SMS / 2, n_blks = (N + 255) / 256, num_st = (K / 64 + 1) / 2;
   int best = 192;
@@ -1803,7 +1803,7 @@ int choose_ts_tile(int64_t M, int64_t N, int64_t K, double* cost_out) {
     if (wide && t % 64 != 0) continue;
     const int64_t tiles = n_blks * ((M + t - 1) / t), waves = (tiles + P - 1) / P;
     double cost = wide ? double(waves) * (double(num_st) * (8.0 * (t / 2) + 60.0) + 1800.0 + 14.0 * t) / 0.95
-                       : double(waves) * (double(num_st) * (700.0 + 2.0 * t) + 600.0);
+                       : double(waves) * (double(num_st) * (450.0 + 2.25 * t) + 600.0);
     if (cost < best_cost * 0.999) { best_cost = cost; best = t; }
   }
   if (cost_out) *cost_out = best_cost;
@@ -1855,9 +1855,10 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
         const int64_t m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), n_tiles = (N + tn - 1) / tn, max_pairs = QDM_NUM_SMS / 2;
         bstat = n_tiles <= max_pairs && m_tiles * n_tiles >= 3 * max_pairs;
       }
-      // 256-channel blocks: N = 320 idles 3/8 of the MMA rows and dequant warps of its second block; with many token tiles
-      // (M >= 16384) the AWQ-tensor kernel's 160-wide tiles win there (65536 x 320 x 1280: 68.8 vs 76.1 us); N = 640 ties
-      const bool wasteful = ((N + 255) / 256) * 256 * 4 > int64_t(N) * 5 && M >= 16384;
+      // 256-channel blocks: N = 320 idles 3/8 and N = 640 1/6 of the MMA rows and dequant warps of the last block; with many
+      // token tiles (M >= 16384) the AWQ-tensor kernel's 160- / 224-wide tiles win there (65536 x 320 x 1280: 60.0 vs 74.2 us,
+      // 16384 x 640 x 2560: 49.9 vs 54.6, 32768 x 640 x 2560: 89.8 vs 102.5; 16384 x 640 x 640 ties)
+      const bool wasteful = ((N + 255) / 256) * 256 * 100 > int64_t(N) * 115 && M >= 16384;
       take = !bstat && !wasteful && tiles <= int64_t(opt.ts_waves) * (QDM_NUM_SMS / 2);
     }
     if (take) {

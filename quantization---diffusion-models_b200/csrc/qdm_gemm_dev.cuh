@@ -102,6 +102,14 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return done;
 }
+// One thread of a converged warp, the way the compiler understands it: a branch on elect.sync's predicate is known to be
+// taken by exactly one lane, so instructions with uniform-register operands inside it (tcgen05.mma / commit, TMA) need no
+// per-instruction "for each active lane" loop (ELECT + BRA.U.ANY around every UTCHMMA when the condition is `lane == 0`).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // Spin on the non-blocking test: on a barrier that is (about to be) complete this returns tens of cycles after the phase
 // flips, where mbarrier.try_wait costs ~250-450 cycles even on an already complete phase (measured in the TS kernel's trace:
 // the MMA issuer idled the tensor pipe for ~450 of every ~1250 cycles).  Only for waits that are known to be short.

@@ -315,7 +315,7 @@ qdm_w4rp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     // ===================================================== TMA producer: A (both CTAs, each its 128 rows)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -331,7 +331,7 @@ qdm_w4rp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 1, 2 * BLOCK_M, sub_n);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -362,7 +362,7 @@ qdm_w4rp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 3) {
     // ===================================================== raw producer: one bulk copy per sub-tile part per 128 k rows
-    if (lane == 0) {
+    if (elect_one()) {
       int rs = 0;
       uint32_t rphase = 0;
       const int nblk_part = nloc / RP_BLK_COLS;

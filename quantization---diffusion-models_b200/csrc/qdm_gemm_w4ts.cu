@@ -298,7 +298,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
   if (warp == 0) {
     // ===================================================== TMA producer: x, this CTA's half of the tile's tokens
-    if (lane == 0) {
+    if (elect_one()) {
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
@@ -327,7 +327,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {   // elect.sync, not `lane == 0`: the compiler then knows ONE lane runs this (qdm_gemm_dev.cuh)
       const uint32_t idesc = make_idesc(1, BF16 ? 1 : 0, 0, 2 * BLOCK_M, Ts);
       int stage = 0, as = 0;
       uint32_t phase = 0;

@@ -86,11 +86,13 @@ def test_w4a16_baseline_shape(qdm, model, M, N, K, dt):
     if (M, N, K) in ((4096, 1280, 1280), (8192, 1280, 1280), (4096, 2432, 2432), (1232, 1280, 768), (333, 2432, 2432), (4096, 10240, 1280),
                      (4096, 9728, 2432), (16384, 5120, 640)):
         assert variant == "ts", (variant, tile)
-    if (M, N, K) in ((4096, 1280, 5120), (4096, 2432, 9728), (16384, 640, 2560)):   # one wave less / long main loop: wide tile
+    if (M, N, K) in ((4096, 1280, 5120),):                                            # one wave less on a long main loop: wide tile
         assert variant == "ts" and tile > 192, (variant, tile)
-    if (M, N, K) in ((4096, 10240, 1280), (16384, 5120, 640), (8192, 1280, 1280)):   # many waves, short K: overlapped epilogue
+    if (M, N, K) in ((4096, 10240, 1280), (16384, 5120, 640), (8192, 1280, 1280), (4096, 9728, 2432)):   # overlapped epilogue
         assert variant == "ts" and tile <= 192, (variant, tile)
-    if (M, N, K) in ((65536, 320, 320), (65536, 2560, 320), (65536, 320, 1280)):
+    if (M, N, K) in ((16384, 640, 2560), (32768, 640, 2560), (16384, 640, 640)):      # N = 640 with many token tiles
+        assert variant == "pair", (variant, tile)
+    if (M, N, K) in ((65536, 320, 320), (65536, 2560, 320), (65536, 320, 1280)):      # K = 320 / N = 320 with many token tiles
         assert variant in ("pair", "bstat"), (variant, tile)
 
 
