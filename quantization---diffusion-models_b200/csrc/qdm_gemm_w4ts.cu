@@ -388,6 +388,10 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // (256-byte rows: a quarter of the TMA rows that per-warp 64-byte boxes need) and warp 4 stores it with one TMA
     // store per 32 tokens; two staging tiles alternate.  The whole epilogue overlaps the next tile's main loop.
     const int ew = warp - 4;
+    // the thread that issues (and later waits for) the TMA stores: elected once, so that both happen on the same lane and the
+    // compiler knows the branch is taken by one lane (no per-instruction active-lane loop around the store)
+    const bool el = elect_one();
+    const bool epi_leader = el && warp == 4;
     TRC_DECL;
     int trc_it = 0;
     uint32_t chunk = 0;
@@ -412,7 +416,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c), v);
         const uint32_t stg = epi_base + (chunk % uint32_t(C::EPI_TILES)) * 8192u;
-        if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::EPI_TILES - 1) : "memory");   // the store of EPI_TILES chunks ago has read this tile
+        if (epi_leader) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(C::EPI_TILES - 1) : "memory");   // the store of EPI_TILES chunks ago has read this tile
         asm volatile("bar.sync 1, 128;" ::: "memory");
         tmem_ld_wait();
 #pragma unroll
@@ -425,7 +429,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 128 && n0 < p.N) tma_store_2d(&map_y, stg, n0, m0 + c);   // 128 channels x 32 tokens, clipped at N and M
+        if (epi_leader && n0 < p.N) tma_store_2d(&map_y, stg, n0, m0 + c);   // 128 channels x 32 tokens, clipped at N and M
       }
       }
       tc_fence_before();
@@ -434,7 +438,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       ++trc_it;
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
     }
-    if (threadIdx.x == 128) tma_store_wait_all();
+    if (epi_leader) tma_store_wait_all();
   } else if (warp >= 8) {
     // ===================================================== dequant: registers -> TMEM
     const int set = (warp - 8) >> 2, q = warp & 3;                       // TMEM lane quarter = warp % 4
