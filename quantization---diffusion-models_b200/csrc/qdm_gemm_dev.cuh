@@ -434,6 +434,9 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
   // stream-K: part_row + q * part_stride is this lane's entry in the q-th earlier partial accumulator of the tile (fp32,
   // layout [half][16-byte chunk][128 rows], see qdm_gemm2_sk_kernel); the partials are added in slot order, so the
   // result does not depend on timing
+  // the lane that issues and later waits for this warp's TMA stores: elect.sync tells the compiler that one lane runs those
+  // branches (no active-lane loop around the store); `&& lane == 0` pins the choice so that successive calls agree on it
+  const bool store_leader = elect_one() && lane == 0;
   const int n_end = min(n0 + (tile_w ? tile_w : p.tile_n), p.N);   // columns of this (sub-)tile that exist
   const int row = row0 + lane;
   float sxr = 1.f;
@@ -468,7 +471,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
     const int width = min(EPI_COLS, n_end - nc);            // columns of the chunk inside the tile
     const bool whole = width == EPI_COLS;
     if (hh == 0) {   // the previous stores of this warp must have read the staging buffer before it is overwritten
-      if (lane == 0) tma_store_wait_read();
+      if (store_leader) tma_store_wait_read();
       __syncwarp();
     }
 #pragma unroll
@@ -505,7 +508,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, const CUtens
 #ifdef QDM_EXP_NOSTORE   // timing experiment only (no output): what the epilogue's TMA stores cost
       if (false) {
 #else
-      if (lane == 0) {
+      if (store_leader) {
 #endif
         if (whole) {
           tma_store_2d(map_y, stg, nc, row0);
