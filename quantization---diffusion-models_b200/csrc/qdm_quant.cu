@@ -436,30 +436,38 @@ quant_rows_warp_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int6
 // 16-byte loads up front (NV in flight), the row statistics come from a shuffle butterfly and the row is
 // quantised from registers -- one pass over HBM (elem read + outputs), unlike the two-pass kernel above.
 // I8OUT: emit int8 codes + fp32 scale (the A8 of W8A8) instead of the fake-quantised row.
-template <typename T, int MODE, int NV, bool I8OUT>
+// LPR = lanes per row (32, 16 or 8): short rows (K = 320 / 640 activations: 40 / 80 vectors) share a warp, 32 / LPR rows at a
+// time, so that every lane still has ~5 loads in flight and the butterfly has log2(LPR) steps -- with one warp per 640-byte
+// row the per-token quantiser ran at 0.44 of the HBM peak (issue-bound on the per-row overhead), against 0.86 at K = 1280.
+template <typename T, int MODE, int NV, bool I8OUT, int LPR = 32>
 __global__ void __launch_bounds__(kQThreads)
 quant_rows_reg_kernel(const T* __restrict__ x, int64_t rows, int cols, float max_int, float min_int,
                       T* __restrict__ dq, int8_t* __restrict__ codes,
                       T* __restrict__ scales, T* __restrict__ zeros, float* __restrict__ sx) {
   constexpr int V = ElemTraits<T>::kVec;
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;                          // rows per warp
+  const int lane = threadIdx.x & (LPR - 1);              // lane inside the row's group
+  const int sub = (threadIdx.x & 31) / LPR;              // which of the warp's rows
   const int wpb = kQThreads / 32;
   const float dummy[V] = {};
   const float dummy8[8] = {};
-  for (int64_t row = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows;
-       row += int64_t(gridDim.x) * wpb) {
+  for (int64_t row0 = (int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5)) * RPW; row0 < rows;
+       row0 += int64_t(gridDim.x) * wpb * RPW) {
+    // a group past the last row works on the last row again and skips every store (the shuffles below need all lanes)
+    const bool row_on = row0 + sub < rows;
+    const int64_t row = row_on ? row0 + sub : rows - 1;
     const T* p = x + row * cols;
     Vec16<T> raw[NV];
 #pragma unroll
     for (int t = 0; t < NV; ++t) {
-      const int e = (t * 32 + lane) * V;
+      const int e = (t * LPR + lane) * V;
       if (e < cols) raw[t] = ld_vec16_stream(p + e);
     }
     if constexpr (std::is_same<T, __half>::value) {
       __half2 m2 = __float2half2_rn((MODE == Q_ZP) ? -INFINITY : 0.f), n2 = __float2half2_rn(INFINITY);
 #pragma unroll
       for (int t = 0; t < NV; ++t) {
-        if ((t * 32 + lane) * V < cols) {
+        if ((t * LPR + lane) * V < cols) {
           __half2 a, b;
           fold_h<MODE>(as_h2x4(raw[t]), a, b);
           m2 = __hmax2(m2, a);
@@ -467,17 +475,17 @@ quant_rows_reg_kernel(const T* __restrict__ x, int64_t rows, int cols, float max
         }
       }
       float mx, mn, s, z, r;
-      reduce_h<MODE>(m2, n2, 32, mx, mn);
+      reduce_h<MODE>(m2, n2, LPR, mx, mn);
       group_params_h<MODE>(mx, mn, max_int, rcp_approx(max_int), s, z, r);
-      if (lane == 0) {
+      if (lane == 0 && row_on) {
         if (I8OUT) sx[row] = s;
         if (scales) scales[row] = __float2half_rn(s);
         if (zeros && MODE == Q_ZP) zeros[row] = __float2half_rn(z);
       }
-      if (!dq && !codes) continue;
+      if ((!dq && !codes) || !row_on) continue;
 #pragma unroll
       for (int t = 0; t < NV; ++t) {
-        const int e = (t * 32 + lane) * V;
+        const int e = (t * LPR + lane) * V;
         if (e < cols) {
           H2x4 o, cq;
           rtn_vec_h<MODE, false>(as_h2x4(raw[t]), s, r, z, min_int, max_int, dummy8, dummy8, o, cq);
@@ -489,7 +497,7 @@ quant_rows_reg_kernel(const T* __restrict__ x, int64_t rows, int cols, float max
       float mx = (MODE == Q_ZP) ? -INFINITY : 0.f, mn = INFINITY;
   #pragma unroll
       for (int t = 0; t < NV; ++t) {
-        const int e = (t * 32 + lane) * V;
+        const int e = (t * LPR + lane) * V;
         if (e < cols) {
   #pragma unroll
           for (int j = 0; j < V; ++j) {
@@ -499,23 +507,23 @@ quant_rows_reg_kernel(const T* __restrict__ x, int64_t rows, int cols, float max
         }
       }
   #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = LPR / 2; o > 0; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (MODE == Q_ZP) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
       }
       float s, z;
       group_params<T, MODE>(mx, mn, max_int, s, z);
-      if (lane == 0) {
+      if (lane == 0 && row_on) {
         if (I8OUT) sx[row] = s;
         if (scales) scales[row] = ElemTraits<T>::from_f(s);
         if (zeros && MODE == Q_ZP) zeros[row] = ElemTraits<T>::from_f(z);
       }
-      if (!dq && !codes) continue;
+      if ((!dq && !codes) || !row_on) continue;
       const float amax = (MODE == Q_ZP) ? fmaxf(fabsf(mx), fabsf(mn)) : mx;
       const bool fast = fastdiv_ok<T>(s, amax);
   #pragma unroll
       for (int t = 0; t < NV; ++t) {
-        const int e = (t * 32 + lane) * V;
+        const int e = (t * LPR + lane) * V;
         if (e < cols) {
           float xv[V], cq[V];
           Vec16<T> o;
@@ -968,12 +976,30 @@ int launch_rows_reg(const T* x, int64_t rows, int64_t cols, float max_int, float
     quant_rows_reg_kernel<T, MODE, NV, I8OUT><<<(unsigned)grid, kQThreads, 0, st>>>(x, rows, int(cols), max_int, min_int, \
                                                                           dq, codes, scales, zeros, sx); \
   } while (0)
-  if (nv <= 1) QDM_ROWS_REG(1);
+  // short rows share a warp (<= 8 vectors per lane at 8 / 16 lanes per row)
+#define QDM_ROWS_SUB(LPR)                                                                             \
+  do {                                                                                                \
+    static int occ = 0;                                                                               \
+    if (occ == 0) {                                                                                   \
+      QDM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, quant_rows_reg_kernel<T, MODE, 8, I8OUT, LPR>, kQThreads, 0)); \
+      if (occ < 1) occ = 1;                                                                           \
+    }                                                                                                 \
+    const int64_t rpc = int64_t(kQThreads / 32) * (32 / LPR);                                         \
+    int64_t grid = (rows + rpc - 1) / rpc;                                                            \
+    if (grid > int64_t(QDM_NUM_SMS) * occ) grid = int64_t(QDM_NUM_SMS) * occ;                         \
+    quant_rows_reg_kernel<T, MODE, 8, I8OUT, LPR><<<(unsigned)grid, kQThreads, 0, st>>>(x, rows, int(cols), max_int, min_int, \
+                                                                               dq, codes, scales, zeros, sx); \
+  } while (0)
+  const int64_t vecs = (cols + V - 1) / V;
+  if (vecs > 32 && vecs <= 64 && rows >= 1024) QDM_ROWS_SUB(8);
+  else if (vecs > 64 && vecs <= 128 && rows >= 1024) QDM_ROWS_SUB(16);
+  else if (nv <= 1) QDM_ROWS_REG(1);
   else if (nv <= 2) QDM_ROWS_REG(2);
   else if (nv <= 4) QDM_ROWS_REG(4);
   else if (nv <= 8) QDM_ROWS_REG(8);
   else QDM_ROWS_REG(16);
 #undef QDM_ROWS_REG
+#undef QDM_ROWS_SUB
   QDM_LAUNCH_CHECK();
   return QDM_OK;
 }

@@ -32,7 +32,7 @@ def main():
                 if m_ > 32 and (m_, n_, k_) not in seen:
                     seen.append((m_, n_, k_))
         cases = seen
-        tiles = [0, 384, 320, 256, 192, 160, 128, 96, 64]
+        tiles = [0] if os.environ.get("TS_PROBE_AUTO") else [0, 384, 320, 256, 192, 160, 128, 96, 64]
     else:
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (16384, 640, 640), (4096, 1280, 5120), (8192, 1280, 1280),
                  (4096, 2432, 2432), (4096, 9728, 2432), (1232, 1280, 768), (333, 2432, 2432), (65536, 2560, 320), (65536, 320, 320)]
