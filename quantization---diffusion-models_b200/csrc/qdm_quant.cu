@@ -373,12 +373,24 @@ quant_rows_warp_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int6
     };
     float mx = (MODE == Q_ZP) ? -INFINITY : 0.f, mn = INFINITY;
     if (vec_ok) {
-      for (int64_t e = int64_t(lane) * V; e < cols; e += 32 * V) {
-        Vec16<T> v = ld_vec16(p + e);
+      // four 16-byte loads per lane in flight (rows longer than the register kernel's 4096 elements, e.g. K = 5120
+      // activations, were latency-bound at one load per lane per trip: 1.7 TB/s)
+      constexpr int U = 4;
+      for (int64_t e0 = int64_t(lane) * V; e0 < cols; e0 += int64_t(U) * 32 * V) {
+        Vec16<T> v[U];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          float f = prep(ElemTraits<T>::to_f(v.v[j]), e + j);
-          if (MODE == Q_ZP) { mx = fmaxf(mx, f); mn = fminf(mn, f); } else mx = fmaxf(mx, fabsf(f));
+        for (int u = 0; u < U; ++u)
+          if (e0 + int64_t(u) * 32 * V < cols) v[u] = ld_vec16(p + e0 + int64_t(u) * 32 * V);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t e = e0 + int64_t(u) * 32 * V;
+          if (e < cols) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              float f = prep(ElemTraits<T>::to_f(v[u].v[j]), e + j);
+              if (MODE == Q_ZP) { mx = fmaxf(mx, f); mn = fminf(mn, f); } else mx = fmaxf(mx, fabsf(f));
+            }
+          }
         }
       }
     } else {
@@ -405,20 +417,30 @@ quant_rows_warp_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, int6
       return d;
     };
     if (vec_ok) {
-      for (int64_t e = int64_t(lane) * V; e < cols; e += 32 * V) {
-        Vec16<T> v = ld_vec16(p + e);
-        Vec16<T> o;
-        int8_t cb[V];
+      constexpr int U = 4;
+      for (int64_t e0 = int64_t(lane) * V; e0 < cols; e0 += int64_t(U) * 32 * V) {
+        Vec16<T> vv[U];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          float code;
-          o.v[j] = ElemTraits<T>::from_f(finish(prep(ElemTraits<T>::to_f(v.v[j]), e + j), e + j, code));
-          cb[j] = code_to_i8<MODE>(code);
-        }
-        if (dq) st_vec16(dq + row * cols + e, o);
-        if (codes) {
+        for (int u = 0; u < U; ++u)
+          if (e0 + int64_t(u) * 32 * V < cols) vv[u] = ld_vec16(p + e0 + int64_t(u) * 32 * V);
 #pragma unroll
-          for (int j = 0; j < V; ++j) codes[row * cols + e + j] = cb[j];
+        for (int u = 0; u < U; ++u) {
+          const int64_t e = e0 + int64_t(u) * 32 * V;
+          if (e >= cols) continue;
+          Vec16<T> o;
+          uint32_t pk[V / 4];
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float code;
+            o.v[j] = ElemTraits<T>::from_f(finish(prep(ElemTraits<T>::to_f(vv[u].v[j]), e + j), e + j, code));
+            const uint32_t bb = uint32_t(uint8_t(code_to_i8<MODE>(code)));
+            if ((j & 3) == 0) pk[j / 4] = bb; else pk[j / 4] |= bb << (8 * (j & 3));
+          }
+          if (dq) st_vec16(dq + row * cols + e, o);
+          if (codes) {   // V consecutive codes as one 4- / 8-byte store (row * cols + e is a multiple of V: vec_ok)
+            if (V == 8) *reinterpret_cast<uint2*>(codes + row * cols + e) = make_uint2(pk[0], pk[V / 4 - 1]);
+            else *reinterpret_cast<uint32_t*>(codes + row * cols + e) = pk[0];
+          }
         }
       }
     } else {
@@ -703,11 +725,21 @@ actquant_token_i8_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, co
       return v;
     };
     float mx = 0.f;
+    constexpr int U = 4;   // 16-byte loads per lane in flight (this kernel serves rows longer than 4096 elements, e.g. K = 5120)
     if (vec_ok) {
-      for (int64_t e = int64_t(lane) * V; e < cols; e += 32 * V) {
-        Vec16<T> v = ld_vec16(p + e);
+      for (int64_t e0 = int64_t(lane) * V; e0 < cols; e0 += int64_t(U) * 32 * V) {
+        Vec16<T> v[U];
 #pragma unroll
-        for (int j = 0; j < V; ++j) mx = fmaxf(mx, fabsf(prep(ElemTraits<T>::to_f(v.v[j]), e + j)));
+        for (int u = 0; u < U; ++u)
+          if (e0 + int64_t(u) * 32 * V < cols) v[u] = ld_vec16(p + e0 + int64_t(u) * 32 * V);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t e = e0 + int64_t(u) * 32 * V;
+          if (e < cols) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) mx = fmaxf(mx, fabsf(prep(ElemTraits<T>::to_f(v[u].v[j]), e + j)));
+          }
+        }
       }
     } else {
       for (int64_t e = lane; e < cols; e += 32) mx = fmaxf(mx, fabsf(prep(ElemTraits<T>::to_f(p[e]), e)));
@@ -717,16 +749,24 @@ actquant_token_i8_kernel(const T* __restrict__ x, int64_t rows, int64_t cols, co
     group_params<T, Q_SYM_NOCLAMP>(mx, 0.f, 127.f, s, z);
     if (lane == 0) sx[row] = s;
     if (vec_ok) {
-      for (int64_t e = int64_t(lane) * V; e < cols; e += 32 * V) {
-        Vec16<T> v = ld_vec16(p + e);
-        int8_t cb[V];
+      for (int64_t e0 = int64_t(lane) * V; e0 < cols; e0 += int64_t(U) * 32 * V) {
+        Vec16<T> v[U];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const float q = rintf(rnd<T>(__fdiv_rn(prep(ElemTraits<T>::to_f(v.v[j]), e + j), s)));
-          cb[j] = code_to_i8<Q_SYM_NOCLAMP>(q);
+        for (int u = 0; u < U; ++u)
+          if (e0 + int64_t(u) * 32 * V < cols) v[u] = ld_vec16(p + e0 + int64_t(u) * 32 * V);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t e = e0 + int64_t(u) * 32 * V;
+          if (e >= cols) continue;
+          int8_t cb[V];
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float q = rintf(rnd<T>(__fdiv_rn(prep(ElemTraits<T>::to_f(v[u].v[j]), e + j), s)));
+            cb[j] = code_to_i8<Q_SYM_NOCLAMP>(q);
+          }
+          if (V == 8) *reinterpret_cast<uint2*>(xq + row * cols + e) = *reinterpret_cast<const uint2*>(cb);
+          else *reinterpret_cast<uint32_t*>(xq + row * cols + e) = *reinterpret_cast<const uint32_t*>(cb);
         }
-        if (V == 8) *reinterpret_cast<uint2*>(xq + row * cols + e) = *reinterpret_cast<const uint2*>(cb);
-        else *reinterpret_cast<uint32_t*>(xq + row * cols + e) = *reinterpret_cast<const uint32_t*>(cb);
       }
     } else {
       for (int64_t e = lane; e < cols; e += 32) {
