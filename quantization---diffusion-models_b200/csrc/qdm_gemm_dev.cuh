@@ -110,15 +110,6 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-// Spin on the non-blocking test: on a barrier that is (about to be) complete this returns tens of cycles after the phase
-// flips, where mbarrier.try_wait costs ~250-450 cycles even on an already complete phase (measured in the TS kernel's trace:
-// the MMA issuer idled the tensor pipe for ~450 of every ~1250 cycles).  Only for waits that are known to be short.
-__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
-  uint32_t polls = 0;
-  while (!mbar_test(bar, parity)) {
-    if (++polls > (1u << 28)) __trap();
-  }
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -341,11 +341,7 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + uint32_t(acc * DW);
         for (int st = 0; st < num_st; ++st) {
-#ifndef TS_MMA_SPIN
           if (!ready) mbar_wait(full_bar(stage), phase);
-#else
-          if (!ready) mbar_spin(full_bar(stage), phase);
-#endif
           TRC(p.trace, 1, (ready ? 2000000 : 9000000) + trc_it);    // 9 = the stage was not yet complete at the peek: waited
           if ((trc_it & 15) == 0) TRCG(p.trace, 1, 10000000 + trc_it);
           ++trc_it;
@@ -544,11 +540,9 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       if (q == 0 && lane == 0) TRC(p.trace, 3 + set, 1000000 + trc_it);
 #pragma unroll
       for (int j = 0; j < TS_KB; ++j) unpack(f[j], o[j]);
-#ifndef TS_LATE_PREFETCH
       // the packed words are dead once unpacked: load the set's NEXT stage into the same registers now, so the loads fly
       // while this stage waits for its TMEM slot, stores and arrives
       prefetch(f);
-#endif
       // slot free = the MMAs of stage wg = g - NS are complete = phase wg / NXS of that stage's release barrier.  The phase
       // after it needs this very stage to be consumed first (NXS > NS), so the waiter never sees the barrier two phases on.
       if (wg >= 0) mbar_wait(x_empty_bar(wg % NXS), uint32_t(wg / NXS) & 1u);
@@ -574,9 +568,6 @@ qdm_w4ts_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       for (int u = 0; u < TS_DIST; ++u) {
         if (it + u < mine) {
           process(ring[u]);
-#ifdef TS_LATE_PREFETCH
-          prefetch(ring[u]);
-#endif
         }
       }
     }
