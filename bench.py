@@ -75,25 +75,33 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def step_traffic():
-    """DRAM bytes of one step (sum over its 184 launches) from the newest committed ncu launch list, or None."""
+def step_traffic(n_launches=None):
+    """DRAM bytes of one step (sum over its launches) from the newest committed ncu launch list whose launch count is the
+    step's, or None."""
     import glob
-    try:
-        with open(sorted(glob.glob(os.path.join(ROOT, "profiles", "step_traffic_r*.json")))[-1]) as f:
-            return json.load(f)["dram_bytes_per_step"]
-    except (OSError, KeyError, ValueError, IndexError):
-        return None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "step_traffic_r*.json")), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if n_launches is None or d.get("launches", sum(d.get("kernels", {}).values())) == n_launches:
+                return d["dram_bytes_per_step"]
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
-def layer_list():
+def layer_list(fused=False):
+    """The step's Linear calls.  fused=True: the same Linears with the same-input ones (attn1 q/k/v per block, attn2 k/v of all
+    blocks, the 22 time_emb_proj) as one launch each on the N-concatenated packed weight (fused_utils.fuse_linears; the
+    reference's utils/fused_utils.py:87-96): entries carry a 6th field, the members' N."""
     shapes = importlib.import_module("quantization---diffusion-models_b200.shapes")
-    return shapes, shapes.sd15_unet_linears(batch=8, cfg=True)
+    return shapes, (shapes.sd15_unet_linears_fused(batch=8, cfg=True) if fused else shapes.sd15_unet_linears(batch=8, cfg=True))
 
 
 def per_shape_roofline_ms(shapes, layers, peaks):
     """sum over the step's launches of max(flops / tensor peak, algorithmic bytes / HBM peak), in ms"""
     tot = 0.0
-    for _, m, n, k, c in layers:
+    for _, m, n, k, c in (e[:5] for e in layers):
         by = shapes.gemm_bytes_w4a16(m, n, k, shapes.group_for(k))
         tot += c * max(2.0 * m * n * k / (peaks["bf16_burst"] * 1e12), by / (peaks["hbm"] * 1e9))
     return tot * 1e3
@@ -104,7 +112,7 @@ def workload_config(shapes, layers, world):
     sample of this workload; what the sample was is said in its `cpu_baseline.sample`)."""
     return {"workload": "sd15_unet_w4a16_linears_b8cfg",
             "reference_config": "SD1.5 UNet W4A16 AWQ group-128, 512x512 latents batch 8 (CFG -> B_eff 16)",
-            "linear_calls_per_step": sum(c for *_, c in layers), "distinct_shapes": len(layers),
+            "linear_calls_per_step": sum(e[4] for e in layers), "distinct_shapes": len(layers),
             "tflop_per_step": shapes.total_flops(layers) / 1e12, "group_size": "128 (64 where K=320)",
             "l2": "per-step working set (>1.5 GB of activations + 184 distinct weights) exceeds the 126 MB L2",
             "parallelism": f"dp{world} (prompt-batched, no collective in the step)"}
@@ -163,23 +171,31 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def build_layers(q, shapes, layers, dev, dtype):
-    """random-init weights of every distinct Linear, AWQ-quantised on the GPU by the fused RTN+pack kernel;
-    one activation buffer per distinct (M, K), one output buffer per distinct (M, N)."""
+    """random-init weights of every Linear of the step (distinct per layer instance, like the real UNet), AWQ-quantised on
+    the GPU by the fused RTN+pack kernel; one activation buffer per distinct (M, K); outputs come from the op itself
+    (allocated by the API like the reference's F.linear).  `layers` may be the fused inventory (6-field entries): then every
+    member Linear is built as its own WQLinear_GEMM and the launch is fused_utils.fuse_linears of the members.
+    Returns (xs, launches, members): `launches` = the step as launched, `members` = the same Linears one by one."""
     import torch
     lin = importlib.import_module("quantization---diffusion-models_b200.linear")
+    fu = importlib.import_module("quantization---diffusion-models_b200.fused_utils")
     g = torch.Generator(device=dev).manual_seed(42)
-    xs, ys, mods = {}, {}, []
-    for name, m, n, k, cnt in layers:
+    xs, launches, members = {}, [], []
+    for e in layers:
+        name, m, n, k, cnt = e[:5]
+        parts = e[5] if len(e) > 5 else (n,)
         if (m, k) not in xs:
             xs[(m, k)] = torch.randn(m, k, generator=g, device=dev, dtype=dtype)
-        if (m, n) not in ys:
-            ys[(m, n)] = None  # outputs come from the op itself (allocated by the API like the reference's F.linear)
-        for _ in range(cnt):  # distinct weights per layer instance, like the real UNet
-            fl = torch.nn.Linear(k, n, bias=True, device=dev, dtype=dtype)
-            fl.weight.data = torch.randn(n, k, generator=g, device=dev, dtype=dtype) * 0.02
-            mods.append((name, lin.WQLinear_GEMM.from_linear(fl, 4, shapes.group_for(k)), (m, k)))
-            del fl
-    return xs, mods
+        for inst in range(cnt):
+            mem = []
+            for pn in parts:
+                fl = torch.nn.Linear(k, pn, bias=True, device=dev, dtype=dtype)
+                fl.weight.data = torch.randn(pn, k, generator=g, device=dev, dtype=dtype) * 0.02
+                mem.append(lin.WQLinear_GEMM.from_linear(fl, 4, shapes.group_for(k)))
+                del fl
+            members += [(name, mm, (m, k), inst) for mm in mem]
+            launches.append((name, mem[0] if len(mem) == 1 else fu.fuse_linears(mem), (m, k), inst))
+    return xs, launches, members
 
 
 
@@ -277,23 +293,34 @@ def sub_denoise(args, dev, rank, world, sync_max):
     model.generate(prompts, lat=lat, num_inference_steps=2)
     sync_max(0.0)
 
-    def timed_loop(graph):
-        model.generate(prompts, lat=lat, num_inference_steps=2, cuda_graph=graph)   # warm-up (captures the step when graph)
+    def timed_loop(graph, fuse=False):
+        model.generate(prompts, lat=lat, num_inference_steps=2, cuda_graph=graph, fuse_layers=fuse)   # warm-up (captures the step when graph)
         sync_max(0.0)
         q.ops.launch_count(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = model.generate(prompts, lat=lat, num_inference_steps=steps, cuda_graph=graph)
+        r = model.generate(prompts, lat=lat, num_inference_steps=steps, cuda_graph=graph, fuse_layers=fuse)
         e1.record()
         torch.cuda.synchronize()
         return sync_max(e0.elapsed_time(e1) * 1e-3), r, q.ops.launch_count()
 
+    def rel(a, b):
+        return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6))
+
     sec_eager, res_eager, launches = timed_loop(False)
-    sec, res, _ = timed_loop(True)
+    sec_graph, res_graph, _ = timed_loop(True)
+    fused_members = model.fuse_layers()
+    sec_feager, res_feager, launches_fused = timed_loop(False, True)
+    sec, res, _ = timed_loop(True, True)
     out = {"it_per_s": steps / sec, "images_it_per_s": world * batch * steps / sec, "steps": steps, "batch_per_gpu": batch, "quant": "w4a16 g128",
            "seconds": sec, "finite": bool(torch.isfinite(res).all()), "it_per_s_eager": steps / sec_eager,
-           "graph_equals_eager": bool(torch.equal(res, res_eager)), "libqdm_launches_per_step": launches // steps,
-           "how": "generate(..., cuda_graph=True): every denoiser call replayed from one CUDA graph (skeletons.SkeletonPipeline._graph_step); it_per_s_eager = the same loop launched eagerly",
+           "it_per_s_graph_unfused": steps / sec_graph, "it_per_s_eager_fused": steps / sec_feager,
+           "graph_vs_eager_max_rel": rel(res_graph, res_eager), "fused_vs_unfused_max_rel": rel(res, res_graph),
+           "libqdm_launches_per_step": launches_fused // steps, "libqdm_launches_per_step_unfused": launches // steps,
+           "fused_members": fused_members,
+           "how": "generate(..., cuda_graph=True, fuse_layers=True): every denoiser call replayed from one CUDA graph (skeletons.SkeletonPipeline."
+                  "_graph_step), same-input packed projections as one launch each + qdm_geglu (fused_utils.fuse_projections); it_per_s_eager = "
+                  "the unfused loop launched eagerly; *_max_rel = max |a - b| / max |b| of the final latents after the 50 steps",
            "model": "SD1.5 UNet skeleton (random init), packed Linears + 1x1 / 3x3 convolutions", "scaling": "weak (data parallel, no collective in the loop)"}
     del model
     torch.cuda.empty_cache()
@@ -401,18 +428,25 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     q = importlib.import_module("quantization---diffusion-models_b200")
     q._lib.check(q._lib.load().qdm_device_check(local))
-    shapes, layers = layer_list()
+    fused = not args.no_fuse
+    shapes, layers_unfused = layer_list()
+    layers = layer_list(fused=True)[1] if fused else layers_unfused
     dtype = torch.float16
-    flops_step = shapes.total_flops(layers)
-    xs, mods = build_layers(q, shapes, layers, dev, dtype)
+    flops_step = shapes.total_flops(layers_unfused)
+    assert abs(shapes.total_flops(layers) - flops_step) < 1e-6 * flops_step   # fusing changes the launches, not the work
+    xs, mods, members = build_layers(q, shapes, layers, dev, dtype)
     n_calls = len(mods)
     torch.cuda.synchronize()
 
-    def step():
-        y = None
-        for _, mod, key in mods:
-            y = mod(xs[key])
-        return y
+    def step_of(lst):
+        def step():
+            y = None
+            for _, mod, key, _ in lst:
+                y = mod(xs[key])
+            return y
+        return step
+
+    step = step_of(mods)
 
     def barrier():
         if world > 1:
@@ -436,57 +470,66 @@ def run_ours(args):
             ms = t.item()
         return ms
 
-    # ---- device-resident throughput.  The 184 launches of a step are captured once in a CUDA graph (the tensor
-    # maps are by-value kernel parameters, so the capture is exact) and replayed: per-launch host work (Python,
-    # ctypes, cuTensorMapEncodeTiled) would otherwise bound the short small-M launches.
+    # ---- device-resident throughput.  The launches of a step are captured once in a CUDA graph (the tensor maps are
+    # by-value kernel parameters, so the capture is exact) and replayed: per-launch host work (Python, ctypes,
+    # cuTensorMapEncodeTiled) would otherwise bound the short small-M launches.
     step()   # first call of every module builds its kernel-native weight copy (WQLinear_GEMM._repacked): not part of a step
     torch.cuda.synchronize()
     run_step = step
     graph = None
     if not args.no_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step()
+        graph = _graph_of(torch, step)
         run_step = graph.replay
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     q.ops.launch_count(reset=True)
     ms = timed(run_step, args.steps, args.warmup)
-    launches = n_calls * args.steps   # one libqdm kernel per Linear call (checked against the library's counter below)
+    launches = n_calls * args.steps   # one libqdm kernel per launch of the step (checked against the library's counter below)
     if graph is None:
         assert q.ops.launch_count() == n_calls * (args.steps + args.warmup), q.ops.launch_count()
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms / args.steps
     value = world * flops_step / (ms_step * 1e-3) / 1e12
 
-    # ---- end to end: step inputs from pinned host memory, final output back to the host.  The staging buffers are
-    # allocated (and first touched) while this process is bound to the CPUs of the GPU's own NUMA node, so that 8 ranks
-    # do not pull their 382 MB per step across the socket interconnect.
+    # ---- the same Linears launched one by one (184 launches: the round-1 / round-2 form of this line), for continuity
+    unfused = None
+    if fused and not args.no_graph:
+        step_members = step_of(members)
+        step_members()
+        torch.cuda.synchronize()
+        g_members = _graph_of(torch, step_members)
+        ms_members = timed(g_members.replay, args.steps, args.warmup) / args.steps
+        unfused = {"ms_per_step": ms_members, "tflops": world * flops_step / (ms_members * 1e-3) / 1e12, "launches_per_step": len(members),
+                   "what": "every Linear as its own launch (no same-input fusion), one CUDA graph"}
+        del g_members
+    for _, mm, _, _ in members:   # the members' kernel-native copies are not needed again
+        mm.__dict__.pop("_rp", None)
+
+    # ---- end to end: the step's EXTERNAL inputs from pinned host memory, final output back to the host.  Every Linear
+    # reads the host-supplied activation of its (M, K) except ff.net.2, which reads what it reads in the model: the GEGLU of
+    # its own block's ff.net.0.proj output, computed on the device (ops.geglu, one HBM pass, inside the timed region and not
+    # counted as FLOPs).  The staging buffers are allocated (and first touched) while this process is bound to the CPUs of
+    # the GPU's own NUMA node.
+    chain_keys = {key for name, _, key, _ in mods if name.endswith("ff.net.2")} if not args.no_chain else set()
+    ext_keys = [k for k in xs if k not in chain_keys]
     numa = NumaBinding(local)
     with numa:
-        host_x = {k: torch.empty(v.shape, dtype=dtype).pin_memory().copy_(v) for k, v in xs.items()}
-        last_key = mods[-1][2]
+        host_x = {k: torch.empty(xs[k].shape, dtype=dtype).pin_memory().copy_(xs[k]) for k in ext_keys}
         y_probe = step()
         host_y = torch.empty(y_probe.shape, dtype=dtype).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host_x.values())
     d2h = host_y.numel() * host_y.element_size()
 
-    # The step's inputs are staged on a copy stream in order of first use; the layer that first reads an input waits
-    # for that copy only, so H2D (382 MB over PCIe) overlaps the GEMMs of the inputs that have already landed.  The
-    # whole step -- 8 H2D copies, 184 WQLinear_GEMM.forward launches, the D2H read -- is one two-stream CUDA graph.
+    # The inputs are staged on a copy stream in order of first use; the layer that first reads an input waits for that copy
+    # only, so H2D overlaps the GEMMs of the inputs that have already landed.  The whole step -- the H2D copies, the
+    # WQLinear_GEMM.forward launches, the GEGLUs, the D2H read -- is one two-stream CUDA graph.
     copy_stream = torch.cuda.Stream()
     first_use = []
-    for _, _, key in mods:
-        if key not in first_use:
+    for _, _, key, _ in mods:
+        if key not in first_use and key not in chain_keys:
             first_use.append(key)
+    n_geglu = sum(1 for name, _, key, _ in mods if name.endswith("ff.net.2") and key in chain_keys)
 
     def step_e2e():
         cur = torch.cuda.current_stream()
@@ -498,12 +541,18 @@ def run_ours(args):
                 evs[k] = torch.cuda.Event()
                 evs[k].record(copy_stream)
         seen = set()
+        ff_out = {}
         y = None
-        for _, mod, key in mods:
+        for name, mod, key, inst in mods:
+            if key in chain_keys and name.endswith("ff.net.2"):
+                y = mod(q.ops.geglu(ff_out.pop((name[:-len("ff.net.2")], key[0], inst))))
+                continue
             if key not in seen:
                 cur.wait_event(evs[key])
                 seen.add(key)
             y = mod(xs[key])
+            if chain_keys and name.endswith("ff.net.0.proj"):
+                ff_out[(name[:-len("ff.net.0.proj")], key[0], inst)] = y
         host_y.copy_(y, non_blocking=True)
         cur.wait_stream(copy_stream)
 
@@ -534,17 +583,17 @@ def run_ours(args):
         return x
 
     variants = {}
-    for _, mod, key in mods:   # which kernel each Linear call of the step runs (dispatch is shape dependent)
+    for _, mod, key, _ in mods:   # which kernel each launch of the step runs (dispatch is shape dependent)
         mod(xs[key])
         v, tile = q.ops.gemm_last_variant()
         variants[v] = variants.get(v, 0) + 1
-    del graph, mods
+    del graph, mods, members
     if not args.no_graph:
         del graph_e2e
     torch.cuda.empty_cache()
     extra = {}
     if not args.no_extras:
-        for name, fn in (("w8a8", lambda: sub_w8a8(q, shapes, layers, dev, dtype, args.steps, args.warmup, timed)),
+        for name, fn in (("w8a8", lambda: sub_w8a8(q, shapes, layers_unfused, dev, dtype, args.steps, args.warmup, timed)),
                          ("denoise", lambda: sub_denoise(args, dev, rank, world, sync_max)),
                          ("calib", lambda: sub_calib(args, dev, rank, world, sync_max, blocks=args.blocks))):
             try:
@@ -560,28 +609,41 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
-    achieved = flops_step / (ms_step * 1e-3) / 1e12  # per GPU; the step is 184 launches of this one kernel
+    achieved = flops_step / (ms_step * 1e-3) / 1e12  # per GPU; every launch of the step is one kernel of the W4A16 family
+    alg_bytes = sum(e[4] * shapes.gemm_bytes_w4a16(e[1], e[2], e[3], shapes.group_for(e[3])) for e in layers)
+    how = (f"{n_calls} launches: the step's 184 Linears with the same-input ones as one launch each on the N-concatenated packed weight "
+           "(fused_utils.fuse_linears, utils/fused_utils.py:87-96: attn1 q/k/v per block, attn2 k/v of all 16 blocks, the 22 time_emb_proj)"
+           if fused else "184 launches, one per Linear")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": workload_config(shapes, layers, world),
-        "launch": "eager" if args.no_graph else "one CUDA graph of the step's 184 launches",
+        "config": workload_config(shapes, layers_unfused, world),
+        "launch": ("eager, " if args.no_graph else "one CUDA graph, ") + how,
+        "launches_per_step": n_calls,
         "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "host_numa_node": numa.node},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                "host_numa_node": numa.node, "geglu_launches_per_step": n_geglu,
+                "inputs": ("every Linear's input from pinned host memory except ff.net.2, which reads geglu(ff.net.0.proj output) of its own "
+                           "block computed on the device (qdm_geglu, inside the timed region, not counted as FLOPs)" if chain_keys else
+                           "every Linear's input from pinned host memory")},
         # the timed region is short (0.1 s at full clocks, far below the power cap), so the honest denominator is the BURST
-        # cuBLAS bf16 peak; frac_sustained and the per-shape roofline (65 of the 184 launches are HBM-bound shapes) beside it
+        # cuBLAS bf16 peak; frac_sustained and the per-shape roofline (HBM-bound shapes counted at the HBM rate) beside it
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_burst"], "traffic": step_traffic(),
+                     "frac": achieved / peaks["bf16_burst"], "traffic": step_traffic(n_calls),
                      "frac_sustained_peak": achieved / peaks["bf16_sustained"],
                      "frac_per_shape_roofline": per_shape_roofline_ms(shapes, layers, peaks) / ms_step,
+                     "algorithmic_bytes_per_step": alg_bytes,
                      "kernel": "W4A16 family, launches per step by kernel: " + json.dumps(variants),
                      "peak_kind": "bf16 cuBLAS burst, " + peaks["source"],
-                     "note": "2*M*N*K summed over the step's 184 launches / CUDA-event time of the step (one CUDA graph); traffic = DRAM read+write "
-                             "bytes of the same 184 launches from the committed ncu launch list (algorithmic bytes 9.87 GB per step); "
-                             "frac_per_shape_roofline = sum over launches of max(flops / burst peak, algorithmic bytes / measured HBM) / step time"},
+                     "note": f"2*M*N*K summed over the step's Linears / CUDA-event time of the step ({n_calls} launches, one CUDA graph); traffic = DRAM "
+                             "read+write bytes of the same launches from the committed ncu launch list (null until a list of this launch count "
+                             "is committed); frac_per_shape_roofline = sum over launches of max(flops / burst peak, algorithmic bytes / "
+                             "measured HBM) / step time"},
         "clocks": clocks,
     }
+    if unfused is not None:
+        line["unfused"] = unfused
     line.update(extra)
     if world == 1:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference(20.0).items() if k in ("value", "unit", "cores", "kind", "sample")}
@@ -602,6 +664,9 @@ def run_tables(args):
         layers = shapes_mod.sdxl_unet_linears(batch=4, cfg=True)
     elif args.model == "sd35":    # BASELINE config 4: SD3.5-L MMDiT, 1024^2, batch 1
         layers = shapes_mod.sd35_mmdit_linears(batch=1)
+    if args.fused:                # the launches of the model with fused_utils.fuse_projections applied
+        layers = [e[:5] for e in getattr(shapes_mod, {"sd15": "sd15_unet_linears_fused", "sdxl": "sdxl_unet_linears_fused",
+                                                      "sd35": "sd35_mmdit_linears_fused"}[args.model])()]
     counts = {}
     for _, m_, n_, k_, c_ in layers:
         counts[(m_, n_, k_)] = counts.get((m_, n_, k_), 0) + c_
@@ -954,6 +1019,9 @@ def main():
     ap.add_argument("--layers", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-fuse", action="store_true", help="every Linear as its own launch (no same-input fusion)")
+    ap.add_argument("--no-chain", action="store_true", help="e2e: ff.net.2 inputs from the host too (no on-device GEGLU)")
+    ap.add_argument("--fused", action="store_true", help="--layers: the fused launch inventory of the model")
     ap.add_argument("--no-extras", action="store_true", help="skip the w8a8 / denoise / calib sub-records of the line")
     ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn", "kernels", "conv"])
     ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl", "sd35"])

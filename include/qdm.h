@@ -300,6 +300,11 @@ int qdm_conv3x3_nhwc_w4a16(const void* x, const int32_t* qweight, const int32_t*
 size_t qdm_gemm_workspace_bytes(void);
 int qdm_gemm_set_workspace(void* workspace, size_t bytes, void* stream);
 
+/* GEGLU of a diffusers FeedForward between its two quantized Linears (`ff.net.0.proj` -> `ff.net.2`, the pair the reference
+ * quantizes in models/StableDiffusion1_x.py:121-137):  y[m, f] = x[m, f] * gelu_erf(x[m, F + f]),  x [M, 2F], y [M, F].
+ * fp32 math with the dtype roundings of the two torch ops (F.gelu, mul).  f16 / bf16; F % 8 == 0; 16-byte aligned. */
+int qdm_geglu(const void* x, int dtype, int64_t M, int64_t F, void* y, void* stream);
+
 /* Tile-shape override for bring-up and A/B timing: 0 = heuristic, 1 = single-CTA tiles (128 x N),
  * 2 = CTA-pair tiles (cta_group::2, 256 x N), 4 = quad clusters, 8 = stream-K, 16 / 32 = repacked-weight kernel with one /
  * two sub-tiles (+ (sub-tile width << 8) to pin the width), 64 = ignore the repacked copy.  Process-wide, test-only;

@@ -54,6 +54,7 @@ SIGNATURES = {
     "qdm_quant_pack_awq": (c_int, [_P, _I, _L, _L, _I, _P, _P, _P, _P, _P]),
     "qdm_dequant_awq": (c_int, [_P, _P, _P, _I, _L, _L, _I, _P, _P]),
     "qdm_actquant_token_i8": (c_int, [_P, _I, _L, _L, _P, _P, _P, _P]),
+    "qdm_geglu": (c_int, [_P, _I, _L, _L, _P, _P]),
     "qdm_set_gemm_mode": (c_int, [_I]),
     "qdm_gemm_f16": (c_int, [_P, _P, _P, _P, _I, _L, _L, _L, _P]),
     "qdm_gemm_f16_kn": (c_int, [_P, _P, _P, _P, _I, _L, _L, _L, _P]),

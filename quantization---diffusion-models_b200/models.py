@@ -232,6 +232,7 @@ class BaseAWQForDiffusion:
         `shard` = (rank, world) for the sharded search."""
         if hasattr(self.pipeline, "invalidate_graphs"):
             self.pipeline.invalidate_graphs()          # captured denoise steps point at the modules about to be replaced
+        self.unfuse_layers()                           # fused copies of the packed tensors about to be replaced
         quant_config = dict(quant_config)
         if quant_act and quant_config.get('version', 'fake_act').lower() != 'fake_act':
             quant_config['version'] = 'fake_act'
@@ -265,11 +266,33 @@ class BaseAWQForDiffusion:
 
     # ------------------------------------------------------------------ models/base.py:829-850
     @torch.no_grad()
+    def fuse_layers(self):
+        """Same-input packed projections as one launch each (fused_utils.fuse_projections; the reference's `fuse_layers`
+        switch of from_quantized, models/base.py:736-826, names the same transformation for its LLM blocks).
+        Returns {kind: members fused}; a no-op for models without packed Linears."""
+        from .fused_utils import fuse_projections
+        if hasattr(self.pipeline, "invalidate_graphs"):
+            self.pipeline.invalidate_graphs()
+        self._fused = fuse_projections(self.denoiser())
+        return self._fused
+
+    def unfuse_layers(self):
+        from .fused_utils import unfuse_projections
+        if self.pipeline is not None and getattr(self, "_fused", None):
+            unfuse_projections(self.denoiser())
+            if hasattr(self.pipeline, "invalidate_graphs"):
+                self.pipeline.invalidate_graphs()
+        self._fused = None
+
     def generate(self, prompt, height=512, width=512, num_inference_steps=50, guidance_scale=7.5, negative_prompt=None,
-                 num_images_per_prompt=1, generator=None, device="cpu", lat=None, output_type=None, cuda_graph=False, **kwargs):
-        """models/base.py:829-850.  `cuda_graph=True` replays each denoiser call from a CUDA graph (skeletons.SkeletonPipeline)."""
+                 num_images_per_prompt=1, generator=None, device="cpu", lat=None, output_type=None, cuda_graph=False,
+                 fuse_layers=False, **kwargs):
+        """models/base.py:829-850.  `cuda_graph=True` replays each denoiser call from a CUDA graph (skeletons.SkeletonPipeline);
+        `fuse_layers=True` runs the same-input packed projections as one launch each (fuse_layers(), built once)."""
         if self.pipeline is None:
             raise RuntimeError("The diffusion pipeline is not loaded. Please use `from_pretrained` or `from_quantized` first.")
+        if fuse_layers and not getattr(self, "_fused", None):
+            self.fuse_layers()
         return self.pipeline(prompt=prompt, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
                              num_images_per_prompt=1, generator=generator, latents=lat, output_type=output_type, cuda_graph=cuda_graph)
 

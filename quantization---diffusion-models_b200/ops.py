@@ -358,6 +358,22 @@ def dequant_awq(qweight, qzeros, scales, group):
     return out
 
 
+def geglu(x):
+    """h * F.gelu(gate) with (h, gate) = x.chunk(2, -1): the activation between ff.net.0.proj and ff.net.2 of a diffusers
+    FeedForward (the reference quantizes both Linears, models/StableDiffusion1_x.py:121-137), one HBM pass."""
+    _cuda(x, "x")
+    f2 = x.shape[-1]
+    if f2 % 16:
+        raise ValueError(f"geglu: last dimension {f2} must be a multiple of 16")
+    x2 = x.reshape(-1, f2)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y = torch.empty((*x.shape[:-1], f2 // 2), dtype=x.dtype, device=x.device)
+    with _guard(x.device):
+        check(lib().qdm_geglu(x2.data_ptr(), _dt(x), x2.shape[0], f2 // 2, y.data_ptr(), _stream(x)))
+    return y
+
+
 # ------------------------------------------------------------------ (c)(d) GEMMs
 def _gemm_io(x, n_out, out_dtype=None):
     x2 = x.reshape(-1, x.shape[-1])

@@ -28,10 +28,16 @@ class Attention(nn.Module):
         c = x if context is None else context
         b, t, d = x.shape
         h = self.heads
-        q = self.to_q(x).view(b, t, h, d // h).transpose(1, 2)
-        k = self.to_k(c).view(b, c.shape[1], h, d // h).transpose(1, 2)
-        v = self.to_v(c).view(b, c.shape[1], h, d // h).transpose(1, 2)
-        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, t, d)
+        # fused_utils.fuse_projections: self-attention q / k / v as one packed GEMM (`_qkv`); cross-attention k / v computed
+        # once per step for every block by the denoiser's grouped launch (`_pre`, consumed here)
+        pre, qkv = self.__dict__.pop("_pre", None), self.__dict__.get("_qkv")
+        if context is None and qkv is not None:
+            q, k, v = qkv(x).split(d, dim=-1)
+        else:
+            q = self.to_q(x)
+            k, v = pre if pre is not None else (self.to_k(c), self.to_v(c))
+        sp = lambda y: y.unflatten(-1, (h, d // h)).transpose(1, 2)
+        o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(b, t, d)
         return self.to_out[1](self.to_out[0](o))
 
 
@@ -41,7 +47,11 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        h, gate = self.proj(x).chunk(2, dim=-1)
+        y = self.proj(x)
+        if self.__dict__.get("_fused_act"):   # fused_utils.fuse_projections: one pass instead of gelu + mul and their temporaries
+            from .ops import geglu
+            return geglu(y)
+        h, gate = y.chunk(2, dim=-1)
         return h * F.gelu(gate)
 
 
@@ -117,7 +127,8 @@ class ResnetBlock2D(nn.Module):
 
     def forward(self, x, temb):
         h = self.conv1(F.silu(self.norm1(x)))
-        h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
+        pre = self.__dict__.pop("_pre", None)   # this block's slice of the grouped time-embedding projection (fused_utils)
+        h = h + (pre if pre is not None else self.time_emb_proj(F.silu(temb)))[:, :, None, None]
         h = self.conv2(F.silu(self.norm2(h)))
         return h + (x if self.conv_shortcut is None else self.conv_shortcut(x))
 
@@ -211,6 +222,9 @@ class UNet2DConditionSkeleton(nn.Module):
         temb = self.time_embedding(sinusoidal(t, self.channels[0], x.dtype))
         if self.add_embedding is not None and added is not None:
             temb = temb + self.add_embedding(added)
+        if "_ctx_kv" in self.__dict__ or "_temb_all" in self.__dict__:   # grouped launches of the same-input projections
+            from .fused_utils import grouped_prepass
+            grouped_prepass(self, context=context, temb=temb)
         h = self.conv_in(x)
         skips = [h]
         for blk in self.down_blocks:
@@ -253,7 +267,8 @@ class AdaLayerNormZero(nn.Module):
         self.n = n
 
     def forward(self, x, emb):
-        parts = self.linear(F.silu(emb)).chunk(self.n, dim=1)
+        pre = self.__dict__.pop("_pre", None)   # this module's slice of the grouped modulation launch (fused_utils)
+        parts = (pre if pre is not None else self.linear(F.silu(emb))).chunk(self.n, dim=1)
         shift, scale = parts[0], parts[1]
         return self.norm(x) * (1 + scale[:, None]) + shift[:, None], parts[2:]
 
@@ -269,7 +284,8 @@ class AdaLayerNormContinuous(nn.Module):
         self.norm = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
 
     def forward(self, x, emb):
-        scale, shift = self.linear(F.silu(emb)).chunk(2, dim=1)
+        pre = self.__dict__.pop("_pre", None)
+        scale, shift = (pre if pre is not None else self.linear(F.silu(emb))).chunk(2, dim=1)
         return self.norm(x) * (1 + scale[:, None]) + shift[:, None], ()
 
 
@@ -285,10 +301,14 @@ class JointAttention(nn.Module):
     def forward(self, x, c):
         b, t, d = x.shape
         h = self.heads
-        sp = lambda y: y.view(b, -1, h, d // h).transpose(1, 2)
-        q = torch.cat([sp(self.to_q(x)), sp(self.add_q_proj(c))], dim=2)
-        k = torch.cat([sp(self.to_k(x)), sp(self.add_k_proj(c))], dim=2)
-        v = torch.cat([sp(self.to_v(x)), sp(self.add_v_proj(c))], dim=2)
+        sp = lambda y: y.unflatten(-1, (h, d // h)).transpose(1, 2)
+        qkv, add_qkv = self.__dict__.get("_qkv"), self.__dict__.get("_add_qkv")   # fused_utils.fuse_projections
+        xq, xk, xv = qkv(x).split(d, dim=-1) if qkv is not None else (self.to_q(x), self.to_k(x), self.to_v(x))
+        cq, ck, cv = (add_qkv(c).split(d, dim=-1) if add_qkv is not None
+                      else (self.add_q_proj(c), self.add_k_proj(c), self.add_v_proj(c)))
+        q = torch.cat([sp(xq), sp(cq)], dim=2)
+        k = torch.cat([sp(xk), sp(ck)], dim=2)
+        v = torch.cat([sp(xv), sp(cv)], dim=2)
         o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, -1, d)
         xo, co = o[:, :t], o[:, t:]
         return self.to_out[0](xo), (self.to_add_out(co) if self.to_add_out is not None else None)
@@ -357,6 +377,9 @@ class MMDiTSkeleton(nn.Module):
     def forward(self, x, t, context, pooled):
         b, c, hh, ww = x.shape
         emb = self.time_text_embed(t, pooled)
+        if "_adaln_all" in self.__dict__:   # every block's AdaLN modulation in one launch
+            from .fused_utils import grouped_prepass
+            grouped_prepass(self, emb=emb)
         h = self.pos_embed(x)
         ctx = self.context_embedder(context)
         for blk in self.transformer_blocks:

@@ -163,6 +163,11 @@ def gemm_w8a8(xq, sx, wq, sw, bias=None, out_dtype=torch.float16):
     return y.to(out_dtype)
 
 
+def geglu(x):
+    h, gate = x.chunk(2, dim=-1)
+    return h * torch.nn.functional.gelu(gate)
+
+
 def conv3x3_weight_taps(w):
     n, c, kh, kw = w.shape
     return w.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
@@ -182,7 +187,8 @@ def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
 
 NAMES = ("colabsmax", "colabssum", "colstats", "rowabsmax", "absmax", "awq_wsum", "sqdiff_sum", "quant_group",
          "quant_rowwise", "quant_tensor", "actquant_token_i8", "quant_pack_awq", "dequant_awq", "pack_awq", "unpack_awq",
-         "awq_clip_search", "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "w4a16_repack_ts", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16")
+         "awq_clip_search", "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "w4a16_repack_ts", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16",
+         "geglu")
 
 
 @contextlib.contextmanager

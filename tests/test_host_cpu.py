@@ -403,3 +403,58 @@ def test_fake_act_checkpoint_keeps_activation_quantisers(tmp_path):
         lins2 = [m for m in again.denoiser().modules() if type(m).__name__ == "WxAxLinear"]
         assert lins2 and all(l.n_bits_A == 8 for l in lins2)
         assert torch.equal(again.generate(["p"], lat=lat, num_inference_steps=1), out)
+
+
+def test_fused_inventories_keep_the_work():
+    """shapes.*_fused: same FLOPs and the same member Linears as the per-Linear inventories; SD1.5 184 calls -> 100 launches."""
+    S = importlib.import_module(PKG + ".shapes")
+    for plain, fused in ((S.sd15_unet_linears, S.sd15_unet_linears_fused), (S.sdxl_unet_linears, S.sdxl_unet_linears_fused),
+                         (S.sd35_mmdit_linears, S.sd35_mmdit_linears_fused)):
+        a, b = plain(), fused()
+        assert S.total_flops(a) == S.total_flops(b)
+        assert sum(c for *_, c in a) == sum(e[4] * len(e[5]) for e in b)
+        assert all(sum(e[5]) == e[2] for e in b)
+        members = sorted((e[1], n, e[3]) for e in b for _ in range(e[4]) for n in e[5])
+        assert members == sorted((m, n, k) for _, m, n, k, c in a for _ in range(c))
+    sd15 = S.sd15_unet_linears_fused()
+    assert sum(e[4] for e in sd15) == 100
+    by_name = {e[0]: e for e in sd15}
+    assert by_name["attn2.to_kv(all blocks)"][1:4] == (1232, 24960, 768) and len(by_name["attn2.to_kv(all blocks)"][5]) == 32
+    assert by_name["time_emb_proj(all resnets)"][1:4] == (16, 17600, 1280)
+    assert by_name["C320.attn1.to_qkv"][1:5] == (65536, 960, 320, 5)
+
+
+@pytest.mark.parametrize("kind", ["sd15", "sdxl", "sd35"])
+def test_fuse_layers_host_logic(kind):
+    """fuse_layers() on a packed skeleton (oracle-backed ops): the fused tensors are the members' concatenated along N
+    (utils/fused_utils.py:87-96), the state dict is unchanged, the denoised latents equal the unfused model's, and
+    unfuse_layers() / a new quantize() drop the fused copies."""
+    fu = importlib.import_module(PKG + ".fused_utils")
+    with patched_ops():
+        M, model = tiny_model(kind)
+        lat = torch.randn(2, model.pipeline.latent_channels, model.pipeline.latent_size, model.pipeline.latent_size,
+                          generator=torch.Generator().manual_seed(6)).half()
+        model.quantize(quant_config={"zero_point": True, "q_group_size": 64, "w_bit": 4, "version": "gemm"}, quantType="awq")
+        ref = model.generate(["a", "b"], lat=lat, num_inference_steps=2)
+        keys = set(model.denoiser().state_dict().keys())
+        done = model.fuse_layers()
+        assert done["self_qkv"] > 0 and (done["adaln"] > 0 if kind == "sd35" else done["context_kv"] > 0 and done["time_emb_proj"] > 0)
+        assert set(model.denoiser().state_dict().keys()) == keys
+        den = model.denoiser()
+        n_checked = 0
+        for m in den.modules():
+            qkv = m.__dict__.get("_qkv")
+            if qkv is not None:
+                for name in ("qweight", "qzeros", "scales"):
+                    assert torch.equal(getattr(qkv, name), torch.cat([getattr(l, name) for l in (m.to_q, m.to_k, m.to_v)], dim=1))
+                assert qkv.out_features == 3 * m.to_q.out_features
+                n_checked += 1
+        assert n_checked * 3 <= done["self_qkv"] and n_checked > 0
+        out = model.generate(["a", "b"], lat=lat, num_inference_steps=2, fuse_layers=True)
+        assert ((out.float() - ref.float()).abs().max() / ref.float().abs().max()).item() <= 2e-3
+        assert not any("_pre" in m.__dict__ for m in den.modules())          # every grouped slice was consumed by its member
+        model.unfuse_layers()
+        assert not any(k in m.__dict__ for m in den.modules() for k in ("_qkv", "_add_qkv", "_ctx_kv", "_temb_all", "_adaln_all", "_fused_act"))
+        assert torch.equal(model.generate(["a", "b"], lat=lat, num_inference_steps=2), ref)
+    with pytest.raises(TypeError):
+        fu.fuse_linears([torch.nn.Linear(8, 8)])

@@ -33,6 +33,17 @@ def main():
                     seen.append((m_, n_, k_))
         cases = seen
         tiles = [0] if os.environ.get("TS_PROBE_AUTO") else [0, 384, 320, 256, 192, 160, 128, 96, 64]
+    elif what == "fused":   # the launch shapes fused_utils.fuse_projections adds (M > 32)
+        base, seen = set(), []
+        for layers in (S.sd15_unet_linears(), S.sdxl_unet_linears(), S.sd35_mmdit_linears()):
+            base |= {(m_, n_, k_) for _, m_, n_, k_, _ in layers}
+        for layers in (S.sd15_unet_linears_fused(), S.sdxl_unet_linears_fused(), S.sd35_mmdit_linears_fused()):
+            for e in layers:
+                c = (e[1], e[2], e[3])
+                if e[1] > 32 and c not in base and c not in seen:
+                    seen.append(c)
+        cases = seen
+        tiles = [0] if os.environ.get("TS_PROBE_AUTO") else [0, 384, 320, 256, 192, 160, 128]
     else:
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (16384, 640, 640), (4096, 1280, 5120), (8192, 1280, 1280),
                  (4096, 2432, 2432), (4096, 9728, 2432), (1232, 1280, 768), (333, 2432, 2432), (65536, 2560, 320), (65536, 320, 320)]
