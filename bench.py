@@ -236,29 +236,40 @@ def int8_dense_peak(torch, dev):
 
 
 def sub_w8a8(q, shapes, layers, dev, dtype, steps, warmup, timed):
-    """Kernel (d) on the same workload: every Linear call of the step through W8A8Linear.forward = per-token int8
-    quantiser (qdm_actquant_token_i8) + int8 tcgen05 GEMM with the dequant scales in the epilogue; one CUDA graph.
-    Also the GEMMs alone on pre-quantised activations, and the measured INT8 dense peak as the roofline denominator."""
+    """Kernel (d) on the same workload: every Linear of the step through W8A8Linear.forward = per-token int8 quantiser
+    (qdm_actquant_token_i8) + int8 tcgen05 GEMM with the dequant scales in the epilogue; one CUDA graph.  `layers` is the fused
+    inventory: same-input Linears are one W8A8Linear (fused_utils.fuse_linears), so a shared input is quantised once.
+    Also the GEMMs alone on pre-quantised activations, the per-Linear (unfused) step, and the measured INT8 dense peak."""
     import torch
     lin = importlib.import_module("quantization---diffusion-models_b200.linear")
+    fu = importlib.import_module("quantization---diffusion-models_b200.fused_utils")
     g = torch.Generator(device=dev).manual_seed(43)
-    xs, mods = {}, []
-    for name, m, n, k, cnt in layers:
+    xs, mods, members = {}, [], []
+    for e in layers:
+        name, m, n, k, cnt = e[:5]
+        parts = e[5] if len(e) > 5 else (n,)
         if k % 16:
             continue
         if (m, k) not in xs:
             xs[(m, k)] = torch.randn(m, k, generator=g, device=dev, dtype=dtype)
         for _ in range(cnt):
-            fl = torch.nn.Linear(k, n, bias=True, device=dev, dtype=dtype)
-            fl.weight.data = torch.randn(n, k, generator=g, device=dev, dtype=dtype) * 0.02
-            mods.append((lin.W8A8Linear.from_float(fl), (m, k)))
-            del fl
+            mem = []
+            for pn in parts:
+                fl = torch.nn.Linear(k, pn, bias=True, device=dev, dtype=dtype)
+                fl.weight.data = torch.randn(pn, k, generator=g, device=dev, dtype=dtype) * 0.02
+                mem.append(lin.W8A8Linear.from_float(fl))
+                del fl
+            members += [(mm, (m, k)) for mm in mem]
+            mods.append((mem[0] if len(mem) == 1 else fu.fuse_linears(mem), (m, k)))
     flops = sum(2.0 * key[0] * mod.out_features * key[1] for mod, key in mods)
 
-    def step():
-        for mod, key in mods:
-            mod(xs[key])
+    def step_of(lst):
+        def step():
+            for mod, key in lst:
+                mod(xs[key])
+        return step
 
+    step = step_of(mods)
     pre = {key: q.ops.actquant_token_i8(x) for key, x in xs.items()}
 
     def step_gemm_only():
@@ -271,12 +282,15 @@ def sub_w8a8(q, shapes, layers, dev, dtype, steps, warmup, timed):
     launches = q.ops.launch_count()
     ms = timed(_graph_of(torch, step).replay, steps, warmup) / steps
     ms_g = timed(_graph_of(torch, step_gemm_only).replay, steps, warmup) / steps
+    ms_u = timed(_graph_of(torch, step_of(members)).replay, steps, warmup) / steps if len(members) != len(mods) else ms
     peak = int8_dense_peak(torch, dev)
     tf, tf_g = flops / ms / 1e9, flops / ms_g / 1e9
     return {"tflops": tf, "ms_per_step": ms, "gemm_only_tflops": tf_g, "gemm_only_ms_per_step": ms_g, "launches_per_step": launches,
+            "unfused_ms_per_step": ms_u, "unfused_tflops": flops / ms_u / 1e9, "linears_per_step": len(members),
             "tflop_per_step": flops / 1e12, "int8_dense_peak_tops": peak, "peak_how": "torch._int_mm (cuBLASLt int8) 8192^3, best of 10, this run",
             "frac_of_int8_peak": (tf_g / peak) if peak else None,
-            "what": "W8A8Linear.forward over the step's Linear calls: qdm_actquant_token_i8 + qdm_gemm_w8a8 (quantize/fake_quant.py:86-118)"}
+            "what": "W8A8Linear.forward over the step's Linears (same-input ones fused: one activation quantisation + one GEMM): "
+                    "qdm_actquant_token_i8 + qdm_gemm_w8a8 (quantize/fake_quant.py:86-118); unfused_* = every Linear on its own"}
 
 
 def sub_denoise(args, dev, rank, world, sync_max):
@@ -524,12 +538,21 @@ def run_ours(args):
     # The inputs are staged on a copy stream in order of first use; the layer that first reads an input waits for that copy
     # only, so H2D overlaps the GEMMs of the inputs that have already landed.  The whole step -- the H2D copies, the
     # WQLinear_GEMM.forward launches, the GEGLUs, the D2H read -- is one two-stream CUDA graph.
+    # Launch order of the e2e step: the Linears whose inputs are smallest first (the order of a step's Linears is free in this
+    # workload; a chained ff.net.2 stays behind its ff.net.0.proj), so the GEMMs start after the first kilobytes have landed
+    # instead of after the largest activation.
+    def ext_key(name, key):
+        return (key[0], key[1] // 4) if (key in chain_keys and name.endswith("ff.net.2")) else key
+    in_bytes = lambda k: k[0] * k[1] * 2
+    mods_e2e = sorted(mods, key=lambda e: in_bytes(ext_key(e[0], e[2])))   # stable: ties keep the step's order
     copy_stream = torch.cuda.Stream()
     first_use = []
-    for _, _, key, _ in mods:
+    for _, _, key, _ in mods_e2e:
         if key not in first_use and key not in chain_keys:
             first_use.append(key)
     n_geglu = sum(1 for name, _, key, _ in mods if name.endswith("ff.net.2") and key in chain_keys)
+
+    last_mod = mods[-1][1]   # the step's result read back to the host: the output of the step's last Linear, as in `step`
 
     def step_e2e():
         cur = torch.cuda.current_stream()
@@ -542,18 +565,20 @@ def run_ours(args):
                 evs[k].record(copy_stream)
         seen = set()
         ff_out = {}
-        y = None
-        for name, mod, key, inst in mods:
+        y_out = None
+        for name, mod, key, inst in mods_e2e:
             if key in chain_keys and name.endswith("ff.net.2"):
                 y = mod(q.ops.geglu(ff_out.pop((name[:-len("ff.net.2")], key[0], inst))))
-                continue
-            if key not in seen:
-                cur.wait_event(evs[key])
-                seen.add(key)
-            y = mod(xs[key])
-            if chain_keys and name.endswith("ff.net.0.proj"):
-                ff_out[(name[:-len("ff.net.0.proj")], key[0], inst)] = y
-        host_y.copy_(y, non_blocking=True)
+            else:
+                if key not in seen:
+                    cur.wait_event(evs[key])
+                    seen.add(key)
+                y = mod(xs[key])
+                if chain_keys and name.endswith("ff.net.0.proj"):
+                    ff_out[(name[:-len("ff.net.0.proj")], key[0], inst)] = y
+            if mod is last_mod:
+                y_out = y
+        host_y.copy_(y_out, non_blocking=True)
         cur.wait_stream(copy_stream)
 
     run_e2e = step_e2e
@@ -593,7 +618,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
     extra = {}
     if not args.no_extras:
-        for name, fn in (("w8a8", lambda: sub_w8a8(q, shapes, layers_unfused, dev, dtype, args.steps, args.warmup, timed)),
+        for name, fn in (("w8a8", lambda: sub_w8a8(q, shapes, layers, dev, dtype, args.steps, args.warmup, timed)),
                          ("denoise", lambda: sub_denoise(args, dev, rank, world, sync_max)),
                          ("calib", lambda: sub_calib(args, dev, rank, world, sync_max, blocks=args.blocks))):
             try:
@@ -936,6 +961,8 @@ def run_kernels(args):
         ("b quant_rowwise 8-bit (fake_quant.py:86)", lambda: q.ops.quant_rowwise(x, 8), 4 * nx),
         ("b actquant_token_i8 (fake_quant.py:109)", lambda: q.ops.actquant_token_i8(x), 3 * nx + 4 * rows),
         ("b dequant_awq (packing_utils.py:87)", None, 0),
+        ("act geglu [65536, 2560] -> [65536, 1280] (ff.net.0.proj -> ff.net.2)", lambda: q.ops.geglu(x), 3 * nx),
+        ("ref torch h * F.gelu(gate) on the same tensor", lambda: x[:, :cols // 2] * torch.nn.functional.gelu(x[:, cols // 2:]), 3 * nx),
         ("ref torch copy_ (same bytes model: 2 B in + 2 B out)", lambda: dq_out.copy_(w), 4 * nw),
     ]
     qw, qz, sc, _ = q.ops.quant_pack_awq(w, 128)

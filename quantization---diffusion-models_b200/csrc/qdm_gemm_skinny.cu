@@ -4,7 +4,12 @@
 // built around the weight stream:
 //   * a warp-step is a [16 k rows x 64 columns] block of packed words: lane (nl = lane / 4, t = lane % 4) loads the word
 //     of column group nl (8 adjacent words = one 32-byte sector per row) from rows kk + 4 t + {0, 1, 2, 3} -- every
-//     sector it touches is fully used; two register buffers keep 16-32 loads in flight per lane;
+//     sector it touches is fully used.  RING build (N % 32 == 0, the 16-byte alignment of every row piece): each warp streams
+//     its packed words through a private shared-memory ring filled by 16-byte cp.async (4 chunks of 64 k rows x 32 B:
+//     6-8 KB per warp, ~100 KB per SM in flight -- the 4-byte register loads of the first version kept 32-64 KB per SM in
+//     flight and reached 1.0-1.8 TB/s); rows are stored permuted so that the lanes' word reads are conflict-free.  The
+//     zero points / scales of the NEXT quantisation group are prefetched into registers when a group is entered.
+//     Fallback (N % 32 != 0): two register buffers keep 16-32 4-byte loads in flight per lane;
 //   * the weights are the A operand of mma.sync.m16n8k16 (W^T [16 columns x 16 k] times x^T [16 k x 8 rows]): which
 //     physical row / column plays which logical (n, k) of the fragment is free as long as A, B and the output agree, so
 //     the lane's four words ARE four A fragments (column pairs (2j, 2j+1) of its word, j = 0..3) without any shuffle:
@@ -54,7 +59,18 @@ __device__ __forceinline__ uint32_t sub_mul2(uint32_t v, uint32_t zm, uint32_t s
   }
 }
 
-template <bool BF16, int MT>
+constexpr int SK_RING = 4;                        // cp.async ring depth (chunks of SK_U warp-steps) per warp
+constexpr int SK_CHUNK_BYTES = SK_U * 16 * 32;    // 64 k rows x 32 B
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool on) {
+  const int n = on ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool BF16, int MT, bool RING>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__ qweight, const uint32_t* __restrict__ qzeros,
                     const uint16_t* __restrict__ scales, const uint16_t* __restrict__ bias, uint16_t* __restrict__ y,
@@ -65,8 +81,14 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   uint16_t* xs = reinterpret_cast<uint16_t*>(sk_smem_raw);
   const int k_slice = steps_per_cta * 16;
   const int pitch = k_slice + 16;
-  float* red = reinterpret_cast<float*>(xs + 8 * MT * pitch);
-  float* part = red + SK_WARPS * 4 * MT * 4 * 32;   // [WN column groups][4 j][MT][4][32]
+  // per-warp area: the cp.async ring [SK_RING][64 rows x 32 B] during the main loop (RING), the warp's partial sums
+  // [4 j][MT][4][32] after it (the same bytes: a warp writes its sums only when it is done with its ring)
+  constexpr int WARP_AREA = RING ? SK_RING * SK_CHUNK_BYTES : 4 * MT * 4 * 32 * 4;
+  static_assert(WARP_AREA >= 4 * MT * 4 * 32 * 4, "the partial sums fit the ring");
+  uint8_t* area0 = reinterpret_cast<uint8_t*>(xs + 8 * MT * pitch);
+  auto red_w = [&](int w) { return reinterpret_cast<float*>(area0 + w * WARP_AREA); };
+  float* part = reinterpret_cast<float*>(area0 + SK_WARPS * WARP_AREA);   // [WN column groups][4 j][MT][4][32]
+  const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(area0)) + (threadIdx.x >> 5) * WARP_AREA;
 
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = int(cluster.block_rank()), csize = int(cluster.num_blocks());
@@ -103,8 +125,32 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   const int g_pre = (w_lo << 4) / group;
   uint32_t zw_pre = 0u;
   uint4 sv_pre = make_uint4(0, 0, 0, 0);
+  // RING: lane L copies the 16-byte pieces L, L + 32, L + 64, L + 96 of a chunk; piece p = (k row p / 2, half p % 2) of the
+  // warp's 32-byte column window; row r of a chunk is stored at row (r & ~15) | ((r & 3) << 2) | ((r >> 2) & 3), so that
+  // the word reads of lanes (nl, t) -- rows 4 t + i -- fall into 32 different banks
+  const int wc0 = (int(blockIdx.x) * WN + wn) * 8;
+  auto ring_issue = [&](int chunk) {   // chunk index counted from w_lo in units of SK_U steps
+    const int s0 = w_lo + chunk * SK_U;
+    const uint32_t dst0 = ring0 + uint32_t(chunk % SK_RING) * SK_CHUNK_BYTES;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int pce = lane + 32 * q4, r = pce >> 1, h = pce & 1;
+      const int rp = (r & ~15) | ((r & 3) << 2) | ((r >> 2) & 3);
+      const bool on = (s0 + (r >> 4)) < w_hi && (wc0 + 4 * h) < words_per_row;
+      const uint32_t* src = qweight + int64_t((s0 << 4) + r) * words_per_row + wc0 + 4 * h;
+      cp_async16_zfill(dst0 + uint32_t(rp * 32 + h * 16), on ? src : qweight, on);
+    }
+  };
+  const int n_chunks = (w_hi - w_lo + SK_U - 1) / SK_U;
+  if (RING) {
+#pragma unroll
+    for (int c = 0; c < SK_RING - 1; ++c) {
+      if (c < n_chunks) ring_issue(c);
+      cp_async_commit();
+    }
+  }
   if (w_lo < w_hi) {
-    load_words(wa, w_lo);
+    if (!RING) load_words(wa, w_lo);
     if (col_on) {
       zw_pre = __ldg(qzeros + int64_t(g_pre) * words_per_row + wc);
       sv_pre = __ldg(reinterpret_cast<const uint4*>(scales + int64_t(g_pre) * N + 8 * wc));
@@ -146,11 +192,13 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
       const int g = kk / group;                         // group % 16 == 0: a step never straddles two groups
       if (g != g_cur) {
         g_cur = g;
-        uint32_t zw = zw_pre;
-        uint4 sv = sv_pre;
-        if (col_on && g != g_pre) {
-          zw = __ldg(qzeros + int64_t(g) * words_per_row + wc);
-          sv = __ldg(reinterpret_cast<const uint4*>(scales + int64_t(g) * N + 8 * wc));
+        // zw_pre / sv_pre hold this group's parameters (requested when the previous group was entered, or before the x
+        // staging for the first one); request the next group's now: they are needed group / 16 steps from here
+        const uint32_t zw = zw_pre;
+        const uint4 sv = sv_pre;
+        if (col_on && (g + 1) * group < (w_hi << 4)) {
+          zw_pre = __ldg(qzeros + int64_t(g + 1) * words_per_row + wc);
+          sv_pre = __ldg(reinterpret_cast<const uint4*>(scales + int64_t(g + 1) * N + 8 * wc));
         }
         const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
@@ -191,11 +239,26 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
         for (int m = 0; m < MT; ++m) mma_w_x<BF16>(acc[j][m], a[j], xb[m].x, xb[m].y);
     }
   };
-  for (int s0 = w_lo; s0 < w_hi; s0 += 2 * SK_U) {        // wa holds chunk s0
-    if (s0 + SK_U < w_hi) load_words(wb, s0 + SK_U);
-    do_chunk(wa, s0);
-    if (s0 + 2 * SK_U < w_hi) load_words(wa, s0 + 2 * SK_U);
-    if (s0 + SK_U < w_hi) do_chunk(wb, s0 + SK_U);
+  if (RING) {
+    for (int c = 0; c < n_chunks; ++c) {
+      cp_async_wait<SK_RING - 2>();   // chunk c has landed (this lane's pieces) ...
+      __syncwarp();                   // ... and every lane's; all lanes are also done reading chunk c - 1
+      if (c + SK_RING - 1 < n_chunks) ring_issue(c + SK_RING - 1);   // into the slot of chunk c - 1
+      cp_async_commit();
+#pragma unroll
+      for (int u = 0; u < SK_U; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)   // row 16 u + 4 t + i is stored at row 16 u + 4 i + t
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wa[u][i]) : "r"(ring0 + uint32_t(c % SK_RING) * SK_CHUNK_BYTES + uint32_t((16 * u + 4 * i + t) * 32 + nl * 4)));
+      do_chunk(wa, w_lo + c * SK_U);
+    }
+  } else {
+    for (int s0 = w_lo; s0 < w_hi; s0 += 2 * SK_U) {        // wa holds chunk s0
+      if (s0 + SK_U < w_hi) load_words(wb, s0 + SK_U);
+      do_chunk(wa, s0);
+      if (s0 + 2 * SK_U < w_hi) load_words(wa, s0 + 2 * SK_U);
+      if (s0 + SK_U < w_hi) do_chunk(wb, s0 + SK_U);
+    }
   }
 
   // fold the warps' K chunks (fixed order), then the cluster's K slices (fixed order)
@@ -204,13 +267,13 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) red[(((warp * 4 + j) * MT + m) * 4 + i) * 32 + lane] = acc[j][m][i];
+      for (int i = 0; i < 4; ++i) red_w(warp)[((j * MT + m) * 4 + i) * 32 + lane] = acc[j][m][i];
   __syncthreads();
   constexpr int PER_LANE = 4 * MT * 4;
   for (int it = warp; it < WN * PER_LANE; it += SK_WARPS) {   // item = (column group, element): sum its WK slices
     const int cg_ = it / PER_LANE, e = it - cg_ * PER_LANE;
-    float v = red[(cg_ * PER_LANE + e) * 32 + lane];          // warp index = k * WN + cg_
-    for (int k = 1; k < WK; ++k) v += red[((k * WN + cg_) * PER_LANE + e) * 32 + lane];
+    float v = red_w(cg_)[e * 32 + lane];                      // warp index = k * WN + cg_
+    for (int k = 1; k < WK; ++k) v += red_w(k * WN + cg_)[e * 32 + lane];
     part[it * 32 + lane] = v;
   }
   cluster.sync();   // every CTA's `part` is complete and visible cluster-wide
@@ -237,14 +300,16 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   cluster.sync();   // every CTA's shared memory stays alive until its peers have read it
 }
 
-size_t skinny_smem(int mt, int steps_per_cta, int wn) {
-  return size_t(8 * mt) * (steps_per_cta * 16 + 16) * 2 + size_t(SK_WARPS + wn) * 4 * mt * 4 * 32 * sizeof(float);
+size_t skinny_smem(int mt, int steps_per_cta, int wn, bool ring) {
+  const size_t sums = size_t(4) * mt * 4 * 32 * sizeof(float);
+  const size_t warp_area = ring ? size_t(SK_RING) * SK_CHUNK_BYTES : sums;
+  return size_t(8 * mt) * (steps_per_cta * 16 + 16) * 2 + SK_WARPS * warp_area + wn * sums;
 }
 
-template <bool BF16, int MT>
+template <bool BF16, int MT, bool RING>
 int skinny_launch(dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
                   const void* bias, void* y, int M, int N, int K, int group, int steps_per_cta, int wn, cudaStream_t st) {
-  auto kern = w4a16_skinny_kernel<BF16, MT>;
+  auto kern = w4a16_skinny_kernel<BF16, MT, RING>;
   static size_t smem_set = 0;   // per instantiation; grows monotonically
   if (smem > 48 * 1024 && smem > smem_set) {
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -269,15 +334,21 @@ int skinny_launch(dim3 grid, int ks, size_t smem, const void* x, const int32_t* 
   return QDM_OK;
 }
 
-template <bool BF16>
+template <bool BF16, bool RING>
 int skinny_mt(int mt, dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
               const void* bias, void* y, int M, int N, int K, int group, int spc, int wn, cudaStream_t st) {
   switch (mt) {
-    case 1: return skinny_launch<BF16, 1>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
-    case 2: return skinny_launch<BF16, 2>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
-    case 3: return skinny_launch<BF16, 3>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
-    default: return skinny_launch<BF16, 4>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 1: return skinny_launch<BF16, 1, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 2: return skinny_launch<BF16, 2, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 3: return skinny_launch<BF16, 3, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    default: return skinny_launch<BF16, 4, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
   }
+}
+
+// the 16-byte cp.async pieces need every k row's column window 16-byte aligned
+bool skinny_ring_ok(int64_t N) {
+  static const bool off = getenv("QDM_SKINNY_NO_RING") != nullptr;   // A/B switch, read once
+  return N % 32 == 0 && !off;
 }
 
 // Work split: WN = 4 column groups per CTA (128 contiguous bytes of every k row) when N is wide enough, K over the
@@ -293,11 +364,12 @@ void skinny_plan(int64_t M, int64_t N, int64_t K, int* ks_out, int* spc_out, int
   const int64_t resident = int64_t(mt <= 2 ? 2 : 1) * QDM_NUM_SMS;
   while (ks < 8 && col_blocks * ks * 2 <= resident && steps / (2 * ks) >= 2 * wk) ks *= 2;
   int spc = int((steps + ks - 1) / ks);
-  while (ks < 8 && skinny_smem(mt, spc, wn) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
+  const bool ring = skinny_ring_ok(N);
+  while (ks < 8 && skinny_smem(mt, spc, wn, ring) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
   *ks_out = ks;
   *spc_out = spc;
   *wn_out = wn;
-  *smem_out = skinny_smem(mt, spc, wn);
+  *smem_out = skinny_smem(mt, spc, wn, ring);
 }
 
 }  // namespace
@@ -318,6 +390,9 @@ int qdm_gemm_w4a16_skinny(const void* x, const int32_t* qweight, const int32_t* 
   skinny_plan(M, N, K, &ks, &spc, &wn, &smem);
   const int mt = int((M + 7) / 8);
   dim3 grid((unsigned)((N + 64 * wn - 1) / (64 * wn)), (unsigned)ks);
-  return is_bf16 ? skinny_mt<true>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st)
-                 : skinny_mt<false>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st);
+  if (skinny_ring_ok(N))
+    return is_bf16 ? skinny_mt<true, true>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st)
+                   : skinny_mt<false, true>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st);
+  return is_bf16 ? skinny_mt<true, false>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st)
+                 : skinny_mt<false, false>(mt, grid, ks, smem, x, qweight, qzeros, scales, bias, y, (int)M, (int)N, (int)K, group, spc, wn, st);
 }

@@ -1,4 +1,4 @@
-"""Same-input packed projections as ONE W4A16 launch.
+"""Same-input packed projections as ONE W4A16 (or W8A8) launch.
 
 The AWQ GEMM layout (utils/packing_utils.py:37-102) keeps the output channels on the last axis of all three tensors
 (qweight [K, N/8], qzeros [K/g, N/8], scales [K/g, N]) and packs 8 ADJACENT channels into a word, so the packed
@@ -21,14 +21,42 @@ the fused copy costs another 0.5 B / weight of the fused members.
 import torch
 import torch.nn.functional as F
 
-from .linear import WQLinear_GEMM
+from .linear import W8A8Linear, WQLinear_GEMM
+
+
+def _cat_bias(linears, dev, dtype):
+    if not any(l.bias is not None for l in linears):
+        return None
+    return torch.cat([l.bias if l.bias is not None else torch.zeros(l.out_features, device=dev, dtype=dtype) for l in linears])
+
+
+def _fuse_w8a8(linears):
+    """W8A8Linear members (int8 codes [N, K], one fp32 scale per output row): rows concatenate; the shared input is quantised
+    per token ONCE for all members (quantize/fake_quant.py:109-118 runs once per member in the reference)."""
+    first = linears[0]
+    for l in linears:
+        if not isinstance(l, W8A8Linear) or (l.in_features, l.out_dtype) != (first.in_features, first.out_dtype):
+            raise ValueError("fuse_linears: W8A8 members differ in in_features / dtype")
+        if (l.smooth is None) != (first.smooth is None) or (l.smooth is not None and not torch.equal(l.smooth, first.smooth)):
+            raise ValueError("fuse_linears: W8A8 members must share the SmoothQuant activation divisor")
+    dev = first.qweight.device
+    fused = W8A8Linear(first.in_features, sum(l.out_features for l in linears), False, dev, first.out_dtype)
+    fused.qweight = torch.cat([l.qweight for l in linears], dim=0).contiguous()
+    fused.w_scales = torch.cat([l.w_scales for l in linears]).contiguous()
+    fused.smooth = first.smooth
+    fused.bias = _cat_bias(linears, dev, first.out_dtype)
+    fused.split_sizes = [l.out_features for l in linears]
+    return fused
 
 
 def fuse_linears(linears, device=None, dim=1, operation=torch.cat):
     """utils/fused_utils.py:145-163 -- `linears` read the same input; returns one WQLinear_GEMM with
     out_features = sum.  Unlike the reference the members are left intact and a bias is carried (zeros for a member
-    that has none), so that the fused module is a drop-in for the members' concatenated outputs."""
+    that has none), so that the fused module is a drop-in for the members' concatenated outputs.
+    W8A8Linear members (this repo's kernel (d) module) fuse the same way along their output rows."""
     first = linears[0]
+    if isinstance(first, W8A8Linear):
+        return _fuse_w8a8(linears)
     for l in linears:
         if not isinstance(l, WQLinear_GEMM):
             raise TypeError(f"fuse_linears: {type(l).__name__} is not a WQLinear_GEMM")
@@ -64,12 +92,17 @@ def _slices(sizes):
 
 
 def _packed(*mods):
-    return all(isinstance(m, WQLinear_GEMM) for m in mods)
+    return all(isinstance(m, WQLinear_GEMM) for m in mods) or all(isinstance(m, W8A8Linear) for m in mods)
 
 
 def _same(mods):
     f = mods[0]
-    return all((m.in_features, m.group_size, m.scales.dtype) == (f.in_features, f.group_size, f.scales.dtype) for m in mods)
+    if isinstance(f, W8A8Linear):
+        return all(isinstance(m, W8A8Linear) and m.in_features == f.in_features and m.out_dtype == f.out_dtype and
+                   ((m.smooth is None and f.smooth is None) or (m.smooth is not None and f.smooth is not None and torch.equal(m.smooth, f.smooth)))
+                   for m in mods)
+    return all(isinstance(m, WQLinear_GEMM) and (m.in_features, m.group_size, m.scales.dtype) == (f.in_features, f.group_size, f.scales.dtype)
+               for m in mods)
 
 
 def fuse_projections(denoiser):

@@ -110,6 +110,32 @@ def test_fuse_linears_equals_members(qdm, M, K, parts, bias, dt):
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("M,K,parts", [(4096, 1280, (1280, 1280, 1280)), (1232, 768, (320, 640, 1280, 320)), (300, 320, (320, 320, 320))])
+def test_fuse_w8a8_equals_members(qdm, M, K, parts, dt):
+    """W8A8Linear members: rows of int8 codes and row scales concatenate; the shared input is quantised once.  Integer
+    accumulation is exact, so the fused output equals the members' bit for bit."""
+    linear = importlib.import_module(PKG + ".linear")
+    fu = importlib.import_module(PKG + ".fused_utils")
+    g = torch.Generator(device=DEV).manual_seed(9 + M + K)
+    smooth = (torch.rand(K, generator=g, device=DEV) + 0.5).to(DT[dt])
+    mems = []
+    for i, n in enumerate(parts):
+        lin = torch.nn.Linear(K, n, bias=i != 1, device=DEV, dtype=DT[dt])
+        lin.weight.data = (torch.randn(n, K, generator=g, device=DEV) * 0.05).to(DT[dt])
+        mems.append(linear.W8A8Linear.from_float(lin, smooth=smooth))
+    fused = fu.fuse_linears(mems)
+    x = torch.randn(2, M // 2, K, generator=g, device=DEV, dtype=DT[dt])
+    qdm.ops.launch_count(reset=True)
+    y = fused(x)
+    assert qdm.ops.launch_count() == 2                         # one per-token quantiser + one GEMM
+    want = torch.cat([m(x) for m in mems], dim=-1)
+    assert torch.equal(y, want)
+    mems[1].smooth = smooth * 2
+    with pytest.raises(ValueError):
+        fu.fuse_linears(mems)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
 @pytest.mark.parametrize("shape", [(4096, 2560), (3, 77, 5120), (1, 16), (1000, 10240), (65536, 2560)])
 def test_geglu_vs_torch(qdm, shape, dt):
     g = torch.Generator(device=DEV).manual_seed(sum(shape))
@@ -129,6 +155,22 @@ def test_geglu_vs_torch(qdm, shape, dt):
     assert (y[fin] == ref[fin]).float().mean().item() >= 0.98
     with pytest.raises(ValueError):
         qdm.ops.geglu(torch.zeros(4, 24, device=DEV, dtype=DT[dt]))
+
+
+def test_fused_w8a8_denoiser_matches_unfused(qdm):
+    """BASELINE config 3 in small: SmoothQuant alpha = 0.5 + real W8A8 modules on the SDXL skeleton, fused against unfused."""
+    M = importlib.import_module(PKG + ".models")
+    model = M.StableDiffusionXL.from_skeleton(device=DEV, channels=(320, 640), depth=(0, 2), latent_size=32)
+    lat = torch.randn(2, 4, 32, 32, generator=torch.Generator().manual_seed(11)).half().to(DEV)
+    model.calib_samples = model.default_calib_samples(1, 2)
+    model.quantize(quant_config={"w_bit": 8, "version": "w8a8"}, quantType="sq", alpha=0.5, calib_num_infer_steps=1)
+    assert any(type(m).__name__ == "W8A8Linear" for m in model.denoiser().modules())
+    ref = model.generate(["a", "b"], lat=lat, num_inference_steps=3)
+    done = model.fuse_layers()
+    assert done["self_qkv"] > 0 and done["context_kv"] > 0 and done["time_emb_proj"] > 0
+    out = model.generate(["a", "b"], lat=lat, num_inference_steps=3, fuse_layers=True)
+    err = ((out.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
+    assert err <= TOL, err            # the GEMMs are bit-equal; qdm_geglu may differ from gelu + mul in the last bit
 
 
 @pytest.mark.parametrize("kind", ["sd15", "sdxl", "sd35"])

@@ -458,3 +458,18 @@ def test_fuse_layers_host_logic(kind):
         assert torch.equal(model.generate(["a", "b"], lat=lat, num_inference_steps=2), ref)
     with pytest.raises(TypeError):
         fu.fuse_linears([torch.nn.Linear(8, 8)])
+
+
+def test_fuse_layers_w8a8_host_logic():
+    """SmoothQuant + W8A8 modules (oracle-backed ops): q / k / v share the SmoothQuant divisor, so they fuse; the fused model's
+    latents equal the unfused model's."""
+    with patched_ops():
+        M, model = tiny_sd15()
+        lat = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(6)).half()
+        model.calib_samples = model.default_calib_samples(1, 2)
+        model.quantize(quant_config={"w_bit": 8, "version": "w8a8"}, quantType="sq", alpha=0.5, calib_num_infer_steps=1)
+        ref = model.generate(["a", "b"], lat=lat, num_inference_steps=2)
+        done = model.fuse_layers()
+        assert done["self_qkv"] > 0 and done["context_kv"] > 0
+        out = model.generate(["a", "b"], lat=lat, num_inference_steps=2, fuse_layers=True)
+        assert ((out.float() - ref.float()).abs().max() / ref.float().abs().max()).item() <= 2e-3
