@@ -85,7 +85,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   // [4 j][MT][4][32] after it (the same bytes: a warp writes its sums only when it is done with its ring)
   constexpr int WARP_AREA = RING ? SK_RING * SK_CHUNK_BYTES : 4 * MT * 4 * 32 * 4;
   static_assert(WARP_AREA >= 4 * MT * 4 * 32 * 4, "the partial sums fit the ring");
-  uint8_t* area0 = reinterpret_cast<uint8_t*>(xs + 8 * MT * pitch);
+  uint8_t* area0 = reinterpret_cast<uint8_t*>(xs + M * pitch);   // only the M real rows of x are staged (rows >= M are zero registers)
   auto red_w = [&](int w) { return reinterpret_cast<float*>(area0 + w * WARP_AREA); };
   float* part = reinterpret_cast<float*>(area0 + SK_WARPS * WARP_AREA);   // [WN column groups][4 j][MT][4][32]
   const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(area0)) + (threadIdx.x >> 5) * WARP_AREA;
@@ -122,7 +122,8 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
     }
   };
   // first chunk of packed words and the first group's zero points / scales: in flight while x is staged
-  const int g_pre = (w_lo << 4) / group;
+  const int gshift = 31 - __clz(group);   // group is a power of two (checked by the caller): no integer division in the loop
+  const int g_pre = (w_lo << 4) >> gshift;
   uint32_t zw_pre = 0u;
   uint4 sv_pre = make_uint4(0, 0, 0, 0);
   // RING: lane L copies the 16-byte pieces L, L + 32, L + 64, L + 96 of a chunk; piece p = (k row p / 2, half p % 2) of the
@@ -160,14 +161,14 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   // the loads above are constants (packed words, zeros, scales): they fly while the previous kernel drains; x and y belong
   // to earlier kernels and are not touched before this wait
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // stage this CTA's k slice of x (rows >= M are zeros)
+  // stage this CTA's k slice of the M rows of x
   {
     const int vec_per_row = k_slice >> 3;
     const int k0 = s_lo << 4;
-    for (int idx = threadIdx.x; idx < 8 * MT * vec_per_row; idx += SK_WARPS * 32) {
+    for (int idx = threadIdx.x; idx < M * vec_per_row; idx += SK_WARPS * 32) {
       const int row = idx / vec_per_row, c8 = idx - row * vec_per_row;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (row < M && k0 + c8 * 8 < K) v = __ldg(reinterpret_cast<const uint4*>(x + int64_t(row) * K + k0) + c8);
+      if (k0 + c8 * 8 < K) v = __ldg(reinterpret_cast<const uint4*>(x + int64_t(row) * K + k0) + c8);
       *reinterpret_cast<uint4*>(xs + row * pitch + c8 * 8) = v;
     }
   }
@@ -189,7 +190,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
       const int st = s0 + u;
       if (st >= w_hi) break;
       const int kk = st << 4;
-      const int g = kk / group;                         // group % 16 == 0: a step never straddles two groups
+      const int g = kk >> gshift;                       // group = 64 * 2^j: a step never straddles two groups
       if (g != g_cur) {
         g_cur = g;
         // zw_pre / sv_pre hold this group's parameters (requested when the previous group was entered, or before the x
@@ -214,7 +215,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
       uint2 xb[MT];
 #pragma unroll
       for (int m = 0; m < MT; ++m)
-        xb[m] = *reinterpret_cast<const uint2*>(xs + (8 * m + nl) * pitch + (kk - (s_lo << 4)) + 4 * t);
+        xb[m] = (8 * m + nl < M) ? *reinterpret_cast<const uint2*>(xs + (8 * m + nl) * pitch + (kk - (s_lo << 4)) + 4 * t) : make_uint2(0u, 0u);
       // unpack: P = (byte b of row r, byte b of row r + 1) -> nibbles 2b (low) and 2b + 1 (high) of both rows
       uint32_t a[4][4];
 #pragma unroll
@@ -300,10 +301,11 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   cluster.sync();   // every CTA's shared memory stays alive until its peers have read it
 }
 
-size_t skinny_smem(int mt, int steps_per_cta, int wn, bool ring) {
+size_t skinny_smem(int64_t M, int steps_per_cta, int wn, bool ring) {
+  const int mt = int((M + 7) / 8);
   const size_t sums = size_t(4) * mt * 4 * 32 * sizeof(float);
   const size_t warp_area = ring ? size_t(SK_RING) * SK_CHUNK_BYTES : sums;
-  return size_t(8 * mt) * (steps_per_cta * 16 + 16) * 2 + SK_WARPS * warp_area + wn * sums;
+  return size_t(M) * (steps_per_cta * 16 + 16) * 2 + SK_WARPS * warp_area + wn * sums;
 }
 
 template <bool BF16, int MT, bool RING>
@@ -365,11 +367,11 @@ void skinny_plan(int64_t M, int64_t N, int64_t K, int* ks_out, int* spc_out, int
   while (ks < 8 && col_blocks * ks * 2 <= resident && steps / (2 * ks) >= 2 * wk) ks *= 2;
   int spc = int((steps + ks - 1) / ks);
   const bool ring = skinny_ring_ok(N);
-  while (ks < 8 && skinny_smem(mt, spc, wn, ring) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
+  while (ks < 8 && skinny_smem(M, spc, wn, ring) > 160 * 1024) { ks *= 2; spc = int((steps + ks - 1) / ks); }
   *ks_out = ks;
   *spc_out = spc;
   *wn_out = wn;
-  *smem_out = skinny_smem(mt, spc, wn, ring);
+  *smem_out = skinny_smem(M, spc, wn, ring);
 }
 
 }  // namespace

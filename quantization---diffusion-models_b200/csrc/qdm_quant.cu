@@ -960,32 +960,64 @@ __global__ void __launch_bounds__(256)
 dequant_awq_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
                    const T* __restrict__ scales, uint32_t total_words, uint32_t n_words, uint32_t group,
                    T* __restrict__ out) {
-  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total_words; i += gridDim.x * 256u) {
-    const uint32_t k = i / n_words, c = i - k * n_words;
-    const uint32_t g = k / group;
-    const uint32_t qw = (uint32_t)__ldg(qweight + i);
-    const uint32_t zw = (uint32_t)__ldg(qzeros + g * n_words + c);
-    const T* sp = scales + (int64_t(g) * n_words + c) * 8;
-    T* dst = out + int64_t(i) * 8;
-    T sv[8], o[8];
-    if (sizeof(T) == 2) {
-      *reinterpret_cast<uint4*>(sv) = *reinterpret_cast<const uint4*>(sp);
-    } else {
+  const uint32_t stride = gridDim.x * 256u;
+  for (uint32_t i0 = blockIdx.x * 256u + threadIdx.x; i0 < total_words; i0 += 2 * stride) {
+    // two words per thread-step: all six loads are issued before the first unpack
+    uint32_t qw[2], zw[2];
+    uint4 sv[2];
+    const T* sp[2];
+    bool on[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sv[j] = sp[j];
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t i = i0 + u * stride;
+      on[u] = i < total_words;
+      const uint32_t ii = on[u] ? i : i0;
+      const uint32_t k = ii / n_words, c = ii - k * n_words;
+      const uint32_t g = k / group;
+      qw[u] = (uint32_t)__ldg(qweight + ii);
+      zw[u] = (uint32_t)__ldg(qzeros + g * n_words + c);
+      sp[u] = scales + (int64_t(g) * n_words + c) * 8;
+      if constexpr (sizeof(T) == 2) sv[u] = __ldg(reinterpret_cast<const uint4*>(sp[u]));
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float qf = __uint_as_float(((qw >> (4 * j)) & 0xFu) | 0x4B000000u);
-      const float zf = __uint_as_float(((zw >> (4 * j)) & 0xFu) | 0x4B000000u);
-      const int col = 2 * (j & 3) + (j >> 2);                // AWQ order {0,2,4,6,1,3,5,7}[j]
-      o[col] = ElemTraits<T>::from_f(__fmul_rn(__fsub_rn(qf, zf), ElemTraits<T>::to_f(sv[col])));
-    }
-    if (sizeof(T) == 2) {
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
-    } else {
+    for (int u = 0; u < 2; ++u) {
+      if (!on[u]) continue;
+      T* dst = out + int64_t(i0 + u * stride) * 8;
+      if constexpr (sizeof(T) == 2) {
+        // 16-bit types, packed: nibbles i and i + 4 of a word are the ADJACENT columns 2i, 2i + 1 (AWQ order), so
+        // (w >> 4i) & 0x000F000F or-ed into the mantissas of (1024 | 1024) [fp16] / (128 | 128) [bf16] is the pair
+        // (magic + q_2i, magic + q_2i+1); the packed subtract of the zero-point pair is exact and the packed multiply by
+        // the scale pair rounds once -- the same value as the fp32 form below, 6 instructions per two outputs, not ~16
+        constexpr uint32_t MAGIC = std::is_same<T, __half>::value ? 0x64006400u : 0x43004300u;
+        const uint32_t s2[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+        uint32_t o2[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = o[j];
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t q2 = ((qw[u] >> (4 * i)) & 0x000F000Fu) | MAGIC;
+          const uint32_t z2 = ((zw[u] >> (4 * i)) & 0x000F000Fu) | MAGIC;
+          if constexpr (std::is_same<T, __half>::value) {
+            const __half2 r = __hmul2(__hsub2(*reinterpret_cast<const __half2*>(&q2), *reinterpret_cast<const __half2*>(&z2)),
+                                      *reinterpret_cast<const __half2*>(&s2[i]));
+            o2[i] = *reinterpret_cast<const uint32_t*>(&r);
+          } else {
+            const __nv_bfloat162 r = __hmul2(__hsub2(*reinterpret_cast<const __nv_bfloat162*>(&q2), *reinterpret_cast<const __nv_bfloat162*>(&z2)),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&s2[i]));
+            o2[i] = *reinterpret_cast<const uint32_t*>(&r);
+          }
+        }
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(o2[0]), "r"(o2[1]), "r"(o2[2]), "r"(o2[3]) : "memory");
+      } else {
+        T o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float qf = __uint_as_float(((qw[u] >> (4 * j)) & 0xFu) | 0x4B000000u);
+          const float zf = __uint_as_float(((zw[u] >> (4 * j)) & 0xFu) | 0x4B000000u);
+          const int col = 2 * (j & 3) + (j >> 2);                // AWQ order {0,2,4,6,1,3,5,7}[j]
+          o[col] = ElemTraits<T>::from_f(__fmul_rn(__fsub_rn(qf, zf), ElemTraits<T>::to_f(sp[u][col])));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = o[j];
+      }
     }
   }
 }

@@ -448,13 +448,72 @@ awq_wsum_stage1(const T* __restrict__ w, int64_t n_rows, int64_t k_cols, int lan
     }
   };
   const int64_t step = int64_t(gridDim.y) * kColWarps;
-  for (int64_t r = int64_t(blockIdx.y) * kColWarps + warp; r < n_rows; r += 2 * step) {   // two loads in flight
-    const bool two = r + step < n_rows;
-    Vec16<T> va, vb;
-    if (active) va = ld_vec16_stream(w + r * k_cols + c0);
-    if (active && two) vb = ld_vec16_stream(w + (r + step) * k_cols + c0);
-    row_step(va, true);
-    if (two) row_step(vb, true);
+  if constexpr (std::is_same<T, __half>::value) {
+    // fp16: rows in PAIRS -- the two rows' lane maxima travel through the group butterfly as the two halves of one half2
+    // (half the shuffles per row), the quotients |w| / (max + 1e-6) are formed two at a time with packed fp32 FMAs
+    // (fma.rn.f32x2: same rounding as the scalar form, half the issue slots); four 16-byte loads in flight per thread.
+    // Rows are still accumulated in the order r, r + step, r + 2 step, ...: bit-identical sums to the one-row form.
+    float2 acc2[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc2[p] = make_float2(0.f, 0.f);
+    auto pair_step = [&](const Vec16<T>& va, const Vec16<T>& vb, bool have_b) {
+      __half2 a2[4], b2[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        a2[p] = active ? __habs2(reinterpret_cast<const __half2*>(&va)[p]) : __float2half2_rn(0.f);
+        b2[p] = (active && have_b) ? __habs2(reinterpret_cast<const __half2*>(&vb)[p]) : __float2half2_rn(0.f);
+      }
+      __half2 ma = __hmax2(__hmax2(a2[0], a2[1]), __hmax2(a2[2], a2[3]));
+      __half2 mb = __hmax2(__hmax2(b2[0], b2[1]), __hmax2(b2[2], b2[3]));
+      ma = __hmax2(ma, __lowhigh2highlow(ma));
+      mb = __hmax2(mb, __lowhigh2highlow(mb));
+      __half2 m2 = __lows2half2(ma, mb);   // (row a, row b)
+      switch (lanes_per_group) {
+        case 32: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 16));
+        case 16: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 8));
+        case 8: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 4));
+        case 4: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
+        case 2: m2 = __hmax2(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
+        default: break;
+      }
+      const float da = rnd<T>(__fadd_rn(__low2float(m2), 1e-6f)), db = rnd<T>(__fadd_rn(__high2float(m2), 1e-6f));
+      const float ra = rcp_approx(da), rb = rcp_approx(db);
+      auto add_row = [&](const __half2 (&x2)[4], float d, float r) {
+        const float2 rr = make_float2(r, r), nd = make_float2(-d, -d);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float2 af = __half22float2(x2[p]);
+          const float2 q0 = __fmul2_rn(af, rr);
+          const float2 e = __ffma2_rn(q0, nd, af);          // exact remainder a - q0 * d
+          const float2 q1 = __ffma2_rn(e, rr, q0);
+          acc2[p] = __fadd2_rn(acc2[p], __half22float2(__floats2half2_rn(q1.x, q1.y)));
+        }
+      };
+      add_row(a2, da, ra);
+      if (have_b) add_row(b2, db, rb);
+    };
+    for (int64_t r = int64_t(blockIdx.y) * kColWarps + warp; r < n_rows; r += 4 * step) {
+      Vec16<T> v[4];
+      bool have[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        have[u] = r + u * step < n_rows;
+        if (active && have[u]) v[u] = ld_vec16_stream(w + (r + u * step) * k_cols + c0);
+      }
+      pair_step(v[0], v[1], have[1]);
+      if (have[2]) pair_step(v[2], v[3], have[3]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { acc[2 * p] = acc2[p].x; acc[2 * p + 1] = acc2[p].y; }
+  } else {
+    for (int64_t r = int64_t(blockIdx.y) * kColWarps + warp; r < n_rows; r += 2 * step) {   // two loads in flight
+      const bool two = r + step < n_rows;
+      Vec16<T> va, vb;
+      if (active) va = ld_vec16_stream(w + r * k_cols + c0);
+      if (active && two) vb = ld_vec16_stream(w + (r + step) * k_cols + c0);
+      row_step(va, true);
+      if (two) row_step(vb, true);
+    }
   }
   __shared__ float sm[kColWarps][32 * V + 1];
 #pragma unroll

@@ -35,6 +35,12 @@ for f, w in [
     ("ts_models_r02.txt", "`tools/ts_probe.py models`: every Linear shape with M > 32 of the three denoisers: AWQ-tensor kernels vs cuBLAS f16 vs the TS kernel at 5 token-tile widths"),
     ("calib_scaling_r02.json", "`bench.py --mode calib --model sd35 --calib-batches 8` at 1 / 2 / 4 / 8 GPUs: seconds per model, phase times (max over ranks), codes checksum"),
     ("topo_8gpu_box_r02.txt", "`nvidia-smi topo -m` + `lscpu` of the 8-GPU box (one NUMA node, 32 vCPUs: what bounds the end-to-end leg at N = 8)"),
+    ("bench_line_r02_fused.json", "`bench.py` at 1 GPU, FINAL build of the round: the step with the same-input Linears fused (100 launches), the per-Linear step (`unfused`) beside it, e2e with the on-device GEGLU chain, W8A8 on the fused inventory, denoise with `fuse_layers`"),
+    ("launches_bench_step_fused_r02.csv, step_by_shape_fused_r02.txt, step_traffic_r02_fused.json", "ncu launch list of one eager FUSED bench step (100 launches), aggregated by shape; `roofline.traffic` of the final line"),
+    ("gemm_layers_fused_r02.json, gemm_layers_fused_sdxl_r02.json, gemm_layers_fused_sd35_r02.json, ts_fused_r02.txt", "`bench.py --layers --fused [--model ..]` and `tools/ts_probe.py fused`: the launch shapes the fusion creates, module dispatch vs cuBLAS f16 vs forced TS tile widths"),
+    ("w4a16_bstat_65536x960x320_r02.txt", "ncu summary + top stalled SASS of the B-stationary kernel on the fused q/k/v launch of the 64 x 64 level"),
+    ("w4a16_skinny_1x1104128x2432_r02.txt, skinny_w4a16_times_r02.txt", "the skinny kernel on the grouped AdaLN launch of SD3.5-L (ncu, cp.async ring build) and its times before / after the ring"),
+    ("kernels_ab_r02.json, kernels_ab_ncu_r02.txt", "`bench.py --mode kernels` (HBM fraction of the (a)/(b) kernels + qdm_geglu) and the ncu summaries of awq_wsum / quant_pack_awq / dequant_awq / fused-search quant_group / geglu"),
 ]:
     A(f"| `{f}` | {w} |")
 
@@ -45,7 +51,9 @@ for name, ms in [("round 1 final", 5.198), ("round 2 start (shape-parity work, c
                  ("TS kernel, first dispatch (few-wave + text-token shapes)", 4.907), ("TS kernel: issuer rewritten (peeks inside one asm block, one commit per stage), TS default", 4.610),
                  ("role-local PDL waits (weights fetched while the previous kernel drains)", 4.580),
                  ("wide tiles (two sub-tiles, 16 MMAs per weight stage) where the fitted cost model prefers them; `bench_line_r02.json`", load("bench_line_r02.json")["ms_per_step"]),
-                 (f"8 GPUs, build before the wide tiles (per-GPU step; aggregate {n8['value']:.0f} TFLOP/s)", n8["ms_per_step"])]:
+                 (f"8 GPUs, build before the wide tiles (per-GPU step; aggregate {n8['value']:.0f} TFLOP/s)", n8["ms_per_step"]),
+                 ("elect.sync roles + register quantiser (same 184 launches; `unfused` of `bench_line_r02_fused.json`)", load("bench_line_r02_fused.json")["unfused"]["ms_per_step"]),
+                 ("same-input Linears fused: 184 Linears in 100 launches (`fused_utils.fuse_linears`); `bench_line_r02_fused.json`", load("bench_line_r02_fused.json")["ms_per_step"])]:
     A(f"| {name} | {ms:.3f} | {3732.3 / ms:.0f} | {3.7323 / ms / 1.6976:.2f} |")
 
 A("\n## W4A16 per shape, module dispatch (us, cold L2) — SD1.5 / SDXL / SD3.5-L\n")
@@ -66,6 +74,38 @@ for m in ("sd15", "sdxl", "sd35"):
         t1 += c * (o["w4a16"]["ms"] if o else r["w4a16"]["ms"])
         A(f"| {k[0]} | {k[1]} | {k[2]} | {c} | {r['w4a16_kernel'][0]} ({r['w4a16_kernel'][1]}) | {(o['w4a16']['ms'] * 1e3 if o else float('nan')):.1f} | {r['w4a16']['ms'] * 1e3:.1f} | {r['cublas_f16']['ms'] * 1e3:.1f} | {r['w8a8_gemm']['ms'] * 1e3:.1f} |")
     A(f"\nwhole Linear pass: round 1 {t1 * 1e3:.0f} us -> round 2 {t2 * 1e3:.0f} us; cuBLAS f16 on the fake-quant weights {tc * 1e3:.0f} us.")
+
+A("\n## The launch shapes the same-input fusion creates (us, cold L2)\n")
+A("`fused_utils.fuse_projections`: self-attention q/k/v as one launch per block, cross-attention k/v of ALL blocks as one launch per step,")
+A("the grouped time_emb_proj / AdaLN modulation launch.  Only the shapes that differ from the per-Linear inventory:\n")
+A("| model | M | N | K | launches | members replaced | kernel (tile) | fused | members one by one | cuBLAS f16 (fused) |\n|---|---:|---:|---:|---:|---:|---|---:|---:|---:|")
+import importlib, sys
+sys.path.insert(0, os.path.dirname(R))
+S = importlib.import_module("quantization---diffusion-models_b200.shapes")
+for m, ff, plain in (("sd15", "gemm_layers_fused_r02.json", "gemm_layers_r02.json"), ("sdxl", "gemm_layers_fused_sdxl_r02.json", "gemm_layers_sdxl_r02.json"),
+                     ("sd35", "gemm_layers_fused_sd35_r02.json", "gemm_layers_sd35_r02.json")):
+    fr = {(r["M"], r["N"], r["K"]): r for r in rows_of(load(ff))}
+    pr = {(r["M"], r["N"], r["K"]): r for r in rows_of(load(plain))}
+    inv = {"sd15": S.sd15_unet_linears_fused, "sdxl": S.sdxl_unet_linears_fused, "sd35": S.sd35_mmdit_linears_fused}[m]()
+    tot_f = sum(r["calls_per_step"] * r["w4a16"]["ms"] for r in fr.values())
+    tot_p = sum(r["calls_per_step"] * r["w4a16"]["ms"] for r in pr.values())
+    for e in inv:
+        k = (e[1], e[2], e[3])
+        if len(e[5]) == 1 or k not in fr:
+            continue
+        r = fr[k]
+        sep = sum(pr[(e[1], n, e[3])]["w4a16"]["ms"] for n in e[5] if (e[1], n, e[3]) in pr)
+        A(f"| {m} | {k[0]} | {k[1]} | {k[2]} | {e[4]} | {len(e[5])} | {r['w4a16_kernel'][0]} ({r['w4a16_kernel'][1]}) | {r['w4a16']['ms'] * 1e3:.1f} | {sep * 1e3:.1f} | {r['cublas_f16']['ms'] * 1e3:.1f} |")
+    A(f"| {m} | | | | | | **whole Linear pass** | **{tot_f * 1e3:.0f}** | **{tot_p * 1e3:.0f}** | |")
+
+kab = load("kernels_ab_r02.json")
+A("\n## HBM-bound kernels (a) / (b) and qdm_geglu (`bench.py --mode kernels`, tensors larger than L2)\n")
+A(f"fraction of the measured HBM copy rate ({kab['peaks']['hbm']:.0f} GB/s); round 1 values from `kernels_ab_r01.json`\n")
+old_k = {r["kernel"]: r for r in load("kernels_ab_r01.json")["rows"]}
+A("| kernel | us | GB/s | fraction | round 1 |\n|---|---:|---:|---:|---:|")
+for r in kab["rows"]:
+    o = old_k.get(r["kernel"])
+    A(f"| {r['kernel']} | {r['ms'] * 1e3:.1f} | {r['GBps']:.0f} | {r['frac_of_hbm_peak']:.2f} | {(o['frac_of_hbm_peak'] if o else float('nan')):.2f} |")
 
 c = load("calib_scaling_r02.json")
 A("\n## AWQ calibration of the SD3.5-Large skeleton (BASELINE config 4), sharded\n")
