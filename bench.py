@@ -285,7 +285,12 @@ def sub_w8a8(q, shapes, layers, dev, dtype, steps, warmup, timed):
     ms_u = timed(_graph_of(torch, step_of(members)).replay, steps, warmup) / steps if len(members) != len(mods) else ms
     peak = int8_dense_peak(torch, dev)
     tf, tf_g = flops / ms / 1e9, flops / ms_g / 1e9
+    # per-shape roofline of the GEMMs: max(int8 tensor time, algorithmic bytes at the measured HBM rate), summed over the launches
+    pk = measured_peaks()
+    roof_ms = sum(max(2.0 * key[0] * mod.out_features * key[1] / ((peak or 3000.0) * 1e12),
+                      shapes.gemm_bytes_w8a8(key[0], mod.out_features, key[1]) / (pk["hbm"] * 1e9)) for mod, key in mods) * 1e3
     return {"tflops": tf, "ms_per_step": ms, "gemm_only_tflops": tf_g, "gemm_only_ms_per_step": ms_g, "launches_per_step": launches,
+            "gemm_only_frac_per_shape_roofline": roof_ms / ms_g,
             "unfused_ms_per_step": ms_u, "unfused_tflops": flops / ms_u / 1e9, "linears_per_step": len(members),
             "tflop_per_step": flops / 1e12, "int8_dense_peak_tops": peak, "peak_how": "torch._int_mm (cuBLASLt int8) 8192^3, best of 10, this run",
             "frac_of_int8_peak": (tf_g / peak) if peak else None,

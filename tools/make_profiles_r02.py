@@ -36,6 +36,7 @@ for f, w in [
     ("calib_scaling_r02.json", "`bench.py --mode calib --model sd35 --calib-batches 8` at 1 / 2 / 4 / 8 GPUs: seconds per model, phase times (max over ranks), codes checksum"),
     ("topo_8gpu_box_r02.txt", "`nvidia-smi topo -m` + `lscpu` of the 8-GPU box (one NUMA node, 32 vCPUs: what bounds the end-to-end leg at N = 8)"),
     ("bench_line_r02_fused.json", "`bench.py` at 1 GPU, FINAL build of the round: the step with the same-input Linears fused (100 launches), the per-Linear step (`unfused`) beside it, e2e with the on-device GEGLU chain, W8A8 on the fused inventory, denoise with `fuse_layers`"),
+    ("bench_line_r02_fused_n2.json, bench_line_r02_fused_n8.json", "the same final line at 2 and 8 GPUs (torchrun, NCCL): device-resident and end-to-end aggregates, per-GPU W8A8 / denoise, sharded SD3.5-L calibration with its codes checksum"),
     ("launches_bench_step_fused_r02.csv, step_by_shape_fused_r02.txt, step_traffic_r02_fused.json", "ncu launch list of one eager FUSED bench step (100 launches), aggregated by shape; `roofline.traffic` of the final line"),
     ("gemm_layers_fused_r02.json, gemm_layers_fused_sdxl_r02.json, gemm_layers_fused_sd35_r02.json, ts_fused_r02.txt", "`bench.py --layers --fused [--model ..]` and `tools/ts_probe.py fused`: the launch shapes the fusion creates, module dispatch vs cuBLAS f16 vs forced TS tile widths"),
     ("w4a16_bstat_65536x960x320_r02.txt", "ncu summary + top stalled SASS of the B-stationary kernel on the fused q/k/v launch of the 64 x 64 level"),
