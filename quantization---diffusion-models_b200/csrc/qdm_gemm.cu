@@ -1120,7 +1120,7 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
-// ---------------------------------------------------------------- B-stationary CTA-pair kernel (W4, K <= 384)
+// ---------------------------------------------------------------- B-stationary CTA-pair kernel (W4, K <= 320)
 // For the K = 320 layers of the UNet (M = 65536 tokens: 40 of the step's 184 launches, 37 % of its time) a pair's B tile
 // part is tiny: K x nloc fp16 = 80 KB.  The generic kernel re-fetches and re-dequantises it for every one of the pair's
 // ~7-35 tiles and pays packed-operand TMA rows, dequant latency and a B stage per k-block for it.  Here every pair keeps
@@ -1130,14 +1130,17 @@ qdm_gemm2_sk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // k-blocks per tile the epilogue is as long as the main loop.
 struct CfgBS {
   static constexpr int NLOC = 128;
+  // 6 A stages + 5 resident k-blocks (K <= 320: every small-K layer of the three denoisers) instead of 5 + 6 (K <= 384): the
+  // kernel is bound by the bytes of A in flight per SM x the L2 latency, measured 65536 x 2560 x 320 94.9 -> 90.8 us,
+  // 65536 x 960 x 320 43.2 -> 41.7, 65536 x 320 x 320 24.1 -> 23.1
 #ifndef QDM_BS_ASTAGES
-#define QDM_BS_ASTAGES 5
+#define QDM_BS_ASTAGES 6
 #endif
 #ifndef QDM_BS_KB
-#define QDM_BS_KB 6
+#define QDM_BS_KB 5
 #endif
   static constexpr int A_STAGES = QDM_BS_ASTAGES;
-  static constexpr int BST_KB = QDM_BS_KB;                // resident k-blocks: K <= 384
+  static constexpr int BST_KB = QDM_BS_KB;                // resident k-blocks: K <= 320
   static constexpr int B_KB_BYTES = NLOC * ROW_BYTES;     // 16 KB per k-block
   static constexpr int RAW_N = 2;                         // raw ring, used once; afterwards staging of epilogue set 1
   static constexpr int RAW_BYTES = RAW_N * RawCfg<NLOC>::BYTES;
@@ -1842,7 +1845,7 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
   // 79.4 vs 89.2 us (cuBLAS f16 79.4), 4096 x 2432 x 2432: 41.5 vs 56.3, 8192 x 1280 x 1280: 26.1 vs 33.7, the text-token
   // shapes 333 x 2432 x 9728: 44.6 vs 63.9 and 1232 x 1280 x 768: 9.0 vs 11.3 (any multiple of 32 tokens per tile, a hidden
   // epilogue, no shared-memory round trip of the weights, one barrier test + one commit per K = 128 on the issuing thread).
-  // It loses where K <= 384 with many tiles (the B-stationary kernel dequantises each weight once per CTA, not once per
+  // It loses where K <= 320 with many tiles (the B-stationary kernel dequantises each weight once per CTA, not once per
   // tile: 65536 x 320 x 320 25.2 vs 31.8) and where N = 320 leaves most of a 256-channel block empty.
   if (blob_ts && !conv && K >= 128 && M > 32 && (g_force_ctas == 128 || (g_force_ctas == 0 && !g_no_rp && !opt.no_rp))) {
     bool take = g_force_ctas == 128;
