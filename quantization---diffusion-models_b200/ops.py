@@ -177,13 +177,17 @@ def awq_wsum(w, group):
     return out
 
 
-def sqdiff_sum(a, b):
-    """(a - b).float().pow(2).sum() as a float64 0-dim tensor (quantize/quantizer.py:777)."""
+def sqdiff_sum(a, b, out=None):
+    """(a - b).float().pow(2).sum() as a float64 0-dim tensor (quantize/quantizer.py:777).  `out`: a one-element float64
+    device tensor (e.g. a slot of the search's loss table) written in place."""
     _cuda(a, "a"), _cuda(b, "b")
     if a.shape != b.shape or a.dtype != b.dtype:
         raise ValueError("sqdiff_sum: shape/dtype mismatch")
     ac, bc = a.contiguous(), b.contiguous()
-    out = torch.empty((), dtype=torch.float64, device=a.device)
+    if out is None:
+        out = torch.empty((), dtype=torch.float64, device=a.device)
+    elif out.dtype != torch.float64 or out.numel() != 1 or out.device != a.device:
+        raise ValueError("sqdiff_sum: out must be a one-element float64 tensor on the inputs' device")
     L = lib()
     ws = _ws(a.device, L.qdm_sqdiff_workspace_bytes(ac.numel()))
     with _guard(a.device):

@@ -57,8 +57,12 @@ def awq_wsum(w, group):
     return (g.abs() / (g.abs().amax(dim=1, keepdim=True) + 1e-6)).view(w.shape).float().sum(0)
 
 
-def sqdiff_sum(a, b):
-    return (a - b).float().pow(2).double().sum()
+def sqdiff_sum(a, b, out=None):
+    v = (a - b).float().pow(2).double().sum()
+    if out is None:
+        return v
+    out.copy_(v)
+    return out
 
 
 def quant_group(w, group, n_bits=4, zero_point=True, no_clamp=False, pre_mul=None, clip_max=None, post_div=None,

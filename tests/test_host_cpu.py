@@ -473,3 +473,20 @@ def test_fuse_layers_w8a8_host_logic():
         assert done["self_qkv"] > 0 and done["context_kv"] > 0
         out = model.generate(["a", "b"], lat=lat, num_inference_steps=2, fuse_layers=True)
         assert ((out.float() - ref.float()).abs().max() / ref.float().abs().max()).item() <= 2e-3
+
+
+def test_ratio_scales_all_rows_equal_the_per_point_vectors():
+    """AwqQuantizer._ratio_scales_all: the batched scale vectors of the 20-point grid are bit-identical to the per-point
+    `_ratio_scales` (quantizer.py:717-725), incl. zero / inf statistics, duo and single scaling, every dtype."""
+    Q = importlib.import_module(PKG + ".quantizer")
+    for duo in (True, False):
+        q = Q.AwqQuantizer.__new__(Q.AwqQuantizer)
+        q.duo_scaling = duo
+        for dt in (torch.float32, torch.float16, torch.bfloat16):
+            g = torch.Generator().manual_seed(0)
+            xm, wm = (torch.rand(640, generator=g) * 3).to(dt), torch.rand(640, generator=g).to(dt)
+            xm[5], wm[7], xm[9] = 0, 0, float("inf")
+            rows = q._ratio_scales_all(xm, wm, list(range(20)))
+            assert all(torch.equal(rows[i], q._ratio_scales(xm, wm, i / 20)) for i in range(20))
+            sub = q._ratio_scales_all(xm, wm, [3, 7, 19])
+            assert all(torch.equal(sub[j], q._ratio_scales(xm, wm, i / 20)) for j, i in enumerate([3, 7, 19]))
