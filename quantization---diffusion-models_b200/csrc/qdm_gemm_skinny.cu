@@ -70,7 +70,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool BF16, int MT, bool RING>
+// POST (M <= 8): zero point and scale are applied to the fp32 accumulator once per quantisation group instead of to every
+// weight pair.  The tensor core is fed the raw codes -- fp16: the nibble IS the fp16 subnormal q * 2^-24 (`p & 0x000F000F`, one
+// lop3 per weight pair; the high nibble of a byte stays in place as 16 q * 2^-24), bf16: (16 + q) / 16 -- the per-step sums of x
+// come from shared memory, and at a group boundary  y += s_c * (F_c * acc_g - (off_c + z_c) * sum_k x)  with F_c = 2^24 / 2^20
+// (fp16 low / high nibble) or 16 (bf16).  ~1.6 instead of ~3 issue slots per weight, which is what bounds this kernel.  The
+// products q * x are exact in fp32 and the scale is applied in fp32: closer to the exact product than the per-weight form
+// (which rounds every (q - z) * s to 16 bits first), equal to it within ~2^-11 relative -- the GEMM parity bar is 1e-2.
+#ifndef SK_F16_OFF
+#define SK_F16_OFF 0        // fp16 code offset: 0 = subnormal codes; 1024 = (1024 + q) * 2^-24 (normal numbers, A/B fallback)
+#endif
+
+template <bool BF16>
+__device__ __forceinline__ float h16_to_f(uint32_t bits) {
+  return BF16 ? __uint_as_float(bits << 16) : __half2float(__ushort_as_half((unsigned short)bits));
+}
+
+template <bool BF16, int MT, bool RING, bool POST>
 __global__ void __launch_bounds__(SK_WARPS * 32)
 w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__ qweight, const uint32_t* __restrict__ qzeros,
                     const uint16_t* __restrict__ scales, const uint16_t* __restrict__ bias, uint16_t* __restrict__ y,
@@ -88,6 +104,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   uint8_t* area0 = reinterpret_cast<uint8_t*>(xs + M * pitch);   // only the M real rows of x are staged (rows >= M are zero registers)
   auto red_w = [&](int w) { return reinterpret_cast<float*>(area0 + w * WARP_AREA); };
   float* part = reinterpret_cast<float*>(area0 + SK_WARPS * WARP_AREA);   // [WN column groups][4 j][MT][4][32]
+  float* xsum_s = part + WN * 4 * MT * 4 * 32;                            // POST: [k16 step of this CTA][8 MT rows] sums of x
   const uint32_t ring0 = uint32_t(__cvta_generic_to_shared(area0)) + (threadIdx.x >> 5) * WARP_AREA;
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -173,6 +190,21 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
     }
   }
   __syncthreads();
+  if (POST) {   // sum of the 16 x values of every (k16 step, row): what the code offset / zero point multiplies
+    for (int idx = threadIdx.x; idx < steps_per_cta * 8 * MT; idx += SK_WARPS * 32) {
+      const int stp = idx / (8 * MT), row = idx - stp * (8 * MT);
+      float sum = 0.f;
+      if (row < M && s_lo + stp < steps_total) {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(xs + row * pitch + 16 * stp);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(xs + row * pitch + 16 * stp + 8);
+        const uint32_t h[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += h16_to_f<BF16>(h[e] & 0xFFFFu) + h16_to_f<BF16>(h[e] >> 16);
+      }
+      xsum_s[idx] = sum;
+    }
+    __syncthreads();
+  }
 
   float acc[4][MT][4];
 #pragma unroll
@@ -184,6 +216,36 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
 
   int g_cur = -1;
   uint32_t zm[8], sc2[8];   // per column of this lane's word: (magic + z) and the scale, each duplicated into both halves
+  // POST: the current group's partial sums of codes * x, the sums of x they belong to, and the group's fp32 parameters
+  float acc_g[POST ? 4 : 1][POST ? MT : 1][4], xs_acc[POST ? MT : 1][2], sc_f[POST ? 8 : 1], kz_f[POST ? 8 : 1];
+  if (POST) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc_g[POST ? j : 0][POST ? m : 0][i] = 0.f;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) xs_acc[POST ? m : 0][0] = xs_acc[POST ? m : 0][1] = 0.f;
+  }
+  auto flush_group = [&]() {   // y += s_c * (F_c * acc_g - (off_c + z_c) * sum x), then the group accumulators restart
+    if constexpr (POST) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = 2 * j + (i >> 1);
+            const float fc = BF16 ? 16.f : ((c & 2) ? 1048576.f : 16777216.f);   // high nibbles of a byte carry 16 q
+            const float v = __fmaf_rn(acc_g[j][m][i], fc, -kz_f[c] * xs_acc[m][i & 1]);
+            acc[j][m][i] = __fmaf_rn(sc_f[c], v, acc[j][m][i]);
+            acc_g[j][m][i] = 0.f;
+          }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) xs_acc[m][0] = xs_acc[m][1] = 0.f;
+    }
+  };
   auto do_chunk = [&](const uint32_t (&w)[SK_U][4], int s0) {
 #pragma unroll
     for (int u = 0; u < SK_U; ++u) {
@@ -192,6 +254,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
       const int kk = st << 4;
       const int g = kk >> gshift;                       // group = 64 * 2^j: a step never straddles two groups
       if (g != g_cur) {
+        if (POST && g_cur >= 0) flush_group();
         g_cur = g;
         // zw_pre / sv_pre hold this group's parameters (requested when the previous group was entered, or before the x
         // staging for the first one); request the next group's now: they are needed group / 16 steps from here
@@ -209,6 +272,10 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
           zm[c] = MAGIC | z | (z << 16);
           const uint32_t s16 = (c & 1) ? (sw[c >> 1] >> 16) : (sw[c >> 1] & 0xFFFFu);
           sc2[c] = s16 | (s16 << 16);
+          if constexpr (POST) {
+            sc_f[c] = h16_to_f<BF16>(s16);
+            kz_f[c] = float(z) + (BF16 ? 16.f : float(SK_F16_OFF) / ((c & 2) ? 16.f : 1.f));
+          }
         }
       }
       // x fragment: rows kk + 4t .. 4t + 3 of x row nl (+ 8 per m-tile)
@@ -230,14 +297,33 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
           const int c_lo = (2 * b < 4) ? 2 * (2 * b) : 2 * (2 * b - 4) + 1;
           const int c_hi = (2 * b + 1 < 4) ? 2 * (2 * b + 1) : 2 * (2 * b + 1 - 4) + 1;
           // column c = 2j (+1): fragment j = c / 2, register (c & 1) + 2 * rp
-          a[c_lo >> 1][(c_lo & 1) + 2 * rp] = sub_mul2<BF16>(lo, zm[c_lo], sc2[c_lo]);
-          a[c_hi >> 1][(c_hi & 1) + 2 * rp] = sub_mul2<BF16>(hi, zm[c_hi], sc2[c_hi]);
+          if constexpr (POST) {
+            constexpr uint32_t OFFB = SK_F16_OFF ? 0x04000400u : 0u;   // exponent field 1: 2^-24 * (1024 + mantissa)
+            a[c_lo >> 1][(c_lo & 1) + 2 * rp] = BF16 ? (((p << 3) & 0x00780078u) | 0x3F803F80u) : ((p & 0x000F000Fu) | OFFB);
+            a[c_hi >> 1][(c_hi & 1) + 2 * rp] = BF16 ? (((p >> 1) & 0x00780078u) | 0x3F803F80u) : ((p & 0x00F000F0u) | OFFB);
+          } else {
+            a[c_lo >> 1][(c_lo & 1) + 2 * rp] = sub_mul2<BF16>(lo, zm[c_lo], sc2[c_lo]);
+            a[c_hi >> 1][(c_hi & 1) + 2 * rp] = sub_mul2<BF16>(hi, zm[c_hi], sc2[c_hi]);
+          }
         }
       }
+      if constexpr (POST) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+        for (int m = 0; m < MT; ++m) {
+          const float2 s2 = *reinterpret_cast<const float2*>(xsum_s + (st - s_lo) * (8 * MT) + 8 * m + 2 * t);
+          xs_acc[m][0] += s2.x;
+          xs_acc[m][1] += s2.y;
+        }
 #pragma unroll
-        for (int m = 0; m < MT; ++m) mma_w_x<BF16>(acc[j][m], a[j], xb[m].x, xb[m].y);
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_w_x<BF16>(acc_g[j][m], a[j], xb[m].x, xb[m].y);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int m = 0; m < MT; ++m) mma_w_x<BF16>(acc[j][m], a[j], xb[m].x, xb[m].y);
+      }
     }
   };
   if (RING) {
@@ -262,6 +348,7 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
     }
   }
 
+  if (POST && g_cur >= 0) flush_group();   // the last group of this warp's k range
   // fold the warps' K chunks (fixed order), then the cluster's K slices (fixed order)
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -301,17 +388,23 @@ w4a16_skinny_kernel(const uint16_t* __restrict__ x, const uint32_t* __restrict__
   cluster.sync();   // every CTA's shared memory stays alive until its peers have read it
 }
 
+bool skinny_post_ok(int mt) {
+  static const bool off = getenv("QDM_SKINNY_NO_POST") != nullptr;   // A/B switch, read once
+  return mt == 1 && !off;   // M <= 8; at M = 16 the second accumulator set costs the second resident CTA (measured 16.2 vs 15.1 us)
+}
+
 size_t skinny_smem(int64_t M, int steps_per_cta, int wn, bool ring) {
   const int mt = int((M + 7) / 8);
   const size_t sums = size_t(4) * mt * 4 * 32 * sizeof(float);
   const size_t warp_area = ring ? size_t(SK_RING) * SK_CHUNK_BYTES : sums;
-  return size_t(M) * (steps_per_cta * 16 + 16) * 2 + SK_WARPS * warp_area + wn * sums;
+  const size_t xsum = skinny_post_ok(mt) ? size_t(steps_per_cta) * 8 * mt * sizeof(float) : 0;
+  return size_t(M) * (steps_per_cta * 16 + 16) * 2 + SK_WARPS * warp_area + wn * sums + xsum;
 }
 
-template <bool BF16, int MT, bool RING>
+template <bool BF16, int MT, bool RING, bool POST>
 int skinny_launch(dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
                   const void* bias, void* y, int M, int N, int K, int group, int steps_per_cta, int wn, cudaStream_t st) {
-  auto kern = w4a16_skinny_kernel<BF16, MT, RING>;
+  auto kern = w4a16_skinny_kernel<BF16, MT, RING, POST>;
   static size_t smem_set = 0;   // per instantiation; grows monotonically
   if (smem > 48 * 1024 && smem > smem_set) {
     QDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -339,11 +432,13 @@ int skinny_launch(dim3 grid, int ks, size_t smem, const void* x, const int32_t* 
 template <bool BF16, bool RING>
 int skinny_mt(int mt, dim3 grid, int ks, size_t smem, const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
               const void* bias, void* y, int M, int N, int K, int group, int spc, int wn, cudaStream_t st) {
+  const bool post = skinny_post_ok(mt);
   switch (mt) {
-    case 1: return skinny_launch<BF16, 1, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
-    case 2: return skinny_launch<BF16, 2, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
-    case 3: return skinny_launch<BF16, 3, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
-    default: return skinny_launch<BF16, 4, RING>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 1: return post ? skinny_launch<BF16, 1, RING, true>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st)
+                        : skinny_launch<BF16, 1, RING, false>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 2: return skinny_launch<BF16, 2, RING, false>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    case 3: return skinny_launch<BF16, 3, RING, false>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
+    default: return skinny_launch<BF16, 4, RING, false>(grid, ks, smem, x, qweight, qzeros, scales, bias, y, M, N, K, group, spc, wn, st);
   }
 }
 

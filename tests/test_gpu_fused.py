@@ -103,7 +103,9 @@ def test_fuse_linears_equals_members(qdm, M, K, parts, bias, dt):
     want = torch.cat([m(x) for m in mems], dim=-1)
     assert y.shape == want.shape
     err = ((y.float() - want.float()).abs().max() / want.float().abs().max()).item()
-    assert err <= 2e-3, err          # same codes, same fp32 accumulation; the tile shape (summation order) may differ
+    # same codes, fp32 accumulation; the kernels may differ in summation order and in where the scale is applied (per weight,
+    # rounded to the 16-bit type, or per group in fp32 -- the M <= 8 kernel): one ulp of the type at the largest magnitude
+    assert err <= (2e-3 if dt == "f16" else 8e-3), err
     with pytest.raises(ValueError):
         other = linear.WQLinear_GEMM(4, grp, K * 2, 64, False, DEV, DT[dt])
         fu.fuse_linears([mems[0], other])
