@@ -746,6 +746,9 @@ def run_tables(args):
         cases = sorted({(m, n, k) for _, m, n, k, _ in layers}, reverse=True)
     rows = []
     g = torch.Generator(device=dev).manual_seed(42)
+    i8_peak = int8_dense_peak(torch, dev) if args.sweep else None     # the W8A8 denominator, this run
+    if i8_peak:
+        peaks = dict(peaks, int8_dense_tops=i8_peak, int8_how="torch._int_mm (cuBLASLt int8) 8192^3, best of 10, this run")
     for m, n, k in cases:
         grp = shapes_mod.group_for(k)
         x = torch.randn(m, k, generator=g, device=dev, dtype=torch.float16)
@@ -763,12 +766,21 @@ def run_tables(args):
         r["f16_tcgen05"] = {"ms": t, "tflops": flops / t / 1e9}
         t = time_fn(lambda: torch.nn.functional.linear(x, dq))
         r["cublas_f16"] = {"ms": t, "tflops": flops / t / 1e9}
+        if args.sweep:    # config 5's third arm: the unquantised bf16 Linear (cuBLAS), the roofline denominator's own kernel
+            xb, wb = x.bfloat16(), dq.bfloat16()
+            t = time_fn(lambda: torch.nn.functional.linear(xb, wb))
+            r["cublas_bf16"] = {"ms": t, "tflops": flops / t / 1e9, "frac": flops / t / 1e9 / peaks["bf16_burst"]}
+            del xb, wb
         if k % 16 == 0:
             xq, sx = q.ops.actquant_token_i8(x)
             _, wq, sw, _ = q.ops.quant_rowwise(w, 8, want_dq=False, want_codes=True, want_scales=True)
             swf = sw.float()
             t = time_fn(lambda: q.ops.gemm_w8a8(xq, sx, wq, swf))
             r["w8a8_gemm"] = {"ms": t, "tflops": flops / t / 1e9}
+            if i8_peak:   # roofline of kernel (d): min(measured int8 tensor peak, algorithmic bytes at the measured HBM rate)
+                by8 = shapes_mod.gemm_bytes_w8a8(m, n, k)
+                roof8 = min(i8_peak, flops / by8 * peaks["hbm"] / 1e3)
+                r["w8a8_gemm"].update(roof_tops=roof8, frac=flops / t / 1e9 / roof8)
             t2 = time_fn(lambda: q.ops.actquant_token_i8(x))
             r["w8a8_actquant"] = {"ms": t2, "gbs": 3.0 * m * k / t2 / 1e6}
         rows.append(r)
@@ -1030,6 +1042,28 @@ def run_conv(args):
              "ours_f16_padded_grid_ms": t_ms(lambda: q.ops.conv3x3_f16(x_cl, taps, b, padded=True)),
              "ours_f16_from_nchw_ms": t_ms(lambda: q.ops.conv3x3_f16(x, taps, b)),
              "ours_w4a16_ms": t_ms(lambda: q.ops.conv3x3_w4a16(x_cl, qw, qz, sc, grp, b))}
+        for k in list(r):
+            if k.endswith("_ms"):
+                r[k[:-3] + "_tflops"] = flops / r[k] / 1e9
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    # the three stride-2 down-samplers (Downsample2D: 3x3, stride 2, padding 1) of the same UNet: qdm_conv3x3s2_nhwc_*
+    for C, H in ((320, 64), (640, 32), (1280, 16)):
+        x = torch.randn(B, C, H, H, generator=g, device=dev, dtype=torch.float16)
+        x_cl = x.contiguous(memory_format=torch.channels_last)
+        w = torch.randn(C, C, 3, 3, generator=g, device=dev, dtype=torch.float16) * 0.03
+        w_cl = w.contiguous(memory_format=torch.channels_last)
+        b = torch.randn(C, generator=g, device=dev, dtype=torch.float16)
+        taps = q.ops.conv3x3_weight_taps(w)
+        grp = 128 if (9 * C) % 128 == 0 else 64
+        qw, qz, sc, _ = q.ops.quant_pack_awq(taps, grp)
+        flops = 2.0 * B * (H // 2) * (H // 2) * C * 9 * C
+        r = {"C": C, "N": C, "H": H, "stride": 2, "gflop": flops / 1e9,
+             "cudnn_nchw_ms": t_ms(lambda: torch.nn.functional.conv2d(x, w, b, 2, 1)),
+             "cudnn_nhwc_ms": t_ms(lambda: torch.nn.functional.conv2d(x_cl, w_cl, b, 2, 1)),
+             "ours_f16_ms": t_ms(lambda: q.ops.conv3x3_f16(x_cl, taps, b, stride=2)),
+             "ours_f16_from_nchw_ms": t_ms(lambda: q.ops.conv3x3_f16(x, taps, b, stride=2)),
+             "ours_w4a16_ms": t_ms(lambda: q.ops.conv3x3_w4a16(x_cl, qw, qz, sc, grp, b, stride=2))}
         for k in list(r):
             if k.endswith("_ms"):
                 r[k[:-3] + "_tflops"] = flops / r[k] / 1e9

@@ -292,6 +292,19 @@ int qdm_conv3x3_nhwc_w4a16(const void* x, const int32_t* qweight, const int32_t*
                            const void* bias, void* y, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
                            int64_t N, int group, void* stream);
 
+/* 3x3 / STRIDE 2 / padding 1 convolution (the UNet down-samplers, Downsample2D: quantize/fake_quant.py:337-341 runs them
+ * through cuDNN with the module's stride) in the direct form: x [B, H, W, C] NHWC unpadded, H and W even,
+ * y [B, H/2, W/2, N] NHWC; output pixel (ho, wo) = sum over taps of x[b, 2*ho + dy - 1, 2*wo + dx - 1, :] @ W[:, dy, dx, :]^T.
+ * Same kernels and the same 4-D tensor map as the stride-1 direct form; the map's element (traversal) strides of 2 along
+ * w and h make the TMA unit fetch every other pixel of a box twice as large, so a tile in shared memory is the same
+ * 128 output pixels x 64 channels and nothing is gathered or materialised.  Needs qdm_conv3x3_direct_ok(H/2, W/2);
+ * other geometries return QDM_ERR_UNSUPPORTED (the caller keeps cuDNN for those). */
+int qdm_conv3x3s2_nhwc_f16(const void* x, const void* w_tap, const void* bias, void* y, int dtype,
+                           int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream);
+int qdm_conv3x3s2_nhwc_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                             const void* bias, void* y, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
+                             int64_t N, int group, void* stream);
+
 /* Optional workspace of the W4A16 GEMM (device memory owned by the caller, qdm_gemm_workspace_bytes() bytes, kept until
  * replaced or cleared with NULL; one per device).  With it, problems whose whole-tile waves would leave CTA pairs idle
  * (few tiles with a long K, a nearly empty last wave) run the stream-K kernel, which parks partial fp32 accumulators

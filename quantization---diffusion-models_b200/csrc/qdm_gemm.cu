@@ -457,7 +457,7 @@ qdm_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           auto load_a = [&]() {
             if (p.conv_w) {
               const int hrow = m0 / p.conv_w;
-              tma_load_4d(a_dst, &map_a, full_bar(stage), ka, tap % 3 - 1, hrow % p.conv_h + tap / 3 - 1, hrow / p.conv_h);
+              tma_load_4d(a_dst, &map_a, full_bar(stage), ka, tap % 3 - 1, (hrow % p.conv_h) * p.conv_stride + tap / 3 - 1, hrow / p.conv_h);
             } else {
               tma_load_2d(a_dst, &map_a, full_bar(stage), ka, ma);
             }
@@ -732,7 +732,7 @@ qdm_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int tap = kc / p.conv_cin;
             if (p.conv_w) {
               const int hrow = m0 / p.conv_w;
-              tma_load_4d_pair(a_dst, &map_a, lf, kc - tap * p.conv_cin, tap % 3 - 1, hrow % p.conv_h + tap / 3 - 1, hrow / p.conv_h);
+              tma_load_4d_pair(a_dst, &map_a, lf, kc - tap * p.conv_cin, tap % 3 - 1, (hrow % p.conv_h) * p.conv_stride + tap / 3 - 1, hrow / p.conv_h);
             } else {
               tma_load_2d_pair(a_dst, &map_a, lf, kc - tap * p.conv_cin, m0 + p.conv_off[tap]);
             }
@@ -1649,29 +1649,36 @@ int check_common(const char* fn, const void* x, const void* w, void* y, int dtyp
 // the output grid are computed too (from wrapped-around neighbours) and are ignored by the caller; rows shifted out
 // of [0, M) are zero-filled by TMA.
 struct ConvGeom {
-  int64_t B, H, W, C;
-  bool direct;   // unpadded NHWC input behind a 4-D tensor map (see GemmParams::conv_w)
+  int64_t B, H, W, C;   // INPUT grid
+  bool direct;          // unpadded NHWC input behind a 4-D tensor map (see GemmParams::conv_w)
+  int stride = 1;       // 1, or 2 (direct form only): output grid H/2 x W/2, output pixel (ho, wo) reads input rows 2*ho + dy - 1
+  int64_t Ho() const { return H / stride; }
+  int64_t Wo() const { return W / stride; }
 };
-// a 128-row tile must be a box of whole image rows: W divides 128 and the box is either a divisor of H image rows or a
-// whole number of images
+// a 128-row tile must be a box of whole (output) image rows: W divides 128 and the box is either a divisor of H image
+// rows or a whole number of images
 bool conv_direct_ok(int64_t H, int64_t W) {
   if (W <= 0 || H <= 0 || W > 128 || 128 % W) return false;
   const int64_t rows = 128 / W;
   return rows <= H ? H % rows == 0 : rows % H == 0;
 }
+// Stride 2: the box spans stride * (output pixels) input coordinates and the map's element strides (traversal strides)
+// make the TMA unit fetch every other pixel of it, so the tile in shared memory is the same 128 rows x 64 channels as at
+// stride 1; the box start (2*ho0 + dy - 1, dx - 1) may be -1, which is the zero padding.
 int make_map_nhwc(CUtensorMap* map, const void* ptr, const ConvGeom& g) {
-  const int64_t rows = 128 / g.W;
-  const int64_t bh = rows <= g.H ? rows : g.H, bb = rows <= g.H ? 1 : rows / g.H;
+  const int64_t st = g.stride, ho = g.Ho(), wo = g.Wo();
+  const int64_t rows = 128 / wo;
+  const int64_t bh = rows <= ho ? rows : ho, bb = rows <= ho ? 1 : rows / ho;
   cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
   cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)g.W, (cuuint32_t)bh, (cuuint32_t)bb};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)(wo * st), (cuuint32_t)(bh * st), (cuuint32_t)bb};
+  cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    qdm_set_error("cuTensorMapEncodeTiled failed (%d) for NHWC [%lld, %lld, %lld, %lld]", (int)r, (long long)g.B, (long long)g.H,
-                  (long long)g.W, (long long)g.C);
+    qdm_set_error("cuTensorMapEncodeTiled failed (%d) for NHWC [%lld, %lld, %lld, %lld] stride %d", (int)r, (long long)g.B,
+                  (long long)g.H, (long long)g.W, (long long)g.C, g.stride);
     return QDM_ERR_CUDA;
   }
   return QDM_OK;
@@ -1680,17 +1687,20 @@ int conv_check(const char* fn, const ConvGeom& g, int64_t N) {
   QDM_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.C > 0 && N > 0, "%s: empty problem", fn);
   QDM_REQUIRE(g.C % 64 == 0, "%s: C=%lld must be a multiple of 64 (one k-block never straddles two taps)", fn, (long long)g.C);
   QDM_REQUIRE(g.B * (g.H + 2) * (g.W + 2) < (1LL << 31) && 9 * g.C < (1LL << 31), "%s: dimension too large", fn);
-  if (g.direct && !conv_direct_ok(g.H, g.W)) {
-    qdm_set_error("%s: H=%lld W=%lld cannot be tiled by whole image rows (W must divide 128); use the padded-grid entry",
-                  fn, (long long)g.H, (long long)g.W);
+  QDM_REQUIRE(g.stride == 1 || (g.stride == 2 && g.direct && g.H % 2 == 0 && g.W % 2 == 0),
+              "%s: stride 2 needs even H=%lld, W=%lld", fn, (long long)g.H, (long long)g.W);
+  if (g.direct && !conv_direct_ok(g.Ho(), g.Wo())) {
+    qdm_set_error("%s: output grid %lld x %lld cannot be tiled by whole image rows (its width must divide 128)%s",
+                  fn, (long long)g.Ho(), (long long)g.Wo(), g.stride == 1 ? "; use the padded-grid entry" : "");
     return QDM_ERR_UNSUPPORTED;
   }
   return QDM_OK;
 }
-int64_t conv_rows(const ConvGeom& g) { return g.direct ? g.B * g.H * g.W : g.B * (g.H + 2) * (g.W + 2); }
+int64_t conv_rows(const ConvGeom& g) { return g.direct ? g.B * g.Ho() * g.Wo() : g.B * (g.H + 2) * (g.W + 2); }
 void conv_fill(GemmParams* p, const ConvGeom& g) {
   p->conv_cin = int(g.C);
-  if (g.direct) { p->conv_w = int(g.W); p->conv_h = int(g.H); }
+  p->conv_stride = g.stride;
+  if (g.direct) { p->conv_w = int(g.Wo()); p->conv_h = int(g.Ho()); }
   for (int dy = 0; dy < 3; ++dy)
     for (int dx = 0; dx < 3; ++dx) p->conv_off[dy * 3 + dx] = int((dy - 1) * (g.W + 2) + (dx - 1));
 }
@@ -1767,6 +1777,14 @@ extern "C" int qdm_conv3x3_nhwc_f16(const void* x, const void* w_tap, const void
   int rc = conv_check("qdm_conv3x3_nhwc_f16", g, N);
   if (rc) return rc;
   return gemm_f16_impl("qdm_conv3x3_nhwc_f16", x, w_tap, bias, y, dtype, conv_rows(g), N, 9 * C, &g, (cudaStream_t)stream);
+}
+
+extern "C" int qdm_conv3x3s2_nhwc_f16(const void* x, const void* w_tap, const void* bias, void* y, int dtype,
+                                      int64_t B, int64_t H, int64_t W, int64_t C, int64_t N, void* stream) {
+  const ConvGeom g{B, H, W, C, true, 2};
+  int rc = conv_check("qdm_conv3x3s2_nhwc_f16", g, N);
+  if (rc) return rc;
+  return gemm_f16_impl("qdm_conv3x3s2_nhwc_f16", x, w_tap, bias, y, dtype, conv_rows(g), N, 9 * C, &g, (cudaStream_t)stream);
 }
 
 extern "C" int qdm_gemm_f16_kn(const void* x, const void* w_kn, const void* bias, void* y, int dtype,
@@ -1991,6 +2009,15 @@ extern "C" int qdm_conv3x3_nhwc_w4a16(const void* x, const int32_t* qweight, con
                                       int64_t N, int group, void* stream) {
   const ConvGeom g{B, H, W, C, true};
   int rc = conv_check("qdm_conv3x3_nhwc_w4a16", g, N);
+  if (rc) return rc;
+  return gemm_w4a16_impl(x, qweight, qzeros, scales, bias, y, dtype, conv_rows(g), N, 9 * C, group, &g, stream);
+}
+
+extern "C" int qdm_conv3x3s2_nhwc_w4a16(const void* x, const int32_t* qweight, const int32_t* qzeros, const void* scales,
+                                        const void* bias, void* y, int dtype, int64_t B, int64_t H, int64_t W, int64_t C,
+                                        int64_t N, int group, void* stream) {
+  const ConvGeom g{B, H, W, C, true, 2};
+  int rc = conv_check("qdm_conv3x3s2_nhwc_w4a16", g, N);
   if (rc) return rc;
   return gemm_w4a16_impl(x, qweight, qzeros, scales, bias, y, dtype, conv_rows(g), N, 9 * C, group, &g, stream);
 }

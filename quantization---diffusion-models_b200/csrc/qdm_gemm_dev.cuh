@@ -320,6 +320,9 @@ struct GemmParams {
   // a box of whole image rows (W divides 128) and tap (dy, dx) shifts its (w, h) start by (dx-1, dy-1) -- the hardware's
   // out-of-bounds zero fill is the padding, so there is neither a padded copy nor a wasted border row.
   int conv_w, conv_h;
+  // stride of the direct form (1 or 2): conv_w / conv_h are then the OUTPUT grid, the box start moves by conv_stride
+  // input rows per output row and the tensor map's element strides skip every other pixel (qdm_conv3x3s2_*)
+  int conv_stride;
   const uint8_t* rp_blob;    // W4 repacked weights (qdm_w4a16_repack): [K/128][rp_nb] blocks of RP_BLK_BYTES
   int rp_nb;                 // 16-column blocks per k-group row of the blob = ceil(N / 16)
   float* sk_data;            // stream-K: partial accumulators, [pair][rank][128 rows][256] fp32

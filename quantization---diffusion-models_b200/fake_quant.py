@@ -225,8 +225,8 @@ class WxAxConv2d(nn.Module):
             n, _, h, wd = q_x.shape
             y = tokens_as_nchw(ops.gemm_f16(nchw_as_tokens(q_x), w.reshape(self.out_channels, self.in_channels), b), n, h, wd)
         elif self.conv3x3_gemm and self._conv3x3_gemm(q_x):
-            # 3x3 / stride 1 / pad 1: one implicit GEMM over the zero-padded NHWC grid (qdm_conv3x3_f16)
-            y = ops.conv3x3_f16(q_x, self._taps(w), b)
+            # 3x3 / pad 1: one implicit GEMM (qdm_conv3x3_f16 / _nhwc_f16 at stride 1, qdm_conv3x3s2_nhwc_f16 at stride 2)
+            y = ops.conv3x3_f16(q_x, self._taps(w), b, stride=self.stride[0])
         else:
             y = torch.nn.functional.conv2d(q_x, w, b, self.stride, self.padding, self.dilation, self.groups)
         return self.output_quant(y).to(x.dtype)
@@ -238,7 +238,9 @@ class WxAxConv2d(nn.Module):
     conv3x3_gemm = os.environ.get("QDM_CONV_GEMM", "0") == "1"
 
     def _conv3x3_gemm(self, x):
-        return (self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1)
+        if self.stride == (2, 2) and not (x.dim() == 4 and ops.conv3x3_stride2_ok(x.shape[2], x.shape[3])):
+            return False
+        return (self.kernel_size == (3, 3) and self.stride in ((1, 1), (2, 2)) and self.padding == (1, 1)
                 and self.dilation == (1, 1) and self.groups == 1 and x.dim() == 4 and x.is_cuda
                 and x.dtype in (torch.float16, torch.bfloat16)
                 and self.in_channels % 64 == 0 and self.out_channels % 8 == 0)

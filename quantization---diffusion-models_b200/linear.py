@@ -201,9 +201,10 @@ class QConv1x1(nn.Module):
 
 
 def is_conv3x3_gemm(conv):
-    """3x3 / stride 1 / padding 1 / ungrouped with C % 64 == 0: the geometry `qdm_conv3x3_*` runs as one implicit GEMM."""
+    """3x3 / stride 1 or 2 / padding 1 / ungrouped with C % 64 == 0: the geometry `qdm_conv3x3_*` / `qdm_conv3x3s2_*` run
+    as one implicit GEMM (stride 2 = the UNet down-samplers; grids the kernel cannot tile fall back to cuDNN at run time)."""
     t = lambda v: (v, v) if isinstance(v, int) else tuple(v)
-    return (t(conv.kernel_size) == (3, 3) and t(conv.stride) == (1, 1) and not isinstance(conv.padding, str)
+    return (t(conv.kernel_size) == (3, 3) and t(conv.stride) in ((1, 1), (2, 2)) and not isinstance(conv.padding, str)
             and t(conv.padding) == (1, 1) and t(conv.dilation) == (1, 1) and conv.groups == 1
             and conv.in_channels % 64 == 0 and conv.out_channels % 8 == 0)
 
@@ -220,21 +221,23 @@ def conv_group(k_flat, group_size):
 
 
 class QConv3x3(nn.Module):
-    """a 3x3 / stride 1 / padding 1 `nn.Conv2d` (the resnet convolutions, about half of
-    the SD1.5 UNet's FLOPs) from PACKED int4 weights: the weight [N, C, 3, 3] is flattened tap-major to [N, 9C],
+    """a 3x3 / padding 1 `nn.Conv2d` of stride 1 (the resnet convolutions, about half of
+    the SD1.5 UNet's FLOPs) or stride 2 (the down-samplers, `qdm_conv3x3s2_nhwc_w4a16`) from PACKED int4 weights: the weight [N, C, 3, 3] is flattened tap-major to [N, 9C],
     quantised per group along that axis by the fused RTN + pack kernel (kernel b) and consumed by the W4A16 GEMM
     (kernel c) running as an implicit GEMM over the zero-padded NHWC grid (`qdm_conv3x3_w4a16`, no im2col buffer).
     Buffers follow WQLinear_GEMM (`qweight [9C, N/8]`, `qzeros`, `scales`, `bias`).  The reference only fake-quantises
     convolution weights and calls cuDNN (fake_quant.py:263-398)."""
 
-    def __init__(self, w_bit, group_size, in_channels, out_channels, bias, dev, dtype=torch.float16):
+    def __init__(self, w_bit, group_size, in_channels, out_channels, bias, dev, dtype=torch.float16, stride=1):
         super().__init__()
         if w_bit != 4:
             raise NotImplementedError("Only 4-bit are supported for now.")
+        if stride not in (1, 2):
+            raise ValueError("QConv3x3: stride must be 1 or 2")
         k = 9 * in_channels
         assert in_channels % 64 == 0 and out_channels % 8 == 0 and k % group_size == 0
         self.in_channels, self.out_channels, self.w_bit, self.group_size = in_channels, out_channels, w_bit, group_size
-        self.kernel_size, self.stride, self.padding, self.dilation, self.groups = (3, 3), (1, 1), (1, 1), (1, 1), 1
+        self.kernel_size, self.stride, self.padding, self.dilation, self.groups = (3, 3), (stride, stride), (1, 1), (1, 1), 1
         self.register_buffer("qweight", torch.zeros((k, out_channels // 8), dtype=torch.int32, device=dev))
         self.register_buffer("qzeros", torch.zeros((k // group_size, out_channels // 8), dtype=torch.int32, device=dev))
         self.register_buffer("scales", torch.zeros((k // group_size, out_channels), dtype=dtype, device=dev))
@@ -246,9 +249,10 @@ class QConv3x3(nn.Module):
     @classmethod
     def from_conv(cls, conv, w_bit, group_size, init_only=False):
         if not is_conv3x3_gemm(conv):
-            raise ValueError("QConv3x3 needs a 3x3 / stride 1 / padding 1 / ungrouped convolution with C % 64 == 0")
+            raise ValueError("QConv3x3 needs a 3x3 / stride 1 or 2 / padding 1 / ungrouped convolution with C % 64 == 0")
         dev, dtype = conv.weight.device, conv.weight.dtype
-        m = cls(w_bit, group_size, conv.in_channels, conv.out_channels, conv.bias is not None, dev, dtype)
+        stride = conv.stride if isinstance(conv.stride, int) else conv.stride[0]
+        m = cls(w_bit, group_size, conv.in_channels, conv.out_channels, conv.bias is not None, dev, dtype, stride)
         if init_only:
             return m
         m.qweight, m.qzeros, m.scales, _ = ops.quant_pack_awq(ops.conv3x3_weight_taps(conv.weight.data), group_size)
@@ -261,7 +265,13 @@ class QConv3x3(nn.Module):
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise ValueError(f"expected [B, {self.in_channels}, H, W], got {tuple(x.shape)}")
         xs = x if x.dtype == self.scales.dtype else x.to(self.scales.dtype)
-        y = ops.conv3x3_w4a16(xs, self.qweight, self.qzeros, self.scales, self.group_size, self.bias)
+        st = self.stride[0]
+        if st == 2 and not ops.conv3x3_stride2_ok(x.shape[2], x.shape[3]):
+            # a grid the stride-2 tensor map cannot tile (odd sizes, output width not dividing 128): cuDNN on the
+            # dequantised weight, as the reference does for every convolution (fake_quant.py:337-341)
+            y = torch.nn.functional.conv2d(xs, self.dequantize().to(xs.dtype), self.bias, 2, 1)
+        else:
+            y = ops.conv3x3_w4a16(xs, self.qweight, self.qzeros, self.scales, self.group_size, self.bias, stride=st)
         return y if y.dtype == x.dtype else y.to(x.dtype)
 
     def dequantize(self):
@@ -270,4 +280,5 @@ class QConv3x3(nn.Module):
         return w.reshape(self.out_channels, 3, 3, self.in_channels).permute(0, 3, 1, 2).contiguous()
 
     def extra_repr(self):
-        return f"{self.in_channels}, {self.out_channels}, kernel_size=(3, 3), padding=(1, 1), w_bit={self.w_bit}, group_size={self.group_size}"
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size=(3, 3), stride={self.stride}, padding=(1, 1), "
+                f"w_bit={self.w_bit}, group_size={self.group_size}")

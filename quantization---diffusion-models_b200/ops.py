@@ -535,14 +535,29 @@ def conv3x3_weight_taps(w):
     return w.permute(0, 2, 3, 1).reshape(n, 9 * c).contiguous()
 
 
-def _conv3x3_io(x, n_out, padded=None):
+def conv3x3_stride2_ok(h, w):
+    """True when the 3x3 / stride 2 / padding 1 convolution of an h x w grid runs on `qdm_conv3x3s2_*` (even sizes whose
+    output grid tiles by whole image rows, see include/qdm.h)."""
+    return h % 2 == 0 and w % 2 == 0 and bool(lib().qdm_conv3x3_direct_ok(h // 2, w // 2))
+
+
+def _conv3x3_io(x, n_out, padded=None, stride=1):
     """Returns (x_in, y_out, (b, h, w, c), direct).  direct (W divides 128, see qdm_conv3x3_direct_ok): x as unpadded
     NHWC -- a free view when x is channels-last in memory, one transpose copy otherwise -- and a dense NHWC output.
-    Otherwise the padded-grid form: NHWC with a one-pixel zero border and an output on the same grid."""
+    Otherwise the padded-grid form: NHWC with a one-pixel zero border and an output on the same grid.  stride 2 exists
+    in the direct form only (output [B, H/2, W/2, N])."""
     _cuda(x, "x")
     if x.dim() != 4:
         raise ValueError(f"expected [B, C, H, W], got {tuple(x.shape)}")
     b, c, h, w = x.shape
+    if stride == 2:
+        if padded:
+            raise ValueError("the stride-2 convolution has no padded-grid form")
+        if not conv3x3_stride2_ok(h, w):
+            raise ValueError(f"stride-2 convolution of a {h} x {w} grid is not supported (even sizes, output width dividing 128)")
+        return x.permute(0, 2, 3, 1).contiguous(), torch.empty((b, h // 2, w // 2, n_out), dtype=x.dtype, device=x.device), (b, h, w, c), True
+    if stride != 1:
+        raise ValueError(f"stride must be 1 or 2, got {stride}")
     # measured (profiles/conv3x3_r01.json): the direct form wins for rows of >= 32 pixels (no padded copy, no border
     # rows); for 16- and 8-pixel rows the 4-D boxes are fetched more slowly than they save and the padded grid wins
     direct = (w >= 32 and bool(lib().qdm_conv3x3_direct_ok(h, w))) if padded is None else not padded
@@ -561,23 +576,24 @@ def _conv3x3_out(y, h, w, direct):
     return (y if direct else y[:, 1:h + 1, 1:w + 1, :]).permute(0, 3, 1, 2)
 
 
-def conv3x3_f16(x, w_tap, bias=None, padded=None):
-    """F.conv2d(x, w, bias, stride=1, padding=1) for a 3x3 kernel, w_tap = conv3x3_weight_taps(w) (fake-quant weights,
+def conv3x3_f16(x, w_tap, bias=None, padded=None, stride=1):
+    """F.conv2d(x, w, bias, stride=stride, padding=1) for a 3x3 kernel, w_tap = conv3x3_weight_taps(w) (fake-quant weights,
     quantize/fake_quant.py:337-341), as one tcgen05 GEMM whose A rows are fetched per tap by TMA; C % 64 == 0,
-    N % 8 == 0.  `padded` forces the padded-grid (True) or direct (False) form; default: direct when the geometry allows."""
+    N % 8 == 0.  `padded` forces the padded-grid (True) or direct (False) form; default: direct when the geometry allows.
+    stride 2 (the down-samplers): direct form only, see conv3x3_stride2_ok."""
     _cuda(w_tap, "w_tap")
     if w_tap.dtype != x.dtype or w_tap.dim() != 2 or w_tap.shape[1] != 9 * x.shape[1]:
         raise ValueError(f"w_tap must be [N, {9 * x.shape[1]}] of dtype {x.dtype}")
-    x_in, y, (b, h, w, c), direct = _conv3x3_io(x, w_tap.shape[0], padded)
+    x_in, y, (b, h, w, c), direct = _conv3x3_io(x, w_tap.shape[0], padded, stride)
     wt = w_tap.contiguous()
     bs = bias.to(x.dtype).contiguous() if bias is not None else None
-    fn = lib().qdm_conv3x3_nhwc_f16 if direct else lib().qdm_conv3x3_f16
+    fn = lib().qdm_conv3x3s2_nhwc_f16 if stride == 2 else lib().qdm_conv3x3_nhwc_f16 if direct else lib().qdm_conv3x3_f16
     with _guard(x.device):
         check(fn(x_in.data_ptr(), wt.data_ptr(), _ptr(bs), y.data_ptr(), _dt(x_in), b, h, w, c, wt.shape[0], _stream(x)))
     return _conv3x3_out(y, h, w, direct)
 
 
-def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
+def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None, stride=1):
     """The same convolution from AWQ-packed int4 weights of w_tap (qweight [9C, N/8], qzeros / scales per group)."""
     _cuda(qweight, "qweight")
     n = scales.shape[1]
@@ -585,9 +601,9 @@ def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
         raise ValueError("x and scales must share a dtype")
     if qweight.shape[0] != 9 * x.shape[1] or qweight.shape[1] * 8 != n:
         raise ValueError(f"qweight must be [{9 * x.shape[1]}, N/8]")
-    x_in, y, (b, h, w, c), direct = _conv3x3_io(x, n, padded)
+    x_in, y, (b, h, w, c), direct = _conv3x3_io(x, n, padded, stride)
     bs = bias.to(x.dtype).contiguous() if bias is not None else None
-    fn = lib().qdm_conv3x3_nhwc_w4a16 if direct else lib().qdm_conv3x3_w4a16
+    fn = lib().qdm_conv3x3s2_nhwc_w4a16 if stride == 2 else lib().qdm_conv3x3_nhwc_w4a16 if direct else lib().qdm_conv3x3_w4a16
     with _guard(x.device):
         check(fn(x_in.data_ptr(), qweight.data_ptr(), qzeros.data_ptr(), scales.data_ptr(), _ptr(bs), y.data_ptr(),
                  _dt(x_in), b, h, w, c, n, int(group), _stream(x)))

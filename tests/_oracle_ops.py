@@ -181,17 +181,25 @@ def _taps_to_conv(w_tap, c):
     return w_tap.reshape(w_tap.shape[0], 3, 3, c).permute(0, 3, 1, 2)
 
 
-def conv3x3_f16(x, w_tap, bias=None, padded=None):
-    return O.conv2d_fake(x, _taps_to_conv(w_tap, x.shape[1]), bias, 1, 1)
+def conv3x3_stride2_ok(h, w):
+    wo, ho = w // 2, h // 2
+    if h % 2 or w % 2 or wo <= 0 or wo > 128 or 128 % wo:
+        return False
+    rows = 128 // wo
+    return ho % rows == 0 if rows <= ho else rows % ho == 0
 
 
-def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None):
-    return conv3x3_f16(x, dequant_awq(qweight, qzeros, scales, group).t(), bias)
+def conv3x3_f16(x, w_tap, bias=None, padded=None, stride=1):
+    return O.conv2d_fake(x, _taps_to_conv(w_tap, x.shape[1]), bias, stride, 1)
+
+
+def conv3x3_w4a16(x, qweight, qzeros, scales, group, bias=None, padded=None, stride=1):
+    return conv3x3_f16(x, dequant_awq(qweight, qzeros, scales, group).t(), bias, stride=stride)
 
 
 NAMES = ("colabsmax", "colabssum", "colstats", "rowabsmax", "absmax", "awq_wsum", "sqdiff_sum", "quant_group",
          "quant_rowwise", "quant_tensor", "actquant_token_i8", "quant_pack_awq", "dequant_awq", "pack_awq", "unpack_awq",
-         "awq_clip_search", "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "w4a16_repack_ts", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16",
+         "awq_clip_search", "gemm_f16", "gemm_f16_kn", "gemm_w4a16", "w4a16_repack", "w4a16_repack_ts", "gemm_w8a8", "conv3x3_weight_taps", "conv3x3_f16", "conv3x3_w4a16", "conv3x3_stride2_ok",
          "geglu")
 
 

@@ -131,12 +131,12 @@ def test_gemm_w4a16_stream_k(qdm):
 
 
 # ------------------------------------------------------------------ 3x3 convolution as an implicit GEMM
-def ref_conv3x3(x, w, bias):
+def ref_conv3x3(x, w, bias, stride=1):
     """F.conv2d in fp32 without TF32, on the GPU (the reference's own op, fake_quant.py:339, at full precision)."""
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     try:
-        y = torch.nn.functional.conv2d(x.float().cuda(), w.float().cuda(), None if bias is None else bias.float().cuda(), 1, 1)
+        y = torch.nn.functional.conv2d(x.float().cuda(), w.float().cuda(), None if bias is None else bias.float().cuda(), stride, 1)
     finally:
         torch.backends.cudnn.allow_tf32 = old
     return y.cpu()
@@ -184,6 +184,71 @@ def test_conv3x3_implicit_gemm(qdm, dt, B, C, N, H, W):
         y4 = qdm.ops.conv3x3_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV), padded=padded)
         assert y4.shape == (B, N, H, W) and y4.dtype == DT[dt]
         assert max_rel_err(y4, ref4) <= TOL, (padded,)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("B,C,N,H,W", [(16, 320, 320, 64, 64), (16, 640, 640, 32, 32), (16, 1280, 1280, 16, 16), (1, 64, 64, 16, 16),
+                                       (3, 128, 72, 8, 8), (2, 64, 128, 32, 16), (1, 64, 64, 256, 256), (5, 64, 64, 4, 4),
+                                       (2, 64, 64, 2, 2)])
+def test_conv3x3_stride2_implicit_gemm(qdm, dt, B, C, N, H, W):
+    """qdm_conv3x3s2_nhwc_f16 / _w4a16 (the UNet down-samplers: 3x3, stride 2, padding 1) against F.conv2d on the same
+    (fake-quant) weights; the first three cases are the SD1.5 down-samplers at batch 8 + CFG."""
+    g = torch.Generator().manual_seed(7 * B + C + N + H + W)
+    x = torch.randn(B, C, H, W, generator=g).to(DT[dt])
+    w = (torch.randn(N, C, 3, 3, generator=g) * 0.03).to(DT[dt])
+    b = torch.randn(N, generator=g).to(DT[dt])
+    taps = qdm.ops.conv3x3_weight_taps(w.to(DEV))
+    assert qdm.ops.conv3x3_stride2_ok(H, W)
+    ref = ref_conv3x3(x, w, b, 2)
+    for xin in (x.to(DEV), x.to(DEV).contiguous(memory_format=torch.channels_last)):
+        y = qdm.ops.conv3x3_f16(xin, taps, b.to(DEV), stride=2)
+        assert y.shape == (B, N, H // 2, W // 2) and y.dtype == DT[dt]
+        assert y.is_contiguous(memory_format=torch.channels_last) or y.shape[2] * y.shape[3] == 1
+        assert max_rel_err(y, ref) <= TOL
+    assert max_rel_err(qdm.ops.conv3x3_f16(x.to(DEV), taps, None, stride=2), ref_conv3x3(x, w, None, 2)) <= TOL
+    group = 64
+    oq, oz, os_, dq = O.awq_from_linear(taps.cpu(), group, 4)
+    qweight, qzeros, scales = torch.from_numpy(oq).to(DEV), torch.from_numpy(oz).to(DEV), os_.to(DEV)
+    ref4 = ref_conv3x3(x, dq.reshape(N, 3, 3, C).permute(0, 3, 1, 2), b, 2)
+    y4 = qdm.ops.conv3x3_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV), stride=2)
+    assert y4.shape == (B, N, H // 2, W // 2) and max_rel_err(y4, ref4) <= TOL
+
+
+def test_conv3x3_stride2_modules_and_bad_inputs(qdm):
+    import importlib
+    L = importlib.import_module(qdm.__name__ + ".linear")
+    fq = importlib.import_module(qdm.__name__ + ".fake_quant")
+    g = torch.Generator().manual_seed(5)
+    conv = torch.nn.Conv2d(128, 192, 3, stride=2, padding=1).half().to(DEV)
+    x = torch.randn(2, 128, 16, 16, generator=g).half().to(DEV)
+    assert L.is_conv3x3_gemm(conv)
+    q = L.QConv3x3.from_conv(conv, 4, L.conv_group(9 * 128, 128))
+    assert q.stride == (2, 2)
+    ref = torch.nn.functional.conv2d(x.float(), q.dequantize().float(), conv.bias.float(), 2, 1)
+    y = q(x)
+    assert y.shape == (2, 192, 8, 8) and max_rel_err(y.cpu(), ref.cpu()) <= TOL
+    # a grid the tensor map cannot tile (odd, or an output width that does not divide 128): cuDNN on the dequantised weight
+    for hw in ((15, 16), (16, 24)):
+        xo = torch.randn(2, 128, *hw, generator=g).half().to(DEV)
+        assert not qdm.ops.conv3x3_stride2_ok(*hw)
+        refo = torch.nn.functional.conv2d(xo.float(), q.dequantize().float(), conv.bias.float(), 2, 1)
+        assert max_rel_err(q(xo).cpu(), refo.cpu()) <= TOL
+        with pytest.raises(ValueError, match="stride-2"):
+            qdm.ops.conv3x3_f16(xo, qdm.ops.conv3x3_weight_taps(conv.weight.data), None, stride=2)
+    with pytest.raises(ValueError, match="padded-grid"):
+        qdm.ops.conv3x3_f16(x, qdm.ops.conv3x3_weight_taps(conv.weight.data), None, padded=True, stride=2)
+    # fake-quant module: implicit GEMM when switched on, same result as its cuDNN path
+    m = fq.WxAxConv2d.from_float(conv, weight_quant="per_channel", n_bits_W=8)
+    default = fq.WxAxConv2d.conv3x3_gemm
+    try:
+        fq.WxAxConv2d.conv3x3_gemm = True
+        assert m._conv3x3_gemm(x) and not m._conv3x3_gemm(torch.randn(2, 128, 15, 16, device=DEV).half())
+        y_gemm = m(x)
+        fq.WxAxConv2d.conv3x3_gemm = False
+        y_dnn = m(x)
+    finally:
+        fq.WxAxConv2d.conv3x3_gemm = default
+    assert y_gemm.shape == y_dnn.shape == (2, 192, 8, 8) and max_rel_err(y_gemm.cpu(), y_dnn.cpu()) <= TOL
 
 
 def test_conv3x3_modules_and_bad_inputs(qdm):

@@ -202,7 +202,7 @@ def _torch_twin(model):
             new.weight.data = m.inner.dequantize().reshape(m.out_channels, m.in_channels, 1, 1)
             m = m.inner
         elif kind == "QConv3x3":
-            new = nn.Conv2d(m.in_channels, m.out_channels, 3, padding=1, bias=m.bias is not None, device=DEV, dtype=m.scales.dtype)
+            new = nn.Conv2d(m.in_channels, m.out_channels, 3, stride=m.stride, padding=1, bias=m.bias is not None, device=DEV, dtype=m.scales.dtype)
             new.weight.data = m.dequantize()
         else:
             continue

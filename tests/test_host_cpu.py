@@ -49,8 +49,8 @@ def test_swap_pointwise_convs_and_checkpoint(version, inner, tmp_path):
                        quantType="awq")
         mods = [m for m in model.denoiser().modules() if type(m).__name__ == "QConv1x1"]
         assert len(mods) == n_pw > 0 and all(type(m.inner).__name__ == inner for m in mods)
-        # 3x3 / stride 1 / pad 1 convolutions with C % 64 == 0 carry packed int4 weights too (implicit-GEMM kernel c);
-        # conv_in (C = 4), conv_out and the stride-2 down-samplers keep fake-quant weights
+        # 3x3 / pad 1 convolutions (stride 1 and the stride-2 down-samplers) with C % 64 == 0 carry packed int4 weights
+        # too (implicit-GEMM kernel c); conv_in (C = 4) and conv_out (N = 4) keep fake-quant weights
         n_q3 = sum(1 for m in model.denoiser().modules() if type(m).__name__ == "QConv3x3")
         n_fake = sum(1 for m in model.denoiser().modules() if type(m).__name__ == "WxAxConv2d")
         assert n_q3 + n_fake == n_33 and n_fake >= 2
@@ -189,7 +189,8 @@ def test_conv_helpers():
     L = importlib.import_module(PKG + ".linear")
     C = torch.nn.Conv2d
     assert L.is_pointwise_conv(C(8, 16, 1)) and not L.is_pointwise_conv(C(8, 16, 1, stride=2)) and not L.is_pointwise_conv(C(8, 16, 3, padding=1))
-    assert L.is_conv3x3_gemm(C(64, 16, 3, padding=1)) and not L.is_conv3x3_gemm(C(64, 16, 3, padding=1, stride=2))
+    assert L.is_conv3x3_gemm(C(64, 16, 3, padding=1)) and L.is_conv3x3_gemm(C(64, 16, 3, padding=1, stride=2))   # down-samplers too
+    assert not L.is_conv3x3_gemm(C(64, 16, 3, padding=1, stride=3)) and not L.is_conv3x3_gemm(C(64, 16, 3, padding=1, stride=(2, 1)))
     assert not L.is_conv3x3_gemm(C(4, 320, 3, padding=1)) and not L.is_conv3x3_gemm(C(64, 16, 3)) and not L.is_conv3x3_gemm(C(64, 4, 3, padding=1))
     assert not L.is_conv3x3_gemm(C(64, 64, 3, padding=1, groups=2)) and not L.is_conv3x3_gemm(C(64, 64, 3, padding="same"))
     assert [L.conv_group(9 * c, 128) for c in (64, 320, 640, 960, 1280, 1920, 2560)] == [64, 64, 128, 64, 128, 128, 128]
