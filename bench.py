@@ -119,38 +119,46 @@ def workload_config(shapes, layers, world):
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference(sample_budget_s=20.0, steps=1, warmup=0):
+def cpu_reference(sample_budget_s=20.0, steps=1, warmup=0, full=False):
     """The reference's CPU torch path for this workload: F.linear(x, W_fakequant, bias) in fp32 math on all
     host cores (WxAxLinear.forward, quantize/fake_quant.py:223; the oracle restates it as linear_fake).
-    Bounded sample: one call per distinct layer shape with M capped so the whole pass fits the budget."""
+    full=False (the `cpu_baseline` of the GPU arm's line): a bounded sample, one call per distinct layer shape with M
+    capped at 4096 rows.  full=True (`--impl reference`): the WHOLE step -- every one of the step's 184 Linear calls at its
+    full M (the calls of one distinct shape reuse that shape's tensors; the pass still streams > 1 GB of activations) --
+    so that the reference arm's config is the GPU arm's; the time budget only limits how many timed passes run."""
     import torch
     import oracle.qdm_oracle as O
 
     shapes, layers = layer_list()
     torch.set_num_threads(os.cpu_count() or 1)
-    cap_m = 4096
-    sample = [(n, min(m, cap_m), nn_, k) for n, m, nn_, k, c in layers]
-    flops = sum(2.0 * m * nn_ * k for _, m, nn_, k in sample)
+    cap_m = None if full else 4096
+    sample = [(n, m if full else min(m, cap_m), nn_, k, c if full else 1) for n, m, nn_, k, c in layers]
+    flops = sum(2.0 * m * nn_ * k * c for _, m, nn_, k, c in sample)
     g = torch.Generator().manual_seed(42)
-    data = []
-    for name, m, nn_, k in sample:
+    data, xs = [], {}
+    for name, m, nn_, k, c in sample:
         w = (torch.randn(nn_, k, generator=g) * 0.02).half()
         wq = O.rtn_group(w, shapes.group_for(k), True, 4)[0]
-        data.append((torch.randn(m, k, generator=g).half(), wq, torch.zeros(nn_).half()))
+        if (m, k) not in xs:
+            xs[(m, k)] = torch.randn(m, k, generator=g).half()
+        data.append((xs[(m, k)], wq, torch.zeros(nn_).half(), c))
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        for x, wq, b in data:
-            O.linear_fake(x, wq, b)
+        for x, wq, b, c in data:
+            for _ in range(c):
+                O.linear_fake(x, wq, b)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
         if sum(times) > sample_budget_s:
             break
     dt = sum(times) / len(times)
+    what = (f"the whole step: all {sum(c for *_, c in sample)} F.linear calls of the SD1.5 UNet step at full M "
+            f"({len(sample)} distinct shapes, each shape's calls on that shape's tensors)" if full else
+            f"one F.linear per distinct SD1.5 UNet Linear shape ({len(sample)} shapes), M capped at {cap_m} rows")
     return {"value": flops / dt / 1e12, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"one F.linear per distinct SD1.5 UNet Linear shape ({len(sample)} shapes), M capped at {cap_m} rows, "
-                      f"{flops / 1e9:.1f} GFLOP per pass, fp16 fake-quant weights, fp32 math",
+            "sample": f"{what}, {flops / 1e9:.1f} GFLOP per pass, fp16 fake-quant weights, fp32 math",
             "ms_per_pass": dt * 1e3, "passes": len(times)}
 
 
@@ -159,7 +167,7 @@ def run_reference(args):
     if rank != 0:
         return
     shapes, layers = layer_list()
-    cb = cpu_reference(sample_budget_s=120.0, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    cb = cpu_reference(sample_budget_s=150.0, steps=max(1, args.steps), warmup=max(0, args.warmup), full=True)
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["passes"],
             "warmup": args.warmup, "ms_per_step": cb["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference",
@@ -733,7 +741,15 @@ def run_tables(args):
         def body():
             flush.zero_()
             fn()
-        return max(graph_ms(body) - flush_ms, 1e-4)
+        if not args.sweep:
+            return max(graph_ms(body) - flush_ms, 1e-4)
+        # sweep: the large cases run seconds at the power cap and the case after them used to inherit the lowered clocks
+        # (4096 x 6144 x 1536 right after 65536 x 6144 x 6144 read 0.37 for every kernel but cuBLAS): pause, best of two
+        best = 1e9
+        for _ in range(2):
+            time.sleep(0.25)
+            best = min(best, max(graph_ms(body) - flush_ms, 1e-4))
+        return best
 
     if args.sweep:
         cases = []

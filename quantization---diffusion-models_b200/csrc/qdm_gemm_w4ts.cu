@@ -38,8 +38,24 @@ namespace {
 #ifndef TS_ORDER
 #define TS_ORDER 0   // 0: token blocks fastest (pairs share a weight slab), 1: channel blocks fastest (pairs share a token tile)
 #endif
-#define TS_NBLK(tile) (TS_ORDER ? (tile) % n_blks : (tile) / m_blks)
-#define TS_MBLK(tile) (TS_ORDER ? (tile) / n_blks : (tile) % m_blks)
+// Tile order (TS_ORDER 0): PANELS of p.group_m token blocks; inside a panel the token blocks run fastest and the channel
+// blocks slowest, so concurrently running pairs share a weight slab and the panel's activations (group_m * T * K * 2 bytes,
+// sized by the host to stay in L2) are fetched from DRAM once and re-read from L2 by the panel's other channel blocks.
+// group_m = m_blks is the plain "token blocks fastest" order (every shape whose activations fit L2 as a whole); without
+// panels a problem whose activations exceed L2 streams them from DRAM once per channel block
+// (65536 x 3072 x 3072: 12 x 403 MB = 750 us of DRAM time in a 1000 us kernel).
+__device__ __forceinline__ int ts_nblk(int tile, int m_blks, int n_blks, int gm) {
+  if (TS_ORDER) return tile % n_blks;
+  const int per = gm * n_blks, pnl = tile / per, r = tile - pnl * per;
+  return r / min(gm, m_blks - pnl * gm);
+}
+__device__ __forceinline__ int ts_mblk(int tile, int m_blks, int n_blks, int gm) {
+  if (TS_ORDER) return tile / n_blks;
+  const int per = gm * n_blks, pnl = tile / per, r = tile - pnl * per, gsz = min(gm, m_blks - pnl * gm);
+  return pnl * gm + r % gsz;
+}
+#define TS_NBLK(tile) ts_nblk(tile, m_blks, n_blks, p.group_m)
+#define TS_MBLK(tile) ts_mblk(tile, m_blks, n_blks, p.group_m)
 constexpr int TS_KB = 2;                       // k-blocks (64 k) per pipeline stage: K = 128 per stage
 constexpr int TS_DIST = 1;                     // packed words are prefetched this many of a set's stages ahead (one set stage = two
                                                // pipeline stages of lead time; the registers go to the unpacked values instead)
@@ -229,6 +245,7 @@ __device__ __forceinline__ uint32_t ts_issue_kblock_wide(uint32_t tmem_c0, uint3
 struct TsParams {
   int M, N, K;                 // tokens, output channels, reduction
   int tile_t;                  // tokens per tile (multiple of 16, <= 256)
+  int group_m;                 // token blocks per panel of the tile order (see ts_nblk); >= 1, m_blks = no panels
   const uint32_t* words;       // [K/64][N][8]
   const uint32_t* sz;          // [K/64][N]
   const void* bias;            // [N] dtype or null
@@ -674,6 +691,19 @@ int qdm_w4ts_gemm(const void* x, const void* blob, const void* bias, void* y, in
   p.M = int(M); p.N = int(N); p.K = int(K); p.tile_t = tile_t; p.bias = bias; p.y = y;
   p.words = static_cast<const uint32_t*>(blob);
   p.sz = p.words + (K / 64) * N * 8;
+  {
+    // panel height of the tile order: the panel's activations must survive in L2 while the panel's channel blocks pass
+    // over them (32 MB of the 126 MB: the weights, the output stream and the other die's copies share it); at least 8
+    // token blocks so that the (L2-resident) weights are not re-read more often than necessary.
+    // QDM_W4_TS_GM: A/B knob, read once (-1: no panels, n > 0: that many token blocks).
+    static const int gm_env = getenv("QDM_W4_TS_GM") ? atoi(getenv("QDM_W4_TS_GM")) : 0;
+    const int64_t m_blks = (M + tile_t - 1) / tile_t, per_blk = int64_t(tile_t) * K * 2;
+    int64_t gm = (int64_t(32) << 20) / per_blk;
+    if (gm < 8) gm = 8;
+    if (gm_env > 0) gm = gm_env;
+    if (gm > m_blks || gm_env < 0) gm = m_blks;
+    p.group_m = int(gm);
+  }
   if (wide) {
     if (tile_t <= 256) return is_bf16 ? launch_ts<128, true, true>(mx, my, p, st) : launch_ts<128, false, true>(mx, my, p, st);
     if (tile_t <= 320) return is_bf16 ? launch_ts<160, true, true>(mx, my, p, st) : launch_ts<160, false, true>(mx, my, p, st);

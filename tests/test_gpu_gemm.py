@@ -286,7 +286,7 @@ def test_conv3x3_modules_and_bad_inputs(qdm):
     assert max_rel_err(q(x.to(DEV)), O.conv2d_fake(x, want, b0, 1, 1)) <= TOL
     assert L.conv_group(9 * 320, 128) == 64 and L.conv_group(9 * 640, 128) == 128 and L.conv_group(9 * 64, 0) == 64
     with pytest.raises(ValueError):
-        L.QConv3x3.from_conv(torch.nn.Conv2d(128, 192, 3, padding=1, stride=2).to(DEV).half(), 4, 64)
+        L.QConv3x3.from_conv(torch.nn.Conv2d(128, 192, 3, padding=1, stride=3).to(DEV).half(), 4, 64)
     with pytest.raises(ValueError):
         qdm.ops.conv3x3_f16(torch.zeros(1, 100, 4, 4, dtype=torch.float16, device=DEV),
                             torch.zeros(8, 900, dtype=torch.float16, device=DEV))     # C % 64 != 0

@@ -280,3 +280,42 @@ def test_w4a16_writes_only_its_output(qdm, case):
     assert y.data_ptr() == out.data_ptr()
     assert bool((big[:guard] == 12345.0).all()) and bool((big[guard + M:] == 12345.0).all()), qdm.ops.gemm_last_variant()
     assert rel_err_gpu(y, ref_linear_gpu(x, dq, b)) <= TOL, qdm.ops.gemm_last_variant()
+
+
+def test_w4a16_ts_panel_tile_order():
+    """The TS kernel's tile order in panels of `group_m` token blocks (qdm_gemm_w4ts.cu, ts_nblk / ts_mblk): forced panel
+    heights through the read-once QDM_W4_TS_GM knob in a fresh process -- 1 (channel blocks fastest), 3 (a ragged last
+    panel: 5 token blocks of 192 = 3 + 2) and -1 (no panels) must all give the fp32 reference's result, and identical bits."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import importlib, sys, torch
+sys.path.insert(0, %r)
+q = importlib.import_module("quantization---diffusion-models_b200")
+g = torch.Generator(device="cuda:0").manual_seed(3)
+out = []
+for (M, N, K, tile) in ((900, 712, 384, 192), (1500, 520, 256, 128), (1100, 264, 512, 384)):
+    x = torch.randn(M, K, generator=g, device="cuda:0", dtype=torch.float16)
+    w = (torch.randn(N, K, generator=g, device="cuda:0") * 0.05).half()
+    import oracle.qdm_oracle as O
+    oq, oz, os_, dq = O.awq_from_linear(w.cpu(), 128, 4)
+    qw, qz, sc = torch.from_numpy(oq).cuda(), torch.from_numpy(oz).cuda(), os_.cuda()
+    bts = q.ops.w4a16_repack_ts(qw, qz, sc, 128)
+    q.ops.set_gemm_mode(128 | (tile << 8))
+    y = q.ops.gemm_w4a16(x, qw, qz, sc, 128, None, None, bts)
+    assert tuple(q.ops.gemm_last_variant()) == ("ts", tile), q.ops.gemm_last_variant()
+    ref = x.float() @ dq.cuda().float().t()
+    err = ((y.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err <= 1e-2, err
+    out.append(int(y.view(torch.int16).long().sum().item()))
+print("SUMS", out)
+''' % root
+    sums = {}
+    for v in ("0", "1", "3", "-1"):
+        env = dict(os.environ, QDM_W4_TS_GM=v)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        sums[v] = [l for l in r.stdout.splitlines() if l.startswith("SUMS")][-1]
+    assert sums["1"] == sums["3"] == sums["-1"] == sums["0"]          # the tile order does not change a single output bit

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Bring-up probe of the TMEM-A W4A16 kernel (qdm_gemm_w4ts.cu): correctness against the fp32 reference and GPU-side time
-against the other W4 kernels and cuBLAS, per shape and token-tile width.   python tools/ts_probe.py [check|time] [dtype]"""
+against the other W4 kernels and cuBLAS, per shape and token-tile width.   python tools/ts_probe.py [check|time|quick|models|fused|sweep] [dtype]"""
 import importlib
 import os
 import sys
@@ -44,6 +44,9 @@ def main():
                     seen.append(c)
         cases = seen
         tiles = [0] if os.environ.get("TS_PROBE_AUTO") else [0, 384, 320, 256, 192, 160, 128]
+    elif what == "sweep":    # BASELINE config 5 corners: long-running problems at the power cap
+        cases = [(32768, 4096, 4096), (65536, 3072, 3072), (16384, 6144, 6144), (65536, 1536, 1536), (16384, 2048, 8192), (4096, 2048, 2048)]
+        tiles = [0, 384, 320, 256, 192, 160]
     else:
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (16384, 640, 640), (4096, 1280, 5120), (8192, 1280, 1280),
                  (4096, 2432, 2432), (4096, 9728, 2432), (1232, 1280, 768), (333, 2432, 2432), (65536, 2560, 320), (65536, 320, 320)]
