@@ -69,5 +69,16 @@ def test_new_entry_points_validate_arguments(qdm):
     ok = lambda h, w: bool(lib.qdm_conv3x3_direct_ok(h, w))
     assert ok(64, 64) and ok(32, 32) and ok(16, 16) and ok(8, 8) and ok(128, 128) and ok(4, 4) and ok(16, 8)
     assert not ok(96, 96) and not ok(5, 7) and not ok(12, 16) and not ok(256, 256) and not ok(0, 8)
+    # stride-2 form (the down-samplers): even input sizes whose OUTPUT grid tiles 128 rows; same channel rule
+    assert lib.qdm_conv3x3s2_nhwc_f16(16, 16, None, 16, 0, 1, 15, 16, 64, 64, None) == E.QDM_ERR_INVALID
+    assert "stride 2 needs even" in E.last_error()
+    rc = lib.qdm_conv3x3s2_nhwc_f16(16, 16, None, 16, 0, 1, 16, 24, 64, 64, None)
+    assert rc == E.QDM_ERR_UNSUPPORTED and "output grid 8 x 12" in E.last_error()
+    assert lib.qdm_conv3x3s2_nhwc_f16(16, 16, None, 16, 0, 1, 16, 16, 100, 64, None) == E.QDM_ERR_INVALID
+    assert lib.qdm_conv3x3s2_nhwc_w4a16(16, 16, 16, 16, None, 16, 0, 1, 15, 15, 64, 64, 64, None) == E.QDM_ERR_INVALID
+    import importlib
+    sys_ops = importlib.import_module("_oracle_ops")           # the CPU mirror used by the host-logic tests agrees with the library
+    for h, w in ((64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (2, 2), (256, 256), (15, 16), (16, 24), (32, 16), (512, 512), (6, 6)):
+        assert sys_ops.conv3x3_stride2_ok(h, w) == (h % 2 == 0 and w % 2 == 0 and ok(h // 2, w // 2)), (h, w)
     # packed-weight convolution: the group must be 64 * 2^j dividing 9 C
     assert lib.qdm_conv3x3_w4a16(16, 16, 16, 16, None, 16, 0, 1, 8, 8, 320, 64, 128, None) == E.QDM_ERR_INVALID
