@@ -324,6 +324,18 @@ int qdm_geglu(const void* x, int dtype, int64_t M, int64_t F, void* y, void* str
  * not part of the reference interface. */
 int qdm_set_gemm_mode(int ctas);
 
+/* Kernel-family switches of the W4A16 dispatcher for tests and A/B timing, a process-wide OR-mask on top of the
+ * QDM_W4_NO_* environment switches (which are read once, at the first GEMM call): a set bit takes that family out of the
+ * dispatch -- e.g. QDM_W4_NO_SMALLM sends every M <= 32 problem to the cluster-split-K skinny kernel, QDM_W4_NO_SMALLM |
+ * QDM_W4_NO_SKINNY to the tcgen05 kernels.  0 restores the heuristic.  Test-only; not part of the reference interface. */
+#define QDM_W4_NO_SMALLM 1
+#define QDM_W4_NO_SKINNY 2
+#define QDM_W4_NO_TMA    4
+#define QDM_W4_NO_BSTAT  8
+#define QDM_W4_NO_SK     16
+#define QDM_W4_NO_RP     32
+int qdm_set_w4_disable(int mask);
+
 /* Test hook (synchronous, allocates 16 bytes): sweeps EVERY (dividend, divisor) pair of 16-bit values of
  * `dtype` (QDM_F16 | QDM_BF16) inside the window in which the quantise kernels replace IEEE division by a
  * reciprocal + two FMAs, and compares against __fdiv_rn after the dtype rounding.

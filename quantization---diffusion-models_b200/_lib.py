@@ -74,6 +74,7 @@ SIGNATURES = {
     "qdm_conv3x3_nhwc_w4a16": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _L, _L, _L, _L, _I, _P]),
     "qdm_conv3x3s2_nhwc_f16": (c_int, [_P, _P, _P, _P, _I, _L, _L, _L, _L, _L, _P]),
     "qdm_conv3x3s2_nhwc_w4a16": (c_int, [_P, _P, _P, _P, _P, _P, _I, _L, _L, _L, _L, _L, _I, _P]),
+    "qdm_set_w4_disable": (c_int, [_I]),
     "qdm_selftest_fastdiv": (c_int, [_I, _P]),
     "qdm_gemm_workspace_bytes": (c_size_t, []),
     "qdm_gemm_set_workspace": (c_int, [_P, _Z, _P]),

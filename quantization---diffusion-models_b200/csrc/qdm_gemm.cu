@@ -1557,6 +1557,16 @@ const W4Opts& w4_opts() {
   static const W4Opts o;
   return o;
 }
+// qdm_set_w4_disable: a process-wide OR-mask on top of the environment switches, for tests and A/B timing that must flip a
+// kernel family off and on inside one process (the environment is only read once)
+int g_w4_disable = 0;
+W4Opts w4_opts_now() {
+  W4Opts o = w4_opts();
+  const int d = g_w4_disable;
+  o.no_smallm |= (d & QDM_W4_NO_SMALLM) != 0; o.no_skinny |= (d & QDM_W4_NO_SKINNY) != 0; o.no_tma |= (d & QDM_W4_NO_TMA) != 0;
+  o.no_bstat |= (d & QDM_W4_NO_BSTAT) != 0; o.no_sk |= (d & QDM_W4_NO_SK) != 0; o.no_rp |= (d & QDM_W4_NO_RP) != 0;
+  return o;
+}
 
 // which kernel the last GEMM call of this thread launched (tests assert the dispatch; qdm_gemm_last_variant)
 thread_local int g_last_variant = 0, g_last_tile = 0;
@@ -1756,6 +1766,13 @@ extern "C" int qdm_set_gemm_mode(int ctas) {
   return QDM_OK;
 }
 
+extern "C" int qdm_set_w4_disable(int mask) {
+  const int all = QDM_W4_NO_SMALLM | QDM_W4_NO_SKINNY | QDM_W4_NO_TMA | QDM_W4_NO_BSTAT | QDM_W4_NO_SK | QDM_W4_NO_RP;
+  QDM_REQUIRE((mask & ~all) == 0, "qdm_set_w4_disable: unknown bits in mask 0x%x", mask);
+  g_w4_disable = mask;
+  return QDM_OK;
+}
+
 extern "C" int qdm_gemm_f16(const void* x, const void* w, const void* bias, void* y, int dtype,
                             int64_t M, int64_t N, int64_t K, void* stream) {
   return gemm_f16_impl("qdm_gemm_f16", x, w, bias, y, dtype, M, N, K, nullptr, (cudaStream_t)stream);
@@ -1848,7 +1865,7 @@ static int gemm_w4a16_impl(const void* x, const int32_t* qweight, const int32_t*
   // qdm_gemm_smallm.cu is as fast or faster up to ~2 M weights (16 x 1280 x 320: 4.7 vs 8.1 us, 16 x 1280 x 1280: 9.5 vs
   // 9.8 us); above that its sector over-fetch dominates and the sector-wide cluster-split-K kernel of qdm_gemm_skinny.cu
   // wins (1 x 2432 x 2432: 10 vs 21.6 us; 1 x 14592 x 2432: 18.1 vs 32.6 us on the tcgen05 kernel).
-  const W4Opts& opt = w4_opts();
+  const W4Opts opt = w4_opts_now();
   const bool small_w = N * K <= (int64_t(1) << 21) && qdm_gemm_w4a16_smallm_fits(M, N, K) && !opt.no_smallm;
   if (!conv && !small_w && qdm_gemm_w4a16_skinny_fits(M, N, K) && g_force_ctas == 0 && !opt.no_skinny) {
     note_variant(QDM_GEMM_SKINNY, 0);

@@ -72,6 +72,15 @@ def set_gemm_mode(ctas=0):
     check(lib().qdm_set_gemm_mode(int(ctas)))
 
 
+W4_NO_SMALLM, W4_NO_SKINNY, W4_NO_TMA, W4_NO_BSTAT, W4_NO_SK, W4_NO_RP = 1, 2, 4, 8, 16, 32
+
+
+def set_w4_disable(mask=0):
+    """OR-mask of W4_NO_* bits: takes kernel families out of the W4A16 dispatch for this process (tests / A-B timing);
+    0 restores the heuristic.  The QDM_W4_NO_* environment switches are read once and cannot be flipped in-process."""
+    check(lib().qdm_set_w4_disable(int(mask)))
+
+
 def launch_count(reset=False):
     return int(lib().qdm_launch_count(1 if reset else 0))
 

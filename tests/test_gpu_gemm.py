@@ -302,9 +302,9 @@ SKINNY_SHAPES = [(8, 1280, 2816, 128), (1, 2432, 256, 128), (5, 72, 192, 64), (3
 @pytest.mark.parametrize("M,N,K,group", SKINNY_SHAPES)
 def test_gemm_w4a16_skinny_forced(qdm, dt, M, N, K, group):
     """The cluster-split-K mma.sync kernel (qdm_gemm_skinny.cu) on every shape class it accepts -- ragged N (not a
-    multiple of 64 / 256), one k16 step per warp, 1..4 m-tiles, group 64 / 128 / 256 -- forced with QDM_W4_NO_SMALLM=1
-    (the dispatcher otherwise keeps the one-word-column kernel below ~2 M weights).  Deterministic call to call."""
-    import os
+    multiple of 64 / 256), one k16 step per warp, 1..4 m-tiles, group 64 / 128 / 256 -- forced with
+    set_w4_disable(W4_NO_SMALLM) (the dispatcher otherwise keeps the one-word-column kernel below ~2 M weights; the
+    QDM_W4_NO_* environment switches are read once per process and cannot force anything here).  Deterministic call to call."""
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(DT[dt])
     w = (torch.randn(N, K, generator=g) * 0.05).to(DT[dt])
@@ -312,11 +312,12 @@ def test_gemm_w4a16_skinny_forced(qdm, dt, M, N, K, group):
     oq, oz, os_, dq = O.awq_from_linear(w, group, 4)
     qweight, qzeros, scales = torch.from_numpy(oq).to(DEV), torch.from_numpy(oz).to(DEV), os_.to(DEV)
     try:
-        os.environ["QDM_W4_NO_SMALLM"] = "1"
+        qdm.ops.set_w4_disable(qdm.ops.W4_NO_SMALLM)
         y1 = qdm.ops.gemm_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV))
+        assert qdm.ops.gemm_last_variant()[0] == "skinny", qdm.ops.gemm_last_variant()
         y2 = qdm.ops.gemm_w4a16(x.to(DEV), qweight, qzeros, scales, group, b.to(DEV))
     finally:
-        os.environ.pop("QDM_W4_NO_SMALLM", None)
+        qdm.ops.set_w4_disable(0)
     assert y1.shape == (M, N) and y1.dtype == DT[dt] and torch.equal(y1, y2)
     assert max_rel_err(y1, ref_linear(x, dq, b)) <= TOL
     y_kn = qdm.ops.gemm_f16_kn(x.to(DEV), qdm.ops.dequant_awq(qweight, qzeros, scales, group), b.to(DEV))
@@ -326,7 +327,6 @@ def test_gemm_w4a16_skinny_forced(qdm, dt, M, N, K, group):
 def test_gemm_w4a16_skinny_vs_other_kernels(qdm):
     """The three W4A16 kernels an M <= 32 problem can take agree up to accumulation order on the same packed weights:
     skinny (forced), the one-word-column small-M kernel (where it fits) and the tcgen05 kernel."""
-    import os
     g = torch.Generator().manual_seed(21)
     for M, N, K, group in [(16, 1280, 1280, 128), (2, 14592, 2432, 128)]:
         x = torch.randn(M, K, generator=g).half().to(DEV)
@@ -334,14 +334,16 @@ def test_gemm_w4a16_skinny_vs_other_kernels(qdm):
         b = torch.randn(N, generator=g).half().to(DEV)
         qweight, qzeros, scales, dq = qdm.ops.quant_pack_awq(w, group, want_dq=True)
         try:
-            os.environ["QDM_W4_NO_SMALLM"] = "1"
+            qdm.ops.set_w4_disable(qdm.ops.W4_NO_SMALLM)
             y_sk = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)          # skinny
-            os.environ["QDM_W4_NO_SKINNY"] = "1"
+            assert qdm.ops.gemm_last_variant()[0] == "skinny"
+            qdm.ops.set_w4_disable(qdm.ops.W4_NO_SMALLM | qdm.ops.W4_NO_SKINNY)
             y_tc = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)          # tcgen05
-            os.environ.pop("QDM_W4_NO_SMALLM", None)
+            assert qdm.ops.gemm_last_variant()[0] in ("single", "pair", "streamk")
+            qdm.ops.set_w4_disable(qdm.ops.W4_NO_SKINNY)
             y_sm = qdm.ops.gemm_w4a16(x, qweight, qzeros, scales, group, b)          # small-M where it fits, else tcgen05
+            assert qdm.ops.gemm_last_variant()[0] == ("smallm" if N * K <= (13 << 19) else qdm.ops.gemm_last_variant()[0])
         finally:
-            os.environ.pop("QDM_W4_NO_SKINNY", None)
-            os.environ.pop("QDM_W4_NO_SMALLM", None)
+            qdm.ops.set_w4_disable(0)
         assert max_rel_err(y_sk, ref_linear(x.cpu(), dq.cpu(), b.cpu())) <= TOL
         assert max_rel_err(y_sk, y_tc.cpu()) <= 2e-3 and max_rel_err(y_sk, y_sm.cpu()) <= 2e-3
