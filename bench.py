@@ -631,9 +631,12 @@ def run_ours(args):
     torch.cuda.empty_cache()
     extra = {}
     if not args.no_extras:
+        wanted = [w for w in args.extras.split(",") if w]
         for name, fn in (("w8a8", lambda: sub_w8a8(q, shapes, layers, dev, dtype, args.steps, args.warmup, timed)),
                          ("denoise", lambda: sub_denoise(args, dev, rank, world, sync_max)),
                          ("calib", lambda: sub_calib(args, dev, rank, world, sync_max, blocks=args.blocks))):
+            if name not in wanted:
+                continue
             try:
                 extra[name] = fn()
             except Exception as e:   # a sub-record must never take the headline metric down with it
@@ -1105,6 +1108,7 @@ def main():
     ap.add_argument("--no-chain", action="store_true", help="e2e: ff.net.2 inputs from the host too (no on-device GEGLU)")
     ap.add_argument("--fused", action="store_true", help="--layers: the fused launch inventory of the model")
     ap.add_argument("--no-extras", action="store_true", help="skip the w8a8 / denoise / calib sub-records of the line")
+    ap.add_argument("--extras", default="w8a8,denoise,calib", help="which sub-records to run (comma-separated)")
     ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn", "kernels", "conv"])
     ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl", "sd35"])
     ap.add_argument("--quant", default="w4a16", choices=["fp16", "w4a16", "w8a8"])

@@ -473,6 +473,13 @@ quant_rows_reg_kernel(const T* __restrict__ x, int64_t rows, int cols, float max
   const int wpb = kQThreads / 32;
   const float dummy[V] = {};
   const float dummy8[8] = {};
+  if (I8OUT) {
+    // the A8 quantiser sits between two GEMMs of a W8A8 model: launched with programmatic stream serialisation
+    // (launch_rows_reg), it lets the GEMM that follows set up while it runs and itself becomes resident while the GEMM
+    // before it drains; nothing of an earlier kernel is touched before the wait.  Both are no-ops in a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   for (int64_t row0 = (int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5)) * RPW; row0 < rows;
        row0 += int64_t(gridDim.x) * wpb * RPW) {
     // a group past the last row works on the last row again and skips every store (the shuffles below need all lanes)
@@ -1030,6 +1037,23 @@ int grid_for(int64_t work_items, int per_block) {
   return int(b);
 }
 
+// kQThreads-wide launch, with programmatic stream serialisation when PDL (the kernel then starts with
+// griddepcontrol.launch_dependents + griddepcontrol.wait); QDM_NO_PDL=1 launches plainly (A/B switch, read once)
+template <bool PDL, typename Kern, typename... Args>
+cudaError_t launch_maybe_pdl(Kern kern, unsigned grid, cudaStream_t st, Args... args) {
+  static const bool no_pdl = getenv("QDM_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kQThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = (PDL && !no_pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <typename T, int MODE, bool I8OUT>
 int launch_rows_reg(const T* x, int64_t rows, int64_t cols, float max_int, float min_int,
                     T* dq, int8_t* codes, T* scales, T* zeros, float* sx, cudaStream_t st) {
@@ -1045,8 +1069,8 @@ int launch_rows_reg(const T* x, int64_t rows, int64_t cols, float max_int, float
     }                                                                                                 \
     int64_t grid = (rows + kQThreads / 32 - 1) / (kQThreads / 32);                                    \
     if (grid > int64_t(QDM_NUM_SMS) * occ) grid = int64_t(QDM_NUM_SMS) * occ;                         \
-    quant_rows_reg_kernel<T, MODE, NV, I8OUT><<<(unsigned)grid, kQThreads, 0, st>>>(x, rows, int(cols), max_int, min_int, \
-                                                                          dq, codes, scales, zeros, sx); \
+    QDM_CUDA_OK(launch_maybe_pdl<I8OUT>(quant_rows_reg_kernel<T, MODE, NV, I8OUT>, (unsigned)grid, st, x, rows, int(cols), max_int, \
+                                        min_int, dq, codes, scales, zeros, sx));                          \
   } while (0)
   // short rows share a warp (<= 8 vectors per lane at 8 / 16 lanes per row)
 #define QDM_ROWS_SUB(LPR)                                                                             \
@@ -1059,8 +1083,8 @@ int launch_rows_reg(const T* x, int64_t rows, int64_t cols, float max_int, float
     const int64_t rpc = int64_t(kQThreads / 32) * (32 / LPR);                                         \
     int64_t grid = (rows + rpc - 1) / rpc;                                                            \
     if (grid > int64_t(QDM_NUM_SMS) * occ) grid = int64_t(QDM_NUM_SMS) * occ;                         \
-    quant_rows_reg_kernel<T, MODE, 8, I8OUT, LPR><<<(unsigned)grid, kQThreads, 0, st>>>(x, rows, int(cols), max_int, min_int, \
-                                                                               dq, codes, scales, zeros, sx); \
+    QDM_CUDA_OK(launch_maybe_pdl<I8OUT>(quant_rows_reg_kernel<T, MODE, 8, I8OUT, LPR>, (unsigned)grid, st, x, rows, int(cols),   \
+                                        max_int, min_int, dq, codes, scales, zeros, sx));                 \
   } while (0)
   const int64_t vecs = (cols + V - 1) / V;
   if (vecs > 32 && vecs <= 64 && rows >= 1024) QDM_ROWS_SUB(8);
