@@ -47,6 +47,9 @@ def main():
     elif what == "sweep":    # BASELINE config 5 corners: long-running problems at the power cap
         cases = [(32768, 4096, 4096), (65536, 3072, 3072), (16384, 6144, 6144), (65536, 1536, 1536), (16384, 2048, 8192), (4096, 2048, 2048)]
         tiles = [0, 384, 320, 256, 192, 160]
+    elif what == "sweep_small":    # the config-5 shapes below 0.70 of the bf16 peak
+        cases = [(4096, 1536, 1536), (4096, 2048, 2048), (8192, 1536, 1536), (4096, 3072, 3072), (8192, 2048, 2048)]
+        tiles = [0, 384, 320, 256, 192, 160, 128]
     else:
         cases = [(4096, 10240, 1280), (4096, 1280, 1280), (16384, 5120, 640), (16384, 640, 640), (4096, 1280, 5120), (8192, 1280, 1280),
                  (4096, 2432, 2432), (4096, 9728, 2432), (1232, 1280, 768), (333, 2432, 2432), (65536, 2560, 320), (65536, 320, 320)]
