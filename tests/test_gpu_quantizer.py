@@ -425,3 +425,40 @@ def test_wxax_conv_vs_reference_fixture(qdm):
                 assert max_rel_err(y_d, ref) <= 1e-2
     finally:
         fq.WxAxConv2d.conv3x3_gemm = default
+
+
+def test_wxax_conv_stride2_vs_reference_fixture(qdm):
+    """The down-sampler form of WxAxConv2d (3x3, stride 2, padding 1) against the reference-generated fixture
+    (tools/gen_golden.py conv_s2): fake-quant weight bit-exact; forward on the stride-2 implicit GEMM
+    (qdm_conv3x3s2_nhwc_f16: one libqdm launch) where the grid tiles, on cuDNN for the odd 15 x 16 grid (no libqdm launch);
+    the packed-int4 module on the same convolution against F.conv2d on ITS dequantised weight."""
+    fq = importlib.import_module(PKG + ".fake_quant")
+    L = importlib.import_module(PKG + ".linear")
+    g = Golden("wxax_conv_s2.npz")
+    default = fq.WxAxConv2d.conv3x3_gemm
+    seen = set()
+    try:
+        fq.WxAxConv2d.conv3x3_gemm = True
+        for tag, dt, wq, bits, ksz in g.cases():
+            w, b, x = g.get(tag + "_w"), g.get(tag + "_b"), g.get(tag + "_x")
+            conv = torch.nn.Conv2d(w.shape[1], w.shape[0], 3, stride=2, padding=1, bias=True)
+            conv.weight.data, conv.bias.data = w.clone(), b.clone()
+            conv = conv.to(DEV)
+            m = fq.WxAxConv2d.from_float(conv, weight_quant=wq, act_quant="per_tensor", n_bits_W=int(bits))
+            assert_bit_equal(m.weight, g.get(tag + "_wq"), f"{tag} fake-quant conv weight")
+            tiles = qdm.ops.conv3x3_stride2_ok(x.shape[2], x.shape[3])
+            seen.add(tiles)
+            qdm.ops.launch_count(reset=True)
+            y = m(x.to(DEV))
+            assert qdm.ops.launch_count() == (1 if tiles else 0)
+            ref = g.get(tag + "_y")
+            assert y.shape == ref.shape and y.dtype == ref.dtype
+            assert max_rel_err(y, ref) <= 1e-2
+            if w.shape[0] % 64 == 0:
+                q4 = L.QConv3x3.from_conv(conv, 4, L.conv_group(9 * w.shape[1], 128))
+                y4 = q4(x.to(DEV))
+                ref4 = torch.nn.functional.conv2d(x.to(DEV).float(), q4.dequantize().float(), b.to(DEV).float(), 2, 1)
+                assert y4.shape == ref.shape and max_rel_err(y4.cpu(), ref4.cpu()) <= 1e-2
+    finally:
+        fq.WxAxConv2d.conv3x3_gemm = default
+    assert seen == {True, False}

@@ -149,3 +149,20 @@ def test_wxax_conv_matches_reference():
         ref = g.get(tag + "_y")
         assert y.shape == ref.shape
         assert ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item() <= 2e-3
+
+
+def test_wxax_conv_stride2_matches_reference():
+    """A8 for the UNet down-samplers (3x3, stride 2, padding 1): the reference's WxAxConv2d.from_float + forward
+    (fake_quant.py:263-398 keeps the module's stride) vs the oracle; fixture from tools/gen_golden.py conv_s2."""
+    g = Golden("wxax_conv_s2.npz")
+    n = 0
+    for tag, dt, wq, bits, ksz in g.cases():
+        w, b, x = g.get(tag + "_w"), g.get(tag + "_b"), g.get(tag + "_x")
+        wf = (O.rtn_rows(w, int(bits))[0] if wq == "per_channel" else O.rtn_tensor(w, int(bits))[0]).reshape(w.shape)
+        assert_bit_equal(wf, g.get(tag + "_wq"), f"{tag} fake-quant conv weight")
+        y = O.conv2d_fake(x, wf, b, 2, 1)
+        ref = g.get(tag + "_y")
+        assert y.shape == ref.shape == (x.shape[0], w.shape[0], (x.shape[2] + 1) // 2, (x.shape[3] + 1) // 2)
+        assert ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item() <= 2e-3
+        n += 1
+    assert n == 4

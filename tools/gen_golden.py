@@ -301,6 +301,31 @@ def gen_wxax_conv(r):
     np.savez_compressed(os.path.join(OUT, "wxax_conv.npz"), **d)
 
 
+def gen_wxax_conv_s2(r):
+    """The same for the UNet down-samplers (Downsample2D: 3x3, stride 2, padding 1), which the B200 path runs as an
+    implicit GEMM behind a tensor map with element strides of 2 (qdm_conv3x3s2_nhwc_*); reference on CPU, fp16."""
+    fq = r.fake_quant
+    d, cases, i = {}, [], 0
+    for cin, cout, h, w, wqs in ((64, 64, 8, 8, ("per_tensor", "per_channel")), (128, 72, 16, 16, ("per_channel",)),
+                                 (64, 72, 15, 16, ("per_tensor",))):   # the last: an odd grid (stays on cuDNN)
+        for wq, bits in ((q_, 8) for q_ in wqs):
+            g = torch.Generator().manual_seed(1400 + i)
+            conv = torch.nn.Conv2d(cin, cout, 3, stride=2, padding=1, bias=True)
+            conv.weight.data = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+            conv.bias.data = torch.randn(cout, generator=g)
+            conv.to(torch.float16)
+            x = torch.randn(2, cin, h, w, generator=g).to(torch.float16)
+            m = fq.WxAxConv2d.from_float(conv, weight_quant=wq, act_quant="per_tensor", n_bits_W=bits)
+            y = m(x)
+            tag = f"s{i}"
+            enc(d, tag + "_w", conv.weight.data), enc(d, tag + "_b", conv.bias.data), enc(d, tag + "_x", x)
+            enc(d, tag + "_wq", m.weight), enc(d, tag + "_y", y)
+            cases.append(f"{tag},f16,{wq},{bits},3")
+            i += 1
+    d["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(OUT, "wxax_conv_s2.npz"), **d)
+
+
 def gen_act_quant(r):
     """A6 / A5 activation fake quantisers that the first fixtures did not cover: the NCHW per-(n, c, patch) quantiser
     (fake_quant.py:134-153, incl. its `group_size -= 2` fallback) and the 16-bit forms the reference's default
@@ -341,6 +366,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "conv":   # only the convolution fixture (added later; the others are unchanged)
         torch.set_grad_enabled(False)
         gen_wxax_conv(ref_shim.ref())
+    elif len(sys.argv) > 1 and sys.argv[1] == "conv_s2":   # only the stride-2 convolution fixture (round 2, later)
+        torch.set_grad_enabled(False)
+        gen_wxax_conv_s2(ref_shim.ref())
     elif len(sys.argv) > 1 and sys.argv[1] == "acts":  # only the activation-quantiser fixture (round 2)
         torch.set_grad_enabled(False)
         gen_act_quant(ref_shim.ref())
