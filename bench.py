@@ -306,6 +306,78 @@ def sub_w8a8(q, shapes, layers, dev, dtype, steps, warmup, timed):
                     "qdm_actquant_token_i8 + qdm_gemm_w8a8 (quantize/fake_quant.py:86-118); unfused_* = every Linear on its own"}
 
 
+def sub_config5(q, shapes, dev):
+    """BASELINE config 5 in the driver's own line: four corners of the GEMM sweep (`bench.py --sweep` has all 33 shapes,
+    profiles/gemm_sweep_r02.json), W4A16 (kernel c, module dispatch) and the W8A8 GEMM (kernel d) against cuBLAS bf16 on the same
+    shapes.  GPU-side time of one launch with a cold L2: CUDA graph of 10 x (256 MB flush, launch) minus the flushes alone.
+    Rank-local (no collective); never raises."""
+    import torch
+    try:
+        peaks = measured_peaks()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def graph_ms(body, reps=10):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                for _ in range(reps):
+                    body()
+            g_.replay()
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g_.replay(); e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) / reps)
+            return best
+
+        flush_ms = graph_ms(lambda: flush.zero_())
+
+        def time_fn(fn):
+            def body():
+                flush.zero_()
+                fn()
+            return max(graph_ms(body) - flush_ms, 1e-4)
+
+        i8_peak = int8_dense_peak(torch, dev)
+        g = torch.Generator(device=dev).manual_seed(45)
+        rows = []
+        for m, n, k in ((4096, 4096, 4096), (16384, 4096, 4096), (65536, 3072, 3072), (16384, 6144, 1536)):
+            grp = shapes.group_for(k)
+            x = torch.randn(m, k, generator=g, device=dev, dtype=torch.float16)
+            w = torch.randn(n, k, generator=g, device=dev, dtype=torch.float16) * 0.02
+            qw, qz, sc, dq = q.ops.quant_pack_awq(w, grp, want_dq=True)
+            bts = q.ops.w4a16_repack_ts(qw, qz, sc, grp)
+            flops = 2.0 * m * n * k
+            t4 = time_fn(lambda: q.ops.gemm_w4a16(x, qw, qz, sc, grp, None, None, bts))
+            kern = list(q.ops.gemm_last_variant())
+            xb, wb = x.bfloat16(), dq.bfloat16()
+            tb = time_fn(lambda: torch.nn.functional.linear(xb, wb))
+            del xb, wb
+            xq, sx = q.ops.actquant_token_i8(x)
+            _, wq, sw, _ = q.ops.quant_rowwise(w, 8, want_dq=False, want_codes=True, want_scales=True)
+            swf = sw.float()
+            t8 = time_fn(lambda: q.ops.gemm_w8a8(xq, sx, wq, swf))
+            r = {"M": m, "N": n, "K": k, "w4a16_kernel": kern,
+                 "w4a16_tflops": flops / t4 / 1e9, "w4a16_frac_bf16_burst_peak": flops / t4 / 1e9 / peaks["bf16_burst"],
+                 "cublas_bf16_tflops": flops / tb / 1e9, "w8a8_gemm_tops": flops / t8 / 1e9,
+                 "w8a8_frac_int8_peak": (flops / t8 / 1e9 / i8_peak) if i8_peak else None}
+            rows.append(r)
+            del x, w, qw, qz, sc, dq, bts, xq, sx, wq, sw, swf
+            torch.cuda.empty_cache()
+        return {"rows": rows, "bf16_burst_peak_tflops": peaks["bf16_burst"], "int8_dense_peak_tops": i8_peak,
+                "peak_how": "bf16: MEASURED_PEAKS.json burst (fallback if absent); int8: torch._int_mm 8192^3 best of 10, this run",
+                "what": "BASELINE config 5 corners: one launch, cold L2, GPU-side graph timing; the full 33-shape table is bench.py --sweep"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def sub_denoise(args, dev, rank, world, sync_max):
     """BASELINE config 2: SD1.5 UNet skeleton, W4A16 AWQ g128, 512^2 latents batch 8 + CFG, 50-step loop through generate();
     prompt-batched data parallel, no collective in the loop.  it/s = denoise steps per second per replica."""
@@ -633,6 +705,7 @@ def run_ours(args):
     if not args.no_extras:
         wanted = [w for w in args.extras.split(",") if w]
         for name, fn in (("w8a8", lambda: sub_w8a8(q, shapes, layers, dev, dtype, args.steps, args.warmup, timed)),
+                         ("config5", lambda: sub_config5(q, shapes, dev)),
                          ("denoise", lambda: sub_denoise(args, dev, rank, world, sync_max)),
                          ("calib", lambda: sub_calib(args, dev, rank, world, sync_max, blocks=args.blocks))):
             if name not in wanted:
@@ -1108,7 +1181,7 @@ def main():
     ap.add_argument("--no-chain", action="store_true", help="e2e: ff.net.2 inputs from the host too (no on-device GEGLU)")
     ap.add_argument("--fused", action="store_true", help="--layers: the fused launch inventory of the model")
     ap.add_argument("--no-extras", action="store_true", help="skip the w8a8 / denoise / calib sub-records of the line")
-    ap.add_argument("--extras", default="w8a8,denoise,calib", help="which sub-records to run (comma-separated)")
+    ap.add_argument("--extras", default="w8a8,config5,denoise,calib", help="which sub-records to run (comma-separated)")
     ap.add_argument("--mode", default="linears", choices=["linears", "denoise", "calib", "rtn", "kernels", "conv"])
     ap.add_argument("--model", default="sd15", choices=["sd15", "sdxl", "sd35"])
     ap.add_argument("--quant", default="w4a16", choices=["fp16", "w4a16", "w8a8"])
